@@ -1,0 +1,181 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_goldens.py
+
+The reference has no tests or golden vectors of its own; these fixtures are
+"outputs of the reference itself run here".  Inputs are synthetic (oracle.qmix.synth_batch);
+weights are the reference's own init, perturbed so every LayerNorm gain/bias and every
+Linear bias is non-trivial and the target nets differ from the live nets.
+Every array the CUDA path must reproduce is stored: sampled indices, loss, grad_norm, Q_tot,
+clipped grads, post-Adam params, post-polyak targets, PER weights/priorities/tree leaves.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import ref_harness as rh  # noqa: E402
+from oracle.qmix import QmixConfig, synth_batch, randomize_all  # noqa: E402
+
+
+def build_reference_qmix(cfg, extra_flags=(), T=8, seed=1):
+    rh.import_reference()
+    from offpolicy.algorithms.qmix.qmix import QMix
+    from offpolicy.algorithms.qmix.algorithm.QMixPolicy import QMixPolicy
+    sp = rh.gym_spaces()
+    flags = ["--algorithm_name", "qmix", "--hidden_size", str(cfg.hidden), "--gain", str(cfg.gain),
+             "--hypernet_layers", str(cfg.hyper_layers), "--lr", str(cfg.lr)] + list(extra_flags)
+    args = rh.make_args(flags)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    info = dict(obs_space=[cfg.obs_dim], share_obs_space=[cfg.state_dim], act_space=sp.Discrete(cfg.act_dim),
+                cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
+    dev = torch.device("cpu")
+    pol = QMixPolicy({"args": args, "device": dev}, info)
+    tr = QMix(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=dev, episode_length=T)
+    # non-trivial weights everywhere; targets != live
+    randomize_all(pol.q_network, 11)
+    randomize_all(tr.mixer, 12)
+    tr.hard_target_updates()
+    randomize_all(tr.target_policies["policy_0"].q_network, 13, scale=0.05)
+    randomize_all(tr.target_mixer, 14, scale=0.05)
+    return args, pol, tr
+
+
+def sd_np(prefix, module):
+    return {prefix + k: v.detach().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def to_ref_batch(b, weights=None, idx=None):
+    obs, share, acts, rew, dones, dones_env, avail = b
+    d = lambda x: {"policy_0": x}
+    return (d(obs), d(share), d(acts), d(rew), d(dones), d(dones_env), d(avail), weights, idx)
+
+
+def gen_qmix(name, cfg, flags=(), B=4, T=8, steps=2, avail_p=0.7, var_len=True, per=False):
+    args, pol, tr = build_reference_qmix(cfg, flags, T)
+    out = {}
+    out.update(sd_np("init.agent.", pol.q_network))
+    out.update(sd_np("init.mixer.", tr.mixer))
+    out.update(sd_np("init.tgt_agent.", tr.target_policies["policy_0"].q_network))
+    out.update(sd_np("init.tgt_mixer.", tr.target_mixer))
+    for s in range(steps):
+        b = synth_batch(cfg, B, T, seed=100 + s, avail_p=avail_p, var_len=var_len)
+        for k, v in zip(["obs", "share", "acts", "rew", "dones", "dones_env", "avail"], b):
+            out["s%d.in.%s" % (s, k)] = v
+        w = idx = None
+        if per:
+            w = np.random.RandomState(7 + s).rand(B).astype(np.float64) * 0.9 + 0.1
+            idx = np.arange(B)
+            out["s%d.in.weights" % s] = w
+        info, prio, _ = tr.train_policy_on_batch(to_ref_batch(b, w, idx))
+        out["s%d.loss" % s] = info["loss"].detach().numpy()
+        out["s%d.grad_norm" % s] = np.asarray(float(info["grad_norm"]), np.float32)
+        out["s%d.Q_tot" % s] = info["Q_tot"].detach().numpy()
+        if prio is not None:
+            out["s%d.prio" % s] = np.asarray(prio)
+        names = [k for k, _ in pol.q_network.named_parameters()]
+        for k, p in pol.q_network.named_parameters():
+            if p.grad is not None:
+                out["s%d.grad.agent.%s" % (s, k)] = p.grad.numpy().copy()
+        for k, p in tr.mixer.named_parameters():
+            out["s%d.grad.mixer.%s" % (s, k)] = p.grad.numpy().copy()
+        tr.soft_target_updates()
+        out.update(sd_np("s%d.agent." % s, pol.q_network))
+        out.update(sd_np("s%d.mixer." % s, tr.mixer))
+        out.update(sd_np("s%d.tgt_agent." % s, tr.target_policies["policy_0"].q_network))
+        out.update(sd_np("s%d.tgt_mixer." % s, tr.target_mixer))
+    out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, cfg.hidden, cfg.mixer_hidden,
+                                cfg.hyper_hidden, cfg.hyper_layers, B, T, steps])
+    out["meta.flags"] = np.array([args.use_double_q, args.use_huber_loss, per], dtype=np.int64)
+    out["meta.hparams"] = np.array([args.gamma, args.lr, args.opti_eps, args.max_grad_norm, args.tau, args.huber_delta,
+                                    args.per_nu, args.per_eps], dtype=np.float64)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024), "loss", out["s0.loss"])
+
+
+def gen_replay(name="replay_small"):
+    """Uniform + PER sampling goldens from the reference buffers (indices, gathered bytes, IS weights, leaves)."""
+    rh.import_reference()
+    from offpolicy.utils.rec_buffer import RecReplayBuffer, PrioritizedRecReplayBuffer
+    sp = rh.gym_spaces()
+    N, O, A, S, T, E = 3, 6, 5, 7, 4, 16
+    info = {"policy_0": dict(obs_space=[O], share_obs_space=[S], act_space=sp.Discrete(A))}
+    agents = {"policy_0": list(range(N))}
+    out = {"meta": np.array([N, O, A, S, T, E])}
+    rs = np.random.RandomState(3)
+
+    def episodes(n):
+        d = lambda x: {"policy_0": x.astype(np.float32)}
+        de = (rs.rand(T, n, 1) < 0.2).astype(np.float32)
+        de = np.maximum.accumulate(de, axis=0)
+        return (d(rs.randn(T + 1, n, N, O)), d(np.repeat(rs.randn(T + 1, n, 1, S), N, axis=2)),
+                d(np.eye(A)[rs.randint(0, A, (T, n, N))]), d(np.repeat(rs.randn(T, n, 1, 1), N, axis=2)),
+                d(np.repeat(de[:, :, None], N, axis=2)), d(de), d((rs.rand(T + 1, n, N, A) < 0.6)))
+
+    for norm in (False, True):
+        tag = "norm" if norm else "plain"
+        buf = RecReplayBuffer(info, agents, E, T, True, True, use_reward_normalization=norm)
+        ins = []
+        for n_ep in (5, 7, 9):          # third insert wraps the ring (5+7+9 = 21 > 16)
+            ep = episodes(n_ep)
+            ins.append(ep)
+            r = buf.insert(n_ep, *ep)
+            out["%s.idx_range%d" % (tag, len(ins))] = np.asarray(r)
+        for j, ep in enumerate(ins):
+            for k, f in zip(["obs", "share", "acts", "rew", "dones", "dones_env", "avail"], ep):
+                out["%s.ins%d.%s" % (tag, j, k)] = f["policy_0"]
+        np.random.seed(123)
+        for d in range(3):
+            state_pos = np.random.get_state()[2]
+            smp = buf.sample(6)
+            for k, f in zip(["obs", "share", "acts", "rew", "dones", "dones_env", "avail"], smp[:7]):
+                out["%s.draw%d.%s" % (tag, d, k)] = np.ascontiguousarray(f["policy_0"])
+        # the indices themselves (reference does not return them): replay the stream
+        np.random.seed(123)
+        out["%s.inds" % tag] = np.stack([np.random.choice(len(buf), 6) for _ in range(3)])
+
+    # PER: prime leaves through update_priorities (insert priming is broken in the reference, App. D-2)
+    per = PrioritizedRecReplayBuffer(0.6, info, agents, E, T, True, True)
+    ep = episodes(6)
+    per.insert(6, *ep)
+    ep2 = episodes(6)
+    per.insert(6, *ep2)
+    pr = (rs.rand(12) * 3 + 0.05).astype(np.float32)
+    per.update_priorities(np.arange(12), pr, "policy_0")
+    out["per.prio0"] = pr
+    out["per.leaves0"] = per._it_sums["policy_0"]._value.copy()
+    out["per.minleaves0"] = per._it_mins["policy_0"]._value.copy()
+    np.random.seed(77)
+    smp = per.sample(5, 0.4, "policy_0")
+    out["per.w0"], out["per.idx0"] = smp[7], smp[8]
+    # duplicate-index write-back: last write wins
+    idx = np.array([3, 5, 3, 7, 5, 3])
+    pr2 = np.array([0.5, 1.5, 2.5, 0.25, 4.0, 0.125], np.float32)
+    per.update_priorities(idx, pr2, "policy_0")
+    out["per.upd_idx"], out["per.upd_prio"] = idx, pr2
+    out["per.leaves1"] = per._it_sums["policy_0"]._value.copy()
+    out["per.minleaves1"] = per._it_mins["policy_0"]._value.copy()
+    out["per.maxprio1"] = np.asarray(per.max_priorities["policy_0"])
+    smp = per.sample(8, 0.7, "policy_0")
+    out["per.w1"], out["per.idx1"] = smp[7], smp[8]
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    small = QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48)
+    gen_qmix("qmix_small", small)
+    gen_qmix("qmix_small_huber_nodq", small, flags=["--use_huber_loss", "--use_double_q", "--huber_delta", "0.5"], steps=1)
+    gen_qmix("qmix_small_per", small, flags=["--use_per"], per=True, steps=1)
+    gen_qmix("qmix_small_hyper1", QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48, hyper_layers=1), steps=1)
+    gen_qmix("qmix_5ag", QmixConfig(n_agents=5, obs_dim=17, act_dim=11, state_dim=23), B=3, T=6, steps=1)
+    gen_replay()
