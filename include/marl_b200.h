@@ -1,0 +1,211 @@
+/* marl_b200.h -- C-ABI of the B200-native recurrent off-policy MARL update engine (libmarl_b200.so).
+ *
+ * The reference (marlbenchmark/off-policy) is pure Python and has NO FFI/plugin interface
+ * (SURVEY.md section 8(b)): the seam is Python class construction by dotted module path inside
+ * offpolicy/runner/rnn/base_runner.py:7,110-178.  This header is therefore the boundary a maintainer
+ * would bind with ctypes from drop-in classes of the same dotted names; every
+ * entry point below cites the reference function it replaces.
+ *
+ * Conventions
+ *   - plain C: opaque handles, POD structs, raw pointers and sizes; no torch / C++ types.
+ *   - every function returns 0 on success, non-zero on error; mx_last_error() gives the message
+ *     (the reference signals errors with Python asserts/exceptions; the Python mirror re-raises).
+ *   - nothing here allocates device memory: the caller owns every device buffer (sizes come from the
+ *     *_layout / *_bytes queries, which need no GPU) and passes raw device pointers.
+ *   - every launch goes to the cudaStream_t given (as void*), is asynchronous and never synchronises.
+ *     Host pointers given to *_async calls must stay valid until the stream reaches that point
+ *     (cudaMemcpyAsync rules); use pinned memory for real asynchrony.
+ *   - all floating-point data is fp32 unless stated; PER trees are fp64 like the reference
+ *     (offpolicy/utils/segment_tree.py:38,104).
+ */
+#ifndef MARL_B200_H
+#define MARL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MX_ABI_VERSION 1
+#define MX_MAX_NAME 64
+
+typedef struct mx_replay mx_replay;   /* one policy's episode store + sampler (RecPolicyBuffer + PER trees) */
+typedef struct mx_qmix mx_qmix;       /* recurrent QMIX / VDN learner (QMix trainer + QMixPolicy nets + QMixer) */
+
+const char* mx_last_error(void);
+int mx_abi_version(void);
+/* 1 when built by nvcc for sm_100a, 0 for the CPU-emulated unit-test build (tests/emu; never shipped) */
+int mx_is_cuda_build(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Episode replay (HBM-resident SoA, episode-major).
+ * Replaces RecPolicyBuffer.__init__/insert/sample_inds (offpolicy/utils/rec_buffer.py:85-240),
+ * RecReplayBuffer.sample (:62-82) and PrioritizedRecReplayBuffer (:243-324) + SumSegmentTree /
+ * MinSegmentTree (offpolicy/utils/segment_tree.py).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mx_replay_cfg {
+  int32_t capacity;        /* buffer_size: max episodes                              rec_buffer.py:103 */
+  int32_t episode_len;     /* T                                                      rec_buffer.py:104 */
+  int32_t n_agents;        /* N                                                                        */
+  int32_t obs_dim;         /* O                                                                        */
+  int32_t share_dim;       /* S (use_same_share_obs=True layout: one state per step) rec_buffer.py:123 */
+  int32_t act_dim;         /* A (one-hot width, or continuous action width)                            */
+  int32_t use_avail;       /* store avail_acts                                       rec_buffer.py:131 */
+  int32_t use_per;         /* allocate fp64 sum/min trees                            rec_buffer.py:252 */
+  int32_t reward_norm;     /* use_reward_normalization                               rec_buffer.py:209 */
+  int32_t max_batch;       /* largest batch_size that will be sampled                                  */
+  double per_alpha;        /* PER exponent                                           rec_buffer.py:250 */
+} mx_replay_cfg;
+
+/* byte offsets of every region inside the single device blob the caller allocates for a replay */
+typedef struct mx_replay_layout {
+  int32_t obs_ld, share_ld, act_ld;         /* padded innermost strides (multiples of 4 floats)       */
+  int64_t ep_obs, ep_share, ep_acts, ep_avail, ep_rew, ep_dones, ep_dones_env, ep_actidx; /* floats per episode (padded) */
+  int64_t off_obs, off_share, off_acts, off_avail, off_rew, off_dones, off_dones_env, off_actidx;
+  int64_t off_sum_tree, off_min_tree;       /* fp64 [2*tree_cap] each                                  */
+  int64_t off_rng;                          /* uint32 key[624] + pos                                   */
+  int64_t off_state;                        /* device scalars: filled, cursor, max_priority (fp64) ... */
+  int64_t off_stage;                        /* staging area for one insert call (time-major raw)       */
+  int64_t stage_bytes;
+  /* batch region (the sampled batch, same field layout with capacity -> max_batch) */
+  int64_t off_b_obs, off_b_share, off_b_acts, off_b_avail, off_b_rew, off_b_dones, off_b_dones_env, off_b_actidx;
+  int64_t off_b_idx;                        /* int64 [max_batch]   sampled episode indices             */
+  int64_t off_b_weights;                    /* fp64  [max_batch]   PER importance weights              */
+  int64_t off_b_wf32;                       /* fp32  [max_batch]   same, as consumed by the learner    */
+  int64_t off_rstats;                       /* fp64 [4]: masked reward sum, sumsq, count, pad          */
+  int32_t tree_cap;                         /* next pow2 >= capacity                                   */
+  int64_t total_bytes;
+} mx_replay_layout;
+
+int mx_replay_layout_query(const mx_replay_cfg* cfg, mx_replay_layout* out);
+
+/* `blob` = device memory of layout.total_bytes, zero-filled by the caller before create. */
+int mx_replay_create(const mx_replay_cfg* cfg, void* blob, void* stream, mx_replay** out);
+void mx_replay_destroy(mx_replay* r);
+
+/* Ring insert of n_ep whole episodes (rec_buffer.py:146-190).  Arrays are the runner's time-major
+ * host (or device) arrays: obs (T+1,n_ep,N,O), share_obs (T+1,n_ep,S) [agent axis already dropped],
+ * acts (T,n_ep,N,A), rewards (T,n_ep,N), dones (T,n_ep,N), dones_env (T,n_ep), avail (T+1,n_ep,N,A)
+ * or NULL.  `first_slot_out` receives current_i before the insert; slots wrap modulo capacity.
+ * PER: every inserted slot's leaf is primed with max_priority**alpha (intent of rec_buffer.py:263-268). */
+typedef struct mx_episodes {
+  const float *obs, *share_obs, *acts, *rewards, *dones, *dones_env, *avail;
+} mx_episodes;
+int mx_replay_insert_async(mx_replay* r, const mx_episodes* ep, int32_t n_ep, int32_t* first_slot_out, void* stream);
+int32_t mx_replay_len(const mx_replay* r);      /* filled_i  (rec_buffer.py:36-37)  */
+int32_t mx_replay_cursor(const mx_replay* r);   /* current_i                         */
+
+/* NumPy legacy MT19937 state living on the device (np.random.seed / get_state) */
+int mx_replay_seed(mx_replay* r, uint32_t seed, void* stream);
+int mx_replay_set_rng_state(mx_replay* r, const uint32_t key[624], int32_t pos, void* stream);
+int mx_replay_get_rng_state(mx_replay* r, uint32_t key[624], int32_t* pos, void* stream); /* synchronises */
+
+/* RecReplayBuffer.sample (rec_buffer.py:62-82): draw B indices with np.random.choice semantics from the
+ * device-resident stream, then gather every field of those episodes into the batch region. */
+int mx_replay_sample_uniform(mx_replay* r, int32_t B, void* stream);
+/* Same gather for caller-provided indices (host-drawn np.random.choice keeps the process-global NumPy
+ * stream shared with the env loop, exactly like the reference).  idx_dev: int64[B] on the device. */
+int mx_replay_gather(mx_replay* r, const int64_t* idx_dev, int32_t B, void* stream);
+/* PrioritizedRecReplayBuffer.sample (rec_buffer.py:272-304): masses from np.random.random semantics,
+ * fp64 prefix-sum descent, IS weights, gather. */
+int mx_replay_sample_per(mx_replay* r, int32_t B, double beta, void* stream);
+/* update_priorities (rec_buffer.py:306-324): leaf = prio**alpha into both trees, duplicate idx: last wins;
+ * max_priority = max(max_priority, max(prio)).  prio_dev fp32[B] (the trainer hands NumPy fp32), or pass
+ * leaves_f64_dev != NULL to store pre-powered fp64 leaf values verbatim (parity tests). */
+int mx_replay_update_priorities(mx_replay* r, const int64_t* idx_dev, const float* prio_dev,
+                                const double* leaves_f64_dev, const double* max_prio_host, int32_t B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Recurrent QMIX / VDN learner.
+ * Replaces QMix.__init__/train_policy_on_batch/soft_target_updates/hard_target_updates
+ * (offpolicy/algorithms/qmix/qmix.py:11-216), QMixPolicy.get_q_values/q_values_from_actions/
+ * actions_from_q (qmix/algorithm/QMixPolicy.py:42-174), AgentQFunction.forward
+ * (agent_q_function.py:34-67), RNNBase/MLPBase/ACTLayer (algorithms/utils/{rnn,mlp,act}.py),
+ * QMixer.forward (q_mixer.py:68-94), clip_grad_norm_ + Adam (qmix.py:190-193), soft_update
+ * (utils/util.py:123-134).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mx_qmix_cfg {
+  int32_t n_agents, obs_dim, act_dim, state_dim;
+  int32_t hidden;            /* must be 64 (config.py:63 default)                  */
+  int32_t mixer_hidden;      /* mixer_hidden_dim (32)                              */
+  int32_t hyper_hidden;      /* hypernet_hidden_dim (64)                           */
+  int32_t hyper_layers;      /* 1 or 2                                             */
+  int32_t episode_len;       /* T                                                  */
+  int32_t max_batch;         /* B upper bound (workspace sizing)                   */
+  int32_t vdn;               /* 1: sum mixer (vdn_mixer.py:28-40 intent)           */
+  int32_t double_q;          /* use_double_q                                       */
+  int32_t use_huber;         /* use_huber_loss                                     */
+  int32_t use_per;           /* importance weights + new priorities                */
+  int32_t use_avail;         /* avail_acts present in the batch                    */
+  int32_t world_size;        /* data-parallel ranks (1 = single GPU)               */
+  float gamma, huber_delta, per_nu, per_eps;
+  float lr, adam_beta1, adam_beta2, adam_eps, max_grad_norm, tau;
+} mx_qmix_cfg;
+
+typedef struct mx_param_entry {
+  char name[MX_MAX_NAME];    /* reference state_dict key, prefixed "agent." or "mixer."  */
+  int64_t offset;            /* in floats, inside the flat parameter vector; 16-byte aligned */
+  int32_t rows, cols;        /* cols == 0 for 1-D tensors */
+} mx_param_entry;
+
+/* Flat parameter vector layout.  Returns the number of entries (<= max_entries); *total_floats = padded P. */
+int mx_qmix_param_layout(const mx_qmix_cfg* cfg, mx_param_entry* out, int32_t max_entries, int64_t* total_floats);
+int64_t mx_qmix_workspace_bytes(const mx_qmix_cfg* cfg);
+
+/* device buffers, each `total_floats` fp32: theta (live), theta_tgt, adam_m, adam_v; workspace zero-filled. */
+int mx_qmix_create(const mx_qmix_cfg* cfg, float* theta, float* theta_tgt, float* adam_m, float* adam_v,
+                   void* workspace, int64_t workspace_bytes, mx_qmix** out);
+void mx_qmix_destroy(mx_qmix* q);
+
+/* The sampled batch (device pointers, episode-major, padded strides as in mx_replay_layout). */
+typedef struct mx_batch {
+  int32_t B;
+  int32_t obs_ld, share_ld, act_ld;
+  const float* obs;        /* [B][T+1][N][obs_ld]  */
+  const float* share;      /* [B][T+1][share_ld]   */
+  const float* acts;       /* [B][T][N][act_ld]  one-hot (unused by QMIX when act_idx given) */
+  const int32_t* act_idx;  /* [B][T][N]            argmax of the one-hot action (QMixPolicy.py:89) */
+  const float* avail;      /* [B][T+1][N][act_ld]  or NULL */
+  const float* rewards;    /* [B][T][N]            agent 0's stream is used (qmix.py:159) */
+  const float* dones;      /* [B][T][N]            (unused by QMIX) */
+  const float* dones_env;  /* [B][T]               */
+  const float* weights;    /* [B] fp32 PER importance weights or NULL */
+  const int64_t* idx;      /* [B] or NULL */
+} mx_batch;
+int mx_replay_batch(const mx_replay* r, int32_t B, mx_batch* out);   /* view of the replay's batch region */
+
+/* One learner step = QMix.train_policy_on_batch (qmix.py:77-200): forward (live + target agent nets over
+ * T+1 steps, mixers), TD target, masked MSE/Huber, BPTT, global-norm clip, Adam.  With world_size > 1 the
+ * step stops after producing the flat gradient-numerator buffer; the caller all-reduces
+ * mx_qmix_grad_buffer() (sum) and calls mx_qmix_apply(). */
+int mx_qmix_step(mx_qmix* q, const mx_batch* batch, void* stream);
+int mx_qmix_backward_only(mx_qmix* q, const mx_batch* batch, void* stream);  /* everything up to the reduced grads */
+int mx_qmix_apply(mx_qmix* q, void* stream);                                 /* norm + clip + Adam + info scalars   */
+/* flat fp32 buffer to all-reduce: [grad numerators (P) | sum(1-bad) | loss numerator | sum Q_tot(1-bad) | elements ] */
+float* mx_qmix_grad_buffer(mx_qmix* q, int64_t* n_floats);
+/* device fp32[4]: loss, grad_norm (pre-clip), Q_tot, denom -- qmix.py:195-198 */
+const float* mx_qmix_info(mx_qmix* q);
+/* device fp32[B] new PER priorities (qmix.py:179-181) valid after a step with use_per */
+const float* mx_qmix_priorities(mx_qmix* q);
+
+int mx_qmix_soft_update(mx_qmix* q, void* stream);   /* qmix.py:211-216 + util.py:123-134 (all registered params) */
+int mx_qmix_hard_update(mx_qmix* q, void* stream);   /* qmix.py:203-209 */
+
+/* Debug / parity: look up a named fp32 (or int32) region of the workspace written by the last step.
+ * Returns byte offset into the workspace and element count; names are listed in DESIGN.md. */
+int mx_qmix_ws_lookup(const mx_qmix* q, const char* name, int64_t* byte_offset, int64_t* n_elems);
+
+/* Whole-step CUDA graph: [sample (uniform|per) ->] step [-> priority write-back] [-> soft update], captured once
+ * and replayed.  flags: bit0 sample uniform, bit1 sample PER, bit2 soft update, bit3 PER write-back. */
+typedef struct mx_graph mx_graph;
+int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta, uint32_t flags, void* stream, mx_graph** out);
+int mx_graph_launch(mx_graph* g, void* stream);
+void mx_graph_destroy(mx_graph* g);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches counter) */
+int64_t mx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

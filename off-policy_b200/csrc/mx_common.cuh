@@ -1,0 +1,79 @@
+// Common device/host helpers for the B200 (sm_100a) off-policy MARL update engine.
+//
+// Build modes:
+//   * product:  nvcc -gencode arch=compute_100a,code=sm_100a  (the only thing shipped / loaded / timed)
+//   * MARL_EMU: g++ with tests/emu/emu_runtime.h -- CPU fiber emulation of the SIMT kernels, used by the
+//               `-m "not gpu"` unit tests only (kernel-logic checks in a container without a GPU).
+#pragma once
+#include <stdint.h>
+
+#ifdef MARL_EMU
+#include "emu_runtime.h"
+#define MX_EMU 1
+#else
+#include <cuda_runtime.h>
+#define MX_EMU 0
+#define MX_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#define MX_H 64          // hidden size the kernels are specialised for (reference default, config.py:63)
+#define MX_G (3 * MX_H)  // GRU gate rows [r; z; n]
+
+#define MX_DEVINL __device__ __forceinline__
+
+// dynamic shared memory base
+#if MX_EMU
+#define MX_DYN_SMEM(name) float* name = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(emu::dyn_smem()) + 15) & ~uintptr_t(15))
+#else
+#define MX_DYN_SMEM(name)                                    \
+  extern __shared__ __align__(16) unsigned char _mx_smem[]; \
+  float* name = reinterpret_cast<float*>(_mx_smem)
+#endif
+
+MX_DEVINL int mx_imin(int a, int b) { return a < b ? a : b; }
+MX_DEVINL int mx_imax(int a, int b) { return a > b ? a : b; }
+static inline int mx_ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int mx_round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline int64_t mx_round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+MX_DEVINL float mx_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+MX_DEVINL double mx_warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+MX_DEVINL float mx_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+MX_DEVINL float mx_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+MX_DEVINL float4 mx_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+MX_DEVINL void mx_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// streaming 16-byte global load/store (read-once data: bypass L1 allocation)
+MX_DEVINL float4 mx_ld4_stream(const float* p) {
+#if MX_EMU
+  return *reinterpret_cast<const float4*>(p);
+#else
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+#endif
+}
+MX_DEVINL void mx_st4_stream(float* p, float4 v) {
+#if MX_EMU
+  *reinterpret_cast<float4*>(p) = v;
+#else
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#endif
+}
+
+// LayerNorm statistics the way ATen's CPU/CUDA kernels define them: biased variance, eps inside the sqrt.
+#define MX_LN_EPS 1e-5f

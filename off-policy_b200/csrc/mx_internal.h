@@ -1,0 +1,91 @@
+// Internal host-side structures shared by the translation units of libmarl_b200.
+#pragma once
+#include "../../include/marl_b200.h"
+#include "mx_common.cuh"
+
+#include <string>
+
+void mx_set_error(const char* fmt, ...);
+extern long long g_mx_launches;
+#define MX_COUNT() (++g_mx_launches)
+
+#if MX_EMU
+static inline int mx_num_sms() { return 4; }
+#define MX_CHECK_LAUNCH(what) 0
+#else
+int mx_num_sms();
+int mx_check_launch(const char* what);
+#define MX_CHECK_LAUNCH(what) mx_check_launch(what)
+#endif
+
+// ---- replay ------------------------------------------------------------------------------------
+struct MxReplayState {   // device-resident scalars (off_state)
+  int32_t filled;
+  int32_t cursor;
+  int32_t rng_pos;
+  int32_t pad;
+  double max_priority;
+  double reward_mean, reward_std;
+};
+
+struct mx_replay {
+  mx_replay_cfg cfg;
+  mx_replay_layout L;
+  char* blob;
+  int32_t filled, cursor;   // host mirror (inserts are host-driven)
+};
+
+// ---- agent net / mixer parameter layouts (offsets in floats inside the flat vector) --------------
+struct MxNetLayout {       // RNNBase (LN -> fc1 -> LN -> fc2 -> LN -> GRU -> LN) + Linear head
+  int in_dim, out_dim;
+  int fn_g, fn_b;
+  int w1, b1, ln1_g, ln1_b;
+  int wh, bh, lnh_g, lnh_b;   // fc_h: registered, unused in forward (mlp.py:21-29); polyak-averaged only
+  int w2, b2, ln2_g, ln2_b;
+  int wih, whh, bih, bhh;
+  int lno_g, lno_b;
+  int wq, bq;
+  int size;                   // floats, multiple of 4
+};
+struct MxMixLayout {
+  int S, N, ME, HY, layers;
+  int w1a, b1a, w1b, b1b;     // hyper_w1: (layers==2) Linear(S,HY) -> ReLU -> Linear(HY,N*ME); (layers==1) only "b" = Linear(S,N*ME)
+  int w2a, b2a, w2b, b2b;     // hyper_w2
+  int wb1, bb1;               // hyper_b1 Linear(S,ME)
+  int wb2a, bb2a, wb2b, bb2b; // hyper_b2 Linear(S,HY) -> ReLU -> Linear(HY,1)
+  int size;
+};
+int mx_net_layout(int in_dim, int out_dim, int base, MxNetLayout* L);
+int mx_mix_layout(int S, int N, int ME, int HY, int layers, int base, MxMixLayout* L);
+
+// ---- QMIX learner workspace -----------------------------------------------------------------------
+struct MxQmixWs {           // offsets in floats into the workspace
+  int64_t gi[2], hall[2];   // [net][M][3H], [net][M][H]
+  int64_t u1, u2, st0, st1, st2, sto, gates, hn;   // live-net activations kept for backward
+  int64_t qall[2];          // [net][M][A]  (debug + greedy)
+  int64_t greedy;           // int32 [M]
+  int64_t q_taken, q_next;  // [B*T][N]
+  int64_t qtot, qtot_next, err, huberp;  // [B*T]
+  int64_t dq_taken;         // [B*T][N]
+  int64_t dh_out;           // [M][H]
+  int64_t dgi;              // [M][3H]
+  int64_t gpart;            // [npart][P]
+  int64_t grad;             // [P + 8]   flat gradient numerators + scalars (all-reduce payload)
+  int64_t info;             // [8]
+  int64_t prio;             // [max_batch]
+  int64_t spart;            // [npart][8] per-CTA scalar partials (denominator, loss numerator, sum Q_tot)
+  int64_t adam_t;           // double[4]: step count, beta1^t, beta2^t
+  int64_t total;
+};
+
+struct mx_qmix {
+  mx_qmix_cfg cfg;
+  MxNetLayout agent;
+  MxMixLayout mix;
+  int64_t P;               // padded parameter count
+  int npart;               // number of per-CTA gradient partials
+  float *theta, *theta_tgt, *adam_m, *adam_v;
+  float* ws;
+  int64_t ws_bytes;
+  MxQmixWs W;
+};
