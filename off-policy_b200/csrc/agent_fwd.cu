@@ -1,0 +1,330 @@
+// Forward kernels of the recurrent agent network (RNNBase + Linear head), live and target nets in one launch.
+//
+//   k_front_fwd   time-batched front: LN(x) -> fc1 -> ReLU -> LN -> fc2 -> ReLU -> LN -> W_ih (all T+1 steps at once)
+//                 reference: algorithms/utils/mlp.py:25-29,76-87 + the input half of nn.GRU (rnn.py:21)
+//   k_gru_fwd     the serial recurrence h_t = GRU(gi_t, h_{t-1}), W_hh resident in registers, h in shared memory
+//                 reference: nn.GRU called from algorithms/utils/rnn.py:19-23 (gate order r,z,n; h_0 = 0)
+//   k_qhead       LN(h_t) -> Linear(H,A), taken-action gather, avail-masked greedy argmax (double-Q), target gather
+//                 reference: rnn.py:22, act.py:32, QMixPolicy.py:69-93,102-174, utils/util.py:297-302, qmix.py:134-148
+//
+// Row order: row-step m = (b*(T+1) + t)*N + n (episode-major, exactly the sampled batch's memory order), so the
+// front kernels see one dense [M][ld] matrix; the reference stacks agents on the batch axis instead (qmix.py:108).
+#include "mx_internal.h"
+#include "mx_kernels.h"
+#include "mx_tile.cuh"
+
+// =====================================================================================================
+// front forward
+// =====================================================================================================
+template <int RM>
+__global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
+  constexpr int TM = 16 * RM;
+  MX_DYN_SMEM(smem);
+  const int net = blockIdx.y;
+  const float* __restrict__ th = a.theta[net];
+  const MxNetLayout L = a.L;
+  const int I = L.in_dim, Ipad = (I + 3) & ~3;
+  const int lda = mx_ld_dev(Ipad > MX_H ? Ipad : MX_H);
+  const int ldw = lda;
+  float* A_s = smem;                 // [TM][lda]
+  float* Wc = A_s + TM * lda;        // [64][ldw]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+  const bool live = (net == 0);
+  const int ntiles = (a.M + TM - 1) / TM;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m0 = tile * TM;
+    // ---- load the input rows, LayerNorm over the I features (warp per row) ----
+    for (int r = warp; r < TM; r += MX_TILE_THREADS / 32) {
+      const int m = m0 + r;
+      float* row = A_s + r * lda;
+      if (m < a.M) {
+        const float* x = a.X + (size_t)m * a.ldx;
+        float s = 0.f;
+        for (int c = lane; c < I; c += 32) s += x[c];
+        const float mean = mx_warp_sum(s) / (float)I;
+        float q = 0.f;
+        for (int c = lane; c < I; c += 32) { float d = x[c] - mean; q += d * d; }
+        const float rstd = rsqrtf(mx_warp_sum(q) / (float)I + MX_LN_EPS);
+        for (int c = lane; c < Ipad; c += 32) {
+          float v = 0.f;
+          if (c < I) v = a.feature_norm ? ((x[c] - mean) * rstd * th[L.fn_g + c] + th[L.fn_b + c]) : x[c];
+          row[c] = v;
+        }
+        if (live && lane == 0 && a.st0) { a.st0[2 * (size_t)m] = mean; a.st0[2 * (size_t)m + 1] = rstd; }
+      } else {
+        for (int c = lane; c < Ipad; c += 32) row[c] = 0.f;
+      }
+    }
+    // ---- fc1 and fc2: Linear -> ReLU -> LayerNorm, output becomes the next layer's A operand ----
+    for (int layer = 0; layer < 2; ++layer) {
+      const int K = layer == 0 ? I : MX_H, Kpad = (K + 3) & ~3;
+      const int w_off = layer == 0 ? L.w1 : L.w2, b_off = layer == 0 ? L.b1 : L.b2;
+      const int g_off = layer == 0 ? L.ln1_g : L.ln2_g, be_off = layer == 0 ? L.ln1_b : L.ln2_b;
+      mx_stage_weight(Wc, ldw, th + w_off, MX_H, K, K, 0, 0, Kpad);
+      __syncthreads();
+      float acc[RM][4];
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      mx_mm_nt<RM>(A_s, lda, Wc, ldw, Kpad, acc);
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaxf(acc[i][j] + th[b_off + tx + 16 * j], 0.f);
+      float mean[RM], rstd[RM];
+      mx_row_stats64<RM>(acc, mean, rstd);
+      float* u_out = layer == 0 ? a.u1 : a.u2;
+      float* st_out = layer == 0 ? a.st1 : a.st2;
+      __syncthreads();   // every thread is done reading A_s / Wc
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        const int r = ty * RM + i, m = m0 + r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = tx + 16 * j;
+          A_s[r * lda + c] = (acc[i][j] - mean[i]) * rstd[i] * th[g_off + c] + th[be_off + c];
+          if (live && m < a.M && u_out) u_out[(size_t)m * MX_H + c] = acc[i][j];
+        }
+        if (live && m < a.M && tx == 0 && st_out) { st_out[2 * (size_t)m] = mean[i]; st_out[2 * (size_t)m + 1] = rstd[i]; }
+      }
+      // (the next mx_stage_weight writes Wc, which nobody reads any more; A_s is published by the barrier below)
+    }
+    // ---- gi = x2 . W_ih^T + b_ih, three 64-row chunks (r, z, n) ----
+    float* gi = a.gi[net];
+    for (int c3 = 0; c3 < 3; ++c3) {
+      mx_stage_weight(Wc, ldw, th + L.wih, MX_G, MX_H, MX_H, 64 * c3, 0, MX_H);
+      __syncthreads();
+      float acc[RM][4];
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      mx_mm_nt<RM>(A_s, lda, Wc, ldw, MX_H, acc);
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        const int m = m0 + ty * RM + i;
+        if (m < a.M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = 64 * c3 + tx + 16 * j;
+            gi[(size_t)m * MX_G + c] = acc[i][j] + th[L.bih + c];
+          }
+        }
+      }
+      __syncthreads();   // Wc is restaged next; A_s is rewritten by the next tile
+    }
+  }
+}
+
+// =====================================================================================================
+// GRU recurrence
+// =====================================================================================================
+template <int RPC>
+__global__ void __launch_bounds__(MX_G) k_gru_fwd(GruFwdArgs a) {
+  __shared__ __align__(16) float h_s[RPC][MX_H];
+  __shared__ float pre_s[RPC][MX_G];     // r,z: gi + gh ; n: gh_n (incl. b_hn)
+  __shared__ float gin_s[RPC][MX_H];     // gi_n
+  const int net = blockIdx.y;
+  const float* __restrict__ th = a.theta[net];
+  const int j = threadIdx.x;             // gate row 0..191
+  const int row0 = blockIdx.x * RPC;
+  const bool live = (net == 0);
+  // W_hh row j resident in registers for the whole sequence
+  float w[MX_H];
+#pragma unroll
+  for (int k = 0; k < MX_H; ++k) w[k] = th[a.whh + j * MX_H + k];
+  const float bias = th[a.bhh + j];
+  for (int idx = j; idx < RPC * MX_H; idx += MX_G) (&h_s[0][0])[idx] = 0.f;   // h_0 = 0 (QMixPolicy.py:193-196)
+
+  const float* gi = a.gi[net];
+  float* hall = a.hall[net];
+  const int T1 = a.T + 1, N = a.N;
+  size_t mrow[RPC];
+  bool valid[RPC];
+#pragma unroll
+  for (int r = 0; r < RPC; ++r) {
+    const int row = row0 + r;
+    valid[r] = row < a.R;
+    const int b = valid[r] ? row / N : 0, n = valid[r] ? row % N : 0;
+    mrow[r] = ((size_t)b * T1) * N + n;      // + t*N per step
+  }
+  float g_next[RPC];
+#pragma unroll
+  for (int r = 0; r < RPC; ++r) g_next[r] = valid[r] ? gi[mrow[r] * MX_G + j] : 0.f;
+  __syncthreads();
+
+  for (int t = 0; t < T1; ++t) {
+    float g_cur[RPC];
+#pragma unroll
+    for (int r = 0; r < RPC; ++r) {
+      g_cur[r] = g_next[r];
+      if (t + 1 < T1 && valid[r]) g_next[r] = gi[(mrow[r] + (size_t)(t + 1) * N) * MX_G + j];   // prefetch next step
+    }
+    float acc[RPC];
+#pragma unroll
+    for (int r = 0; r < RPC; ++r) acc[r] = bias;
+#pragma unroll
+    for (int k = 0; k < MX_H; k += 4) {
+#pragma unroll
+      for (int r = 0; r < RPC; ++r) {
+        const float4 h4 = mx_ld4(&h_s[r][k]);
+        acc[r] = fmaf(w[k], h4.x, acc[r]);
+        acc[r] = fmaf(w[k + 1], h4.y, acc[r]);
+        acc[r] = fmaf(w[k + 2], h4.z, acc[r]);
+        acc[r] = fmaf(w[k + 3], h4.w, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPC; ++r) {
+      if (j < 2 * MX_H) pre_s[r][j] = acc[r] + g_cur[r];
+      else { pre_s[r][j] = acc[r]; gin_s[r][j - 2 * MX_H] = g_cur[r]; }
+    }
+    __syncthreads();
+    for (int idx = j; idx < RPC * MX_H; idx += MX_G) {
+      const int r = idx / MX_H, i = idx % MX_H;
+      const float rg = mx_sigmoid(pre_s[r][i]);
+      const float zg = mx_sigmoid(pre_s[r][MX_H + i]);
+      const float hn = pre_s[r][2 * MX_H + i];
+      const float ng = tanhf(gin_s[r][i] + rg * hn);
+      const float hp = h_s[r][i];
+      const float hnew = (1.f - zg) * ng + zg * hp;
+      h_s[r][i] = hnew;                     // only this thread touches h_s[r][i] in this phase
+      const int row = row0 + r;
+      if (row < a.R) {
+        const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
+        hall[mm * MX_H + i] = hnew;
+        if (live) {
+          a.gates[mm * MX_G + i] = rg;
+          a.gates[mm * MX_G + MX_H + i] = zg;
+          a.gates[mm * MX_G + 2 * MX_H + i] = ng;
+          a.hn[mm * MX_H + i] = hn;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// =====================================================================================================
+// Q head + action selection (one warp per row-step)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_qhead(QHeadArgs a) {
+  __shared__ float wq_s[2][32 * MX_H];   // A <= 32
+  __shared__ float bq_s[2][32];
+  __shared__ float lg_s[2][MX_H], lb_s[2][MX_H];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int A = a.A;
+  for (int net = 0; net < 2; ++net) {
+    const float* th = a.theta[net];
+    for (int i = tid; i < A * MX_H; i += blockDim.x) wq_s[net][i] = th[a.wq + i];
+    for (int i = tid; i < A; i += blockDim.x) bq_s[net][i] = th[a.bq + i];
+    for (int i = tid; i < MX_H; i += blockDim.x) { lg_s[net][i] = th[a.lno_g + i]; lb_s[net][i] = th[a.lno_b + i]; }
+  }
+  __syncthreads();
+  const int wglobal = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+  const int wtotal = gridDim.x * (blockDim.x >> 5);
+  const int T1 = a.T + 1, N = a.N;
+  for (int m = wglobal; m < a.M; m += wtotal) {
+    const int n = m % N;
+    const int bt = m / N;
+    const int t = bt % T1, b = bt / T1;
+    float q_live_at_act = 0.f, tq_sel = 0.f;
+    int greedy = 0;
+    // ---------------- live ----------------
+    {
+      const float* h = a.hall[0] + (size_t)m * MX_H;
+      const float h0 = h[lane], h1 = h[lane + 32];
+      const float mean = mx_warp_sum(h0 + h1) * (1.f / MX_H);
+      const float d0 = h0 - mean, d1 = h1 - mean;
+      const float rstd = rsqrtf(mx_warp_sum(d0 * d0 + d1 * d1) * (1.f / MX_H) + MX_LN_EPS);
+      if (lane == 0) { a.sto[2 * (size_t)m] = mean; a.sto[2 * (size_t)m + 1] = rstd; }
+      const float y0 = d0 * rstd * lg_s[0][lane] + lb_s[0][lane];
+      const float y1 = d1 * rstd * lg_s[0][lane + 32] + lb_s[0][lane + 32];
+      const int act = (t < a.T) ? a.act_idx[((size_t)b * a.T + t) * N + n] : 0;
+      float best = 0.f;
+      for (int k = 0; k < A; ++k) {
+        float q = mx_warp_sum(y0 * wq_s[0][k * MX_H + lane] + y1 * wq_s[0][k * MX_H + lane + 32]) + bq_s[0][k];
+        if (a.qall0 && lane == 0) a.qall0[(size_t)m * A + k] = q;
+        if (k == act) q_live_at_act = q;
+        float qm = q;
+        if (a.avail && a.avail[(size_t)m * a.act_ld + k] == 0.f) qm = -1e10f;     // util.py:297-302
+        if (k == 0 || qm > best) { best = qm; greedy = k; }                     // first maximum wins
+      }
+    }
+    // ---------------- target ----------------
+    {
+      const float* h = a.hall[1] + (size_t)m * MX_H;
+      const float h0 = h[lane], h1 = h[lane + 32];
+      const float mean = mx_warp_sum(h0 + h1) * (1.f / MX_H);
+      const float d0 = h0 - mean, d1 = h1 - mean;
+      const float rstd = rsqrtf(mx_warp_sum(d0 * d0 + d1 * d1) * (1.f / MX_H) + MX_LN_EPS);
+      const float y0 = d0 * rstd * lg_s[1][lane] + lb_s[1][lane];
+      const float y1 = d1 * rstd * lg_s[1][lane + 32] + lb_s[1][lane + 32];
+      float tbest = 0.f;
+      for (int k = 0; k < A; ++k) {
+        float q = mx_warp_sum(y0 * wq_s[1][k * MX_H + lane] + y1 * wq_s[1][k * MX_H + lane + 32]) + bq_s[1][k];
+        if (a.qall1 && lane == 0) a.qall1[(size_t)m * A + k] = q;
+        if (a.double_q) { if (k == greedy) tq_sel = q; }
+        else if (k == 0 || q > tbest) { tbest = q; tq_sel = q; }                 // plain max, no avail mask (qmix.py:144)
+      }
+    }
+    if (lane == 0) {
+      if (a.greedy) a.greedy[m] = greedy;
+      if (t < a.T) a.q_taken[((size_t)b * a.T + t) * N + n] = q_live_at_act;
+      if (t >= 1) a.q_next[((size_t)b * a.T + (t - 1)) * N + n] = tq_sel;
+    }
+  }
+}
+
+// =====================================================================================================
+// launchers
+// =====================================================================================================
+size_t mx_front_fwd_smem(int in_dim, int RM) {
+  const int Ipad = mx_round_up(in_dim, 4);
+  const int lda = mx_ld(Ipad > MX_H ? Ipad : MX_H);
+  return (size_t)(16 * RM + 64) * lda * sizeof(float);
+}
+
+int mx_launch_front_fwd(const FrontFwdArgs& a, int nets, cudaStream_t s) {
+  const int RM = 2;
+  const int ntiles = mx_ceil_div(a.M, 16 * RM);
+  int gx = mx_num_sms() / nets;
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  const size_t smem = mx_front_fwd_smem(a.L.in_dim, RM);
+  auto kern = k_front_fwd<2>;
+#if !MX_EMU
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { mx_set_error("front_fwd: smem %zu too large", smem); return 1; }
+    configured = smem;
+  }
+#endif
+  MX_LAUNCH(kern, dim3(gx, nets), dim3(MX_TILE_THREADS), smem, s, a);
+  MX_COUNT();
+  return MX_CHECK_LAUNCH("front_fwd");
+}
+
+int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s) {
+  const int sms = mx_num_sms();
+  int rpc = 1;
+  while (rpc < 4 && mx_ceil_div(a.R, rpc) * nets > 2 * sms) rpc *= 2;
+  dim3 grid(mx_ceil_div(a.R, rpc), nets);
+  if (rpc == 1) MX_LAUNCH(k_gru_fwd<1>, grid, dim3(MX_G), 0, s, a);
+  else if (rpc == 2) MX_LAUNCH(k_gru_fwd<2>, grid, dim3(MX_G), 0, s, a);
+  else MX_LAUNCH(k_gru_fwd<4>, grid, dim3(MX_G), 0, s, a);
+  MX_COUNT();
+  return MX_CHECK_LAUNCH("gru_fwd");
+}
+
+int mx_launch_qhead(const QHeadArgs& a, cudaStream_t s) {
+  if (a.A > 32) { mx_set_error("qhead: act_dim %d > 32 unsupported", a.A); return 1; }
+  int grid = mx_ceil_div(a.M, 8);
+  const int cap = mx_num_sms() * 4;
+  if (grid > cap) grid = cap;
+  MX_LAUNCH(k_qhead, dim3(grid), dim3(256), 0, s, a);
+  MX_COUNT();
+  return MX_CHECK_LAUNCH("qhead");
+}

@@ -32,9 +32,9 @@
 
 MX_DEVINL int mx_imin(int a, int b) { return a < b ? a : b; }
 MX_DEVINL int mx_imax(int a, int b) { return a > b ? a : b; }
-static inline int mx_ceil_div(int a, int b) { return (a + b - 1) / b; }
-static inline int mx_round_up(int a, int b) { return (a + b - 1) / b * b; }
-static inline int64_t mx_round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+__host__ __device__ static inline int mx_ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int mx_round_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ static inline int64_t mx_round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 MX_DEVINL float mx_warp_sum(float v) {
 #pragma unroll

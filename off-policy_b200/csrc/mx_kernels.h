@@ -1,0 +1,126 @@
+// Kernel argument blocks + launcher prototypes (internal).
+#pragma once
+#include "mx_internal.h"
+
+struct FrontFwdArgs {
+  const float* X;          // [M][ldx] dense input rows
+  int ldx, M;
+  int feature_norm;
+  const float* theta[2];   // live, target flat parameter vectors
+  MxNetLayout L;
+  float* gi[2];            // [M][3H]
+  float *u1, *u2;          // live: post-ReLU pre-LN activations [M][H]
+  float *st0, *st1, *st2;  // live: (mean, rstd) per row for the three LayerNorms
+};
+size_t mx_front_fwd_smem(int in_dim, int RM);
+int mx_launch_front_fwd(const FrontFwdArgs& a, int nets, cudaStream_t s);
+
+struct GruFwdArgs {
+  const float* theta[2];
+  int whh, bhh;
+  const float* gi[2];
+  float* hall[2];          // [M][H]  h_t after step t
+  float* gates;            // live [M][3H] (r, z, n)
+  float* hn;               // live [M][H]  W_hn h + b_hn
+  int R, T, N;             // rows = B*N, episode length, agents
+};
+int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s);
+
+struct QHeadArgs {
+  const float* theta[2];
+  int wq, bq, lno_g, lno_b;
+  const float* hall[2];
+  float* sto;              // live post-GRU LN stats [M][2]
+  const int32_t* act_idx;  // [B][T][N]
+  const float* avail;      // [M][act_ld] or null
+  int act_ld;
+  int M, T, N, A, double_q;
+  float *q_taken, *q_next; // [B*T][N]
+  int32_t* greedy;         // [M] (debug)
+  float *qall0, *qall1;    // [M][A] (debug) or null
+};
+int mx_launch_qhead(const QHeadArgs& a, cudaStream_t s);
+
+struct MixerArgs {
+  const float *theta, *theta_tgt;
+  MxMixLayout L;
+  int vdn;
+  const float* share;      // [B][T+1][share_ld]
+  int share_ld;
+  const float *q_taken, *q_next;   // [E][N]
+  const float* rewards;    // [B][T][N]
+  const float* dones_env;  // [B][T]
+  const float* weights;    // [B] or null
+  int B, T, N;
+  float gamma, huber_delta;
+  int use_huber;
+  float *qtot, *qtot_next, *err;   // [E]
+  float* dq_taken;         // [E][N]
+  float* gpart;            // [npart][P]   this kernel writes the mixer slice of partial blockIdx.x
+  long long P;
+  float* spart;            // [npart][8]   (sum(1-bad), loss numerator, sum Q_tot(1-bad))
+};
+int mx_launch_mixer(const MixerArgs& a, int* nparts_used, cudaStream_t s);
+
+struct QHeadBwdArgs {
+  const float* theta;
+  int wq, bq, lno_g, lno_b;
+  const float* hall;       // live [M][H]
+  const float* sto;        // [M][2]
+  const int32_t* act_idx;
+  const float* dq_taken;   // [E][N]
+  int M, T, N, A;
+  float* dh_out;           // [M][H]
+  float* gpart;
+  long long P;
+};
+int mx_launch_qhead_bwd(const QHeadBwdArgs& a, int* nparts_used, cudaStream_t s);
+
+struct GruBwdArgs {
+  const float* theta;
+  int whh;
+  const float* hall;       // live [M][H]
+  const float* gates;      // [M][3H]
+  const float* hn;         // [M][H]
+  const float* dh_out;     // [M][H]
+  float* dgi;              // [M][3H]   d(loss)/d(gi) ; t == T rows are zero-filled
+  int R, T, N;
+};
+int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s);
+
+struct FrontBwdArgs {
+  const float* X;          // [M][ldx]
+  int ldx, M, T, N;
+  int feature_norm;
+  const float* theta;
+  MxNetLayout L;
+  const float *u1, *u2, *st0, *st1, *st2;
+  const float* dgi;        // [M][3H]
+  const float* gates;      // [M][3H] (r needed for dgh_n)
+  const float* hall;       // [M][H]
+  float* gpart;
+  long long P;
+};
+int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s);
+
+struct OptimArgs {
+  float *theta, *theta_tgt, *adam_m, *adam_v;
+  const float* gpart;
+  float* grad;             // [P + 8]
+  long long P;
+  int seg_begin[4], seg_end[4], seg_parts[4], nseg;   // parameter segments and how many partials each has
+  const float* spart;
+  int spart_n;
+  float* info;             // [8]
+  double* adam_t;          // [4]
+  // loss / PER finalisation
+  const float* err;        // [B][T] masked TD errors
+  int B, T;
+  float per_nu, per_eps;
+  float* prio;             // [B] or null
+  float lr, beta1, beta2, eps, max_grad_norm, tau;
+  int world_size;
+};
+int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s);
+int mx_launch_adam(const OptimArgs& a, cudaStream_t s);
+int mx_launch_polyak(float* tgt, const float* src, long long n, float tau, cudaStream_t s);

@@ -1,0 +1,142 @@
+// Gradient partial reduction, loss / PER finalisation, global-norm clip + Adam, Polyak target update.
+//
+// reference: torch.nn.utils.clip_grad_norm_(params, max_grad_norm) + torch.optim.Adam.step (qmix.py:190-193),
+// soft_update (utils/util.py:123-134), PER priorities (qmix.py:176-181), train_info (qmix.py:195-198).
+//
+// Pipeline:  k_grad_reduce  : grad[i] = sum over per-CTA partials (deterministic order); block `gridDim.x-1`
+//                             also finalises the scalar sums, the PER priorities and bumps the Adam step count
+//            [NCCL all-reduce of grad[0 .. P+4) when world_size > 1]
+//            k_adam         : every CTA recomputes ||grad||^2 over the whole (L2-resident) buffer in the same
+//                             order -- no grid-wide barrier needed -- then clips and updates its own slice.
+#include <math.h>
+
+#include "mx_internal.h"
+#include "mx_kernels.h"
+
+__global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
+  const int tid = threadIdx.x;
+  if (blockIdx.x == gridDim.x - 1) {
+    // ---- scalar sums: sum(1-bad), loss numerator, sum Q_tot(1-bad) ----
+    __shared__ float red[3][256];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int i = tid; i < a.spart_n; i += blockDim.x) { s0 += a.spart[i * 8]; s1 += a.spart[i * 8 + 1]; s2 += a.spart[i * 8 + 2]; }
+    red[0][tid] = s0; red[1][tid] = s1; red[2][tid] = s2;
+    __syncthreads();
+    if (tid == 0) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      for (int i = 0; i < (int)blockDim.x; ++i) { t0 += red[0][i]; t1 += red[1][i]; t2 += red[2][i]; }
+      a.grad[a.P + 0] = t0;
+      a.grad[a.P + 1] = t1;
+      a.grad[a.P + 2] = t2;
+      a.grad[a.P + 3] = (float)(a.B * a.T);
+      a.adam_t[0] += 1.0;                                  // Adam step count (1-based)
+    }
+    // ---- PER: new priority = (1-nu) * mean_t|e| + nu * max_t|e| + eps  (mean over all T, masked steps are zeros) ----
+    if (a.prio) {
+      for (int b = tid; b < a.B; b += blockDim.x) {
+        float mx = 0.f, sm = 0.f;
+        for (int t = 0; t < a.T; ++t) {
+          const float e = fabsf(a.err[(size_t)b * a.T + t]);
+          sm += e;
+          mx = fmaxf(mx, e);
+        }
+        a.prio[b] = (1.f - a.per_nu) * (sm / (float)a.T) + a.per_nu * mx + a.per_eps;
+      }
+    }
+    return;
+  }
+  const long long i = (long long)blockIdx.x * blockDim.x + tid;
+  if (i >= a.P) return;
+  int parts = 0;
+  for (int s = 0; s < a.nseg; ++s)
+    if (i >= a.seg_begin[s] && i < a.seg_end[s]) parts = a.seg_parts[s];
+  float g = 0.f;
+  for (int p = 0; p < parts; ++p) g += a.gpart[(size_t)p * a.P + i];
+  a.grad[i] = g;
+}
+
+__global__ void __launch_bounds__(256) k_adam(OptimArgs a) {
+  __shared__ double red[256];
+  __shared__ float s_coef, s_invd;
+  const int tid = threadIdx.x;
+  const float denom = a.grad[a.P + 0];
+  const float invd = 1.0f / denom;
+  // ||g||^2 over the full vector, identical summation order in every CTA
+  double ss = 0.0;
+  const long long P4 = a.P / 4;
+  for (long long i = tid; i < P4; i += blockDim.x) {
+    const float4 g = mx_ld4(a.grad + 4 * i);
+    const float gx = g.x * invd, gy = g.y * invd, gz = g.z * invd, gw = g.w * invd;
+    ss += (double)gx * gx + (double)gy * gy + (double)gz * gz + (double)gw * gw;
+  }
+  red[tid] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)blockDim.x; ++i) t += red[i];
+    const float norm = (float)sqrt(t);
+    float coef = a.max_grad_norm / (norm + 1e-6f);       // clip_grad_norm_: always applied, clamped to 1
+    if (coef > 1.f) coef = 1.f;
+    s_coef = coef;
+    s_invd = invd;
+    if (blockIdx.x == 0) {
+      a.info[0] = a.grad[a.P + 1] * invd;                // loss
+      a.info[1] = norm;                                  // grad_norm (pre-clip)
+      a.info[2] = a.grad[a.P + 2] / a.grad[a.P + 3];     // Q_tot mean over all (t,b)
+      a.info[3] = denom;
+    }
+  }
+  __syncthreads();
+  const float scale = s_coef * s_invd;
+  const double t = a.adam_t[0];
+  const float bc1 = (float)(1.0 - pow((double)a.beta1, t));
+  const float bc2s = (float)sqrt(1.0 - pow((double)a.beta2, t));
+  const float step = a.lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < a.P; i += (long long)gridDim.x * blockDim.x) {
+    const float g = a.grad[i] * scale;
+    float m = a.adam_m[i], v = a.adam_v[i];
+    m = m + (g - m) * (1.f - a.beta1);                   // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * a.beta2 + (1.f - a.beta2) * g * g;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float den = sqrtf(v) / bc2s + a.eps;
+    a.theta[i] = a.theta[i] - step * (m / den);
+    a.adam_m[i] = m;
+    a.adam_v[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_polyak(float* __restrict__ tgt, const float* __restrict__ src, long long n4, float tau) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 t = mx_ld4(tgt + 4 * i);
+    const float4 s = mx_ld4(src + 4 * i);
+    t.x = t.x * (1.0f - tau) + s.x * tau;                // util.py:132-134
+    t.y = t.y * (1.0f - tau) + s.y * tau;
+    t.z = t.z * (1.0f - tau) + s.z * tau;
+    t.w = t.w * (1.0f - tau) + s.w * tau;
+    mx_st4(tgt + 4 * i, t);
+  }
+}
+
+int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s) {
+  const int grid = (int)((a.P + 255) / 256) + 1;
+  MX_LAUNCH(k_grad_reduce, dim3(grid), dim3(256), 0, s, a);
+  MX_COUNT();
+  return MX_CHECK_LAUNCH("grad_reduce");
+}
+int mx_launch_adam(const OptimArgs& a, cudaStream_t s) {
+  int grid = (int)((a.P + 1023) / 1024);
+  const int sms = mx_num_sms();
+  if (grid > sms) grid = sms;
+  MX_LAUNCH(k_adam, dim3(grid), dim3(256), 0, s, a);
+  MX_COUNT();
+  return MX_CHECK_LAUNCH("adam");
+}
+int mx_launch_polyak(float* tgt, const float* src, long long n, float tau, cudaStream_t s) {
+  const long long n4 = n / 4;
+  int grid = (int)((n4 + 255) / 256);
+  const int sms = mx_num_sms();
+  if (grid > sms) grid = sms;
+  if (grid < 1) grid = 1;
+  MX_LAUNCH(k_polyak, dim3(grid), dim3(256), 0, s, tgt, src, n4, tau);
+  MX_COUNT();
+  return MX_CHECK_LAUNCH("polyak");
+}

@@ -1,0 +1,394 @@
+// Recurrent QMIX / VDN learner: parameter + workspace layout, the step's launch sequence, CUDA-graph capture.
+// reference: offpolicy/algorithms/qmix/qmix.py (QMix), see include/marl_b200.h for the per-entry-point mapping.
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "mx_internal.h"
+#include "mx_kernels.h"
+
+// =====================================================================================================
+// parameter layouts (names = the reference's state_dict keys)
+// =====================================================================================================
+static int take(int& off, int n) { int o = off; off += mx_round_up(n, 4); return o; }
+
+int mx_net_layout(int in_dim, int out_dim, int base, MxNetLayout* L) {
+  const int H = MX_H;
+  int o = base;
+  L->in_dim = in_dim; L->out_dim = out_dim;
+  L->fn_g = take(o, in_dim); L->fn_b = take(o, in_dim);
+  L->w1 = take(o, H * in_dim); L->b1 = take(o, H); L->ln1_g = take(o, H); L->ln1_b = take(o, H);
+  L->wh = take(o, H * H); L->bh = take(o, H); L->lnh_g = take(o, H); L->lnh_b = take(o, H);
+  L->w2 = take(o, H * H); L->b2 = take(o, H); L->ln2_g = take(o, H); L->ln2_b = take(o, H);
+  L->wih = take(o, 3 * H * H); L->whh = take(o, 3 * H * H); L->bih = take(o, 3 * H); L->bhh = take(o, 3 * H);
+  L->lno_g = take(o, H); L->lno_b = take(o, H);
+  L->wq = take(o, out_dim * H); L->bq = take(o, out_dim);
+  L->size = o - base;
+  return 0;
+}
+
+int mx_mix_layout(int S, int N, int ME, int HY, int layers, int base, MxMixLayout* L) {
+  int o = base;
+  L->S = S; L->N = N; L->ME = ME; L->HY = HY; L->layers = layers;
+  if (layers == 2) {
+    L->w1a = take(o, HY * S); L->b1a = take(o, HY); L->w1b = take(o, N * ME * HY); L->b1b = take(o, N * ME);
+    L->w2a = take(o, HY * S); L->b2a = take(o, HY); L->w2b = take(o, ME * HY); L->b2b = take(o, ME);
+  } else {
+    L->w1a = L->b1a = L->w2a = L->b2a = -1;
+    L->w1b = take(o, N * ME * S); L->b1b = take(o, N * ME);
+    L->w2b = take(o, ME * S); L->b2b = take(o, ME);
+  }
+  L->wb1 = take(o, ME * S); L->bb1 = take(o, ME);
+  L->wb2a = take(o, HY * S); L->bb2a = take(o, HY); L->wb2b = take(o, HY); L->bb2b = take(o, 1);
+  L->size = o - base;
+  return 0;
+}
+
+static int check_cfg(const mx_qmix_cfg* c) {
+  if (!c) { mx_set_error("null cfg"); return 1; }
+  if (c->hidden != MX_H) { mx_set_error("hidden_size %d unsupported: kernels are specialised for %d", c->hidden, MX_H); return 1; }
+  if (c->n_agents <= 0 || c->obs_dim <= 0 || c->act_dim <= 0 || c->state_dim <= 0 || c->episode_len <= 0 || c->max_batch <= 0) {
+    mx_set_error("mx_qmix: non-positive dimension"); return 1;
+  }
+  if (c->act_dim > 32 || c->n_agents > 32) { mx_set_error("mx_qmix: act_dim and n_agents must be <= 32"); return 1; }
+  if (!c->vdn && c->hyper_layers != 1 && c->hyper_layers != 2) { mx_set_error("hypernet_layers must be 1 or 2"); return 1; }
+  return 0;
+}
+
+static void layouts(const mx_qmix_cfg* c, MxNetLayout* A, MxMixLayout* M, int64_t* P) {
+  mx_net_layout(c->obs_dim, c->act_dim, 0, A);
+  memset(M, 0, sizeof(*M));
+  M->size = 0;
+  if (!c->vdn) mx_mix_layout(c->state_dim, c->n_agents, c->mixer_hidden, c->hyper_hidden, c->hyper_layers, A->size, M);
+  *P = (int64_t)A->size + M->size;
+}
+
+extern "C" int mx_qmix_param_layout(const mx_qmix_cfg* c, mx_param_entry* out, int32_t max_entries, int64_t* total_floats) {
+  if (check_cfg(c)) return -1;
+  MxNetLayout A; MxMixLayout M; int64_t P;
+  layouts(c, &A, &M, &P);
+  std::vector<mx_param_entry> v;
+  auto add = [&](const char* name, int off, int rows, int cols) {
+    mx_param_entry e;
+    memset(&e, 0, sizeof(e));
+    snprintf(e.name, MX_MAX_NAME, "%s", name);
+    e.offset = off; e.rows = rows; e.cols = cols;
+    v.push_back(e);
+  };
+  const int H = MX_H, I = c->obs_dim, Aq = c->act_dim;
+  add("agent.rnn.feature_norm.weight", A.fn_g, I, 0); add("agent.rnn.feature_norm.bias", A.fn_b, I, 0);
+  add("agent.rnn.mlp.fc1.0.weight", A.w1, H, I); add("agent.rnn.mlp.fc1.0.bias", A.b1, H, 0);
+  add("agent.rnn.mlp.fc1.2.weight", A.ln1_g, H, 0); add("agent.rnn.mlp.fc1.2.bias", A.ln1_b, H, 0);
+  add("agent.rnn.mlp.fc_h.0.weight", A.wh, H, H); add("agent.rnn.mlp.fc_h.0.bias", A.bh, H, 0);
+  add("agent.rnn.mlp.fc_h.2.weight", A.lnh_g, H, 0); add("agent.rnn.mlp.fc_h.2.bias", A.lnh_b, H, 0);
+  add("agent.rnn.mlp.fc2.0.0.weight", A.w2, H, H); add("agent.rnn.mlp.fc2.0.0.bias", A.b2, H, 0);
+  add("agent.rnn.mlp.fc2.0.2.weight", A.ln2_g, H, 0); add("agent.rnn.mlp.fc2.0.2.bias", A.ln2_b, H, 0);
+  add("agent.rnn.rnn.rnn.weight_ih_l0", A.wih, 3 * H, H); add("agent.rnn.rnn.rnn.weight_hh_l0", A.whh, 3 * H, H);
+  add("agent.rnn.rnn.rnn.bias_ih_l0", A.bih, 3 * H, 0); add("agent.rnn.rnn.rnn.bias_hh_l0", A.bhh, 3 * H, 0);
+  add("agent.rnn.rnn.norm.weight", A.lno_g, H, 0); add("agent.rnn.rnn.norm.bias", A.lno_b, H, 0);
+  add("agent.q.action_out.weight", A.wq, Aq, H); add("agent.q.action_out.bias", A.bq, Aq, 0);
+  if (!c->vdn) {
+    const int S = c->state_dim, N = c->n_agents, ME = c->mixer_hidden, HY = c->hyper_hidden;
+    if (c->hyper_layers == 2) {
+      add("mixer.hyper_w1.0.weight", M.w1a, HY, S); add("mixer.hyper_w1.0.bias", M.b1a, HY, 0);
+      add("mixer.hyper_w1.2.weight", M.w1b, N * ME, HY); add("mixer.hyper_w1.2.bias", M.b1b, N * ME, 0);
+      add("mixer.hyper_w2.0.weight", M.w2a, HY, S); add("mixer.hyper_w2.0.bias", M.b2a, HY, 0);
+      add("mixer.hyper_w2.2.weight", M.w2b, ME, HY); add("mixer.hyper_w2.2.bias", M.b2b, ME, 0);
+    } else {
+      add("mixer.hyper_w1.weight", M.w1b, N * ME, S); add("mixer.hyper_w1.bias", M.b1b, N * ME, 0);
+      add("mixer.hyper_w2.weight", M.w2b, ME, S); add("mixer.hyper_w2.bias", M.b2b, ME, 0);
+    }
+    add("mixer.hyper_b1.weight", M.wb1, ME, S); add("mixer.hyper_b1.bias", M.bb1, ME, 0);
+    add("mixer.hyper_b2.0.weight", M.wb2a, HY, S); add("mixer.hyper_b2.0.bias", M.bb2a, HY, 0);
+    add("mixer.hyper_b2.2.weight", M.wb2b, 1, HY); add("mixer.hyper_b2.2.bias", M.bb2b, 1, 0);
+  }
+  if (total_floats) *total_floats = P;
+  const int n = (int)v.size();
+  if (out) for (int i = 0; i < n && i < max_entries; ++i) out[i] = v[i];
+  return n;
+}
+
+// =====================================================================================================
+// workspace
+// =====================================================================================================
+static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W) {
+  const int64_t B = c->max_batch, T = c->episode_len, N = c->n_agents;
+  const int64_t M = B * (T + 1) * N, E = B * T;
+  int64_t o = 0;
+  auto tk = [&](int64_t n) { int64_t r = o; o += (n + 63) / 64 * 64; return r; };
+  for (int k = 0; k < 2; ++k) { W->gi[k] = tk(M * MX_G); W->hall[k] = tk(M * MX_H); W->qall[k] = tk(M * c->act_dim); }
+  W->u1 = tk(M * MX_H); W->u2 = tk(M * MX_H);
+  W->st0 = tk(M * 2); W->st1 = tk(M * 2); W->st2 = tk(M * 2); W->sto = tk(M * 2);
+  W->gates = tk(M * MX_G); W->hn = tk(M * MX_H);
+  W->greedy = tk(M);
+  W->q_taken = tk(E * N); W->q_next = tk(E * N);
+  W->qtot = tk(E); W->qtot_next = tk(E); W->err = tk(E); W->huberp = tk(E);
+  W->dq_taken = tk(E * N);
+  W->dh_out = tk(M * MX_H);
+  W->dgi = tk(M * MX_G);
+  W->gpart = tk((int64_t)npart * P);
+  W->grad = tk(P + 8);
+  W->info = tk(8);
+  W->prio = tk(B);
+  W->spart = tk((int64_t)npart * 8);
+  W->adam_t = tk(8);
+  W->total = o;
+  return o * 4;
+}
+
+static int qmix_npart() { return mx_num_sms(); }
+
+extern "C" int64_t mx_qmix_workspace_bytes(const mx_qmix_cfg* c) {
+  if (check_cfg(c)) return -1;
+  MxNetLayout A; MxMixLayout M; int64_t P;
+  layouts(c, &A, &M, &P);
+  MxQmixWs W;
+  return ws_layout(c, P, qmix_npart(), &W);
+}
+
+extern "C" int mx_qmix_create(const mx_qmix_cfg* c, float* theta, float* theta_tgt, float* adam_m, float* adam_v, void* workspace,
+                              int64_t workspace_bytes, mx_qmix** out) {
+  if (check_cfg(c)) return 1;
+  if (!theta || !theta_tgt || !adam_m || !adam_v || !workspace || !out) { mx_set_error("mx_qmix_create: null buffer"); return 1; }
+  mx_qmix* q = new mx_qmix();
+  q->cfg = *c;
+  layouts(c, &q->agent, &q->mix, &q->P);
+  q->npart = qmix_npart();
+  const int64_t need = ws_layout(c, q->P, q->npart, &q->W);
+  if (workspace_bytes < need) { mx_set_error("mx_qmix_create: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need); delete q; return 1; }
+  q->theta = theta; q->theta_tgt = theta_tgt; q->adam_m = adam_m; q->adam_v = adam_v;
+  q->ws = (float*)workspace;
+  q->ws_bytes = workspace_bytes;
+  *out = q;
+  return 0;
+}
+extern "C" void mx_qmix_destroy(mx_qmix* q) { delete q; }
+
+extern "C" int mx_qmix_ws_lookup(const mx_qmix* q, const char* name, int64_t* byte_offset, int64_t* n_elems) {
+  const mx_qmix_cfg& c = q->cfg;
+  const int64_t B = c.max_batch, T = c.episode_len, N = c.n_agents;
+  const int64_t M = B * (T + 1) * N, E = B * T;
+  struct Ent { const char* n; int64_t off, cnt; };
+  const MxQmixWs& W = q->W;
+  const Ent tab[] = {
+      {"gi_live", W.gi[0], M * MX_G}, {"gi_tgt", W.gi[1], M * MX_G}, {"h_live", W.hall[0], M * MX_H}, {"h_tgt", W.hall[1], M * MX_H},
+      {"q_live", W.qall[0], M * c.act_dim}, {"q_tgt", W.qall[1], M * c.act_dim}, {"u1", W.u1, M * MX_H}, {"u2", W.u2, M * MX_H},
+      {"st0", W.st0, M * 2}, {"st1", W.st1, M * 2}, {"st2", W.st2, M * 2}, {"sto", W.sto, M * 2}, {"gates", W.gates, M * MX_G},
+      {"hn", W.hn, M * MX_H}, {"greedy", W.greedy, M}, {"q_taken", W.q_taken, E * N}, {"q_next", W.q_next, E * N}, {"qtot", W.qtot, E},
+      {"qtot_next", W.qtot_next, E}, {"err", W.err, E}, {"dq_taken", W.dq_taken, E * N}, {"dh_out", W.dh_out, M * MX_H},
+      {"dgi", W.dgi, M * MX_G}, {"grad", W.grad, q->P + 8}, {"info", W.info, 8}, {"prio", W.prio, B}, {"gpart", W.gpart, (int64_t)q->npart * q->P},
+  };
+  for (const Ent& e : tab)
+    if (!strcmp(e.n, name)) { *byte_offset = e.off * 4; *n_elems = e.cnt; return 0; }
+  mx_set_error("ws_lookup: unknown region '%s'", name);
+  return 1;
+}
+
+extern "C" float* mx_qmix_grad_buffer(mx_qmix* q, int64_t* n_floats) {
+  if (n_floats) *n_floats = q->P + 4;
+  return q->ws + q->W.grad;
+}
+extern "C" const float* mx_qmix_info(mx_qmix* q) { return q->ws + q->W.info; }
+extern "C" const float* mx_qmix_priorities(mx_qmix* q) { return q->ws + q->W.prio; }
+
+// =====================================================================================================
+// the step
+// =====================================================================================================
+static int check_batch(const mx_qmix* q, const mx_batch* b) {
+  const mx_qmix_cfg& c = q->cfg;
+  if (!b || b->B <= 0 || b->B > c.max_batch) { mx_set_error("qmix step: batch size outside [1, max_batch=%d]", c.max_batch); return 1; }
+  if (!b->obs || !b->share || !b->act_idx || !b->rewards || !b->dones_env) { mx_set_error("qmix step: missing batch field"); return 1; }
+  if (c.use_avail && !b->avail) { mx_set_error("qmix step: use_avail set but batch has no avail"); return 1; }
+  if (c.use_per && !b->weights) { mx_set_error("qmix step: use_per set but batch has no importance weights"); return 1; }
+  if (b->obs_ld < c.obs_dim || b->share_ld < c.state_dim) { mx_set_error("qmix step: batch strides smaller than dims"); return 1; }
+  return 0;
+}
+
+static OptimArgs optim_args(mx_qmix* q, int B, const int parts[3]) {
+  const mx_qmix_cfg& c = q->cfg;
+  OptimArgs o;
+  memset(&o, 0, sizeof(o));
+  float* ws = q->ws;
+  o.theta = q->theta; o.theta_tgt = q->theta_tgt; o.adam_m = q->adam_m; o.adam_v = q->adam_v;
+  o.gpart = ws + q->W.gpart; o.grad = ws + q->W.grad; o.P = q->P;
+  o.nseg = c.vdn ? 2 : 3;
+  o.seg_begin[0] = 0; o.seg_end[0] = q->agent.lno_g; o.seg_parts[0] = parts[0];
+  o.seg_begin[1] = q->agent.lno_g; o.seg_end[1] = q->agent.size; o.seg_parts[1] = parts[1];
+  o.seg_begin[2] = q->agent.size; o.seg_end[2] = (int)q->P; o.seg_parts[2] = parts[2];
+  o.spart = ws + q->W.spart; o.spart_n = parts[2];
+  o.info = ws + q->W.info;
+  o.adam_t = reinterpret_cast<double*>(ws + q->W.adam_t);
+  o.err = ws + q->W.err; o.B = B; o.T = c.episode_len;
+  o.per_nu = c.per_nu; o.per_eps = c.per_eps;
+  o.prio = c.use_per ? ws + q->W.prio : nullptr;
+  o.lr = c.lr; o.beta1 = c.adam_beta1; o.beta2 = c.adam_beta2; o.eps = c.adam_eps; o.max_grad_norm = c.max_grad_norm; o.tau = c.tau;
+  o.world_size = c.world_size;
+  return o;
+}
+
+extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream) {
+  if (check_batch(q, b)) return 1;
+  const mx_qmix_cfg& c = q->cfg;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* ws = q->ws;
+  const MxQmixWs& W = q->W;
+  const int B = b->B, T = c.episode_len, N = c.n_agents;
+  const int M = B * (T + 1) * N;
+
+  FrontFwdArgs ff;
+  memset(&ff, 0, sizeof(ff));
+  ff.X = b->obs; ff.ldx = b->obs_ld; ff.M = M; ff.feature_norm = 1;
+  ff.theta[0] = q->theta; ff.theta[1] = q->theta_tgt; ff.L = q->agent;
+  ff.gi[0] = ws + W.gi[0]; ff.gi[1] = ws + W.gi[1];
+  ff.u1 = ws + W.u1; ff.u2 = ws + W.u2; ff.st0 = ws + W.st0; ff.st1 = ws + W.st1; ff.st2 = ws + W.st2;
+  if (mx_launch_front_fwd(ff, 2, s)) return 1;
+
+  GruFwdArgs gf;
+  memset(&gf, 0, sizeof(gf));
+  gf.theta[0] = q->theta; gf.theta[1] = q->theta_tgt; gf.whh = q->agent.whh; gf.bhh = q->agent.bhh;
+  gf.gi[0] = ff.gi[0]; gf.gi[1] = ff.gi[1]; gf.hall[0] = ws + W.hall[0]; gf.hall[1] = ws + W.hall[1];
+  gf.gates = ws + W.gates; gf.hn = ws + W.hn; gf.R = B * N; gf.T = T; gf.N = N;
+  if (mx_launch_gru_fwd(gf, 2, s)) return 1;
+
+  QHeadArgs qh;
+  memset(&qh, 0, sizeof(qh));
+  qh.theta[0] = q->theta; qh.theta[1] = q->theta_tgt;
+  qh.wq = q->agent.wq; qh.bq = q->agent.bq; qh.lno_g = q->agent.lno_g; qh.lno_b = q->agent.lno_b;
+  qh.hall[0] = gf.hall[0]; qh.hall[1] = gf.hall[1]; qh.sto = ws + W.sto;
+  qh.act_idx = b->act_idx; qh.avail = c.use_avail ? b->avail : nullptr; qh.act_ld = b->act_ld;
+  qh.M = M; qh.T = T; qh.N = N; qh.A = c.act_dim; qh.double_q = c.double_q;
+  qh.q_taken = ws + W.q_taken; qh.q_next = ws + W.q_next;
+  qh.greedy = reinterpret_cast<int32_t*>(ws + W.greedy);
+  qh.qall0 = ws + W.qall[0]; qh.qall1 = ws + W.qall[1];
+  if (mx_launch_qhead(qh, s)) return 1;
+
+  int parts[3] = {0, 0, 0};
+  MixerArgs mx;
+  memset(&mx, 0, sizeof(mx));
+  mx.theta = q->theta; mx.theta_tgt = q->theta_tgt; mx.L = q->mix; mx.vdn = c.vdn;
+  mx.share = b->share; mx.share_ld = b->share_ld;
+  mx.q_taken = qh.q_taken; mx.q_next = qh.q_next;
+  mx.rewards = b->rewards; mx.dones_env = b->dones_env; mx.weights = c.use_per ? b->weights : nullptr;
+  mx.B = B; mx.T = T; mx.N = N; mx.gamma = c.gamma; mx.huber_delta = c.huber_delta; mx.use_huber = c.use_huber;
+  mx.qtot = ws + W.qtot; mx.qtot_next = ws + W.qtot_next; mx.err = ws + W.err; mx.dq_taken = ws + W.dq_taken;
+  mx.gpart = ws + W.gpart; mx.P = q->P; mx.spart = ws + W.spart;
+  if (mx_launch_mixer(mx, &parts[2], s)) return 1;
+
+  QHeadBwdArgs hb;
+  memset(&hb, 0, sizeof(hb));
+  hb.theta = q->theta; hb.wq = q->agent.wq; hb.bq = q->agent.bq; hb.lno_g = q->agent.lno_g; hb.lno_b = q->agent.lno_b;
+  hb.hall = gf.hall[0]; hb.sto = qh.sto; hb.act_idx = b->act_idx; hb.dq_taken = mx.dq_taken;
+  hb.M = M; hb.T = T; hb.N = N; hb.A = c.act_dim; hb.dh_out = ws + W.dh_out; hb.gpart = mx.gpart; hb.P = q->P;
+  if (mx_launch_qhead_bwd(hb, &parts[1], s)) return 1;
+
+  GruBwdArgs gb;
+  memset(&gb, 0, sizeof(gb));
+  gb.theta = q->theta; gb.whh = q->agent.whh; gb.hall = gf.hall[0]; gb.gates = gf.gates; gb.hn = gf.hn; gb.dh_out = hb.dh_out;
+  gb.dgi = ws + W.dgi; gb.R = B * N; gb.T = T; gb.N = N;
+  if (mx_launch_gru_bwd(gb, s)) return 1;
+
+  FrontBwdArgs fb;
+  memset(&fb, 0, sizeof(fb));
+  fb.X = b->obs; fb.ldx = b->obs_ld; fb.M = M; fb.T = T; fb.N = N; fb.feature_norm = 1;
+  fb.theta = q->theta; fb.L = q->agent; fb.u1 = ff.u1; fb.u2 = ff.u2; fb.st0 = ff.st0; fb.st1 = ff.st1; fb.st2 = ff.st2;
+  fb.dgi = gb.dgi; fb.gates = gf.gates; fb.hall = gf.hall[0]; fb.gpart = mx.gpart; fb.P = q->P;
+  if (mx_launch_front_bwd(fb, &parts[0], s)) return 1;
+
+  OptimArgs o = optim_args(q, B, parts);
+  return mx_launch_grad_reduce(o, s);
+}
+
+extern "C" int mx_qmix_apply(mx_qmix* q, void* stream) {
+  const int parts[3] = {0, 0, 0};
+  OptimArgs o = optim_args(q, q->cfg.max_batch, parts);
+  return mx_launch_adam(o, (cudaStream_t)stream);
+}
+
+extern "C" int mx_qmix_step(mx_qmix* q, const mx_batch* b, void* stream) {
+  if (mx_qmix_backward_only(q, b, stream)) return 1;
+  if (q->cfg.world_size > 1) return 0;   // caller all-reduces mx_qmix_grad_buffer(), then mx_qmix_apply()
+  return mx_qmix_apply(q, stream);
+}
+
+extern "C" int mx_qmix_soft_update(mx_qmix* q, void* stream) {
+  return mx_launch_polyak(q->theta_tgt, q->theta, q->P, q->cfg.tau, (cudaStream_t)stream);
+}
+extern "C" int mx_qmix_hard_update(mx_qmix* q, void* stream) {
+  cudaMemcpyAsync(q->theta_tgt, q->theta, (size_t)q->P * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  return 0;
+}
+
+// =====================================================================================================
+// whole-step CUDA graph
+// =====================================================================================================
+struct mx_graph {
+#if !MX_EMU
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+#endif
+  mx_replay* r;
+  mx_qmix* q;
+  int B;
+  double beta;
+  uint32_t flags;
+  int n_kernels;
+};
+
+static int run_sequence(mx_replay* r, mx_qmix* q, int B, double beta, uint32_t flags, void* stream) {
+  if (flags & 1u) { if (mx_replay_sample_uniform(r, B, stream)) return 1; }
+  else if (flags & 2u) { if (mx_replay_sample_per(r, B, beta, stream)) return 1; }
+  mx_batch b;
+  if (mx_replay_batch(r, B, &b)) return 1;
+  if (mx_qmix_step(q, &b, stream)) return 1;
+  if (flags & 8u) {
+    if (mx_replay_update_priorities(r, b.idx, mx_qmix_priorities(q), nullptr, nullptr, B, stream)) return 1;
+  }
+  if (flags & 4u) { if (mx_qmix_soft_update(q, stream)) return 1; }
+  return 0;
+}
+
+extern "C" int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta, uint32_t flags, void* stream, mx_graph** out) {
+  if (!r || !q || !out) { mx_set_error("mx_graph_capture: null argument"); return 1; }
+  mx_graph* g = new mx_graph();
+  g->r = r; g->q = q; g->B = B; g->beta = beta; g->flags = flags;
+#if !MX_EMU
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { mx_set_error("cudaStreamBeginCapture failed"); delete g; return 1; }
+  int rc = run_sequence(r, q, B, beta, flags, stream);
+  cudaError_t e = cudaStreamEndCapture(s, &g->graph);
+  if (rc || e != cudaSuccess) { mx_set_error("graph capture failed: %s", rc ? mx_last_error() : cudaGetErrorString(e)); delete g; return 1; }
+  if (cudaGraphInstantiate(&g->exec, g->graph, 0) != cudaSuccess) { mx_set_error("cudaGraphInstantiate failed"); delete g; return 1; }
+  size_t nn = 0;
+  cudaGraphGetNodes(g->graph, nullptr, &nn);
+  std::vector<cudaGraphNode_t> nodes(nn);
+  if (nn) cudaGraphGetNodes(g->graph, nodes.data(), &nn);
+  g->n_kernels = 0;
+  for (size_t i = 0; i < nn; ++i) {
+    cudaGraphNodeType ty;
+    if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) g->n_kernels++;
+  }
+#endif
+  *out = g;
+  return 0;
+}
+
+extern "C" int mx_graph_launch(mx_graph* g, void* stream) {
+#if !MX_EMU
+  if (cudaGraphLaunch(g->exec, (cudaStream_t)stream) != cudaSuccess) { mx_set_error("cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+  g_mx_launches += g->n_kernels;   // kernel nodes replayed by this launch
+  return 0;
+#else
+  return run_sequence(g->r, g->q, g->B, g->beta, g->flags, stream);
+#endif
+}
+
+extern "C" void mx_graph_destroy(mx_graph* g) {
+  if (!g) return;
+#if !MX_EMU
+  cudaGraphExecDestroy(g->exec);
+  cudaGraphDestroy(g->graph);
+#endif
+  delete g;
+}

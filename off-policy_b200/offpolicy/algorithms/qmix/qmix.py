@@ -1,0 +1,203 @@
+"""Drop-in `QMix` trainer (reference: offpolicy/algorithms/qmix/qmix.py) on the fused sm_100a learner.
+
+Same constructor and methods as the reference class -- `train_policy_on_batch`, `soft_target_updates`,
+`hard_target_updates`, `prep_training`, `prep_rollout`, attribute `mixer` -- so
+offpolicy/runner/rnn/base_runner.py:143,259-284,314,337 drives it unchanged.  One call of
+`train_policy_on_batch` = one `mx_qmix_step` (csrc/qmix.cu): live + target agent nets over the T+1 steps,
+mixers, TD target, masked MSE/Huber, BPTT, global-norm clip and Adam, all on the device.  Live/target
+parameters and Adam moments are four flat fp32 vectors; `policies[p].q_network` and `self.mixer` are named
+views of the live vector with the reference's state_dict keys.
+
+Data-parallel use (`torch.distributed` initialised, world size G > 1): each rank owns a replay shard and
+samples its own batch; the per-rank gradient NUMERATORS plus the loss denominators are summed with a
+single all-reduce of one flat buffer, after which every rank applies the identical clip + Adam update
+(the reference has no distributed path: utils/util.py:148-153 is dead code).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from offpolicy._b200 import capi
+from offpolicy._b200.flat import FlatModule, reference_style_init
+from offpolicy.algorithms.qmix.algorithm.QMixPolicy import qmix_cfg_struct, param_entries
+from offpolicy.utils.rec_buffer import SampledBatch, DeviceArray
+
+
+class _HostBatch(object):
+    """Device copy of a batch handed over in the reference's NumPy layout (rec_buffer.py:82): the compatibility
+    path for callers that sample elsewhere.  Layout conversion is torch plumbing, not a hot path."""
+
+    def __init__(self, cfg, dev):
+        self.cfg, self.dev = cfg, dev
+        B, T, N = cfg.max_batch, cfg.episode_len, cfg.n_agents
+        r4 = lambda v: (v + 3) // 4 * 4
+        self.obs_ld, self.share_ld, self.act_ld = r4(cfg.obs_dim), r4(cfg.state_dim), r4(cfg.act_dim)
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+        self.obs = z(B, T + 1, N, self.obs_ld)
+        self.share = z(B, T + 1, self.share_ld)
+        self.acts = z(B, T, N, self.act_ld)
+        self.act_idx = z(B, T, N, dt=torch.int32)
+        self.avail = z(B, T + 1, N, self.act_ld)
+        self.rew = z(B, T, N)
+        self.dones = z(B, T, N)
+        self.dones_env = z(B, T)
+        self.weights = z(B)
+
+    def pack(self, batch, p_id, use_avail, use_per):
+        obs, share, acts, rew, dones, dones_env, avail, weights, idx = batch
+        c, dev = self.cfg, self.dev
+        t = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32).to(dev)
+        o = t(obs[p_id])                                   # (N, T+1, B, O)
+        B = o.shape[2]
+        self.obs[:B, :, :, :c.obs_dim] = o.permute(2, 1, 0, 3)
+        self.share[:B, :, :c.state_dim] = t(share[p_id]).permute(1, 0, 2)
+        a = t(acts[p_id]).permute(2, 1, 0, 3)              # (B, T, N, A)
+        self.acts[:B, :, :, :c.act_dim] = a
+        self.act_idx[:B] = a.max(dim=-1)[1].to(torch.int32)
+        if use_avail:
+            self.avail[:B, :, :, :c.act_dim] = t(avail[p_id]).permute(2, 1, 0, 3)
+        self.rew[:B] = t(rew[p_id])[..., 0].permute(2, 1, 0)
+        self.dones[:B] = t(dones[p_id])[..., 0].permute(2, 1, 0)
+        self.dones_env[:B] = t(dones_env[p_id])[..., 0].permute(1, 0)
+        if use_per:
+            self.weights[:B] = t(weights)
+        b = capi.Batch()
+        b.B = B
+        b.obs_ld, b.share_ld, b.act_ld = self.obs_ld, self.share_ld, self.act_ld
+        b.obs, b.share, b.acts, b.act_idx = self.obs.data_ptr(), self.share.data_ptr(), self.acts.data_ptr(), self.act_idx.data_ptr()
+        b.avail = self.avail.data_ptr() if use_avail else None
+        b.rewards, b.dones, b.dones_env = self.rew.data_ptr(), self.dones.data_ptr(), self.dones_env.data_ptr()
+        b.weights = self.weights.data_ptr() if use_per else None
+        b.idx = None
+        return b
+
+
+class QMix(object):
+    def __init__(self, args, num_agents, policies, policy_mapping_fn, device=None, episode_length=None, vdn=False):
+        self.args = args
+        self.use_per = args.use_per
+        self.device = device
+        self.num_agents = num_agents
+        self.policies = policies
+        self.policy_mapping_fn = policy_mapping_fn
+        self.policy_ids = sorted(list(self.policies.keys()))
+        self.policy_agents = {p: sorted(a for a in range(num_agents) if policy_mapping_fn(a) == p) for p in self.policies}
+        if self.policy_ids != ["policy_0"]:
+            raise NotImplementedError("B200 QMIX path: only the shared-policy configuration ('policy_0') is implemented")
+        self.episode_length = args.episode_length if episode_length is None else episode_length
+        self.use_same_share_obs = getattr(args, "use_same_share_obs", True)
+        self.vdn = bool(vdn)
+        pol = self.policies["policy_0"]
+        self.use_avail = bool(getattr(args, "use_available_actions", True))
+        self.max_batch = int(getattr(args, "batch_size", 32))
+
+        lib = capi.lib()
+        self.dev = capi.device()
+        self.world_size = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        self.cfg = qmix_cfg_struct(args, num_agents, pol.obs_dim, pol.act_dim, pol.central_obs_dim, self.episode_length, self.max_batch,
+                                   vdn=self.vdn, use_avail=True, world_size=self.world_size)
+        entries, total = param_entries(self.cfg)
+        self.entries, self.P = entries, total
+        z = lambda: torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.theta, self.theta_tgt, self.adam_m, self.adam_v = z(), z(), z(), z()
+        # adopt the policy's agent weights, initialise the mixer like the reference, then re-bind the views
+        src = pol.q_network.state_dict()
+        pol.q_network.bind(self.theta)
+        pol.q_network.load_state_dict(src)
+        self.mixer = FlatModule(self.theta, entries, "mixer.")
+        if not self.vdn:
+            init = reference_style_init([e for e in entries if e[0].startswith("mixer.")],
+                                        dict(state_dim=pol.central_obs_dim, n_agents=num_agents, mixer_hidden=args.mixer_hidden_dim,
+                                             hyper_hidden=args.hypernet_hidden_dim, hidden=args.hidden_size, obs_dim=pol.obs_dim,
+                                             act_dim=pol.act_dim), gain=1.0, use_orthogonal=args.use_orthogonal,
+                                        hyper_layers=args.hypernet_layers)
+            self.mixer.load_state_dict({k[len("mixer."):]: v for k, v in init.items()})
+        self.theta_tgt.copy_(self.theta)                                               # qmix.py:63-64 (deepcopy)
+        self.target_q_network = FlatModule(self.theta_tgt, entries, "agent.")
+        self.target_mixer = FlatModule(self.theta_tgt, entries, "mixer.")
+        self.parameters = pol.q_network.parameters() + self.mixer.parameters()          # qmix.py:66-70 (order kept)
+
+        nbytes = int(lib.mx_qmix_workspace_bytes(C.byref(self.cfg)))
+        if nbytes < 0:
+            raise capi.MxError(lib.mx_last_error().decode())
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
+        h = C.c_void_p()
+        capi.check(lib.mx_qmix_create(C.byref(self.cfg), capi.ptr(self.theta), capi.ptr(self.theta_tgt), capi.ptr(self.adam_m),
+                                      capi.ptr(self.adam_v), capi.ptr(self.workspace), nbytes, C.byref(h)))
+        self.handle = h
+        self._host_batch = None
+        self._info = self.ws_view("info")
+        n = C.c_int64()
+        gptr = lib.mx_qmix_grad_buffer(self.handle, C.byref(n))
+        off = gptr - self.workspace.data_ptr()
+        self._grad_buf = self.workspace[off:off + 4 * int(n.value)].view(torch.float32)
+        if getattr(args, "use_double_q", True):
+            print("double Q learning will be used")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                capi.lib().mx_qmix_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- introspection used by the parity tests ------------------------------------------------------------
+    def ws_view(self, name, dtype=torch.float32):
+        off, n = C.c_int64(), C.c_int64()
+        capi.check(capi.lib().mx_qmix_ws_lookup(self.handle, name.encode(), C.byref(off), C.byref(n)))
+        return self.workspace[off.value:off.value + 4 * n.value].view(dtype)
+
+    def grad_views(self):
+        """Unclipped mean gradients d(loss)/d(param) by reference name (numerators / sum(1-bad))."""
+        g = self.ws_view("grad")
+        denom = g[self.P]
+        out = {}
+        for name, off, rows, cols in self.entries:
+            n = rows * (cols if cols else 1)
+            v = g[off:off + n] / denom
+            out[name] = v.view(rows, cols) if cols else v
+        return out
+
+    # -- the update ----------------------------------------------------------------------------------------------
+    def _device_batch(self, batch):
+        if isinstance(batch, SampledBatch):
+            buf = batch.buffers["policy_0"]
+            if buf.sample_serial != batch.serial["policy_0"]:
+                raise RuntimeError("stale sample: the buffer has been sampled again since this batch was drawn")
+            return buf.batch_struct(batch.B)
+        if self._host_batch is None:
+            self._host_batch = _HostBatch(self.cfg, self.dev)
+        avail = batch[6]["policy_0"] if batch[6] is not None else None
+        if avail is None:
+            raise NotImplementedError("B200 QMIX path: batches without avail_acts must come from the B200 replay buffer")
+        return self._host_batch.pack(batch, "policy_0", True, self.use_per)
+
+    def train_policy_on_batch(self, batch, update_policy_id=None):
+        lib = capi.lib()
+        b = self._device_batch(batch)
+        stream = capi.stream_ptr()
+        if self.world_size > 1:
+            capi.check(lib.mx_qmix_backward_only(self.handle, C.byref(b), stream))
+            torch.distributed.all_reduce(self._grad_buf)
+            capi.check(lib.mx_qmix_apply(self.handle, stream))
+        else:
+            capi.check(lib.mx_qmix_step(self.handle, C.byref(b), stream))
+        info = self._info
+        train_info = {"loss": info[0], "grad_norm": info[1], "Q_tot": info[2]}          # qmix.py:195-198 (0-dim device tensors)
+        new_priorities = DeviceArray(self.ws_view("prio")[:b.B]) if self.use_per else None
+        return train_info, new_priorities, batch[8]
+
+    def hard_target_updates(self):
+        print("hard update targets")
+        capi.check(capi.lib().mx_qmix_hard_update(self.handle, capi.stream_ptr()))
+
+    def soft_target_updates(self):
+        capi.check(capi.lib().mx_qmix_soft_update(self.handle, capi.stream_ptr()))
+
+    def prep_training(self):
+        pass            # no dropout / batch-norm in these nets: train()/eval() are numerical no-ops (qmix.py:218-232)
+
+    def prep_rollout(self):
+        pass

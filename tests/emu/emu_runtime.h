@@ -119,7 +119,7 @@ inline unsigned ballot(int pred) {
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __syncthreads() emu::syncthreads()
 #define __syncwarp(...) emu::warp_barrier()
 #define __threadfence() ((void)0)

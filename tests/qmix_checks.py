@@ -1,0 +1,161 @@
+"""QMIX learner parity checks shared by the emulated (CPU) and real (GPU) test modules.
+
+Tolerances (north_star: "within 1e-4 rel on fp32 losses/grads"): scalars 1e-4 relative; every gradient tensor
+max-abs error <= 1e-4 x max-abs of the reference tensor (+1e-7 abs); parameters after Adam: the UPDATE
+(new - old) within 5e-3 x lr per element (Adam normalises the step to ~lr; for near-zero gradients the step is
+lr*g/eps, i.e. an ABSOLUTE gradient error of 1e-8 already moves the step by 1e-3 x lr -- the reference run with a
+different thread count shows the same spread); Polyak targets 1e-6.
+"""
+import types
+
+import numpy as np
+import torch
+
+from helpers import load_golden, golden_cfg, oracle_from_golden, golden_batch, sub, rel_err
+from replay_checks import Discrete
+
+
+def make_args(cfg, B, **over):
+    a = types.SimpleNamespace(
+        hidden_size=cfg.hidden, layer_N=1, use_ReLU=True, use_feature_normalization=True, use_orthogonal=True, gain=cfg.gain,
+        use_conv1d=False, stacked_frames=1, use_rnn_layer=True, recurrent_N=1, prev_act_inp=False, use_double_q=cfg.double_q,
+        hypernet_layers=cfg.hyper_layers, mixer_hidden_dim=cfg.mixer_hidden, hypernet_hidden_dim=cfg.hyper_hidden, gamma=cfg.gamma,
+        use_per=cfg.use_per, per_nu=cfg.per_nu, per_eps=cfg.per_eps, per_alpha=0.6, use_huber_loss=cfg.huber,
+        huber_delta=cfg.huber_delta, max_grad_norm=cfg.max_grad_norm, lr=cfg.lr, opti_eps=cfg.opti_eps, weight_decay=0, tau=cfg.tau,
+        use_popart=False, use_value_active_masks=False, use_same_share_obs=True, batch_size=B, episode_length=0,
+        epsilon_start=1.0, epsilon_finish=0.05, epsilon_anneal_time=50000, use_available_actions=True)
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+def build_trainer(cfg, B, T, vdn=False, **over):
+    from offpolicy.algorithms.qmix.algorithm.QMixPolicy import QMixPolicy
+    from offpolicy.algorithms.qmix.qmix import QMix
+    from offpolicy._b200 import capi
+    args = make_args(cfg, B, **over)
+    info = dict(obs_space=[cfg.obs_dim], share_obs_space=[cfg.state_dim], act_space=Discrete(cfg.act_dim),
+                cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
+    pol = QMixPolicy({"args": args, "device": capi.device()}, info)
+    tr = QMix(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=capi.device(), episode_length=T, vdn=vdn)
+    return args, pol, tr
+
+
+def load_state(pol, tr, agent_sd, mixer_sd, tgt_agent_sd, tgt_mixer_sd):
+    pol.q_network.load_state_dict(agent_sd)
+    tr.target_q_network.load_state_dict(tgt_agent_sd)
+    if mixer_sd is not None:
+        tr.mixer.load_state_dict(mixer_sd)
+        tr.target_mixer.load_state_dict(tgt_mixer_sd)
+
+
+def ref_tuple(b):
+    d = lambda x: {"policy_0": x}
+    return tuple(d(x) for x in b[:7]) + (b[7], b[8])
+
+
+def to_rows(x, N, B):
+    """oracle (T+1, N*B, D) with row = n*B + b  ->  ours [M][D] with m = (b*(T+1)+t)*N + n"""
+    T1, _, D = x.shape
+    return x.reshape(T1, N, B, D).permute(2, 0, 1, 3).reshape(-1, D)
+
+
+def close(a, b, rtol, atol=1e-7):
+    a = np.asarray(torch.as_tensor(a).detach().cpu(), dtype=np.float64)
+    b = np.asarray(torch.as_tensor(b).detach().cpu(), dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = np.abs(a - b).max()
+    lim = rtol * np.abs(b).max() + atol
+    return err <= lim, err, lim
+
+
+def check_forward_intermediates(tr, L, batch, cfg, B, T):
+    """Localise a kernel bug: every materialised activation vs the oracle's cell-by-cell trace."""
+    from oracle.qmix import agent_trace
+    N = cfg.n_agents
+    M = B * (T + 1) * N
+    E = B * T
+    x = L.stack_agents(batch[0])
+    bad = []
+
+    def cmp(name, ours, want, rtol=2e-5):
+        ok, err, lim = close(ours, want, rtol, 1e-6)
+        if not ok:
+            bad.append("%s: err %.3e > %.3e" % (name, err, lim))
+
+    for tag, net in (("live", L.agent), ("tgt", L.tgt_agent)):
+        trc = agent_trace(net, x)
+        cmp("gi_" + tag, tr.ws_view("gi_" + tag)[:M * 192].view(M, 192), to_rows(trc["gi"], N, B))
+        cmp("h_" + tag, tr.ws_view("h_" + tag)[:M * 64].view(M, 64), to_rows(trc["h"], N, B))
+        cmp("q_" + tag, tr.ws_view("q_" + tag)[:M * cfg.act_dim].view(M, cfg.act_dim), to_rows(trc["q"], N, B), 1e-4)
+        if tag == "live":
+            cmp("u1", tr.ws_view("u1")[:M * 64].view(M, 64), to_rows(trc["u1"], N, B))
+            cmp("u2", tr.ws_view("u2")[:M * 64].view(M, 64), to_rows(trc["u2"], N, B))
+            g = tr.ws_view("gates")[:M * 192].view(M, 192)
+            cmp("r", g[:, :64], to_rows(trc["r"], N, B))
+            cmp("z", g[:, 64:128], to_rows(trc["z"], N, B))
+            cmp("n", g[:, 128:], to_rows(trc["n"], N, B))
+            cmp("hn", tr.ws_view("hn")[:M * 64].view(M, 64), to_rows(trc["hn"], N, B))
+    loss, prio, aux = L.loss_terms(batch)
+    tb = lambda v: v.permute(1, 0, 2).reshape(E, -1)            # oracle (T,B,k) -> ours [b*T+t][k]
+    cmp("q_taken", tr.ws_view("q_taken")[:E * N].view(E, N), tb(aux["q_taken"].detach()), 1e-4)
+    cmp("q_next", tr.ws_view("q_next")[:E * N].view(E, N), tb(aux["tq_next"]), 1e-4)
+    cmp("qtot", tr.ws_view("qtot")[:E].view(E, 1), tb(aux["q_tot"].detach()), 1e-4)
+    cmp("qtot_next", tr.ws_view("qtot_next")[:E].view(E, 1), tb(aux["q_tot_next"]), 1e-4)
+    cmp("err", tr.ws_view("err")[:E].view(E, 1), tb(aux["err"].detach()), 1e-4)
+    return bad
+
+
+def check_step_against(g_or_none, name=None, intermediates=True):
+    g = load_golden(name)
+    L, cfg, B, T, steps = oracle_from_golden(g)
+    args, pol, tr = build_trainer(cfg, B, T)
+    load_state(pol, tr, sub(g, "init.agent."), sub(g, "init.mixer."), sub(g, "init.tgt_agent."), sub(g, "init.tgt_mixer."))
+    problems = []
+    for s in range(steps):
+        batch = golden_batch(g, s)
+        prev = {k: v.clone() for k, v in list(pol.q_network.state_dict().items())}
+        prev_m = {k: v.clone() for k, v in list(tr.mixer.state_dict().items())}
+        info, prio, idx = tr.train_policy_on_batch(ref_tuple(batch))
+        if intermediates and s == 0:
+            problems += check_forward_intermediates(tr, L, batch, cfg, B, T)
+        for key, want in (("loss", g["s%d.loss" % s]), ("grad_norm", g["s%d.grad_norm" % s]), ("Q_tot", g["s%d.Q_tot" % s])):
+            e = rel_err(info[key].cpu(), want)
+            if e > 1e-4:
+                problems.append("step %d %s: rel err %.3e (got %r want %r)" % (s, key, e, float(info[key]), float(want)))
+        if cfg.use_per:
+            ok, err, lim = close(np.asarray(prio), g["s%d.prio" % s], 1e-4)
+            if not ok:
+                problems.append("step %d priorities err %.3e" % (s, err))
+        # gradients: golden holds clipped grads
+        gn = float(g["s%d.grad_norm" % s])
+        coef = min(1.0, cfg.max_grad_norm / (gn + 1e-6))
+        gv = tr.grad_views()
+        for full, ours in gv.items():
+            role, pname = full.split(".", 1)
+            key = "s%d.grad.%s.%s" % (s, role, pname)
+            if key not in g:
+                if float(ours.abs().max()) != 0.0:
+                    problems.append("step %d grad %s should be zero (unused parameter)" % (s, full))
+                continue
+            ok, err, lim = close(ours * coef, g[key], 1e-4)
+            if not ok:
+                problems.append("step %d grad %s: err %.3e > %.3e" % (s, full, err, lim))
+        tr.soft_target_updates()
+        for role, mod, prv in (("agent", pol.q_network, prev), ("mixer", tr.mixer, prev_m)):
+            for k, v in mod.state_dict().items():
+                want = g["s%d.%s.%s" % (s, role, k)]
+                d_ours = (v.cpu() - prv[k].cpu()).numpy()
+                d_want = want - prv[k].cpu().numpy()
+                err = np.abs(d_ours - d_want).max()
+                if err > 5e-3 * cfg.lr + 1e-9:
+                    problems.append("step %d param %s.%s: update err %.3e" % (s, role, k, err))
+        for role, mod in (("tgt_agent", tr.target_q_network), ("tgt_mixer", tr.target_mixer)):
+            for k, v in mod.state_dict().items():
+                ok, err, lim = close(v, g["s%d.%s.%s" % (s, role, k)], 1e-6, 1e-7)
+                if not ok:
+                    problems.append("step %d %s.%s: err %.3e" % (s, role, k, err))
+        # keep the oracle in lock-step for the next step's intermediates
+        L.step(batch)
+        L.soft_update()
+    assert not problems, "\n".join(problems[:40])
