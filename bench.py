@@ -1,0 +1,390 @@
+"""Learner grad-steps/s of the recurrent QMIX update path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one process per GPU; torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+One "step" = sample(B) -> train_policy_on_batch -> soft_target_updates (base_runner.py:259-284) on synthetic
+SMAC-shaped replay data.  Prints ONE JSON line (rank 0).
+  value    : steps/s with everything resident in HBM -- the whole step (device MT19937 draw, gather, fused learner,
+             Adam, Polyak) replayed from one CUDA graph; CUDA-event timed, max over ranks.
+  e2e      : same metric through the drop-in Python API with HOST inputs: every step inserts one freshly collected
+             episode from pinned host memory (H2D), draws indices on the host with np.random.choice (H2D), trains,
+             soft-updates and reads loss/grad_norm/Q_tot back (D2H) -- the runner's per-step sequence.
+  roofline : dominant kernel of the step (per-kernel CUDA-event timing on the launch stream).
+  cpu_baseline : the oracle port of the reference learner timed on the host cores (bounded sample).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "off-policy_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_agents, obs, act, state, T, B, per)    -- BASELINE.json configs
+    "qmix_3m": (3, 30, 9, 48, 60, 32, False),          # configs[1]: the configuration the metric is quoted on
+    "qmix_8m_per": (8, 80, 14, 168, 120, 64, True),    # configs[3]
+    "qmix_2s3z": (5, 80, 11, 120, 120, 32, False),     # configs[4]
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tflops=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tflops=1590.0, tflops_sustained=1400.0, src="fallback")
+
+
+def make_cfg(w):
+    from oracle.qmix import QmixConfig
+    n, o, a, s, T, B, per = WORKLOADS[w]
+    return QmixConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, use_per=per, gain=1.0), T, B
+
+
+def synth_episodes(cfg, T, n, rs):
+    N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    f = [rs.standard_normal((T + 1, n, N, O), dtype=np.float32), np.repeat(rs.standard_normal((T + 1, n, 1, S), dtype=np.float32), N, 2),
+         np.eye(A, dtype=np.float32)[rs.integers(0, A, (T, n, N))], np.repeat(rs.standard_normal((T, n, 1, 1), dtype=np.float32), N, 2),
+         np.zeros((T, n, N, 1), np.float32), np.zeros((T, n, 1), np.float32), np.ones((T + 1, n, N, A), np.float32)]
+    return f
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.samples, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 6 and s[2 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(self.samples))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference learner on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_learner_steps_per_s(cfg, T, B, E, steps, warmup, threads):
+    from oracle.qmix import QmixLearner
+    from oracle.replay import UniformReplay, PrioritizedReplay
+    torch.set_num_threads(threads)
+    rs = np.random.default_rng(0)
+    N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    buf = (PrioritizedReplay(0.6, E, T, N, O, S, A) if cfg.use_per else UniformReplay(E, T, N, O, S, A))
+    for c in range(0, E, 64):
+        n = min(64, E - c)
+        buf.insert(n, *synth_episodes(cfg, T, n, rs))
+    torch.manual_seed(1)
+    np.random.seed(1)
+    L = QmixLearner(cfg, seed=1)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        if cfg.use_per:
+            out, inds = buf.sample(B, 0.4)
+        else:
+            out, inds = buf.sample(B)
+        info, prio, _ = L.step(out)
+        if cfg.use_per:
+            buf.update_priorities(inds, prio)
+        L.soft_update()
+        float(info["loss"])
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return 1.0 / float(np.median(times)), float(np.median(times)) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, T, B = make_cfg(args.workload)
+    cores = os.cpu_count() or 1
+    E = min(args.buffer, 1024)
+    sps, ms = cpu_learner_steps_per_s(cfg, T, B, E, args.steps, args.warmup, cores)
+    line = dict(metric="learner grad-steps/sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=cfg.n_agents, obs_dim=cfg.obs_dim, act_dim=cfg.act_dim,
+                            state_dim=cfg.state_dim, buffer_episodes=E),
+                cpu_baseline=dict(value=sps, unit="steps/s", cores=cores, kind="port",
+                                  sample="%d timed learner steps (sample+train+soft update) of the same workload, replay of %d episodes" % (args.steps, E)),
+                e2e=dict(value=sps, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# algorithmic work per kernel (DESIGN.md "roofline"), H=64
+# ---------------------------------------------------------------------------------------------------------
+def kernel_work(cfg, T, B, P):
+    N, O, A, S, H, ME, HY = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, 64, cfg.mixer_hidden, cfg.hyper_hidden
+    M, E = B * (T + 1) * N, B * T
+    mix = (S * HY + HY * N * ME) + (S * HY + HY * ME) + S * ME + (S * HY + HY) + N * ME + ME
+    fl = {
+        "k_front_fwd": 2 * 2.0 * M * (O * H + H * H + 3 * H * H),
+        "k_gru_fwd": 2 * 2.0 * M * 3 * H * H,
+        "k_qhead": 2 * 2.0 * M * H * A,
+        "k_mixer": 2.0 * E * mix * 4,                    # target fwd + live fwd + live bwd (dgrad + wgrad)
+        "k_qhead_bwd": 2.0 * M * 3 * H,
+        "k_gru_bwd": 2.0 * M * 3 * H * H,
+        "k_front_bwd": 2.0 * M * (2 * 3 * H * H * 2 + 3 * H * H + 2 * H * H + H * H + 2 * O * H + O * H) / 1.0,
+    }
+    fields = 4.0 * B * (N * (T + 1) * O + (T + 1) * S + N * T * A + N * (T + 1) * A + 3 * N * T + T)
+    by = {"k_gather": 2 * fields, "k_adam": 4.0 * P * 7, "k_polyak": 4.0 * P * 3, "k_grad_reduce": 4.0 * P * 2}
+    return fl, by
+
+
+def run_engine(args):
+    from offpolicy._b200 import capi
+    import qmix_checks as qc
+    import replay_checks as rc
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = capi.lib()
+    dev = capi.device()
+    cfg, T, B = make_cfg(args.workload)
+    N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    E = args.buffer // world if world > 1 else args.buffer            # replay sharded by episode across ranks
+    rs = np.random.default_rng(rank)
+    buf = rc.make_buffers(N, O, A, S, T, E, per_alpha=0.6 if cfg.use_per else None, rng="device", max_batch=max(B, 128))
+    for c in range(0, E, 128):
+        n = min(128, E - c)
+        buf.insert(n, *[rc.d(x) for x in synth_episodes(cfg, T, n, rs)])
+    torch.manual_seed(1)
+    np.random.seed(1)
+    args_ns, pol, tr = qc.build_trainer(cfg, B, T)
+    pb = buf.policy_buffers["policy_0"]
+    buf.seed_device_rng(1 + rank)
+    stream = torch.cuda.current_stream()
+    sp = capi.stream_ptr
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident loop ----------------
+    flags = (2 if cfg.use_per else 1) | 4 | (8 if cfg.use_per else 0)
+    graph = None
+    tgraph = None
+    if world == 1:
+        g = C.c_void_p()
+        capi.check(lib.mx_graph_capture(pb.handle, tr.handle, B, 0.4, flags, sp(), C.byref(g)))
+        graph = g
+        kernels_per_step = int(lib.mx_graph_num_kernels(g))
+
+        def step():
+            capi.check(lib.mx_graph_launch(graph, sp()))
+    else:
+        def eager():
+            if cfg.use_per:
+                smp = buf.sample(B, 0.4, "policy_0")
+            else:
+                smp = buf.sample(B)
+            info, prio, idx = tr.train_policy_on_batch(smp)
+            if cfg.use_per:
+                buf.update_priorities(idx, prio, "policy_0")
+            tr.soft_target_updates()
+        for _ in range(3):
+            eager()
+        torch.cuda.synchronize()
+        c0 = lib.mx_launch_count()
+        eager()
+        kernels_per_step = int(lib.mx_launch_count() - c0)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(side):
+                eager()
+                tgraph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(tgraph, stream=side):
+                    eager()
+            torch.cuda.current_stream().wait_stream(side)
+            step = tgraph.replay
+        except Exception as ex:       # NCCL capture unavailable: stay eager
+            sys.stderr.write("graph capture of the data-parallel step failed (%s); running eager\n" % ex)
+            tgraph = None
+            step = eager
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = lib.mx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms_total, op=torch.distributed.ReduceOp.MAX)
+    ms_step = float(ms_total) / args.steps
+    launches = int(lib.mx_launch_count() - launches0)
+    if tgraph is not None:
+        launches = kernels_per_step * args.steps
+
+    # ---------------- e2e: host inputs through the drop-in API ----------------
+    buf.rng = "numpy"
+    fresh = [synth_episodes(cfg, T, 1, rs) for _ in range(8)]
+    h2d = sum(x.nbytes for x in fresh[0]) + B * 8
+    d2h = 12 + (B * 4 if cfg.use_per else 0)
+
+    def e2e_step(i):
+        buf.insert(1, *[rc.d(x) for x in fresh[i % 8]])
+        if cfg.use_per:
+            smp = buf.sample(B, 0.4, "policy_0")
+        else:
+            smp = buf.sample(B)
+        info, prio, idx = tr.train_policy_on_batch(smp)
+        if cfg.use_per:
+            buf.update_priorities(idx, prio, "policy_0")
+        tr.soft_target_updates()
+        return float(info["loss"]), float(info["grad_norm"]), float(info["Q_tot"])     # D2H read of the step's result
+
+    for i in range(5):
+        e2e_step(i)
+    barrier()
+    n_e2e = max(20, min(args.steps, 200))
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        e2e_step(i)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
+    e2e_sps = world * n_e2e / float(e2e_s)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---------------- per-kernel timing (rank 0; eager, CUDA events on the launch stream) ----------------
+    buf.rng = "device"
+    kern = {}
+    reps = 10
+    for rep in range(reps + 2):
+        lib.mx_profile_begin(sp())
+        if cfg.use_per:
+            smp = buf.sample(B, 0.4, "policy_0")
+        else:
+            smp = buf.sample(B)
+        info, prio, idx = tr.train_policy_on_batch(smp)
+        if cfg.use_per:
+            buf.update_priorities(idx, prio, "policy_0")
+        tr.soft_target_updates()
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        n = lib.mx_profile_end(sp(), names, 4096, ms, 64)
+        if rep >= 2:
+            for nm, t in zip(names.value.decode().split(";"), list(ms)[:n]):
+                kern.setdefault(nm, []).append(t)
+    kavg = {k: float(np.mean(v)) for k, v in kern.items()}
+    ksum = sum(kavg.values())
+    fl, by = kernel_work(cfg, T, B, tr.P)
+    top = max(kavg, key=kavg.get)
+    pk = peaks()
+    if top in fl:
+        ach = fl[top] / (kavg[top] * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel=top, achieved=ach, peak=pk["tflops_sustained"], unit="TFLOP/s", frac=ach / pk["tflops_sustained"],
+                    traffic=None, peak_source=pk["src"] + " bf16 sustained (kernel timed inside the step)",
+                    note="FP32 FFMA kernel (1e-4 parity budget); serial-recurrence / latency bound at these sizes, see DESIGN.md")
+    else:
+        ach = by.get(top, 0.0) / (kavg[top] * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel=top, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=None, peak_source=pk["src"])
+    gather_gbs = by["k_gather"] / (kavg.get("k_gather", 1e9) * 1e-3) / 1e9
+    breakdown = {k: dict(ms=round(v, 5), share=round(v / ksum, 4)) for k, v in sorted(kavg.items(), key=lambda kv: -kv[1])}
+
+    # ---------------- CPU baseline (bounded sample) ----------------
+    cores = os.cpu_count() or 1
+    Ecpu = min(args.buffer, 1024)
+    n_cpu = 12 if args.workload == "qmix_3m" else 4
+    sps_all, ms_all = cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, cores)
+    sps_one, ms_one = cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, 1)
+    best = max(sps_all, sps_one)
+
+    value = world * 1000.0 / ms_step
+    line = dict(
+        metric="learner grad-steps/sec", value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=args.workload, batch_per_gpu=B, episode_len=T, n_agents=N, obs_dim=O, act_dim=A, state_dim=S,
+                    buffer_episodes_per_gpu=E, parallelism="dp%d" % world if world > 1 else "single",
+                    value_definition="batch-%d grad-steps/s summed over ranks (each rank samples its own shard; one flat all-reduce)" % B,
+                    l2="inputs gathered from a replay larger than L2 (%.0f MB); the per-step working set is L2-resident by design" %
+                       (pb.L.total_bytes / 1e6),
+                    step="CUDA graph: device MT19937 draw + gather + fused QMIX learner + Adam + Polyak" if (graph or tgraph) else "eager"),
+        e2e=dict(value=e2e_sps, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=n_e2e,
+                 path="RecReplayBuffer.insert(1 episode, pinned) + sample(np.random.choice) + QMix.train_policy_on_batch + soft_target_updates + D2H info"),
+        gpu_launches=launches, kernels_per_step=kernels_per_step,
+        roofline=roof, kernels=breakdown, gather_gbs=gather_gbs,
+        cpu_baseline=dict(value=best, unit="steps/s", cores=cores if sps_all >= sps_one else 1, kind="port",
+                          all_cores_steps_per_s=sps_all, one_thread_steps_per_s=sps_one,
+                          sample="%d timed steps (sample+train+soft update) of the same workload on a %d-episode replay, oracle port of the reference learner" % (n_cpu, Ecpu)),
+        clocks=clocks.summary())
+    print(json.dumps(line))
+    if graph is not None:
+        lib.mx_graph_destroy(graph)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="qmix_3m", choices=sorted(WORKLOADS))
+    ap.add_argument("--buffer", type=int, default=5000, help="replay episodes (scripts/train_smac_qmix.sh default 5000)")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_engine(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -205,6 +205,14 @@ void mx_graph_destroy(mx_graph* g);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches counter) */
 int64_t mx_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline: between begin and end every launch of this library on
+ * `stream` is bracketed by CUDA events.  mx_profile_end synchronises the stream and returns the number of
+ * launches; names are written ';'-separated into names_buf, durations in milliseconds into ms[]. */
+int mx_profile_begin(void* stream);
+int mx_profile_end(void* stream, char* names_buf, int32_t buf_len, float* ms, int32_t max_n);
+/* number of kernel nodes one mx_graph_launch replays */
+int32_t mx_graph_num_kernels(const mx_graph* g);
+
 #ifdef __cplusplus
 }
 #endif

@@ -367,6 +367,7 @@ int mx_launch_qhead_bwd(const QHeadBwdArgs& a, int* nparts_used, cudaStream_t s)
   if (grid < 1) grid = 1;
   MX_LAUNCH(k_qhead_bwd, dim3(grid), dim3(256), 0, s, a);
   MX_COUNT();
+  MX_MARK("k_qhead_bwd", s);
   *nparts_used = grid;
   return MX_CHECK_LAUNCH("qhead_bwd");
 }
@@ -380,6 +381,7 @@ int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
   else if (rpc == 2) MX_LAUNCH(k_gru_bwd<2>, grid, dim3(MX_G), 0, s, a);
   else MX_LAUNCH(k_gru_bwd<4>, grid, dim3(MX_G), 0, s, a);
   MX_COUNT();
+  MX_MARK("k_gru_bwd", s);
   return MX_CHECK_LAUNCH("gru_bwd");
 }
 
@@ -398,6 +400,7 @@ int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s)
 #endif
   MX_LAUNCH(kern, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
   MX_COUNT();
+  MX_MARK("k_front_bwd", s);
   *nparts_used = grid;
   return MX_CHECK_LAUNCH("front_bwd");
 }

@@ -304,6 +304,7 @@ int mx_launch_front_fwd(const FrontFwdArgs& a, int nets, cudaStream_t s) {
 #endif
   MX_LAUNCH(kern, dim3(gx, nets), dim3(MX_TILE_THREADS), smem, s, a);
   MX_COUNT();
+  MX_MARK("k_front_fwd", s);
   return MX_CHECK_LAUNCH("front_fwd");
 }
 
@@ -316,6 +317,7 @@ int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s) {
   else if (rpc == 2) MX_LAUNCH(k_gru_fwd<2>, grid, dim3(MX_G), 0, s, a);
   else MX_LAUNCH(k_gru_fwd<4>, grid, dim3(MX_G), 0, s, a);
   MX_COUNT();
+  MX_MARK("k_gru_fwd", s);
   return MX_CHECK_LAUNCH("gru_fwd");
 }
 
@@ -326,5 +328,6 @@ int mx_launch_qhead(const QHeadArgs& a, cudaStream_t s) {
   if (grid > cap) grid = cap;
   MX_LAUNCH(k_qhead, dim3(grid), dim3(256), 0, s, a);
   MX_COUNT();
+  MX_MARK("k_qhead", s);
   return MX_CHECK_LAUNCH("qhead");
 }

@@ -19,6 +19,55 @@ extern "C" int mx_abi_version(void) { return MX_ABI_VERSION; }
 extern "C" int mx_is_cuda_build(void) { return MX_EMU ? 0 : 1; }
 extern "C" int64_t mx_launch_count(void) { return g_mx_launches; }
 
+int g_mx_prof_on = 0;
+#if MX_EMU
+void mx_prof_mark(const char*, cudaStream_t) {}
+extern "C" int mx_profile_begin(void*) { return 0; }
+extern "C" int mx_profile_end(void*, char*, int32_t, float*, int32_t) { return 0; }
+#else
+#include <string>
+#include <vector>
+static std::vector<std::pair<std::string, cudaEvent_t>> g_marks;
+static cudaEvent_t g_prof_start;
+void mx_prof_mark(const char* name, cudaStream_t s) {
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  g_marks.emplace_back(name, e);
+}
+extern "C" int mx_profile_begin(void* stream) {
+  for (auto& m : g_marks) cudaEventDestroy(m.second);
+  g_marks.clear();
+  cudaEventCreate(&g_prof_start);
+  cudaEventRecord(g_prof_start, (cudaStream_t)stream);
+  g_mx_prof_on = 1;
+  return 0;
+}
+extern "C" int mx_profile_end(void* stream, char* names_buf, int32_t buf_len, float* ms, int32_t max_n) {
+  g_mx_prof_on = 0;
+  cudaStreamSynchronize((cudaStream_t)stream);
+  std::string names;
+  cudaEvent_t prev = g_prof_start;
+  int n = 0;
+  for (auto& m : g_marks) {
+    if (n < max_n) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, prev, m.second);
+      ms[n] = t;
+      if (n) names += ";";
+      names += m.first;
+      ++n;
+    }
+    prev = m.second;
+  }
+  if (names_buf && buf_len > 0) snprintf(names_buf, buf_len, "%s", names.c_str());
+  for (auto& m : g_marks) cudaEventDestroy(m.second);
+  g_marks.clear();
+  cudaEventDestroy(g_prof_start);
+  return n;
+}
+#endif
+
 #if !MX_EMU
 int mx_num_sms() {
   static int sms = 0;

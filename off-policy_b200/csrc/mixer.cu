@@ -366,6 +366,7 @@ int mx_launch_mixer(const MixerArgs& a, int* nparts_used, cudaStream_t s) {
     if (grid > sms) grid = sms;
     MX_LAUNCH(k_vdn_mix, dim3(grid), dim3(256), 0, s, a);
     MX_COUNT();
+    MX_MARK("k_vdn_mix", s);
     *nparts_used = grid;
     return MX_CHECK_LAUNCH("vdn_mix");
   }
@@ -385,6 +386,7 @@ int mx_launch_mixer(const MixerArgs& a, int* nparts_used, cudaStream_t s) {
   if (RM == 1) MX_LAUNCH(k_mixer<1>, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
   else MX_LAUNCH(k_mixer<2>, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
   MX_COUNT();
+  MX_MARK("k_mixer", s);
   *nparts_used = grid;
   return MX_CHECK_LAUNCH("mixer");
 }

@@ -7,7 +7,10 @@
 
 void mx_set_error(const char* fmt, ...);
 extern long long g_mx_launches;
+extern int g_mx_prof_on;
+void mx_prof_mark(const char* name, cudaStream_t s);
 #define MX_COUNT() (++g_mx_launches)
+#define MX_MARK(name, s) do { if (g_mx_prof_on) mx_prof_mark((name), (s)); } while (0)
 
 #if MX_EMU
 static inline int mx_num_sms() { return 4; }

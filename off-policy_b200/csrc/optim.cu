@@ -120,6 +120,7 @@ int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s) {
   const int grid = (int)((a.P + 255) / 256) + 1;
   MX_LAUNCH(k_grad_reduce, dim3(grid), dim3(256), 0, s, a);
   MX_COUNT();
+  MX_MARK("k_grad_reduce", s);
   return MX_CHECK_LAUNCH("grad_reduce");
 }
 int mx_launch_adam(const OptimArgs& a, cudaStream_t s) {
@@ -128,6 +129,7 @@ int mx_launch_adam(const OptimArgs& a, cudaStream_t s) {
   if (grid > sms) grid = sms;
   MX_LAUNCH(k_adam, dim3(grid), dim3(256), 0, s, a);
   MX_COUNT();
+  MX_MARK("k_adam", s);
   return MX_CHECK_LAUNCH("adam");
 }
 int mx_launch_polyak(float* tgt, const float* src, long long n, float tau, cudaStream_t s) {
@@ -138,5 +140,6 @@ int mx_launch_polyak(float* tgt, const float* src, long long n, float tau, cudaS
   if (grid < 1) grid = 1;
   MX_LAUNCH(k_polyak, dim3(grid), dim3(256), 0, s, tgt, src, n4, tau);
   MX_COUNT();
+  MX_MARK("k_polyak", s);
   return MX_CHECK_LAUNCH("polyak");
 }

@@ -317,6 +317,7 @@ extern "C" int mx_qmix_soft_update(mx_qmix* q, void* stream) {
 }
 extern "C" int mx_qmix_hard_update(mx_qmix* q, void* stream) {
   cudaMemcpyAsync(q->theta_tgt, q->theta, (size_t)q->P * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  MX_MARK("hard_update_memcpy", (cudaStream_t)stream);
   return 0;
 }
 
@@ -383,6 +384,8 @@ extern "C" int mx_graph_launch(mx_graph* g, void* stream) {
   return run_sequence(g->r, g->q, g->B, g->beta, g->flags, stream);
 #endif
 }
+
+extern "C" int32_t mx_graph_num_kernels(const mx_graph* g) { return g ? g->n_kernels : 0; }
 
 extern "C" void mx_graph_destroy(mx_graph* g) {
   if (!g) return;

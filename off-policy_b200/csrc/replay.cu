@@ -523,6 +523,7 @@ extern "C" int mx_replay_insert_async(mx_replay* r, const mx_episodes* ep, int32
   if (grid < 1) grid = 1;
   MX_LAUNCH(k_insert_scatter, dim3(grid), dim3(256), 0, s, a);
   MX_COUNT();
+  MX_MARK("k_insert_scatter", s);
   if (c.use_per) {
     TreeUpd u;
     memset(&u, 0, sizeof(u));
@@ -532,6 +533,7 @@ extern "C" int mx_replay_insert_async(mx_replay* r, const mx_episodes* ep, int32
     int th = mx_round_up(n_ep, 32);
     MX_LAUNCH(k_tree_update, dim3(1), dim3(th), 0, s, u);
     MX_COUNT();
+    MX_MARK("k_tree_update", s);
   }
   if (first_slot_out) *first_slot_out = first;
   r->cursor = a.new_cursor;
@@ -573,8 +575,10 @@ static int launch_gather(mx_replay* r, const int64_t* idx_dev, int B, cudaStream
     MX_LAUNCH(k_reward_stats, dim3(g), dim3(256), 0, s, cat<float>(r, L.off_rew), cat<float>(r, L.off_dones_env), (long long)L.ep_rew,
               (long long)L.ep_dones_env, c.episode_len, c.n_agents, cat<MxReplayState>(r, L.off_state), rs);
     MX_COUNT();
+    MX_MARK("k_reward_stats", s);
     MX_LAUNCH(k_reward_stats_fin, dim3(1), dim3(32), 0, s, rs, at<MxReplayState>(r, L.off_state));
     MX_COUNT();
+    MX_MARK("k_reward_stats_fin", s);
   }
   GatherArgs g;
   memset(&g, 0, sizeof(g));
@@ -612,6 +616,7 @@ static int launch_gather(mx_replay* r, const int64_t* idx_dev, int B, cudaStream
   else if (grid > sms) grid = grid / sms * sms;
   MX_LAUNCH(k_gather, dim3(grid), dim3(256), 0, s, g);
   MX_COUNT();
+  MX_MARK("k_gather", s);
   return MX_CHECK_LAUNCH("gather");
 }
 
@@ -632,6 +637,7 @@ extern "C" int mx_replay_sample_uniform(mx_replay* r, int32_t B, void* stream) {
   d.idx_out = at<long long>(r, r->L.off_b_idx);
   MX_LAUNCH(k_draw, dim3(1), dim3(256), 0, s, d);
   MX_COUNT();
+  MX_MARK("k_draw", s);
   return launch_gather(r, at<int64_t>(r, r->L.off_b_idx), B, s);
 }
 
@@ -662,6 +668,7 @@ extern "C" int mx_replay_sample_per(mx_replay* r, int32_t B, double beta, void* 
   d.w32_out = at<float>(r, r->L.off_b_wf32);
   MX_LAUNCH(k_draw, dim3(1), dim3(256), 0, s, d);
   MX_COUNT();
+  MX_MARK("k_draw", s);
   return launch_gather(r, at<int64_t>(r, r->L.off_b_idx), B, s);
 }
 
@@ -679,6 +686,7 @@ extern "C" int mx_replay_update_priorities(mx_replay* r, const int64_t* idx_dev,
   u.state = at<MxReplayState>(r, r->L.off_state); u.update_max = 1;
   MX_LAUNCH(k_tree_update, dim3(1), dim3(mx_round_up(B, 32)), 0, s, u);
   MX_COUNT();
+  MX_MARK("k_tree_update", s);
   return MX_CHECK_LAUNCH("tree_update");
 }
 

@@ -100,6 +100,9 @@ def _declare(lib):
         "mx_graph_capture": (C.c_int, [vp, vp, i32, dbl, u32, vp, C.POINTER(vp)]),
         "mx_graph_launch": (C.c_int, [vp, vp]),
         "mx_graph_destroy": (None, [vp]),
+        "mx_graph_num_kernels": (i32, [vp]),
+        "mx_profile_begin": (C.c_int, [vp]),
+        "mx_profile_end": (C.c_int, [vp, C.c_char_p, i32, C.POINTER(C.c_float), i32]),
     }
     missing = []
     for name, (res, args) in sig.items():

@@ -1,0 +1,200 @@
+"""QMIX learner parity on the real sm_100a kernels through the C-ABI: reference goldens, the oracle at the
+BASELINE.json sizes, CUDA-graph replay, and size-independent properties."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import qmix_checks as qc
+import replay_checks as rc
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+GOLDENS = ["qmix_small", "qmix_small_huber_nodq", "qmix_small_per", "qmix_small_hyper1", "qmix_5ag"]
+
+
+@pytest.mark.parametrize("name", GOLDENS)
+def test_step_matches_reference_golden(gpu_engine, name):
+    qc.check_step_against(None, name)
+
+
+def _oracle_and_trainer(cfg, B, T, seed=3, vdn=False, **over):
+    from oracle.qmix import QmixLearner, randomize_all
+    L = QmixLearner(cfg, seed=seed)
+    randomize_all(L.agent, 1)
+    if not vdn:
+        randomize_all(L.mixer, 2)
+    L.sync_targets()
+    randomize_all(L.tgt_agent, 3, 0.05)
+    if not vdn:
+        randomize_all(L.tgt_mixer, 4, 0.05)
+    args, pol, tr = qc.build_trainer(cfg, B, T, vdn=vdn, **over)
+    qc.load_state(pol, tr, L.agent.state_dict(), None if vdn else L.mixer.state_dict(), L.tgt_agent.state_dict(),
+                  None if vdn else L.tgt_mixer.state_dict())
+    return L, args, pol, tr
+
+
+def _compare_step(L, pol, tr, batch, cfg, steps=1, tol=1e-4):
+    for s in range(steps):
+        info, prio, _ = tr.train_policy_on_batch(qc.ref_tuple(batch))
+        gv = {k: v.clone() for k, v in tr.grad_views().items()}
+        tr.soft_target_updates()
+        ref, rprio, _ = L.step(batch)
+        coef = min(1.0, cfg.max_grad_norm / (float(ref["grad_norm"]) + 1e-6))
+        L.soft_update()
+        for k in ("loss", "grad_norm", "Q_tot"):
+            assert rel_err(info[k].cpu(), ref[k]) < tol, (s, k, float(info[k]), float(ref[k]))
+        if rprio is not None:
+            assert rel_err(np.asarray(prio), rprio) < tol
+        named = dict(("agent." + k, p) for k, p in L.agent.named_parameters())
+        if not cfg.vdn:
+            named.update(("mixer." + k, p) for k, p in L.mixer.named_parameters())
+        for k, p in named.items():
+            if p.grad is None:
+                assert float(gv[k].abs().max()) == 0.0
+                continue
+            ok, err, lim = qc.close(gv[k] * coef, p.grad, tol)
+            assert ok, (s, k, err, lim)
+        for k, v in pol.q_network.state_dict().items():
+            assert float((v.cpu() - L.agent.state_dict()[k]).abs().max()) <= 5e-3 * cfg.lr * (s + 1) + 1e-7, (s, k)
+        for k, v in tr.target_q_network.state_dict().items():
+            assert float((v.cpu() - L.tgt_agent.state_dict()[k]).abs().max()) <= 1e-6, (s, k)
+
+
+def test_config2_3m_full_size_vs_oracle(gpu_engine):
+    """BASELINE config 2: QMIX 3m shapes, B=32, T=60 -- three consecutive steps (Adam state, Polyak)."""
+    from oracle.qmix import QmixConfig, synth_batch
+    torch.set_num_threads(8)
+    cfg = QmixConfig(gain=1.0)
+    L, args, pol, tr = _oracle_and_trainer(cfg, 32, 60)
+    batch = synth_batch(cfg, 32, 60, seed=5, avail_p=0.8, var_len=True) + (None, None)
+    _compare_step(L, pol, tr, batch, cfg, steps=3)
+
+
+def test_config4_8m_per_full_size_vs_oracle(gpu_engine):
+    """BASELINE config 4: 8 agents, obs 80, A=14, S=168, T=120, B=64 with PER weights and priorities."""
+    from oracle.qmix import QmixConfig, synth_batch
+    torch.set_num_threads(8)
+    cfg = QmixConfig(n_agents=8, obs_dim=80, act_dim=14, state_dim=168, use_per=True)
+    L, args, pol, tr = _oracle_and_trainer(cfg, 64, 120)
+    w = (np.random.RandomState(2).rand(64) * 0.9 + 0.1)
+    batch = synth_batch(cfg, 64, 120, seed=6, avail_p=0.8, var_len=True) + (w, np.arange(64))
+    _compare_step(L, pol, tr, batch, cfg, steps=1)
+
+
+def test_config5_2s3z_vs_oracle(gpu_engine):
+    from oracle.qmix import QmixConfig, synth_batch
+    torch.set_num_threads(8)
+    cfg = QmixConfig(n_agents=5, obs_dim=80, act_dim=11, state_dim=120)
+    L, args, pol, tr = _oracle_and_trainer(cfg, 32, 120)
+    batch = synth_batch(cfg, 32, 120, seed=7, avail_p=0.8, var_len=False) + (None, None)
+    _compare_step(L, pol, tr, batch, cfg, steps=1)
+
+
+def test_vdn_vs_oracle(gpu_engine):
+    """VDN = sum mixer (reference is shape-broken, App. D-1: pinned against the oracle's intent restatement)."""
+    from oracle.qmix import QmixConfig, synth_batch
+    cfg = QmixConfig(vdn=True)
+    L, args, pol, tr = _oracle_and_trainer(cfg, 8, 20, vdn=True)
+    batch = synth_batch(cfg, 8, 20, seed=8, avail_p=0.7, var_len=True) + (None, None)
+    _compare_step(L, pol, tr, batch, cfg, steps=2)
+
+
+def _filled_buffer(cfg, T, E, B, per=False, seed=0):
+    rs = np.random.RandomState(seed)
+    N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    buf = rc.make_buffers(N, O, A, S, T, E, per_alpha=0.6 if per else None, rng="device", max_batch=max(B, 64))
+    for c in range(0, E, 64):
+        n = min(64, E - c)
+        ep = [rs.randn(T + 1, n, N, O), np.repeat(rs.randn(T + 1, n, 1, S), N, 2), np.eye(A)[rs.randint(0, A, (T, n, N))],
+              np.repeat(rs.randn(T, n, 1, 1), N, 2), np.zeros((T, n, N, 1)), np.zeros((T, n, 1)), np.ones((T + 1, n, N, A))]
+        buf.insert(n, *[rc.d(x.astype(np.float32)) for x in ep])
+    return buf
+
+
+def test_sample_train_end_to_end_and_graph_replay(gpu_engine):
+    """sample (device MT19937) -> train -> soft update through the drop-in classes equals the oracle fed with the same
+    indices; then the same sequence replayed from ONE captured CUDA graph gives the same parameters."""
+    from oracle.qmix import QmixConfig
+    capi = gpu_engine
+    lib = capi.lib()
+    cfg = QmixConfig(gain=1.0)
+    B, T, E = 32, 60, 256
+    results = []
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        buf = _filled_buffer(cfg, T, E, B)
+        L, args, pol, tr = _oracle_and_trainer(cfg, B, T)
+        buf.seed_device_rng(123)
+        np.random.seed(123)
+        pb = buf.policy_buffers["policy_0"]
+        if mode == "eager":
+            for s in range(4):
+                smp = buf.sample(B)
+                idx = np.asarray(pb.sampled_indices(B))
+                assert np.array_equal(idx, np.random.choice(E, B))
+                info, _, _ = tr.train_policy_on_batch(smp)
+                tr.soft_target_updates()
+                host = tuple(smp[i]["policy_0"] for i in range(7)) + (None, None)
+                ref, _, _ = L.step(host)
+                L.soft_update()
+                assert rel_err(info["loss"].cpu(), ref["loss"]) < 1e-4
+                assert rel_err(info["grad_norm"].cpu(), ref["grad_norm"]) < 1e-4
+        else:
+            g = C.c_void_p()
+            capi.check(lib.mx_graph_capture(pb.handle, tr.handle, B, 0.0, 1 | 4, capi.stream_ptr(), C.byref(g)))
+            assert lib.mx_graph_num_kernels(g) >= 10
+            for s in range(4):
+                capi.check(lib.mx_graph_launch(g, capi.stream_ptr()))
+            torch.cuda.synchronize()
+            lib.mx_graph_destroy(g)
+        results.append((tr.theta.clone(), tr.theta_tgt.clone(), tr.adam_m.clone()))
+    # same kernels, same order; shared-memory float atomics inside two kernels make the last bits scheduling-dependent
+    for a, b in zip(results[0], results[1]):
+        assert float((a - b).abs().max()) <= 1e-6 * float(a.abs().max()) + 1e-7
+
+
+def test_size_independent_properties_full_size(gpu_engine):
+    """At config-2 size: (1) permuting the episodes of a batch leaves loss / grad_norm unchanged (summation order only);
+    (2) soft update with tau=1 equals a hard update; (3) hard update is idempotent; (4) lr=0 leaves parameters bit-identical."""
+    from oracle.qmix import QmixConfig, synth_batch
+    cfg = QmixConfig(gain=1.0)
+    B, T = 32, 60
+    batch = synth_batch(cfg, B, T, seed=21, avail_p=0.8, var_len=True)
+    perm = np.random.RandomState(0).permutation(B)
+    pbatch = tuple(x[..., perm, :] if x.ndim == 4 else x[:, perm] for x in batch)
+    outs = []
+    for bt in (batch, pbatch):
+        L, args, pol, tr = _oracle_and_trainer(cfg, B, T)
+        info, _, _ = tr.train_policy_on_batch(qc.ref_tuple(bt + (None, None)))
+        outs.append((float(info["loss"]), float(info["grad_norm"]), float(info["Q_tot"])))
+    for a, b in zip(*outs):
+        assert abs(a - b) <= 2e-5 * abs(a)
+    L, args, pol, tr = _oracle_and_trainer(cfg, B, T, tau=1.0)
+    tr.soft_target_updates()
+    assert torch.equal(tr.theta, tr.theta_tgt)
+    tr.hard_target_updates()
+    tr.hard_target_updates()
+    assert torch.equal(tr.theta, tr.theta_tgt)
+    L, args, pol, tr = _oracle_and_trainer(cfg, B, T, lr=0.0)
+    before = tr.theta.clone()
+    tr.train_policy_on_batch(qc.ref_tuple(batch + (None, None)))
+    assert torch.equal(before, tr.theta)
+
+
+def test_error_behaviour(gpu_engine):
+    """Errors surface as exceptions like the reference's asserts (rec_buffer.py:287-289; qmix needs H=64)."""
+    from oracle.qmix import QmixConfig
+    from offpolicy._b200.capi import MxError
+    cfg = QmixConfig()
+    buf = _filled_buffer(cfg, 4, 8, 4, per=True)
+    with pytest.raises(AssertionError):
+        buf.sample(8, 0.4, "policy_0")          # len(self) > batch_size
+    with pytest.raises(AssertionError):
+        buf.sample(4, 0.0, "policy_0")          # beta > 0
+    with pytest.raises(AssertionError):
+        buf.update_priorities(np.array([0, 1]), np.array([1.0, -1.0], np.float32), "policy_0")
+    with pytest.raises(MxError):
+        qc.build_trainer(QmixConfig(hidden=128), 4, 4)
