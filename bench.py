@@ -99,6 +99,20 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference learner on the host cores
 # ---------------------------------------------------------------------------------------------------------
+def best_cpu_threads(cfg, T, B, E):
+    """The reference sets torch.set_num_threads(n_training_threads); on a many-core host more threads are SLOWER for
+    these tiny ops, so the baseline uses the fastest of a few thread counts (probed with 3 timed steps each)."""
+    cores = os.cpu_count() or 1
+    best, best_sps = 1, 0.0
+    for th in sorted({1, 4, 8, 16, min(32, cores)}):
+        if th > cores:
+            continue
+        sps, _ = cpu_learner_steps_per_s(cfg, T, B, E, 3, 1, th)
+        if sps > best_sps:
+            best, best_sps = th, sps
+    return best
+
+
 def cpu_learner_steps_per_s(cfg, T, B, E, steps, warmup, threads):
     from oracle.qmix import QmixLearner
     from oracle.replay import UniformReplay, PrioritizedReplay
@@ -134,14 +148,14 @@ def run_reference(args):
     if rank != 0:
         return
     cfg, T, B = make_cfg(args.workload)
-    cores = os.cpu_count() or 1
     E = min(args.buffer, 1024)
+    cores = best_cpu_threads(cfg, T, B, E)
     sps, ms = cpu_learner_steps_per_s(cfg, T, B, E, args.steps, args.warmup, cores)
     line = dict(metric="learner grad-steps/sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=cfg.n_agents, obs_dim=cfg.obs_dim, act_dim=cfg.act_dim,
                             state_dim=cfg.state_dim, buffer_episodes=E),
-                cpu_baseline=dict(value=sps, unit="steps/s", cores=cores, kind="port",
+                cpu_baseline=dict(value=sps, unit="steps/s", cores=cores, host_cores=os.cpu_count(), kind="port",
                                   sample="%d timed learner steps (sample+train+soft update) of the same workload, replay of %d episodes" % (args.steps, E)),
                 e2e=dict(value=sps, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -205,17 +219,16 @@ def run_engine(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident loop ----------------
-    flags = (2 if cfg.use_per else 1) | 4 | (8 if cfg.use_per else 0)
     graph = None
     tgraph = None
+    run_stream = torch.cuda.current_stream()
     if world == 1:
-        g = C.c_void_p()
-        capi.check(lib.mx_graph_capture(pb.handle, tr.handle, B, 0.4, flags, sp(), C.byref(g)))
-        graph = g
-        kernels_per_step = int(lib.mx_graph_num_kernels(g))
-
-        def step():
-            capi.check(lib.mx_graph_launch(graph, sp()))
+        from offpolicy._b200.graph import StepGraph
+        torch.cuda.synchronize()
+        graph = StepGraph(buf, tr, B, beta=0.4)
+        kernels_per_step = graph.num_kernels
+        run_stream = graph.stream
+        step = graph.launch
     else:
         def eager():
             if cfg.use_per:
@@ -253,10 +266,10 @@ def run_engine(args):
     launches0 = lib.mx_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        e0.record()
+        e0.record(run_stream)
         for _ in range(args.steps):
             step()
-        e1.record()
+        e1.record(run_stream)
         barrier()
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -339,11 +352,11 @@ def run_engine(args):
     breakdown = {k: dict(ms=round(v, 5), share=round(v / ksum, 4)) for k, v in sorted(kavg.items(), key=lambda kv: -kv[1])}
 
     # ---------------- CPU baseline (bounded sample) ----------------
-    cores = os.cpu_count() or 1
     Ecpu = min(args.buffer, 1024)
-    n_cpu = 12 if args.workload == "qmix_3m" else 4
+    n_cpu = 20 if args.workload == "qmix_3m" else 5
+    cores = best_cpu_threads(cfg, T, B, Ecpu)
     sps_all, ms_all = cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, cores)
-    sps_one, ms_one = cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, 1)
+    sps_one, ms_one = (sps_all, ms_all) if cores == 1 else cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, 1)
     best = max(sps_all, sps_one)
 
     value = world * 1000.0 / ms_step
@@ -360,13 +373,13 @@ def run_engine(args):
                  path="RecReplayBuffer.insert(1 episode, pinned) + sample(np.random.choice) + QMix.train_policy_on_batch + soft_target_updates + D2H info"),
         gpu_launches=launches, kernels_per_step=kernels_per_step,
         roofline=roof, kernels=breakdown, gather_gbs=gather_gbs,
-        cpu_baseline=dict(value=best, unit="steps/s", cores=cores if sps_all >= sps_one else 1, kind="port",
-                          all_cores_steps_per_s=sps_all, one_thread_steps_per_s=sps_one,
+        cpu_baseline=dict(value=best, unit="steps/s", cores=cores if sps_all >= sps_one else 1, host_cores=os.cpu_count(), kind="port",
+                          best_threads_steps_per_s=sps_all, one_thread_steps_per_s=sps_one,
                           sample="%d timed steps (sample+train+soft update) of the same workload on a %d-episode replay, oracle port of the reference learner" % (n_cpu, Ecpu)),
         clocks=clocks.summary())
     print(json.dumps(line))
     if graph is not None:
-        lib.mx_graph_destroy(graph)
+        graph.close()
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -356,7 +356,18 @@ extern "C" int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta
   g->r = r; g->q = q; g->B = B; g->beta = beta; g->flags = flags;
 #if !MX_EMU
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { mx_set_error("cudaStreamBeginCapture failed"); delete g; return 1; }
+  if (!s) { mx_set_error("mx_graph_capture: needs a non-default stream (the legacy stream cannot be captured)"); delete g; return 1; }
+  {
+    cudaError_t be = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    if (be != cudaSuccess) {
+      mx_set_error("cudaStreamBeginCapture failed: %s", cudaGetErrorString(be));
+      cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) { cudaGraph_t tmp = nullptr; cudaStreamEndCapture(s, &tmp); if (tmp) cudaGraphDestroy(tmp); }
+      cudaGetLastError();
+      delete g;
+      return 1;
+    }
+  }
   int rc = run_sequence(r, q, B, beta, flags, stream);
   cudaError_t e = cudaStreamEndCapture(s, &g->graph);
   if (rc || e != cudaSuccess) { mx_set_error("graph capture failed: %s", rc ? mx_last_error() : cudaGetErrorString(e)); delete g; return 1; }

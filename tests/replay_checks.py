@@ -69,9 +69,11 @@ def check_device_rng_stream(seed=321, E=37, B=16, rounds=45):
     rs = np.random.RandomState(0)
     ep = lambda n: [d(rs.randn(T + 1, n, N, O)), d(rs.randn(T + 1, n, N, S)), d(np.eye(A)[rs.randint(0, A, (T, n, N))]),
                     d(rs.randn(T, n, N, 1)), d(np.zeros((T, n, N, 1))), d(np.zeros((T, n, 1))), d(np.ones((T + 1, n, N, A)))]
-    for _ in range(3):
-        buf.insert(B, *ep(B))
-    buf.insert(5, *ep(5))
+    left = E
+    while left > 0:
+        n = min(B, left)
+        buf.insert(n, *ep(n))
+        left -= n
     assert len(buf) == E
     buf.seed_device_rng(seed)
     np.random.seed(seed)

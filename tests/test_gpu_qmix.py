@@ -143,13 +143,14 @@ def test_sample_train_end_to_end_and_graph_replay(gpu_engine):
                 assert rel_err(info["loss"].cpu(), ref["loss"]) < 1e-4
                 assert rel_err(info["grad_norm"].cpu(), ref["grad_norm"]) < 1e-4
         else:
-            g = C.c_void_p()
-            capi.check(lib.mx_graph_capture(pb.handle, tr.handle, B, 0.0, 1 | 4, capi.stream_ptr(), C.byref(g)))
-            assert lib.mx_graph_num_kernels(g) >= 10
-            for s in range(4):
-                capi.check(lib.mx_graph_launch(g, capi.stream_ptr()))
+            from offpolicy._b200.graph import StepGraph
             torch.cuda.synchronize()
-            lib.mx_graph_destroy(g)
+            g = StepGraph(buf, tr, B)
+            assert g.num_kernels >= 10
+            for s in range(4):
+                g.launch()
+            g.synchronize()
+            g.close()
         results.append((tr.theta.clone(), tr.theta_tgt.clone(), tr.adam_m.clone()))
     # same kernels, same order; shared-memory float atomics inside two kernels make the last bits scheduling-dependent
     for a, b in zip(results[0], results[1]):
