@@ -179,6 +179,13 @@ int mx_replay_batch(const mx_replay* r, int32_t B, mx_batch* out);   /* view of 
  * step stops after producing the flat gradient-numerator buffer; the caller all-reduces
  * mx_qmix_grad_buffer() (sum) and calls mx_qmix_apply(). */
 int mx_qmix_step(mx_qmix* q, const mx_batch* batch, void* stream);
+/* flags: MX_STEP_FUSE_SOFT_UPDATE -> the Adam kernel's epilogue also applies the Polyak target update
+ * (= train_policy_on_batch immediately followed by soft_target_updates, base_runner.py:272-280, one launch fewer). */
+#define MX_STEP_FUSE_SOFT_UPDATE 1u
+int mx_qmix_step_ex(mx_qmix* q, const mx_batch* batch, uint32_t flags, void* stream);
+int mx_qmix_apply_ex(mx_qmix* q, uint32_t flags, void* stream);
+/* parity/debug: also materialise per-action Q values ("q_live"/"q_tgt") and greedy actions in the workspace */
+int mx_qmix_set_debug(mx_qmix* q, int32_t on);
 int mx_qmix_backward_only(mx_qmix* q, const mx_batch* batch, void* stream);  /* everything up to the reduced grads */
 int mx_qmix_apply(mx_qmix* q, void* stream);                                 /* norm + clip + Adam + info scalars   */
 /* flat fp32 buffer to all-reduce: [grad numerators (P) | sum(1-bad) | loss numerator | sum Q_tot(1-bad) | elements ] */

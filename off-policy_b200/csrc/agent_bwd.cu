@@ -71,6 +71,9 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
 // =====================================================================================================
 template <int RPC>
 __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
+  // Operands of step t (r, z, n, hn, h_{t-1}, dL/dh_t: six 64-float rows per sequence row) are prefetched two steps
+  // ahead with cp.async into a 3-slot shared-memory ring, so no global latency sits on the serial chain.
+  __shared__ __align__(16) float ops_s[3][RPC][6][MX_H];
   __shared__ __align__(16) float dgh_s[RPC][MX_G];
   __shared__ float part_s[RPC][3][MX_H];
   const int j = threadIdx.x;
@@ -80,10 +83,33 @@ __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
 #pragma unroll
   for (int jj = 0; jj < MX_H; ++jj) wT[jj] = a.theta[a.whh + (p * MX_H + jj) * MX_H + k];
   const int T1 = a.T + 1, N = a.N;
-  // the gate phase is done by threads idx < RPC*64 (strided); each owns dh_carry for its (row, i) pairs
-  float carry[(RPC * MX_H + MX_G - 1) / MX_G];
+
+  auto prefetch = [&](int t) {
+    if (t >= 0) {
+      for (int c = j; c < RPC * 6 * 16; c += MX_G) {            // 16-byte pieces: RPC rows x 6 operands x 16
+        const int r = c / 96, rem = c % 96, op = rem / 16, q4 = rem % 16;
+        const int row = row0 + r;
+        float* dst = &ops_s[t % 3][r][op][4 * q4];
+        if (row < a.R) {
+          const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
+          const float* src;
+          if (op < 3) src = a.gates + mm * MX_G + op * MX_H;
+          else if (op == 3) src = a.hn + mm * MX_H;
+          else if (op == 4) src = t > 0 ? a.hall + (mm - N) * MX_H : nullptr;
+          else src = a.dh_out + mm * MX_H;
+          if (src) mx_cp16(dst, src + 4 * q4);
+          else mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
+          mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+    }
+    mx_cp_commit();
+  };
+
+  float carry[RPC];
 #pragma unroll
-  for (int c = 0; c < (RPC * MX_H + MX_G - 1) / MX_G; ++c) carry[c] = 0.f;
+  for (int r = 0; r < RPC; ++r) carry[r] = 0.f;
   // zero the t == T rows of dgi
   for (int idx = j; idx < RPC * MX_G; idx += MX_G) {
     const int r = idx / MX_G, c = idx % MX_G;
@@ -93,54 +119,54 @@ __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
       a.dgi[mm * MX_G + c] = 0.f;
     }
   }
+  prefetch(a.T - 1);
+  prefetch(a.T - 2);
+  mx_cp_wait<1>();
+  __syncthreads();
   for (int t = a.T - 1; t >= 0; --t) {
-    int ci = 0;
-    for (int idx = j; idx < RPC * MX_H; idx += MX_G, ++ci) {
-      const int r = idx / MX_H, i = idx % MX_H;
-      const int row = row0 + r;
-      float d_r = 0.f, d_z = 0.f, d_n = 0.f, d_hn = 0.f, dhz = 0.f;
-      if (row < a.R) {
-        const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
-        const float rg = a.gates[mm * MX_G + i], zg = a.gates[mm * MX_G + MX_H + i], ng = a.gates[mm * MX_G + 2 * MX_H + i];
-        const float hn = a.hn[mm * MX_H + i];
-        const float hp = t > 0 ? a.hall[(mm - N) * MX_H + i] : 0.f;
-        const float dh = a.dh_out[mm * MX_H + i] + carry[ci];
-        const float dn = dh * (1.f - zg);
-        const float dz = dh * (hp - ng);
-        d_n = dn * (1.f - ng * ng);              // d pre-activation of n
-        d_z = dz * zg * (1.f - zg);
-        d_r = d_n * hn * rg * (1.f - rg);
-        d_hn = d_n * rg;                         // gradient reaching W_hn h + b_hn
-        dhz = dh * zg;
-        a.dgi[mm * MX_G + i] = d_r;
-        a.dgi[mm * MX_G + MX_H + i] = d_z;
-        a.dgi[mm * MX_G + 2 * MX_H + i] = d_n;
+    prefetch(t - 2);
+    if (p == 0) {
+#pragma unroll
+      for (int r = 0; r < RPC; ++r) {
+        const float* o = &ops_s[t % 3][r][0][0];
+        const float rg = o[k], zg = o[MX_H + k], ng = o[2 * MX_H + k], hn = o[3 * MX_H + k], hp = o[4 * MX_H + k];
+        const float dh = o[5 * MX_H + k] + carry[r];
+        const float d_n = dh * (1.f - zg) * (1.f - ng * ng);     // d pre-activation of n
+        const float d_z = dh * (hp - ng) * zg * (1.f - zg);
+        const float d_r = d_n * hn * rg * (1.f - rg);
+        dgh_s[r][k] = d_r; dgh_s[r][MX_H + k] = d_z; dgh_s[r][2 * MX_H + k] = d_n * rg;   // gradient reaching W_hn h + b_hn
+        carry[r] = dh * zg;
+        const int row = row0 + r;
+        if (row < a.R) {
+          const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
+          a.dgi[mm * MX_G + k] = d_r;
+          a.dgi[mm * MX_G + MX_H + k] = d_z;
+          a.dgi[mm * MX_G + 2 * MX_H + k] = d_n;
+        }
       }
-      dgh_s[r][i] = d_r; dgh_s[r][MX_H + i] = d_z; dgh_s[r][2 * MX_H + i] = d_hn;
-      carry[ci] = dhz;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
-      float acc = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int jj = 0; jj < MX_H; jj += 4) {
         const float4 d4 = mx_ld4(&dgh_s[r][p * MX_H + jj]);
-        acc = fmaf(wT[jj], d4.x, acc);
-        acc = fmaf(wT[jj + 1], d4.y, acc);
-        acc = fmaf(wT[jj + 2], d4.z, acc);
-        acc = fmaf(wT[jj + 3], d4.w, acc);
+        a0 = fmaf(wT[jj], d4.x, a0);
+        a1 = fmaf(wT[jj + 1], d4.y, a1);
+        a2 = fmaf(wT[jj + 2], d4.z, a2);
+        a3 = fmaf(wT[jj + 3], d4.w, a3);
       }
-      part_s[r][p][k] = acc;
+      part_s[r][p][k] = (a0 + a1) + (a2 + a3);
     }
+    mx_cp_wait<1>();          // operands of step t-1 have landed (only the newest group may still be in flight)
     __syncthreads();
-    ci = 0;
-    for (int idx = j; idx < RPC * MX_H; idx += MX_G, ++ci) {
-      const int r = idx / MX_H, i = idx % MX_H;
-      carry[ci] += part_s[r][0][i] + part_s[r][1][i] + part_s[r][2][i];
+    if (p == 0) {
+#pragma unroll
+      for (int r = 0; r < RPC; ++r) carry[r] += part_s[r][0][k] + part_s[r][1][k] + part_s[r][2][k];
     }
-    // (part_s / dgh_s are rewritten only after the next barrier pair)
   }
+  mx_cp_wait<0>();
 }
 
 // =====================================================================================================
@@ -148,7 +174,7 @@ __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
 // =====================================================================================================
 struct FrontBwdSmem {
   int ldi, ld64, ldg;
-  int o_dgi, o_dgn, o_x, o_hp, o_u, o_da, o_x0, o_xh0, o_wc, o_col, total;
+  int o_dgi, o_dgn, o_x, o_hp, o_u, o_da, o_x0, o_xh0, o_wc, o_col, o_stat, o_lnp, total;
 };
 static FrontBwdSmem front_bwd_smem(int in_dim, int TM) {
   FrontBwdSmem s;
@@ -157,47 +183,47 @@ static FrontBwdSmem front_bwd_smem(int in_dim, int TM) {
   int o = 0;
   s.o_dgi = o; o += TM * s.ldg;     // dgi tile (r,z,n)
   s.o_dgn = o; o += TM * s.ld64;    // dgi_n * r  (gradient reaching W_hn h)
-  s.o_x = o; o += TM * s.ld64;      // x2, later x1
+  s.o_x = o; o += TM * s.ld64;      // r gate (staging), then x2, later x1
   s.o_hp = o; o += TM * s.ld64;     // h_{t-1}
   s.o_u = o; o += TM * s.ld64;      // u2, later u1 (post-ReLU, pre-LN)
   s.o_da = o; o += TM * s.ld64;     // gradient w.r.t. the Linear output (after ReLU mask)
-  s.o_x0 = o; o += TM * s.ldi;      // LN0 output (fc1 input)
+  s.o_x0 = o; o += TM * s.ldi;      // raw input rows, then LN0 output (fc1 input)
   s.o_xh0 = o; o += TM * s.ldi;     // normalised input before the affine
   s.o_wc = o; o += 64 * s.ld64;
   s.o_col = o; o += 2 * I64 + 4 * 64;   // column accumulators for LayerNorm gains/biases
+  s.o_stat = o; o += 3 * TM * 2;        // (mean, rstd) of LN0 / LN1 / LN2 for the tile rows
+  s.o_lnp = o; o += 4 * 64;             // ln1_g, ln1_b, ln2_g, ln2_b
   s.total = o;
   return s;
 }
 
 // LayerNorm backward on a 64-wide row spread over a half-warp; v = upstream grad w.r.t. LN output (cols 4tx+j),
-// u = LN input.  Returns grad w.r.t. LN input, masked by ReLU (u > 0), and accumulates dgamma/dbeta column sums.
+// u = LN input.  Returns grad w.r.t. LN input, masked by ReLU (u > 0); dgamma/dbeta partials accumulate in registers.
 template <int RM>
-MX_DEVINL void ln64_bwd_relu(float (&v)[RM][4], const float* u_s, int ld, const float* st, int m0, int M, const float* gamma, float* dg_col,
-                             float* db_col) {
+MX_DEVINL void ln64_bwd_relu(float (&v)[RM][4], const float* u_s, int ld, const float* stat /*[TM][2]*/, const float* gamma_s,
+                             float (&dg)[4], float (&db)[4]) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
   for (int i = 0; i < RM; ++i) {
-    const int r = ty * RM + i, m = m0 + r;
-    float mean = 0.f, rstd = 0.f;
-    if (m < M) { mean = st[2 * (size_t)m]; rstd = st[2 * (size_t)m + 1]; }
+    const int r = ty * RM + i;
+    const float mean = stat[2 * r], rstd = stat[2 * r + 1];
+    const float4 u4 = mx_ld4(u_s + r * ld + 4 * tx);
+    const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
     float xh[4], dx[4], s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = 4 * tx + j;
-      const float uu = u_s[r * ld + c];
-      xh[j] = (uu - mean) * rstd;
-      atomicAdd(&dg_col[c], v[i][j] * xh[j]);
-      atomicAdd(&db_col[c], v[i][j]);
-      dx[j] = v[i][j] * gamma[c];
+      xh[j] = (uu[j] - mean) * rstd;
+      dg[j] = fmaf(v[i][j], xh[j], dg[j]);
+      db[j] += v[i][j];
+      dx[j] = v[i][j] * gamma_s[4 * tx + j];
       s1 += dx[j]; s2 += dx[j] * xh[j];
     }
     s1 = mx_row16_sum(s1) * (1.f / 64.f);
     s2 = mx_row16_sum(s2) * (1.f / 64.f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float uu = u_s[r * ld + 4 * tx + j];
       const float du = rstd * (dx[j] - s1 - xh[j] * s2);
-      v[i][j] = uu > 0.f ? du : 0.f;
+      v[i][j] = uu[j] > 0.f ? du : 0.f;
     }
   }
 }
@@ -215,32 +241,47 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
   float* col0g = smem + sm.o_col; float* col0b = col0g + I64;          // LN0 gain / bias grads   [I64] each
   float* col1g = col0b + I64; float* col1b = col1g + 64;               // LN1
   float* col2g = col1b + 64; float* col2b = col2g + 64;                // LN2
+  float* st0_s = smem + sm.o_stat; float* st1_s = st0_s + 2 * TM; float* st2_s = st1_s + 2 * TM;
+  float* ln1g_s = smem + sm.o_lnp; float* ln1b_s = ln1g_s + 64; float* ln2g_s = ln1b_s + 64; float* ln2b_s = ln2g_s + 64;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int ntiles = (a.M + TM - 1) / TM;
   const int T1 = a.T + 1, N = a.N;
+  const bool ldx_vec = (a.ldx & 3) == 0;
   float* gp = a.gpart + (size_t)blockIdx.x * a.P;
   for (int i = tid; i < 2 * I64 + 4 * 64; i += MX_TILE_THREADS) col0g[i] = 0.f;
+  if (tid < 64) { ln1g_s[tid] = th[L.ln1_g + tid]; ln1b_s[tid] = th[L.ln1_b + tid]; ln2g_s[tid] = th[L.ln2_g + tid]; ln2b_s[tid] = th[L.ln2_b + tid]; }
+  float dg1[4] = {0.f, 0.f, 0.f, 0.f}, db1[4] = {0.f, 0.f, 0.f, 0.f}, dg2[4] = {0.f, 0.f, 0.f, 0.f}, db2[4] = {0.f, 0.f, 0.f, 0.f};
   int iter = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
     const int m0 = tile * TM;
     const bool accum = iter > 0;
     __syncthreads();
-    // ---- stage the tile: dgi, dgi_n*r, h_{t-1}, u2, x2 = LN2(u2) ----
-    for (int idx = tid; idx < TM * MX_G; idx += MX_TILE_THREADS) {
-      const int r = idx / MX_G, c = idx % MX_G, m = m0 + r;
-      dgi_s[r * sm.ldg + c] = m < a.M ? a.dgi[(size_t)m * MX_G + c] : 0.f;
+    // ---- stage the tile's raw operands with cp.async: dgi, r gate, u2, u1?, h_{t-1}, the input rows, LN statistics ----
+    mx_stage_rows(dgi_s, sm.ldg, a.dgi, MX_G, m0, a.M, TM, MX_G);
+    mx_stage_rows(x_s, sm.ld64, a.gates, MX_G, m0, a.M, TM, MX_H);          // r gate = first 64 columns of the gates row
+    mx_stage_rows(u_s, sm.ld64, a.u2, MX_H, m0, a.M, TM, MX_H);
+    for (int r = tid >> 4; r < TM; r += MX_TILE_THREADS / 16) {
+      const int m = m0 + r;
+      const bool has = m < a.M && ((m / N) % T1) > 0;
+      float* d = hp_s + r * sm.ld64 + 4 * tx;
+      if (has) mx_cp16(d, a.hall + (size_t)(m - N) * MX_H + 4 * tx);
+      else mx_st4(d, make_float4(0.f, 0.f, 0.f, 0.f));
     }
+    if (ldx_vec) mx_stage_rows(x0_s, sm.ldi, a.X, a.ldx, m0, a.M, TM, mx_round_up(I, 4));
+    mx_cp_commit();
+    for (int i = tid; i < 3 * TM * 2; i += MX_TILE_THREADS) {
+      const int which = i / (2 * TM), rr = (i % (2 * TM)) >> 1, comp = i & 1;
+      const int m = m0 + rr;
+      const float* src = which == 0 ? a.st0 : (which == 1 ? a.st1 : a.st2);
+      st0_s[i] = (m < a.M && (which > 0 || a.feature_norm)) ? src[2 * (size_t)m + comp] : 0.f;
+    }
+    mx_cp_wait<0>();
+    __syncthreads();
     for (int idx = tid; idx < TM * MX_H; idx += MX_TILE_THREADS) {
-      const int r = idx / MX_H, c = idx % MX_H, m = m0 + r;
-      float dn = 0.f, hp = 0.f, u2 = 0.f, x2 = 0.f;
-      if (m < a.M) {
-        dn = a.dgi[(size_t)m * MX_G + 2 * MX_H + c] * a.gates[(size_t)m * MX_G + c];
-        const int t = (m / N) % T1;
-        if (t > 0) hp = a.hall[(size_t)(m - N) * MX_H + c];
-        u2 = a.u2[(size_t)m * MX_H + c];
-        x2 = (u2 - a.st2[2 * (size_t)m]) * a.st2[2 * (size_t)m + 1] * th[L.ln2_g + c] + th[L.ln2_b + c];
-      }
-      dgn_s[r * sm.ld64 + c] = dn; hp_s[r * sm.ld64 + c] = hp; u_s[r * sm.ld64 + c] = u2; x_s[r * sm.ld64 + c] = x2;
+      const int r = idx >> 6, c = idx & 63;
+      const int o = r * sm.ld64 + c;
+      dgn_s[o] = dgi_s[r * sm.ldg + 2 * MX_H + c] * x_s[o];                                // dgi_n * r
+      x_s[o] = (m0 + r < a.M) ? (u_s[o] - st2_s[2 * r]) * st2_s[2 * r + 1] * ln2g_s[c] + ln2b_s[c] : 0.f;   // x2 = LN2(u2)
     }
     __syncthreads();
     // ---- GRU weight gradients: dW_ih = dgi^T x2 ; dW_hh = [dgi_r, dgi_z, dgi_n*r]^T h_{t-1} ----
@@ -248,7 +289,6 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
       mx_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
       const float* dgh = nb < 2 ? dgi_s + nb * 64 : dgn_s;
       const int ldd = nb < 2 ? sm.ldg : sm.ld64;
-      // rows nb*64.. of W_hh: reuse the block routine on the 64-row slice
       mx_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
     }
     mx_colsum(dgi_s, sm.ldg, TM, MX_G, gp + L.bih, accum);
@@ -267,21 +307,18 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
       mx_mm_nn<RM>(dgi_s + nc * 64, sm.ldg, Wc, sm.ld64, v);
     }
     // ---- LN2 backward + ReLU mask -> da2 ----
-    ln64_bwd_relu<RM>(v, u_s, sm.ld64, a.st2, m0, a.M, th + L.ln2_g, col2g, col2b);
+    ln64_bwd_relu<RM>(v, u_s, sm.ld64, st2_s, ln2g_s, dg2, db2);
     __syncthreads();     // x_s (x2), u_s (u2) no longer needed by anyone
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
-#pragma unroll
-      for (int jx = 0; jx < 4; ++jx) da_s[(ty * RM + i) * sm.ld64 + 4 * tx + jx] = v[i][jx];
-    // stage u1 and x1 = LN1(u1)
+    for (int i = 0; i < RM; ++i) mx_st4(da_s + (ty * RM + i) * sm.ld64 + 4 * tx, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+    mx_stage_rows(u_s, sm.ld64, a.u1, MX_H, m0, a.M, TM, MX_H);
+    mx_cp_commit();
+    mx_cp_wait<0>();
+    __syncthreads();
     for (int idx = tid; idx < TM * MX_H; idx += MX_TILE_THREADS) {
-      const int r = idx / MX_H, c = idx % MX_H, m = m0 + r;
-      float u1 = 0.f, x1 = 0.f;
-      if (m < a.M) {
-        u1 = a.u1[(size_t)m * MX_H + c];
-        x1 = (u1 - a.st1[2 * (size_t)m]) * a.st1[2 * (size_t)m + 1] * th[L.ln1_g + c] + th[L.ln1_b + c];
-      }
-      u_s[r * sm.ld64 + c] = u1; x_s[r * sm.ld64 + c] = x1;
+      const int r = idx >> 6, c = idx & 63;
+      const int o = r * sm.ld64 + c;
+      x_s[o] = (m0 + r < a.M) ? (u_s[o] - st1_s[2 * r]) * st1_s[2 * r + 1] * ln1g_s[c] + ln1b_s[c] : 0.f;   // x1 = LN1(u1)
     }
     __syncthreads();
     // ---- fc2: dW2 = da2^T x1, db2 ; dx1 = da2 . W2 ----
@@ -294,20 +331,18 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
 #pragma unroll
       for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
     mx_mm_nn<RM>(da_s, sm.ld64, Wc, sm.ld64, v);
-    ln64_bwd_relu<RM>(v, u_s, sm.ld64, a.st1, m0, a.M, th + L.ln1_g, col1g, col1b);
+    ln64_bwd_relu<RM>(v, u_s, sm.ld64, st1_s, ln1g_s, dg1, db1);
     __syncthreads();     // da_s (da2) consumed by everyone
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
-#pragma unroll
-      for (int jx = 0; jx < 4; ++jx) da_s[(ty * RM + i) * sm.ld64 + 4 * tx + jx] = v[i][jx];
-    // stage x0 = LN0(x) and the normalised input
+    for (int i = 0; i < RM; ++i) mx_st4(da_s + (ty * RM + i) * sm.ld64 + 4 * tx, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+    // x0 = LN0(x) and the normalised input, in place over the staged raw rows
     for (int idx = tid; idx < TM * I64; idx += MX_TILE_THREADS) {
-      const int r = idx / I64, c = idx % I64, m = m0 + r;
+      const int r = idx / I64, c = idx - r * I64, m = m0 + r;
       float xh = 0.f, x0 = 0.f;
       if (m < a.M && c < I) {
-        const float x = a.X[(size_t)m * a.ldx + c];
+        const float x = ldx_vec ? x0_s[r * sm.ldi + c] : a.X[(size_t)m * a.ldx + c];
         if (a.feature_norm) {
-          xh = (x - a.st0[2 * (size_t)m]) * a.st0[2 * (size_t)m + 1];
+          xh = (x - st0_s[2 * r]) * st0_s[2 * r + 1];
           x0 = xh * th[L.fn_g + c] + th[L.fn_b + c];
         } else x0 = x;
       }
@@ -328,33 +363,32 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
           for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
         mx_mm_nn<RM>(da_s, sm.ld64, Wc, sm.ld64, v);
 #pragma unroll
-        for (int i = 0; i < RM; ++i)
+        for (int jx = 0; jx < 4; ++jx) {
+          const int c = kb * 64 + 4 * tx + jx;
+          if (c < I) {
+            float sg = 0.f, sb = 0.f;
 #pragma unroll
-          for (int jx = 0; jx < 4; ++jx) {
-            const int c = kb * 64 + 4 * tx + jx;
-            if (c < I) {
-              atomicAdd(&col0g[c], v[i][jx] * xh0_s[(ty * RM + i) * sm.ldi + c]);
-              atomicAdd(&col0b[c], v[i][jx]);
-            }
+            for (int i = 0; i < RM; ++i) { sg = fmaf(v[i][jx], xh0_s[(ty * RM + i) * sm.ldi + c], sg); sb += v[i][jx]; }
+            atomicAdd(&col0g[c], sg);
+            atomicAdd(&col0b[c], sb);
           }
+        }
       }
     }
   }
+  // ---- LayerNorm gain / bias gradients: per-thread partials -> per-CTA column sums -> this CTA's gradient partial ----
+#pragma unroll
+  for (int jx = 0; jx < 4; ++jx) {
+    const int c = 4 * tx + jx;
+    atomicAdd(&col1g[c], dg1[jx]); atomicAdd(&col1b[c], db1[jx]);
+    atomicAdd(&col2g[c], dg2[jx]); atomicAdd(&col2b[c], db2[jx]);
+  }
   __syncthreads();
-  // ---- LayerNorm gain / bias gradients accumulated over all tiles of this CTA ----
   for (int c = tid; c < MX_H; c += MX_TILE_THREADS) {
     gp[L.ln2_g + c] = col2g[c]; gp[L.ln2_b + c] = col2b[c];
     gp[L.ln1_g + c] = col1g[c]; gp[L.ln1_b + c] = col1b[c];
   }
   for (int c = tid; c < I; c += MX_TILE_THREADS) { gp[L.fn_g + c] = col0g[c]; gp[L.fn_b + c] = col0b[c]; }
-  if (iter == 0) {
-    // a CTA without tiles still owns a partial: publish zeros for the slices this kernel is responsible for
-    for (int i = tid; i < MX_H * I; i += MX_TILE_THREADS) gp[L.w1 + i] = 0.f;
-    for (int i = tid; i < MX_H * MX_H; i += MX_TILE_THREADS) gp[L.w2 + i] = 0.f;
-    for (int i = tid; i < MX_G * MX_H; i += MX_TILE_THREADS) { gp[L.wih + i] = 0.f; gp[L.whh + i] = 0.f; }
-    for (int i = tid; i < MX_G; i += MX_TILE_THREADS) { gp[L.bih + i] = 0.f; gp[L.bhh + i] = 0.f; }
-    for (int i = tid; i < MX_H; i += MX_TILE_THREADS) { gp[L.b1 + i] = 0.f; gp[L.b2 + i] = 0.f; }
-  }
 }
 
 // =====================================================================================================

@@ -34,7 +34,40 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int m0 = tile * TM;
-    // ---- load the input rows, LayerNorm over the I features (warp per row) ----
+    // ---- load the input rows (all loads of a warp's rows issued before any use), LayerNorm over the I features ----
+    if (I <= 128) {
+      constexpr int RW = TM / (MX_TILE_THREADS / 32);       // rows per warp
+      float xv[RW][4];
+#pragma unroll
+      for (int q = 0; q < RW; ++q) {
+        const int m = m0 + warp + q * (MX_TILE_THREADS / 32);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = lane + 32 * u;
+          xv[q][u] = (m < a.M && c < I) ? a.X[(size_t)m * a.ldx + c] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RW; ++q) {
+        const int r = warp + q * (MX_TILE_THREADS / 32), m = m0 + r;
+        float* row = A_s + r * lda;
+        const float mean = mx_warp_sum(xv[q][0] + xv[q][1] + xv[q][2] + xv[q][3]) / (float)I;
+        float qq = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const float d = (lane + 32 * u < I) ? xv[q][u] - mean : 0.f; qq += d * d; }
+        const float rstd = rsqrtf(mx_warp_sum(qq) / (float)I + MX_LN_EPS);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = lane + 32 * u;
+          if (c < Ipad) {
+            float v = 0.f;
+            if (c < I && m < a.M) v = a.feature_norm ? ((xv[q][u] - mean) * rstd * th[L.fn_g + c] + th[L.fn_b + c]) : xv[q][u];
+            row[c] = v;
+          }
+        }
+        if (live && lane == 0 && a.st0 && m < a.M) { a.st0[2 * (size_t)m] = mean; a.st0[2 * (size_t)m + 1] = rstd; }
+      }
+    } else
     for (int r = warp; r < TM; r += MX_TILE_THREADS / 32) {
       const int m = m0 + r;
       float* row = A_s + r * lda;
@@ -123,15 +156,17 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
 // =====================================================================================================
 template <int RPC>
 __global__ void __launch_bounds__(MX_G) k_gru_fwd(GruFwdArgs a) {
+  // thread j owns gate row j of W_hh (registers) for the whole sequence: p = j/64 selects r / z / n, i = j%64 the unit.
+  // Per step: mat-vec (4 independent accumulators) -> r,z threads apply the sigmoid and publish -> barrier ->
+  // n threads finish tanh + the state update -> barrier.  Transcendentals are ex2/rcp based (abs err ~1e-7).
   __shared__ __align__(16) float h_s[RPC][MX_H];
-  __shared__ float pre_s[RPC][MX_G];     // r,z: gi + gh ; n: gh_n (incl. b_hn)
-  __shared__ float gin_s[RPC][MX_H];     // gi_n
+  __shared__ float rz_s[RPC][2 * MX_H];
   const int net = blockIdx.y;
   const float* __restrict__ th = a.theta[net];
-  const int j = threadIdx.x;             // gate row 0..191
+  const int j = threadIdx.x;
+  const int p = j / MX_H, i = j % MX_H;
   const int row0 = blockIdx.x * RPC;
   const bool live = (net == 0);
-  // W_hh row j resident in registers for the whole sequence
   float w[MX_H];
 #pragma unroll
   for (int k = 0; k < MX_H; ++k) w[k] = th[a.whh + j * MX_H + k];
@@ -164,42 +199,41 @@ __global__ void __launch_bounds__(MX_G) k_gru_fwd(GruFwdArgs a) {
     }
     float acc[RPC];
 #pragma unroll
-    for (int r = 0; r < RPC; ++r) acc[r] = bias;
+    for (int r = 0; r < RPC; ++r) {
+      float a0 = bias, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-    for (int k = 0; k < MX_H; k += 4) {
+      for (int k = 0; k < MX_H; k += 4) {
+        const float4 h4 = mx_ld4(&h_s[r][k]);
+        a0 = fmaf(w[k], h4.x, a0);
+        a1 = fmaf(w[k + 1], h4.y, a1);
+        a2 = fmaf(w[k + 2], h4.z, a2);
+        a3 = fmaf(w[k + 3], h4.w, a3);
+      }
+      acc[r] = (a0 + a1) + (a2 + a3);
+    }
+    if (p < 2) {
 #pragma unroll
       for (int r = 0; r < RPC; ++r) {
-        const float4 h4 = mx_ld4(&h_s[r][k]);
-        acc[r] = fmaf(w[k], h4.x, acc[r]);
-        acc[r] = fmaf(w[k + 1], h4.y, acc[r]);
-        acc[r] = fmaf(w[k + 2], h4.z, acc[r]);
-        acc[r] = fmaf(w[k + 3], h4.w, acc[r]);
+        const float g = mx_sigmoid_fast(acc[r] + g_cur[r]);
+        rz_s[r][j] = g;
+        if (live && valid[r]) a.gates[(mrow[r] + (size_t)t * N) * MX_G + j] = g;
       }
     }
-#pragma unroll
-    for (int r = 0; r < RPC; ++r) {
-      if (j < 2 * MX_H) pre_s[r][j] = acc[r] + g_cur[r];
-      else { pre_s[r][j] = acc[r]; gin_s[r][j - 2 * MX_H] = g_cur[r]; }
-    }
     __syncthreads();
-    for (int idx = j; idx < RPC * MX_H; idx += MX_G) {
-      const int r = idx / MX_H, i = idx % MX_H;
-      const float rg = mx_sigmoid(pre_s[r][i]);
-      const float zg = mx_sigmoid(pre_s[r][MX_H + i]);
-      const float hn = pre_s[r][2 * MX_H + i];
-      const float ng = tanhf(gin_s[r][i] + rg * hn);
-      const float hp = h_s[r][i];
-      const float hnew = (1.f - zg) * ng + zg * hp;
-      h_s[r][i] = hnew;                     // only this thread touches h_s[r][i] in this phase
-      const int row = row0 + r;
-      if (row < a.R) {
-        const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
-        hall[mm * MX_H + i] = hnew;
-        if (live) {
-          a.gates[mm * MX_G + i] = rg;
-          a.gates[mm * MX_G + MX_H + i] = zg;
-          a.gates[mm * MX_G + 2 * MX_H + i] = ng;
-          a.hn[mm * MX_H + i] = hn;
+    if (p == 2) {
+#pragma unroll
+      for (int r = 0; r < RPC; ++r) {
+        const float rg = rz_s[r][i], zg = rz_s[r][MX_H + i];
+        const float ng = mx_tanh_fast(g_cur[r] + rg * acc[r]);
+        const float hnew = (1.f - zg) * ng + zg * h_s[r][i];
+        h_s[r][i] = hnew;                      // every mat-vec read of h_s finished before the barrier above
+        if (valid[r]) {
+          const size_t mm = mrow[r] + (size_t)t * N;
+          hall[mm * MX_H + i] = hnew;
+          if (live) {
+            a.gates[mm * MX_G + 2 * MX_H + i] = ng;
+            a.hn[mm * MX_H + i] = acc[r];
+          }
         }
       }
     }
@@ -232,33 +266,35 @@ __global__ void __launch_bounds__(256) k_qhead(QHeadArgs a) {
     const int t = bt % T1, b = bt / T1;
     float q_live_at_act = 0.f, tq_sel = 0.f;
     int greedy = 0;
+    // all global operands of this row-step first (one round trip), then the arithmetic
+    const float* hl = a.hall[0] + (size_t)m * MX_H;
+    const float* ht = a.hall[1] + (size_t)m * MX_H;
+    const float hl0 = hl[lane], hl1 = hl[lane + 32], ht0 = ht[lane], ht1 = ht[lane + 32];
+    const int act = (t < a.T) ? a.act_idx[((size_t)b * a.T + t) * N + n] : 0;
+    float av = 1.f;
+    if (a.avail && lane < A) av = a.avail[(size_t)m * a.act_ld + lane];
+    const unsigned avail_mask = __ballot_sync(0xffffffffu, av != 0.f);
     // ---------------- live ----------------
     {
-      const float* h = a.hall[0] + (size_t)m * MX_H;
-      const float h0 = h[lane], h1 = h[lane + 32];
-      const float mean = mx_warp_sum(h0 + h1) * (1.f / MX_H);
-      const float d0 = h0 - mean, d1 = h1 - mean;
+      const float mean = mx_warp_sum(hl0 + hl1) * (1.f / MX_H);
+      const float d0 = hl0 - mean, d1 = hl1 - mean;
       const float rstd = rsqrtf(mx_warp_sum(d0 * d0 + d1 * d1) * (1.f / MX_H) + MX_LN_EPS);
       if (lane == 0) { a.sto[2 * (size_t)m] = mean; a.sto[2 * (size_t)m + 1] = rstd; }
       const float y0 = d0 * rstd * lg_s[0][lane] + lb_s[0][lane];
       const float y1 = d1 * rstd * lg_s[0][lane + 32] + lb_s[0][lane + 32];
-      const int act = (t < a.T) ? a.act_idx[((size_t)b * a.T + t) * N + n] : 0;
       float best = 0.f;
       for (int k = 0; k < A; ++k) {
         float q = mx_warp_sum(y0 * wq_s[0][k * MX_H + lane] + y1 * wq_s[0][k * MX_H + lane + 32]) + bq_s[0][k];
         if (a.qall0 && lane == 0) a.qall0[(size_t)m * A + k] = q;
         if (k == act) q_live_at_act = q;
-        float qm = q;
-        if (a.avail && a.avail[(size_t)m * a.act_ld + k] == 0.f) qm = -1e10f;     // util.py:297-302
+        const float qm = ((avail_mask >> k) & 1u) ? q : -1e10f;                 // util.py:297-302
         if (k == 0 || qm > best) { best = qm; greedy = k; }                     // first maximum wins
       }
     }
     // ---------------- target ----------------
     {
-      const float* h = a.hall[1] + (size_t)m * MX_H;
-      const float h0 = h[lane], h1 = h[lane + 32];
-      const float mean = mx_warp_sum(h0 + h1) * (1.f / MX_H);
-      const float d0 = h0 - mean, d1 = h1 - mean;
+      const float mean = mx_warp_sum(ht0 + ht1) * (1.f / MX_H);
+      const float d0 = ht0 - mean, d1 = ht1 - mean;
       const float rstd = rsqrtf(mx_warp_sum(d0 * d0 + d1 * d1) * (1.f / MX_H) + MX_LN_EPS);
       const float y0 = d0 * rstd * lg_s[1][lane] + lb_s[1][lane];
       const float y1 = d1 * rstd * lg_s[1][lane + 32] + lb_s[1][lane + 32];

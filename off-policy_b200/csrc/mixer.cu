@@ -179,15 +179,22 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_mixer(MixerArgs a, MixSmem 
     // ================= target forward: Q_tot'(q_next[t], s[t+1]) =================
     for (int pass = 0; pass < 2; ++pass) {
       const bool tgt = (pass == 0);
-      for (int idx = tid; idx < TE * S64; idx += MX_TILE_THREADS) {
-        const int r = idx / S64, c = idx % S64;
-        const int e = e0 + r;
-        float v = 0.f;
-        if (e < E && c < L.S) {
-          const int b = e / a.T, t = e % a.T;
-          v = a.share[((size_t)b * (a.T + 1) + t + (tgt ? 1 : 0)) * a.share_ld + c];
+      {   // state rows: 16-byte async copies (share_ld is a multiple of 4 and its pad columns are zero)
+        const int nc4 = S64 >> 2, src4 = a.share_ld >> 2;
+        for (int r = tid >> 4; r < TE; r += MX_TILE_THREADS / 16) {
+          const int e = e0 + r;
+          const float* src = nullptr;
+          if (e < E) {
+            const int b = e / a.T, t = e % a.T;
+            src = a.share + ((size_t)b * (a.T + 1) + t + (tgt ? 1 : 0)) * a.share_ld;
+          }
+          for (int c4 = tid & 15; c4 < nc4; c4 += 16) {
+            float* d = s_s + r * sm.ldS + 4 * c4;
+            if (src && c4 < src4) mx_cp16(d, src + 4 * c4);
+            else mx_st4(d, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
         }
-        s_s[r * sm.ldS + c] = v;
+        mx_cp_commit();
       }
       for (int idx = tid; idx < TE * 32; idx += MX_TILE_THREADS) {
         const int r = idx / 32, n = idx % 32;
@@ -196,6 +203,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_mixer(MixerArgs a, MixSmem 
         if (e < E && n < L.N) v = (tgt ? a.q_next : a.q_taken)[(size_t)e * L.N + n];
         q_s[idx] = v;
       }
+      mx_cp_wait<0>();
       __syncthreads();
       mixer_forward<RM>(tgt ? a.theta_tgt : a.theta, L, sm, smem, tgt ? Qn_s : Q_s);
     }

@@ -75,5 +75,43 @@ MX_DEVINL void mx_st4_stream(float* p, float4 v) {
 #endif
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS): all of a thread's copies are in flight at once ----
+MX_DEVINL void mx_cp16(float* sdst, const float* gsrc) {
+#if MX_EMU
+  *reinterpret_cast<float4*>(sdst) = *reinterpret_cast<const float4*>(gsrc);
+#else
+  unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+#endif
+}
+MX_DEVINL void mx_cp4(float* sdst, const float* gsrc) {
+#if MX_EMU
+  *sdst = *gsrc;
+#else
+  unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+#endif
+}
+MX_DEVINL void mx_cp_commit() {
+#if !MX_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+MX_DEVINL void mx_cp_wait() {   // wait until at most N of this thread's committed groups are still pending
+#if !MX_EMU
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// fast transcendental forms for the recurrence (absolute error ~1e-7: ex2.approx + rcp.approx)
+MX_DEVINL float mx_sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+MX_DEVINL float mx_tanh_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __expf(-2.0f * ax);
+  const float r = __fdividef(1.0f - t, 1.0f + t);
+  return x < 0.f ? -r : r;
+}
+
 // LayerNorm statistics the way ATen's CPU/CUDA kernels define them: biased variance, eps inside the sqrt.
 #define MX_LN_EPS 1e-5f

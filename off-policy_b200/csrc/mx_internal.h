@@ -87,6 +87,7 @@ struct mx_qmix {
   MxMixLayout mix;
   int64_t P;               // padded parameter count
   int npart;               // number of per-CTA gradient partials
+  int debug;               // also materialise q_all / greedy (parity tests)
   float *theta, *theta_tgt, *adam_m, *adam_v;
   float* ws;
   int64_t ws_bytes;

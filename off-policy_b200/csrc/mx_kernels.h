@@ -120,6 +120,7 @@ struct OptimArgs {
   float* prio;             // [B] or null
   float lr, beta1, beta2, eps, max_grad_norm, tau;
   int world_size;
+  int fuse_polyak;          // Adam epilogue also applies the soft target update (graph mode)
 };
 int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s);
 int mx_launch_adam(const OptimArgs& a, cudaStream_t s);

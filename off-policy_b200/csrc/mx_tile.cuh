@@ -19,17 +19,52 @@
 static inline int mx_ld(int k) { return mx_round_up(k, 8) + 4; }   // host helper: padded leading dimension
 MX_DEVINL int mx_ld_dev(int k) { return ((k + 7) / 8) * 8 + 4; }
 
-// Stage rows [row0, row0+64) x cols [col0, col0+ncols) of a row-major global matrix W[nrows][ldg] into
-// Wc[64][ldw]; rows/cols outside the matrix are zero-filled; ncols_pad (multiple of 4) columns are written.
+// Stage rows [row0, row0+64) x cols [col0, col0+ncols_pad) of a row-major global matrix W[nrows][ldg] into
+// Wc[64][ldw] with cp.async (16-byte copies when rows are 16-byte aligned, 4-byte copies otherwise); rows / cols
+// outside the matrix are zero-filled.  Returns after this thread's copies have landed; the caller's
+// __syncthreads() publishes the chunk.
 MX_DEVINL void mx_stage_weight(float* Wc, int ldw, const float* __restrict__ W, int nrows, int ncols_total, int ldg, int row0, int col0,
                                int ncols_pad) {
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < 64 * ncols_pad; idx += MX_TILE_THREADS) {
-    int r = idx / ncols_pad, c = idx - r * ncols_pad;
-    int gr = row0 + r, gc = col0 + c;
-    float v = 0.f;
-    if (gr < nrows && gc < ncols_total) v = __ldg(W + (size_t)gr * ldg + gc);
-    Wc[r * ldw + c] = v;
+  const bool vec = ((ldg & 3) == 0) && ((col0 & 3) == 0) && ((ncols_total & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  if (vec) {
+    const int nc4 = ncols_pad >> 2;
+    for (int r = tid >> 4; r < 64; r += MX_TILE_THREADS / 16) {
+      const int gr = row0 + r;
+      for (int c4 = tid & 15; c4 < nc4; c4 += 16) {
+        const int gc = col0 + 4 * c4;
+        float* dst = Wc + r * ldw + 4 * c4;
+        if (gr < nrows && gc < ncols_total) mx_cp16(dst, W + (size_t)gr * ldg + gc);
+        else mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
+  } else {
+    for (int r = tid >> 5; r < 64; r += MX_TILE_THREADS / 32) {
+      const int gr = row0 + r;
+      for (int c = tid & 31; c < ncols_pad; c += 32) {
+        const int gc = col0 + c;
+        float* dst = Wc + r * ldw + c;
+        if (gr < nrows && gc < ncols_total) mx_cp4(dst, W + (size_t)gr * ldg + gc);
+        else *dst = 0.f;
+      }
+    }
+  }
+  mx_cp_commit();
+  mx_cp_wait<0>();
+}
+
+// Copy `nrows_tile` rows of `ncols` floats (ncols % 4 == 0, rows 16-byte aligned, row stride ldg) starting at global
+// row m0 into dst[r][ldd]; rows >= M are zero-filled.  Asynchronous: caller commits / waits.
+MX_DEVINL void mx_stage_rows(float* dst, int ldd, const float* __restrict__ src, size_t ldg, int m0, int M, int nrows_tile, int ncols) {
+  const int tid = threadIdx.x;
+  const int nc4 = ncols >> 2;
+  for (int r = tid >> 4; r < nrows_tile; r += MX_TILE_THREADS / 16) {
+    const int m = m0 + r;
+    for (int c4 = tid & 15; c4 < nc4; c4 += 16) {
+      float* d = dst + r * ldd + 4 * c4;
+      if (m < M) mx_cp16(d, src + (size_t)m * ldg + 4 * c4);
+      else mx_st4(d, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
   }
 }
 

@@ -50,26 +50,37 @@ __global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
   int parts = 0;
   for (int s = 0; s < a.nseg; ++s)
     if (i >= a.seg_begin[s] && i < a.seg_end[s]) parts = a.seg_parts[s];
-  float g = 0.f;
-  for (int p = 0; p < parts; ++p) g += a.gpart[(size_t)p * a.P + i];
-  a.grad[i] = g;
+  // four independent chains keep >= 8 partial loads in flight (fixed order -> deterministic result)
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  const float* gp = a.gpart + i;
+  int p = 0;
+#pragma unroll 2
+  for (; p + 4 <= parts; p += 4) {
+    g0 += gp[(size_t)p * a.P];
+    g1 += gp[(size_t)(p + 1) * a.P];
+    g2 += gp[(size_t)(p + 2) * a.P];
+    g3 += gp[(size_t)(p + 3) * a.P];
+  }
+  for (; p < parts; ++p) g0 += gp[(size_t)p * a.P];
+  a.grad[i] = (g0 + g1) + (g2 + g3);
 }
 
-__global__ void __launch_bounds__(256) k_adam(OptimArgs a) {
-  __shared__ double red[256];
+__global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
+  __shared__ double red[1024];
   __shared__ float s_coef, s_invd;
   const int tid = threadIdx.x;
   const float denom = a.grad[a.P + 0];
   const float invd = 1.0f / denom;
   // ||g||^2 over the full vector, identical summation order in every CTA
-  double ss = 0.0;
+  float sf = 0.f;
   const long long P4 = a.P / 4;
+#pragma unroll 4
   for (long long i = tid; i < P4; i += blockDim.x) {
     const float4 g = mx_ld4(a.grad + 4 * i);
     const float gx = g.x * invd, gy = g.y * invd, gz = g.z * invd, gw = g.w * invd;
-    ss += (double)gx * gx + (double)gy * gy + (double)gz * gz + (double)gw * gw;
+    sf += (gx * gx + gy * gy) + (gz * gz + gw * gw);
   }
-  red[tid] = ss;
+  red[tid] = (double)sf;
   __syncthreads();
   if (tid == 0) {
     double t = 0.0;
@@ -98,9 +109,11 @@ __global__ void __launch_bounds__(256) k_adam(OptimArgs a) {
     m = m + (g - m) * (1.f - a.beta1);                   // exp_avg.lerp_(grad, 1 - beta1)
     v = v * a.beta2 + (1.f - a.beta2) * g * g;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float den = sqrtf(v) / bc2s + a.eps;
-    a.theta[i] = a.theta[i] - step * (m / den);
+    const float th_new = a.theta[i] - step * (m / den);
+    a.theta[i] = th_new;
     a.adam_m[i] = m;
     a.adam_v[i] = v;
+    if (a.fuse_polyak) a.theta_tgt[i] = a.theta_tgt[i] * (1.0f - a.tau) + th_new * a.tau;   // util.py:132-134 fused epilogue
   }
 }
 
@@ -124,10 +137,10 @@ int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s) {
   return MX_CHECK_LAUNCH("grad_reduce");
 }
 int mx_launch_adam(const OptimArgs& a, cudaStream_t s) {
-  int grid = (int)((a.P + 1023) / 1024);
+  int grid = (int)((a.P + 4095) / 4096);
   const int sms = mx_num_sms();
   if (grid > sms) grid = sms;
-  MX_LAUNCH(k_adam, dim3(grid), dim3(256), 0, s, a);
+  MX_LAUNCH(k_adam, dim3(grid), dim3(1024), 0, s, a);
   MX_COUNT();
   MX_MARK("k_adam", s);
   return MX_CHECK_LAUNCH("adam");

@@ -156,6 +156,7 @@ extern "C" int mx_qmix_create(const mx_qmix_cfg* c, float* theta, float* theta_t
   q->cfg = *c;
   layouts(c, &q->agent, &q->mix, &q->P);
   q->npart = qmix_npart();
+  q->debug = 0;
   const int64_t need = ws_layout(c, q->P, q->npart, &q->W);
   if (workspace_bytes < need) { mx_set_error("mx_qmix_create: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need); delete q; return 1; }
   q->theta = theta; q->theta_tgt = theta_tgt; q->adam_m = adam_m; q->adam_v = adam_v;
@@ -260,8 +261,8 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   qh.act_idx = b->act_idx; qh.avail = c.use_avail ? b->avail : nullptr; qh.act_ld = b->act_ld;
   qh.M = M; qh.T = T; qh.N = N; qh.A = c.act_dim; qh.double_q = c.double_q;
   qh.q_taken = ws + W.q_taken; qh.q_next = ws + W.q_next;
-  qh.greedy = reinterpret_cast<int32_t*>(ws + W.greedy);
-  qh.qall0 = ws + W.qall[0]; qh.qall1 = ws + W.qall[1];
+  qh.greedy = q->debug ? reinterpret_cast<int32_t*>(ws + W.greedy) : nullptr;
+  qh.qall0 = q->debug ? ws + W.qall[0] : nullptr; qh.qall1 = q->debug ? ws + W.qall[1] : nullptr;
   if (mx_launch_qhead(qh, s)) return 1;
 
   int parts[3] = {0, 0, 0};
@@ -300,17 +301,21 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   return mx_launch_grad_reduce(o, s);
 }
 
-extern "C" int mx_qmix_apply(mx_qmix* q, void* stream) {
+extern "C" int mx_qmix_apply_ex(mx_qmix* q, uint32_t flags, void* stream) {
   const int parts[3] = {0, 0, 0};
   OptimArgs o = optim_args(q, q->cfg.max_batch, parts);
+  o.fuse_polyak = (flags & MX_STEP_FUSE_SOFT_UPDATE) ? 1 : 0;
   return mx_launch_adam(o, (cudaStream_t)stream);
 }
+extern "C" int mx_qmix_apply(mx_qmix* q, void* stream) { return mx_qmix_apply_ex(q, 0, stream); }
 
-extern "C" int mx_qmix_step(mx_qmix* q, const mx_batch* b, void* stream) {
+extern "C" int mx_qmix_step_ex(mx_qmix* q, const mx_batch* b, uint32_t flags, void* stream) {
   if (mx_qmix_backward_only(q, b, stream)) return 1;
-  if (q->cfg.world_size > 1) return 0;   // caller all-reduces mx_qmix_grad_buffer(), then mx_qmix_apply()
-  return mx_qmix_apply(q, stream);
+  if (q->cfg.world_size > 1) return 0;   // caller all-reduces mx_qmix_grad_buffer(), then mx_qmix_apply[_ex]()
+  return mx_qmix_apply_ex(q, flags, stream);
 }
+extern "C" int mx_qmix_step(mx_qmix* q, const mx_batch* b, void* stream) { return mx_qmix_step_ex(q, b, 0, stream); }
+extern "C" int mx_qmix_set_debug(mx_qmix* q, int32_t on) { q->debug = on ? 1 : 0; return 0; }
 
 extern "C" int mx_qmix_soft_update(mx_qmix* q, void* stream) {
   return mx_launch_polyak(q->theta_tgt, q->theta, q->P, q->cfg.tau, (cudaStream_t)stream);
@@ -342,11 +347,12 @@ static int run_sequence(mx_replay* r, mx_qmix* q, int B, double beta, uint32_t f
   else if (flags & 2u) { if (mx_replay_sample_per(r, B, beta, stream)) return 1; }
   mx_batch b;
   if (mx_replay_batch(r, B, &b)) return 1;
-  if (mx_qmix_step(q, &b, stream)) return 1;
+  const bool fuse = (flags & 4u) && q->cfg.world_size == 1;
+  if (mx_qmix_step_ex(q, &b, fuse ? MX_STEP_FUSE_SOFT_UPDATE : 0u, stream)) return 1;
   if (flags & 8u) {
     if (mx_replay_update_priorities(r, b.idx, mx_qmix_priorities(q), nullptr, nullptr, B, stream)) return 1;
   }
-  if (flags & 4u) { if (mx_qmix_soft_update(q, stream)) return 1; }
+  if ((flags & 4u) && !fuse) { if (mx_qmix_soft_update(q, stream)) return 1; }
   return 0;
 }
 

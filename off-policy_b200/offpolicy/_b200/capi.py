@@ -89,6 +89,9 @@ def _declare(lib):
         "mx_qmix_create": (C.c_int, [C.POINTER(QmixCfg), vp, vp, vp, vp, vp, i64, C.POINTER(vp)]),
         "mx_qmix_destroy": (None, [vp]),
         "mx_qmix_step": (C.c_int, [vp, C.POINTER(Batch), vp]),
+        "mx_qmix_step_ex": (C.c_int, [vp, C.POINTER(Batch), u32, vp]),
+        "mx_qmix_apply_ex": (C.c_int, [vp, u32, vp]),
+        "mx_qmix_set_debug": (C.c_int, [vp, i32]),
         "mx_qmix_backward_only": (C.c_int, [vp, C.POINTER(Batch), vp]),
         "mx_qmix_apply": (C.c_int, [vp, vp]),
         "mx_qmix_grad_buffer": (vp, [vp, C.POINTER(i64)]),

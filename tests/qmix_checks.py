@@ -38,6 +38,7 @@ def build_trainer(cfg, B, T, vdn=False, **over):
                 cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
     pol = QMixPolicy({"args": args, "device": capi.device()}, info)
     tr = QMix(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=capi.device(), episode_length=T, vdn=vdn)
+    capi.lib().mx_qmix_set_debug(tr.handle, 1)      # also materialise per-action Q values for the intermediate checks
     return args, pol, tr
 
 
