@@ -92,6 +92,11 @@ typedef struct mx_episodes {
   const float *obs, *share_obs, *acts, *rewards, *dones, *dones_env, *avail;
 } mx_episodes;
 int mx_replay_insert_async(mx_replay* r, const mx_episodes* ep, int32_t n_ep, int32_t* first_slot_out, void* stream);
+/* Same insert from ONE packed host block (a single host->device copy): fields in the order obs, share_obs, acts,
+ * rewards, dones, dones_env, avail, each starting at the 256-byte aligned offset reported by
+ * mx_replay_insert_packed_layout (which returns the packed size in bytes for n_ep episodes). */
+int64_t mx_replay_insert_packed_layout(const mx_replay* r, int32_t n_ep, int64_t offsets[7], int64_t counts[7]);
+int mx_replay_insert_packed_async(mx_replay* r, const void* packed, int64_t nbytes, int32_t n_ep, int32_t* first_slot_out, void* stream);
 int32_t mx_replay_len(const mx_replay* r);      /* filled_i  (rec_buffer.py:36-37)  */
 int32_t mx_replay_cursor(const mx_replay* r);   /* current_i                         */
 

@@ -69,11 +69,14 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
 // =====================================================================================================
 // GRU backward through time
 // =====================================================================================================
+#define BWD_PF 4
+#define BWD_RING (BWD_PF + 1)
+
 template <int RPC>
 __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
-  // Operands of step t (r, z, n, hn, h_{t-1}, dL/dh_t: six 64-float rows per sequence row) are prefetched two steps
-  // ahead with cp.async into a 3-slot shared-memory ring, so no global latency sits on the serial chain.
-  __shared__ __align__(16) float ops_s[3][RPC][6][MX_H];
+  // Operands of step t (r, z, n, hn, h_{t-1}, dL/dh_t: six 64-float rows per sequence row) are prefetched BWD_PF steps
+  // ahead with cp.async into a shared-memory ring, so no global (L2) latency sits on the serial chain.
+  __shared__ __align__(16) float ops_s[BWD_RING][RPC][6][MX_H];
   __shared__ __align__(16) float dgh_s[RPC][MX_G];
   __shared__ float part_s[RPC][3][MX_H];
   const int j = threadIdx.x;
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
       for (int c = j; c < RPC * 6 * 16; c += MX_G) {            // 16-byte pieces: RPC rows x 6 operands x 16
         const int r = c / 96, rem = c % 96, op = rem / 16, q4 = rem % 16;
         const int row = row0 + r;
-        float* dst = &ops_s[t % 3][r][op][4 * q4];
+        float* dst = &ops_s[t % BWD_RING][r][op][4 * q4];
         if (row < a.R) {
           const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
           const float* src;
@@ -119,16 +122,16 @@ __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
       a.dgi[mm * MX_G + c] = 0.f;
     }
   }
-  prefetch(a.T - 1);
-  prefetch(a.T - 2);
-  mx_cp_wait<1>();
+#pragma unroll
+  for (int d = 1; d <= BWD_PF; ++d) prefetch(a.T - d);
+  mx_cp_wait<BWD_PF - 1>();
   __syncthreads();
   for (int t = a.T - 1; t >= 0; --t) {
-    prefetch(t - 2);
+    prefetch(t - BWD_PF);              // slot (t-BWD_PF) % RING == (t+1) % RING: last read one full step ago
     if (p == 0) {
 #pragma unroll
       for (int r = 0; r < RPC; ++r) {
-        const float* o = &ops_s[t % 3][r][0][0];
+        const float* o = &ops_s[t % BWD_RING][r][0][0];
         const float rg = o[k], zg = o[MX_H + k], ng = o[2 * MX_H + k], hn = o[3 * MX_H + k], hp = o[4 * MX_H + k];
         const float dh = o[5 * MX_H + k] + carry[r];
         const float d_n = dh * (1.f - zg) * (1.f - ng * ng);     // d pre-activation of n
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
       }
       part_s[r][p][k] = (a0 + a1) + (a2 + a3);
     }
-    mx_cp_wait<1>();          // operands of step t-1 have landed (only the newest group may still be in flight)
+    mx_cp_wait<BWD_PF - 1>();   // operands of step t-1 have landed (the newer groups may still be in flight)
     __syncthreads();
     if (p == 0) {
 #pragma unroll

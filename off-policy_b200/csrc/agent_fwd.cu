@@ -154,13 +154,18 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
 // =====================================================================================================
 // GRU recurrence
 // =====================================================================================================
+#define GRU_PF 4                 // gi rows are prefetched this many steps ahead (L2 latency ~ 2-3 step times)
+#define GRU_RING (GRU_PF + 1)
+
 template <int RPC>
 __global__ void __launch_bounds__(MX_G) k_gru_fwd(GruFwdArgs a) {
   // thread j owns gate row j of W_hh (registers) for the whole sequence: p = j/64 selects r / z / n, i = j%64 the unit.
   // Per step: mat-vec (4 independent accumulators) -> r,z threads apply the sigmoid and publish -> barrier ->
   // n threads finish tanh + the state update -> barrier.  Transcendentals are ex2/rcp based (abs err ~1e-7).
+  // The input-side pre-activations gi_t are streamed GRU_PF steps ahead with cp.async into a shared-memory ring.
   __shared__ __align__(16) float h_s[RPC][MX_H];
   __shared__ float rz_s[RPC][2 * MX_H];
+  __shared__ __align__(16) float gi_s[GRU_RING][RPC][MX_G];
   const int net = blockIdx.y;
   const float* __restrict__ th = a.theta[net];
   const int j = threadIdx.x;
@@ -185,21 +190,33 @@ __global__ void __launch_bounds__(MX_G) k_gru_fwd(GruFwdArgs a) {
     const int b = valid[r] ? row / N : 0, n = valid[r] ? row % N : 0;
     mrow[r] = ((size_t)b * T1) * N + n;      // + t*N per step
   }
-  float g_next[RPC];
+  auto prefetch = [&](int t) {
+    if (t < T1) {
+      for (int c = j; c < RPC * (MX_G / 4); c += MX_G) {
+        const int r = c / (MX_G / 4), q4 = c % (MX_G / 4);
+        const int row = row0 + r;
+        float* dst = &gi_s[t % GRU_RING][r][4 * q4];
+        if (row < a.R) {
+          const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
+          mx_cp16(dst, gi + mm * MX_G + 4 * q4);
+        } else {
+          mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+    }
+    mx_cp_commit();
+  };
 #pragma unroll
-  for (int r = 0; r < RPC; ++r) g_next[r] = valid[r] ? gi[mrow[r] * MX_G + j] : 0.f;
+  for (int t = 0; t < GRU_PF; ++t) prefetch(t);
+  mx_cp_wait<GRU_PF - 1>();
   __syncthreads();
 
   for (int t = 0; t < T1; ++t) {
-    float g_cur[RPC];
+    prefetch(t + GRU_PF);               // slot (t+GRU_PF) % RING == (t-1) % RING: last read in step t-1, two barriers ago
+    float acc[RPC], g_cur[RPC];
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
-      g_cur[r] = g_next[r];
-      if (t + 1 < T1 && valid[r]) g_next[r] = gi[(mrow[r] + (size_t)(t + 1) * N) * MX_G + j];   // prefetch next step
-    }
-    float acc[RPC];
-#pragma unroll
-    for (int r = 0; r < RPC; ++r) {
+      g_cur[r] = gi_s[t % GRU_RING][r][j];
       float a0 = bias, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int k = 0; k < MX_H; k += 4) {
@@ -237,8 +254,10 @@ __global__ void __launch_bounds__(MX_G) k_gru_fwd(GruFwdArgs a) {
         }
       }
     }
+    mx_cp_wait<GRU_PF - 1>();           // gi of step t+1 has landed (this thread's copies); the barrier publishes it
     __syncthreads();
   }
+  mx_cp_wait<0>();
 }
 
 // =====================================================================================================

@@ -39,7 +39,7 @@ static MixSmem mix_smem_layout(const MxMixLayout& L, int TE) {
 
 // Y_s[r][c] = act(sum_k X_s[r][k] W[c][k] + b[c]) for c < Nout (columns up to round_up(Nout,64) are written, zeros beyond)
 template <int RM>
-MX_DEVINL void tile_linear(const float* X_s, int ldx, int K, const float* __restrict__ W, const float* __restrict__ b, int Nout, float* Y_s,
+__device__ MX_NOINLINE void tile_linear(const float* X_s, int ldx, int K, const float* __restrict__ W, const float* __restrict__ b, int Nout, float* Y_s,
                            int ldy, bool relu, float* Wc, int ldw) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int Kpad = (K + 3) & ~3;
@@ -71,7 +71,7 @@ MX_DEVINL void tile_linear(const float* X_s, int ldx, int K, const float* __rest
 // dX_s[r][k] = (mask_s[r][k] > 0 ? 1 : 0) * sum_n dY_s[r][n] W[n][k]   for k < K (written over round_up(K,64) cols).
 // dX_s may alias mask_s (each element is read and written by the same thread).
 template <int RM>
-MX_DEVINL void tile_dgrad_relu(const float* dY_s, int ldy, int Nout, const float* __restrict__ W, int K, float* dX_s, const float* mask_s,
+__device__ MX_NOINLINE void tile_dgrad_relu(const float* dY_s, int ldy, int Nout, const float* __restrict__ W, int K, float* dX_s, const float* mask_s,
                                int ldx, float* Wc, int ldw) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   for (int kb = 0; kb * 64 < K; ++kb) {
@@ -100,7 +100,7 @@ MX_DEVINL void tile_dgrad_relu(const float* dY_s, int ldy, int Nout, const float
 }
 
 // dW (+)= dY_s^T X_s ; db (+)= colsum(dY_s)
-MX_DEVINL void tile_wgrad(const float* dY_s, int ldy, int Nout, const float* X_s, int ldx, int K, int TE, float* dW, float* db, bool accumulate) {
+__device__ MX_NOINLINE void tile_wgrad(const float* dY_s, int ldy, int Nout, const float* X_s, int ldx, int K, int TE, float* dW, float* db, bool accumulate) {
   for (int nb = 0; nb * 64 < Nout; ++nb)
     for (int kb = 0; kb * 64 < K; ++kb) mx_wgrad_block(dY_s + nb * 64, ldy, X_s + kb * 64, ldx, TE, dW, Nout, K, nb * 64, kb * 64, accumulate);
   mx_colsum(dY_s, ldy, TE, Nout, db, accumulate);

@@ -20,6 +20,11 @@
 #define MX_G (3 * MX_H)  // GRU gate rows [r; z; n]
 
 #define MX_DEVINL __device__ __forceinline__
+#if MX_EMU
+#define MX_NOINLINE
+#else
+#define MX_NOINLINE __noinline__
+#endif
 
 // dynamic shared memory base
 #if MX_EMU

@@ -66,12 +66,12 @@ __global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
 }
 
 __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
-  __shared__ double red[1024];
-  __shared__ float s_coef, s_invd;
+  __shared__ double red[32];
+  __shared__ float s_scale, s_step, s_bc2s;
   const int tid = threadIdx.x;
   const float denom = a.grad[a.P + 0];
   const float invd = 1.0f / denom;
-  // ||g||^2 over the full vector, identical summation order in every CTA
+  // ||g||^2 over the full vector, identical summation order in every CTA (no grid-wide barrier needed)
   float sf = 0.f;
   const long long P4 = a.P / 4;
 #pragma unroll 4
@@ -80,29 +80,30 @@ __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
     const float gx = g.x * invd, gy = g.y * invd, gz = g.z * invd, gw = g.w * invd;
     sf += (gx * gx + gy * gy) + (gz * gz + gw * gw);
   }
-  red[tid] = (double)sf;
+  double ds = mx_warp_sum_d((double)sf);
+  if ((tid & 31) == 0) red[tid >> 5] = ds;
   __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
-    for (int i = 0; i < (int)blockDim.x; ++i) t += red[i];
-    const float norm = (float)sqrt(t);
-    float coef = a.max_grad_norm / (norm + 1e-6f);       // clip_grad_norm_: always applied, clamped to 1
-    if (coef > 1.f) coef = 1.f;
-    s_coef = coef;
-    s_invd = invd;
-    if (blockIdx.x == 0) {
-      a.info[0] = a.grad[a.P + 1] * invd;                // loss
-      a.info[1] = norm;                                  // grad_norm (pre-clip)
-      a.info[2] = a.grad[a.P + 2] / a.grad[a.P + 3];     // Q_tot mean over all (t,b)
-      a.info[3] = denom;
+  if (tid < 32) {
+    double t = tid < (int)(blockDim.x >> 5) ? red[tid] : 0.0;
+    t = mx_warp_sum_d(t);
+    if (tid == 0) {
+      const float norm = (float)sqrt(t);
+      float coef = a.max_grad_norm / (norm + 1e-6f);       // clip_grad_norm_: always applied, clamped to 1
+      if (coef > 1.f) coef = 1.f;
+      const double st = a.adam_t[0];
+      s_scale = coef * invd;
+      s_step = a.lr / (float)(1.0 - pow((double)a.beta1, st));
+      s_bc2s = (float)sqrt(1.0 - pow((double)a.beta2, st));
+      if (blockIdx.x == 0) {
+        a.info[0] = a.grad[a.P + 1] * invd;                // loss
+        a.info[1] = norm;                                  // grad_norm (pre-clip)
+        a.info[2] = a.grad[a.P + 2] / a.grad[a.P + 3];     // Q_tot mean over all (t,b)
+        a.info[3] = denom;
+      }
     }
   }
   __syncthreads();
-  const float scale = s_coef * s_invd;
-  const double t = a.adam_t[0];
-  const float bc1 = (float)(1.0 - pow((double)a.beta1, t));
-  const float bc2s = (float)sqrt(1.0 - pow((double)a.beta2, t));
-  const float step = a.lr / bc1;
+  const float scale = s_scale, step = s_step, bc2s = s_bc2s;
   for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < a.P; i += (long long)gridDim.x * blockDim.x) {
     const float g = a.grad[i] * scale;
     float m = a.adam_m[i], v = a.adam_v[i];

@@ -472,44 +472,47 @@ extern "C" int32_t mx_replay_cursor(const mx_replay* r) { return r->cursor; }
 template <class T> static T* at(mx_replay* r, int64_t off) { return reinterpret_cast<T*>(r->blob + off); }
 template <class T> static const T* cat(const mx_replay* r, int64_t off) { return reinterpret_cast<const T*>(r->blob + off); }
 
-extern "C" int mx_replay_insert_async(mx_replay* r, const mx_episodes* ep, int32_t n_ep, int32_t* first_slot_out, void* stream) {
+// field table of one insert call: element counts and byte offsets inside the (256-byte aligned) staging layout
+struct StageField { int64_t count, offset; };
+static int stage_fields(const mx_replay* r, int n_ep, StageField f[7], int64_t* total) {
+  const mx_replay_cfg& c = r->cfg;
+  const int T = c.episode_len, N = c.n_agents;
+  const int64_t cnt[7] = {(int64_t)(T + 1) * n_ep * N * c.obs_dim, (int64_t)(T + 1) * n_ep * c.share_dim, (int64_t)T * n_ep * N * c.act_dim,
+                          (int64_t)T * n_ep * N, (int64_t)T * n_ep * N, (int64_t)T * n_ep, c.use_avail ? (int64_t)(T + 1) * n_ep * N * c.act_dim : 0};
+  int64_t so = 0;
+  for (int i = 0; i < 7; ++i) { f[i].count = cnt[i]; f[i].offset = so; so = align_up(so + cnt[i] * 4, 256); }
+  *total = so;
+  return 0;
+}
+
+static int insert_staged(mx_replay* r, int32_t n_ep, int32_t* first_slot_out, cudaStream_t s) {
   const mx_replay_cfg& c = r->cfg;
   const mx_replay_layout& L = r->L;
-  if (n_ep <= 0 || n_ep > c.max_batch || n_ep > c.capacity) { mx_set_error("mx_replay_insert: n_ep=%d out of range (max_batch %d)", n_ep, c.max_batch); return 1; }
-  if (!ep->obs || !ep->share_obs || !ep->acts || !ep->rewards || !ep->dones || !ep->dones_env || (c.use_avail && !ep->avail)) {
-    mx_set_error("mx_replay_insert: missing field");
-    return 1;
-  }
   const int T = c.episode_len, N = c.n_agents;
-  cudaStream_t s = (cudaStream_t)stream;
+  StageField sf[7];
+  int64_t total;
+  stage_fields(r, n_ep, sf, &total);
+  char* stage = r->blob + L.off_stage;
   InsArgs a;
   memset(&a, 0, sizeof(a));
-  char* stage = r->blob + L.off_stage;
-  int64_t so = 0;
   int nf = 0;
-  auto add = [&](const float* host, float* dst, int Tf, int rows, int D, int ld, int64_t ep_stride) {
-    int64_t cnt = (int64_t)Tf * n_ep * rows * D;
-    float* dsrc = reinterpret_cast<float*>(stage + so);
-    cudaMemcpyAsync(dsrc, host, cnt * 4, cudaMemcpyDefault, s);
-    so = align_up(so + cnt * 4, 256);
-    a.f[nf].src = dsrc; a.f[nf].dst = dst; a.f[nf].Tf = Tf; a.f[nf].rows = rows; a.f[nf].D = D; a.f[nf].ld = ld;
-    a.f[nf].ep_stride = ep_stride; a.f[nf].count = cnt;
+  auto add = [&](int fi, float* dst, int Tf, int rows, int D, int ld, int64_t ep_stride) {
+    a.f[nf].src = reinterpret_cast<const float*>(stage + sf[fi].offset); a.f[nf].dst = dst; a.f[nf].Tf = Tf; a.f[nf].rows = rows; a.f[nf].D = D;
+    a.f[nf].ld = ld; a.f[nf].ep_stride = ep_stride; a.f[nf].count = sf[fi].count;
     ++nf;
-    return dsrc;
   };
-  add(ep->obs, at<float>(r, L.off_obs), T + 1, N, c.obs_dim, L.obs_ld, L.ep_obs);
-  add(ep->share_obs, at<float>(r, L.off_share), T + 1, 1, c.share_dim, L.share_ld, L.ep_share);
-  const float* acts_dev = add(ep->acts, at<float>(r, L.off_acts), T, N, c.act_dim, L.act_ld, L.ep_acts);
-  add(ep->rewards, at<float>(r, L.off_rew), T, N, 1, 1, L.ep_rew);
-  add(ep->dones, at<float>(r, L.off_dones), T, N, 1, 1, L.ep_dones);
-  add(ep->dones_env, at<float>(r, L.off_dones_env), T, 1, 1, 1, L.ep_dones_env);
-  if (c.use_avail) add(ep->avail, at<float>(r, L.off_avail), T + 1, N, c.act_dim, L.act_ld, L.ep_avail);
-  if (so > L.stage_bytes) { mx_set_error("mx_replay_insert: staging overflow"); return 1; }
+  add(0, at<float>(r, L.off_obs), T + 1, N, c.obs_dim, L.obs_ld, L.ep_obs);
+  add(1, at<float>(r, L.off_share), T + 1, 1, c.share_dim, L.share_ld, L.ep_share);
+  add(2, at<float>(r, L.off_acts), T, N, c.act_dim, L.act_ld, L.ep_acts);
+  add(3, at<float>(r, L.off_rew), T, N, 1, 1, L.ep_rew);
+  add(4, at<float>(r, L.off_dones), T, N, 1, 1, L.ep_dones);
+  add(5, at<float>(r, L.off_dones_env), T, 1, 1, 1, L.ep_dones_env);
+  if (c.use_avail) add(6, at<float>(r, L.off_avail), T + 1, N, c.act_dim, L.act_ld, L.ep_avail);
   a.nf = nf;
   const int first = r->cursor % c.capacity;                    // current_i may equal capacity (rec_buffer.py:187)
   a.n_ep = n_ep; a.first_slot = first; a.capacity = c.capacity;
   a.T = T; a.N = N; a.A = c.act_dim; a.act_ld = L.act_ld;
-  a.acts_src = acts_dev;
+  a.acts_src = reinterpret_cast<const float*>(stage + sf[2].offset);
   a.actidx = at<int32_t>(r, L.off_actidx);
   a.ep_actidx = L.ep_actidx;
   a.state = at<MxReplayState>(r, L.off_state);
@@ -539,6 +542,49 @@ extern "C" int mx_replay_insert_async(mx_replay* r, const mx_episodes* ep, int32
   r->cursor = a.new_cursor;
   r->filled = a.new_filled;
   return MX_CHECK_LAUNCH("insert");
+}
+
+static int check_insert(mx_replay* r, int32_t n_ep) {
+  const mx_replay_cfg& c = r->cfg;
+  if (n_ep <= 0 || n_ep > c.max_batch || n_ep > c.capacity) { mx_set_error("mx_replay_insert: n_ep=%d out of range (max_batch %d)", n_ep, c.max_batch); return 1; }
+  return 0;
+}
+
+extern "C" int mx_replay_insert_async(mx_replay* r, const mx_episodes* ep, int32_t n_ep, int32_t* first_slot_out, void* stream) {
+  if (check_insert(r, n_ep)) return 1;
+  if (!ep->obs || !ep->share_obs || !ep->acts || !ep->rewards || !ep->dones || !ep->dones_env || (r->cfg.use_avail && !ep->avail)) {
+    mx_set_error("mx_replay_insert: missing field");
+    return 1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  StageField sf[7];
+  int64_t total;
+  stage_fields(r, n_ep, sf, &total);
+  if (total > r->L.stage_bytes) { mx_set_error("mx_replay_insert: staging overflow"); return 1; }
+  const float* src[7] = {ep->obs, ep->share_obs, ep->acts, ep->rewards, ep->dones, ep->dones_env, ep->avail};
+  char* stage = r->blob + r->L.off_stage;
+  for (int i = 0; i < 7; ++i)
+    if (sf[i].count) cudaMemcpyAsync(stage + sf[i].offset, src[i], sf[i].count * 4, cudaMemcpyDefault, s);
+  return insert_staged(r, n_ep, first_slot_out, s);
+}
+
+extern "C" int64_t mx_replay_insert_packed_layout(const mx_replay* r, int32_t n_ep, int64_t offsets[7], int64_t counts[7]) {
+  StageField sf[7];
+  int64_t total;
+  stage_fields(r, n_ep, sf, &total);
+  for (int i = 0; i < 7; ++i) { offsets[i] = sf[i].offset; counts[i] = sf[i].count; }
+  return total;
+}
+
+extern "C" int mx_replay_insert_packed_async(mx_replay* r, const void* packed, int64_t nbytes, int32_t n_ep, int32_t* first_slot_out, void* stream) {
+  if (check_insert(r, n_ep)) return 1;
+  StageField sf[7];
+  int64_t total;
+  stage_fields(r, n_ep, sf, &total);
+  if (nbytes != total || total > r->L.stage_bytes) { mx_set_error("mx_replay_insert_packed: expected %lld bytes, got %lld", (long long)total, (long long)nbytes); return 1; }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemcpyAsync(r->blob + r->L.off_stage, packed, (size_t)nbytes, cudaMemcpyDefault, s);     // ONE host->device copy per insert
+  return insert_staged(r, n_ep, first_slot_out, s);
 }
 
 extern "C" int mx_replay_seed(mx_replay* r, uint32_t seed, void* stream) {

@@ -146,6 +146,7 @@ class RecPolicyBuffer(object):
         self._stage = [None, None]
         self._stage_evt = [None, None]
         self._stage_i = 0
+        self._pack_cache = {}
         self._idx_dev = torch.zeros(self.max_batch, dtype=torch.int64, device=self.dev)
         self._idx_pin = None
 
@@ -219,8 +220,16 @@ class RecPolicyBuffer(object):
             self._stage[i] = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, pin_memory=pin)
         return i, self._stage[i]
 
+    def _packed_layout(self, n_ep):
+        lay = self._pack_cache.get(n_ep)
+        if lay is None:
+            offs, cnts = (C.c_int64 * 7)(), (C.c_int64 * 7)()
+            total = int(capi.lib().mx_replay_insert_packed_layout(self.handle, n_ep, offs, cnts))
+            lay = (list(offs), list(cnts), total)
+            self._pack_cache[n_ep] = lay
+        return lay
+
     def insert(self, num_insert_episodes, obs, share_obs, acts, rewards, dones, dones_env, avail_acts=None):
-        T, N = self.episode_length, self.num_agents
         n_ep = int(num_insert_episodes)
         acts = np.asarray(acts)
         assert acts.shape[0] == self.episode_length, ("different dimension!")            # rec_buffer.py:165
@@ -229,26 +238,21 @@ class RecPolicyBuffer(object):
         share_obs = np.asarray(share_obs)
         if share_obs.ndim == 4:
             share_obs = share_obs[:, :, 0]                                               # rec_buffer.py:173-175
-        arrs = [np.asarray(obs), share_obs, acts, np.asarray(rewards), np.asarray(dones), np.asarray(dones_env)]
-        shapes = [(T + 1, n_ep, N, self.obs_dim), (T + 1, n_ep, self.share_dim), (T, n_ep, N, self.act_dim),
-                  (T, n_ep, N, 1), (T, n_ep, N, 1), (T, n_ep, 1)]
-        if self.use_avail_acts:
-            arrs.append(np.asarray(avail_acts))
-            shapes.append((T + 1, n_ep, N, self.act_dim))
-        total = sum(int(np.prod(s)) * 4 + 64 for s in shapes)
+        arrs = [obs, share_obs, acts, rewards, dones, dones_env, avail_acts if self.use_avail_acts else None]
+        offs, cnts, total = self._packed_layout(n_ep)
         si, stage = self._staging(total)
-        ptrs, off = [], 0
-        for a, s in zip(arrs, shapes):
-            n = int(np.prod(s))
-            dst = stage[off:off + n * 4].view(torch.float32).numpy()
-            np.copyto(dst, np.asarray(a, dtype=np.float32).reshape(-1), casting="same_kind")
-            ptrs.append(stage.data_ptr() + off)
-            off += (n * 4 + 63) // 64 * 64
-        ep = capi.Episodes(*(ptrs + [None] * (7 - len(ptrs))))
+        host = stage.numpy()
+        for a, o, n in zip(arrs, offs, cnts):
+            if n:
+                a = np.asarray(a)
+                if a.size != n:
+                    raise ValueError("insert: a field has %d elements, expected %d" % (a.size, n))
+                np.copyto(host[o:o + 4 * n].view(np.float32), a.reshape(-1), casting="same_kind")
         first = C.c_int32()
-        capi.check(capi.lib().mx_replay_insert_async(self.handle, C.byref(ep), n_ep, C.byref(first), capi.stream_ptr()))
+        capi.check(capi.lib().mx_replay_insert_packed_async(self.handle, C.c_void_p(stage.data_ptr()), total, n_ep, C.byref(first),
+                                                            capi.stream_ptr()))
         if self.dev.type == "cuda":
-            evt = torch.cuda.Event()
+            evt = self._stage_evt[si] or torch.cuda.Event()
             evt.record(torch.cuda.current_stream(self.dev))
             self._stage_evt[si] = evt
         return (first.value + np.arange(n_ep)) % self.buffer_size
