@@ -71,39 +71,58 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
 // =====================================================================================================
 #define BWD_PF 4
 #define BWD_RING (BWD_PF + 1)
+#define BWD_THREADS 256
 
 template <int RPC>
-__global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
+__global__ void __launch_bounds__(BWD_THREADS) k_gru_bwd(GruBwdArgs a) {
+  // Quad layout: thread = 4*k + p.  Thread (k, p<3) keeps W_hh[p*64 + jj][k], jj < 64 (a third of column k of W_hh^T)
+  // in registers; the three partial sums of dh_{t-1}[k] meet by quad shuffles, lane p==0 does the gate derivatives
+  // and publishes d(gh) into the OTHER shared buffer -> ONE barrier per step.
   // Operands of step t (r, z, n, hn, h_{t-1}, dL/dh_t: six 64-float rows per sequence row) are prefetched BWD_PF steps
   // ahead with cp.async into a shared-memory ring, so no global (L2) latency sits on the serial chain.
   __shared__ __align__(16) float ops_s[BWD_RING][RPC][6][MX_H];
-  __shared__ __align__(16) float dgh_s[RPC][MX_G];
-  __shared__ float part_s[RPC][3][MX_H];
-  const int j = threadIdx.x;
-  const int p = j / MX_H, k = j % MX_H;      // this thread sums rows p*64..p*64+63 of W_hh^T column k
+  __shared__ __align__(16) float dgh_s[2][RPC][MX_G];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int k = tid >> 2, p = tid & 3;
+  const int pw = p < 3 ? p : 0;
   const int row0 = blockIdx.x * RPC;
   float wT[MX_H];
 #pragma unroll
-  for (int jj = 0; jj < MX_H; ++jj) wT[jj] = a.theta[a.whh + (p * MX_H + jj) * MX_H + k];
+  for (int jj = 0; jj < MX_H; ++jj) wT[jj] = a.theta[a.whh + (pw * MX_H + jj) * MX_H + k];
   const int T1 = a.T + 1, N = a.N;
 
+  // prefetch assignment: RPC*96 16-byte pieces per step, up to two per thread
+  constexpr int NPIECE = (RPC * 96 + BWD_THREADS - 1) / BWD_THREADS;
+  const float* pf_src[NPIECE];
+  size_t pf_stride[NPIECE];
+  int pf_dst[NPIECE];       // float offset inside one ring slot, -1: no piece
+  bool pf_hprev[NPIECE];
+#pragma unroll
+  for (int u = 0; u < NPIECE; ++u) {
+    const int c = tid + u * BWD_THREADS;
+    pf_dst[u] = -1; pf_src[u] = nullptr; pf_stride[u] = 0; pf_hprev[u] = false;
+    if (c < RPC * 96) {
+      const int r = c / 96, rem = c % 96, op = rem / 16, q4 = rem % 16;
+      const int row = row0 + r;
+      pf_dst[u] = (r * 6 + op) * MX_H + 4 * q4;
+      if (row < a.R) {
+        const size_t m0 = ((size_t)(row / N) * T1) * N + (row % N);
+        if (op < 3) { pf_src[u] = a.gates + m0 * MX_G + op * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_G; }
+        else if (op == 3) { pf_src[u] = a.hn + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; }
+        else if (op == 4) { pf_src[u] = a.hall + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; pf_hprev[u] = true; }
+        else { pf_src[u] = a.dh_out + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; }
+      }
+    }
+  }
   auto prefetch = [&](int t) {
     if (t >= 0) {
-      for (int c = j; c < RPC * 6 * 16; c += MX_G) {            // 16-byte pieces: RPC rows x 6 operands x 16
-        const int r = c / 96, rem = c % 96, op = rem / 16, q4 = rem % 16;
-        const int row = row0 + r;
-        float* dst = &ops_s[t % BWD_RING][r][op][4 * q4];
-        if (row < a.R) {
-          const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
-          const float* src;
-          if (op < 3) src = a.gates + mm * MX_G + op * MX_H;
-          else if (op == 3) src = a.hn + mm * MX_H;
-          else if (op == 4) src = t > 0 ? a.hall + (mm - N) * MX_H : nullptr;
-          else src = a.dh_out + mm * MX_H;
-          if (src) mx_cp16(dst, src + 4 * q4);
+#pragma unroll
+      for (int u = 0; u < NPIECE; ++u) {
+        if (pf_dst[u] >= 0) {
+          float* dst = &ops_s[t % BWD_RING][0][0][0] + pf_dst[u];
+          const int ts = pf_hprev[u] ? t - 1 : t;            // h_{t-1} lives one step earlier; h_{-1} = 0
+          if (pf_src[u] && ts >= 0) mx_cp16(dst, pf_src[u] + (size_t)ts * pf_stride[u]);
           else mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
-        } else {
-          mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
         }
       }
     }
@@ -114,7 +133,7 @@ __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
 #pragma unroll
   for (int r = 0; r < RPC; ++r) carry[r] = 0.f;
   // zero the t == T rows of dgi
-  for (int idx = j; idx < RPC * MX_G; idx += MX_G) {
+  for (int idx = tid; idx < RPC * MX_G; idx += BWD_THREADS) {
     const int r = idx / MX_G, c = idx % MX_G;
     const int row = row0 + r;
     if (row < a.R) {
@@ -122,12 +141,22 @@ __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
       a.dgi[mm * MX_G + c] = 0.f;
     }
   }
+  size_t mrow[RPC];
+  bool valid[RPC];
+#pragma unroll
+  for (int r = 0; r < RPC; ++r) {
+    const int row = row0 + r;
+    valid[r] = row < a.R;
+    mrow[r] = valid[r] ? ((size_t)(row / N) * T1) * N + (row % N) : 0;
+  }
 #pragma unroll
   for (int d = 1; d <= BWD_PF; ++d) prefetch(a.T - d);
   mx_cp_wait<BWD_PF - 1>();
   __syncthreads();
+  const int q0 = lane & ~3;
   for (int t = a.T - 1; t >= 0; --t) {
-    prefetch(t - BWD_PF);              // slot (t-BWD_PF) % RING == (t+1) % RING: last read one full step ago
+    const int cur = t & 1;
+    prefetch(t - BWD_PF);              // slot (t-BWD_PF) % RING == (t+1) % RING: last read one full step (one barrier) ago
     if (p == 0) {
 #pragma unroll
       for (int r = 0; r < RPC; ++r) {
@@ -137,37 +166,38 @@ __global__ void __launch_bounds__(MX_G) k_gru_bwd(GruBwdArgs a) {
         const float d_n = dh * (1.f - zg) * (1.f - ng * ng);     // d pre-activation of n
         const float d_z = dh * (hp - ng) * zg * (1.f - zg);
         const float d_r = d_n * hn * rg * (1.f - rg);
-        dgh_s[r][k] = d_r; dgh_s[r][MX_H + k] = d_z; dgh_s[r][2 * MX_H + k] = d_n * rg;   // gradient reaching W_hn h + b_hn
+        dgh_s[cur][r][k] = d_r; dgh_s[cur][r][MX_H + k] = d_z; dgh_s[cur][r][2 * MX_H + k] = d_n * rg;   // reaches W_hn h + b_hn
         carry[r] = dh * zg;
-        const int row = row0 + r;
-        if (row < a.R) {
-          const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
+        if (valid[r]) {
+          const size_t mm = mrow[r] + (size_t)t * N;
           a.dgi[mm * MX_G + k] = d_r;
           a.dgi[mm * MX_G + MX_H + k] = d_z;
           a.dgi[mm * MX_G + 2 * MX_H + k] = d_n;
         }
       }
     }
-    __syncthreads();
+    mx_cp_wait<BWD_PF - 1>();   // operands of step t-1 have landed (the newer groups may still be in flight)
+    __syncthreads();            // publishes dgh_s[cur] and the ring slot of step t-1
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
+      float4 dv[MX_H / 4];
+#pragma unroll
+      for (int q = 0; q < MX_H / 4; ++q) dv[q] = mx_ld4(&dgh_s[cur][r][pw * MX_H + 4 * q]);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-      for (int jj = 0; jj < MX_H; jj += 4) {
-        const float4 d4 = mx_ld4(&dgh_s[r][p * MX_H + jj]);
-        a0 = fmaf(wT[jj], d4.x, a0);
-        a1 = fmaf(wT[jj + 1], d4.y, a1);
-        a2 = fmaf(wT[jj + 2], d4.z, a2);
-        a3 = fmaf(wT[jj + 3], d4.w, a3);
+      for (int q = 0; q < MX_H / 4; ++q) {
+        a0 = fmaf(wT[4 * q], dv[q].x, a0);
+        a1 = fmaf(wT[4 * q + 1], dv[q].y, a1);
+        a2 = fmaf(wT[4 * q + 2], dv[q].z, a2);
+        a3 = fmaf(wT[4 * q + 3], dv[q].w, a3);
       }
-      part_s[r][p][k] = (a0 + a1) + (a2 + a3);
+      float part = p < 3 ? (a0 + a1) + (a2 + a3) : 0.f;
+      const float s0 = __shfl_sync(0xffffffffu, part, q0);
+      const float s1 = __shfl_sync(0xffffffffu, part, q0 + 1);
+      const float s2 = __shfl_sync(0xffffffffu, part, q0 + 2);
+      carry[r] += (s0 + s1) + s2;       // dh_{t-1}[k] = z*dh + W_hh^T dgh   (used by lane p == 0)
     }
-    mx_cp_wait<BWD_PF - 1>();   // operands of step t-1 have landed (the newer groups may still be in flight)
-    __syncthreads();
-    if (p == 0) {
-#pragma unroll
-      for (int r = 0; r < RPC; ++r) carry[r] += part_s[r][0][k] + part_s[r][1][k] + part_s[r][2][k];
-    }
+    // the next step writes dgh_s[cur ^ 1]; readers of dgh_s[cur] are separated from its next writer by the next barrier
   }
   mx_cp_wait<0>();
 }
@@ -414,9 +444,9 @@ int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
   int rpc = 1;
   while (rpc < 4 && mx_ceil_div(a.R, rpc) > 2 * sms) rpc *= 2;
   dim3 grid(mx_ceil_div(a.R, rpc));
-  if (rpc == 1) MX_LAUNCH(k_gru_bwd<1>, grid, dim3(MX_G), 0, s, a);
-  else if (rpc == 2) MX_LAUNCH(k_gru_bwd<2>, grid, dim3(MX_G), 0, s, a);
-  else MX_LAUNCH(k_gru_bwd<4>, grid, dim3(MX_G), 0, s, a);
+  if (rpc == 1) MX_LAUNCH(k_gru_bwd<1>, grid, dim3(BWD_THREADS), 0, s, a);
+  else if (rpc == 2) MX_LAUNCH(k_gru_bwd<2>, grid, dim3(BWD_THREADS), 0, s, a);
+  else MX_LAUNCH(k_gru_bwd<4>, grid, dim3(BWD_THREADS), 0, s, a);
   MX_COUNT();
   MX_MARK("k_gru_bwd", s);
   return MX_CHECK_LAUNCH("gru_bwd");

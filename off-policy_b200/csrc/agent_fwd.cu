@@ -156,27 +156,29 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
 // =====================================================================================================
 #define GRU_PF 4                 // gi rows are prefetched this many steps ahead (L2 latency ~ 2-3 step times)
 #define GRU_RING (GRU_PF + 1)
+#define GRU_THREADS 256
 
 template <int RPC>
-__global__ void __launch_bounds__(MX_G) k_gru_fwd(GruFwdArgs a) {
-  // thread j owns gate row j of W_hh (registers) for the whole sequence: p = j/64 selects r / z / n, i = j%64 the unit.
-  // Per step: mat-vec (4 independent accumulators) -> r,z threads apply the sigmoid and publish -> barrier ->
-  // n threads finish tanh + the state update -> barrier.  Transcendentals are ex2/rcp based (abs err ~1e-7).
-  // The input-side pre-activations gi_t are streamed GRU_PF steps ahead with cp.async into a shared-memory ring.
-  __shared__ __align__(16) float h_s[RPC][MX_H];
-  __shared__ float rz_s[RPC][2 * MX_H];
+__global__ void __launch_bounds__(GRU_THREADS) k_gru_fwd(GruFwdArgs a) {
+  // Quad layout: thread = 4*i + p; unit i = 0..63, p = 0 (r gate) / 1 (z gate) / 2 (n gate) / 3 (helper: stores, prefetch).
+  // Thread (i,p<3) keeps row p*64+i of W_hh in registers for the whole sequence.  Per step: 16 broadcast LDS.128 of h,
+  // 64 FFMAs on 4 chains, sigmoid on the r/z lanes, r and z travel to the n lane by quad shuffles (no shared-memory
+  // round trip), the n lane finishes tanh + the state update into the OTHER h buffer -> ONE barrier per step.
+  // gi_t is streamed GRU_PF steps ahead with cp.async into a shared-memory ring.
+  __shared__ __align__(16) float h_s[2][RPC][MX_H];
   __shared__ __align__(16) float gi_s[GRU_RING][RPC][MX_G];
   const int net = blockIdx.y;
   const float* __restrict__ th = a.theta[net];
-  const int j = threadIdx.x;
-  const int p = j / MX_H, i = j % MX_H;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int i = tid >> 2, p = tid & 3;
+  const int gate_row = (p < 3 ? p : 0) * MX_H + i;
   const int row0 = blockIdx.x * RPC;
   const bool live = (net == 0);
   float w[MX_H];
 #pragma unroll
-  for (int k = 0; k < MX_H; ++k) w[k] = th[a.whh + j * MX_H + k];
-  const float bias = th[a.bhh + j];
-  for (int idx = j; idx < RPC * MX_H; idx += MX_G) (&h_s[0][0])[idx] = 0.f;   // h_0 = 0 (QMixPolicy.py:193-196)
+  for (int k = 0; k < MX_H; ++k) w[k] = th[a.whh + gate_row * MX_H + k];
+  const float bias = th[a.bhh + gate_row];
+  for (int idx = tid; idx < 2 * RPC * MX_H; idx += GRU_THREADS) (&h_s[0][0][0])[idx] = 0.f;   // h_0 = 0 (QMixPolicy.py:193-196)
 
   const float* gi = a.gi[net];
   float* hall = a.hall[net];
@@ -190,19 +192,21 @@ __global__ void __launch_bounds__(MX_G) k_gru_fwd(GruFwdArgs a) {
     const int b = valid[r] ? row / N : 0, n = valid[r] ? row % N : 0;
     mrow[r] = ((size_t)b * T1) * N + n;      // + t*N per step
   }
+  // prefetch assignment: RPC*48 16-byte pieces per step, at most one per thread (RPC <= 4)
+  const int pf_r = tid / (MX_G / 4), pf_q = tid % (MX_G / 4);
+  const bool pf_on = tid < RPC * (MX_G / 4);
+  const bool pf_valid = pf_on && (row0 + pf_r) < a.R;
+  const float* pf_src = gi;
+  if (pf_valid) {
+    const int row = row0 + pf_r;
+    pf_src = gi + (((size_t)(row / N) * T1) * N + (row % N)) * MX_G + 4 * pf_q;
+  }
+  const size_t pf_stride = (size_t)N * MX_G;
   auto prefetch = [&](int t) {
-    if (t < T1) {
-      for (int c = j; c < RPC * (MX_G / 4); c += MX_G) {
-        const int r = c / (MX_G / 4), q4 = c % (MX_G / 4);
-        const int row = row0 + r;
-        float* dst = &gi_s[t % GRU_RING][r][4 * q4];
-        if (row < a.R) {
-          const size_t mm = (((size_t)(row / N) * T1) + t) * N + (row % N);
-          mx_cp16(dst, gi + mm * MX_G + 4 * q4);
-        } else {
-          mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-      }
+    if (t < T1 && pf_on) {
+      float* dst = &gi_s[t % GRU_RING][pf_r][4 * pf_q];
+      if (pf_valid) mx_cp16(dst, pf_src + (size_t)t * pf_stride);
+      else mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     mx_cp_commit();
   };
@@ -211,46 +215,41 @@ __global__ void __launch_bounds__(MX_G) k_gru_fwd(GruFwdArgs a) {
   mx_cp_wait<GRU_PF - 1>();
   __syncthreads();
 
+  const int q0 = lane & ~3;
   for (int t = 0; t < T1; ++t) {
-    prefetch(t + GRU_PF);               // slot (t+GRU_PF) % RING == (t-1) % RING: last read in step t-1, two barriers ago
-    float acc[RPC], g_cur[RPC];
+    const int cur = t & 1, nxt = cur ^ 1;
+    prefetch(t + GRU_PF);               // slot (t+GRU_PF) % RING == (t-1) % RING: last read one full step (one barrier) ago
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
-      g_cur[r] = gi_s[t % GRU_RING][r][j];
+      const float g = gi_s[t % GRU_RING][r][gate_row];
+      float4 hv[MX_H / 4];
+#pragma unroll
+      for (int k = 0; k < MX_H / 4; ++k) hv[k] = mx_ld4(&h_s[cur][r][4 * k]);
       float a0 = bias, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-      for (int k = 0; k < MX_H; k += 4) {
-        const float4 h4 = mx_ld4(&h_s[r][k]);
-        a0 = fmaf(w[k], h4.x, a0);
-        a1 = fmaf(w[k + 1], h4.y, a1);
-        a2 = fmaf(w[k + 2], h4.z, a2);
-        a3 = fmaf(w[k + 3], h4.w, a3);
+      for (int k = 0; k < MX_H / 4; ++k) {
+        a0 = fmaf(w[4 * k], hv[k].x, a0);
+        a1 = fmaf(w[4 * k + 1], hv[k].y, a1);
+        a2 = fmaf(w[4 * k + 2], hv[k].z, a2);
+        a3 = fmaf(w[4 * k + 3], hv[k].w, a3);
       }
-      acc[r] = (a0 + a1) + (a2 + a3);
-    }
-    if (p < 2) {
-#pragma unroll
-      for (int r = 0; r < RPC; ++r) {
-        const float g = mx_sigmoid_fast(acc[r] + g_cur[r]);
-        rz_s[r][j] = g;
-        if (live && valid[r]) a.gates[(mrow[r] + (size_t)t * N) * MX_G + j] = g;
-      }
-    }
-    __syncthreads();
-    if (p == 2) {
-#pragma unroll
-      for (int r = 0; r < RPC; ++r) {
-        const float rg = rz_s[r][i], zg = rz_s[r][MX_H + i];
-        const float ng = mx_tanh_fast(g_cur[r] + rg * acc[r]);
-        const float hnew = (1.f - zg) * ng + zg * h_s[r][i];
-        h_s[r][i] = hnew;                      // every mat-vec read of h_s finished before the barrier above
-        if (valid[r]) {
-          const size_t mm = mrow[r] + (size_t)t * N;
-          hall[mm * MX_H + i] = hnew;
-          if (live) {
-            a.gates[mm * MX_G + 2 * MX_H + i] = ng;
-            a.hn[mm * MX_H + i] = acc[r];
-          }
+      const float acc = (a0 + a1) + (a2 + a3);            // p<2: W_h{r,z} h + b ; p==2: hn = W_hn h + b_hn
+      float val = acc;
+      if (p < 2) val = mx_sigmoid_fast(acc + g);
+      const float rg = __shfl_sync(0xffffffffu, val, q0);
+      const float zg = __shfl_sync(0xffffffffu, val, q0 + 1);
+      const float hn = __shfl_sync(0xffffffffu, val, q0 + 2);
+      const float hp = h_s[cur][r][i];
+      const float ng = mx_tanh_fast(g + rg * acc);        // meaningful on the n lane (its g is gi_n, its acc is hn)
+      const float hnew = (1.f - zg) * ng + zg * hp;
+      if (p == 2) h_s[nxt][r][i] = hnew;
+      if (valid[r]) {
+        const size_t mm = mrow[r] + (size_t)t * N;
+        if (p == 2) hall[mm * MX_H + i] = hnew;
+        if (live) {
+          if (p < 2) a.gates[mm * MX_G + gate_row] = val;
+          else if (p == 2) a.gates[mm * MX_G + 2 * MX_H + i] = ng;
+          else a.hn[mm * MX_H + i] = hn;
         }
       }
     }
@@ -368,9 +367,9 @@ int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s) {
   int rpc = 1;
   while (rpc < 4 && mx_ceil_div(a.R, rpc) * nets > 2 * sms) rpc *= 2;
   dim3 grid(mx_ceil_div(a.R, rpc), nets);
-  if (rpc == 1) MX_LAUNCH(k_gru_fwd<1>, grid, dim3(MX_G), 0, s, a);
-  else if (rpc == 2) MX_LAUNCH(k_gru_fwd<2>, grid, dim3(MX_G), 0, s, a);
-  else MX_LAUNCH(k_gru_fwd<4>, grid, dim3(MX_G), 0, s, a);
+  if (rpc == 1) MX_LAUNCH(k_gru_fwd<1>, grid, dim3(GRU_THREADS), 0, s, a);
+  else if (rpc == 2) MX_LAUNCH(k_gru_fwd<2>, grid, dim3(GRU_THREADS), 0, s, a);
+  else MX_LAUNCH(k_gru_fwd<4>, grid, dim3(GRU_THREADS), 0, s, a);
   MX_COUNT();
   MX_MARK("k_gru_fwd", s);
   return MX_CHECK_LAUNCH("gru_fwd");
