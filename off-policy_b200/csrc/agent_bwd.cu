@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
 #define BWD_THREADS 256
 
 template <int RPC>
-__global__ void __launch_bounds__(BWD_THREADS) k_gru_bwd(GruBwdArgs a) {
+__global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
   // Quad layout: thread = 4*k + p.  Thread (k, p<3) keeps W_hh[p*64 + jj][k], jj < 64 (a third of column k of W_hh^T)
   // in registers; the three partial sums of dh_{t-1}[k] meet by quad shuffles, lane p==0 does the gate derivatives
   // and publishes d(gh) into the OTHER shared buffer -> ONE barrier per step.
@@ -442,7 +442,7 @@ int mx_launch_qhead_bwd(const QHeadBwdArgs& a, int* nparts_used, cudaStream_t s)
 int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
   const int sms = mx_num_sms();
   int rpc = 1;
-  while (rpc < 4 && mx_ceil_div(a.R, rpc) > 2 * sms) rpc *= 2;
+  while (rpc < 4 && mx_ceil_div(a.R, rpc) > sms) rpc *= 2;
   dim3 grid(mx_ceil_div(a.R, rpc));
   if (rpc == 1) MX_LAUNCH(k_gru_bwd<1>, grid, dim3(BWD_THREADS), 0, s, a);
   else if (rpc == 2) MX_LAUNCH(k_gru_bwd<2>, grid, dim3(BWD_THREADS), 0, s, a);

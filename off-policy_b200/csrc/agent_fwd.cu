@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
 #define GRU_THREADS 256
 
 template <int RPC>
-__global__ void __launch_bounds__(GRU_THREADS) k_gru_fwd(GruFwdArgs a) {
+__global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
   // Quad layout: thread = 4*i + p; unit i = 0..63, p = 0 (r gate) / 1 (z gate) / 2 (n gate) / 3 (helper: stores, prefetch).
   // Thread (i,p<3) keeps row p*64+i of W_hh in registers for the whole sequence.  Per step: 16 broadcast LDS.128 of h,
   // 64 FFMAs on 4 chains, sigmoid on the r/z lanes, r and z travel to the n lane by quad shuffles (no shared-memory
@@ -219,9 +219,10 @@ __global__ void __launch_bounds__(GRU_THREADS) k_gru_fwd(GruFwdArgs a) {
   for (int t = 0; t < T1; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
     prefetch(t + GRU_PF);               // slot (t+GRU_PF) % RING == (t-1) % RING: last read one full step (one barrier) ago
+    float g[RPC], acc[RPC];
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
-      const float g = gi_s[t % GRU_RING][r][gate_row];
+      g[r] = gi_s[t % GRU_RING][r][gate_row];
       float4 hv[MX_H / 4];
 #pragma unroll
       for (int k = 0; k < MX_H / 4; ++k) hv[k] = mx_ld4(&h_s[cur][r][4 * k]);
@@ -233,23 +234,33 @@ __global__ void __launch_bounds__(GRU_THREADS) k_gru_fwd(GruFwdArgs a) {
         a2 = fmaf(w[4 * k + 2], hv[k].z, a2);
         a3 = fmaf(w[4 * k + 3], hv[k].w, a3);
       }
-      const float acc = (a0 + a1) + (a2 + a3);            // p<2: W_h{r,z} h + b ; p==2: hn = W_hn h + b_hn
-      float val = acc;
-      if (p < 2) val = mx_sigmoid_fast(acc + g);
-      const float rg = __shfl_sync(0xffffffffu, val, q0);
-      const float zg = __shfl_sync(0xffffffffu, val, q0 + 1);
-      const float hn = __shfl_sync(0xffffffffu, val, q0 + 2);
+      acc[r] = (a0 + a1) + (a2 + a3);            // p<2: W_h{r,z} h + b ; p==2: hn = W_hn h + b_hn
+    }
+    float val[RPC], hnew[RPC], ngv[RPC], hnv[RPC];
+#pragma unroll
+    for (int r = 0; r < RPC; ++r) {                // branch-free so the rows' transcendental chains interleave
+      const float sg = mx_sigmoid_fast(acc[r] + g[r]);
+      val[r] = p < 2 ? sg : acc[r];
+    }
+#pragma unroll
+    for (int r = 0; r < RPC; ++r) {
+      const float rg = __shfl_sync(0xffffffffu, val[r], q0);
+      const float zg = __shfl_sync(0xffffffffu, val[r], q0 + 1);
+      hnv[r] = __shfl_sync(0xffffffffu, val[r], q0 + 2);
       const float hp = h_s[cur][r][i];
-      const float ng = mx_tanh_fast(g + rg * acc);        // meaningful on the n lane (its g is gi_n, its acc is hn)
-      const float hnew = (1.f - zg) * ng + zg * hp;
-      if (p == 2) h_s[nxt][r][i] = hnew;
+      ngv[r] = mx_tanh_fast(g[r] + rg * acc[r]);   // meaningful on the n lane (its g is gi_n, its acc is hn)
+      hnew[r] = (1.f - zg) * ngv[r] + zg * hp;
+    }
+#pragma unroll
+    for (int r = 0; r < RPC; ++r) {
+      if (p == 2) h_s[nxt][r][i] = hnew[r];
       if (valid[r]) {
         const size_t mm = mrow[r] + (size_t)t * N;
-        if (p == 2) hall[mm * MX_H + i] = hnew;
+        if (p == 2) hall[mm * MX_H + i] = hnew[r];
         if (live) {
-          if (p < 2) a.gates[mm * MX_G + gate_row] = val;
-          else if (p == 2) a.gates[mm * MX_G + 2 * MX_H + i] = ng;
-          else a.hn[mm * MX_H + i] = hn;
+          if (p < 2) a.gates[mm * MX_G + gate_row] = val[r];
+          else if (p == 2) a.gates[mm * MX_G + 2 * MX_H + i] = ngv[r];
+          else a.hn[mm * MX_H + i] = hnv[r];
         }
       }
     }
@@ -364,8 +375,8 @@ int mx_launch_front_fwd(const FrontFwdArgs& a, int nets, cudaStream_t s) {
 
 int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s) {
   const int sms = mx_num_sms();
-  int rpc = 1;
-  while (rpc < 4 && mx_ceil_div(a.R, rpc) * nets > 2 * sms) rpc *= 2;
+  int rpc = 1;     // one resident CTA per SM (the kernel is register heavy): grow rows-per-CTA until the grid fits one wave
+  while (rpc < 4 && mx_ceil_div(a.R, rpc) * nets > sms) rpc *= 2;
   dim3 grid(mx_ceil_div(a.R, rpc), nets);
   if (rpc == 1) MX_LAUNCH(k_gru_fwd<1>, grid, dim3(GRU_THREADS), 0, s, a);
   else if (rpc == 2) MX_LAUNCH(k_gru_fwd<2>, grid, dim3(GRU_THREADS), 0, s, a);
