@@ -75,21 +75,27 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
 
 template <int RPC>
 __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
-  // Quad layout: thread = 4*k + p.  Thread (k, p<3) keeps W_hh[p*64 + jj][k], jj < 64 (a third of column k of W_hh^T)
-  // in registers; the three partial sums of dh_{t-1}[k] meet by quad shuffles, lane p==0 does the gate derivatives
-  // and publishes d(gh) into the OTHER shared buffer -> ONE barrier per step.
-  // Operands of step t (r, z, n, hn, h_{t-1}, dL/dh_t: six 64-float rows per sequence row) are prefetched BWD_PF steps
-  // ahead with cp.async into a shared-memory ring, so no global (L2) latency sits on the serial chain.
+  // dh_{t-1}[k] = z*dh + sum_{j<192} W_hh[j][k] dgh[j].  Thread = 8*kp + s owns the column pair k = 2kp, 2kp+1 restricted
+  // to the interleaved j-slice {32m + 4s + c : m < 6, c < 4} (2 x 24 weights in registers): 6 conflict-free LDS.128 per
+  // step (24 KB of shared->register traffic per row-step), two 24-FFMA chains, then an 8-lane xor-shuffle reduction.
+  // Lanes s = 0,1 of each octet do the gate derivatives of unit k = 2kp + s and publish d(gh) into the OTHER buffer ->
+  // ONE barrier per step.  Operands of step t (r, z, n, hn, h_{t-1}, dL/dh_t) are streamed BWD_PF steps ahead by cp.async.
   __shared__ __align__(16) float ops_s[BWD_RING][RPC][6][MX_H];
   __shared__ __align__(16) float dgh_s[2][RPC][MX_G];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int k = tid >> 2, p = tid & 3;
-  const int pw = p < 3 ? p : 0;
+  const int tid = threadIdx.x;
+  const int kp = tid >> 3, s = tid & 7;
   const int row0 = blockIdx.x * RPC;
-  float wT[MX_H];
+  float w0[24], w1[24];
 #pragma unroll
-  for (int jj = 0; jj < MX_H; ++jj) wT[jj] = a.theta[a.whh + (pw * MX_H + jj) * MX_H + k];
+  for (int m = 0; m < 6; ++m)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = 32 * m + 4 * s + c;
+      w0[4 * m + c] = a.theta[a.whh + j * MX_H + 2 * kp];
+      w1[4 * m + c] = a.theta[a.whh + j * MX_H + 2 * kp + 1];
+    }
   const int T1 = a.T + 1, N = a.N;
+  const int ku = 2 * kp + (s & 1);          // unit whose gate derivatives this lane computes (lanes s = 0, 1)
 
   // prefetch assignment: RPC*96 16-byte pieces per step, up to two per thread
   constexpr int NPIECE = (RPC * 96 + BWD_THREADS - 1) / BWD_THREADS;
@@ -153,26 +159,25 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
   for (int d = 1; d <= BWD_PF; ++d) prefetch(a.T - d);
   mx_cp_wait<BWD_PF - 1>();
   __syncthreads();
-  const int q0 = lane & ~3;
   for (int t = a.T - 1; t >= 0; --t) {
     const int cur = t & 1;
     prefetch(t - BWD_PF);              // slot (t-BWD_PF) % RING == (t+1) % RING: last read one full step (one barrier) ago
-    if (p == 0) {
+    if (s < 2) {
 #pragma unroll
       for (int r = 0; r < RPC; ++r) {
         const float* o = &ops_s[t % BWD_RING][r][0][0];
-        const float rg = o[k], zg = o[MX_H + k], ng = o[2 * MX_H + k], hn = o[3 * MX_H + k], hp = o[4 * MX_H + k];
-        const float dh = o[5 * MX_H + k] + carry[r];
+        const float rg = o[ku], zg = o[MX_H + ku], ng = o[2 * MX_H + ku], hn = o[3 * MX_H + ku], hp = o[4 * MX_H + ku];
+        const float dh = o[5 * MX_H + ku] + carry[r];
         const float d_n = dh * (1.f - zg) * (1.f - ng * ng);     // d pre-activation of n
         const float d_z = dh * (hp - ng) * zg * (1.f - zg);
         const float d_r = d_n * hn * rg * (1.f - rg);
-        dgh_s[cur][r][k] = d_r; dgh_s[cur][r][MX_H + k] = d_z; dgh_s[cur][r][2 * MX_H + k] = d_n * rg;   // reaches W_hn h + b_hn
+        dgh_s[cur][r][ku] = d_r; dgh_s[cur][r][MX_H + ku] = d_z; dgh_s[cur][r][2 * MX_H + ku] = d_n * rg;   // reaches W_hn h + b_hn
         carry[r] = dh * zg;
         if (valid[r]) {
           const size_t mm = mrow[r] + (size_t)t * N;
-          a.dgi[mm * MX_G + k] = d_r;
-          a.dgi[mm * MX_G + MX_H + k] = d_z;
-          a.dgi[mm * MX_G + 2 * MX_H + k] = d_n;
+          a.dgi[mm * MX_G + ku] = d_r;
+          a.dgi[mm * MX_G + MX_H + ku] = d_z;
+          a.dgi[mm * MX_G + 2 * MX_H + ku] = d_n;
         }
       }
     }
@@ -180,22 +185,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
     __syncthreads();            // publishes dgh_s[cur] and the ring slot of step t-1
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
-      float4 dv[MX_H / 4];
+      float4 dv[6];
 #pragma unroll
-      for (int q = 0; q < MX_H / 4; ++q) dv[q] = mx_ld4(&dgh_s[cur][r][pw * MX_H + 4 * q]);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int m = 0; m < 6; ++m) dv[m] = mx_ld4(&dgh_s[cur][r][32 * m + 4 * s]);
+      float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-      for (int q = 0; q < MX_H / 4; ++q) {
-        a0 = fmaf(wT[4 * q], dv[q].x, a0);
-        a1 = fmaf(wT[4 * q + 1], dv[q].y, a1);
-        a2 = fmaf(wT[4 * q + 2], dv[q].z, a2);
-        a3 = fmaf(wT[4 * q + 3], dv[q].w, a3);
+      for (int m = 0; m < 6; ++m) {
+        p0 = fmaf(w0[4 * m], dv[m].x, p0); p1 = fmaf(w1[4 * m], dv[m].x, p1);
+        p0 = fmaf(w0[4 * m + 1], dv[m].y, p0); p1 = fmaf(w1[4 * m + 1], dv[m].y, p1);
+        p0 = fmaf(w0[4 * m + 2], dv[m].z, p0); p1 = fmaf(w1[4 * m + 2], dv[m].z, p1);
+        p0 = fmaf(w0[4 * m + 3], dv[m].w, p0); p1 = fmaf(w1[4 * m + 3], dv[m].w, p1);
       }
-      float part = p < 3 ? (a0 + a1) + (a2 + a3) : 0.f;
-      const float s0 = __shfl_sync(0xffffffffu, part, q0);
-      const float s1 = __shfl_sync(0xffffffffu, part, q0 + 1);
-      const float s2 = __shfl_sync(0xffffffffu, part, q0 + 2);
-      carry[r] += (s0 + s1) + s2;       // dh_{t-1}[k] = z*dh + W_hh^T dgh   (used by lane p == 0)
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
+      carry[r] += (s & 1) ? p1 : p0;    // dh_{t-1}[ku] = z*dh + W_hh^T dgh   (meaningful on lanes s = 0, 1)
     }
     // the next step writes dgh_s[cur ^ 1]; readers of dgh_s[cur] are separated from its next writer by the next barrier
   }

@@ -160,24 +160,31 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
 
 template <int RPC>
 __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
-  // Quad layout: thread = 4*i + p; unit i = 0..63, p = 0 (r gate) / 1 (z gate) / 2 (n gate) / 3 (helper: stores, prefetch).
-  // Thread (i,p<3) keeps row p*64+i of W_hh in registers for the whole sequence.  Per step: 16 broadcast LDS.128 of h,
-  // 64 FFMAs on 4 chains, sigmoid on the r/z lanes, r and z travel to the n lane by quad shuffles (no shared-memory
-  // round trip), the n lane finishes tanh + the state update into the OTHER h buffer -> ONE barrier per step.
+  // K-split quad layout: thread = 4*i + q owns, for unit i, the r/z/n rows of W_hh restricted to the interleaved
+  // k-slice {16m + 4q + c : m,c < 4} (3 x 16 weights in registers).  Per step a thread reads only ITS 16 h values
+  // (4 conflict-free LDS.128 -> 16 KB of shared->register traffic per row-step instead of 64 KB), runs three
+  // 16-FFMA chains, and the quad completes the dot products with xor-shuffles.  Every lane of the quad then holds the
+  // full pre-activations, so the gates need no shared-memory exchange; h is double-buffered -> ONE barrier per step.
   // gi_t is streamed GRU_PF steps ahead with cp.async into a shared-memory ring.
   __shared__ __align__(16) float h_s[2][RPC][MX_H];
   __shared__ __align__(16) float gi_s[GRU_RING][RPC][MX_G];
   const int net = blockIdx.y;
   const float* __restrict__ th = a.theta[net];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int i = tid >> 2, p = tid & 3;
-  const int gate_row = (p < 3 ? p : 0) * MX_H + i;
+  const int tid = threadIdx.x;
+  const int i = tid >> 2, q = tid & 3;
   const int row0 = blockIdx.x * RPC;
   const bool live = (net == 0);
-  float w[MX_H];
+  float wr[16], wz[16], wn[16];
 #pragma unroll
-  for (int k = 0; k < MX_H; ++k) w[k] = th[a.whh + gate_row * MX_H + k];
-  const float bias = th[a.bhh + gate_row];
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = 16 * m + 4 * q + c;
+      wr[4 * m + c] = th[a.whh + i * MX_H + k];
+      wz[4 * m + c] = th[a.whh + (MX_H + i) * MX_H + k];
+      wn[4 * m + c] = th[a.whh + (2 * MX_H + i) * MX_H + k];
+    }
+  const float br = th[a.bhh + i], bz = th[a.bhh + MX_H + i], bn = th[a.bhh + 2 * MX_H + i];
   for (int idx = tid; idx < 2 * RPC * MX_H; idx += GRU_THREADS) (&h_s[0][0][0])[idx] = 0.f;   // h_0 = 0 (QMixPolicy.py:193-196)
 
   const float* gi = a.gi[net];
@@ -215,52 +222,46 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
   mx_cp_wait<GRU_PF - 1>();
   __syncthreads();
 
-  const int q0 = lane & ~3;
   for (int t = 0; t < T1; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
     prefetch(t + GRU_PF);               // slot (t+GRU_PF) % RING == (t-1) % RING: last read one full step (one barrier) ago
-    float g[RPC], acc[RPC];
+    float pr[RPC], pz[RPC], pn[RPC];
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
-      g[r] = gi_s[t % GRU_RING][r][gate_row];
-      float4 hv[MX_H / 4];
+      float4 hv[4];
 #pragma unroll
-      for (int k = 0; k < MX_H / 4; ++k) hv[k] = mx_ld4(&h_s[cur][r][4 * k]);
-      float a0 = bias, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int m = 0; m < 4; ++m) hv[m] = mx_ld4(&h_s[cur][r][16 * m + 4 * q]);
+      float sr = 0.f, sz = 0.f, sn = 0.f;
 #pragma unroll
-      for (int k = 0; k < MX_H / 4; ++k) {
-        a0 = fmaf(w[4 * k], hv[k].x, a0);
-        a1 = fmaf(w[4 * k + 1], hv[k].y, a1);
-        a2 = fmaf(w[4 * k + 2], hv[k].z, a2);
-        a3 = fmaf(w[4 * k + 3], hv[k].w, a3);
+      for (int m = 0; m < 4; ++m) {
+        sr = fmaf(wr[4 * m], hv[m].x, sr); sz = fmaf(wz[4 * m], hv[m].x, sz); sn = fmaf(wn[4 * m], hv[m].x, sn);
+        sr = fmaf(wr[4 * m + 1], hv[m].y, sr); sz = fmaf(wz[4 * m + 1], hv[m].y, sz); sn = fmaf(wn[4 * m + 1], hv[m].y, sn);
+        sr = fmaf(wr[4 * m + 2], hv[m].z, sr); sz = fmaf(wz[4 * m + 2], hv[m].z, sz); sn = fmaf(wn[4 * m + 2], hv[m].z, sn);
+        sr = fmaf(wr[4 * m + 3], hv[m].w, sr); sz = fmaf(wz[4 * m + 3], hv[m].w, sz); sn = fmaf(wn[4 * m + 3], hv[m].w, sn);
       }
-      acc[r] = (a0 + a1) + (a2 + a3);            // p<2: W_h{r,z} h + b ; p==2: hn = W_hn h + b_hn
-    }
-    float val[RPC], hnew[RPC], ngv[RPC], hnv[RPC];
-#pragma unroll
-    for (int r = 0; r < RPC; ++r) {                // branch-free so the rows' transcendental chains interleave
-      const float sg = mx_sigmoid_fast(acc[r] + g[r]);
-      val[r] = p < 2 ? sg : acc[r];
+      pr[r] = sr; pz[r] = sz; pn[r] = sn;
     }
 #pragma unroll
-    for (int r = 0; r < RPC; ++r) {
-      const float rg = __shfl_sync(0xffffffffu, val[r], q0);
-      const float zg = __shfl_sync(0xffffffffu, val[r], q0 + 1);
-      hnv[r] = __shfl_sync(0xffffffffu, val[r], q0 + 2);
-      const float hp = h_s[cur][r][i];
-      ngv[r] = mx_tanh_fast(g[r] + rg * acc[r]);   // meaningful on the n lane (its g is gi_n, its acc is hn)
-      hnew[r] = (1.f - zg) * ngv[r] + zg * hp;
+    for (int r = 0; r < RPC; ++r) {        // quad all-reduce of the three partial dot products
+      pr[r] += __shfl_xor_sync(0xffffffffu, pr[r], 1); pz[r] += __shfl_xor_sync(0xffffffffu, pz[r], 1); pn[r] += __shfl_xor_sync(0xffffffffu, pn[r], 1);
+      pr[r] += __shfl_xor_sync(0xffffffffu, pr[r], 2); pz[r] += __shfl_xor_sync(0xffffffffu, pz[r], 2); pn[r] += __shfl_xor_sync(0xffffffffu, pn[r], 2);
     }
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
-      if (p == 2) h_s[nxt][r][i] = hnew[r];
+      const float* g = &gi_s[t % GRU_RING][r][0];
+      const float rg = mx_sigmoid_fast(pr[r] + br + g[i]);
+      const float zg = mx_sigmoid_fast(pz[r] + bz + g[MX_H + i]);
+      const float hn = pn[r] + bn;
+      const float ng = mx_tanh_fast(g[2 * MX_H + i] + rg * hn);
+      const float hnew = (1.f - zg) * ng + zg * h_s[cur][r][i];
+      if (q == 0) h_s[nxt][r][i] = hnew;
       if (valid[r]) {
         const size_t mm = mrow[r] + (size_t)t * N;
-        if (p == 2) hall[mm * MX_H + i] = hnew[r];
+        if (q == 0) hall[mm * MX_H + i] = hnew;
         if (live) {
-          if (p < 2) a.gates[mm * MX_G + gate_row] = val[r];
-          else if (p == 2) a.gates[mm * MX_G + 2 * MX_H + i] = ngv[r];
-          else a.hn[mm * MX_H + i] = hnv[r];
+          if (q == 1) { a.gates[mm * MX_G + i] = rg; a.gates[mm * MX_G + MX_H + i] = zg; }
+          else if (q == 2) a.gates[mm * MX_G + 2 * MX_H + i] = ng;
+          else if (q == 3) a.hn[mm * MX_H + i] = hn;
         }
       }
     }
