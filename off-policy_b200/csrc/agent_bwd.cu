@@ -445,7 +445,7 @@ int mx_launch_qhead_bwd(const QHeadBwdArgs& a, int* nparts_used, cudaStream_t s)
 int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
   const int sms = mx_num_sms();
   int rpc = 1;
-  while (rpc < 4 && mx_ceil_div(a.R, rpc) > sms) rpc *= 2;
+  while (rpc < 4 && mx_ceil_div(a.R, rpc) > 2 * sms) rpc *= 2;
   dim3 grid(mx_ceil_div(a.R, rpc));
   if (rpc == 1) MX_LAUNCH(k_gru_bwd<1>, grid, dim3(BWD_THREADS), 0, s, a);
   else if (rpc == 2) MX_LAUNCH(k_gru_bwd<2>, grid, dim3(BWD_THREADS), 0, s, a);
