@@ -170,7 +170,7 @@ def gen_replay(name="replay_small"):
     print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "maddpg" not in sys.argv[1:]:
     torch.set_num_threads(1)
     small = QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48)
     gen_qmix("qmix_small", small)
@@ -179,3 +179,82 @@ if __name__ == "__main__":
     gen_qmix("qmix_small_hyper1", QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48, hyper_layers=1), steps=1)
     gen_qmix("qmix_5ag", QmixConfig(n_agents=5, obs_dim=17, act_dim=11, state_dim=23), B=3, T=6, steps=1)
     gen_replay()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# recurrent MADDPG / MATD3 (Box actions; shared centralised observation)
+# ---------------------------------------------------------------------------------------------------------------
+def gen_maddpg(name, cfg, flags=(), B=4, T=6, steps=2, per=False):
+    from oracle.maddpg import synth_batch_cont
+    rh.import_reference()
+    sp = rh.gym_spaces()
+    algo = "rmatd3" if cfg.td3 else "rmaddpg"
+    args = rh.make_args(["--algorithm_name", algo, "--hidden_size", str(cfg.hidden), "--gain", str(cfg.gain), "--lr", str(cfg.lr)] + list(flags))
+    if cfg.td3:
+        from offpolicy.algorithms.r_matd3.algorithm.rMATD3Policy import R_MATD3Policy as Policy
+        from offpolicy.algorithms.r_matd3.r_matd3 import R_MATD3 as Trainer
+    else:
+        from offpolicy.algorithms.r_maddpg.algorithm.rMADDPGPolicy import R_MADDPGPolicy as Policy
+        from offpolicy.algorithms.r_maddpg.r_maddpg import R_MADDPG as Trainer
+    torch.manual_seed(1)
+    np.random.seed(1)
+    info = dict(obs_space=sp.Box(-np.inf, np.inf, (cfg.obs_dim,)), share_obs_space=sp.Box(-np.inf, np.inf, (cfg.state_dim,)),
+                act_space=sp.Box(-1.0, 1.0, (cfg.act_dim,)), cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
+    dev = torch.device("cpu")
+    pol = Policy({"args": args, "device": dev}, info)
+    tr = Trainer(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=dev, episode_length=T)
+    randomize_all(pol.actor, 21); randomize_all(pol.critic, 22)
+    pol.hard_target_updates()
+    randomize_all(pol.target_actor, 23, scale=0.05); randomize_all(pol.target_critic, 24, scale=0.05)
+    out = {}
+    for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
+        out.update(sd_np("init.%s." % tag, mod))
+    for s in range(steps):
+        b = synth_batch_cont(cfg, B, T, seed=200 + s)
+        for k, v in zip(["obs", "share", "acts", "rew", "dones", "dones_env"], b[:6]):
+            out["s%d.in.%s" % (s, k)] = v
+        w = idx = None
+        if per:
+            w = np.random.RandomState(9 + s).rand(B) * 0.9 + 0.1
+            idx = np.arange(B)
+            out["s%d.in.weights" % s] = w
+        d = lambda x: {"policy_0": x}
+        batch = (d(b[0]), d(b[1]), d(b[2]), d(b[3]), d(b[4]), d(b[5]), d(None), w, idx)
+        torch.manual_seed(1000 + s)
+        if cfg.td3:
+            out["s%d.in.noise" % s] = torch.empty(T + 1, cfg.n_agents * B, cfg.act_dim).normal_(mean=0, std=float(args.target_action_noise_std)).numpy()
+            torch.manual_seed(1000 + s)
+        info_t, prio, _ = tr.shared_train_policy_on_batch("policy_0", batch)
+        out["s%d.critic_loss" % s] = info_t["critic_loss"].detach().numpy()
+        out["s%d.critic_grad_norm" % s] = np.asarray(float(info_t["critic_grad_norm"]), np.float32)
+        out["s%d.update_actor" % s] = np.asarray(int(info_t["update_actor"]))
+        if info_t["update_actor"]:
+            out["s%d.actor_loss" % s] = info_t["actor_loss"].detach().numpy()
+            out["s%d.actor_grad_norm" % s] = np.asarray(float(info_t["actor_grad_norm"]), np.float32)
+            for k, p in pol.actor.named_parameters():
+                if p.grad is not None:
+                    out["s%d.grad.actor.%s" % (s, k)] = p.grad.numpy().copy()
+        if prio is not None:
+            out["s%d.prio" % s] = np.asarray(prio)
+        if info_t["update_actor"]:
+            pol.soft_target_updates()           # runner: base_runner.py:250-252
+        if s == steps - 1:      # parameters only after the last step (keeps the fixture small)
+            for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
+                out.update(sd_np("final.%s." % tag, mod))
+    out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, cfg.hidden, B, T, steps, int(cfg.td3), int(per)])
+    out["meta.hparams"] = np.array([args.gamma, args.lr, args.opti_eps, args.max_grad_norm, args.tau, args.huber_delta, args.per_nu,
+                                    args.per_eps, float(args.target_action_noise_std), args.weight_decay], dtype=np.float64)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024), "critic_loss", out["s0.critic_loss"])
+
+
+def main_maddpg():
+    from oracle.maddpg import MaddpgConfig
+    gen_maddpg("maddpg_box", MaddpgConfig())
+    gen_maddpg("matd3_box", MaddpgConfig(td3=True, actor_update_interval=2))
+    gen_maddpg("maddpg_box_per", MaddpgConfig(use_per=True), flags=["--use_per"], per=True, steps=1)
+
+
+if __name__ == "__main__" and "maddpg" in sys.argv[1:]:
+    main_maddpg()

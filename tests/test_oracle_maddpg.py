@@ -1,0 +1,51 @@
+"""Pin oracle/maddpg.py against outputs of the unmodified reference (tests/golden/ma*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, sub, rel_err
+
+
+def maddpg_from_golden(g):
+    from oracle.maddpg import MaddpgConfig, MaddpgLearner
+    n, o, a, s, h, B, T, steps, td3, per = [int(v) for v in g["meta.cfg"]]
+    gamma, lr, eps, mgn, tau, hd, nu, peps, tn, wd = [float(v) for v in g["meta.hparams"]]
+    cfg = MaddpgConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, hidden=h, gamma=gamma, lr=lr, opti_eps=eps, max_grad_norm=mgn,
+                       tau=tau, huber_delta=hd, per_nu=nu, per_eps=peps, td3=bool(td3), target_noise=tn, weight_decay=wd,
+                       use_per=bool(per), actor_update_interval=2 if td3 else 1)
+    L = MaddpgLearner(cfg)
+    for tag, mod in (("actor", L.actor), ("critic", L.critic), ("tgt_actor", L.tgt_actor), ("tgt_critic", L.tgt_critic)):
+        mod.load_state_dict(sub(g, "init.%s." % tag))
+    return L, cfg, B, T, steps
+
+
+def maddpg_batch(g, s):
+    b = tuple(g["s%d.in.%s" % (s, k)] for k in ("obs", "share", "acts", "rew", "dones", "dones_env"))
+    w = g.get("s%d.in.weights" % s)
+    return b + (None, w, np.arange(b[0].shape[2]) if w is not None else None), g.get("s%d.in.noise" % s)
+
+
+@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_box_per"])
+def test_oracle_reproduces_reference_maddpg(name):
+    torch.set_num_threads(1)
+    g = load_golden(name)
+    L, cfg, B, T, steps = maddpg_from_golden(g)
+    for s in range(steps):
+        batch, noise = maddpg_batch(g, s)
+        info, prio = L.step(batch, noise)
+        assert rel_err(info["critic_loss"], g["s%d.critic_loss" % s]) < 1e-6
+        assert rel_err(info["critic_grad_norm"], g["s%d.critic_grad_norm" % s]) < 1e-5
+        assert int(info["update_actor"]) == int(g["s%d.update_actor" % s])
+        if info["update_actor"]:
+            assert rel_err(info["actor_loss"], g["s%d.actor_loss" % s]) < 1e-5
+            assert rel_err(info["actor_grad_norm"], g["s%d.actor_grad_norm" % s]) < 1e-5
+            for k, gr in L.actor_grads.items():
+                key = "s%d.grad.actor.%s" % (s, k)
+                if key in g:
+                    assert rel_err(gr, g[key]) < 2e-5, key
+            L.soft_update()
+        if cfg.use_per:
+            assert rel_err(prio, g["s%d.prio" % s]) < 1e-5
+    for tag, mod in (("actor", L.actor), ("critic", L.critic), ("tgt_actor", L.tgt_actor), ("tgt_critic", L.tgt_critic)):
+        for k, v in mod.state_dict().items():
+            assert rel_err(v, g["final.%s.%s" % (tag, k)]) < 5e-6, (tag, k)
