@@ -203,6 +203,43 @@ const float* mx_qmix_priorities(mx_qmix* q);
 int mx_qmix_soft_update(mx_qmix* q, void* stream);   /* qmix.py:211-216 + util.py:123-134 (all registered params) */
 int mx_qmix_hard_update(mx_qmix* q, void* stream);   /* qmix.py:203-209 */
 
+/* ------------------------------------------------------------------------------------------------
+ * Recurrent MADDPG / MATD3 learner (shared centralised observation, continuous actions).
+ * Replaces R_MADDPG.shared_train_policy_on_batch / get_update_info (offpolicy/algorithms/r_maddpg/r_maddpg.py:44-331),
+ * R_MADDPG_Actor / R_MADDPG_Critic forward (r_maddpg/algorithm/r_actor_critic.py:7-130), the two Adam steps and
+ * soft/hard target updates of R_MADDPGPolicy (rMADDPGPolicy.py:53-54,162-170), and the R_MATD3 variants
+ * (r_matd3/*: two Q heads, actor every 2nd update, Gaussian target-action noise).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mx_maddpg mx_maddpg;
+typedef struct mx_maddpg_cfg {
+  int32_t n_agents, obs_dim, act_dim, state_dim;   /* act_dim: width of one agent's continuous action; state_dim = cent_obs_dim */
+  int32_t hidden;                 /* must be 64 */
+  int32_t episode_len, max_batch;
+  int32_t num_q;                  /* Q heads: 1 (MADDPG) or 2 (MATD3)                    r_actor_critic.py:93 */
+  int32_t actor_update_interval;  /* 1 (MADDPG) or 2 (MATD3)                             r_maddpg.py:125      */
+  int32_t use_huber, use_per;
+  float gamma, huber_delta, per_nu, per_eps;
+  float lr, adam_beta1, adam_beta2, adam_eps, max_grad_norm, tau, weight_decay;
+  float target_noise;             /* > 0: the caller passes N(0, target_noise) samples for the target actions (MATD3) */
+} mx_maddpg_cfg;
+/* which = 0: actor ("rnn.*", "act.action_out.*"), 1: critic ("rnn.*", "q_outs.k.*"); names = reference state_dict keys */
+int mx_maddpg_param_layout(const mx_maddpg_cfg* cfg, int32_t which, mx_param_entry* out, int32_t max_entries, int64_t* total_floats);
+int64_t mx_maddpg_workspace_bytes(const mx_maddpg_cfg* cfg);
+/* actor_vecs / critic_vecs: {theta, theta_target, adam_m, adam_v}, each of the layout's total_floats; workspace zero-filled */
+int mx_maddpg_create(const mx_maddpg_cfg* cfg, float* const actor_vecs[4], float* const critic_vecs[4], void* workspace,
+                     int64_t workspace_bytes, mx_maddpg** out);
+void mx_maddpg_destroy(mx_maddpg* h);
+/* One update = shared_train_policy_on_batch: critic update, then (every actor_update_interval-th call) the actor update with
+ * the updated critic.  target_noise_dev: fp32 [(T+1)][B][N][act_dim] in batch row order (row = (b*(T+1)+t)*N + n) or NULL.
+ * *update_actor_out tells the caller whether the actor was updated (train_info['update_actor']). */
+int mx_maddpg_step(mx_maddpg* h, const mx_batch* batch, const float* target_noise_dev, int32_t* update_actor_out, void* stream);
+/* device fp32[8]: critic_loss, critic_grad_norm, -, denom, actor_loss, actor_grad_norm, -, denom */
+const float* mx_maddpg_info(mx_maddpg* h);
+const float* mx_maddpg_priorities(mx_maddpg* h);
+int mx_maddpg_grad_views(mx_maddpg* h, int64_t* actor_off_bytes, int64_t* critic_off_bytes);   /* parity tests: numerator grads in the workspace */
+int mx_maddpg_soft_update(mx_maddpg* h, void* stream);   /* rMADDPGPolicy.py:162-165 */
+int mx_maddpg_hard_update(mx_maddpg* h, void* stream);   /* rMADDPGPolicy.py:167-170 */
+
 /* Debug / parity: look up a named fp32 (or int32) region of the workspace written by the last step.
  * Returns byte offset into the workspace and element count; names are listed in DESIGN.md. */
 int mx_qmix_ws_lookup(const mx_qmix* q, const char* name, int64_t* byte_offset, int64_t* n_elems);

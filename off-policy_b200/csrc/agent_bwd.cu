@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
       w0[4 * m + c] = a.theta[a.whh + j * MX_H + 2 * kp];
       w1[4 * m + c] = a.theta[a.whh + j * MX_H + 2 * kp + 1];
     }
-  const int T1 = a.T + 1, N = a.N;
+  const int T1 = a.T1 > 0 ? a.T1 : a.T + 1, N = a.N;
   const int ku = 2 * kp + (s & 1);          // unit whose gate derivatives this lane computes (lanes s = 0, 1)
 
   // prefetch assignment: RPC*96 16-byte pieces per step, up to two per thread
@@ -103,10 +103,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
   size_t pf_stride[NPIECE];
   int pf_dst[NPIECE];       // float offset inside one ring slot, -1: no piece
   bool pf_hprev[NPIECE];
+  const float* pf_h0[NPIECE];
 #pragma unroll
   for (int u = 0; u < NPIECE; ++u) {
     const int c = tid + u * BWD_THREADS;
-    pf_dst[u] = -1; pf_src[u] = nullptr; pf_stride[u] = 0; pf_hprev[u] = false;
+    pf_dst[u] = -1; pf_src[u] = nullptr; pf_stride[u] = 0; pf_hprev[u] = false; pf_h0[u] = nullptr;
     if (c < RPC * 96) {
       const int r = c / 96, rem = c % 96, op = rem / 16, q4 = rem % 16;
       const int row = row0 + r;
@@ -115,7 +116,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
         const size_t m0 = ((size_t)(row / N) * T1) * N + (row % N);
         if (op < 3) { pf_src[u] = a.gates + m0 * MX_G + op * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_G; }
         else if (op == 3) { pf_src[u] = a.hn + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; }
-        else if (op == 4) { pf_src[u] = a.hall + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; pf_hprev[u] = true; }
+        else if (op == 4) { pf_src[u] = a.hall + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; pf_hprev[u] = true;
+                            if (a.h0) pf_h0[u] = a.h0 + (size_t)row * MX_H + 4 * q4; }
         else { pf_src[u] = a.dh_out + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; }
       }
     }
@@ -126,8 +128,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
       for (int u = 0; u < NPIECE; ++u) {
         if (pf_dst[u] >= 0) {
           float* dst = &ops_s[t % BWD_RING][0][0][0] + pf_dst[u];
-          const int ts = pf_hprev[u] ? t - 1 : t;            // h_{t-1} lives one step earlier; h_{-1} = 0
+          const int ts = pf_hprev[u] ? t - 1 : t;            // h_{t-1} lives one step earlier; h_{-1} = h0 (or 0)
           if (pf_src[u] && ts >= 0) mx_cp16(dst, pf_src[u] + (size_t)ts * pf_stride[u]);
+          else if (pf_h0[u]) mx_cp16(dst, pf_h0[u]);
           else mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
         }
       }
@@ -138,15 +141,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
   float carry[RPC];
 #pragma unroll
   for (int r = 0; r < RPC; ++r) carry[r] = 0.f;
-  // zero the t == T rows of dgi
-  for (int idx = tid; idx < RPC * MX_G; idx += BWD_THREADS) {
-    const int r = idx / MX_G, c = idx % MX_G;
-    const int row = row0 + r;
-    if (row < a.R) {
-      const size_t mm = (((size_t)(row / N) * T1) + a.T) * N + (row % N);
-      a.dgi[mm * MX_G + c] = 0.f;
+  // zero the rows of dgi that receive no gradient (t >= TB; for QMIX: the bootstrap step t == T)
+  for (int tz = a.T; tz < T1; ++tz)
+    for (int idx = tid; idx < RPC * MX_G; idx += BWD_THREADS) {
+      const int r = idx / MX_G, c = idx % MX_G;
+      const int row = row0 + r;
+      if (row < a.R) {
+        const size_t mm = (((size_t)(row / N) * T1) + tz) * N + (row % N);
+        a.dgi[mm * MX_G + c] = 0.f;
+      }
     }
-  }
   size_t mrow[RPC];
   bool valid[RPC];
 #pragma unroll
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
 // =====================================================================================================
 struct FrontBwdSmem {
   int ldi, ld64, ldg;
-  int o_dgi, o_dgn, o_x, o_hp, o_u, o_da, o_x0, o_xh0, o_wc, o_col, o_stat, o_lnp, total;
+  int o_dgi, o_dgn, o_x, o_hp, o_u, o_da, o_x0, o_xh0, o_dx0, o_wc, o_col, o_stat, o_lnp, total;
 };
 static FrontBwdSmem front_bwd_smem(int in_dim, int TM) {
   FrontBwdSmem s;
@@ -225,6 +229,7 @@ static FrontBwdSmem front_bwd_smem(int in_dim, int TM) {
   s.o_da = o; o += TM * s.ld64;     // gradient w.r.t. the Linear output (after ReLU mask)
   s.o_x0 = o; o += TM * s.ldi;      // raw input rows, then LN0 output (fc1 input)
   s.o_xh0 = o; o += TM * s.ldi;     // normalised input before the affine
+  s.o_dx0 = o; o += TM * s.ldi;     // gradient w.r.t. the LN0 output (only when the input gradient is requested)
   s.o_wc = o; o += 64 * s.ld64;
   s.o_col = o; o += 2 * I64 + 4 * 64;   // column accumulators for LayerNorm gains/biases
   s.o_stat = o; o += 3 * TM * 2;        // (mean, rstd) of LN0 / LN1 / LN2 for the tile rows
@@ -281,8 +286,10 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
   float* ln1g_s = smem + sm.o_lnp; float* ln1b_s = ln1g_s + 64; float* ln2g_s = ln1b_s + 64; float* ln2b_s = ln2g_s + 64;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int ntiles = (a.M + TM - 1) / TM;
-  const int T1 = a.T + 1, N = a.N;
+  const int T1 = a.T1 > 0 ? a.T1 : a.T + 1, N = a.N;
   const bool ldx_vec = (a.ldx & 3) == 0;
+  const bool wg = !a.skip_wgrad;
+  float* dx0_s = smem + sm.o_dx0;
   float* gp = a.gpart + (size_t)blockIdx.x * a.P;
   for (int i = tid; i < 2 * I64 + 4 * 64; i += MX_TILE_THREADS) col0g[i] = 0.f;
   if (tid < 64) { ln1g_s[tid] = th[L.ln1_g + tid]; ln1b_s[tid] = th[L.ln1_b + tid]; ln2g_s[tid] = th[L.ln2_g + tid]; ln2b_s[tid] = th[L.ln2_b + tid]; }
@@ -301,6 +308,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
       const bool has = m < a.M && ((m / N) % T1) > 0;
       float* d = hp_s + r * sm.ld64 + 4 * tx;
       if (has) mx_cp16(d, a.hall + (size_t)(m - N) * MX_H + 4 * tx);
+      else if (m < a.M && a.h0) mx_cp16(d, a.h0 + (size_t)m * MX_H + 4 * tx);
       else mx_st4(d, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     if (ldx_vec) mx_stage_rows(x0_s, sm.ldi, a.X, a.ldx, m0, a.M, TM, mx_round_up(I, 4));
@@ -321,15 +329,17 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     }
     __syncthreads();
     // ---- GRU weight gradients: dW_ih = dgi^T x2 ; dW_hh = [dgi_r, dgi_z, dgi_n*r]^T h_{t-1} ----
-    for (int nb = 0; nb < 3; ++nb) {
-      mx_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
-      const float* dgh = nb < 2 ? dgi_s + nb * 64 : dgn_s;
-      const int ldd = nb < 2 ? sm.ldg : sm.ld64;
-      mx_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
+    if (wg) {
+      for (int nb = 0; nb < 3; ++nb) {
+        mx_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
+        const float* dgh = nb < 2 ? dgi_s + nb * 64 : dgn_s;
+        const int ldd = nb < 2 ? sm.ldg : sm.ld64;
+        mx_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
+      }
+      mx_colsum(dgi_s, sm.ldg, TM, MX_G, gp + L.bih, accum);
+      mx_colsum(dgi_s, sm.ldg, TM, 2 * MX_H, gp + L.bhh, accum);
+      mx_colsum(dgn_s, sm.ld64, TM, MX_H, gp + L.bhh + 2 * MX_H, accum);
     }
-    mx_colsum(dgi_s, sm.ldg, TM, MX_G, gp + L.bih, accum);
-    mx_colsum(dgi_s, sm.ldg, TM, 2 * MX_H, gp + L.bhh, accum);
-    mx_colsum(dgn_s, sm.ld64, TM, MX_H, gp + L.bhh + 2 * MX_H, accum);
     // ---- dx2 = dgi . W_ih  (three 64-row chunks) ----
     float v[RM][4];
 #pragma unroll
@@ -358,8 +368,10 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     }
     __syncthreads();
     // ---- fc2: dW2 = da2^T x1, db2 ; dx1 = da2 . W2 ----
-    mx_wgrad_block(da_s, sm.ld64, x_s, sm.ld64, TM, gp + L.w2, MX_H, MX_H, 0, 0, accum);
-    mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b2, accum);
+    if (wg) {
+      mx_wgrad_block(da_s, sm.ld64, x_s, sm.ld64, TM, gp + L.w2, MX_H, MX_H, 0, 0, accum);
+      mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b2, accum);
+    }
     mx_stage_weight(Wc, sm.ld64, th + L.w2, MX_H, MX_H, MX_H, 0, 0, 64);
     __syncthreads();
 #pragma unroll
@@ -386,9 +398,11 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     }
     __syncthreads();
     // ---- fc1: dW1 = da1^T x0, db1 ; dx0 = da1 . W1 (only for the LN0 gain/bias) ----
-    for (int kb = 0; kb * 64 < I; ++kb) mx_wgrad_block(da_s, sm.ld64, x0_s + kb * 64, sm.ldi, TM, gp + L.w1, MX_H, I, 0, kb * 64, accum);
-    mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b1, accum);
-    if (a.feature_norm) {
+    if (wg) {
+      for (int kb = 0; kb * 64 < I; ++kb) mx_wgrad_block(da_s, sm.ld64, x0_s + kb * 64, sm.ldi, TM, gp + L.w1, MX_H, I, 0, kb * 64, accum);
+      mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b1, accum);
+    }
+    if (a.feature_norm || a.dX) {
       for (int kb = 0; kb * 64 < I; ++kb) {
         __syncthreads();
         mx_stage_weight(Wc, sm.ld64, th + L.w1, MX_H, I, I, 0, kb * 64, 64);
@@ -404,9 +418,31 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
           if (c < I) {
             float sg = 0.f, sb = 0.f;
 #pragma unroll
-            for (int i = 0; i < RM; ++i) { sg = fmaf(v[i][jx], xh0_s[(ty * RM + i) * sm.ldi + c], sg); sb += v[i][jx]; }
-            atomicAdd(&col0g[c], sg);
-            atomicAdd(&col0b[c], sb);
+            for (int i = 0; i < RM; ++i) {
+              sg = fmaf(v[i][jx], xh0_s[(ty * RM + i) * sm.ldi + c], sg); sb += v[i][jx];
+              if (a.dX) dx0_s[(ty * RM + i) * sm.ldi + c] = v[i][jx];
+            }
+            if (wg && a.feature_norm) { atomicAdd(&col0g[c], sg); atomicAdd(&col0b[c], sb); }
+          }
+        }
+      }
+      if (a.dX) {
+        // gradient w.r.t. the raw input rows: backward of the feature LayerNorm (warp per row)
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int r = warp; r < TM; r += MX_TILE_THREADS / 32) {
+          const int m = m0 + r;
+          if (m >= a.M) continue;
+          float s1 = 0.f, s2 = 0.f;
+          for (int c = lane; c < I; c += 32) {
+            const float dxh = dx0_s[r * sm.ldi + c] * (a.feature_norm ? th[L.fn_g + c] : 1.f);
+            s1 += dxh; s2 += dxh * xh0_s[r * sm.ldi + c];
+          }
+          s1 = mx_warp_sum(s1) / (float)I; s2 = mx_warp_sum(s2) / (float)I;
+          const float rstd = st0_s[2 * r + 1];
+          for (int c = lane; c < I; c += 32) {
+            const float d0 = dx0_s[r * sm.ldi + c];
+            a.dX[(size_t)m * a.ldx + c] = a.feature_norm ? rstd * (d0 * th[L.fn_g + c] - s1 - xh0_s[r * sm.ldi + c] * s2) : d0;
           }
         }
       }
@@ -420,11 +456,13 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     atomicAdd(&col2g[c], dg2[jx]); atomicAdd(&col2b[c], db2[jx]);
   }
   __syncthreads();
-  for (int c = tid; c < MX_H; c += MX_TILE_THREADS) {
-    gp[L.ln2_g + c] = col2g[c]; gp[L.ln2_b + c] = col2b[c];
-    gp[L.ln1_g + c] = col1g[c]; gp[L.ln1_b + c] = col1b[c];
+  if (wg) {
+    for (int c = tid; c < MX_H; c += MX_TILE_THREADS) {
+      gp[L.ln2_g + c] = col2g[c]; gp[L.ln2_b + c] = col2b[c];
+      gp[L.ln1_g + c] = col1g[c]; gp[L.ln1_b + c] = col1b[c];
+    }
+    for (int c = tid; c < I; c += MX_TILE_THREADS) { gp[L.fn_g + c] = col0g[c]; gp[L.fn_b + c] = col0b[c]; }
   }
-  for (int c = tid; c < I; c += MX_TILE_THREADS) { gp[L.fn_g + c] = col0g[c]; gp[L.fn_b + c] = col0b[c]; }
 }
 
 // =====================================================================================================

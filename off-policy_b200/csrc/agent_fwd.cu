@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
   const int tid = threadIdx.x;
   const int i = tid >> 2, q = tid & 3;
   const int row0 = blockIdx.x * RPC;
-  const bool live = (net == 0);
+  const bool live = (net == 0) && a.gates != nullptr;     // only the live net keeps gate activations for the backward pass
   float wr[16], wz[16], wn[16];
 #pragma unroll
   for (int m = 0; m < 4; ++m)
@@ -185,7 +185,10 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
       wn[4 * m + c] = th[a.whh + (2 * MX_H + i) * MX_H + k];
     }
   const float br = th[a.bhh + i], bz = th[a.bhh + MX_H + i], bn = th[a.bhh + 2 * MX_H + i];
-  for (int idx = tid; idx < 2 * RPC * MX_H; idx += GRU_THREADS) (&h_s[0][0][0])[idx] = 0.f;   // h_0 = 0 (QMixPolicy.py:193-196)
+  for (int idx = tid; idx < 2 * RPC * MX_H; idx += GRU_THREADS) {                               // h_0 = 0 (QMixPolicy.py:193-196) or given
+    const int r = (idx / MX_H) % RPC, c = idx % MX_H;
+    (&h_s[0][0][0])[idx] = (a.h0 && row0 + r < a.R) ? a.h0[(size_t)(row0 + r) * MX_H + c] : 0.f;
+  }
 
   const float* gi = a.gi[net];
   float* hall = a.hall[net];

@@ -22,7 +22,8 @@ struct GruFwdArgs {
   float* hall[2];          // [M][H]  h_t after step t
   float* gates;            // live [M][3H] (r, z, n)
   float* hn;               // live [M][H]  W_hn h + b_hn
-  int R, T, N;             // rows = B*N, episode length, agents
+  int R, T, N;             // rows, steps-1 (the kernel runs T+1 steps), agents interleaved per step (m = (b*(T+1)+t)*N + n)
+  const float* h0;         // optional initial hidden state [R][H] (branch steps); null -> zeros
 };
 int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s);
 
@@ -83,14 +84,18 @@ struct GruBwdArgs {
   const float* gates;      // [M][3H]
   const float* hn;         // [M][H]
   const float* dh_out;     // [M][H]
-  float* dgi;              // [M][3H]   d(loss)/d(gi) ; t == T rows are zero-filled
-  int R, T, N;
+  float* dgi;              // [M][3H]   d(loss)/d(gi) ; rows t >= TB are zero-filled
+  int R, T, N;             // T = number of steps to back-propagate (TB)
+  int T1;                  // steps per sequence in memory (0 -> T + 1, the QMIX layout where the bootstrap step has no gradient)
+  const float* h0;         // optional initial hidden state [R][H] used as h_{-1}; null -> zeros
 };
 int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s);
 
 struct FrontBwdArgs {
   const float* X;          // [M][ldx]
-  int ldx, M, T, N;
+  int ldx, M, T, N;         // T: episode length when T1 == 0 (steps per sequence = T + 1)
+  int T1;                   // steps per sequence in memory (0 -> T + 1)
+  const float* h0;          // optional h_{-1} rows [M / T1 ...]: only for T1 == 1 branch rows ([M][H])
   int feature_norm;
   const float* theta;
   MxNetLayout L;
@@ -100,6 +105,8 @@ struct FrontBwdArgs {
   const float* hall;       // [M][H]
   float* gpart;
   long long P;
+  float* dX;               // optional: gradient w.r.t. the input rows [M][ldx] (through the feature LayerNorm)
+  int skip_wgrad;          // 1: data gradient only (frozen network)
 };
 int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s);
 
@@ -121,6 +128,7 @@ struct OptimArgs {
   float lr, beta1, beta2, eps, max_grad_norm, tau;
   int world_size;
   int fuse_polyak;          // Adam epilogue also applies the soft target update (graph mode)
+  float weight_decay;       // torch.optim.Adam(weight_decay): g += wd * p after clipping
 };
 int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s);
 int mx_launch_adam(const OptimArgs& a, cudaStream_t s);

@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
   __syncthreads();
   const float scale = s_scale, step = s_step, bc2s = s_bc2s;
   for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < a.P; i += (long long)gridDim.x * blockDim.x) {
-    const float g = a.grad[i] * scale;
+    float g = a.grad[i] * scale;
+    if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, a.theta[i], g);     // torch Adam: grad.add(param, alpha=weight_decay)
     float m = a.adam_m[i], v = a.adam_v[i];
     m = m + (g - m) * (1.f - a.beta1);                   // exp_avg.lerp_(grad, 1 - beta1)
     v = v * a.beta2 + (1.f - a.beta2) * g * g;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)

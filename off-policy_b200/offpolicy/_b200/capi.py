@@ -45,6 +45,13 @@ class QmixCfg(C.Structure):
                                           "max_grad_norm", "tau")])
 
 
+class MaddpgCfg(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("n_agents", "obs_dim", "act_dim", "state_dim", "hidden", "episode_len", "max_batch", "num_q",
+                                          "actor_update_interval", "use_huber", "use_per")] +
+                [(n, C.c_float) for n in ("gamma", "huber_delta", "per_nu", "per_eps", "lr", "adam_beta1", "adam_beta2", "adam_eps",
+                                          "max_grad_norm", "tau", "weight_decay", "target_noise")])
+
+
 class ParamEntry(C.Structure):
     _fields_ = [("name", C.c_char * MX_MAX_NAME), ("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32)]
 
@@ -102,6 +109,16 @@ def _declare(lib):
         "mx_qmix_soft_update": (C.c_int, [vp, vp]),
         "mx_qmix_hard_update": (C.c_int, [vp, vp]),
         "mx_qmix_ws_lookup": (C.c_int, [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),
+        "mx_maddpg_param_layout": (C.c_int, [C.POINTER(MaddpgCfg), i32, C.POINTER(ParamEntry), i32, C.POINTER(i64)]),
+        "mx_maddpg_workspace_bytes": (i64, [C.POINTER(MaddpgCfg)]),
+        "mx_maddpg_create": (C.c_int, [C.POINTER(MaddpgCfg), C.POINTER(vp), C.POINTER(vp), vp, i64, C.POINTER(vp)]),
+        "mx_maddpg_destroy": (None, [vp]),
+        "mx_maddpg_step": (C.c_int, [vp, C.POINTER(Batch), vp, C.POINTER(i32), vp]),
+        "mx_maddpg_info": (vp, [vp]),
+        "mx_maddpg_priorities": (vp, [vp]),
+        "mx_maddpg_grad_views": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "mx_maddpg_soft_update": (C.c_int, [vp, vp]),
+        "mx_maddpg_hard_update": (C.c_int, [vp, vp]),
         "mx_graph_capture": (C.c_int, [vp, vp, i32, dbl, u32, vp, C.POINTER(vp)]),
         "mx_graph_launch": (C.c_int, [vp, vp]),
         "mx_graph_destroy": (None, [vp]),

@@ -1,0 +1,161 @@
+"""Drop-in `R_MADDPGPolicy` (reference: offpolicy/algorithms/r_maddpg/algorithm/rMADDPGPolicy.py) for continuous (Box)
+action spaces.  `actor`, `critic`, `target_actor`, `target_critic` are named views (reference state_dict keys) of the flat
+device vectors the CUDA learner updates in place; the two Adam states live beside them.  Rollout-time `get_actions`
+(one env step) runs a handful of torch ops on those views; everything update-time is inside `mx_maddpg_step`.
+Discrete / MultiDiscrete action spaces (Gumbel-softmax actors) are not built yet and raise."""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from offpolicy._b200 import capi
+from offpolicy._b200.flat import FlatModule
+from offpolicy._b200.host_util import space_dim, is_discrete
+
+
+def maddpg_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, max_batch, td3, target_noise, actor_update_interval):
+    return capi.MaddpgCfg(n_agents=n_agents, obs_dim=obs_dim, act_dim=act_dim, state_dim=state_dim, hidden=args.hidden_size,
+                          episode_len=episode_len, max_batch=max_batch, num_q=2 if td3 else 1, actor_update_interval=actor_update_interval,
+                          use_huber=int(args.use_huber_loss), use_per=int(args.use_per), gamma=args.gamma, huber_delta=args.huber_delta,
+                          per_nu=args.per_nu, per_eps=args.per_eps, lr=args.lr, adam_beta1=0.9, adam_beta2=0.999, adam_eps=args.opti_eps,
+                          max_grad_norm=args.max_grad_norm, tau=args.tau, weight_decay=float(getattr(args, "weight_decay", 0) or 0),
+                          target_noise=float(target_noise or 0.0))
+
+
+def maddpg_entries(cfg, which):
+    lib = capi.lib()
+    total = C.c_int64()
+    n = lib.mx_maddpg_param_layout(C.byref(cfg), which, None, 0, C.byref(total))
+    if n < 0:
+        raise capi.MxError(lib.mx_last_error().decode())
+    arr = (capi.ParamEntry * n)()
+    lib.mx_maddpg_param_layout(C.byref(cfg), which, arr, n, C.byref(total))
+    return [(e.name.decode(), int(e.offset), int(e.rows), int(e.cols)) for e in arr], int(total.value)
+
+
+def _init_net(mod, in_dim, hidden, out_specs, gain, use_orthogonal):
+    """Reference construction order (RNNBase then the head, mlp.py:14-23, rnn.py:8-17, act.py / r_actor_critic.py:90-93)."""
+    import torch.nn as nn
+    init_w = nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_
+    relu_gain = nn.init.calculate_gain("relu")
+    sd = {}
+
+    def linear(prefix, i, o, g):
+        m = nn.Linear(i, o)
+        init_w(m.weight.data, gain=g)
+        m.bias.data.zero_()
+        sd[prefix + ".weight"], sd[prefix + ".bias"] = m.weight.data, m.bias.data
+
+    def lnorm(prefix, n):
+        sd[prefix + ".weight"], sd[prefix + ".bias"] = torch.ones(n), torch.zeros(n)
+
+    lnorm("rnn.feature_norm", in_dim)
+    linear("rnn.mlp.fc1.0", in_dim, hidden, relu_gain); lnorm("rnn.mlp.fc1.2", hidden)
+    linear("rnn.mlp.fc_h.0", hidden, hidden, relu_gain); lnorm("rnn.mlp.fc_h.2", hidden)
+    for k in ("0.weight", "0.bias", "2.weight", "2.bias"):
+        sd["rnn.mlp.fc2.0." + k] = sd["rnn.mlp.fc_h." + k].clone()
+    gru = nn.GRU(hidden, hidden, num_layers=1)
+    for name, p in gru.named_parameters():
+        if "bias" in name:
+            p.data.zero_()
+        else:
+            init_w(p.data)
+        sd["rnn.rnn.rnn." + name] = p.data
+    lnorm("rnn.rnn.norm", hidden)
+    for prefix, o, g in out_specs:
+        linear(prefix, hidden, o, g)
+    mod.load_state_dict({k: v.reshape(mod.views[k].shape) for k, v in sd.items()})
+
+
+class R_MADDPGPolicy(object):
+    def __init__(self, config, policy_config, target_noise=None, td3=False, train=True):
+        self.config = config
+        self.device = config["device"]
+        self.args = self.config["args"]
+        self.tau, self.lr, self.opti_eps = self.args.tau, self.args.lr, self.args.opti_eps
+        self.weight_decay = getattr(self.args, "weight_decay", 0)
+        if getattr(self.args, "prev_act_inp", False):
+            raise NotImplementedError("B200 R-MADDPG path: --prev_act_inp is not implemented")
+        self.central_obs_dim, self.central_act_dim = policy_config["cent_obs_dim"], policy_config["cent_act_dim"]
+        self.obs_space, self.act_space = policy_config["obs_space"], policy_config["act_space"]
+        self.obs_dim, self.act_dim = space_dim(self.obs_space), space_dim(self.act_space)
+        self.output_dim = self.act_dim
+        self.hidden_size = self.args.hidden_size
+        self.discrete = is_discrete(self.act_space)
+        self.multidiscrete = False
+        if self.discrete:
+            raise NotImplementedError("B200 R-MADDPG path: only continuous (Box) action spaces are implemented so far")
+        self.td3, self.target_noise = bool(td3), target_noise
+        n_agents = self.central_act_dim // self.act_dim
+        capi.lib()
+        self.dev = capi.device()
+        cfg = maddpg_cfg_struct(self.args, n_agents, self.obs_dim, self.act_dim, self.central_obs_dim, 1, 1, td3, target_noise, 1)
+        self._a_entries, self.Pa = maddpg_entries(cfg, 0)
+        self._c_entries, self.Pc = maddpg_entries(cfg, 1)
+        z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.actor_vecs = [z(self.Pa) for _ in range(4)]      # theta, target, adam m, adam v
+        self.critic_vecs = [z(self.Pc) for _ in range(4)]
+        self.actor = FlatModule(self.actor_vecs[0], self._a_entries, "")
+        self.target_actor = FlatModule(self.actor_vecs[1], self._a_entries, "")
+        self.critic = FlatModule(self.critic_vecs[0], self._c_entries, "")
+        self.target_critic = FlatModule(self.critic_vecs[1], self._c_entries, "")
+        _init_net(self.actor, self.obs_dim, self.hidden_size, [("act.action_out", self.act_dim, self.args.gain)], self.args.gain,
+                  self.args.use_orthogonal)
+        _init_net(self.critic, self.central_obs_dim + self.central_act_dim, self.hidden_size,
+                  [("q_outs.%d" % k, 1, 1.0) for k in range(2 if td3 else 1)], 1.0, self.args.use_orthogonal)
+        self.actor_vecs[1].copy_(self.actor_vecs[0])          # rMADDPGPolicy.py:49-50
+        self.critic_vecs[1].copy_(self.critic_vecs[0])
+        self._trainer = None
+
+    # -- rollout-time single step ------------------------------------------------------------------------------
+    def _actor_step(self, views, obs, h):
+        p, H = views, self.hidden_size
+        x = F.layer_norm(obs, (self.obs_dim,), p["rnn.feature_norm.weight"], p["rnn.feature_norm.bias"])
+        x = F.layer_norm(F.relu(F.linear(x, p["rnn.mlp.fc1.0.weight"], p["rnn.mlp.fc1.0.bias"])), (H,), p["rnn.mlp.fc1.2.weight"], p["rnn.mlp.fc1.2.bias"])
+        x = F.layer_norm(F.relu(F.linear(x, p["rnn.mlp.fc2.0.0.weight"], p["rnn.mlp.fc2.0.0.bias"])), (H,), p["rnn.mlp.fc2.0.2.weight"], p["rnn.mlp.fc2.0.2.bias"])
+        gi = F.linear(x, p["rnn.rnn.rnn.weight_ih_l0"], p["rnn.rnn.rnn.bias_ih_l0"])
+        gh = F.linear(h, p["rnn.rnn.rnn.weight_hh_l0"], p["rnn.rnn.rnn.bias_hh_l0"])
+        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        h2 = (1 - z) * n + z * h
+        y = F.layer_norm(h2, (H,), p["rnn.rnn.norm.weight"], p["rnn.rnn.norm.bias"])
+        return F.linear(y, p["act.action_out.weight"], p["act.action_out.bias"]), h2
+
+    def get_actions(self, obs, prev_actions, rnn_states, available_actions=None, t_env=None, explore=False, use_target=False, use_gumbel=False):
+        views = (self.target_actor if use_target else self.actor).views
+        o = torch.as_tensor(np.asarray(obs), dtype=torch.float32).to(self.dev)
+        h = torch.as_tensor(rnn_states, dtype=torch.float32).to(self.dev)
+        with torch.no_grad():
+            if o.dim() == 3:
+                outs = []
+                for t in range(o.shape[0]):
+                    a, h = self._actor_step(views, o[t], h)
+                    outs.append(a)
+                out = torch.stack(outs)
+            else:
+                out, h = self._actor_step(views, o, h)
+        if explore:
+            assert o.dim() == 2, "Cannot do exploration on a sequence!"
+            out = torch.empty(out.shape).normal_(mean=0, std=self.args.act_noise_std).to(out.device) + out     # util.py:217-218
+        elif use_target and self.target_noise is not None:
+            out = torch.empty(out.shape).normal_(mean=0, std=self.target_noise).to(out.device) + out
+        return out, h, None
+
+    def get_random_actions(self, obs, available_actions=None):
+        return np.random.uniform(self.act_space.low, self.act_space.high, size=(obs.shape[0], self.act_dim))
+
+    def init_hidden(self, num_agents, batch_size):
+        if num_agents == -1:
+            return torch.zeros(batch_size, self.hidden_size)
+        return torch.zeros(num_agents, batch_size, self.hidden_size)
+
+    def soft_target_updates(self):
+        if self._trainer is None:
+            raise RuntimeError("soft_target_updates: no trainer attached")
+        capi.check(capi.lib().mx_maddpg_soft_update(self._trainer.handle, capi.stream_ptr()))
+
+    def hard_target_updates(self):
+        self.actor_vecs[1].copy_(self.actor_vecs[0])
+        self.critic_vecs[1].copy_(self.critic_vecs[0])

@@ -1,0 +1,107 @@
+"""R-MADDPG / R-MATD3 learner parity checks (emulated CPU build and real GPU): reference goldens + the pinned oracle in lock-step."""
+import types
+
+import numpy as np
+import torch
+
+from helpers import load_golden, sub, rel_err
+from qmix_checks import close
+from test_oracle_maddpg import maddpg_from_golden, maddpg_batch
+
+
+class Box(object):
+    def __init__(self, d, low=-1.0, high=1.0):
+        self.shape = (d,)
+        self.low = np.full(d, low, np.float32)
+        self.high = np.full(d, high, np.float32)
+
+
+def make_args(cfg, B):
+    return types.SimpleNamespace(
+        hidden_size=cfg.hidden, layer_N=1, use_ReLU=True, use_feature_normalization=True, use_orthogonal=True, gain=cfg.gain,
+        use_conv1d=False, stacked_frames=1, use_rnn_layer=True, recurrent_N=1, prev_act_inp=False, gamma=cfg.gamma, use_per=cfg.use_per,
+        per_nu=cfg.per_nu, per_eps=cfg.per_eps, use_huber_loss=cfg.huber, huber_delta=cfg.huber_delta, max_grad_norm=cfg.max_grad_norm,
+        lr=cfg.lr, opti_eps=cfg.opti_eps, weight_decay=cfg.weight_decay, tau=cfg.tau, use_popart=False, use_value_active_masks=False,
+        use_same_share_obs=True, batch_size=B, episode_length=0, epsilon_start=1.0, epsilon_finish=0.05, epsilon_anneal_time=50000,
+        act_noise_std=0.1, target_action_noise_std=cfg.target_noise)
+
+
+def build(cfg, B, T):
+    from offpolicy._b200 import capi
+    if cfg.td3:
+        from offpolicy.algorithms.r_matd3.algorithm.rMATD3Policy import R_MATD3Policy as Policy
+        from offpolicy.algorithms.r_matd3.r_matd3 import R_MATD3 as Trainer
+    else:
+        from offpolicy.algorithms.r_maddpg.algorithm.rMADDPGPolicy import R_MADDPGPolicy as Policy
+        from offpolicy.algorithms.r_maddpg.r_maddpg import R_MADDPG as Trainer
+    args = make_args(cfg, B)
+    info = dict(obs_space=Box(cfg.obs_dim, -np.inf, np.inf), share_obs_space=Box(cfg.state_dim, -np.inf, np.inf), act_space=Box(cfg.act_dim),
+                cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
+    pol = Policy({"args": args, "device": capi.device()}, info)
+    tr = Trainer(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=capi.device(), episode_length=T)
+    return args, pol, tr
+
+
+def ref_tuple(b):
+    d = lambda x: {"policy_0": x}
+    return tuple(d(x) for x in b[:7]) + (b[7], b[8])
+
+
+def named_views(flat, entries):
+    out = {}
+    for name, off, rows, cols in entries:
+        n = rows * (cols if cols else 1)
+        out[name] = flat[off:off + n].view(rows, cols) if cols else flat[off:off + n]
+    return out
+
+
+def check_golden(name):
+    g = load_golden(name)
+    L, cfg, B, T, steps = maddpg_from_golden(g)
+    args, pol, tr = build(cfg, B, T)
+    for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
+        mod.load_state_dict(sub(g, "init.%s." % tag))
+    problems = []
+    for s in range(steps):
+        batch, noise = maddpg_batch(g, s)
+        torch.manual_seed(1000 + s)                         # the trainer draws the MATD3 noise from torch's CPU RNG like the reference
+        info, prio, _ = tr.shared_train_policy_on_batch("policy_0", ref_tuple(batch))
+        ref, rprio = L.step(batch, noise)
+        ga, gc = tr.grad_views()
+        for key in ("critic_loss", "critic_grad_norm"):
+            e = rel_err(info[key].cpu(), g["s%d.%s" % (s, key)])
+            if e > 1e-4:
+                problems.append("step %d %s rel err %.3e (got %r want %r)" % (s, key, e, float(info[key]), float(g["s%d.%s" % (s, key)])))
+        coef = min(1.0, cfg.max_grad_norm / (float(ref["critic_grad_norm"]) + 1e-6))
+        cviews = named_views(gc, pol._c_entries)
+        for k, gr in L.critic_grads.items():
+            ok, err, lim = close(cviews[k] / gc[pol.Pc] * coef, gr, 1e-4)
+            if not ok:
+                problems.append("step %d critic grad %s err %.3e > %.3e" % (s, k, err, lim))
+        assert bool(info["update_actor"]) == bool(int(g["s%d.update_actor" % s]))
+        if info["update_actor"]:
+            for key in ("actor_loss", "actor_grad_norm"):
+                e = rel_err(info[key].cpu(), g["s%d.%s" % (s, key)])
+                if e > 1e-4:
+                    problems.append("step %d %s rel err %.3e (got %r want %r)" % (s, key, e, float(info[key]), float(g["s%d.%s" % (s, key)])))
+            coef = min(1.0, cfg.max_grad_norm / (float(g["s%d.actor_grad_norm" % s]) + 1e-6))
+            aviews = named_views(ga, pol._a_entries)
+            for k, v in aviews.items():
+                key = "s%d.grad.actor.%s" % (s, k)
+                if key in g:
+                    ok, err, lim = close(v / ga[pol.Pa] * coef, g[key], 1e-4)
+                    if not ok:
+                        problems.append("step %d actor grad %s err %.3e > %.3e" % (s, k, err, lim))
+            pol.soft_target_updates()
+            L.soft_update()
+        if cfg.use_per:
+            ok, err, lim = close(np.asarray(prio), g["s%d.prio" % s], 1e-4)
+            if not ok:
+                problems.append("step %d priorities err %.3e" % (s, err))
+    for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
+        for k, v in mod.state_dict().items():
+            want = g["final.%s.%s" % (tag, k)]
+            err = np.abs(v.cpu().numpy() - want).max()
+            if err > 5e-3 * cfg.lr * steps + 1e-7:
+                problems.append("final %s.%s err %.3e" % (tag, k, err))
+    assert not problems, "\n".join(problems[:40])
