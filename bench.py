@@ -46,6 +46,120 @@ def peaks():
     return dict(hbm=6650.0, tflops=1590.0, tflops_sustained=1400.0, src="fallback")
 
 
+MADDPG_WORKLOADS = {
+    # name: (n_agents, obs, act (Box), state, T, B, td3)    -- BASELINE.json configs[2]: MPE simple_spread shapes, continuous actions
+    "rmaddpg_spread": (3, 18, 2, 54, 25, 32, False),
+    "rmatd3_spread": (3, 18, 2, 54, 25, 32, True),
+}
+
+
+def run_maddpg(args):
+    """R-MADDPG / R-MATD3 learner (BASELINE config 3): sample -> shared_train_policy_on_batch -> soft update, eager launches
+    (one C call enqueues the ~40 kernels of an update); CPU arm = the pinned oracle port."""
+    from offpolicy._b200 import capi
+    import maddpg_checks as mc
+    import replay_checks as rc
+    from oracle.maddpg import MaddpgConfig, MaddpgLearner, synth_batch_cont
+    n, o, a, sdim, T, B, td3 = MADDPG_WORKLOADS[args.workload]
+    cfg = MaddpgConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim, td3=td3, actor_update_interval=2 if td3 else 1, gain=1.0)
+    E = min(args.buffer, 5000)
+    rs = np.random.default_rng(0)
+
+    def episodes(k):
+        return [rs.standard_normal((T + 1, k, n, o), dtype=np.float32), np.repeat(rs.standard_normal((T + 1, k, 1, sdim), dtype=np.float32), n, 2),
+                rs.uniform(-1, 1, (T, k, n, a)).astype(np.float32), np.repeat(rs.standard_normal((T, k, 1, 1), dtype=np.float32), n, 2),
+                np.zeros((T, k, n, 1), np.float32), np.zeros((T, k, 1), np.float32)]
+
+    if args.impl == "reference":
+        from oracle.replay import UniformReplay
+        th = best_threads = 8
+        torch.set_num_threads(th)
+        buf = UniformReplay(min(E, 1024), T, n, o, sdim, a, use_avail=False)
+        for c in range(0, min(E, 1024), 64):
+            buf.insert(64, *episodes(64), None)
+        L = MaddpgLearner(cfg, seed=1)
+        np.random.seed(1)
+        times = []
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            out, inds = buf.sample(B)
+            noise = torch.empty(T + 1, n * B, a).normal_(0, cfg.target_noise).numpy() if td3 else None
+            info, _ = L.step(out, noise)
+            if info["update_actor"]:
+                L.soft_update()
+            float(info["critic_loss"])
+            if s >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        sps = 1.0 / float(np.median(times))
+        print(json.dumps(dict(metric="learner grad-steps/sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
+                              warmup=args.warmup, ms_per_step=1e3 / sps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                              data="synthetic", config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=n),
+                              cpu_baseline=dict(value=sps, unit="steps/s", cores=th, kind="port", sample="%d timed updates" % args.steps),
+                              e2e=dict(value=sps, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+        return
+    torch.cuda.set_device(0)
+    lib = capi.lib()
+    from offpolicy.utils.rec_buffer import RecReplayBuffer
+    info = {"policy_0": dict(obs_space=[o], share_obs_space=[sdim], act_space=mc.Box(a))}
+    buf = RecReplayBuffer(info, {"policy_0": list(range(n))}, E, T, True, False, rng="device", max_batch=128)
+    for c in range(0, E, 128):
+        k = min(128, E - c)
+        buf.insert(k, *[rc.d(x) for x in episodes(k)], None)
+    torch.manual_seed(1)
+    margs, pol, tr = mc.build(cfg, B, T)
+    buf.seed_device_rng(1)
+
+    def step():
+        smp = buf.sample(B)
+        info_t, _, _ = tr.shared_train_policy_on_batch("policy_0", smp)
+        if info_t["update_actor"]:
+            pol.soft_target_updates()
+        return info_t
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = lib.mx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = int(lib.mx_launch_count() - l0)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        float(step()["critic_loss"])
+    torch.cuda.synchronize()
+    e2e = 50 / (time.perf_counter() - t0)
+    torch.set_num_threads(8)
+    L = MaddpgLearner(cfg, seed=1)
+    tms = []
+    for s in range(8):
+        batch = synth_batch_cont(cfg, B, T, seed=s) + (None, None)
+        noise = torch.empty(T + 1, n * B, a).normal_(0, cfg.target_noise).numpy() if td3 else None
+        t0 = time.perf_counter()
+        i2, _ = L.step(batch, noise)
+        if i2["update_actor"]:
+            L.soft_update()
+        if s >= 2:
+            tms.append(time.perf_counter() - t0)
+    cpu = 1.0 / float(np.median(tms))
+    print(json.dumps(dict(metric="learner grad-steps/sec", value=1000.0 / ms, unit="steps/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3),
+                          ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                          config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim,
+                                      buffer_episodes=E, step="eager: device MT19937 sample + mx_maddpg_step (+ soft update when the actor was updated)"),
+                          e2e=dict(value=e2e, unit="steps/s", h2d_bytes_per_step=0 if not td3 else (T + 1) * n * B * a * 4, d2h_bytes_per_step=4,
+                                   path="RecReplayBuffer.sample + R_MADDPG.shared_train_policy_on_batch + soft_target_updates + D2H critic_loss"),
+                          gpu_launches=launches, kernels_per_step=launches / args.steps,
+                          roofline=dict(bound="tensor", kernel="(many small launches)", achieved=None, peak=peaks()["tflops_sustained"], unit="TFLOP/s",
+                                        frac=None, traffic=None, note="launch/latency bound at B=32, T=25; see DESIGN.md"),
+                          cpu_baseline=dict(value=cpu, unit="steps/s", cores=8, kind="port", sample="6 timed updates of the same workload (oracle port)"),
+                          clocks=clocks.summary())))
+
+
 def make_cfg(w):
     from oracle.qmix import QmixConfig
     n, o, a, s, T, B, per = WORKLOADS[w]
@@ -395,9 +509,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="qmix_3m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="qmix_3m", choices=sorted(WORKLOADS) + sorted(MADDPG_WORKLOADS))
     ap.add_argument("--buffer", type=int, default=5000, help="replay episodes (scripts/train_smac_qmix.sh default 5000)")
     a = ap.parse_args()
+    if a.workload in MADDPG_WORKLOADS:
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_maddpg(a)
+        return
     if a.impl == "reference":
         run_reference(a)
     else:
