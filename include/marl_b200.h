@@ -251,6 +251,15 @@ int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta, uint32_t 
 int mx_graph_launch(mx_graph* g, void* stream);
 void mx_graph_destroy(mx_graph* g);
 
+/* tcgen05 building block probe (parity tests): Y[M][N] = X[M][K] . W[N][K]^T on the 5th-gen tensor cores with TF32
+ * operands; passes = 1 (plain TF32) or 3 (3xTF32 hi/lo split, fp32-level accuracy); swap_ls selects which descriptor field
+ * carries the K-direction core-matrix stride.  N % 16 == 0, N <= 256, K % 8 == 0, K <= 64. */
+int mx_tc_linear_probe(const float* X, const float* W, float* Y, int32_t M, int32_t N, int32_t K, int32_t passes, int32_t swap_ls, void* stream);
+
+/* runtime options: "front_tc" = 1 routes the time-batched front layers through the tcgen05 3xTF32 kernel (k_front_fwd_tc)
+ * instead of the FFMA kernel; "tc_swap_ls" selects the shared-memory descriptor stride convention (see mx_tc_linear_probe). */
+int mx_set_option(const char* name, int32_t value);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches counter) */
 int64_t mx_launch_count(void);
 
