@@ -424,12 +424,8 @@ def run_engine(args):
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
     e2e_sps = world * n_e2e / float(e2e_s)
 
-    if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
-        return
-
-    # ---------------- per-kernel timing (rank 0; eager, CUDA events on the launch stream) ----------------
+    # ---------------- per-kernel timing (eager, CUDA events on the launch stream) ----------------
+    # every rank runs this loop: the eager step contains the all-reduce, so the collective counts must match on all ranks
     buf.rng = "device"
     kern = {}
     reps, inner = 6, 8
@@ -454,6 +450,11 @@ def run_engine(args):
             for k, (nm, t) in enumerate(zip(names.value.decode().split(";"), list(ms)[:n])):
                 if k >= per:
                     kern.setdefault(nm, []).append(t)
+    barrier()
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     kavg = {k: float(np.median(v)) for k, v in kern.items()}
     ksum = sum(kavg.values())
     fl, by = kernel_work(cfg, T, B, tr.P)
