@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
   if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
 }
 
-int g_mx_front_tc = 0;        // 0: FFMA kernel, 1: tcgen05 kernel (set through mx_set_option)
+int g_mx_front_tc = 1;        // 1: tcgen05 3xTF32 kernel (default), 0: FFMA kernel (mx_set_option("front_tc", 0))
 int g_mx_tc_swap = 0;
 
 int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {

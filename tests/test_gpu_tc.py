@@ -37,23 +37,23 @@ def test_3xtf32_building_block_matches_fp64(gpu_engine):
         assert 1e-5 < e1 < 5e-3, (M, N, K, e1)   # plain TF32 really is ~1e-3: the split is what buys the parity budget
 
 
+@pytest.mark.parametrize("front_tc", [1, 0])
 @pytest.mark.parametrize("name", ["qmix_small", "qmix_5ag"])
-def test_qmix_step_with_tcgen05_front_matches_reference_golden(gpu_engine, name):
+def test_qmix_step_front_paths_match_reference_golden(gpu_engine, name, front_tc):
+    """The tcgen05 front kernel is the default; the FFMA kernel stays selectable and both must hold parity."""
     lib = gpu_engine.lib()
-    swap = detect_swap(gpu_engine)
-    lib.mx_set_option(b"tc_swap_ls", swap)
-    lib.mx_set_option(b"front_tc", 1)
+    assert detect_swap(gpu_engine) == 0          # the convention compiled in as the default
+    lib.mx_set_option(b"front_tc", front_tc)
     try:
         qc.check_step_against(None, name)
     finally:
-        lib.mx_set_option(b"front_tc", 0)
+        lib.mx_set_option(b"front_tc", 1)
 
 
 def test_config2_full_size_with_tcgen05_front_vs_oracle(gpu_engine):
     from test_gpu_qmix import _oracle_and_trainer, _compare_step
     from oracle.qmix import QmixConfig, synth_batch
     lib = gpu_engine.lib()
-    lib.mx_set_option(b"tc_swap_ls", detect_swap(gpu_engine))
     lib.mx_set_option(b"front_tc", 1)
     try:
         torch.set_num_threads(8)
@@ -62,4 +62,4 @@ def test_config2_full_size_with_tcgen05_front_vs_oracle(gpu_engine):
         batch = synth_batch(cfg, 32, 60, seed=5, avail_p=0.8, var_len=True) + (None, None)
         _compare_step(L, pol, tr, batch, cfg, steps=2)
     finally:
-        lib.mx_set_option(b"front_tc", 0)
+        lib.mx_set_option(b"front_tc", 1)
