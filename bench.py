@@ -452,9 +452,11 @@ def run_engine(args):
                     kern.setdefault(nm, []).append(t)
     barrier()
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
-        return
+        # stay alive until rank 0 has printed its line, then leave without tearing NCCL down (destroy_process_group after
+        # CUDA graphs that captured collectives can block at exit)
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        os._exit(0)
     kavg = {k: float(np.median(v)) for k, v in kern.items()}
     ksum = sum(kavg.values())
     fl, by = kernel_work(cfg, T, B, tr.P)
@@ -498,10 +500,12 @@ def run_engine(args):
                           sample="%d timed steps (sample+train+soft update) of the same workload on a %d-episode replay, oracle port of the reference learner" % (n_cpu, Ecpu)),
         clocks=clocks.summary())
     print(json.dumps(line))
+    sys.stdout.flush()
     if graph is not None:
         graph.close()
     if world > 1:
-        torch.distributed.destroy_process_group()
+        torch.distributed.barrier()
+        os._exit(0)
 
 
 def main():
