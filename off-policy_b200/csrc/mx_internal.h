@@ -78,6 +78,7 @@ struct MxQmixWs {           // offsets in floats into the workspace
   int64_t prio;             // [max_batch]
   int64_t spart;            // [npart][8] per-CTA scalar partials (denominator, loss numerator, sum Q_tot)
   int64_t adam_t;           // double[4]: step count, beta1^t, beta2^t
+  int64_t tcimg[2];         // pre-split TF32 weight images of the agent front layers (live, target)
   int64_t total;
 };
 

@@ -9,6 +9,8 @@
 #include "mx_internal.h"
 #include "mx_kernels.h"
 
+extern int g_mx_front_tc;
+
 // =====================================================================================================
 // parameter layouts (names = the reference's state_dict keys)
 // =====================================================================================================
@@ -134,6 +136,7 @@ static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W
   W->prio = tk(B);
   W->spart = tk((int64_t)npart * 8);
   W->adam_t = tk(8);
+  W->tcimg[0] = tk((int64_t)mx_tc_image_floats(c->obs_dim)); W->tcimg[1] = tk((int64_t)mx_tc_image_floats(c->obs_dim));
   W->total = o;
   return o * 4;
 }
@@ -244,6 +247,14 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   ff.theta[0] = q->theta; ff.theta[1] = q->theta_tgt; ff.L = q->agent;
   ff.gi[0] = ws + W.gi[0]; ff.gi[1] = ws + W.gi[1];
   ff.u1 = ws + W.u1; ff.u2 = ws + W.u2; ff.st0 = ws + W.st0; ff.st1 = ws + W.st1; ff.st2 = ws + W.st2;
+#if !MX_EMU
+  if (g_mx_front_tc && c.obs_dim <= 64) {       // weights changed in the last Adam / Polyak: rebuild the TF32 hi/lo images (18k elements per net)
+    for (int k = 0; k < 2; ++k) {
+      if (mx_launch_tc_prep_weights(k == 0 ? q->theta : q->theta_tgt, q->agent, ws + W.tcimg[k], s)) return 1;
+      ff.tc_img[k] = ws + W.tcimg[k];
+    }
+  }
+#endif
   if (mx_launch_front_fwd(ff, 2, s)) return 1;
 
   GruFwdArgs gf;

@@ -162,6 +162,35 @@ __device__ __forceinline__ void tc_stage_weight(char* hi, char* lo, const float*
   }
 }
 
+// Weight images: [w1 hi | w1 lo | w2 hi | w2 lo | w_ih hi | w_ih lo], each already in the UMMA core-matrix layout, so a CTA
+// stages all three layers with straight 16-byte cp.async copies (no per-CTA conversion).  Rebuilt once per step.
+__global__ void __launch_bounds__(256) k_tc_prep_weights(const float* __restrict__ th, MxNetLayout L, float* __restrict__ img) {
+  const int I = L.in_dim, Kp = (I + 7) & ~7;
+  const int n1 = MX_H * Kp, n2 = MX_H * MX_H, n3 = MX_G * MX_H;
+  char* base = reinterpret_cast<char*>(img);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2 + n3; idx += gridDim.x * blockDim.x) {
+    int n, k, K, Kd;
+    const float* W;
+    char *hi, *lo;
+    if (idx < n1) { n = idx / Kp; k = idx - n * Kp; K = I; Kd = Kp; W = th + L.w1; hi = base; lo = base + n1 * 4; }
+    else if (idx < n1 + n2) { const int j = idx - n1; n = j / MX_H; k = j % MX_H; K = MX_H; Kd = MX_H; W = th + L.w2; hi = base + 2 * n1 * 4; lo = hi + n2 * 4; }
+    else { const int j = idx - n1 - n2; n = j / MX_H; k = j % MX_H; K = MX_H; Kd = MX_H; W = th + L.wih; hi = base + (2 * n1 + 2 * n2) * 4; lo = hi + n3 * 4; }
+    tc::put_split(hi, lo, n, k, Kd, k < K ? W[(size_t)n * K + k] : 0.f);
+  }
+}
+
+size_t mx_tc_image_floats(int in_dim) {
+  const int Kp = mx_round_up(in_dim, 8);
+  return (size_t)2 * (MX_H * Kp + MX_H * MX_H + MX_G * MX_H);
+}
+int mx_launch_tc_prep_weights(const float* theta, const MxNetLayout& L, float* img, cudaStream_t s) {
+  const int n = MX_H * mx_round_up(L.in_dim, 8) + MX_H * MX_H + MX_G * MX_H;
+  k_tc_prep_weights<<<dim3((n + 255) / 256), dim3(256), 0, s>>>(theta, L, img);
+  MX_COUNT();
+  MX_MARK("k_tc_prep_weights", s);
+  return MX_CHECK_LAUNCH("tc_prep_weights");
+}
+
 // write this thread's row (64 values) into the A tiles, 16 bytes at a time
 __device__ __forceinline__ void tc_put_row64(char* hi, char* lo, int r, const float (&x)[64]) {
 #pragma unroll
@@ -179,7 +208,8 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar_s;
   __shared__ uint32_t tmem_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ float par_s[6 * MX_H + MX_G + 2 * 64];      // b1,g1,be1,b2,g2,be2 | b_ih | fn_g, fn_b
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int net = blockIdx.y;
   const float* __restrict__ th = a.theta[net];
   const MxNetLayout L = a.L;
@@ -194,9 +224,28 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
     tc::mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  tc_stage_weight(w1h, w1l, th + L.w1, MX_H, I, Kp);
-  tc_stage_weight(w2h, w2l, th + L.w2, MX_H, MX_H, MX_H);
-  tc_stage_weight(wih, wil, th + L.wih, MX_G, MX_H, MX_H);
+  if (a.tc_img[net]) {
+    // the image is byte-identical to the shared-memory weight region: straight 16-byte async copies
+    const int nvec = (sm.total - sm.o_w1h) >> 4;
+    const float* src = a.tc_img[net];
+    float* dst = reinterpret_cast<float*>(w1h);
+    for (int v = tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
+    mx_cp_commit();
+  } else {
+    tc_stage_weight(w1h, w1l, th + L.w1, MX_H, I, Kp);
+    tc_stage_weight(w2h, w2l, th + L.w2, MX_H, MX_H, MX_H);
+    tc_stage_weight(wih, wil, th + L.wih, MX_G, MX_H, MX_H);
+  }
+  for (int i = tid; i < MX_H; i += blockDim.x) {
+    par_s[i] = th[L.b1 + i]; par_s[MX_H + i] = th[L.ln1_g + i]; par_s[2 * MX_H + i] = th[L.ln1_b + i];
+    par_s[3 * MX_H + i] = th[L.b2 + i]; par_s[4 * MX_H + i] = th[L.ln2_g + i]; par_s[5 * MX_H + i] = th[L.ln2_b + i];
+    par_s[6 * MX_H + MX_G + i] = i < I ? th[L.fn_g + i] : 0.f; par_s[6 * MX_H + MX_G + 64 + i] = i < I ? th[L.fn_b + i] : 0.f;
+  }
+  for (int i = tid; i < MX_G; i += blockDim.x) par_s[6 * MX_H + i] = th[L.bih + i];
+  const float* bih_s = par_s + 6 * MX_H;
+  const float* fng_s = par_s + 6 * MX_H + MX_G;
+  const float* fnb_s = fng_s + 64;
+  mx_cp_wait<0>();
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
@@ -204,15 +253,22 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
   const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
   uint32_t phase = 0;
   const int ntiles = (a.M + 127) / 128;
+  const int I4 = (I + 3) >> 2;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int m = tile * 128 + tid;
     const bool ok = m < a.M;
-    // ---- input row: LayerNorm over I features, split, write the layer-1 A tile (K = Kp) ----
+    // ---- input row (thread per row, 16-byte loads): LayerNorm over I features, split, write the layer-1 A tile (K = Kp) ----
     {
       float x[64];
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && c4 < I4) v = *reinterpret_cast<const float4*>(a.X + (size_t)m * a.ldx + 4 * c4);
+        x[4 * c4] = v.x; x[4 * c4 + 1] = v.y; x[4 * c4 + 2] = v.z; x[4 * c4 + 3] = v.w;
+      }
       float s = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) { x[c] = (ok && c < I) ? a.X[(size_t)m * a.ldx + c] : 0.f; s += x[c]; }
+      for (int c = 0; c < 64; ++c) { if (c >= I) x[c] = 0.f; s += x[c]; }
       const float mean = s / (float)I;
       float q = 0.f;
 #pragma unroll
@@ -220,11 +276,20 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
       const float rstd = rsqrtf(q / (float)I + MX_LN_EPS);
       if (live && ok && a.st0) { a.st0[2 * (size_t)m] = mean; a.st0[2 * (size_t)m + 1] = rstd; }
 #pragma unroll
-      for (int c = 0; c < 64; ++c)
-        if (c < Kp) {
-          float v = 0.f;
-          if (c < I) v = a.feature_norm ? ((x[c] - mean) * rstd * th[L.fn_g + c] + th[L.fn_b + c]) : x[c];
-          tc::put_split(a_hi, a_lo, tid, c, Kp, v);
+      for (int c4 = 0; c4 < 16; ++c4)
+        if (4 * c4 < Kp) {
+          float4 h, l;
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = 4 * c4 + j;
+            v[j] = c < I ? (a.feature_norm ? ((x[c] - mean) * rstd * fng_s[c] + fnb_s[c]) : x[c]) : 0.f;
+          }
+          h.x = tc::to_tf32(v[0]); h.y = tc::to_tf32(v[1]); h.z = tc::to_tf32(v[2]); h.w = tc::to_tf32(v[3]);
+          l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+          const uint32_t o = tc::core_off_bytes(tid, 4 * c4, Kp);
+          *reinterpret_cast<float4*>(a_hi + o) = h;
+          *reinterpret_cast<float4*>(a_lo + o) = l;
         }
     }
     // ---- fc1, fc2 ----
@@ -245,10 +310,10 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
 #pragma unroll
         for (int c = 0; c < 32; ++c) { v[c] = t0[c]; v[32 + c] = t1[c]; }
       }
-      const int b_off = layer == 0 ? L.b1 : L.b2, g_off = layer == 0 ? L.ln1_g : L.ln2_g, be_off = layer == 0 ? L.ln1_b : L.ln2_b;
+      const float* bs = par_s + layer * 3 * MX_H;
       float s = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) { v[c] = fmaxf(v[c] + th[b_off + c], 0.f); s += v[c]; }
+      for (int c = 0; c < 64; ++c) { v[c] = fmaxf(v[c] + bs[c], 0.f); s += v[c]; }
       const float mean = s * (1.f / 64.f);
       float q = 0.f;
 #pragma unroll
@@ -262,7 +327,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
         if (st_out) { st_out[2 * (size_t)m] = mean; st_out[2 * (size_t)m + 1] = rstd; }
       }
 #pragma unroll
-      for (int c = 0; c < 64; ++c) v[c] = (v[c] - mean) * rstd * th[g_off + c] + th[be_off + c];
+      for (int c = 0; c < 64; ++c) v[c] = (v[c] - mean) * rstd * bs[MX_H + c] + bs[2 * MX_H + c];
       tc_put_row64(a_hi, a_lo, tid, v);      // the MMAs that read the previous A tile have completed (mbarrier)
     }
     // ---- gi = x2 . W_ih^T + b_ih ----
@@ -282,8 +347,8 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4)
           *reinterpret_cast<float4*>(gi + (size_t)m * MX_G + c0 + 4 * c4) =
-              make_float4(t0[4 * c4] + th[L.bih + c0 + 4 * c4], t0[4 * c4 + 1] + th[L.bih + c0 + 4 * c4 + 1], t0[4 * c4 + 2] + th[L.bih + c0 + 4 * c4 + 2],
-                          t0[4 * c4 + 3] + th[L.bih + c0 + 4 * c4 + 3]);
+              make_float4(t0[4 * c4] + bih_s[c0 + 4 * c4], t0[4 * c4 + 1] + bih_s[c0 + 4 * c4 + 1], t0[4 * c4 + 2] + bih_s[c0 + 4 * c4 + 2],
+                          t0[4 * c4 + 3] + bih_s[c0 + 4 * c4 + 3]);
       }
     }
     tc::fence_before();
@@ -394,4 +459,7 @@ extern "C" int mx_tc_linear_probe(const float*, const float*, float*, int32_t, i
   mx_set_error("tcgen05 kernels cannot be emulated");
   return 1;
 }
+#endif
+#if MX_EMU
+size_t mx_tc_image_floats(int in_dim) { return (size_t)2 * (MX_H * mx_round_up(in_dim, 8) + MX_H * MX_H + MX_G * MX_H); }
 #endif
