@@ -220,7 +220,10 @@ typedef struct mx_maddpg_cfg {
   int32_t use_huber, use_per;
   float gamma, huber_delta, per_nu, per_eps;
   float lr, adam_beta1, adam_beta2, adam_eps, max_grad_norm, tau, weight_decay;
-  float target_noise;             /* > 0: the caller passes N(0, target_noise) samples for the target actions (MATD3) */
+  float target_noise;             /* > 0: the caller passes noise for the target actions (MATD3): N(0, target_noise) samples for
+                                     Box actions (util.py:217-218), Gumbel(0,1) draws for Discrete actions (util.py:127-130) */
+  int32_t discrete;               /* 1: Discrete(act_dim) actions -- one-hot buffer actions, arg-max one-hot / hard Gumbel-softmax
+                                     actor outputs (rMADDPGPolicy.py:104-120, util.py:106-166); 0: Box(act_dim)              */
 } mx_maddpg_cfg;
 /* which = 0: actor ("rnn.*", "act.action_out.*"), 1: critic ("rnn.*", "q_outs.k.*"); names = reference state_dict keys */
 int mx_maddpg_param_layout(const mx_maddpg_cfg* cfg, int32_t which, mx_param_entry* out, int32_t max_entries, int64_t* total_floats);
@@ -233,6 +236,11 @@ void mx_maddpg_destroy(mx_maddpg* h);
  * the updated critic.  target_noise_dev: fp32 [(T+1)][B][N][act_dim] in batch row order (row = (b*(T+1)+t)*N + n) or NULL.
  * *update_actor_out tells the caller whether the actor was updated (train_info['update_actor']). */
 int mx_maddpg_step(mx_maddpg* h, const mx_batch* batch, const float* target_noise_dev, int32_t* update_actor_out, void* stream);
+/* Same, for Discrete actors: actor_noise_dev = the Gumbel(0,1) draws of the actor update's `use_gumbel=True` call
+ * (r_maddpg.py:277), fp32 [B][T+1][N][act_dim] in batch row order (the t = T slice is ignored), required on calls that
+ * update the actor; batch->avail (or NULL) masks unavailable actions to -1e10 like util.py:115,141. */
+int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* batch, const float* target_noise_dev, const float* actor_noise_dev,
+                      int32_t* update_actor_out, void* stream);
 /* device fp32[8]: critic_loss, critic_grad_norm, -, denom, actor_loss, actor_grad_norm, -, denom */
 const float* mx_maddpg_info(mx_maddpg* h);
 const float* mx_maddpg_priorities(mx_maddpg* h);

@@ -252,18 +252,62 @@ __global__ void __launch_bounds__(256) k_actor_loss(ActorLossArgs a) {   // ONE 
   }
 }
 
-// d(actor action of agent i at (b,t)) = dX[(i,b,t)][S + i*Ac + k]   ->   dense head gradient of the actor [M_a][Ac]
-__global__ void __launch_bounds__(256) k_scatter_actor_grad(const float* dX, int ldx, int B, int T, int N, int S, int Ac, float* dact) {
-  const long long total = (long long)B * (T + 1) * N * Ac;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % Ac);
-    long long m = idx / Ac;
+// d(actor action of agent i at (b,t)) = dX[(i,b,t)][S + i*Ac + k]   ->   dense head gradient of the actor [M_a][Ac].
+// Discrete actors (soft != null): the action is the straight-through hard Gumbel-softmax sample, so the gradient reaches the
+// logits through the soft sample y = softmax(logits + g):  dlogit_k = y_k (d_k - sum_j d_j y_j)            (util.py:160-165)
+__global__ void __launch_bounds__(256) k_scatter_actor_grad(const float* dX, int ldx, int B, int T, int N, int S, int Ac, const float* soft, float* dact) {
+  const long long rows = (long long)B * (T + 1) * N;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < rows; m += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(m % N);
     const long long bt1 = m / N;
     const int t = (int)(bt1 % (T + 1)), b = (int)(bt1 / (T + 1));
-    float v = 0.f;
-    if (t < T) v = dX[(((size_t)n * B + b) * T + t) * ldx + S + n * Ac + k];
-    dact[idx] = v;
+    float d[8];
+    for (int k = 0; k < Ac; ++k) d[k] = t < T ? dX[(((size_t)n * B + b) * T + t) * ldx + S + n * Ac + k] : 0.f;
+    if (soft) {
+      float dot = 0.f;
+      for (int k = 0; k < Ac; ++k) dot += d[k] * soft[m * Ac + k];
+      for (int k = 0; k < Ac; ++k) d[k] = soft[m * Ac + k] * (d[k] - dot);
+    }
+    for (int k = 0; k < Ac; ++k) dact[m * Ac + k] = d[k];
+  }
+}
+
+// Discrete action heads (Ac <= 8, one thread per row).  mode 0: `onehot_from_logits` = every maximal logit is hot
+// (util.py:106-118);  mode 1: hard Gumbel-softmax, value (y_hard - y) + y with y = softmax(logits + g) and y_hard the
+// one-hot of y's maxima (util.py:133-166, temperature 1).  Unavailable actions are forced to -1e10 first (util.py:115, 141).
+struct ActXformArgs {
+  int M, Ac, mode;
+  const float* logits;      // [M][Ac]  (already includes the Gumbel draw when gumbel == null)
+  const float* gumbel;      // [M][Ac] or null
+  const float* avail;       // [M][avail_ld] or null
+  int avail_ld;
+  float* out;               // [M][Ac]
+  float* soft;              // [M][Ac] soft sample (mode 1) or null
+};
+__global__ void __launch_bounds__(256) k_act_transform(ActXformArgs a) {
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < a.M; m += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    float mx = -INFINITY;
+    for (int k = 0; k < a.Ac; ++k) {
+      float x = a.logits[m * a.Ac + k];
+      if (a.gumbel) x += a.gumbel[m * a.Ac + k];
+      if (a.avail && a.avail[m * a.avail_ld + k] == 0.f) x = -1e10f;
+      v[k] = x;
+      mx = fmaxf(mx, x);
+    }
+    if (a.mode == 0) {
+      for (int k = 0; k < a.Ac; ++k) a.out[m * a.Ac + k] = v[k] == mx ? 1.f : 0.f;
+      continue;
+    }
+    float sum = 0.f;
+    for (int k = 0; k < a.Ac; ++k) { v[k] = expf(v[k] - mx); sum += v[k]; }
+    float ymax = 0.f;
+    for (int k = 0; k < a.Ac; ++k) { v[k] = v[k] / sum; ymax = fmaxf(ymax, v[k]); }
+    for (int k = 0; k < a.Ac; ++k) {
+      const float hard = v[k] == ymax ? 1.f : 0.f;
+      a.out[m * a.Ac + k] = (hard - v[k]) + v[k];
+      if (a.soft) a.soft[m * a.Ac + k] = v[k];
+    }
   }
 }
 
@@ -272,7 +316,7 @@ __global__ void __launch_bounds__(256) k_scatter_actor_grad(const float* dX, int
 // =====================================================================================================
 struct MxMaddpgWs {
   // actor (rows Ma = B*(T+1)*N)
-  int64_t a_gi[2], a_h[2], a_u1, a_u2, a_st0, a_st1, a_st2, a_sto, a_gates, a_hn, a_out, a_nact, a_dout, a_dh, a_dgi;
+  int64_t a_gi[2], a_h[2], a_u1, a_u2, a_st0, a_st1, a_st2, a_sto, a_gates, a_hn, a_out, a_nact, a_dout, a_dh, a_dgi, a_act, a_soft;
   // critic sequences (rows Mc = B*T)
   int64_t c_x, c_gi[2], c_h[2], c_u1, c_u2, c_st0, c_st1, c_st2, c_sto, c_gates, c_hn, c_q, c_dq, c_dh, c_dgi, c_err;
   // target branch (rows Mc)
@@ -364,7 +408,7 @@ static int64_t maddpg_ws_layout(const mx_maddpg_cfg* c, int64_t Pa, int64_t Pc, 
   for (int k = 0; k < 2; ++k) { W->a_gi[k] = tk(Ma * MX_G); W->a_h[k] = tk(Ma * MX_H); }
   W->a_u1 = tk(Ma * MX_H); W->a_u2 = tk(Ma * MX_H); W->a_st0 = tk(Ma * 2); W->a_st1 = tk(Ma * 2); W->a_st2 = tk(Ma * 2); W->a_sto = tk(Ma * 2);
   W->a_gates = tk(Ma * MX_G); W->a_hn = tk(Ma * MX_H); W->a_out = tk(Ma * Ac); W->a_nact = tk(Ma * Ac); W->a_dout = tk(Ma * Ac);
-  W->a_dh = tk(Ma * MX_H); W->a_dgi = tk(Ma * MX_G);
+  W->a_dh = tk(Ma * MX_H); W->a_dgi = tk(Ma * MX_G); W->a_act = tk(Ma * Ac); W->a_soft = tk(Ma * Ac);
   W->c_x = tk(Mc * ldc);
   for (int k = 0; k < 2; ++k) { W->c_gi[k] = tk(Mc * MX_G); W->c_h[k] = tk(Mc * MX_H); }
   W->c_u1 = tk(Mc * MX_H); W->c_u2 = tk(Mc * MX_H); W->c_st0 = tk(Mc * 2); W->c_st1 = tk(Mc * 2); W->c_st2 = tk(Mc * 2); W->c_sto = tk(Mc * 2);
@@ -458,11 +502,20 @@ static int optimise(mx_maddpg* h, bool actor, const int parts[2], int head_parts
 }
 
 extern "C" int mx_maddpg_step(mx_maddpg* h, const mx_batch* b, const float* target_noise_dev, int32_t* update_actor_out, void* stream) {
+  return mx_maddpg_step_ex(h, b, target_noise_dev, nullptr, update_actor_out, stream);
+}
+
+extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* target_noise_dev, const float* actor_noise_dev,
+                                 int32_t* update_actor_out, void* stream) {
   const mx_maddpg_cfg& c = h->cfg;
   if (!b || b->B <= 0 || b->B > c.max_batch) { mx_set_error("maddpg step: batch size outside [1, max_batch=%d]", c.max_batch); return 1; }
   if (!b->obs || !b->share || !b->acts || !b->rewards || !b->dones || !b->dones_env) { mx_set_error("maddpg step: missing batch field"); return 1; }
   if (c.use_per && !b->weights) { mx_set_error("maddpg step: use_per set but batch has no importance weights"); return 1; }
   if (c.target_noise > 0.f && !target_noise_dev) { mx_set_error("maddpg step: MATD3 target noise expected"); return 1; }
+  {
+    const bool upd = (h->num_updates % (c.actor_update_interval > 0 ? c.actor_update_interval : 1)) == 0;
+    if (c.discrete && upd && !actor_noise_dev) { mx_set_error("maddpg step: discrete actor update needs the Gumbel draws (actor_noise_dev)"); return 1; }
+  }
   cudaStream_t s = (cudaStream_t)stream;
   float* ws = h->ws;
   const MxMaddpgWs& W = h->W;
@@ -495,6 +548,13 @@ extern "C" int mx_maddpg_step(mx_maddpg* h, const mx_batch* b, const float* targ
   MX_LAUNCH(k_head_fwd, dim3(launch1d((long long)Ma * 32)), dim3(256), 0, s, ha); MX_COUNT(); MX_MARK("k_head_fwd", s);
   ha.theta = h->th_a_tgt; ha.h = gf.hall[1]; ha.sto = nullptr; ha.out = ws + W.a_nact; ha.noise = c.target_noise > 0.f ? target_noise_dev : nullptr;
   MX_LAUNCH(k_head_fwd, dim3(launch1d((long long)Ma * 32)), dim3(256), 0, s, ha); MX_COUNT(); MX_MARK("k_head_fwd", s);
+  if (c.discrete) {      // target actions: arg-max one-hot (MADDPG) / hard Gumbel-softmax sample (MATD3; the head added the draw)
+    ActXformArgs ax;
+    memset(&ax, 0, sizeof(ax));
+    ax.M = Ma; ax.Ac = Ac; ax.mode = c.target_noise > 0.f ? 1 : 0; ax.logits = ws + W.a_nact; ax.out = ws + W.a_nact;
+    ax.avail = b->avail; ax.avail_ld = b->act_ld;
+    MX_LAUNCH(k_act_transform, dim3(launch1d(Ma)), dim3(256), 0, s, ax); MX_COUNT(); MX_MARK("k_act_transform", s);
+  }
 
   // ---------- B. critic over the buffer sequence (live + target) ----------
   PackArgs pk;
@@ -579,7 +639,14 @@ extern "C" int mx_maddpg_step(mx_maddpg* h, const mx_batch* b, const float* targ
     g2.theta[0] = h->th_c; g2.whh = LC.whh; g2.bhh = LC.bhh; g2.gi[0] = f2.gi[0]; g2.hall[0] = ws + W.c_h[0]; g2.R = B; g2.T = T - 1; g2.N = 1;
     g2.gates = ws + W.c_gates; g2.hn = ws + W.c_hn;
     if (mx_launch_gru_fwd(g2, 1, s)) return 1;
-    pk.mode = 2; pk.x = ws + W.r_x; pk.actor_out = ws + W.a_out; pk.hseq = g2.hall[0]; pk.h0 = ws + W.r_h0;
+    if (c.discrete) {    // the live actor's hard Gumbel-softmax sample (straight-through), r_maddpg.py:277
+      ActXformArgs ax;
+      memset(&ax, 0, sizeof(ax));
+      ax.M = Ma; ax.Ac = Ac; ax.mode = 1; ax.logits = ws + W.a_out; ax.gumbel = actor_noise_dev; ax.out = ws + W.a_act; ax.soft = ws + W.a_soft;
+      ax.avail = b->avail; ax.avail_ld = b->act_ld;
+      MX_LAUNCH(k_act_transform, dim3(launch1d(Ma)), dim3(256), 0, s, ax); MX_COUNT(); MX_MARK("k_act_transform", s);
+    }
+    pk.mode = 2; pk.x = ws + W.r_x; pk.actor_out = ws + (c.discrete ? W.a_act : W.a_out); pk.hseq = g2.hall[0]; pk.h0 = ws + W.r_h0;
     MX_LAUNCH(k_pack_critic_in, dim3(launch1d((long long)Mr * ldc)), dim3(256), 0, s, pk); MX_COUNT(); MX_MARK("k_pack_critic_in", s);
     FrontFwdArgs fr;
     memset(&fr, 0, sizeof(fr));
@@ -614,7 +681,8 @@ extern "C" int mx_maddpg_step(mx_maddpg* h, const mx_batch* b, const float* targ
     fbr.gpart = ws + W.gpart_c; fbr.P = h->Pc; fbr.dX = ws + W.r_dx; fbr.skip_wgrad = 1;
     int dummy = 0;
     if (mx_launch_front_bwd(fbr, &dummy, s)) return 1;
-    MX_LAUNCH(k_scatter_actor_grad, dim3(launch1d((long long)Ma * Ac)), dim3(256), 0, s, (const float*)(ws + W.r_dx), ldc, B, T, N, S, Ac, ws + W.a_dout);
+    MX_LAUNCH(k_scatter_actor_grad, dim3(launch1d(Ma)), dim3(256), 0, s, (const float*)(ws + W.r_dx), ldc, B, T, N, S, Ac,
+              (const float*)(c.discrete ? ws + W.a_soft : nullptr), ws + W.a_dout);
     MX_COUNT(); MX_MARK("k_scatter_actor_grad", s);
     // actor backward + Adam
     const int ahead_grid = mx_imin_host(mx_num_sms(), mx_ceil_div(Ma, 32));

@@ -94,6 +94,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two back-to-back 32-column loads, one wait (the wait names every destination register so no use can move above it)
+#define MX_TMEM_LD32_ASYNC(taddr, r)                                                                                                        \
+  asm volatile(                                                                                                                             \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                                            \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n" \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),          \
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),              \
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),              \
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                                                 \
+      : "r"(taddr))
+#define MX_TMEM_WAIT32(r)                                                                                                                   \
+  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                                             \
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),  \
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),     \
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),     \
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory")
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r0[32], r1[32];
+  MX_TMEM_LD32_ASYNC(taddr, r0);
+  MX_TMEM_LD32_ASYNC(taddr + 32, r1);
+  MX_TMEM_WAIT32(r0);      // wait::ld covers every outstanding load of this thread
+  MX_TMEM_WAIT32(r1);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
+}
+
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -191,6 +217,28 @@ int mx_launch_tc_prep_weights(const float* theta, const MxNetLayout& L, float* i
   return MX_CHECK_LAUNCH("tc_prep_weights");
 }
 
+// 64-term sums on 8 independent chains (a thread owns a whole row: no other warp hides FADD latency for it)
+__device__ __forceinline__ float tc_sum64(const float (&v)[64]) {
+  float p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = v[i];
+#pragma unroll
+  for (int c = 8; c < 64; c += 8)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] += v[c + i];
+  return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+}
+__device__ __forceinline__ float tc_sumsq64(const float (&v)[64], float mean, int n_valid) {
+  float p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; c += 8)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = (c + i < n_valid) ? v[c + i] - mean : 0.f; p[i] = fmaf(d, d, p[i]); }
+  return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+}
+
 // write this thread's row (64 values) into the A tiles, 16 bytes at a time
 __device__ __forceinline__ void tc_put_row64(char* hi, char* lo, int r, const float (&x)[64]) {
 #pragma unroll
@@ -226,10 +274,13 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
   }
   if (a.tc_img[net]) {
     // the image is byte-identical to the shared-memory weight region: straight 16-byte async copies
-    const int nvec = (sm.total - sm.o_w1h) >> 4;
+    // two groups: fc1+fc2 first, W_ih (two thirds of the bytes) lands while the first two layers run
+    const int nvec = (sm.total - sm.o_w1h) >> 4, nvec12 = (sm.o_wih - sm.o_w1h) >> 4;
     const float* src = a.tc_img[net];
     float* dst = reinterpret_cast<float*>(w1h);
-    for (int v = tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
+    for (int v = tid; v < nvec12; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
+    mx_cp_commit();
+    for (int v = nvec12 + tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
     mx_cp_commit();
   } else {
     tc_stage_weight(w1h, w1l, th + L.w1, MX_H, I, Kp);
@@ -245,9 +296,8 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
   const float* bih_s = par_s + 6 * MX_H;
   const float* fng_s = par_s + 6 * MX_H + MX_G;
   const float* fnb_s = fng_s + 64;
-  mx_cp_wait<0>();
   tc::fence_before();
-  __syncthreads();
+  __syncthreads();        // parameters, TMEM address and the mbarrier are visible; the weight copies are still in flight
   tc::fence_after();
   const uint32_t tmem_base = tmem_s;
   const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -266,14 +316,10 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
         if (ok && c4 < I4) v = *reinterpret_cast<const float4*>(a.X + (size_t)m * a.ldx + 4 * c4);
         x[4 * c4] = v.x; x[4 * c4 + 1] = v.y; x[4 * c4 + 2] = v.z; x[4 * c4 + 3] = v.w;
       }
-      float s = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) { if (c >= I) x[c] = 0.f; s += x[c]; }
-      const float mean = s / (float)I;
-      float q = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) { const float d = c < I ? x[c] - mean : 0.f; q += d * d; }
-      const float rstd = rsqrtf(q / (float)I + MX_LN_EPS);
+      for (int c = 0; c < 64; ++c) if (c >= I) x[c] = 0.f;
+      const float mean = tc_sum64(x) / (float)I;
+      const float rstd = rsqrtf(tc_sumsq64(x, mean, I) / (float)I + MX_LN_EPS);
       if (live && ok && a.st0) { a.st0[2 * (size_t)m] = mean; a.st0[2 * (size_t)m + 1] = rstd; }
 #pragma unroll
       for (int c4 = 0; c4 < 16; ++c4)
@@ -294,6 +340,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
     }
     // ---- fc1, fc2 ----
     for (int layer = 0; layer < 2; ++layer) {
+      mx_cp_wait<1>();
       tc::fence_async_smem();
       tc::fence_before();
       __syncthreads();
@@ -303,22 +350,12 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
       phase ^= 1;
       tc::fence_after();
       float v[64];
-      {
-        float t0[32], t1[32];
-        tc::tmem_ld32(tmem_row, t0);
-        tc::tmem_ld32(tmem_row + 32, t1);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) { v[c] = t0[c]; v[32 + c] = t1[c]; }
-      }
+      tc::tmem_ld64(tmem_row, v);
       const float* bs = par_s + layer * 3 * MX_H;
-      float s = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) { v[c] = fmaxf(v[c] + bs[c], 0.f); s += v[c]; }
-      const float mean = s * (1.f / 64.f);
-      float q = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) { const float d = v[c] - mean; q += d * d; }
-      const float rstd = rsqrtf(q * (1.f / 64.f) + MX_LN_EPS);
+      for (int c = 0; c < 64; ++c) v[c] = fmaxf(v[c] + bs[c], 0.f);
+      const float mean = tc_sum64(v) * (1.f / 64.f);
+      const float rstd = rsqrtf(tc_sumsq64(v, mean, 64) * (1.f / 64.f) + MX_LN_EPS);
       float* u_out = layer == 0 ? a.u1 : a.u2;
       float* st_out = layer == 0 ? a.st1 : a.st2;
       if (live && ok && u_out) {
@@ -331,6 +368,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
       tc_put_row64(a_hi, a_lo, tid, v);      // the MMAs that read the previous A tile have completed (mbarrier)
     }
     // ---- gi = x2 . W_ih^T + b_ih ----
+    mx_cp_wait<0>();
     tc::fence_async_smem();
     tc::fence_before();
     __syncthreads();
@@ -340,12 +378,13 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
     phase ^= 1;
     tc::fence_after();
     float* gi = a.gi[net];
-    for (int c0 = 0; c0 < MX_G; c0 += 32) {
-      float t0[32];
-      tc::tmem_ld32(tmem_row + c0, t0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < MX_G; c0 += 64) {
+      float t0[64];
+      tc::tmem_ld64(tmem_row + c0, t0);
       if (ok) {
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4)
+        for (int c4 = 0; c4 < 16; ++c4)
           *reinterpret_cast<float4*>(gi + (size_t)m * MX_G + c0 + 4 * c4) =
               make_float4(t0[4 * c4] + bih_s[c0 + 4 * c4], t0[4 * c4 + 1] + bih_s[c0 + 4 * c4 + 1], t0[4 * c4 + 2] + bih_s[c0 + 4 * c4 + 2],
                           t0[4 * c4 + 3] + bih_s[c0 + 4 * c4 + 3]);

@@ -49,7 +49,8 @@ class MaddpgCfg(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("n_agents", "obs_dim", "act_dim", "state_dim", "hidden", "episode_len", "max_batch", "num_q",
                                           "actor_update_interval", "use_huber", "use_per")] +
                 [(n, C.c_float) for n in ("gamma", "huber_delta", "per_nu", "per_eps", "lr", "adam_beta1", "adam_beta2", "adam_eps",
-                                          "max_grad_norm", "tau", "weight_decay", "target_noise")])
+                                          "max_grad_norm", "tau", "weight_decay", "target_noise")] +
+                [("discrete", C.c_int32)])
 
 
 class ParamEntry(C.Structure):
@@ -114,6 +115,7 @@ def _declare(lib):
         "mx_maddpg_create": (C.c_int, [C.POINTER(MaddpgCfg), C.POINTER(vp), C.POINTER(vp), vp, i64, C.POINTER(vp)]),
         "mx_maddpg_destroy": (None, [vp]),
         "mx_maddpg_step": (C.c_int, [vp, C.POINTER(Batch), vp, C.POINTER(i32), vp]),
+        "mx_maddpg_step_ex": (C.c_int, [vp, C.POINTER(Batch), vp, vp, C.POINTER(i32), vp]),
         "mx_maddpg_info": (vp, [vp]),
         "mx_maddpg_priorities": (vp, [vp]),
         "mx_maddpg_grad_views": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),

@@ -1,8 +1,9 @@
 """Drop-in `R_MADDPGPolicy` (reference: offpolicy/algorithms/r_maddpg/algorithm/rMADDPGPolicy.py) for continuous (Box)
-action spaces.  `actor`, `critic`, `target_actor`, `target_critic` are named views (reference state_dict keys) of the flat
+and Discrete action spaces.  `actor`, `critic`, `target_actor`, `target_critic` are named views (reference state_dict keys) of the flat
 device vectors the CUDA learner updates in place; the two Adam states live beside them.  Rollout-time `get_actions`
 (one env step) runs a handful of torch ops on those views; everything update-time is inside `mx_maddpg_step`.
-Discrete / MultiDiscrete action spaces (Gumbel-softmax actors) are not built yet and raise."""
+Discrete actors follow rMADDPGPolicy.py:104-120: arg-max one-hot, hard Gumbel-softmax (draws from torch's CPU RNG like
+utils/util.py:127-140) and epsilon-greedy exploration.  MultiDiscrete action spaces are not built and raise."""
 import ctypes as C
 
 import numpy as np
@@ -11,16 +12,40 @@ import torch.nn.functional as F
 
 from offpolicy._b200 import capi
 from offpolicy._b200.flat import FlatModule
-from offpolicy._b200.host_util import space_dim, is_discrete
+from offpolicy._b200.host_util import space_dim, is_discrete, LinearDecay
 
 
-def maddpg_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, max_batch, td3, target_noise, actor_update_interval):
+def sample_gumbel(shape, eps=1e-20):
+    """utils/util.py:127-130: one `uniform_` draw from torch's CPU generator."""
+    u = torch.empty(*shape).uniform_()
+    return -torch.log(-torch.log(u + eps) + eps)
+
+
+def onehot_from_logits(logits, avail=None):
+    """utils/util.py:106-118 (eps = 0): every maximal logit is hot; unavailable actions are forced to -1e10."""
+    if avail is not None:
+        logits = logits.clone()
+        logits[torch.as_tensor(np.asarray(avail), dtype=torch.float32).to(logits.device) == 0] = -1e10
+    return (logits == logits.max(dim=-1, keepdim=True)[0]).float()
+
+
+def gumbel_softmax_hard(logits, avail=None):
+    """utils/util.py:133-166 with hard=True, temperature 1: the Gumbel draw is added on the CPU (util.py:137-139)."""
+    y = logits.cpu() + sample_gumbel(logits.shape)
+    if avail is not None:
+        y[torch.as_tensor(np.asarray(avail), dtype=torch.float32) == 0] = -1e10
+    y = F.softmax(y / 1.0, dim=-1)
+    return ((onehot_from_logits(y) - y) + y).to(logits.device)
+
+
+def maddpg_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, max_batch, td3, target_noise, actor_update_interval,
+                      discrete=False):
     return capi.MaddpgCfg(n_agents=n_agents, obs_dim=obs_dim, act_dim=act_dim, state_dim=state_dim, hidden=args.hidden_size,
                           episode_len=episode_len, max_batch=max_batch, num_q=2 if td3 else 1, actor_update_interval=actor_update_interval,
                           use_huber=int(args.use_huber_loss), use_per=int(args.use_per), gamma=args.gamma, huber_delta=args.huber_delta,
                           per_nu=args.per_nu, per_eps=args.per_eps, lr=args.lr, adam_beta1=0.9, adam_beta2=0.999, adam_eps=args.opti_eps,
                           max_grad_norm=args.max_grad_norm, tau=args.tau, weight_decay=float(getattr(args, "weight_decay", 0) or 0),
-                          target_noise=float(target_noise or 0.0))
+                          target_noise=float(target_noise or 0.0), discrete=int(bool(discrete)))
 
 
 def maddpg_entries(cfg, which):
@@ -83,14 +108,16 @@ class R_MADDPGPolicy(object):
         self.output_dim = self.act_dim
         self.hidden_size = self.args.hidden_size
         self.discrete = is_discrete(self.act_space)
-        self.multidiscrete = False
-        if self.discrete:
-            raise NotImplementedError("B200 R-MADDPG path: only continuous (Box) action spaces are implemented so far")
+        self.multidiscrete = "MultiDiscrete" in self.act_space.__class__.__name__
+        if self.multidiscrete:
+            raise NotImplementedError("B200 R-MADDPG path: MultiDiscrete action spaces are not implemented (Box and Discrete are)")
+        if self.discrete and train:
+            self.exploration = LinearDecay(self.args.epsilon_start, self.args.epsilon_finish, self.args.epsilon_anneal_time)   # :57-60
         self.td3, self.target_noise = bool(td3), target_noise
         n_agents = self.central_act_dim // self.act_dim
         capi.lib()
         self.dev = capi.device()
-        cfg = maddpg_cfg_struct(self.args, n_agents, self.obs_dim, self.act_dim, self.central_obs_dim, 1, 1, td3, target_noise, 1)
+        cfg = maddpg_cfg_struct(self.args, n_agents, self.obs_dim, self.act_dim, self.central_obs_dim, 1, 1, td3, target_noise, 1, self.discrete)
         self._a_entries, self.Pa = maddpg_entries(cfg, 0)
         self._c_entries, self.Pc = maddpg_entries(cfg, 1)
         z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.dev)
@@ -136,6 +163,25 @@ class R_MADDPGPolicy(object):
                 out = torch.stack(outs)
             else:
                 out, h = self._actor_step(views, o, h)
+        eps = None
+        if self.discrete:                                                                   # rMADDPGPolicy.py:104-120
+            if use_gumbel or (use_target and self.target_noise is not None):
+                out = gumbel_softmax_hard(out, available_actions)
+            elif explore:
+                assert o.dim() == 2, "Cannot do exploration on a sequence!"
+                onehot_actions = gumbel_softmax_hard(out, available_actions)
+                batch_size = o.shape[0]
+                eps = self.exploration.eval(t_env)
+                rand_numbers = np.random.rand(batch_size, 1)
+                logits = torch.ones(batch_size, self.act_dim)
+                if available_actions is not None:
+                    logits[torch.as_tensor(np.asarray(available_actions), dtype=torch.float32) == 0] = -1e10     # avail_choose, util.py:297-302
+                random_actions = torch.distributions.OneHotCategorical(logits=logits).sample().numpy()
+                take_random = (rand_numbers < eps).astype(int)
+                out = (1 - take_random) * onehot_actions.cpu().numpy() + take_random * random_actions
+            else:
+                out = onehot_from_logits(out, available_actions)
+            return out, h, eps
         if explore:
             assert o.dim() == 2, "Cannot do exploration on a sequence!"
             out = torch.empty(out.shape).normal_(mean=0, std=self.args.act_noise_std).to(out.device) + out     # util.py:217-218
@@ -144,6 +190,11 @@ class R_MADDPGPolicy(object):
         return out, h, None
 
     def get_random_actions(self, obs, available_actions=None):
+        if self.discrete:                                                                   # rMADDPGPolicy.py:143-150
+            logits = torch.ones(obs.shape[0], self.act_dim)
+            if available_actions is not None:
+                logits[torch.as_tensor(np.asarray(available_actions), dtype=torch.float32) == 0] = -1e10
+            return torch.distributions.OneHotCategorical(logits=logits).sample().numpy()
         return np.random.uniform(self.act_space.low, self.act_space.high, size=(obs.shape[0], self.act_dim))
 
     def init_hidden(self, num_agents, batch_size):

@@ -3,7 +3,9 @@
 `shared_train_policy_on_batch(p_id, batch)` = one `mx_maddpg_step`: target-actor next actions, critic sequence + target
 branch steps, TD target, critic loss/backward/Adam, then (every `actor_update_interval`-th call) the actor update through
 the updated critic -- all on the device.  MATD3's Gaussian target-action noise is drawn on the host with the reference's
-own call (`torch.empty(shape).normal_`, utils/util.py:217-218) so a seeded run consumes torch's CPU RNG identically.
+own call (`torch.empty(shape).normal_`, utils/util.py:217-218) so a seeded run consumes torch's CPU RNG identically; for
+Discrete actors the Gumbel draws of the target actions (MATD3) and of the actor update (`use_gumbel=True`, r_maddpg.py:277) are
+drawn the same way (utils/util.py:127-130), in the reference's order.
 `cent_train_policy_on_batch` (per-agent centralised observations) is unusable in the reference and is not built."""
 import ctypes as C
 
@@ -11,12 +13,12 @@ import numpy as np
 import torch
 
 from offpolicy._b200 import capi
-from offpolicy.algorithms.r_maddpg.algorithm.rMADDPGPolicy import maddpg_cfg_struct
+from offpolicy.algorithms.r_maddpg.algorithm.rMADDPGPolicy import maddpg_cfg_struct, sample_gumbel
 from offpolicy.utils.rec_buffer import SampledBatch, DeviceArray
 
 
 class _HostBatchC(object):
-    """Device copy of a reference-layout NumPy batch (continuous actions)."""
+    """Device copy of a reference-layout NumPy batch."""
 
     def __init__(self, cfg, dev):
         B, T, N = cfg.max_batch, cfg.episode_len, cfg.n_agents
@@ -26,6 +28,7 @@ class _HostBatchC(object):
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
         self.obs, self.share, self.acts = z(B, T + 1, N, self.obs_ld), z(B, T + 1, self.share_ld), z(B, T, N, self.act_ld)
         self.rew, self.dones, self.dones_env, self.weights = z(B, T, N), z(B, T, N), z(B, T), z(B)
+        self.avail = None
         self.dev = dev
 
     def pack(self, batch, p_id, use_per):
@@ -42,11 +45,17 @@ class _HostBatchC(object):
         self.dones_env[:B] = t(dones_env[p_id])[..., 0].permute(1, 0)
         if use_per:
             self.weights[:B] = t(weights)
+        has_avail = _avail is not None and _avail.get(p_id) is not None
+        if has_avail:
+            if self.avail is None:
+                self.avail = torch.ones(c.max_batch, c.episode_len + 1, c.n_agents, self.act_ld, dtype=torch.float32, device=self.dev)
+            self.avail[:B, :, :, :c.act_dim] = t(_avail[p_id]).permute(2, 1, 0, 3)
         b = capi.Batch()
         b.B, b.obs_ld, b.share_ld, b.act_ld = B, self.obs_ld, self.share_ld, self.act_ld
         b.obs, b.share, b.acts = self.obs.data_ptr(), self.share.data_ptr(), self.acts.data_ptr()
         b.rewards, b.dones, b.dones_env = self.rew.data_ptr(), self.dones.data_ptr(), self.dones_env.data_ptr()
         b.weights = self.weights.data_ptr() if use_per else None
+        b.avail = self.avail.data_ptr() if has_avail else None
         return b
 
 
@@ -70,7 +79,7 @@ class R_MADDPG(object):
         lib = capi.lib()
         self.dev = capi.device()
         self.cfg = maddpg_cfg_struct(args, num_agents, pol.obs_dim, pol.act_dim, pol.central_obs_dim, self.episode_length, self.max_batch,
-                                     pol.td3, pol.target_noise if pol.td3 else 0.0, actor_update_interval)
+                                     pol.td3, pol.target_noise if pol.td3 else 0.0, actor_update_interval, pol.discrete)
         nbytes = int(lib.mx_maddpg_workspace_bytes(C.byref(self.cfg)))
         if nbytes < 0:
             raise capi.MxError(lib.mx_last_error().decode())
@@ -87,6 +96,7 @@ class R_MADDPG(object):
         self._prio = self.workspace[pp:pp + 4 * self.max_batch].view(torch.float32)
         self._host_batch = None
         self._noise_dev = None
+        self._actor_noise_dev = None
 
     def __del__(self):
         try:
@@ -120,10 +130,23 @@ class R_MADDPG(object):
         if not pol.td3:
             return None
         T, N, Ac = self.episode_length, self.num_agents, pol.act_dim
-        noise = torch.empty(T + 1, N * B, Ac).normal_(mean=0, std=float(pol.target_noise))          # util.py:217-218
+        if pol.discrete:
+            noise = sample_gumbel((T + 1, N * B, Ac))                                              # util.py:137 via rMADDPGPolicy.py:105-106
+        else:
+            noise = torch.empty(T + 1, N * B, Ac).normal_(mean=0, std=float(pol.target_noise))      # util.py:217-218
         ours = noise.view(T + 1, N, B, Ac).permute(2, 0, 1, 3).contiguous()                      # -> [b][t][n][Ac]
         self._noise_dev = ours.to(self.dev, non_blocking=True)
         return self._noise_dev
+
+    def _actor_noise(self, B):
+        """Gumbel draws of the actor update's `get_actions(..., use_gumbel=True)` over obs[:-1] (r_maddpg.py:277), padded to T+1 steps."""
+        pol = self.policies["policy_0"]
+        T, N, Ac = self.episode_length, self.num_agents, pol.act_dim
+        g = sample_gumbel((T, N * B, Ac))
+        ours = torch.zeros(B, T + 1, N, Ac)
+        ours[:, :T] = g.view(T, N, B, Ac).permute(2, 0, 1, 3)
+        self._actor_noise_dev = ours.to(self.dev, non_blocking=True)
+        return self._actor_noise_dev
 
     def train_policy_on_batch(self, update_policy_id, batch):
         if self.use_same_share_obs:
@@ -137,8 +160,11 @@ class R_MADDPG(object):
         lib = capi.lib()
         b = self._device_batch(batch)
         noise = self._target_noise(b.B)
+        pol = self.policies["policy_0"]
+        will_update_actor = self.num_updates[update_policy_id] % self.actor_update_interval == 0
+        actor_noise = self._actor_noise(b.B) if (pol.discrete and will_update_actor) else None
         upd = C.c_int32()
-        capi.check(lib.mx_maddpg_step(self.handle, C.byref(b), capi.ptr(noise), C.byref(upd), capi.stream_ptr()))
+        capi.check(lib.mx_maddpg_step_ex(self.handle, C.byref(b), capi.ptr(noise), capi.ptr(actor_noise), C.byref(upd), capi.stream_ptr()))
         info = self._info
         train_info = {"critic_loss": info[0], "critic_grad_norm": info[1]}
         if upd.value:

@@ -7,7 +7,9 @@ r_maddpg/algorithm/rMADDPGPolicy.py:11-170 (two Adams with weight_decay, Polyak 
 
   1. next actions: target actor over the full (T+1)-sequence of every agent (rows agent-major), Box actions are the raw
      output (MADDPG) or + N(0, target_noise) (MATD3, `gaussian_noise`, util.py:217-218 -- drawn by the caller from the
-     torch CPU RNG exactly like the reference and handed in as `noise`); drop t=0, concat agents on the feature axis.
+     torch CPU RNG exactly like the reference and handed in as `noise`); Discrete actions are the arg-max one-hot of the
+     logits (MADDPG, `onehot_from_logits` util.py:106-125) or a hard Gumbel-softmax sample (MATD3, util.py:127-166;
+     `noise` = the Gumbel(0,1) draws); drop t=0, concat agents on the feature axis.
   2. Q_k = critic(cent_obs[:-1], buffer cent_act) as one sequence from h0 = 0                                 (:162)
   3. target: h <- 0; for t: _, h = target_critic(obs_t, act_t, h); Q'_t = min_k target_critic(obs_{t+1}, nact_t, h)  (:168-182)
   4. y = r(agent 0) + gamma (1 - dones_env) Q'; Q_k, y masked by (1 - curr_dones) (dones_env shifted by one step);
@@ -15,6 +17,8 @@ r_maddpg/algorithm/rMADDPGPolicy.py:11-170 (two Adams with weight_decay, Polyak 
   5. actor (every actor_update_interval updates), with the UPDATED critic: actor over obs[:-1]; N stacked copies of the
      batch, copy i has agent i's action replaced by the actor's; Q_t = critic(obs_t, replaced_t, h)[head 0] with h advanced on
      buffer actions only; actor_loss = -sum Q (1 - done_mask_i) / sum(1 - done_mask); clip 10; Adam(actor)    (:236-327)
+     Discrete: the actor's actions are hard Gumbel-softmax samples with the straight-through gradient of the soft sample
+     (`use_gumbel=True`, r_maddpg.py:277; `actor_noise` = the Gumbel draws of that call).
 """
 import copy
 from dataclasses import dataclass
@@ -50,6 +54,29 @@ class MaddpgConfig:
     target_noise: float = 0.2
     actor_update_interval: int = 1
     gain: float = 0.01
+    discrete: bool = False            # Discrete(act_dim): one-hot actions, Gumbel-softmax actor
+
+
+def onehot_of_max(x, avail=None):
+    """`onehot_from_logits` without exploration (util.py:106-118): every maximal entry is hot; unavailable -> -1e10."""
+    if avail is not None:
+        x = torch.where(avail == 0, torch.full_like(x, -1e10), x)
+    return (x == x.max(dim=-1, keepdim=True)[0]).float()
+
+
+def hard_gumbel_softmax(logits, gumbel, avail=None):
+    """util.py:133-166 with temperature 1 and hard=True: value (y_hard - y) + y, gradient of the soft sample y."""
+    y = logits + gumbel
+    if avail is not None:
+        y = torch.where(avail == 0, torch.full_like(y, -1e10), y)
+    y = torch.softmax(y / 1.0, dim=-1)
+    return (onehot_of_max(y) - y).detach() + y
+
+
+def sample_gumbel(shape, eps=1e-20):
+    """util.py:127-130: one uniform_ draw from torch's CPU generator."""
+    u = torch.empty(*shape).uniform_()
+    return -torch.log(-torch.log(u + eps) + eps)
 
 
 class _ActHead(nn.Module):
@@ -123,9 +150,9 @@ class MaddpgLearner(object):
             return small * e ** 2 / 2 + (1 - small) * d * (e.abs() - d / 2)
         return e ** 2
 
-    def step(self, batch, noise=None):
+    def step(self, batch, noise=None, actor_noise=None):
         cfg = self.cfg
-        obs, share, acts, rew, dones, dones_env, _avail, weights, _idx = batch
+        obs, share, acts, rew, dones, dones_env, avail, weights, _idx = batch
         N, B, T = cfg.n_agents, obs.shape[2], acts.shape[1]
         t32 = lambda x: torch.as_tensor(x, dtype=torch.float32)
         s = t32(share)
@@ -133,13 +160,16 @@ class MaddpgLearner(object):
         r = t32(rew[0])
         curr = torch.cat([torch.zeros(1, B, 1), de[:T - 1]], 0)
         x_all = self.stack(obs)                                        # (T+1, N*B, O)
+        av_all = self.stack(avail) if (avail is not None and cfg.discrete) else None
         cent_act = torch.cat(list(t32(acts)), dim=-1)                  # (T, B, N*Ac) agents on the feature axis
         update_actor = self.num_updates % cfg.actor_update_interval == 0
         info = {}
         # 1. next actions from the target actor
         with torch.no_grad():
             nact, _ = self.tgt_actor(x_all)
-            if cfg.td3:
+            if cfg.discrete:
+                nact = hard_gumbel_softmax(nact, t32(noise), av_all) if cfg.td3 else onehot_of_max(nact, av_all)
+            elif cfg.td3:
                 nact = nact + t32(noise)
             nact = nact[1:]
             cent_nact = torch.cat(nact.split(B, dim=1), dim=-1)        # (T, B, N*Ac)
@@ -177,6 +207,8 @@ class MaddpgLearner(object):
             for p in self.critic.parameters():
                 p.requires_grad = False
             a_seq, _ = self.actor(x_all[:-1])                          # (T, N*B, Ac)
+            if cfg.discrete:
+                a_seq = hard_gumbel_softmax(a_seq, t32(actor_noise), None if av_all is None else av_all[:-1])
             agent_a = a_seq.split(B, dim=1)
             buf_a = list(t32(acts))
             dm = torch.cat([torch.cat([torch.zeros(1, B, 1), t32(dones[i])[:T - 1]], 0) for i in range(N)], dim=1)   # (T, N*B, 1)
@@ -234,3 +266,20 @@ def synth_batch_cont(cfg, B, T, seed=0, var_len=True):
                 dn = min(L[b], rs.randint(T // 3, T + 1))       # an agent may die earlier than the episode ends
                 dones[n, dn - 1:, b, 0] = 1.0
     return obs, share, acts, rew, dones, dones_env, None
+
+
+def synth_batch_disc(cfg, B, T, seed=0, var_len=True):
+    """Same as `synth_batch_cont` with one-hot buffer actions (Discrete(act_dim))."""
+    b = list(synth_batch_cont(cfg, B, T, seed, var_len))
+    rs = np.random.RandomState(seed + 7919)
+    a = rs.randint(0, cfg.act_dim, size=(cfg.n_agents, T, B))
+    b[2] = np.eye(cfg.act_dim, dtype=np.float32)[a]
+    return tuple(b)
+
+
+def synth_avail(cfg, B, T, seed=0):
+    """Bernoulli(0.7) availability, action 0 always available: (N, T+1, B, A)."""
+    rs = np.random.RandomState(seed + 104729)
+    av = (rs.rand(cfg.n_agents, T + 1, B, cfg.act_dim) < 0.7).astype(np.float32)
+    av[..., 0] = 1.0
+    return av

@@ -184,8 +184,8 @@ if __name__ == "__main__" and "maddpg" not in sys.argv[1:]:
 # ---------------------------------------------------------------------------------------------------------------
 # recurrent MADDPG / MATD3 (Box actions; shared centralised observation)
 # ---------------------------------------------------------------------------------------------------------------
-def gen_maddpg(name, cfg, flags=(), B=4, T=6, steps=2, per=False):
-    from oracle.maddpg import synth_batch_cont
+def gen_maddpg(name, cfg, flags=(), B=4, T=6, steps=2, per=False, use_avail=False):
+    from oracle.maddpg import synth_batch_cont, synth_batch_disc, synth_avail
     rh.import_reference()
     sp = rh.gym_spaces()
     algo = "rmatd3" if cfg.td3 else "rmaddpg"
@@ -199,7 +199,8 @@ def gen_maddpg(name, cfg, flags=(), B=4, T=6, steps=2, per=False):
     torch.manual_seed(1)
     np.random.seed(1)
     info = dict(obs_space=sp.Box(-np.inf, np.inf, (cfg.obs_dim,)), share_obs_space=sp.Box(-np.inf, np.inf, (cfg.state_dim,)),
-                act_space=sp.Box(-1.0, 1.0, (cfg.act_dim,)), cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
+                act_space=sp.Discrete(cfg.act_dim) if cfg.discrete else sp.Box(-1.0, 1.0, (cfg.act_dim,)), cent_obs_dim=cfg.state_dim,
+                cent_act_dim=cfg.act_dim * cfg.n_agents)
     dev = torch.device("cpu")
     pol = Policy({"args": args, "device": dev}, info)
     tr = Trainer(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=dev, episode_length=T)
@@ -209,8 +210,23 @@ def gen_maddpg(name, cfg, flags=(), B=4, T=6, steps=2, per=False):
     out = {}
     for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
         out.update(sd_np("init.%s." % tag, mod))
+    # rollout-time get_actions (one env step): greedy and exploring, seeded (rMADDPGPolicy.py:62-128)
+    rs = np.random.RandomState(77)
+    a_obs = rs.randn(cfg.n_agents * B, cfg.obs_dim).astype(np.float32)
+    a_h = (0.3 * rs.randn(cfg.n_agents * B, cfg.hidden)).astype(np.float32)
+    out["act.in.obs"], out["act.in.h"] = a_obs, a_h
+    with torch.no_grad():
+        a, h2, _ = pol.get_actions(a_obs, None, torch.from_numpy(a_h), explore=False)
+        out["act.greedy"], out["act.new_h"] = np.asarray(a), h2.numpy()
+        torch.manual_seed(5); np.random.seed(5)
+        a, _, eps = pol.get_actions(a_obs, None, torch.from_numpy(a_h), t_env=20000, explore=True)
+        out["act.explore"] = np.asarray(a, dtype=np.float32)
+        if eps is not None:
+            out["act.eps"] = np.asarray(eps, np.float64)
+        torch.manual_seed(6); np.random.seed(6)
+        out["act.random"] = np.asarray(pol.get_random_actions(a_obs), dtype=np.float32)
     for s in range(steps):
-        b = synth_batch_cont(cfg, B, T, seed=200 + s)
+        b = (synth_batch_disc if cfg.discrete else synth_batch_cont)(cfg, B, T, seed=200 + s)
         for k, v in zip(["obs", "share", "acts", "rew", "dones", "dones_env"], b[:6]):
             out["s%d.in.%s" % (s, k)] = v
         w = idx = None
@@ -219,9 +235,20 @@ def gen_maddpg(name, cfg, flags=(), B=4, T=6, steps=2, per=False):
             idx = np.arange(B)
             out["s%d.in.weights" % s] = w
         d = lambda x: {"policy_0": x}
-        batch = (d(b[0]), d(b[1]), d(b[2]), d(b[3]), d(b[4]), d(b[5]), d(None), w, idx)
+        av = synth_avail(cfg, B, T, seed=300 + s) if use_avail else None
+        if use_avail:
+            out["s%d.in.avail" % s] = av
+        batch = (d(b[0]), d(b[1]), d(b[2]), d(b[3]), d(b[4]), d(b[5]), d(av), w, idx)
         torch.manual_seed(1000 + s)
-        if cfg.td3:
+        if cfg.discrete:
+            # replay the reference's own draws: target actor (MATD3 only), then the actor update's Gumbel-softmax
+            from offpolicy.utils.util import sample_gumbel as ref_gumbel
+            if cfg.td3:
+                out["s%d.in.noise" % s] = ref_gumbel((T + 1, cfg.n_agents * B, cfg.act_dim)).numpy()
+            if tr.num_updates["policy_0"] % tr.actor_update_interval == 0:
+                out["s%d.in.actor_noise" % s] = ref_gumbel((T, cfg.n_agents * B, cfg.act_dim)).numpy()
+            torch.manual_seed(1000 + s)
+        elif cfg.td3:
             out["s%d.in.noise" % s] = torch.empty(T + 1, cfg.n_agents * B, cfg.act_dim).normal_(mean=0, std=float(args.target_action_noise_std)).numpy()
             torch.manual_seed(1000 + s)
         info_t, prio, _ = tr.shared_train_policy_on_batch("policy_0", batch)
@@ -241,7 +268,8 @@ def gen_maddpg(name, cfg, flags=(), B=4, T=6, steps=2, per=False):
         if s == steps - 1:      # parameters only after the last step (keeps the fixture small)
             for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
                 out.update(sd_np("final.%s." % tag, mod))
-    out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, cfg.hidden, B, T, steps, int(cfg.td3), int(per)])
+    out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, cfg.hidden, B, T, steps, int(cfg.td3), int(per),
+                                int(cfg.discrete)])
     out["meta.hparams"] = np.array([args.gamma, args.lr, args.opti_eps, args.max_grad_norm, args.tau, args.huber_delta, args.per_nu,
                                     args.per_eps, float(args.target_action_noise_std), args.weight_decay], dtype=np.float64)
     path = os.path.join(HERE, name + ".npz")
@@ -254,6 +282,9 @@ def main_maddpg():
     gen_maddpg("maddpg_box", MaddpgConfig())
     gen_maddpg("matd3_box", MaddpgConfig(td3=True, actor_update_interval=2))
     gen_maddpg("maddpg_box_per", MaddpgConfig(use_per=True), flags=["--use_per"], per=True, steps=1)
+    gen_maddpg("maddpg_disc", MaddpgConfig(act_dim=5, discrete=True))
+    gen_maddpg("matd3_disc", MaddpgConfig(act_dim=5, discrete=True, td3=True, actor_update_interval=2), steps=3)
+    gen_maddpg("matd3_disc_avail", MaddpgConfig(act_dim=5, discrete=True, td3=True, actor_update_interval=2), steps=3, use_avail=True)
 
 
 if __name__ == "__main__" and "maddpg" in sys.argv[1:]:

@@ -6,7 +6,7 @@ import torch
 
 from helpers import load_golden, sub, rel_err
 from qmix_checks import close
-from test_oracle_maddpg import maddpg_from_golden, maddpg_batch
+from test_oracle_maddpg import maddpg_from_golden, maddpg_batch, actor_noise
 
 
 class Box(object):
@@ -14,6 +14,11 @@ class Box(object):
         self.shape = (d,)
         self.low = np.full(d, low, np.float32)
         self.high = np.full(d, high, np.float32)
+
+
+class Discrete(object):
+    def __init__(self, n):
+        self.n = n
 
 
 def make_args(cfg, B):
@@ -35,7 +40,7 @@ def build(cfg, B, T):
         from offpolicy.algorithms.r_maddpg.algorithm.rMADDPGPolicy import R_MADDPGPolicy as Policy
         from offpolicy.algorithms.r_maddpg.r_maddpg import R_MADDPG as Trainer
     args = make_args(cfg, B)
-    info = dict(obs_space=Box(cfg.obs_dim, -np.inf, np.inf), share_obs_space=Box(cfg.state_dim, -np.inf, np.inf), act_space=Box(cfg.act_dim),
+    info = dict(obs_space=Box(cfg.obs_dim, -np.inf, np.inf), share_obs_space=Box(cfg.state_dim, -np.inf, np.inf), act_space=Discrete(cfg.act_dim) if cfg.discrete else Box(cfg.act_dim),
                 cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
     pol = Policy({"args": args, "device": capi.device()}, info)
     tr = Trainer(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=capi.device(), episode_length=T)
@@ -64,9 +69,9 @@ def check_golden(name):
     problems = []
     for s in range(steps):
         batch, noise = maddpg_batch(g, s)
-        torch.manual_seed(1000 + s)                         # the trainer draws the MATD3 noise from torch's CPU RNG like the reference
+        torch.manual_seed(1000 + s)                         # the trainer draws the MATD3 / Gumbel noise from torch's CPU RNG like the reference
         info, prio, _ = tr.shared_train_policy_on_batch("policy_0", ref_tuple(batch))
-        ref, rprio = L.step(batch, noise)
+        ref, rprio = L.step(batch, noise, actor_noise(g, s))
         ga, gc = tr.grad_views()
         for key in ("critic_loss", "critic_grad_norm"):
             e = rel_err(info[key].cpu(), g["s%d.%s" % (s, key)])
@@ -105,3 +110,30 @@ def check_golden(name):
             if err > 5e-3 * cfg.lr * steps + 1e-7:
                 problems.append("final %s.%s err %.3e" % (tag, k, err))
     assert not problems, "\n".join(problems[:40])
+
+
+def check_get_actions(name):
+    """Rollout-time `get_actions` / `get_random_actions` against the reference (seeded), rMADDPGPolicy.py:62-160."""
+    g = load_golden(name)
+    L, cfg, B, T, steps = maddpg_from_golden(g)
+    args, pol, tr = build(cfg, B, T)
+    pol.actor.load_state_dict(sub(g, "init.actor."))
+    obs, h = g["act.in.obs"], torch.from_numpy(g["act.in.h"])
+    a, h2, _ = pol.get_actions(obs, None, h, explore=False)
+    a = a.cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    if cfg.discrete:
+        assert np.array_equal(a, g["act.greedy"])
+    else:
+        assert np.abs(a - g["act.greedy"]).max() < 1e-5
+    assert np.abs(h2.cpu().numpy() - g["act.new_h"]).max() < 1e-5
+    torch.manual_seed(5); np.random.seed(5)
+    a, _, eps = pol.get_actions(obs, None, h, t_env=20000, explore=True)
+    a = a.cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    if cfg.discrete:
+        assert abs(eps - float(g["act.eps"])) < 1e-12
+        assert np.array_equal(a.astype(np.float32), g["act.explore"])
+    else:
+        assert np.abs(a - g["act.explore"]).max() < 1e-5
+    torch.manual_seed(6); np.random.seed(6)
+    r = np.asarray(pol.get_random_actions(obs), dtype=np.float32)
+    assert np.array_equal(r, g["act.random"])

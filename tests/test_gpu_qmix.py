@@ -204,7 +204,7 @@ def test_error_behaviour(gpu_engine):
 # ---------------------------------------------------------------------------------------------------------------
 # recurrent MADDPG / MATD3 (BASELINE config 3)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_box_per"])
+@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_box_per", "maddpg_disc", "matd3_disc", "matd3_disc_avail"])
 def test_maddpg_matches_reference_golden(gpu_engine, name):
     import maddpg_checks as mc
     mc.check_golden(name)
@@ -245,3 +245,48 @@ def test_config3_maddpg_spread_full_size_vs_oracle(gpu_engine, td3):
     for ours, ref in ((pol.actor, L.actor), (pol.critic, L.critic), (pol.target_actor, L.tgt_actor), (pol.target_critic, L.tgt_critic)):
         for k, v in ours.state_dict().items():
             assert float((v.cpu() - ref.state_dict()[k]).abs().max()) <= 5e-3 * cfg.lr * 3 + 1e-7, k
+
+
+@pytest.mark.parametrize("td3", [False, True])
+def test_config3_maddpg_spread_discrete_full_size_vs_oracle(gpu_engine, td3):
+    """MPE simple_spread's real action space is Discrete(5) (envs/mpe/environment.py:62-63): arg-max one-hot / hard Gumbel-softmax
+    target actions and the straight-through Gumbel-softmax actor update, full size (N=3, T=25, B=32), vs the pinned oracle."""
+    import maddpg_checks as mc
+    from oracle.maddpg import MaddpgConfig, MaddpgLearner, synth_batch_disc, sample_gumbel
+    from oracle.qmix import randomize_all
+    torch.set_num_threads(8)
+    cfg = MaddpgConfig(act_dim=5, discrete=True, td3=td3, actor_update_interval=2 if td3 else 1, gain=1.0)
+    B, T = 32, 25
+    L = MaddpgLearner(cfg, seed=5)
+    randomize_all(L.actor, 1); randomize_all(L.critic, 2)
+    L.sync_targets()
+    randomize_all(L.tgt_actor, 3, 0.05); randomize_all(L.tgt_critic, 4, 0.05)
+    args, pol, tr = mc.build(cfg, B, T)
+    for ours, ref in ((pol.actor, L.actor), (pol.critic, L.critic), (pol.target_actor, L.tgt_actor), (pol.target_critic, L.tgt_critic)):
+        ours.load_state_dict(ref.state_dict())
+    for s in range(3):
+        batch = synth_batch_disc(cfg, B, T, seed=40 + s) + (None, None)
+        upd = s % cfg.actor_update_interval == 0
+        torch.manual_seed(77 + s)
+        noise = sample_gumbel((T + 1, cfg.n_agents * B, cfg.act_dim)).numpy() if td3 else None
+        anoise = sample_gumbel((T, cfg.n_agents * B, cfg.act_dim)).numpy() if upd else None
+        torch.manual_seed(77 + s)
+        info, _, _ = tr.shared_train_policy_on_batch("policy_0", mc.ref_tuple(batch))
+        ref, _ = L.step(batch, noise, anoise)
+        assert rel_err(info["critic_loss"].cpu(), ref["critic_loss"]) < 1e-4
+        assert rel_err(info["critic_grad_norm"].cpu(), ref["critic_grad_norm"]) < 1e-4
+        assert bool(info["update_actor"]) == bool(ref["update_actor"]) == upd
+        if ref["update_actor"]:
+            assert rel_err(info["actor_loss"].cpu(), ref["actor_loss"]) < 1e-4
+            assert rel_err(info["actor_grad_norm"].cpu(), ref["actor_grad_norm"]) < 2e-4
+            pol.soft_target_updates()
+            L.soft_update()
+    for ours, ref in ((pol.actor, L.actor), (pol.critic, L.critic), (pol.target_actor, L.tgt_actor), (pol.target_critic, L.tgt_critic)):
+        for k, v in ours.state_dict().items():
+            assert float((v.cpu() - ref.state_dict()[k]).abs().max()) <= 5e-3 * cfg.lr * 3 + 1e-7, k
+
+
+@pytest.mark.parametrize("name", ["maddpg_box", "maddpg_disc", "matd3_disc"])
+def test_maddpg_rollout_actions_match_reference(gpu_engine, name):
+    import maddpg_checks as mc
+    mc.check_get_actions(name)

@@ -8,11 +8,13 @@ from helpers import load_golden, sub, rel_err
 
 def maddpg_from_golden(g):
     from oracle.maddpg import MaddpgConfig, MaddpgLearner
-    n, o, a, s, h, B, T, steps, td3, per = [int(v) for v in g["meta.cfg"]]
+    meta = [int(v) for v in g["meta.cfg"]]
+    n, o, a, s, h, B, T, steps, td3, per = meta[:10]
+    disc = bool(meta[10]) if len(meta) > 10 else False
     gamma, lr, eps, mgn, tau, hd, nu, peps, tn, wd = [float(v) for v in g["meta.hparams"]]
     cfg = MaddpgConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, hidden=h, gamma=gamma, lr=lr, opti_eps=eps, max_grad_norm=mgn,
                        tau=tau, huber_delta=hd, per_nu=nu, per_eps=peps, td3=bool(td3), target_noise=tn, weight_decay=wd,
-                       use_per=bool(per), actor_update_interval=2 if td3 else 1)
+                       use_per=bool(per), actor_update_interval=2 if td3 else 1, discrete=disc)
     L = MaddpgLearner(cfg)
     for tag, mod in (("actor", L.actor), ("critic", L.critic), ("tgt_actor", L.tgt_actor), ("tgt_critic", L.tgt_critic)):
         mod.load_state_dict(sub(g, "init.%s." % tag))
@@ -22,17 +24,21 @@ def maddpg_from_golden(g):
 def maddpg_batch(g, s):
     b = tuple(g["s%d.in.%s" % (s, k)] for k in ("obs", "share", "acts", "rew", "dones", "dones_env"))
     w = g.get("s%d.in.weights" % s)
-    return b + (None, w, np.arange(b[0].shape[2]) if w is not None else None), g.get("s%d.in.noise" % s)
+    return b + (g.get("s%d.in.avail" % s), w, np.arange(b[0].shape[2]) if w is not None else None), g.get("s%d.in.noise" % s)
 
 
-@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_box_per"])
+def actor_noise(g, s):
+    return g.get("s%d.in.actor_noise" % s)
+
+
+@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_box_per", "maddpg_disc", "matd3_disc", "matd3_disc_avail"])
 def test_oracle_reproduces_reference_maddpg(name):
     torch.set_num_threads(1)
     g = load_golden(name)
     L, cfg, B, T, steps = maddpg_from_golden(g)
     for s in range(steps):
         batch, noise = maddpg_batch(g, s)
-        info, prio = L.step(batch, noise)
+        info, prio = L.step(batch, noise, actor_noise(g, s))
         assert rel_err(info["critic_loss"], g["s%d.critic_loss" % s]) < 1e-6
         assert rel_err(info["critic_grad_norm"], g["s%d.critic_grad_norm" % s]) < 1e-5
         assert int(info["update_actor"]) == int(g["s%d.update_actor" % s])
@@ -49,3 +55,17 @@ def test_oracle_reproduces_reference_maddpg(name):
     for tag, mod in (("actor", L.actor), ("critic", L.critic), ("tgt_actor", L.tgt_actor), ("tgt_critic", L.tgt_critic)):
         for k, v in mod.state_dict().items():
             assert rel_err(v, g["final.%s.%s" % (tag, k)]) < 5e-6, (tag, k)
+
+
+def test_oracle_gumbel_draws_match_reference_stream():
+    """`sample_gumbel` consumes torch's CPU generator like the reference (util.py:127-130): the goldens' noise was produced by
+    the reference's own function after `torch.manual_seed(1000 + s)`."""
+    from oracle.maddpg import sample_gumbel
+    g = load_golden("matd3_disc")
+    meta = [int(v) for v in g["meta.cfg"]]
+    n, a, B, T = meta[0], meta[2], meta[5], meta[6]
+    torch.manual_seed(1000)
+    g1 = sample_gumbel((T + 1, n * B, a))
+    g2 = sample_gumbel((T, n * B, a))
+    assert np.array_equal(g1.numpy(), g["s0.in.noise"])
+    assert np.array_equal(g2.numpy(), g["s0.in.actor_noise"])
