@@ -48,8 +48,11 @@ def peaks():
 
 MADDPG_WORKLOADS = {
     # name: (n_agents, obs, act (Box), state, T, B, td3)    -- BASELINE.json configs[2]: MPE simple_spread shapes, continuous actions
-    "rmaddpg_spread": (3, 18, 2, 54, 25, 32, False),
-    "rmatd3_spread": (3, 18, 2, 54, 25, 32, True),
+    "rmaddpg_spread": (3, 18, 2, 54, 25, 32, False, False),
+    "rmatd3_spread": (3, 18, 2, 54, 25, 32, True, False),
+    # the env's real action space, Discrete(5) (envs/mpe/environment.py:62-63): one-hot actions, Gumbel-softmax actors
+    "rmaddpg_spread_disc": (3, 18, 5, 54, 25, 32, False, True),
+    "rmatd3_spread_disc": (3, 18, 5, 54, 25, 32, True, True),
 }
 
 
@@ -59,16 +62,23 @@ def run_maddpg(args):
     from offpolicy._b200 import capi
     import maddpg_checks as mc
     import replay_checks as rc
-    from oracle.maddpg import MaddpgConfig, MaddpgLearner, synth_batch_cont
-    n, o, a, sdim, T, B, td3 = MADDPG_WORKLOADS[args.workload]
-    cfg = MaddpgConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim, td3=td3, actor_update_interval=2 if td3 else 1, gain=1.0)
+    from oracle.maddpg import MaddpgConfig, MaddpgLearner, synth_batch_cont, synth_batch_disc, sample_gumbel
+    n, o, a, sdim, T, B, td3, disc = MADDPG_WORKLOADS[args.workload]
+    cfg = MaddpgConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim, td3=td3, actor_update_interval=2 if td3 else 1, gain=1.0, discrete=disc)
     E = min(args.buffer, 5000)
     rs = np.random.default_rng(0)
 
     def episodes(k):
         return [rs.standard_normal((T + 1, k, n, o), dtype=np.float32), np.repeat(rs.standard_normal((T + 1, k, 1, sdim), dtype=np.float32), n, 2),
-                rs.uniform(-1, 1, (T, k, n, a)).astype(np.float32), np.repeat(rs.standard_normal((T, k, 1, 1), dtype=np.float32), n, 2),
+                (np.eye(a, dtype=np.float32)[rs.integers(0, a, (T, k, n))] if disc else rs.uniform(-1, 1, (T, k, n, a)).astype(np.float32)), np.repeat(rs.standard_normal((T, k, 1, 1), dtype=np.float32), n, 2),
                 np.zeros((T, k, n, 1), np.float32), np.zeros((T, k, 1), np.float32)]
+
+    def cpu_noise(s):
+        """the draws the reference makes per update (util.py:127-130, 217-218)"""
+        upd = s % cfg.actor_update_interval == 0
+        if disc:
+            return (sample_gumbel((T + 1, n * B, a)).numpy() if td3 else None), (sample_gumbel((T, n * B, a)).numpy() if upd else None)
+        return (torch.empty(T + 1, n * B, a).normal_(0, cfg.target_noise).numpy() if td3 else None), None
 
     if args.impl == "reference":
         from oracle.replay import UniformReplay
@@ -83,8 +93,8 @@ def run_maddpg(args):
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             out, inds = buf.sample(B)
-            noise = torch.empty(T + 1, n * B, a).normal_(0, cfg.target_noise).numpy() if td3 else None
-            info, _ = L.step(out, noise)
+            noise, anoise = cpu_noise(s)
+            info, _ = L.step(out, noise, anoise)
             if info["update_actor"]:
                 L.soft_update()
             float(info["critic_loss"])
@@ -100,7 +110,7 @@ def run_maddpg(args):
     torch.cuda.set_device(0)
     lib = capi.lib()
     from offpolicy.utils.rec_buffer import RecReplayBuffer
-    info = {"policy_0": dict(obs_space=[o], share_obs_space=[sdim], act_space=mc.Box(a))}
+    info = {"policy_0": dict(obs_space=[o], share_obs_space=[sdim], act_space=mc.Discrete(a) if disc else mc.Box(a))}
     buf = RecReplayBuffer(info, {"policy_0": list(range(n))}, E, T, True, False, rng="device", max_batch=128)
     for c in range(0, E, 128):
         k = min(128, E - c)
@@ -138,10 +148,10 @@ def run_maddpg(args):
     L = MaddpgLearner(cfg, seed=1)
     tms = []
     for s in range(8):
-        batch = synth_batch_cont(cfg, B, T, seed=s) + (None, None)
-        noise = torch.empty(T + 1, n * B, a).normal_(0, cfg.target_noise).numpy() if td3 else None
+        batch = (synth_batch_disc if disc else synth_batch_cont)(cfg, B, T, seed=s) + (None, None)
         t0 = time.perf_counter()
-        i2, _ = L.step(batch, noise)
+        noise, anoise = cpu_noise(s)
+        i2, _ = L.step(batch, noise, anoise)
         if i2["update_actor"]:
             L.soft_update()
         if s >= 2:
@@ -151,7 +161,8 @@ def run_maddpg(args):
                           ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                           config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim,
                                       buffer_episodes=E, step="eager: device MT19937 sample + mx_maddpg_step (+ soft update when the actor was updated)"),
-                          e2e=dict(value=e2e, unit="steps/s", h2d_bytes_per_step=0 if not td3 else (T + 1) * n * B * a * 4, d2h_bytes_per_step=4,
+                          e2e=dict(value=e2e, unit="steps/s", h2d_bytes_per_step=((T + 1) * n * B * a * 4 if td3 else 0) + ((T + 1) * n * B * a * 4 // cfg.actor_update_interval if disc else 0),
+                                   d2h_bytes_per_step=4,
                                    path="RecReplayBuffer.sample + R_MADDPG.shared_train_policy_on_batch + soft_target_updates + D2H critic_loss"),
                           gpu_launches=launches, kernels_per_step=launches / args.steps,
                           roofline=dict(bound="tensor", kernel="(many small launches)", achieved=None, peak=peaks()["tflops_sustained"], unit="TFLOP/s",

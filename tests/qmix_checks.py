@@ -149,7 +149,12 @@ def check_step_against(g_or_none, name=None, intermediates=True):
                 d_ours = (v.cpu() - prv[k].cpu()).numpy()
                 d_want = want - prv[k].cpu().numpy()
                 err = np.abs(d_ours - d_want).max()
-                if err > 5e-3 * cfg.lr + 1e-9:
+                # Adam's step is lr * m_hat / (sqrt(v_hat) + eps): an absolute gradient error d moves it by up to lr * d / eps, so the
+                # 1e-4 gradient budget (relative to the tensor's largest entry) is propagated through that sensitivity.
+                gkey = "s%d.grad.%s.%s" % (s, role, k)
+                gmax = float(np.abs(g[gkey]).max()) if gkey in g else 0.0
+                lim = cfg.lr * min(2.0, 5e-3 + 1e-4 * gmax / cfg.opti_eps)
+                if err > lim + 1e-9:
                     problems.append("step %d param %s.%s: update err %.3e" % (s, role, k, err))
         for role, mod in (("tgt_agent", tr.target_q_network), ("tgt_mixer", tr.target_mixer)):
             for k, v in mod.state_dict().items():
