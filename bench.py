@@ -57,8 +57,9 @@ MADDPG_WORKLOADS = {
 
 
 def run_maddpg(args):
-    """R-MADDPG / R-MATD3 learner (BASELINE config 3): sample -> shared_train_policy_on_batch -> soft update, eager launches
-    (one C call enqueues the ~40 kernels of an update); CPU arm = the pinned oracle port."""
+    """R-MADDPG / R-MATD3 learner (BASELINE config 3): sample -> shared_train_policy_on_batch -> soft update.  `value`: the
+    whole update replayed from captured CUDA graphs; `e2e`: the eager drop-in calls (one C call enqueues the ~40 kernels of an
+    update) with a D2H loss read per step; CPU arm = the pinned oracle port."""
     from offpolicy._b200 import capi
     import maddpg_checks as mc
     import replay_checks as rc
@@ -126,19 +127,25 @@ def run_maddpg(args):
             pol.soft_target_updates()
         return info_t
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(3):
         step()
     torch.cuda.synchronize()
+    from offpolicy._b200.graph import MaddpgStepGraph
+    graph = MaddpgStepGraph(buf, tr, B)
+    for _ in range(max(args.warmup, 3)):
+        graph.launch()
+    graph.synchronize()
     l0 = lib.mx_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(0) as clocks:
-        e0.record()
+        e0.record(graph.stream)
         for _ in range(args.steps):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
+            graph.launch()
+        e1.record(graph.stream)
+        graph.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     launches = int(lib.mx_launch_count() - l0)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(50):
         float(step()["critic_loss"])
@@ -160,7 +167,8 @@ def run_maddpg(args):
     print(json.dumps(dict(metric="learner grad-steps/sec", value=1000.0 / ms, unit="steps/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3),
                           ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                           config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim,
-                                      buffer_episodes=E, step="eager: device MT19937 sample + mx_maddpg_step (+ soft update when the actor was updated)"),
+                                      buffer_episodes=E, step="CUDA graphs (one per update_actor variant): device MT19937 sample + mx_maddpg_step (+ soft update when the actor was updated); "
+                                           "noise drawn on the host from torch's CPU RNG like the reference and copied H2D per update"),
                           e2e=dict(value=e2e, unit="steps/s", h2d_bytes_per_step=((T + 1) * n * B * a * 4 if td3 else 0) + ((T + 1) * n * B * a * 4 // cfg.actor_update_interval if disc else 0),
                                    d2h_bytes_per_step=4,
                                    path="RecReplayBuffer.sample + R_MADDPG.shared_train_policy_on_batch + soft_target_updates + D2H critic_loss"),

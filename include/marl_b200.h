@@ -241,6 +241,13 @@ int mx_maddpg_step(mx_maddpg* h, const mx_batch* batch, const float* target_nois
  * update the actor; batch->avail (or NULL) masks unavailable actions to -1e10 like util.py:115,141. */
 int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* batch, const float* target_noise_dev, const float* actor_noise_dev,
                       int32_t* update_actor_out, void* stream);
+/* Whole-update CUDA graph (declared with mx_graph below): [sample ->] step [-> PER write-back] [-> soft update when the actor
+ * was updated, base_runner.py:250-252]; flags as for mx_graph_capture.  One graph per variant (update_actor = 1 / 0); the two
+ * noise pointers are fixed device buffers the caller refills before every mx_graph_launch. */
+struct mx_graph;
+int mx_maddpg_graph_capture(mx_replay* r, mx_maddpg* h, int32_t B, double beta, uint32_t flags, const float* target_noise_dev,
+                            const float* actor_noise_dev, int32_t update_actor, void* stream, struct mx_graph** out);
+int64_t mx_maddpg_num_updates(const mx_maddpg* h);   /* updates done so far (self.num_updates[p_id], r_maddpg.py:125) */
 /* device fp32[8]: critic_loss, critic_grad_norm, -, denom, actor_loss, actor_grad_norm, -, denom */
 const float* mx_maddpg_info(mx_maddpg* h);
 const float* mx_maddpg_priorities(mx_maddpg* h);

@@ -336,6 +336,7 @@ struct mx_maddpg {
   float* ws;
   MxMaddpgWs W;
   int64_t num_updates;
+  int force_update_actor = -1;      // graph capture: -1 = decide from num_updates, 0 / 1 = record this variant
 };
 
 static inline int mx_imin_host(int a, int b) { return a < b ? a : b; }
@@ -512,8 +513,10 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   if (!b->obs || !b->share || !b->acts || !b->rewards || !b->dones || !b->dones_env) { mx_set_error("maddpg step: missing batch field"); return 1; }
   if (c.use_per && !b->weights) { mx_set_error("maddpg step: use_per set but batch has no importance weights"); return 1; }
   if (c.target_noise > 0.f && !target_noise_dev) { mx_set_error("maddpg step: MATD3 target noise expected"); return 1; }
+  const bool update_actor = h->force_update_actor >= 0 ? h->force_update_actor != 0
+                                                     : (h->num_updates % (c.actor_update_interval > 0 ? c.actor_update_interval : 1)) == 0;
   {
-    const bool upd = (h->num_updates % (c.actor_update_interval > 0 ? c.actor_update_interval : 1)) == 0;
+    const bool upd = update_actor;
     if (c.discrete && upd && !actor_noise_dev) { mx_set_error("maddpg step: discrete actor update needs the Gumbel draws (actor_noise_dev)"); return 1; }
   }
   cudaStream_t s = (cudaStream_t)stream;
@@ -522,7 +525,6 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   const int B = b->B, T = c.episode_len, N = c.n_agents, K = c.num_q, Ac = c.act_dim, S = c.state_dim;
   const int Ma = B * (T + 1) * N, Mc = B * T, Mr = N * B * T;
   const int ldc = mx_round_up(critic_in_dim(&c), 4);
-  const bool update_actor = (h->num_updates % (c.actor_update_interval > 0 ? c.actor_update_interval : 1)) == 0;
   const MxNetLayout& LA = h->actor;
   const MxNetLayout& LC = h->critic;
   const int hstride = MX_H + 4;
@@ -706,9 +708,32 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
     if (optimise(h, true, aparts, ahead_grid, s)) return 1;
   }
   if (update_actor_out) *update_actor_out = update_actor ? 1 : 0;
-  h->num_updates += 1;
+  if (h->force_update_actor < 0) h->num_updates += 1;      // (graph replays count in mx_graph_launch)
   return 0;
 }
+
+// [sample ->] shared_train_policy_on_batch [-> PER write-back] [-> soft update] as one CUDA graph.  The actor is updated only
+// every actor_update_interval-th call, so the caller records one graph per variant (update_actor = 1 / 0) and replays the one
+// the update counter asks for; the noise buffers are fixed device buffers the caller refills before each launch.
+extern "C" int mx_maddpg_graph_capture(mx_replay* r, mx_maddpg* h, int32_t B, double beta, uint32_t flags, const float* target_noise_dev,
+                                       const float* actor_noise_dev, int32_t update_actor, void* stream, mx_graph** out) {
+  if (!r || !h || !out) { mx_set_error("mx_maddpg_graph_capture: null argument"); return 1; }
+  auto seq = [=](void* st) -> int {
+    if (flags & 1u) { if (mx_replay_sample_uniform(r, B, st)) return 1; }
+    else if (flags & 2u) { if (mx_replay_sample_per(r, B, beta, st)) return 1; }
+    mx_batch b;
+    if (mx_replay_batch(r, B, &b)) return 1;
+    h->force_update_actor = update_actor ? 1 : 0;
+    const int rc = mx_maddpg_step_ex(h, &b, target_noise_dev, actor_noise_dev, nullptr, st);
+    h->force_update_actor = -1;
+    if (rc) return 1;
+    if (flags & 8u) { if (mx_replay_update_priorities(r, b.idx, mx_maddpg_priorities(h), nullptr, nullptr, B, st)) return 1; }
+    if ((flags & 4u) && update_actor) { if (mx_maddpg_soft_update(h, st)) return 1; }      // base_runner.py:250-252
+    return 0;
+  };
+  return mx_graph_capture_seq(seq, [h]() { h->num_updates += 1; }, stream, out);
+}
+extern "C" int64_t mx_maddpg_num_updates(const mx_maddpg* h) { return h->num_updates; }
 
 extern "C" int mx_maddpg_soft_update(mx_maddpg* h, void* stream) {
   if (mx_launch_polyak(h->th_c_tgt, h->th_c, h->Pc, h->cfg.tau, (cudaStream_t)stream)) return 1;

@@ -3,6 +3,7 @@
 #include "../../include/marl_b200.h"
 #include "mx_common.cuh"
 
+#include <functional>
 #include <string>
 
 void mx_set_error(const char* fmt, ...);
@@ -20,6 +21,18 @@ int mx_num_sms();
 int mx_check_launch(const char* what);
 #define MX_CHECK_LAUNCH(what) mx_check_launch(what)
 #endif
+
+// whole-step CUDA graph (qmix.cu): the recorded launch sequence, kept for the emulated build which simply re-runs it
+struct mx_graph {
+#if !MX_EMU
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+#endif
+  std::function<int(void*)> seq;
+  std::function<void()> after_launch;     // host-side bookkeeping a replay must repeat (e.g. the learner's update counter)
+  int n_kernels = 0;
+};
+int mx_graph_capture_seq(std::function<int(void*)> seq, std::function<void()> after_launch, void* stream, mx_graph** out);
 
 // ---- replay ------------------------------------------------------------------------------------
 struct MxReplayState {   // device-resident scalars (off_state)

@@ -340,19 +340,6 @@ extern "C" int mx_qmix_hard_update(mx_qmix* q, void* stream) {
 // =====================================================================================================
 // whole-step CUDA graph
 // =====================================================================================================
-struct mx_graph {
-#if !MX_EMU
-  cudaGraph_t graph;
-  cudaGraphExec_t exec;
-#endif
-  mx_replay* r;
-  mx_qmix* q;
-  int B;
-  double beta;
-  uint32_t flags;
-  int n_kernels;
-};
-
 static int run_sequence(mx_replay* r, mx_qmix* q, int B, double beta, uint32_t flags, void* stream) {
   if (flags & 1u) { if (mx_replay_sample_uniform(r, B, stream)) return 1; }
   else if (flags & 2u) { if (mx_replay_sample_per(r, B, beta, stream)) return 1; }
@@ -367,13 +354,13 @@ static int run_sequence(mx_replay* r, mx_qmix* q, int B, double beta, uint32_t f
   return 0;
 }
 
-extern "C" int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta, uint32_t flags, void* stream, mx_graph** out) {
-  if (!r || !q || !out) { mx_set_error("mx_graph_capture: null argument"); return 1; }
+// Record `seq` (the library's own launch sequence) on `stream` into an executable graph.
+int mx_graph_capture_seq(std::function<int(void*)> seq, std::function<void()> after_launch, void* stream, mx_graph** out) {
   mx_graph* g = new mx_graph();
-  g->r = r; g->q = q; g->B = B; g->beta = beta; g->flags = flags;
+  g->seq = seq; g->after_launch = after_launch; g->n_kernels = 0;
 #if !MX_EMU
   cudaStream_t s = (cudaStream_t)stream;
-  if (!s) { mx_set_error("mx_graph_capture: needs a non-default stream (the legacy stream cannot be captured)"); delete g; return 1; }
+  if (!s) { mx_set_error("graph capture: needs a non-default stream (the legacy stream cannot be captured)"); delete g; return 1; }
   {
     cudaError_t be = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
     if (be != cudaSuccess) {
@@ -385,7 +372,7 @@ extern "C" int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta
       return 1;
     }
   }
-  int rc = run_sequence(r, q, B, beta, flags, stream);
+  int rc = seq(stream);
   cudaError_t e = cudaStreamEndCapture(s, &g->graph);
   if (rc || e != cudaSuccess) { mx_set_error("graph capture failed: %s", rc ? mx_last_error() : cudaGetErrorString(e)); delete g; return 1; }
   if (cudaGraphInstantiate(&g->exec, g->graph, 0) != cudaSuccess) { mx_set_error("cudaGraphInstantiate failed"); delete g; return 1; }
@@ -393,7 +380,6 @@ extern "C" int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta
   cudaGraphGetNodes(g->graph, nullptr, &nn);
   std::vector<cudaGraphNode_t> nodes(nn);
   if (nn) cudaGraphGetNodes(g->graph, nodes.data(), &nn);
-  g->n_kernels = 0;
   for (size_t i = 0; i < nn; ++i) {
     cudaGraphNodeType ty;
     if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) g->n_kernels++;
@@ -403,13 +389,21 @@ extern "C" int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta
   return 0;
 }
 
+extern "C" int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta, uint32_t flags, void* stream, mx_graph** out) {
+  if (!r || !q || !out) { mx_set_error("mx_graph_capture: null argument"); return 1; }
+  return mx_graph_capture_seq([=](void* st) { return run_sequence(r, q, B, beta, flags, st); }, nullptr, stream, out);
+}
+
 extern "C" int mx_graph_launch(mx_graph* g, void* stream) {
 #if !MX_EMU
   if (cudaGraphLaunch(g->exec, (cudaStream_t)stream) != cudaSuccess) { mx_set_error("cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
   g_mx_launches += g->n_kernels;   // kernel nodes replayed by this launch
+  if (g->after_launch) g->after_launch();
   return 0;
 #else
-  return run_sequence(g->r, g->q, g->B, g->beta, g->flags, stream);
+  const int rc = g->seq(stream);
+  if (!rc && g->after_launch) g->after_launch();
+  return rc;
 #endif
 }
 

@@ -123,6 +123,8 @@ def _declare(lib):
         "mx_maddpg_hard_update": (C.c_int, [vp, vp]),
         "mx_set_option": (C.c_int, [C.c_char_p, i32]),
         "mx_tc_linear_probe": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "mx_maddpg_graph_capture": (C.c_int, [vp, vp, i32, dbl, u32, vp, vp, i32, vp, C.POINTER(vp)]),
+        "mx_maddpg_num_updates": (i64, [vp]),
         "mx_graph_capture": (C.c_int, [vp, vp, i32, dbl, u32, vp, C.POINTER(vp)]),
         "mx_graph_launch": (C.c_int, [vp, vp]),
         "mx_graph_destroy": (None, [vp]),

@@ -43,3 +43,81 @@ class StepGraph(object):
             self.close()
         except Exception:
             pass
+
+
+class MaddpgStepGraph(object):
+    """[sample ->] R_MADDPG.shared_train_policy_on_batch [-> soft update] as CUDA graphs (one per update_actor variant).
+
+    Per `launch()` the host only draws the noise the reference would draw (MATD3 target noise / Gumbel draws, torch CPU RNG,
+    same order as r_maddpg.py) into pinned buffers, enqueues their H2D copies on the graph's stream and replays the graph."""
+
+    def __init__(self, buffer, trainer, batch_size, beta=0.4, soft_update=True, p_id="policy_0"):
+        lib = capi.lib()
+        self.lib = lib
+        pb = buffer.policy_buffers[p_id]
+        per = bool(getattr(trainer, "use_per", False))
+        self.flags = (SAMPLE_PER | PER_WRITEBACK if per else SAMPLE_UNIFORM) | (SOFT_UPDATE if soft_update else 0)
+        self.trainer, self.B, self.p_id = trainer, int(batch_size), p_id
+        pol = trainer.policies[p_id]
+        self.pol = pol
+        T, N, Ac = trainer.episode_length, trainer.num_agents, pol.act_dim
+        dev = capi.device()
+        self.cuda = dev.type == "cuda"            # (the CPU-emulated unit-test build re-runs the sequence instead of a graph)
+        self.stream = torch.cuda.Stream(device=dev) if self.cuda else None
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream(dev))
+        self._sp = C.c_void_p(self.stream.cuda_stream if self.cuda else 0)
+        shape = (self.B, T + 1, N, Ac)
+        self.tnoise_dev = torch.zeros(shape, dtype=torch.float32, device=dev) if pol.td3 else None
+        self.anoise_dev = torch.zeros(shape, dtype=torch.float32, device=dev) if pol.discrete else None
+        self.tnoise_host = torch.zeros(shape, dtype=torch.float32).pin_memory() if pol.td3 and self.cuda else (torch.zeros(shape) if pol.td3 else None)
+        self.anoise_host = torch.zeros(shape, dtype=torch.float32).pin_memory() if pol.discrete and self.cuda else (torch.zeros(shape) if pol.discrete else None)
+        self.graphs = {}
+        variants = (1, 0) if trainer.actor_update_interval > 1 else (1,)
+        for upd in variants:
+            g = C.c_void_p()
+            capi.check(lib.mx_maddpg_graph_capture(pb.handle, trainer.handle, self.B, float(beta), self.flags, capi.ptr(self.tnoise_dev),
+                                                   capi.ptr(self.anoise_dev), upd, self._sp, C.byref(g)))
+            self.graphs[upd] = g
+        self.num_kernels = {u: int(lib.mx_graph_num_kernels(g)) for u, g in self.graphs.items()}
+        self._keep = (buffer, trainer)
+
+    def launch(self):
+        tr, pol = self.trainer, self.pol
+        T, N, Ac, B = tr.episode_length, tr.num_agents, pol.act_dim, self.B
+        upd = 1 if tr.num_updates[self.p_id] % tr.actor_update_interval == 0 else 0
+        with torch.cuda.stream(self.stream) if self.cuda else _null():
+            if pol.td3:
+                n = tr.draw_target_noise(B)                                     # (T+1, N*B, Ac), reference row order
+                self.tnoise_host.copy_(n.view(T + 1, N, B, Ac).permute(2, 0, 1, 3))
+                self.tnoise_dev.copy_(self.tnoise_host, non_blocking=True)
+            if pol.discrete and upd:
+                g = tr.draw_actor_noise(B)                                      # (T, N*B, Ac)
+                self.anoise_host[:, :T].copy_(g.view(T, N, B, Ac).permute(2, 0, 1, 3))
+                self.anoise_dev.copy_(self.anoise_host, non_blocking=True)
+        capi.check(self.lib.mx_graph_launch(self.graphs[upd], self._sp))
+        tr.num_updates[self.p_id] += 1
+        return bool(upd)
+
+    def synchronize(self):
+        if self.cuda:
+            self.stream.synchronize()
+
+    def close(self):
+        for g in self.graphs.values():
+            self.lib.mx_graph_destroy(g)
+        self.graphs = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _null(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

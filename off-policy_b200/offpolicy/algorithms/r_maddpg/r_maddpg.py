@@ -124,16 +124,26 @@ class R_MADDPG(object):
             self._host_batch = _HostBatchC(self.cfg, self.dev)
         return self._host_batch.pack(batch, "policy_0", self.use_per)
 
+    def draw_target_noise(self, B):
+        """The draw the reference makes for the target actions of one update: (T+1, N*B, Ac), agent-major rows, CPU RNG."""
+        pol = self.policies["policy_0"]
+        T, N, Ac = self.episode_length, self.num_agents, pol.act_dim
+        if pol.discrete:
+            return sample_gumbel((T + 1, N * B, Ac))                                               # util.py:137 via rMADDPGPolicy.py:105-106
+        return torch.empty(T + 1, N * B, Ac).normal_(mean=0, std=float(pol.target_noise))          # util.py:217-218
+
+    def draw_actor_noise(self, B):
+        """Gumbel draws of the actor update's `get_actions(..., use_gumbel=True)` over obs[:-1] (r_maddpg.py:277): (T, N*B, Ac)."""
+        pol = self.policies["policy_0"]
+        return sample_gumbel((self.episode_length, self.num_agents * B, pol.act_dim))
+
     def _target_noise(self, B):
-        """N(0, target_noise) for every target action, drawn exactly like the reference (agent-major rows, CPU RNG)."""
+        """N(0, target_noise) / Gumbel draws for every target action, in batch row order on the device."""
         pol = self.policies["policy_0"]
         if not pol.td3:
             return None
         T, N, Ac = self.episode_length, self.num_agents, pol.act_dim
-        if pol.discrete:
-            noise = sample_gumbel((T + 1, N * B, Ac))                                              # util.py:137 via rMADDPGPolicy.py:105-106
-        else:
-            noise = torch.empty(T + 1, N * B, Ac).normal_(mean=0, std=float(pol.target_noise))      # util.py:217-218
+        noise = self.draw_target_noise(B)
         ours = noise.view(T + 1, N, B, Ac).permute(2, 0, 1, 3).contiguous()                      # -> [b][t][n][Ac]
         self._noise_dev = ours.to(self.dev, non_blocking=True)
         return self._noise_dev
@@ -142,7 +152,7 @@ class R_MADDPG(object):
         """Gumbel draws of the actor update's `get_actions(..., use_gumbel=True)` over obs[:-1] (r_maddpg.py:277), padded to T+1 steps."""
         pol = self.policies["policy_0"]
         T, N, Ac = self.episode_length, self.num_agents, pol.act_dim
-        g = sample_gumbel((T, N * B, Ac))
+        g = self.draw_actor_noise(B)
         ours = torch.zeros(B, T + 1, N, Ac)
         ours[:, :T] = g.view(T, N, B, Ac).permute(2, 0, 1, 3)
         self._actor_noise_dev = ours.to(self.dev, non_blocking=True)

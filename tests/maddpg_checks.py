@@ -137,3 +137,50 @@ def check_get_actions(name):
     torch.manual_seed(6); np.random.seed(6)
     r = np.asarray(pol.get_random_actions(obs), dtype=np.float32)
     assert np.array_equal(r, g["act.random"])
+
+
+def check_graph_matches_eager(td3, disc, B=4, T=6, E=16, steps=4):
+    """sample -> shared_train_policy_on_batch -> soft update through the drop-in classes, eager vs the captured whole-update
+    CUDA graphs (one per update_actor variant): same device RNG stream, same torch CPU noise stream -> same parameters."""
+    import replay_checks as rc
+    from offpolicy.utils.rec_buffer import RecReplayBuffer
+    from offpolicy._b200.graph import MaddpgStepGraph
+    from oracle.maddpg import MaddpgConfig
+    from oracle.qmix import randomize_all
+    cfg = MaddpgConfig(act_dim=5 if disc else 2, discrete=disc, td3=td3, actor_update_interval=2 if td3 else 1, gain=1.0)
+    n, o, a, sdim = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    results = []
+    for mode in ("eager", "graph"):
+        rs = np.random.RandomState(3)
+        info = {"policy_0": dict(obs_space=[o], share_obs_space=[sdim], act_space=Discrete(a) if disc else Box(a))}
+        buf = RecReplayBuffer(info, {"policy_0": list(range(n))}, E, T, True, False, rng="device", max_batch=max(B, E))
+        acts = np.eye(a, dtype=np.float32)[rs.randint(0, a, (T, E, n))] if disc else rs.uniform(-1, 1, (T, E, n, a)).astype(np.float32)
+        ep = [rs.randn(T + 1, E, n, o).astype(np.float32), np.repeat(rs.randn(T + 1, E, 1, sdim).astype(np.float32), n, 2), acts,
+              np.repeat(rs.randn(T, E, 1, 1).astype(np.float32), n, 2), np.zeros((T, E, n, 1), np.float32), np.zeros((T, E, 1), np.float32)]
+        buf.insert(E, *[rc.d(x) for x in ep], None)
+        torch.manual_seed(1)
+        args, pol, tr = build(cfg, B, T)
+        init = torch.Generator().manual_seed(11)
+        for vec in (pol.actor_vecs[0], pol.critic_vecs[0]):
+            vec.add_((0.05 * torch.randn(vec.shape, generator=init)).to(vec.device))
+        pol.hard_target_updates()
+        buf.seed_device_rng(5)
+        torch.manual_seed(99)
+        upds = []
+        if mode == "eager":
+            for s in range(steps):
+                smp = buf.sample(B)
+                info_t, _, _ = tr.shared_train_policy_on_batch("policy_0", smp)
+                upds.append(bool(info_t["update_actor"]))
+                if info_t["update_actor"]:
+                    pol.soft_target_updates()
+        else:
+            g = MaddpgStepGraph(buf, tr, B)
+            for s in range(steps):
+                upds.append(g.launch())
+            g.synchronize()
+            g.close()
+        results.append(([v.clone().cpu() for v in pol.actor_vecs + pol.critic_vecs], upds))
+    assert results[0][1] == results[1][1]
+    for x, y in zip(results[0][0], results[1][0]):
+        assert float((x - y).abs().max()) <= 1e-6 * float(x.abs().max()) + 1e-7

@@ -12,3 +12,8 @@ def test_step_matches_reference_golden(emu_engine, name):
 @pytest.mark.parametrize("name", ["maddpg_box", "maddpg_disc", "matd3_disc"])
 def test_rollout_actions_match_reference(emu_engine, name):
     mc.check_get_actions(name)
+
+
+@pytest.mark.parametrize("td3,disc", [(False, False), (True, True)])
+def test_whole_update_graph_matches_eager(emu_engine, td3, disc):
+    mc.check_graph_matches_eager(td3, disc)

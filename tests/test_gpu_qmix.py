@@ -290,3 +290,9 @@ def test_config3_maddpg_spread_discrete_full_size_vs_oracle(gpu_engine, td3):
 def test_maddpg_rollout_actions_match_reference(gpu_engine, name):
     import maddpg_checks as mc
     mc.check_get_actions(name)
+
+
+@pytest.mark.parametrize("td3,disc", [(False, False), (True, False), (False, True), (True, True)])
+def test_maddpg_whole_update_graph_matches_eager(gpu_engine, td3, disc):
+    import maddpg_checks as mc
+    mc.check_graph_matches_eager(td3, disc, B=32, T=25, E=64, steps=4)
