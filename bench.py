@@ -109,6 +109,7 @@ def run_maddpg(args):
                               e2e=dict(value=sps, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
         return
     torch.cuda.set_device(0)
+    torch.set_num_threads(1)        # tiny host ops (noise draws): the reference's default n_training_threads = 1 (config.py:17-18)
     lib = capi.lib()
     from offpolicy.utils.rec_buffer import RecReplayBuffer
     info = {"policy_0": dict(obs_space=[o], share_obs_space=[sdim], act_space=mc.Discrete(a) if disc else mc.Box(a))}
@@ -326,6 +327,7 @@ def run_engine(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
     torch.cuda.set_device(local)
+    torch.set_num_threads(1)        # host side of the engine arm: the reference's own default (config.py n_training_threads = 1)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = capi.lib()
@@ -535,7 +537,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="qmix_3m", choices=sorted(WORKLOADS) + sorted(MADDPG_WORKLOADS))
     ap.add_argument("--buffer", type=int, default=5000, help="replay episodes (scripts/train_smac_qmix.sh default 5000)")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=int (mx_set_option), e.g. --opt pdl=0 --opt front_tc=0")
     a = ap.parse_args()
+    if a.impl != "reference" and a.opt:
+        from offpolicy._b200 import capi
+        for kv in a.opt:
+            k, v = kv.split("=")
+            capi.check(capi.lib().mx_set_option(k.encode(), int(v)))
     if a.workload in MADDPG_WORKLOADS:
         if int(os.environ.get("RANK", "0")) == 0:
             run_maddpg(a)

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
   for (int i = tid; i < A * MX_H; i += blockDim.x) { wq_s[i] = a.theta[a.wq + i]; dwq_s[i] = 0.f; }
   for (int i = tid; i < 32; i += blockDim.x) dbq_s[i] = 0.f;
   for (int i = tid; i < MX_H; i += blockDim.x) { dg_s[i] = 0.f; db_s[i] = 0.f; lg_s[i] = a.theta[a.lno_g + i]; lb_s[i] = a.theta[a.lno_b + i]; }
+  MX_PDL_WAIT();
   __syncthreads();
   const int wglobal = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
   const int wtotal = gridDim.x * (blockDim.x >> 5);
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
     }
   const int T1 = a.T1 > 0 ? a.T1 : a.T + 1, N = a.N;
   const int ku = 2 * kp + (s & 1);          // unit whose gate derivatives this lane computes (lanes s = 0, 1)
+  MX_PDL_WAIT();        // W_hh columns above are parameter data; the operand streams below are the predecessor's outputs
 
   // prefetch assignment: RPC*96 16-byte pieces per step, up to two per thread
   constexpr int NPIECE = (RPC * 96 + BWD_THREADS - 1) / BWD_THREADS;
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
   if (tid < 64) { ln1g_s[tid] = th[L.ln1_g + tid]; ln1b_s[tid] = th[L.ln1_b + tid]; ln2g_s[tid] = th[L.ln2_g + tid]; ln2b_s[tid] = th[L.ln2_b + tid]; }
   float dg1[4] = {0.f, 0.f, 0.f, 0.f}, db1[4] = {0.f, 0.f, 0.f, 0.f}, dg2[4] = {0.f, 0.f, 0.f, 0.f}, db2[4] = {0.f, 0.f, 0.f, 0.f};
   int iter = 0;
+  MX_PDL_WAIT();
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
     const int m0 = tile * TM;
     const bool accum = iter > 0;
@@ -473,7 +476,7 @@ int mx_launch_qhead_bwd(const QHeadBwdArgs& a, int* nparts_used, cudaStream_t s)
   const int cap = mx_num_sms();
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  MX_LAUNCH(k_qhead_bwd, dim3(grid), dim3(256), 0, s, a);
+  MX_LAUNCH_PDL(k_qhead_bwd, dim3(grid), dim3(256), 0, s, a);
   MX_COUNT();
   MX_MARK("k_qhead_bwd", s);
   *nparts_used = grid;
@@ -485,9 +488,9 @@ int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
   int rpc = 1;
   while (rpc < 4 && mx_ceil_div(a.R, rpc) > 2 * sms) rpc *= 2;
   dim3 grid(mx_ceil_div(a.R, rpc));
-  if (rpc == 1) MX_LAUNCH(k_gru_bwd<1>, grid, dim3(BWD_THREADS), 0, s, a);
-  else if (rpc == 2) MX_LAUNCH(k_gru_bwd<2>, grid, dim3(BWD_THREADS), 0, s, a);
-  else MX_LAUNCH(k_gru_bwd<4>, grid, dim3(BWD_THREADS), 0, s, a);
+  if (rpc == 1) MX_LAUNCH_PDL(k_gru_bwd<1>, grid, dim3(BWD_THREADS), 0, s, a);
+  else if (rpc == 2) MX_LAUNCH_PDL(k_gru_bwd<2>, grid, dim3(BWD_THREADS), 0, s, a);
+  else MX_LAUNCH_PDL(k_gru_bwd<4>, grid, dim3(BWD_THREADS), 0, s, a);
   MX_COUNT();
   MX_MARK("k_gru_bwd", s);
   return MX_CHECK_LAUNCH("gru_bwd");
@@ -506,7 +509,7 @@ int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s)
   static size_t configured = 0;
   if (smem > configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
 #endif
-  MX_LAUNCH(kern, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
+  MX_LAUNCH_PDL(kern, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
   MX_COUNT();
   MX_MARK("k_front_bwd", s);
   *nparts_used = grid;

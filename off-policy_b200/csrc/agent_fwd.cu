@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
   const bool live = (net == 0);
   const int ntiles = (a.M + TM - 1) / TM;
+  MX_PDL_WAIT();
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int m0 = tile * TM;
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
       wn[4 * m + c] = th[a.whh + (2 * MX_H + i) * MX_H + k];
     }
   const float br = th[a.bhh + i], bz = th[a.bhh + MX_H + i], bn = th[a.bhh + 2 * MX_H + i];
+  MX_PDL_WAIT();        // the W_hh slice above is parameter data; everything below reads the predecessor's outputs
   for (int idx = tid; idx < 2 * RPC * MX_H; idx += GRU_THREADS) {                               // h_0 = 0 (QMixPolicy.py:193-196) or given
     const int r = (idx / MX_H) % RPC, c = idx % MX_H;
     (&h_s[0][0][0])[idx] = (a.h0 && row0 + r < a.R) ? a.h0[(size_t)(row0 + r) * MX_H + c] : 0.f;
@@ -289,6 +291,7 @@ __global__ void __launch_bounds__(256) k_qhead(QHeadArgs a) {
     for (int i = tid; i < A; i += blockDim.x) bq_s[net][i] = th[a.bq + i];
     for (int i = tid; i < MX_H; i += blockDim.x) { lg_s[net][i] = th[a.lno_g + i]; lb_s[net][i] = th[a.lno_b + i]; }
   }
+  MX_PDL_WAIT();
   __syncthreads();
   const int wglobal = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
   const int wtotal = gridDim.x * (blockDim.x >> 5);
@@ -379,7 +382,7 @@ int mx_launch_front_fwd(const FrontFwdArgs& a, int nets, cudaStream_t s) {
     configured = smem;
   }
 #endif
-  MX_LAUNCH(kern, dim3(gx, nets), dim3(MX_TILE_THREADS), smem, s, a);
+  MX_LAUNCH_PDL(kern, dim3(gx, nets), dim3(MX_TILE_THREADS), smem, s, a);
   MX_COUNT();
   MX_MARK("k_front_fwd", s);
   return MX_CHECK_LAUNCH("front_fwd");
@@ -390,9 +393,9 @@ int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s) {
   int rpc = 1;     // one resident CTA per SM (the kernel is register heavy): grow rows-per-CTA until the grid fits one wave
   while (rpc < 4 && mx_ceil_div(a.R, rpc) * nets > 2 * sms) rpc *= 2;   // two CTAs fit per SM (<= 128 registers): co-resident CTAs hide each other's latencies
   dim3 grid(mx_ceil_div(a.R, rpc), nets);
-  if (rpc == 1) MX_LAUNCH(k_gru_fwd<1>, grid, dim3(GRU_THREADS), 0, s, a);
-  else if (rpc == 2) MX_LAUNCH(k_gru_fwd<2>, grid, dim3(GRU_THREADS), 0, s, a);
-  else MX_LAUNCH(k_gru_fwd<4>, grid, dim3(GRU_THREADS), 0, s, a);
+  if (rpc == 1) MX_LAUNCH_PDL(k_gru_fwd<1>, grid, dim3(GRU_THREADS), 0, s, a);
+  else if (rpc == 2) MX_LAUNCH_PDL(k_gru_fwd<2>, grid, dim3(GRU_THREADS), 0, s, a);
+  else MX_LAUNCH_PDL(k_gru_fwd<4>, grid, dim3(GRU_THREADS), 0, s, a);
   MX_COUNT();
   MX_MARK("k_gru_fwd", s);
   return MX_CHECK_LAUNCH("gru_fwd");
@@ -403,7 +406,7 @@ int mx_launch_qhead(const QHeadArgs& a, cudaStream_t s) {
   int grid = mx_ceil_div(a.M, 8);
   const int cap = mx_num_sms() * 4;
   if (grid > cap) grid = cap;
-  MX_LAUNCH(k_qhead, dim3(grid), dim3(256), 0, s, a);
+  MX_LAUNCH_PDL(k_qhead, dim3(grid), dim3(256), 0, s, a);
   MX_COUNT();
   MX_MARK("k_qhead", s);
   return MX_CHECK_LAUNCH("qhead");

@@ -6,6 +6,10 @@
 
 static thread_local char g_err[512] = "";
 long long g_mx_launches = 0;
+#if !MX_EMU
+int g_mx_pdl = 0;     // measured slower on B200: dependents' prologues share the SM with the latency-bound recurrences
+int g_mx_pdl_skip_next = 0;
+#endif
 
 void mx_set_error(const char* fmt, ...) {
   va_list ap;

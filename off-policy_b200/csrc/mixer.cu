@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_mixer(MixerArgs a, MixSmem 
   float part_den = 0.f, part_loss = 0.f, part_q = 0.f;   // thread 0 only
   const int S64 = mx_round_up(L.S, 64);
   int iter = 0;
+  MX_PDL_WAIT();
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
     const int e0 = tile * TE;
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(256) k_vdn_mix(MixerArgs a) {
   const int E = a.B * a.T;
   const int N = a.N;
   float den = 0.f, ls = 0.f, qs = 0.f;
+  MX_PDL_WAIT();
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
     float Q = 0.f, Qn = 0.f;
     for (int n = 0; n < N; ++n) { Q += a.q_taken[(size_t)e * N + n]; Qn += a.q_next[(size_t)e * N + n]; }
@@ -372,7 +374,7 @@ int mx_launch_mixer(const MixerArgs& a, int* nparts_used, cudaStream_t s) {
   if (a.vdn) {
     int grid = mx_ceil_div(E, 256);
     if (grid > sms) grid = sms;
-    MX_LAUNCH(k_vdn_mix, dim3(grid), dim3(256), 0, s, a);
+    MX_LAUNCH_PDL(k_vdn_mix, dim3(grid), dim3(256), 0, s, a);
     MX_COUNT();
     MX_MARK("k_vdn_mix", s);
     *nparts_used = grid;
@@ -391,8 +393,8 @@ int mx_launch_mixer(const MixerArgs& a, int* nparts_used, cudaStream_t s) {
   if (RM == 1 && smem > conf1) { cudaFuncSetAttribute(k_mixer<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); conf1 = smem; }
   if (RM == 2 && smem > conf2) { cudaFuncSetAttribute(k_mixer<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); conf2 = smem; }
 #endif
-  if (RM == 1) MX_LAUNCH(k_mixer<1>, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
-  else MX_LAUNCH(k_mixer<2>, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
+  if (RM == 1) MX_LAUNCH_PDL(k_mixer<1>, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
+  else MX_LAUNCH_PDL(k_mixer<2>, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
   MX_COUNT();
   MX_MARK("k_mixer", s);
   *nparts_used = grid;

@@ -10,10 +10,43 @@
 #ifdef MARL_EMU
 #include "emu_runtime.h"
 #define MX_EMU 1
+#define MX_LAUNCH_PDL MX_LAUNCH
+#define MX_PDL_WAIT() ((void)0)
+#define MX_PDL_THETA_WRITTEN() ((void)0)
 #else
 #include <cuda_runtime.h>
 #define MX_EMU 0
 #define MX_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+
+// Programmatic dependent launch (PDL).  A kernel launched with MX_LAUNCH_PDL may begin while its stream predecessor is still
+// running; everything it does before MX_PDL_WAIT() overlaps the predecessor's tail, so that part may only touch state the
+// predecessor does not write: its own shared memory / TMEM and the parameter vectors theta / theta_target.  Those are written
+// only by the optimiser kernels, which call MX_PDL_THETA_WRITTEN() so that the NEXT launch is a plain, fully ordered one.
+// MX_PDL_WAIT() = griddepcontrol.wait (returns at once in a plain launch) followed by launch_dependents, i.e. a dependent may
+// start as soon as every CTA of this grid is past its own wait -- never before this grid's predecessor has completed.
+extern int g_mx_pdl;              // 0 (default): every launch is a plain one; mx_set_option("pdl", 1) enables PDL
+extern int g_mx_pdl_skip_next;
+#define MX_PDL_THETA_WRITTEN() (g_mx_pdl_skip_next = 1)
+#define MX_PDL_WAIT()                                                     \
+  do {                                                                    \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                    \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");       \
+  } while (0)
+template <typename... KArgs, typename... Args>
+static inline void mx_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  cfg.attrs = at; cfg.numAttrs = 0;
+  if (g_mx_pdl && !g_mx_pdl_skip_next) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+  }
+  g_mx_pdl_skip_next = 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define MX_LAUNCH_PDL(kern, grid, block, smem, stream, ...) mx_launch_pdl(kern, grid, block, smem, stream, __VA_ARGS__)
 #endif
 
 #define MX_H 64          // hidden size the kernels are specialised for (reference default, config.py:63)

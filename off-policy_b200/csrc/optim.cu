@@ -15,6 +15,7 @@
 
 __global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
   const int tid = threadIdx.x;
+  MX_PDL_WAIT();
   if (blockIdx.x == gridDim.x - 1) {
     // ---- scalar sums: sum(1-bad), loss numerator, sum Q_tot(1-bad) ----
     __shared__ float red[3][256];
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
   __shared__ double red[32];
   __shared__ float s_scale, s_step, s_bc2s;
   const int tid = threadIdx.x;
+  MX_PDL_WAIT();
   const float denom = a.grad[a.P + 0];
   const float invd = 1.0f / denom;
   // ||g||^2 over the full vector, identical summation order in every CTA (no grid-wide barrier needed)
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_polyak(float* __restrict__ tgt, const float* __restrict__ src, long long n4, float tau) {
+  MX_PDL_WAIT();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 t = mx_ld4(tgt + 4 * i);
     const float4 s = mx_ld4(src + 4 * i);
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) k_polyak(float* __restrict__ tgt, const f
 
 int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s) {
   const int grid = (int)((a.P + 255) / 256) + 1;
-  MX_LAUNCH(k_grad_reduce, dim3(grid), dim3(256), 0, s, a);
+  MX_LAUNCH_PDL(k_grad_reduce, dim3(grid), dim3(256), 0, s, a);
   MX_COUNT();
   MX_MARK("k_grad_reduce", s);
   return MX_CHECK_LAUNCH("grad_reduce");
@@ -142,7 +145,8 @@ int mx_launch_adam(const OptimArgs& a, cudaStream_t s) {
   int grid = (int)((a.P + 4095) / 4096);
   const int sms = mx_num_sms();
   if (grid > sms) grid = sms;
-  MX_LAUNCH(k_adam, dim3(grid), dim3(1024), 0, s, a);
+  MX_LAUNCH_PDL(k_adam, dim3(grid), dim3(1024), 0, s, a);
+  MX_PDL_THETA_WRITTEN();
   MX_COUNT();
   MX_MARK("k_adam", s);
   return MX_CHECK_LAUNCH("adam");
@@ -153,7 +157,8 @@ int mx_launch_polyak(float* tgt, const float* src, long long n, float tau, cudaS
   const int sms = mx_num_sms();
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  MX_LAUNCH(k_polyak, dim3(grid), dim3(256), 0, s, tgt, src, n4, tau);
+  MX_LAUNCH_PDL(k_polyak, dim3(grid), dim3(256), 0, s, tgt, src, n4, tau);
+  MX_PDL_THETA_WRITTEN();
   MX_COUNT();
   MX_MARK("k_polyak", s);
   return MX_CHECK_LAUNCH("polyak");

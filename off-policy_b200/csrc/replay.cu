@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
   const long long per_ep = a.cum4[a.nf];
   const long long total = per_ep * a.B;
   float mean = 0.f, stdv = 1.f;
+  MX_PDL_WAIT();
   if (a.rew_field >= 0) { mean = (float)a.state->reward_mean; stdv = (float)a.state->reward_std; }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / per_ep);
@@ -660,7 +661,7 @@ static int launch_gather(mx_replay* r, const int64_t* idx_dev, int B, cudaStream
   int grid = (int)(want < 1 ? 1 : want);
   if (grid > sms * 8) grid = sms * 8;
   else if (grid > sms) grid = grid / sms * sms;
-  MX_LAUNCH(k_gather, dim3(grid), dim3(256), 0, s, g);
+  MX_LAUNCH_PDL(k_gather, dim3(grid), dim3(256), 0, s, g);
   MX_COUNT();
   MX_MARK("k_gather", s);
   return MX_CHECK_LAUNCH("gather");

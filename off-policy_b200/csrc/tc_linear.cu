@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_weights(const float* __restrict
   const int I = L.in_dim, Kp = (I + 7) & ~7;
   const int n1 = MX_H * Kp, n2 = MX_H * MX_H, n3 = MX_G * MX_H;
   char* base = reinterpret_cast<char*>(img);
+  MX_PDL_WAIT();
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2 + n3; idx += gridDim.x * blockDim.x) {
     int n, k, K, Kd;
     const float* W;
@@ -211,7 +212,7 @@ size_t mx_tc_image_floats(int in_dim) {
 }
 int mx_launch_tc_prep_weights(const float* theta, const MxNetLayout& L, float* img, cudaStream_t s) {
   const int n = MX_H * mx_round_up(L.in_dim, 8) + MX_H * MX_H + MX_G * MX_H;
-  k_tc_prep_weights<<<dim3((n + 255) / 256), dim3(256), 0, s>>>(theta, L, img);
+  MX_LAUNCH_PDL(k_tc_prep_weights, dim3((n + 255) / 256), dim3(256), 0, s, theta, L, img);
   MX_COUNT();
   MX_MARK("k_tc_prep_weights", s);
   return MX_CHECK_LAUNCH("tc_prep_weights");
@@ -272,6 +273,13 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
     tc::mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < MX_H; i += blockDim.x) {
+    par_s[i] = th[L.b1 + i]; par_s[MX_H + i] = th[L.ln1_g + i]; par_s[2 * MX_H + i] = th[L.ln1_b + i];
+    par_s[3 * MX_H + i] = th[L.b2 + i]; par_s[4 * MX_H + i] = th[L.ln2_g + i]; par_s[5 * MX_H + i] = th[L.ln2_b + i];
+    par_s[6 * MX_H + MX_G + i] = i < I ? th[L.fn_g + i] : 0.f; par_s[6 * MX_H + MX_G + 64 + i] = i < I ? th[L.fn_b + i] : 0.f;
+  }
+  for (int i = tid; i < MX_G; i += blockDim.x) par_s[6 * MX_H + i] = th[L.bih + i];
+  MX_PDL_WAIT();        // TMEM, the mbarrier and the parameter rows are private / parameter data; the images and inputs are not
   if (a.tc_img[net]) {
     // the image is byte-identical to the shared-memory weight region: straight 16-byte async copies
     // two groups: fc1+fc2 first, W_ih (two thirds of the bytes) lands while the first two layers run
@@ -287,12 +295,6 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
     tc_stage_weight(w2h, w2l, th + L.w2, MX_H, MX_H, MX_H);
     tc_stage_weight(wih, wil, th + L.wih, MX_G, MX_H, MX_H);
   }
-  for (int i = tid; i < MX_H; i += blockDim.x) {
-    par_s[i] = th[L.b1 + i]; par_s[MX_H + i] = th[L.ln1_g + i]; par_s[2 * MX_H + i] = th[L.ln1_b + i];
-    par_s[3 * MX_H + i] = th[L.b2 + i]; par_s[4 * MX_H + i] = th[L.ln2_g + i]; par_s[5 * MX_H + i] = th[L.ln2_b + i];
-    par_s[6 * MX_H + MX_G + i] = i < I ? th[L.fn_g + i] : 0.f; par_s[6 * MX_H + MX_G + 64 + i] = i < I ? th[L.fn_b + i] : 0.f;
-  }
-  for (int i = tid; i < MX_G; i += blockDim.x) par_s[6 * MX_H + i] = th[L.bih + i];
   const float* bih_s = par_s + 6 * MX_H;
   const float* fng_s = par_s + 6 * MX_H + MX_G;
   const float* fnb_s = fng_s + 64;
@@ -415,7 +417,7 @@ int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
   int gx = mx_num_sms() / nets;
   if (gx > ntiles) gx = ntiles;
   if (gx < 1) gx = 1;
-  k_front_fwd_tc<<<dim3(gx, nets), dim3(128), smem, s>>>(a, sm, g_mx_tc_swap);
+  MX_LAUNCH_PDL(k_front_fwd_tc, dim3(gx, nets), dim3(128), smem, s, a, sm, g_mx_tc_swap);
   MX_COUNT();
   MX_MARK("k_front_fwd_tc", s);
   return MX_CHECK_LAUNCH("front_fwd_tc");
@@ -424,6 +426,9 @@ int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
 extern "C" int mx_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "front_tc")) { g_mx_front_tc = value; return 0; }
   if (!strcmp(name, "tc_swap_ls")) { g_mx_tc_swap = value; return 0; }
+#if !MX_EMU
+  if (!strcmp(name, "pdl")) { g_mx_pdl = value; return 0; }
+#endif
   mx_set_error("mx_set_option: unknown option %s", name);
   return 1;
 }

@@ -70,8 +70,13 @@ class MaddpgStepGraph(object):
         shape = (self.B, T + 1, N, Ac)
         self.tnoise_dev = torch.zeros(shape, dtype=torch.float32, device=dev) if pol.td3 else None
         self.anoise_dev = torch.zeros(shape, dtype=torch.float32, device=dev) if pol.discrete else None
-        self.tnoise_host = torch.zeros(shape, dtype=torch.float32).pin_memory() if pol.td3 and self.cuda else (torch.zeros(shape) if pol.td3 else None)
-        self.anoise_host = torch.zeros(shape, dtype=torch.float32).pin_memory() if pol.discrete and self.cuda else (torch.zeros(shape) if pol.discrete else None)
+        # pinned staging ring: a slot is rewritten only after the H2D copy that last read it has completed (its event)
+        self.RING = 4
+        mk = lambda: [torch.zeros(shape, dtype=torch.float32).pin_memory() if self.cuda else torch.zeros(shape) for _ in range(self.RING)]
+        self.tnoise_host = mk() if pol.td3 else None
+        self.anoise_host = mk() if pol.discrete else None
+        self._copied = [None] * self.RING
+        self._slot = 0
         self.graphs = {}
         variants = (1, 0) if trainer.actor_update_interval > 1 else (1,)
         for upd in variants:
@@ -86,15 +91,23 @@ class MaddpgStepGraph(object):
         tr, pol = self.trainer, self.pol
         T, N, Ac, B = tr.episode_length, tr.num_agents, pol.act_dim, self.B
         upd = 1 if tr.num_updates[self.p_id] % tr.actor_update_interval == 0 else 0
+        k = self._slot
+        self._slot = (k + 1) % self.RING
+        if self._copied[k] is not None:
+            self._copied[k].synchronize()
         with torch.cuda.stream(self.stream) if self.cuda else _null():
             if pol.td3:
                 n = tr.draw_target_noise(B)                                     # (T+1, N*B, Ac), reference row order
-                self.tnoise_host.copy_(n.view(T + 1, N, B, Ac).permute(2, 0, 1, 3))
-                self.tnoise_dev.copy_(self.tnoise_host, non_blocking=True)
+                self.tnoise_host[k].copy_(n.view(T + 1, N, B, Ac).permute(2, 0, 1, 3))
+                self.tnoise_dev.copy_(self.tnoise_host[k], non_blocking=True)
             if pol.discrete and upd:
                 g = tr.draw_actor_noise(B)                                      # (T, N*B, Ac)
-                self.anoise_host[:, :T].copy_(g.view(T, N, B, Ac).permute(2, 0, 1, 3))
-                self.anoise_dev.copy_(self.anoise_host, non_blocking=True)
+                self.anoise_host[k][:, :T].copy_(g.view(T, N, B, Ac).permute(2, 0, 1, 3))
+                self.anoise_dev.copy_(self.anoise_host[k], non_blocking=True)
+            if self.cuda and (pol.td3 or pol.discrete):
+                if self._copied[k] is None:
+                    self._copied[k] = torch.cuda.Event()
+                self._copied[k].record(self.stream)
         capi.check(self.lib.mx_graph_launch(self.graphs[upd], self._sp))
         tr.num_updates[self.p_id] += 1
         return bool(upd)
