@@ -111,6 +111,8 @@ int mx_replay_sample_uniform(mx_replay* r, int32_t B, void* stream);
 /* Same gather for caller-provided indices (host-drawn np.random.choice keeps the process-global NumPy
  * stream shared with the env loop, exactly like the reference).  idx_dev: int64[B] on the device. */
 int mx_replay_gather(mx_replay* r, const int64_t* idx_dev, int32_t B, void* stream);
+/* same, indices in (pinned) host memory: one async H2D copy of B int64 + the gather */
+int mx_replay_gather_host(mx_replay* r, const int64_t* idx_host, int32_t B, void* stream);
 /* PrioritizedRecReplayBuffer.sample (rec_buffer.py:272-304): masses from np.random.random semantics,
  * fp64 prefix-sum descent, IS weights, gather. */
 int mx_replay_sample_per(mx_replay* r, int32_t B, double beta, void* stream);
@@ -208,7 +210,7 @@ int mx_qmix_hard_update(mx_qmix* q, void* stream);   /* qmix.py:203-209 */
  * Replaces R_MADDPG.shared_train_policy_on_batch / get_update_info (offpolicy/algorithms/r_maddpg/r_maddpg.py:44-331),
  * R_MADDPG_Actor / R_MADDPG_Critic forward (r_maddpg/algorithm/r_actor_critic.py:7-130), the two Adam steps and
  * soft/hard target updates of R_MADDPGPolicy (rMADDPGPolicy.py:53-54,162-170), and the R_MATD3 variants
- * (r_matd3/*: two Q heads, actor every 2nd update, Gaussian target-action noise).
+ * (r_matd3/...: two Q heads, actor every 2nd update, Gaussian target-action noise).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct mx_maddpg mx_maddpg;
 typedef struct mx_maddpg_cfg {

@@ -695,6 +695,15 @@ extern "C" int mx_replay_gather(mx_replay* r, const int64_t* idx_dev, int32_t B,
   return launch_gather(r, at<int64_t>(r, r->L.off_b_idx), B, s);
 }
 
+// Same gather with the indices still on the host (np.random.choice result in pinned memory): one H2D copy + the gather.
+extern "C" int mx_replay_gather_host(mx_replay* r, const int64_t* idx_host, int32_t B, void* stream) {
+  if (check_sample(r, B)) return 1;
+  if (!idx_host) { mx_set_error("gather_host: null indices"); return 1; }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemcpyAsync(at<int64_t>(r, r->L.off_b_idx), idx_host, (size_t)B * 8, cudaMemcpyHostToDevice, s);
+  return launch_gather(r, at<int64_t>(r, r->L.off_b_idx), B, s);
+}
+
 extern "C" int mx_replay_sample_per(mx_replay* r, int32_t B, double beta, void* stream) {
   if (check_sample(r, B)) return 1;
   if (!r->cfg.use_per) { mx_set_error("sample_per: replay created without use_per"); return 1; }

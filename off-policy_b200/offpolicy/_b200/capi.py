@@ -91,6 +91,7 @@ def _declare(lib):
         "mx_replay_get_rng_state": (C.c_int, [vp, C.POINTER(u32), C.POINTER(i32), vp]),
         "mx_replay_sample_uniform": (C.c_int, [vp, i32, vp]),
         "mx_replay_gather": (C.c_int, [vp, vp, i32, vp]),
+        "mx_replay_gather_host": (C.c_int, [vp, vp, i32, vp]),
         "mx_replay_sample_per": (C.c_int, [vp, i32, dbl, vp]),
         "mx_replay_update_priorities": (C.c_int, [vp, vp, vp, vp, vp, i32, vp]),
         "mx_replay_batch": (C.c_int, [vp, i32, C.POINTER(Batch)]),
@@ -192,11 +193,14 @@ def device():
     return _device
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (lambda i: torch.cuda.current_stream(i).cuda_stream)
+
+
 def stream_ptr():
     """cudaStream_t of torch's current stream (torch is plumbing: memory + streams)."""
     if _device is None or _device.type != "cuda":
         return None
-    return C.c_void_p(torch.cuda.current_stream(_device).cuda_stream)
+    return C.c_void_p(_raw_stream(_device.index or 0))          # (torch.cuda.current_stream() builds a Stream object: ~3 us)
 
 
 def check(rc):

@@ -127,6 +127,8 @@ class QMix(object):
                                       capi.ptr(self.adam_v), capi.ptr(self.workspace), nbytes, C.byref(h)))
         self.handle = h
         self._host_batch = None
+        self.use_step_graph = True          # replay the captured launch sequence for batches that live in a replay's batch region
+        self._graphs, self._graph_keep, self._cap_stream = {}, [], None
         self._info = self.ws_view("info")
         n = C.c_int64()
         gptr = lib.mx_qmix_grad_buffer(self.handle, C.byref(n))
@@ -137,6 +139,7 @@ class QMix(object):
 
     def __del__(self):
         try:
+            self.drop_step_graphs()
             if getattr(self, "handle", None):
                 capi.lib().mx_qmix_destroy(self.handle)
                 self.handle = None
@@ -182,12 +185,36 @@ class QMix(object):
             capi.check(lib.mx_qmix_backward_only(self.handle, C.byref(b), stream))
             torch.distributed.all_reduce(self._grad_buf)
             capi.check(lib.mx_qmix_apply(self.handle, stream))
+        elif self.use_step_graph and isinstance(batch, SampledBatch) and self.dev.type == "cuda":
+            capi.check(lib.mx_graph_launch(self._step_graph(batch, b.B), stream))
         else:
             capi.check(lib.mx_qmix_step(self.handle, C.byref(b), stream))
         info = self._info
         train_info = {"loss": info[0], "grad_norm": info[1], "Q_tot": info[2]}          # qmix.py:195-198 (0-dim device tensors)
         new_priorities = DeviceArray(self.ws_view("prio")[:b.B]) if self.use_per else None
         return train_info, new_priorities, batch[8]
+
+    def _step_graph(self, batch, B):
+        """The learner step on a sampled batch always reads the replay's batch region, so its launch sequence is captured once
+        per (buffer, B) into a CUDA graph (on a private stream; the legacy default stream cannot capture) and replayed on the
+        caller's stream: one cudaGraphLaunch instead of 13 kernel launches per `train_policy_on_batch`."""
+        buf = batch.buffers["policy_0"]
+        key = (id(buf), int(B))
+        g = self._graphs.get(key)
+        if g is None:
+            if self._cap_stream is None:
+                self._cap_stream = torch.cuda.Stream(device=self.dev)
+            torch.cuda.synchronize(self.dev)
+            h = C.c_void_p()
+            capi.check(capi.lib().mx_graph_capture(buf.handle, self.handle, int(B), 0.0, 0, C.c_void_p(self._cap_stream.cuda_stream), C.byref(h)))
+            self._graphs[key] = g = h
+            self._graph_keep.append(buf)
+        return g
+
+    def drop_step_graphs(self):
+        for g in self._graphs.values():
+            capi.lib().mx_graph_destroy(g)
+        self._graphs = {}
 
     def hard_target_updates(self):
         print("hard update targets")

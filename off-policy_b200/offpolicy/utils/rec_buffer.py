@@ -149,6 +149,7 @@ class RecPolicyBuffer(object):
         self._pack_cache = {}
         self._idx_dev = torch.zeros(self.max_batch, dtype=torch.int64, device=self.dev)
         self._idx_pin = None
+        self._idx_ring, self._idx_k = None, 0
 
     def __del__(self):
         try:
@@ -274,8 +275,25 @@ class RecPolicyBuffer(object):
         B = len(inds)
         if B > self.max_batch:
             raise ValueError("batch_size %d exceeds max_batch=%d (pass max_batch= to the buffer)" % (B, self.max_batch))
-        dev = self.upload_indices(inds)
-        capi.check(capi.lib().mx_replay_gather(self.handle, capi.ptr(dev), B, capi.stream_ptr()))
+        if self.dev.type == "cuda":
+            # indices go through a small pinned ring; a slot is rewritten only after the H2D copy that read it has completed
+            if self._idx_ring is None:
+                self._idx_ring = [torch.empty(self.max_batch, dtype=torch.int64, pin_memory=True) for _ in range(4)]
+                self._idx_ring_np = [t.numpy() for t in self._idx_ring]
+                self._idx_ring_ptr = [C.c_void_p(t.data_ptr()) for t in self._idx_ring]
+                self._idx_ring_evt = [None] * 4
+            k = self._idx_k
+            self._idx_k = (k + 1) & 3
+            if self._idx_ring_evt[k] is not None:
+                self._idx_ring_evt[k].synchronize()
+            self._idx_ring_np[k][:B] = inds
+            capi.check(capi.lib().mx_replay_gather_host(self.handle, self._idx_ring_ptr[k], B, capi.stream_ptr()))
+            evt = self._idx_ring_evt[k] or torch.cuda.Event()
+            evt.record()
+            self._idx_ring_evt[k] = evt
+        else:
+            dev = self.upload_indices(inds)
+            capi.check(capi.lib().mx_replay_gather(self.handle, capi.ptr(dev), B, capi.stream_ptr()))
         self.sample_serial += 1
 
     def sample_device_uniform(self, B):
