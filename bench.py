@@ -15,6 +15,7 @@ SMAC-shaped replay data.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import ctypes as C
+import contextlib
 import json
 import os
 import subprocess
@@ -118,7 +119,8 @@ def run_maddpg(args):
         k = min(128, E - c)
         buf.insert(k, *[rc.d(x) for x in episodes(k)], None)
     torch.manual_seed(1)
-    margs, pol, tr = mc.build(cfg, B, T)
+    with contextlib.redirect_stdout(sys.stderr):        # (the drop-in classes mirror the reference's prints)
+        margs, pol, tr = mc.build(cfg, B, T)
     buf.seed_device_rng(1)
 
     def step():
@@ -147,11 +149,15 @@ def run_maddpg(args):
     ms = e0.elapsed_time(e1) / args.steps
     launches = int(lib.mx_launch_count() - l0)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(50):
+    for _ in range(10):
         float(step()["critic_loss"])
     torch.cuda.synchronize()
-    e2e = 50 / (time.perf_counter() - t0)
+    n_e2e = max(50, min(args.steps, 200))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        float(step()["critic_loss"])
+    torch.cuda.synchronize()
+    e2e = n_e2e / (time.perf_counter() - t0)
     torch.set_num_threads(8)
     L = MaddpgLearner(cfg, seed=1)
     tms = []
@@ -342,7 +348,8 @@ def run_engine(args):
         buf.insert(n, *[rc.d(x) for x in synth_episodes(cfg, T, n, rs)])
     torch.manual_seed(1)
     np.random.seed(1)
-    args_ns, pol, tr = qc.build_trainer(cfg, B, T)
+    with contextlib.redirect_stdout(sys.stderr):        # the drop-in QMix mirrors the reference's "double Q learning will be used" print
+        args_ns, pol, tr = qc.build_trainer(cfg, B, T)
     pb = buf.policy_buffers["policy_0"]
     buf.seed_device_rng(1 + rank)
     stream = torch.cuda.current_stream()

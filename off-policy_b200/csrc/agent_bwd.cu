@@ -496,14 +496,30 @@ int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
   return MX_CHECK_LAUNCH("gru_bwd");
 }
 
-int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
-  const int RM = 2, TM = 16 * RM;
+// Tile height: the grid is one persistent CTA per SM, so the kernel takes `waves` tile-times; pick the 16*RM rows per tile that
+// minimise waves * (fixed per-tile cost + RM) -- e.g. 3m: 5856 rows = 183 tiles of 32 (2 waves) but 122 tiles of 48 (1 wave).
+static int front_bwd_pick_rm(int M, int in_dim, int sms) {
+  int best = 2;
+  double best_cost = 1e30;
+  for (int rm = 2; rm <= 4; ++rm) {
+    FrontBwdSmem sm = front_bwd_smem(in_dim, 16 * rm);
+    if ((size_t)sm.total * sizeof(float) + 16 > 227 * 1024) continue;
+    const int tiles = mx_ceil_div(M, 16 * rm);
+    const double cost = (double)mx_ceil_div(tiles, sms) * (1.0 + rm);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = rm; }
+  }
+  return best;
+}
+
+template <int RM>
+static int front_bwd_launch(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
+  const int TM = 16 * RM;
   FrontBwdSmem sm = front_bwd_smem(a.L.in_dim, TM);
   const size_t smem = (size_t)sm.total * sizeof(float) + 16;
   const int ntiles = mx_ceil_div(a.M, TM);
   int grid = mx_num_sms();
   if (grid > ntiles) grid = ntiles;
-  auto kern = k_front_bwd<2>;
+  auto kern = k_front_bwd<RM>;
 #if !MX_EMU
   if (smem > 227 * 1024) { mx_set_error("front_bwd: %zu bytes of shared memory needed (obs_dim too large)", smem); return 1; }
   static size_t configured = 0;
@@ -514,4 +530,11 @@ int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s)
   MX_MARK("k_front_bwd", s);
   *nparts_used = grid;
   return MX_CHECK_LAUNCH("front_bwd");
+}
+
+int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
+  const int rm = front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms());
+  if (rm == 3) return front_bwd_launch<3>(a, nparts_used, s);
+  if (rm == 4) return front_bwd_launch<4>(a, nparts_used, s);
+  return front_bwd_launch<2>(a, nparts_used, s);
 }

@@ -14,7 +14,7 @@ struct FrontFwdArgs {
   const float* tc_img[2];  // optional: pre-split TF32 hi/lo weight images in UMMA layout (mx_launch_tc_prep_weights)
 };
 size_t mx_tc_image_floats(int in_dim);
-int mx_launch_tc_prep_weights(const float* theta, const MxNetLayout& L, float* img, cudaStream_t s);
+int mx_launch_tc_prep_weights(const float* const theta[2], const MxNetLayout& L, float* const img[2], int nets, cudaStream_t s);
 size_t mx_front_fwd_smem(int in_dim, int RM);
 int mx_launch_front_fwd(const FrontFwdArgs& a, int nets, cudaStream_t s);
 

@@ -30,7 +30,11 @@ __global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
       a.grad[a.P + 1] = t1;
       a.grad[a.P + 2] = t2;
       a.grad[a.P + 3] = (float)(a.B * a.T);
-      a.adam_t[0] += 1.0;                                  // Adam step count (1-based)
+      // Adam step count (1-based) and the running powers beta^t for the bias corrections (first step: 1 * beta)
+      const double t_old = a.adam_t[0];
+      a.adam_t[0] = t_old + 1.0;
+      a.adam_t[1] = (t_old == 0.0 ? 1.0 : a.adam_t[1]) * (double)a.beta1;
+      a.adam_t[2] = (t_old == 0.0 ? 1.0 : a.adam_t[2]) * (double)a.beta2;
     }
     // ---- PER: new priority = (1-nu) * mean_t|e| + nu * max_t|e| + eps  (mean over all T, masked steps are zeros) ----
     if (a.prio) {
@@ -51,18 +55,23 @@ __global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
   int parts = 0;
   for (int s = 0; s < a.nseg; ++s)
     if (i >= a.seg_begin[s] && i < a.seg_end[s]) parts = a.seg_parts[s];
-  // four independent chains keep >= 8 partial loads in flight (fixed order -> deterministic result)
-  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  // eight independent chains, unrolled twice: 16 partial loads in flight per thread (fixed order -> deterministic result)
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g5 = 0.f, g6 = 0.f, g7 = 0.f;
   const float* gp = a.gpart + i;
   int p = 0;
 #pragma unroll 2
-  for (; p + 4 <= parts; p += 4) {
+  for (; p + 8 <= parts; p += 8) {
     g0 += gp[(size_t)p * a.P];
     g1 += gp[(size_t)(p + 1) * a.P];
     g2 += gp[(size_t)(p + 2) * a.P];
     g3 += gp[(size_t)(p + 3) * a.P];
+    g4 += gp[(size_t)(p + 4) * a.P];
+    g5 += gp[(size_t)(p + 5) * a.P];
+    g6 += gp[(size_t)(p + 6) * a.P];
+    g7 += gp[(size_t)(p + 7) * a.P];
   }
   for (; p < parts; ++p) g0 += gp[(size_t)p * a.P];
+  g0 += g4; g1 += g5; g2 += g6; g3 += g7;
   a.grad[i] = (g0 + g1) + (g2 + g3);
 }
 
@@ -92,10 +101,9 @@ __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
       const float norm = (float)sqrt(t);
       float coef = a.max_grad_norm / (norm + 1e-6f);       // clip_grad_norm_: always applied, clamped to 1
       if (coef > 1.f) coef = 1.f;
-      const double st = a.adam_t[0];
       s_scale = coef * invd;
-      s_step = a.lr / (float)(1.0 - pow((double)a.beta1, st));
-      s_bc2s = (float)sqrt(1.0 - pow((double)a.beta2, st));
+      s_step = a.lr / (float)(1.0 - a.adam_t[1]);          // beta1^t, beta2^t maintained by k_grad_reduce
+      s_bc2s = (float)sqrt(1.0 - a.adam_t[2]);
       if (blockIdx.x == 0) {
         a.info[0] = a.grad[a.P + 1] * invd;                // loss
         a.info[1] = norm;                                  // grad_norm (pre-clip)

@@ -249,10 +249,10 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   ff.u1 = ws + W.u1; ff.u2 = ws + W.u2; ff.st0 = ws + W.st0; ff.st1 = ws + W.st1; ff.st2 = ws + W.st2;
 #if !MX_EMU
   if (g_mx_front_tc && c.obs_dim <= 64) {       // weights changed in the last Adam / Polyak: rebuild the TF32 hi/lo images (18k elements per net)
-    for (int k = 0; k < 2; ++k) {
-      if (mx_launch_tc_prep_weights(k == 0 ? q->theta : q->theta_tgt, q->agent, ws + W.tcimg[k], s)) return 1;
-      ff.tc_img[k] = ws + W.tcimg[k];
-    }
+    const float* const th2[2] = {q->theta, q->theta_tgt};
+    float* const img2[2] = {ws + W.tcimg[0], ws + W.tcimg[1]};
+    if (mx_launch_tc_prep_weights(th2, q->agent, img2, 2, s)) return 1;
+    ff.tc_img[0] = img2[0]; ff.tc_img[1] = img2[1];
   }
 #endif
   if (mx_launch_front_fwd(ff, 2, s)) return 1;

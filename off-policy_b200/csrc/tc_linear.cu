@@ -190,10 +190,12 @@ __device__ __forceinline__ void tc_stage_weight(char* hi, char* lo, const float*
 
 // Weight images: [w1 hi | w1 lo | w2 hi | w2 lo | w_ih hi | w_ih lo], each already in the UMMA core-matrix layout, so a CTA
 // stages all three layers with straight 16-byte cp.async copies (no per-CTA conversion).  Rebuilt once per step.
-__global__ void __launch_bounds__(256) k_tc_prep_weights(const float* __restrict__ th, MxNetLayout L, float* __restrict__ img) {
+struct TcPrepArgs { const float* th[2]; float* img[2]; };
+__global__ void __launch_bounds__(256) k_tc_prep_weights(TcPrepArgs p, MxNetLayout L) {
+  const float* __restrict__ th = p.th[blockIdx.y];
   const int I = L.in_dim, Kp = (I + 7) & ~7;
   const int n1 = MX_H * Kp, n2 = MX_H * MX_H, n3 = MX_G * MX_H;
-  char* base = reinterpret_cast<char*>(img);
+  char* base = reinterpret_cast<char*>(p.img[blockIdx.y]);
   MX_PDL_WAIT();
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2 + n3; idx += gridDim.x * blockDim.x) {
     int n, k, K, Kd;
@@ -210,9 +212,12 @@ size_t mx_tc_image_floats(int in_dim) {
   const int Kp = mx_round_up(in_dim, 8);
   return (size_t)2 * (MX_H * Kp + MX_H * MX_H + MX_G * MX_H);
 }
-int mx_launch_tc_prep_weights(const float* theta, const MxNetLayout& L, float* img, cudaStream_t s) {
+// one launch for `nets` parameter vectors (live, target)
+int mx_launch_tc_prep_weights(const float* const theta[2], const MxNetLayout& L, float* const img[2], int nets, cudaStream_t s) {
   const int n = MX_H * mx_round_up(L.in_dim, 8) + MX_H * MX_H + MX_G * MX_H;
-  MX_LAUNCH_PDL(k_tc_prep_weights, dim3((n + 255) / 256), dim3(256), 0, s, theta, L, img);
+  TcPrepArgs p;
+  for (int k = 0; k < 2; ++k) { p.th[k] = theta[k < nets ? k : 0]; p.img[k] = img[k < nets ? k : 0]; }
+  MX_LAUNCH_PDL(k_tc_prep_weights, dim3((n + 255) / 256, nets), dim3(256), 0, s, p, L);
   MX_COUNT();
   MX_MARK("k_tc_prep_weights", s);
   return MX_CHECK_LAUNCH("tc_prep_weights");

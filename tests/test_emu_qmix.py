@@ -7,3 +7,14 @@ import qmix_checks as qc
 @pytest.mark.parametrize("name", ["qmix_small", "qmix_small_huber_nodq", "qmix_small_per", "qmix_small_hyper1", "qmix_5ag"])
 def test_step_matches_reference_golden(emu_engine, name):
     qc.check_step_against(None, name)
+
+
+@pytest.mark.parametrize("n_agents,B,T", [(3, 8, 7), (4, 8, 7), (3, 12, 7)])
+def test_front_bwd_tile_heights_vs_oracle(emu_engine, n_agents, B, T):
+    """The backward front kernel picks 32-, 48- or 64-row tiles from the row count and the SM count (4 in the emulator):
+    M = B (T+1) N = 192 -> 48-row tiles, 256 -> 64-row tiles, 288 -> 48-row tiles in two waves."""
+    from oracle.qmix import QmixConfig, synth_batch
+    cfg = QmixConfig(n_agents=n_agents, obs_dim=11, act_dim=5, state_dim=13, gain=1.0)
+    L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T)
+    batch = synth_batch(cfg, B, T, seed=5, avail_p=0.8, var_len=True) + (None, None)
+    qc.compare_step(L, pol, tr, batch, cfg, steps=2)

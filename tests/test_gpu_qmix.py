@@ -20,47 +20,8 @@ def test_step_matches_reference_golden(gpu_engine, name):
     qc.check_step_against(None, name)
 
 
-def _oracle_and_trainer(cfg, B, T, seed=3, vdn=False, **over):
-    from oracle.qmix import QmixLearner, randomize_all
-    L = QmixLearner(cfg, seed=seed)
-    randomize_all(L.agent, 1)
-    if not vdn:
-        randomize_all(L.mixer, 2)
-    L.sync_targets()
-    randomize_all(L.tgt_agent, 3, 0.05)
-    if not vdn:
-        randomize_all(L.tgt_mixer, 4, 0.05)
-    args, pol, tr = qc.build_trainer(cfg, B, T, vdn=vdn, **over)
-    qc.load_state(pol, tr, L.agent.state_dict(), None if vdn else L.mixer.state_dict(), L.tgt_agent.state_dict(),
-                  None if vdn else L.tgt_mixer.state_dict())
-    return L, args, pol, tr
-
-
-def _compare_step(L, pol, tr, batch, cfg, steps=1, tol=1e-4):
-    for s in range(steps):
-        info, prio, _ = tr.train_policy_on_batch(qc.ref_tuple(batch))
-        gv = {k: v.clone() for k, v in tr.grad_views().items()}
-        tr.soft_target_updates()
-        ref, rprio, _ = L.step(batch)
-        coef = min(1.0, cfg.max_grad_norm / (float(ref["grad_norm"]) + 1e-6))
-        L.soft_update()
-        for k in ("loss", "grad_norm", "Q_tot"):
-            assert rel_err(info[k].cpu(), ref[k]) < tol, (s, k, float(info[k]), float(ref[k]))
-        if rprio is not None:
-            assert rel_err(np.asarray(prio), rprio) < tol
-        named = dict(("agent." + k, p) for k, p in L.agent.named_parameters())
-        if not cfg.vdn:
-            named.update(("mixer." + k, p) for k, p in L.mixer.named_parameters())
-        for k, p in named.items():
-            if p.grad is None:
-                assert float(gv[k].abs().max()) == 0.0
-                continue
-            ok, err, lim = qc.close(gv[k] * coef, p.grad, tol)
-            assert ok, (s, k, err, lim)
-        for k, v in pol.q_network.state_dict().items():
-            assert float((v.cpu() - L.agent.state_dict()[k]).abs().max()) <= 5e-3 * cfg.lr * (s + 1) + 1e-7, (s, k)
-        for k, v in tr.target_q_network.state_dict().items():
-            assert float((v.cpu() - L.tgt_agent.state_dict()[k]).abs().max()) <= 1e-6, (s, k)
+_oracle_and_trainer = qc.oracle_and_trainer
+_compare_step = qc.compare_step
 
 
 def test_config2_3m_full_size_vs_oracle(gpu_engine):
