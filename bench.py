@@ -455,6 +455,7 @@ def run_engine(args):
     # ---------------- per-kernel timing (eager, CUDA events on the launch stream) ----------------
     # every rank runs this loop: the eager step contains the all-reduce, so the collective counts must match on all ranks
     buf.rng = "device"
+    tr.use_step_graph = False       # individual launches (with event marks between them), not the captured graph
     kern = {}
     reps, inner = 6, 8
     for rep in range(reps + 1):

@@ -532,8 +532,9 @@ static int front_bwd_launch(const FrontBwdArgs& a, int* nparts_used, cudaStream_
   return MX_CHECK_LAUNCH("front_bwd");
 }
 
+extern int g_mx_front_bwd_rm;
 int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
-  const int rm = front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms());
+  const int rm = g_mx_front_bwd_rm ? g_mx_front_bwd_rm : front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms());
   if (rm == 3) return front_bwd_launch<3>(a, nparts_used, s);
   if (rm == 4) return front_bwd_launch<4>(a, nparts_used, s);
   return front_bwd_launch<2>(a, nparts_used, s);

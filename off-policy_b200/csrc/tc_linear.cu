@@ -408,6 +408,8 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
 
 int g_mx_front_tc = 1;        // 1: tcgen05 3xTF32 kernel (default), 0: FFMA kernel (mx_set_option("front_tc", 0))
 int g_mx_tc_swap = 0;
+int g_mx_mixer_rm = 0;        // tuning overrides (0 = automatic): rows per thread of the mixer / backward front tiles
+int g_mx_front_bwd_rm = 0;
 
 int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
   const int Kp = mx_round_up(a.L.in_dim, 8);
@@ -431,6 +433,8 @@ int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
 extern "C" int mx_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "front_tc")) { g_mx_front_tc = value; return 0; }
   if (!strcmp(name, "tc_swap_ls")) { g_mx_tc_swap = value; return 0; }
+  if (!strcmp(name, "mixer_rm")) { g_mx_mixer_rm = value; return 0; }
+  if (!strcmp(name, "front_bwd_rm")) { g_mx_front_bwd_rm = value; return 0; }
 #if !MX_EMU
   if (!strcmp(name, "pdl")) { g_mx_pdl = value; return 0; }
 #endif
@@ -503,6 +507,8 @@ extern "C" int mx_tc_linear_probe(const float* X, const float* W, float* Y, int3
 }
 #else
 int g_mx_front_tc = 0;
+int g_mx_mixer_rm = 0;
+int g_mx_front_bwd_rm = 0;
 extern "C" int mx_set_option(const char*, int32_t) { return 0; }
 extern "C" int mx_tc_linear_probe(const float*, const float*, float*, int32_t, int32_t, int32_t, int32_t, int32_t, void*) {
   mx_set_error("tcgen05 kernels cannot be emulated");
