@@ -63,8 +63,20 @@ struct MixerArgs {
   float* gpart;            // [npart][P]   this kernel writes the mixer slice of partial blockIdx.x
   long long P;
   float* spart;            // [npart][8]   (sum(1-bad), loss numerator, sum Q_tot(1-bad))
+  // ---- split pipeline (mx_launch_mix_hyper_fwd / _core / _hyper_bwd): per-element hypernet outputs kept in global memory so
+  // that the state-only hypernet layers run beside the agent-net kernels instead of between them (row strides gH/gP/gM floats)
+  float *hyp_h1, *hyp_h2, *hyp_hb;                        // live [E][gH]: post-ReLU hidden layers of hyper_w1 / hyper_w2 / hyper_b2
+  float *hyp_p1[2], *hyp_b1[2], *hyp_p2[2], *hyp_b2[2];   // [live|target]: raw hyper_w1 out [E][gP], hyper_b1 [E][gM], hyper_w2 [E][gM], b2 [E]
+  float *d_q, *d_hp, *d_p2, *d_p1;                        // dL/dQ_tot [E], d(hidden pre-ELU) [E][gM], d(hyper_w2 out) [E][gM], d(hyper_w1 out) [E][gP]
+  int gH, gP, gM;
 };
 int mx_launch_mixer(const MixerArgs& a, int* nparts_used, cudaStream_t s);
+// split form of the same computation (k_mixer == hyper_fwd ; core ; hyper_bwd).  hyper_fwd depends only on the batch's states and
+// the parameters, hyper_bwd only on core's outputs: the learner runs them on a forked branch next to the agent-net kernels.
+int mx_mixer_split_supported(const MxMixLayout& L);
+int mx_launch_mix_hyper_fwd(const MixerArgs& a, cudaStream_t s);
+int mx_launch_mix_core(const MixerArgs& a, int* scalar_parts_used, cudaStream_t s);
+int mx_launch_mix_hyper_bwd(const MixerArgs& a, int* nparts_used, cudaStream_t s);
 
 struct QHeadBwdArgs {
   const float* theta;
