@@ -39,6 +39,15 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel, {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -313,6 +322,9 @@ def kernel_work(cfg, T, B, P):
         "k_gru_fwd": 2 * 2.0 * M * 3 * H * H,
         "k_qhead": 2 * 2.0 * M * H * A,
         "k_mixer": 2.0 * E * mix * 4,                    # target fwd + live fwd + live bwd (dgrad + wgrad)
+        "k_mix_hyper_fwd": 2.0 * E * (mix - N * ME - ME) * 2,         # split pipeline: hypernet layers of the live + target mixers
+        "k_mix_core": 2.0 * E * (N * ME + ME) * 4,                    # q-dependent part: both forwards + backward
+        "k_mix_hyper_bwd": 2.0 * E * (mix - N * ME - ME) * 2,         # dgrad + wgrad of the live hypernets
         "k_qhead_bwd": 2.0 * M * 3 * H,
         "k_gru_bwd": 2.0 * M * 3 * H * H,
         "k_front_bwd": 2.0 * M * (2 * 3 * H * H * 2 + 3 * H * H + 2 * H * H + H * H + 2 * O * H + O * H) / 1.0,
@@ -494,11 +506,11 @@ def run_engine(args):
     if top in fl:
         ach = fl[top] / (kavg[top] * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel=top, achieved=ach, peak=pk["tflops_sustained"], unit="TFLOP/s", frac=ach / pk["tflops_sustained"],
-                    traffic=None, peak_source=pk["src"] + " bf16 sustained (kernel timed inside the step)",
+                    traffic=ncu_traffic(top), peak_source=pk["src"] + " bf16 sustained (kernel timed inside the step)",
                     note="FP32 FFMA kernel (1e-4 parity budget); serial-recurrence / latency bound at these sizes, see DESIGN.md")
     else:
         ach = by.get(top, 0.0) / (kavg[top] * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel=top, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=None, peak_source=pk["src"])
+        roof = dict(bound="hbm", kernel=top, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=ncu_traffic(top), peak_source=pk["src"])
     gather_gbs = by["k_gather"] / (kavg.get("k_gather", 1e9) * 1e-3) / 1e9
     breakdown = {k: dict(ms=round(v, 5), share=round(v / ksum, 4)) for k, v in sorted(kavg.items(), key=lambda kv: -kv[1])}
 
@@ -519,11 +531,13 @@ def run_engine(args):
                     value_definition="batch-%d grad-steps/s summed over ranks (each rank samples its own shard; one flat all-reduce)" % B,
                     l2="inputs gathered from a replay larger than L2 (%.0f MB); the per-step working set is L2-resident by design" %
                        (pb.L.total_bytes / 1e6),
-                    step="CUDA graph: device MT19937 draw + gather + fused QMIX learner + Adam + Polyak" if (graph or tgraph) else "eager"),
+                    step="CUDA graph: device MT19937 draw + gather + fused QMIX learner + Adam + Polyak; state-only kernels (weight images, mixer "
+                         "hypernets) on a forked graph branch beside the agent-net kernels" if (graph or tgraph) else "eager"),
         e2e=dict(value=e2e_sps, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=n_e2e,
                  path="RecReplayBuffer.insert(1 episode, pinned) + sample(np.random.choice) + QMix.train_policy_on_batch + soft_target_updates + D2H info"),
         gpu_launches=launches, kernels_per_step=kernels_per_step,
-        roofline=roof, kernels=breakdown, gather_gbs=gather_gbs,
+        roofline=roof, kernels=breakdown, kernel_sum_ms=round(ksum, 5),        # > ms_per_step when branches of the step graph overlap
+        gather_gbs=gather_gbs,
         cpu_baseline=dict(value=best, unit="steps/s", cores=cores if sps_all >= sps_one else 1, host_cores=os.cpu_count(), kind="port",
                           best_threads_steps_per_s=sps_all, one_thread_steps_per_s=sps_one,
                           sample="%d timed steps (sample+train+soft update) of the same workload on a %d-episode replay, oracle port of the reference learner" % (n_cpu, Ecpu)),

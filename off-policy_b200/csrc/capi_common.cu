@@ -1,6 +1,7 @@
 // Error reporting, launch accounting and device queries shared by every entry point.
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "mx_internal.h"
 
@@ -10,6 +11,17 @@ long long g_mx_launches = 0;
 int g_mx_pdl = 0;     // measured slower on B200: dependents' prologues share the SM with the latency-bound recurrences
 int g_mx_pdl_skip_next = 0;
 #endif
+
+// runtime options shared by the product and the emulated build (mx_set_option)
+int g_mx_mixer_split = 1;      // 1: hypernet-forward / core / hypernet-backward kernels (default); 0: the single fused k_mixer
+int g_mx_mixer_split_rm = 0;   // rows per thread of the split mixer's tiles (0 = automatic)
+int g_mx_overlap = 1;          // 1: state-only kernels (weight-image prep, mixer hypernets) run on a forked branch beside the agent-net kernels
+int mx_set_option_common(const char* name, int value) {
+  if (!strcmp(name, "mixer_split")) { g_mx_mixer_split = value; return 0; }
+  if (!strcmp(name, "mixer_split_rm")) { g_mx_mixer_split_rm = value; return 0; }
+  if (!strcmp(name, "overlap")) { g_mx_overlap = value; return 0; }
+  return -1;
+}
 
 void mx_set_error(const char* fmt, ...) {
   va_list ap;

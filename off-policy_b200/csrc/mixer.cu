@@ -106,13 +106,13 @@ __device__ MX_NOINLINE void tile_wgrad(const float* dY_s, int ldy, int Nout, con
   mx_colsum(dY_s, ldy, TE, Nout, db, accumulate);
 }
 
+// the state-only hypernetwork layers of one tile: h1/h2/hb (post-ReLU), p1 = hyper_w1(s), p2 = hyper_w2(s), b1 = hyper_b1(s)
 template <int RM>
-MX_DEVINL void mixer_forward(const float* __restrict__ th, const MxMixLayout& L, const MixSmem& sm, float* smem, float* Qout /*[TE] in smem*/) {
-  constexpr int TE = 16 * RM;
+MX_DEVINL void mixer_hyper(const float* __restrict__ th, const MxMixLayout& L, const MixSmem& sm, float* smem) {
   float* s_s = smem + sm.o_s;
   float* h1_s = smem + sm.o_h1; float* h2_s = smem + sm.o_h2; float* hb_s = smem + sm.o_hb;
-  float* p1_s = smem + sm.o_p1; float* b1_s = smem + sm.o_b1; float* p2_s = smem + sm.o_p2; float* hid_s = smem + sm.o_hid;
-  float* q_s = smem + sm.o_q; float* Wc = smem + sm.o_wc;
+  float* p1_s = smem + sm.o_p1; float* b1_s = smem + sm.o_b1; float* p2_s = smem + sm.o_p2;
+  float* Wc = smem + sm.o_wc;
   const int NM = L.N * L.ME;
   if (L.layers == 2) {
     tile_linear<RM>(s_s, sm.ldS, L.S, th + L.w1a, th + L.b1a, L.HY, h1_s, sm.ldH, true, Wc, sm.ldw);
@@ -125,6 +125,15 @@ MX_DEVINL void mixer_forward(const float* __restrict__ th, const MxMixLayout& L,
   }
   tile_linear<RM>(s_s, sm.ldS, L.S, th + L.wb1, th + L.bb1, L.ME, b1_s, sm.ldM, false, Wc, sm.ldw);
   tile_linear<RM>(s_s, sm.ldS, L.S, th + L.wb2a, th + L.bb2a, L.HY, hb_s, sm.ldH, true, Wc, sm.ldw);
+}
+
+template <int RM>
+MX_DEVINL void mixer_forward(const float* __restrict__ th, const MxMixLayout& L, const MixSmem& sm, float* smem, float* Qout /*[TE] in smem*/) {
+  constexpr int TE = 16 * RM;
+  float* hb_s = smem + sm.o_hb;
+  float* p1_s = smem + sm.o_p1; float* b1_s = smem + sm.o_b1; float* p2_s = smem + sm.o_p2; float* hid_s = smem + sm.o_hid;
+  float* q_s = smem + sm.o_q;
+  mixer_hyper<RM>(th, L, sm, smem);
   // hidden = ELU(q . |w1| + b1)   (pre-activation kept in hid_s)
   for (int idx = threadIdx.x; idx < TE * L.ME; idx += MX_TILE_THREADS) {
     const int e = idx / L.ME, k = idx % L.ME;
@@ -368,6 +377,266 @@ __global__ void __launch_bounds__(256) k_vdn_mix(MixerArgs a) {
   }
 }
 
+// =====================================================================================================
+// Split pipeline: hyper_fwd ; core ; hyper_bwd  ==  k_mixer, with the per-element hypernet outputs in global
+// memory (L2-resident).  hyper_fwd needs only the sampled states and the parameters, hyper_bwd only core's
+// outputs, so the learner (qmix.cu) runs both on a forked branch beside the agent-net kernels; only the tiny
+// q-dependent core stays between k_qhead and k_qhead_bwd.
+// =====================================================================================================
+// state rows of tile [e0, e0+TE) -> s_s (16-byte async copies; pad columns and rows >= E zero-filled)
+MX_DEVINL void mix_stage_states(const MixerArgs& a, const MixSmem& sm, float* s_s, int e0, int E, int TE, int S64, int tshift) {
+  const int tid = threadIdx.x;
+  const int nc4 = S64 >> 2, src4 = a.share_ld >> 2;
+  for (int r = tid >> 4; r < TE; r += MX_TILE_THREADS / 16) {
+    const int e = e0 + r;
+    const float* src = nullptr;
+    if (e < E) {
+      const int b = e / a.T, t = e % a.T;
+      src = a.share + ((size_t)b * (a.T + 1) + t + tshift) * a.share_ld;
+    }
+    for (int c4 = tid & 15; c4 < nc4; c4 += 16) {
+      float* d = s_s + r * sm.ldS + 4 * c4;
+      if (src && c4 < src4) mx_cp16(d, src + 4 * c4);
+      else mx_st4(d, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+}
+// smem tile [TE][lds] (columns [0, gcols) ) -> global rows e0.. of dst[E][gcols]   (gcols % 4 == 0)
+MX_DEVINL void mix_tile_store(const float* src_s, int lds, float* __restrict__ dst, int gcols, int e0, int E, int TE) {
+  const int nc4 = gcols >> 2;
+  for (int idx = threadIdx.x; idx < TE * nc4; idx += MX_TILE_THREADS) {
+    const int r = idx / nc4, c4 = idx - r * nc4;
+    if (e0 + r < E) mx_st4(dst + (size_t)(e0 + r) * gcols + 4 * c4, mx_ld4(src_s + r * lds + 4 * c4));
+  }
+}
+// global rows e0.. of src[E][gcols] -> smem tile [TE][lds], zero-filled out to `width` columns (width % 4 == 0, width <= lds)
+MX_DEVINL void mix_tile_load(float* dst_s, int lds, int width, const float* __restrict__ src, int gcols, int e0, int E, int TE) {
+  const int nc4 = width >> 2, g4 = gcols >> 2;
+  for (int idx = threadIdx.x; idx < TE * nc4; idx += MX_TILE_THREADS) {
+    const int r = idx / nc4, c4 = idx - r * nc4;
+    float* d = dst_s + r * lds + 4 * c4;
+    if (e0 + r < E && c4 < g4) mx_cp16(d, src + (size_t)(e0 + r) * gcols + 4 * c4);
+    else mx_st4(d, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
+// blockIdx.y = 0: live net on s[t]; 1: target net on s[t+1] (qmix.py:155-157)
+template <int RM>
+__global__ void __launch_bounds__(MX_TILE_THREADS) k_mix_hyper_fwd(MixerArgs a, MixSmem sm) {
+  constexpr int TE = 16 * RM;
+  MX_DYN_SMEM(smem);
+  const MxMixLayout L = a.L;
+  const int E = a.B * a.T;
+  const int ntiles = (E + TE - 1) / TE;
+  const int net = blockIdx.y;
+  const float* th = net ? a.theta_tgt : a.theta;
+  float* s_s = smem + sm.o_s;
+  float* h1_s = smem + sm.o_h1; float* h2_s = smem + sm.o_h2; float* hb_s = smem + sm.o_hb;
+  float* p1_s = smem + sm.o_p1; float* b1_s = smem + sm.o_b1; float* p2_s = smem + sm.o_p2;
+  const int S64 = mx_round_up(L.S, 64);
+  MX_PDL_WAIT();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e0 = tile * TE;
+    mix_stage_states(a, sm, s_s, e0, E, TE, S64, net);
+    mx_cp_commit();
+    mx_cp_wait<0>();
+    __syncthreads();
+    mixer_hyper<RM>(th, L, sm, smem);
+    // b2 = hb . Wb2b + bb2b   (one half-warp per element)
+    {
+      const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+      for (int i = 0; i < RM; ++i) {
+        const int r = ty * RM + i;
+        float v = 0.f;
+        for (int k = tx; k < L.HY; k += 16) v = fmaf(hb_s[r * sm.ldH + k], th[L.wb2b + k], v);
+        v = mx_row16_sum(v);
+        if (tx == 0 && e0 + r < E) a.hyp_b2[net][e0 + r] = v + th[L.bb2b];
+      }
+    }
+    mix_tile_store(p1_s, sm.ldP, a.hyp_p1[net], a.gP, e0, E, TE);
+    mix_tile_store(b1_s, sm.ldM, a.hyp_b1[net], a.gM, e0, E, TE);
+    mix_tile_store(p2_s, sm.ldM, a.hyp_p2[net], a.gM, e0, E, TE);
+    if (net == 0) {     // kept for the backward pass
+      if (L.layers == 2) {
+        mix_tile_store(h1_s, sm.ldH, a.hyp_h1, a.gH, e0, E, TE);
+        mix_tile_store(h2_s, sm.ldH, a.hyp_h2, a.gH, e0, E, TE);
+      }
+      mix_tile_store(hb_s, sm.ldH, a.hyp_hb, a.gH, e0, E, TE);
+    }
+    __syncthreads();
+  }
+}
+
+// One warp per (b,t) element, lanes over the mixer's hidden units: Q_tot' (target), Q_tot (live), TD target, masked loss,
+// dL/dQ_tot and the elementwise part of the live mixer's backward (q_mixer.py:82-93, qmix.py:159-187).
+#define MX_MIX_MAXK 2      // mixer_hidden <= 64
+__global__ void __launch_bounds__(256) k_mix_core(MixerArgs a) {
+  const MxMixLayout L = a.L;
+  const int E = a.B * a.T, N = L.N, ME = L.ME;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float den = 0.f, lsum = 0.f, qsum = 0.f;
+  MX_PDL_WAIT();
+  for (int e = blockIdx.x * nw + warp; e < E; e += gridDim.x * nw) {
+    float Qv[2];
+    float hp[MX_MIX_MAXK], hvv[MX_MIX_MAXK], p2v[MX_MIX_MAXK];
+#pragma unroll
+    for (int net = 1; net >= 0; --net) {
+      const float* q = (net ? a.q_next : a.q_taken) + (size_t)e * N;
+      const float* p1 = a.hyp_p1[net] + (size_t)e * a.gP;
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < MX_MIX_MAXK; ++j) {
+        const int k = lane + 32 * j;
+        if (k < ME) {
+          float v = a.hyp_b1[net][(size_t)e * a.gM + k];
+          for (int n = 0; n < N; ++n) v = fmaf(q[n], fabsf(p1[n * ME + k]), v);
+          const float hv = v > 0.f ? v : (expf(v) - 1.f);
+          const float p2 = a.hyp_p2[net][(size_t)e * a.gM + k];
+          part = fmaf(hv, fabsf(p2), part);
+          if (net == 0) { hp[j] = v; hvv[j] = hv; p2v[j] = p2; }
+        }
+      }
+      Qv[net] = mx_warp_sum(part) + a.hyp_b2[net][e];
+    }
+    const int b = e / a.T, t = e % a.T;
+    const float rew = a.rewards[((size_t)b * a.T + t) * N];              // agent 0 (qmix.py:159)
+    const float de = a.dones_env[(size_t)b * a.T + t];
+    const float bad = t > 0 ? a.dones_env[(size_t)b * a.T + t - 1] : 0.f;     // qmix.py:161
+    const float y = rew + (1.f - de) * a.gamma * Qv[1];
+    const float keep = 1.f - bad;
+    const float err = (Qv[0] - y) * keep;
+    const float w = a.weights ? a.weights[b] : 1.f;
+    float le, dle;
+    if (a.use_huber) {
+      const float ae = fabsf(err);
+      if (ae <= a.huber_delta) { le = 0.5f * err * err; dle = err; }
+      else { le = a.huber_delta * (ae - 0.5f * a.huber_delta); dle = err > 0.f ? a.huber_delta : -a.huber_delta; }
+    } else { le = err * err; dle = 2.f * err; }
+    const float dq = dle * keep * w;
+    if (lane == 0) {
+      a.qtot[e] = Qv[0]; a.qtot_next[e] = Qv[1]; a.err[e] = err; a.d_q[e] = dq;
+      den += keep; lsum += le * w; qsum += Qv[0] * keep;
+    }
+    // elementwise backward: d hid_pre, d p2 ; then d q_taken and d p1
+    float dhp[MX_MIX_MAXK];
+#pragma unroll
+    for (int j = 0; j < MX_MIX_MAXK; ++j) {
+      const int k = lane + 32 * j;
+      dhp[j] = 0.f;
+      if (k < ME) {
+        const float dhid = dq * fabsf(p2v[j]);
+        dhp[j] = dhid * (hp[j] > 0.f ? 1.f : (hvv[j] + 1.f));                      // ELU'(x) = exp(x) for x <= 0
+        a.d_hp[(size_t)e * a.gM + k] = dhp[j];
+        a.d_p2[(size_t)e * a.gM + k] = dq * hvv[j] * (p2v[j] > 0.f ? 1.f : (p2v[j] < 0.f ? -1.f : 0.f));   // d|x| = sign(x)
+      }
+    }
+    const float* p1 = a.hyp_p1[0] + (size_t)e * a.gP;
+    const float* q = a.q_taken + (size_t)e * N;
+    for (int n = 0; n < N; ++n) {
+      float acc = 0.f;
+      const float qn = q[n];
+#pragma unroll
+      for (int j = 0; j < MX_MIX_MAXK; ++j) {
+        const int k = lane + 32 * j;
+        if (k < ME) {
+          const float pv = p1[n * ME + k];
+          acc = fmaf(fabsf(pv), dhp[j], acc);
+          a.d_p1[(size_t)e * a.gP + n * ME + k] = qn * dhp[j] * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f));
+        }
+      }
+      acc = mx_warp_sum(acc);
+      if (lane == 0) a.dq_taken[(size_t)e * N + n] = acc;
+    }
+  }
+  __shared__ float red[3][8];
+  if (lane == 0) { red[0][warp] = den; red[1][warp] = lsum; red[2][warp] = qsum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < nw; ++i) { s0 += red[0][i]; s1 += red[1][i]; s2 += red[2][i]; }
+    float* sp = a.spart + (size_t)blockIdx.x * 8;
+    sp[0] = s0; sp[1] = s1; sp[2] = s2;
+  }
+}
+
+// parameter gradients of the live hypernetworks from core's d p1 / d p2 / d hid_pre / dQ (per-CTA partials like k_mixer)
+template <int RM>
+__global__ void __launch_bounds__(MX_TILE_THREADS) k_mix_hyper_bwd(MixerArgs a, MixSmem sm) {
+  constexpr int TE = 16 * RM;
+  MX_DYN_SMEM(smem);
+  const MxMixLayout L = a.L;
+  const int tid = threadIdx.x;
+  const int E = a.B * a.T;
+  const int ntiles = (E + TE - 1) / TE;
+  float* s_s = smem + sm.o_s;
+  float* h1_s = smem + sm.o_h1; float* h2_s = smem + sm.o_h2; float* hb_s = smem + sm.o_hb;
+  float* p1_s = smem + sm.o_p1; float* p2_s = smem + sm.o_p2; float* hid_s = smem + sm.o_hid;
+  float* Wc = smem + sm.o_wc;
+  float* dQ_s = smem + sm.o_vec;          // [TE]
+  float* gp = a.gpart + (size_t)blockIdx.x * a.P;
+  const int S64 = mx_round_up(L.S, 64), H64 = mx_round_up(L.HY, 64), P64 = mx_round_up(L.N * L.ME, 64), M64 = mx_round_up(L.ME, 64);
+  const int NM = L.N * L.ME;
+  int iter = 0;
+  MX_PDL_WAIT();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+    const int e0 = tile * TE;
+    const bool accum = iter > 0;
+    mix_stage_states(a, sm, s_s, e0, E, TE, S64, 0);
+    if (L.layers == 2) {
+      mix_tile_load(h1_s, sm.ldH, H64, a.hyp_h1, a.gH, e0, E, TE);
+      mix_tile_load(h2_s, sm.ldH, H64, a.hyp_h2, a.gH, e0, E, TE);
+    }
+    mix_tile_load(hb_s, sm.ldH, H64, a.hyp_hb, a.gH, e0, E, TE);
+    mix_tile_load(p1_s, sm.ldP, P64, a.d_p1, a.gP, e0, E, TE);
+    mix_tile_load(p2_s, sm.ldM, M64, a.d_p2, a.gM, e0, E, TE);
+    mix_tile_load(hid_s, sm.ldM, M64, a.d_hp, a.gM, e0, E, TE);
+    mx_cp_commit();
+    if (tid < TE) dQ_s[tid] = (e0 + tid < E) ? a.d_q[e0 + tid] : 0.f;
+    mx_cp_wait<0>();
+    __syncthreads();
+    // -- b2 path: d Wb2b, d bb2b, then hb_s <- d(pre-ReLU hb)
+    for (int k = tid; k < L.HY; k += MX_TILE_THREADS) {
+      float s = 0.f;
+      for (int r = 0; r < TE; ++r) s = fmaf(dQ_s[r], hb_s[r * sm.ldH + k], s);
+      float* p = gp + L.wb2b + k;
+      *p = accum ? (*p + s) : s;
+    }
+    if (tid == 0) {
+      float s = 0.f;
+      for (int r = 0; r < TE; ++r) s += dQ_s[r];
+      float* p = gp + L.bb2b;
+      *p = accum ? (*p + s) : s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < TE * sm.ldH; idx += MX_TILE_THREADS) {
+      const int r = idx / sm.ldH, k = idx % sm.ldH;
+      float v = 0.f;
+      if (k < L.HY && hb_s[idx] > 0.f) v = dQ_s[r] * a.theta[L.wb2b + k];
+      hb_s[idx] = v;
+    }
+    __syncthreads();
+    // -- hyper_b2 first layer, hyper_b1
+    tile_wgrad(hb_s, sm.ldH, L.HY, s_s, sm.ldS, L.S, TE, gp + L.wb2a, gp + L.bb2a, accum);
+    tile_wgrad(hid_s, sm.ldM, L.ME, s_s, sm.ldS, L.S, TE, gp + L.wb1, gp + L.bb1, accum);
+    if (L.layers == 2) {
+      // -- hyper_w2
+      tile_wgrad(p2_s, sm.ldM, L.ME, h2_s, sm.ldH, L.HY, TE, gp + L.w2b, gp + L.b2b, accum);
+      __syncthreads();
+      tile_dgrad_relu<RM>(p2_s, sm.ldM, L.ME, a.theta + L.w2b, L.HY, h2_s, h2_s, sm.ldH, Wc, sm.ldw);
+      tile_wgrad(h2_s, sm.ldH, L.HY, s_s, sm.ldS, L.S, TE, gp + L.w2a, gp + L.b2a, accum);
+      // -- hyper_w1
+      tile_wgrad(p1_s, sm.ldP, NM, h1_s, sm.ldH, L.HY, TE, gp + L.w1b, gp + L.b1b, accum);
+      __syncthreads();
+      tile_dgrad_relu<RM>(p1_s, sm.ldP, NM, a.theta + L.w1b, L.HY, h1_s, h1_s, sm.ldH, Wc, sm.ldw);
+      tile_wgrad(h1_s, sm.ldH, L.HY, s_s, sm.ldS, L.S, TE, gp + L.w1a, gp + L.b1a, accum);
+    } else {
+      tile_wgrad(p2_s, sm.ldM, L.ME, s_s, sm.ldS, L.S, TE, gp + L.w2b, gp + L.b2b, accum);
+      tile_wgrad(p1_s, sm.ldP, NM, s_s, sm.ldS, L.S, TE, gp + L.w1b, gp + L.b1b, accum);
+    }
+    __syncthreads();
+  }
+}
+
 extern int g_mx_mixer_rm;
 int mx_launch_mixer(const MixerArgs& a, int* nparts_used, cudaStream_t s) {
   const int E = a.B * a.T;
@@ -400,4 +669,64 @@ int mx_launch_mixer(const MixerArgs& a, int* nparts_used, cudaStream_t s) {
   MX_MARK("k_mixer", s);
   *nparts_used = grid;
   return MX_CHECK_LAUNCH("mixer");
+}
+
+extern int g_mx_mixer_split_rm;
+int mx_mixer_split_supported(const MxMixLayout& L) { return L.ME <= 32 * MX_MIX_MAXK && L.N <= 32; }
+
+static int mix_split_rm(int E) {
+  if (g_mx_mixer_split_rm) return g_mx_mixer_split_rm;
+  return (E > 16 * mx_num_sms()) ? 2 : 1;
+}
+template <class K>
+static int mix_smem_attr(K kern, size_t smem, size_t* conf) {
+#if !MX_EMU
+  if (smem > 227 * 1024) { mx_set_error("mixer: %zu bytes of shared memory needed (state_dim / n_agents too large)", smem); return 1; }
+  if (smem > *conf) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); *conf = smem; }
+#else
+  (void)kern; (void)smem; (void)conf;
+#endif
+  return 0;
+}
+
+int mx_launch_mix_hyper_fwd(const MixerArgs& a, cudaStream_t s) {
+  const int E = a.B * a.T;
+  const int RM = mix_split_rm(E), TE = 16 * RM;
+  MixSmem sm = mix_smem_layout(a.L, TE);
+  const size_t smem = (size_t)sm.total * sizeof(float) + 16;
+  int grid = mx_ceil_div(E, TE);
+  if (grid > mx_num_sms()) grid = mx_num_sms();
+  static size_t c1 = 0, c2 = 0;
+  if (RM == 1) { if (mix_smem_attr(k_mix_hyper_fwd<1>, smem, &c1)) return 1; MX_LAUNCH_PDL(k_mix_hyper_fwd<1>, dim3(grid, 2), dim3(MX_TILE_THREADS), smem, s, a, sm); }
+  else { if (mix_smem_attr(k_mix_hyper_fwd<2>, smem, &c2)) return 1; MX_LAUNCH_PDL(k_mix_hyper_fwd<2>, dim3(grid, 2), dim3(MX_TILE_THREADS), smem, s, a, sm); }
+  MX_COUNT();
+  MX_MARK("k_mix_hyper_fwd", s);
+  return MX_CHECK_LAUNCH("mix_hyper_fwd");
+}
+
+int mx_launch_mix_core(const MixerArgs& a, int* scalar_parts_used, cudaStream_t s) {
+  const int E = a.B * a.T;
+  int grid = mx_ceil_div(E, 8);
+  if (grid > mx_num_sms()) grid = mx_num_sms();
+  MX_LAUNCH_PDL(k_mix_core, dim3(grid), dim3(256), 0, s, a);
+  MX_COUNT();
+  MX_MARK("k_mix_core", s);
+  *scalar_parts_used = grid;
+  return MX_CHECK_LAUNCH("mix_core");
+}
+
+int mx_launch_mix_hyper_bwd(const MixerArgs& a, int* nparts_used, cudaStream_t s) {
+  const int E = a.B * a.T;
+  const int RM = mix_split_rm(E), TE = 16 * RM;
+  MixSmem sm = mix_smem_layout(a.L, TE);
+  const size_t smem = (size_t)sm.total * sizeof(float) + 16;
+  int grid = mx_ceil_div(E, TE);
+  if (grid > mx_num_sms()) grid = mx_num_sms();
+  static size_t c1 = 0, c2 = 0;
+  if (RM == 1) { if (mix_smem_attr(k_mix_hyper_bwd<1>, smem, &c1)) return 1; MX_LAUNCH_PDL(k_mix_hyper_bwd<1>, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm); }
+  else { if (mix_smem_attr(k_mix_hyper_bwd<2>, smem, &c2)) return 1; MX_LAUNCH_PDL(k_mix_hyper_bwd<2>, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm); }
+  MX_COUNT();
+  MX_MARK("k_mix_hyper_bwd", s);
+  *nparts_used = grid;
+  return MX_CHECK_LAUNCH("mix_hyper_bwd");
 }

@@ -10,6 +10,8 @@ void mx_set_error(const char* fmt, ...);
 extern long long g_mx_launches;
 extern int g_mx_prof_on;
 void mx_prof_mark(const char* name, cudaStream_t s);
+extern int g_mx_mixer_split, g_mx_mixer_split_rm, g_mx_overlap;
+int mx_set_option_common(const char* name, int value);   // 0 when `name` was one of the build-independent options
 #define MX_COUNT() (++g_mx_launches)
 #define MX_MARK(name, s) do { if (g_mx_prof_on) mx_prof_mark((name), (s)); } while (0)
 
@@ -92,6 +94,10 @@ struct MxQmixWs {           // offsets in floats into the workspace
   int64_t spart;            // [npart][8] per-CTA scalar partials (denominator, loss numerator, sum Q_tot)
   int64_t adam_t;           // double[4]: step count, beta1^t, beta2^t
   int64_t tcimg[2];         // pre-split TF32 weight images of the agent front layers (live, target)
+  // split mixer pipeline: per-element hypernet outputs (live: kept for backward; target: forward only) and core's gradients
+  int64_t hyp_h1, hyp_h2, hyp_hb;               // live [E][gH]
+  int64_t hyp_p1[2], hyp_b1[2], hyp_p2[2], hyp_b2[2];
+  int64_t d_q, d_hp, d_p2, d_p1;
   int64_t total;
 };
 
@@ -106,4 +112,13 @@ struct mx_qmix {
   float* ws;
   int64_t ws_bytes;
   MxQmixWs W;
+  int split_ok;            // the split mixer pipeline supports this configuration
+#if !MX_EMU
+  // forked branch for the state-only kernels (weight-image prep, mixer hypernets): one non-blocking stream + fork/join events;
+  // inside a stream capture the same record/wait calls turn into parallel graph branches
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_prep = nullptr, ev_batch = nullptr, ev_hyper = nullptr, ev_core = nullptr, ev_hbwd = nullptr;
+  int prep_pending = 0;    // mx_qmix_prefork() already launched the weight-image prep for the coming step
+#endif
 };
+int mx_qmix_prefork(mx_qmix* q, void* stream);   // optional: start the parameter-only work of the next step before its batch is sampled

@@ -137,6 +137,13 @@ static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W
   W->spart = tk((int64_t)npart * 8);
   W->adam_t = tk(8);
   W->tcimg[0] = tk((int64_t)mx_tc_image_floats(c->obs_dim)); W->tcimg[1] = tk((int64_t)mx_tc_image_floats(c->obs_dim));
+  {
+    const int64_t gH = mx_round_up(c->hyper_hidden, 4), gM = mx_round_up(c->mixer_hidden, 4), gP = mx_round_up(c->n_agents * c->mixer_hidden, 4);
+    const int64_t En = c->vdn ? 0 : E;
+    W->hyp_h1 = tk(En * gH); W->hyp_h2 = tk(En * gH); W->hyp_hb = tk(En * gH);
+    for (int k = 0; k < 2; ++k) { W->hyp_p1[k] = tk(En * gP); W->hyp_b1[k] = tk(En * gM); W->hyp_p2[k] = tk(En * gM); W->hyp_b2[k] = tk(En); }
+    W->d_q = tk(En); W->d_hp = tk(En * gM); W->d_p2 = tk(En * gM); W->d_p1 = tk(En * gP);
+  }
   W->total = o;
   return o * 4;
 }
@@ -165,10 +172,24 @@ extern "C" int mx_qmix_create(const mx_qmix_cfg* c, float* theta, float* theta_t
   q->theta = theta; q->theta_tgt = theta_tgt; q->adam_m = adam_m; q->adam_v = adam_v;
   q->ws = (float*)workspace;
   q->ws_bytes = workspace_bytes;
+  q->split_ok = !c->vdn && mx_mixer_split_supported(q->mix);
+#if !MX_EMU
+  if (cudaStreamCreateWithFlags(&q->side, cudaStreamNonBlocking) != cudaSuccess) { mx_set_error("mx_qmix_create: cudaStreamCreate failed"); delete q; return 1; }
+  cudaEvent_t* evs[6] = {&q->ev_fork, &q->ev_prep, &q->ev_batch, &q->ev_hyper, &q->ev_core, &q->ev_hbwd};
+  for (cudaEvent_t* e : evs) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+#endif
   *out = q;
   return 0;
 }
-extern "C" void mx_qmix_destroy(mx_qmix* q) { delete q; }
+extern "C" void mx_qmix_destroy(mx_qmix* q) {
+  if (!q) return;
+#if !MX_EMU
+  cudaEvent_t evs[6] = {q->ev_fork, q->ev_prep, q->ev_batch, q->ev_hyper, q->ev_core, q->ev_hbwd};
+  for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+  if (q->side) cudaStreamDestroy(q->side);
+#endif
+  delete q;
+}
 
 extern "C" int mx_qmix_ws_lookup(const mx_qmix* q, const char* name, int64_t* byte_offset, int64_t* n_elems) {
   const mx_qmix_cfg& c = q->cfg;
@@ -210,7 +231,7 @@ static int check_batch(const mx_qmix* q, const mx_batch* b) {
   return 0;
 }
 
-static OptimArgs optim_args(mx_qmix* q, int B, const int parts[3]) {
+static OptimArgs optim_args(mx_qmix* q, int B, const int parts[4]) {   // parts: front_bwd, qhead_bwd, mixer gradient partials, scalar partials
   const mx_qmix_cfg& c = q->cfg;
   OptimArgs o;
   memset(&o, 0, sizeof(o));
@@ -221,7 +242,7 @@ static OptimArgs optim_args(mx_qmix* q, int B, const int parts[3]) {
   o.seg_begin[0] = 0; o.seg_end[0] = q->agent.lno_g; o.seg_parts[0] = parts[0];
   o.seg_begin[1] = q->agent.lno_g; o.seg_end[1] = q->agent.size; o.seg_parts[1] = parts[1];
   o.seg_begin[2] = q->agent.size; o.seg_end[2] = (int)q->P; o.seg_parts[2] = parts[2];
-  o.spart = ws + q->W.spart; o.spart_n = parts[2];
+  o.spart = ws + q->W.spart; o.spart_n = parts[3];
   o.info = ws + q->W.info;
   o.adam_t = reinterpret_cast<double*>(ws + q->W.adam_t);
   o.err = ws + q->W.err; o.B = B; o.T = c.episode_len;
@@ -232,6 +253,42 @@ static OptimArgs optim_args(mx_qmix* q, int B, const int parts[3]) {
   return o;
 }
 
+// ---- forked branch helpers ------------------------------------------------------------------------------------------
+// `side` runs work that does not depend on the agent nets; events order it against the caller's stream.  While the caller's
+// stream is being captured the same calls fork / join the capture, i.e. the graph gets two parallel branches.
+#if !MX_EMU
+static inline bool use_overlap(const mx_qmix* q) { return g_mx_overlap && !g_mx_prof_on && q->side; }
+static inline void fork_to_side(mx_qmix* q, cudaEvent_t ev, cudaStream_t s) { cudaEventRecord(ev, s); cudaStreamWaitEvent(q->side, ev, 0); }
+static inline void join_from_side(mx_qmix* q, cudaEvent_t ev, cudaStream_t s) { cudaEventRecord(ev, q->side); cudaStreamWaitEvent(s, ev, 0); }
+#endif
+
+static int launch_prep(mx_qmix* q, cudaStream_t s) {
+#if !MX_EMU
+  const float* const th2[2] = {q->theta, q->theta_tgt};
+  float* const img2[2] = {q->ws + q->W.tcimg[0], q->ws + q->W.tcimg[1]};
+  return mx_launch_tc_prep_weights(th2, q->agent, img2, 2, s);
+#else
+  (void)q; (void)s;
+  return 0;
+#endif
+}
+
+// Parameter-only work of the coming step (TF32 hi/lo weight images of the front layers), started on the side branch so that it
+// overlaps the index draw and the gather.  Optional: mx_qmix_backward_only does it itself when this was not called.
+int mx_qmix_prefork(mx_qmix* q, void* stream) {
+#if !MX_EMU
+  if (!use_overlap(q) || !(g_mx_front_tc && q->cfg.obs_dim <= 64) || q->prep_pending) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  fork_to_side(q, q->ev_fork, s);
+  if (launch_prep(q, q->side)) return 1;
+  cudaEventRecord(q->ev_prep, q->side);
+  q->prep_pending = 1;
+#else
+  (void)q; (void)stream;
+#endif
+  return 0;
+}
+
 extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream) {
   if (check_batch(q, b)) return 1;
   const mx_qmix_cfg& c = q->cfg;
@@ -240,6 +297,28 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   const MxQmixWs& W = q->W;
   const int B = b->B, T = c.episode_len, N = c.n_agents;
   const int M = B * (T + 1) * N;
+  const bool split = g_mx_mixer_split && q->split_ok;
+#if !MX_EMU
+  const bool overlap = use_overlap(q);
+  cudaStream_t side = overlap ? q->side : s;
+#else
+  const bool overlap = false;
+  cudaStream_t side = s;
+#endif
+
+  MixerArgs mx;
+  memset(&mx, 0, sizeof(mx));
+  mx.theta = q->theta; mx.theta_tgt = q->theta_tgt; mx.L = q->mix; mx.vdn = c.vdn;
+  mx.share = b->share; mx.share_ld = b->share_ld;
+  mx.q_taken = ws + W.q_taken; mx.q_next = ws + W.q_next;
+  mx.rewards = b->rewards; mx.dones_env = b->dones_env; mx.weights = c.use_per ? b->weights : nullptr;
+  mx.B = B; mx.T = T; mx.N = N; mx.gamma = c.gamma; mx.huber_delta = c.huber_delta; mx.use_huber = c.use_huber;
+  mx.qtot = ws + W.qtot; mx.qtot_next = ws + W.qtot_next; mx.err = ws + W.err; mx.dq_taken = ws + W.dq_taken;
+  mx.gpart = ws + W.gpart; mx.P = q->P; mx.spart = ws + W.spart;
+  mx.hyp_h1 = ws + W.hyp_h1; mx.hyp_h2 = ws + W.hyp_h2; mx.hyp_hb = ws + W.hyp_hb;
+  for (int k = 0; k < 2; ++k) { mx.hyp_p1[k] = ws + W.hyp_p1[k]; mx.hyp_b1[k] = ws + W.hyp_b1[k]; mx.hyp_p2[k] = ws + W.hyp_p2[k]; mx.hyp_b2[k] = ws + W.hyp_b2[k]; }
+  mx.d_q = ws + W.d_q; mx.d_hp = ws + W.d_hp; mx.d_p2 = ws + W.d_p2; mx.d_p1 = ws + W.d_p1;
+  mx.gH = mx_round_up(c.hyper_hidden, 4); mx.gM = mx_round_up(c.mixer_hidden, 4); mx.gP = mx_round_up(c.n_agents * c.mixer_hidden, 4);
 
   FrontFwdArgs ff;
   memset(&ff, 0, sizeof(ff));
@@ -249,12 +328,16 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   ff.u1 = ws + W.u1; ff.u2 = ws + W.u2; ff.st0 = ws + W.st0; ff.st1 = ws + W.st1; ff.st2 = ws + W.st2;
 #if !MX_EMU
   if (g_mx_front_tc && c.obs_dim <= 64) {       // weights changed in the last Adam / Polyak: rebuild the TF32 hi/lo images (18k elements per net)
-    const float* const th2[2] = {q->theta, q->theta_tgt};
-    float* const img2[2] = {ws + W.tcimg[0], ws + W.tcimg[1]};
-    if (mx_launch_tc_prep_weights(th2, q->agent, img2, 2, s)) return 1;
-    ff.tc_img[0] = img2[0]; ff.tc_img[1] = img2[1];
+    if (q->prep_pending) {                      // mx_qmix_prefork() launched it on the side branch before the batch was sampled
+      cudaStreamWaitEvent(s, q->ev_prep, 0);
+      q->prep_pending = 0;
+    } else if (launch_prep(q, s)) return 1;
+    ff.tc_img[0] = ws + W.tcimg[0]; ff.tc_img[1] = ws + W.tcimg[1];
   }
+  // the mixer's hypernetworks depend on the sampled states and the parameters only: forked branch beside the agent nets
+  if (split && overlap) fork_to_side(q, q->ev_batch, s);
 #endif
+  if (split && overlap) { if (mx_launch_mix_hyper_fwd(mx, side)) return 1; }
   if (mx_launch_front_fwd(ff, 2, s)) return 1;
 
   GruFwdArgs gf;
@@ -276,17 +359,21 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   qh.qall0 = q->debug ? ws + W.qall[0] : nullptr; qh.qall1 = q->debug ? ws + W.qall[1] : nullptr;
   if (mx_launch_qhead(qh, s)) return 1;
 
-  int parts[3] = {0, 0, 0};
-  MixerArgs mx;
-  memset(&mx, 0, sizeof(mx));
-  mx.theta = q->theta; mx.theta_tgt = q->theta_tgt; mx.L = q->mix; mx.vdn = c.vdn;
-  mx.share = b->share; mx.share_ld = b->share_ld;
-  mx.q_taken = qh.q_taken; mx.q_next = qh.q_next;
-  mx.rewards = b->rewards; mx.dones_env = b->dones_env; mx.weights = c.use_per ? b->weights : nullptr;
-  mx.B = B; mx.T = T; mx.N = N; mx.gamma = c.gamma; mx.huber_delta = c.huber_delta; mx.use_huber = c.use_huber;
-  mx.qtot = ws + W.qtot; mx.qtot_next = ws + W.qtot_next; mx.err = ws + W.err; mx.dq_taken = ws + W.dq_taken;
-  mx.gpart = ws + W.gpart; mx.P = q->P; mx.spart = ws + W.spart;
-  if (mx_launch_mixer(mx, &parts[2], s)) return 1;
+  int parts[4] = {0, 0, 0, 0};
+  if (split) {
+    if (!overlap) { if (mx_launch_mix_hyper_fwd(mx, s)) return 1; }
+#if !MX_EMU
+    else join_from_side(q, q->ev_hyper, s);
+#endif
+    if (mx_launch_mix_core(mx, &parts[3], s)) return 1;
+#if !MX_EMU
+    if (overlap) fork_to_side(q, q->ev_core, s);
+#endif
+    if (mx_launch_mix_hyper_bwd(mx, &parts[2], side)) return 1;      // beside k_qhead_bwd / k_gru_bwd / k_front_bwd when forked
+  } else {
+    if (mx_launch_mixer(mx, &parts[2], s)) return 1;
+    parts[3] = parts[2];
+  }
 
   QHeadBwdArgs hb;
   memset(&hb, 0, sizeof(hb));
@@ -308,12 +395,15 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   fb.dgi = gb.dgi; fb.gates = gf.gates; fb.hall = gf.hall[0]; fb.gpart = mx.gpart; fb.P = q->P;
   if (mx_launch_front_bwd(fb, &parts[0], s)) return 1;
 
+#if !MX_EMU
+  if (split && overlap) join_from_side(q, q->ev_hbwd, s);
+#endif
   OptimArgs o = optim_args(q, B, parts);
   return mx_launch_grad_reduce(o, s);
 }
 
 extern "C" int mx_qmix_apply_ex(mx_qmix* q, uint32_t flags, void* stream) {
-  const int parts[3] = {0, 0, 0};
+  const int parts[4] = {0, 0, 0, 0};
   OptimArgs o = optim_args(q, q->cfg.max_batch, parts);
   o.fuse_polyak = (flags & MX_STEP_FUSE_SOFT_UPDATE) ? 1 : 0;
   return mx_launch_adam(o, (cudaStream_t)stream);
@@ -341,6 +431,7 @@ extern "C" int mx_qmix_hard_update(mx_qmix* q, void* stream) {
 // whole-step CUDA graph
 // =====================================================================================================
 static int run_sequence(mx_replay* r, mx_qmix* q, int B, double beta, uint32_t flags, void* stream) {
+  if ((flags & 3u) && mx_qmix_prefork(q, stream)) return 1;      // weight-image prep overlaps the draw + gather
   if (flags & 1u) { if (mx_replay_sample_uniform(r, B, stream)) return 1; }
   else if (flags & 2u) { if (mx_replay_sample_per(r, B, beta, stream)) return 1; }
   mx_batch b;

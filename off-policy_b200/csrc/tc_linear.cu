@@ -431,6 +431,7 @@ int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
 }
 
 extern "C" int mx_set_option(const char* name, int32_t value) {
+  if (mx_set_option_common(name, value) == 0) return 0;
   if (!strcmp(name, "front_tc")) { g_mx_front_tc = value; return 0; }
   if (!strcmp(name, "tc_swap_ls")) { g_mx_tc_swap = value; return 0; }
   if (!strcmp(name, "mixer_rm")) { g_mx_mixer_rm = value; return 0; }
@@ -509,7 +510,7 @@ extern "C" int mx_tc_linear_probe(const float* X, const float* W, float* Y, int3
 int g_mx_front_tc = 0;
 int g_mx_mixer_rm = 0;
 int g_mx_front_bwd_rm = 0;
-extern "C" int mx_set_option(const char*, int32_t) { return 0; }
+extern "C" int mx_set_option(const char* name, int32_t value) { mx_set_option_common(name, value); return 0; }
 extern "C" int mx_tc_linear_probe(const float*, const float*, float*, int32_t, int32_t, int32_t, int32_t, int32_t, void*) {
   mx_set_error("tcgen05 kernels cannot be emulated");
   return 1;

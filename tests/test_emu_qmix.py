@@ -18,3 +18,23 @@ def test_front_bwd_tile_heights_vs_oracle(emu_engine, n_agents, B, T):
     L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T)
     batch = synth_batch(cfg, B, T, seed=5, avail_p=0.8, var_len=True) + (None, None)
     qc.compare_step(L, pol, tr, batch, cfg, steps=2)
+
+
+@pytest.mark.parametrize("name", ["qmix_small", "qmix_small_per", "qmix_small_hyper1"])
+def test_fused_mixer_kernel_matches_reference_golden(emu_engine, name):
+    """`mixer_split=0` selects the single fused k_mixer instead of the default hyper_fwd / core / hyper_bwd pipeline: both must
+    reproduce the reference."""
+    lib = emu_engine.lib()
+    lib.mx_set_option(b"mixer_split", 0)
+    try:
+        c0 = lib.mx_launch_count()
+        qc.check_step_against(None, name)
+        fused = lib.mx_launch_count() - c0
+    finally:
+        lib.mx_set_option(b"mixer_split", 1)
+    c0 = lib.mx_launch_count()
+    qc.check_step_against(None, name)
+    split = lib.mx_launch_count() - c0
+    g = qc.load_golden(name)
+    steps = int(g["meta.steps"]) if "meta.steps" in g else None
+    assert split > fused and (split - fused) % 2 == 0, (split, fused, steps)      # two extra launches per learner step
