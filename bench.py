@@ -433,6 +433,18 @@ def run_engine(args):
     if tgraph is not None:
         launches = kernels_per_step * args.steps
 
+    if args.quick:          # tuning sweeps: the device-resident number only (not a bench line)
+        if rank == 0:
+            print(json.dumps(dict(quick=True, workload=args.workload, value=world * 1000.0 / ms_step, ms_per_step=ms_step, opts=args.opt,
+                                  kernels_per_step=kernels_per_step)))
+            sys.stdout.flush()
+        if graph is not None:
+            graph.close()
+        if world > 1:
+            torch.distributed.barrier()
+            os._exit(0)
+        return
+
     # ---------------- e2e: host inputs through the drop-in API ----------------
     buf.rng = "numpy"
     fresh = [synth_episodes(cfg, T, 1, rs) for _ in range(8)]
@@ -559,6 +571,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="qmix_3m", choices=sorted(WORKLOADS) + sorted(MADDPG_WORKLOADS))
     ap.add_argument("--buffer", type=int, default=5000, help="replay episodes (scripts/train_smac_qmix.sh default 5000)")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning sweeps; not the bench contract line)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=int (mx_set_option), e.g. --opt pdl=0 --opt front_tc=0")
     a = ap.parse_args()
     if a.impl != "reference" and a.opt:

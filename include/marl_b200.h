@@ -257,6 +257,30 @@ int mx_maddpg_grad_views(mx_maddpg* h, int64_t* actor_off_bytes, int64_t* critic
 int mx_maddpg_soft_update(mx_maddpg* h, void* stream);   /* rMADDPGPolicy.py:162-165 */
 int mx_maddpg_hard_update(mx_maddpg* h, void* stream);   /* rMADDPGPolicy.py:167-170 */
 
+/* ------------------------------------------------------------------------------------------------
+ * Rollout-time policy step (one env step of the runners' collect_rollout loops, runner/rnn/smac_runner.py:73-98,
+ * runner/rnn/mpe_runner.py): ONE launch for the whole RNNBase + Linear-head forward of `rows` = n_envs * n_agents rows.
+ * Replaces the single-step branch of QMixPolicy.get_q_values / get_actions (qmix/algorithm/QMixPolicy.py:42-67, 95-174, greedy
+ * arg-max with the -1e10 availability mask of utils/util.py:297-302) and the actor forward of R_MADDPGPolicy.get_actions
+ * (r_maddpg/algorithm/rMADDPGPolicy.py:77-103).  `theta` is a flat vector in the agent-net layout (mx_qmix_param_layout's
+ * "agent." block / mx_maddpg_param_layout which = 0), i.e. the live or the target vector of a learner.  Exploration noise is
+ * applied by the caller (the reference draws it from the process-global NumPy / torch CPU generators).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mx_policy_step_args {
+  const float* theta;      /* device: flat parameters of the network                                   */
+  int32_t in_dim, out_dim; /* obs_dim, act_dim (hidden size is 64)                                     */
+  int32_t rows;            /* n_envs * n_agents                                                        */
+  int32_t x_ld, avail_ld;  /* row strides of x and avail in floats                                     */
+  const float* x;          /* device [rows][x_ld]      observations of this step                       */
+  const float* h_in;       /* device [rows][64]        recurrent state, or NULL for zeros (init_hidden) */
+  float* h_out;            /* device [rows][64]        new recurrent state (may alias h_in)            */
+  float* out;              /* device [rows][out_dim]   Q values / action logits / continuous actions   */
+  const float* avail;      /* device [rows][avail_ld]  available-action mask or NULL                   */
+  int32_t* greedy;         /* device [rows] arg-max action under the mask, or NULL                     */
+  float* greedy_q;         /* device [rows] its value (the reference's greedy_Qs), or NULL             */
+} mx_policy_step_args;
+int mx_policy_step(const mx_policy_step_args* args, void* stream);
+
 /* Debug / parity: look up a named fp32 (or int32) region of the workspace written by the last step.
  * Returns byte offset into the workspace and element count; names are listed in DESIGN.md. */
 int mx_qmix_ws_lookup(const mx_qmix* q, const char* name, int64_t* byte_offset, int64_t* n_elems);

@@ -62,6 +62,11 @@ class Batch(C.Structure):
                 [(n, C.c_void_p) for n in ("obs", "share", "acts", "act_idx", "avail", "rewards", "dones", "dones_env", "weights", "idx")])
 
 
+class PolicyStepArgs(C.Structure):
+    _fields_ = ([("theta", C.c_void_p)] + [(n, C.c_int32) for n in ("in_dim", "out_dim", "rows", "x_ld", "avail_ld")] +
+                [(n, C.c_void_p) for n in ("x", "h_in", "h_out", "out", "avail", "greedy", "greedy_q")])
+
+
 class MxError(RuntimeError):
     pass
 
@@ -122,6 +127,7 @@ def _declare(lib):
         "mx_maddpg_grad_views": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "mx_maddpg_soft_update": (C.c_int, [vp, vp]),
         "mx_maddpg_hard_update": (C.c_int, [vp, vp]),
+        "mx_policy_step": (C.c_int, [C.POINTER(PolicyStepArgs), vp]),
         "mx_set_option": (C.c_int, [C.c_char_p, i32]),
         "mx_tc_linear_probe": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "mx_maddpg_graph_capture": (C.c_int, [vp, vp, i32, dbl, u32, vp, vp, i32, vp, C.POINTER(vp)]),

@@ -3,15 +3,15 @@
 The agent Q-network's parameters are views into the flat device vector the CUDA learner trains in place
 (`q_network.state_dict()` keeps the reference key names).  Update-time methods
 (get_q_values over sequences, q_values_from_actions, greedy actions_from_q) are executed inside the fused
-learner kernels (csrc/agent_fwd.cu); what remains here is the rollout-time surface the runner calls once per
-env step -- single-step forward + epsilon-greedy (QMixPolicy.py:95-191) -- done with a handful of torch ops
-on the same parameter views (SURVEY.md section 8(f).1 lists a dedicated rollout kernel as the next widening).
+learner kernels (csrc/agent_fwd.cu).  The rollout-time surface the runner calls once per env step -- single-step
+forward + masked arg-max (QMixPolicy.py:95-191) -- is ONE launch of k_policy_step (csrc/rollout.cu, SURVEY.md
+section 8(f).1) with the recurrent state resident on the device; the epsilon-greedy draws stay on the host because
+the reference takes them from the process-global NumPy / torch generators.
 """
 import ctypes as C
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from offpolicy._b200 import capi
 from offpolicy._b200.flat import FlatModule, reference_style_init
@@ -72,70 +72,80 @@ class QMixPolicy(object):
         init = reference_style_init(entries, dict(hidden=self.hidden_size, obs_dim=self.obs_dim, act_dim=self.act_dim),
                                     gain=self.args.gain, use_orthogonal=self.args.use_orthogonal)
         self.q_network.load_state_dict({k[len("agent."):]: v for k, v in init.items()})
+        self._roll = None
         if train:
             self.exploration = LinearDecay(self.args.epsilon_start, self.args.epsilon_finish, self.args.epsilon_anneal_time)
 
-    # -- rollout-time forward (one env step, batch = agents) -------------------------------------------
-    def _forward_step(self, obs, h):
-        p = self.q_network.views
-        H = self.hidden_size
-        x = F.layer_norm(obs, (self.obs_dim,), p["rnn.feature_norm.weight"], p["rnn.feature_norm.bias"])
-        x = F.layer_norm(F.relu(F.linear(x, p["rnn.mlp.fc1.0.weight"], p["rnn.mlp.fc1.0.bias"])), (H,),
-                         p["rnn.mlp.fc1.2.weight"], p["rnn.mlp.fc1.2.bias"])
-        x = F.layer_norm(F.relu(F.linear(x, p["rnn.mlp.fc2.0.0.weight"], p["rnn.mlp.fc2.0.0.bias"])), (H,),
-                         p["rnn.mlp.fc2.0.2.weight"], p["rnn.mlp.fc2.0.2.bias"])
-        gi = F.linear(x, p["rnn.rnn.rnn.weight_ih_l0"], p["rnn.rnn.rnn.bias_ih_l0"])
-        gh = F.linear(h, p["rnn.rnn.rnn.weight_hh_l0"], p["rnn.rnn.rnn.bias_hh_l0"])
-        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
-        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
-        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
-        h2 = (1 - z) * n + z * h
-        y = F.layer_norm(h2, (H,), p["rnn.rnn.norm.weight"], p["rnn.rnn.norm.bias"])
-        return F.linear(y, p["q.action_out.weight"], p["q.action_out.bias"]), h2
+    # -- rollout-time surface: one env step per call = ONE launch of k_policy_step (csrc/rollout.cu) ---------------------
+    def _theta(self):
+        """flat live parameter vector whose head is the agent block (re-bound to the trainer's vector once a QMix exists)"""
+        return self.q_network.flat
+
+    def _stepper(self):
+        if self._roll is None:
+            from offpolicy._b200.rollout import PolicyStepper
+            self._roll = PolicyStepper(self.obs_dim, self.act_dim)
+        return self._roll
+
+    def _step(self, obs, rnn_states, available_actions=None):
+        return self._stepper().step(self._theta(), obs, rnn_states, available_actions)
 
     def get_q_values(self, obs_batch, prev_action_batch, rnn_states, action_batch=None):
-        obs = torch.as_tensor(np.asarray(obs_batch), dtype=torch.float32).to(self.dev)
-        h = torch.as_tensor(rnn_states, dtype=torch.float32).to(self.dev)
-        with torch.no_grad():
-            if obs.dim() == 3:          # (seq, batch, dim): step through the sequence
-                qs = []
-                for t in range(obs.shape[0]):
-                    q, h = self._forward_step(obs[t], h)
-                    qs.append(q)
-                q = torch.stack(qs)
-            else:
-                q, h = self._forward_step(obs, h)
+        """QMixPolicy.py:42-67.  (batch, dim) -> one step; (seq, batch, dim) -> the steps in turn, state resident on the device."""
+        obs = np.asarray(obs_batch, dtype=np.float32)
+        if obs.ndim == 3:
+            qs, h = [], rnn_states
+            for t in range(obs.shape[0]):
+                q, h, _, _ = self._step(obs[t], h)
+                qs.append(q)
+            q = torch.from_numpy(np.stack(qs))
+        else:
+            q, h, _, _ = self._step(obs, rnn_states)
+            q = torch.from_numpy(q)
         if action_batch is not None:
             q = self.q_values_from_actions(q, action_batch)
-        return q, h
+        return q, torch.from_numpy(h)
 
     def q_values_from_actions(self, q_batch, action_batch):
         a = torch.as_tensor(np.asarray(action_batch)).to(q_batch.device)
         return torch.gather(q_batch, q_batch.dim() - 1, a.max(dim=-1)[1].unsqueeze(-1))
 
     def get_actions(self, obs, prev_actions, rnn_states, available_actions=None, t_env=None, explore=False):
-        q, h = self.get_q_values(obs, prev_actions, rnn_states)
-        onehot_actions, greedy_Qs = self.actions_from_q(q, available_actions=available_actions, explore=explore, t_env=t_env)
-        return onehot_actions, h, greedy_Qs
+        """QMixPolicy.py:95-100: network step + masked arg-max on the device, epsilon-greedy mixing on the host with the
+        reference's own generator calls (np.random.rand then Categorical.sample, QMixPolicy.py:157-165)."""
+        obs = np.asarray(obs, dtype=np.float32)
+        if obs.ndim != 2:
+            q, h = self.get_q_values(obs, prev_actions, rnn_states)
+            onehot_actions, greedy_Qs = self.actions_from_q(q, available_actions=available_actions, explore=explore, t_env=t_env)
+            return onehot_actions, h, greedy_Qs
+        _, h, greedy, greedy_q = self._step(obs, rnn_states, available_actions)
+        greedy_Qs = torch.from_numpy(greedy_q)
+        if explore:
+            actions = self._eps_greedy(greedy, available_actions, t_env)
+            return onehot(actions, self.act_dim), torch.from_numpy(h), greedy_Qs
+        return onehot(greedy, self.act_dim), torch.from_numpy(h), greedy_Qs.unsqueeze(-1)
+
+    def _eps_greedy(self, greedy, available_actions, t_env):
+        batch = greedy.shape[0]
+        eps = self.exploration.eval(t_env)
+        rand = np.random.rand(batch)                                                  # QMixPolicy.py:160
+        logits = torch.ones(batch, self.act_dim)
+        if available_actions is not None:
+            logits[torch.as_tensor(np.asarray(available_actions)) == 0] = -1e10       # avail_choose, util.py:297-302
+        random_actions = torch.distributions.Categorical(logits=logits).sample().numpy()
+        take = (rand < eps).astype(int)
+        return (1 - take) * greedy + take * random_actions
 
     def actions_from_q(self, q_values, available_actions=None, explore=False, t_env=None):
-        q = q_values.clone()
+        """QMixPolicy.py:102-174 for Q values that are already materialised (API compatibility; get_actions does not come here)."""
+        q = torch.as_tensor(q_values).clone()
         if available_actions is not None:
             av = torch.as_tensor(np.asarray(available_actions)).to(q.device)
-            q[av == 0] = -1e10                                                         # util.py:297-302
+            q[av == 0] = -1e10
         greedy_Qs, greedy = q.max(dim=-1)
         if explore:
             assert q.dim() == 2, "Can only explore on non-sequences"
-            batch = q.shape[0]
-            eps = self.exploration.eval(t_env)
-            rand = np.random.rand(batch)                                              # QMixPolicy.py:160
-            logits = torch.ones(batch, self.act_dim)
-            if available_actions is not None:
-                logits[torch.as_tensor(np.asarray(available_actions)) == 0] = -1e10
-            random_actions = torch.distributions.Categorical(logits=logits).sample().numpy()
-            take = (rand < eps).astype(int)
-            actions = (1 - take) * greedy.cpu().numpy() + take * random_actions
-            return onehot(actions, self.act_dim), greedy_Qs
+            return onehot(self._eps_greedy(greedy.cpu().numpy(), available_actions, t_env), self.act_dim), greedy_Qs
         return onehot(greedy.cpu().numpy(), self.act_dim), greedy_Qs.unsqueeze(-1)
 
     def get_random_actions(self, obs, available_actions=None):

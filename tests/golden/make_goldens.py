@@ -170,7 +170,7 @@ def gen_replay(name="replay_small"):
     print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
-if __name__ == "__main__" and "maddpg" not in sys.argv[1:]:
+if __name__ == "__main__" and "maddpg" not in sys.argv[1:] and "rollout" not in sys.argv[1:]:
     torch.set_num_threads(1)
     small = QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48)
     gen_qmix("qmix_small", small)
@@ -289,3 +289,46 @@ def main_maddpg():
 
 if __name__ == "__main__" and "maddpg" in sys.argv[1:]:
     main_maddpg()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rollout-time QMixPolicy surface (one env step per call): get_actions greedy / exploring, get_random_actions,
+# get_q_values on a short sequence (QMixPolicy.py:42-191)
+# ---------------------------------------------------------------------------------------------------------------
+def gen_qmix_rollout(name="qmix_rollout"):
+    cfg = QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48)
+    args, pol, tr = build_reference_qmix(cfg, (), 8)
+    out = {}
+    out.update(sd_np("init.agent.", pol.q_network))
+    rs = np.random.RandomState(91)
+    R, steps = cfg.n_agents, 4
+    obs = rs.randn(steps, R, cfg.obs_dim).astype(np.float32)
+    avail = (rs.rand(steps, R, cfg.act_dim) < 0.6).astype(np.float32)
+    avail[:, :, 0] = 1.0
+    out["in.obs"], out["in.avail"] = obs, avail
+    with torch.no_grad():
+        h = np.zeros((R, cfg.hidden), np.float32)
+        for t in range(steps):      # the runner's loop: the state returned by one call is handed to the next (smac_runner.py:73-98)
+            a, h2, gq = pol.get_actions(obs[t], None, h, avail[t])
+            out["greedy%d.actions" % t], out["greedy%d.h" % t], out["greedy%d.q" % t] = np.asarray(a, np.float32), h2.numpy().copy(), gq.numpy().copy()
+            h = h2.numpy()
+        q_seq, h_seq = pol.get_q_values(obs, None, torch.zeros(R, cfg.hidden))
+        out["seq.q"], out["seq.h"] = q_seq.numpy().copy(), h_seq.numpy().copy()
+        for tag, av in (("explore", avail[0]), ("explore_noavail", None)):
+            torch.manual_seed(5); np.random.seed(5)
+            a, h2, gq = pol.get_actions(obs[0], None, np.zeros((R, cfg.hidden), np.float32), av, t_env=20000, explore=True)
+            out[tag + ".actions"], out[tag + ".q"] = np.asarray(a, np.float32), gq.numpy().copy()
+        torch.manual_seed(6); np.random.seed(6)
+        out["random.actions"] = np.asarray(pol.get_random_actions(obs[0], avail[0]), np.float32)
+        torch.manual_seed(6); np.random.seed(6)
+        out["random_noavail.actions"] = np.asarray(pol.get_random_actions(obs[0]), np.float32)
+    out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.hidden, steps])
+    out["meta.eps"] = np.array([args.epsilon_start, args.epsilon_finish, args.epsilon_anneal_time], np.float64)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__" and "rollout" in sys.argv[1:]:
+    torch.set_num_threads(1)
+    gen_qmix_rollout()
