@@ -13,13 +13,17 @@ int g_mx_pdl_skip_next = 0;
 #endif
 
 // runtime options shared by the product and the emulated build (mx_set_option)
-int g_mx_mixer_split = 1;      // 1: hypernet-forward / core / hypernet-backward kernels (default); 0: the single fused k_mixer
+int g_mx_mixer_split = 1;      // 1: split mixer (hypernet-forward / core / hypernet-backward kernels) whenever the forked branch is
+                               //    in use; 2: always; 0: always the single fused k_mixer
 int g_mx_mixer_split_rm = 0;   // rows per thread of the split mixer's tiles (0 = automatic)
-int g_mx_overlap = 1;          // 1: state-only kernels (weight-image prep, mixer hypernets) run on a forked branch beside the agent-net kernels
+int g_mx_overlap = 1;          // state-only kernels (weight-image prep, mixer hypernets) on a forked branch beside the agent-net
+                               // kernels: 1 = when the step is latency-bound (rows <= g_mx_overlap_rows), 2 = always, 0 = never
+int g_mx_overlap_rows = 12288; // measured on B200 (profiles/r01l_overlap_sweep.log): 3m (5 856 rows) +16 %, 8m (61 952 rows) -8 %
 int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "mixer_split")) { g_mx_mixer_split = value; return 0; }
   if (!strcmp(name, "mixer_split_rm")) { g_mx_mixer_split_rm = value; return 0; }
   if (!strcmp(name, "overlap")) { g_mx_overlap = value; return 0; }
+  if (!strcmp(name, "overlap_rows")) { g_mx_overlap_rows = value; return 0; }
   return -1;
 }
 

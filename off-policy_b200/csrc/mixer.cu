@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_mix_hyper_fwd(MixerArgs a, 
 // One warp per (b,t) element, lanes over the mixer's hidden units: Q_tot' (target), Q_tot (live), TD target, masked loss,
 // dL/dQ_tot and the elementwise part of the live mixer's backward (q_mixer.py:82-93, qmix.py:159-187).
 #define MX_MIX_MAXK 2      // mixer_hidden <= 64
-__global__ void __launch_bounds__(256) k_mix_core(MixerArgs a) {
+__global__ void __launch_bounds__(512) k_mix_core(MixerArgs a) {
   const MxMixLayout L = a.L;
   const int E = a.B * a.T, N = L.N, ME = L.ME;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -479,6 +479,13 @@ __global__ void __launch_bounds__(256) k_mix_core(MixerArgs a) {
   for (int e = blockIdx.x * nw + warp; e < E; e += gridDim.x * nw) {
     float Qv[2];
     float hp[MX_MIX_MAXK], hvv[MX_MIX_MAXK], p2v[MX_MIX_MAXK];
+    // independent scalar loads first: their latency overlaps the two mixing passes
+    const int b = e / a.T, t = e % a.T;
+    const float rew = a.rewards[((size_t)b * a.T + t) * N];              // agent 0 (qmix.py:159)
+    const float de = a.dones_env[(size_t)b * a.T + t];
+    const float bad = t > 0 ? a.dones_env[(size_t)b * a.T + t - 1] : 0.f;     // qmix.py:161
+    const float w = a.weights ? a.weights[b] : 1.f;
+    const float b2v[2] = {a.hyp_b2[0][e], a.hyp_b2[1][e]};
 #pragma unroll
     for (int net = 1; net >= 0; --net) {
       const float* q = (net ? a.q_next : a.q_taken) + (size_t)e * N;
@@ -496,16 +503,11 @@ __global__ void __launch_bounds__(256) k_mix_core(MixerArgs a) {
           if (net == 0) { hp[j] = v; hvv[j] = hv; p2v[j] = p2; }
         }
       }
-      Qv[net] = mx_warp_sum(part) + a.hyp_b2[net][e];
+      Qv[net] = mx_warp_sum(part) + b2v[net];
     }
-    const int b = e / a.T, t = e % a.T;
-    const float rew = a.rewards[((size_t)b * a.T + t) * N];              // agent 0 (qmix.py:159)
-    const float de = a.dones_env[(size_t)b * a.T + t];
-    const float bad = t > 0 ? a.dones_env[(size_t)b * a.T + t - 1] : 0.f;     // qmix.py:161
     const float y = rew + (1.f - de) * a.gamma * Qv[1];
     const float keep = 1.f - bad;
     const float err = (Qv[0] - y) * keep;
-    const float w = a.weights ? a.weights[b] : 1.f;
     float le, dle;
     if (a.use_huber) {
       const float ae = fabsf(err);
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(256) k_mix_core(MixerArgs a) {
       if (lane == 0) a.dq_taken[(size_t)e * N + n] = acc;
     }
   }
-  __shared__ float red[3][8];
+  __shared__ float red[3][16];
   if (lane == 0) { red[0][warp] = den; red[1][warp] = lsum; red[2][warp] = qsum; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -706,9 +708,9 @@ int mx_launch_mix_hyper_fwd(const MixerArgs& a, cudaStream_t s) {
 
 int mx_launch_mix_core(const MixerArgs& a, int* scalar_parts_used, cudaStream_t s) {
   const int E = a.B * a.T;
-  int grid = mx_ceil_div(E, 8);
-  if (grid > mx_num_sms()) grid = mx_num_sms();
-  MX_LAUNCH_PDL(k_mix_core, dim3(grid), dim3(256), 0, s, a);
+  int grid = mx_ceil_div(E, 16);                  // one warp per element, 16 warps per CTA: 3m (1 920 elements) = 120 CTAs, one pass
+  if (grid > mx_num_sms()) grid = mx_num_sms();   // (spart holds one scalar partial per SM)
+  MX_LAUNCH_PDL(k_mix_core, dim3(grid), dim3(512), 0, s, a);
   MX_COUNT();
   MX_MARK("k_mix_core", s);
   *scalar_parts_used = grid;

@@ -10,7 +10,7 @@ void mx_set_error(const char* fmt, ...);
 extern long long g_mx_launches;
 extern int g_mx_prof_on;
 void mx_prof_mark(const char* name, cudaStream_t s);
-extern int g_mx_mixer_split, g_mx_mixer_split_rm, g_mx_overlap;
+extern int g_mx_mixer_split, g_mx_mixer_split_rm, g_mx_overlap, g_mx_overlap_rows;
 int mx_set_option_common(const char* name, int value);   // 0 when `name` was one of the build-independent options
 #define MX_COUNT() (++g_mx_launches)
 #define MX_MARK(name, s) do { if (g_mx_prof_on) mx_prof_mark((name), (s)); } while (0)
@@ -93,6 +93,7 @@ struct MxQmixWs {           // offsets in floats into the workspace
   int64_t prio;             // [max_batch]
   int64_t spart;            // [npart][8] per-CTA scalar partials (denominator, loss numerator, sum Q_tot)
   int64_t adam_t;           // double[4]: step count, beta1^t, beta2^t
+  int64_t normpart;         // [ceil(P/256)] per-block sums of squares of the reduced gradient numerators
   int64_t tcimg[2];         // pre-split TF32 weight images of the agent front layers (live, target)
   // split mixer pipeline: per-element hypernet outputs (live: kept for backward; target: forward only) and core's gradients
   int64_t hyp_h1, hyp_h2, hyp_hb;               // live [E][gH]
@@ -121,4 +122,4 @@ struct mx_qmix {
   int prep_pending = 0;    // mx_qmix_prefork() already launched the weight-image prep for the coming step
 #endif
 };
-int mx_qmix_prefork(mx_qmix* q, void* stream);   // optional: start the parameter-only work of the next step before its batch is sampled
+int mx_qmix_prefork(mx_qmix* q, int B, void* stream);   // optional: start the parameter-only work of the next step before its batch is sampled

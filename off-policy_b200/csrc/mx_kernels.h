@@ -142,9 +142,12 @@ struct OptimArgs {
   float* prio;             // [B] or null
   float lr, beta1, beta2, eps, max_grad_norm, tau;
   int world_size;
+  float* normpart;          // [mx_grad_reduce_blocks(P)] per-block sum of squares of the reduced numerators (k_grad_reduce -> k_adam),
+  int normpart_n;           //   or null when the gradient is all-reduced in between (world_size > 1)
   int fuse_polyak;          // Adam epilogue also applies the soft target update (graph mode)
   float weight_decay;       // torch.optim.Adam(weight_decay): g += wd * p after clipping
 };
+static inline int mx_grad_reduce_blocks(long long P) { return (int)((P + 255) / 256); }   // 256 parameters per block
 int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s);
 int mx_launch_adam(const OptimArgs& a, cudaStream_t s);
 int mx_launch_polyak(float* tgt, const float* src, long long n, float tau, cudaStream_t s);

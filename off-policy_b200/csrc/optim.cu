@@ -50,29 +50,59 @@ __global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
     }
     return;
   }
-  const long long i = (long long)blockIdx.x * blockDim.x + tid;
-  if (i >= a.P) return;
-  int parts = 0;
-  for (int s = 0; s < a.nseg; ++s)
-    if (i >= a.seg_begin[s] && i < a.seg_end[s]) parts = a.seg_parts[s];
-  // eight independent chains, unrolled twice: 16 partial loads in flight per thread (fixed order -> deterministic result)
-  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g5 = 0.f, g6 = 0.f, g7 = 0.f;
-  const float* gp = a.gpart + i;
-  int p = 0;
-#pragma unroll 2
-  for (; p + 8 <= parts; p += 8) {
-    g0 += gp[(size_t)p * a.P];
-    g1 += gp[(size_t)(p + 1) * a.P];
-    g2 += gp[(size_t)(p + 2) * a.P];
-    g3 += gp[(size_t)(p + 3) * a.P];
-    g4 += gp[(size_t)(p + 4) * a.P];
-    g5 += gp[(size_t)(p + 5) * a.P];
-    g6 += gp[(size_t)(p + 6) * a.P];
-    g7 += gp[(size_t)(p + 7) * a.P];
+  // 64 float4 columns (256 parameters) per block x 4 slices of the partial index: thread (c, sl) sums partials sl, sl+4, ... of
+  // its column with 16-byte loads (8 in flight), then the four slices are added in fixed order -> deterministic result.
+  __shared__ float4 sl_sum[4][64];
+  __shared__ float sq[2];
+  const int c = tid & 63, sl = tid >> 6;
+  const long long i = ((long long)blockIdx.x * 64 + c) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < a.P) {
+    int parts = 0;
+    for (int s = 0; s < a.nseg; ++s)
+      if (i >= a.seg_begin[s] && i < a.seg_end[s]) parts = a.seg_parts[s];     // segment bounds are multiples of 4 floats
+    const float* gp = a.gpart + i;
+    float4 b0 = acc, b1 = acc, b2 = acc, b3 = acc;
+    int p = sl;
+    for (; p + 28 < parts; p += 32) {
+      const float4 v0 = mx_ld4(gp + (size_t)p * a.P), v1 = mx_ld4(gp + (size_t)(p + 4) * a.P);
+      const float4 v2 = mx_ld4(gp + (size_t)(p + 8) * a.P), v3 = mx_ld4(gp + (size_t)(p + 12) * a.P);
+      const float4 v4 = mx_ld4(gp + (size_t)(p + 16) * a.P), v5 = mx_ld4(gp + (size_t)(p + 20) * a.P);
+      const float4 v6 = mx_ld4(gp + (size_t)(p + 24) * a.P), v7 = mx_ld4(gp + (size_t)(p + 28) * a.P);
+      b0.x += v0.x; b0.y += v0.y; b0.z += v0.z; b0.w += v0.w;
+      b1.x += v1.x; b1.y += v1.y; b1.z += v1.z; b1.w += v1.w;
+      b2.x += v2.x; b2.y += v2.y; b2.z += v2.z; b2.w += v2.w;
+      b3.x += v3.x; b3.y += v3.y; b3.z += v3.z; b3.w += v3.w;
+      b0.x += v4.x; b0.y += v4.y; b0.z += v4.z; b0.w += v4.w;
+      b1.x += v5.x; b1.y += v5.y; b1.z += v5.z; b1.w += v5.w;
+      b2.x += v6.x; b2.y += v6.y; b2.z += v6.z; b2.w += v6.w;
+      b3.x += v7.x; b3.y += v7.y; b3.z += v7.z; b3.w += v7.w;
+    }
+    for (; p < parts; p += 4) {
+      const float4 v = mx_ld4(gp + (size_t)p * a.P);
+      b0.x += v.x; b0.y += v.y; b0.z += v.z; b0.w += v.w;
+    }
+    acc.x = (b0.x + b1.x) + (b2.x + b3.x); acc.y = (b0.y + b1.y) + (b2.y + b3.y);
+    acc.z = (b0.z + b1.z) + (b2.z + b3.z); acc.w = (b0.w + b1.w) + (b2.w + b3.w);
   }
-  for (; p < parts; ++p) g0 += gp[(size_t)p * a.P];
-  g0 += g4; g1 += g5; g2 += g6; g3 += g7;
-  a.grad[i] = (g0 + g1) + (g2 + g3);
+  sl_sum[sl][c] = acc;
+  __syncthreads();
+  if (tid < 64) {
+    const float4 s0 = sl_sum[0][tid], s1 = sl_sum[1][tid], s2 = sl_sum[2][tid], s3 = sl_sum[3][tid];
+    float4 g;
+    g.x = (s0.x + s1.x) + (s2.x + s3.x); g.y = (s0.y + s1.y) + (s2.y + s3.y);
+    g.z = (s0.z + s1.z) + (s2.z + s3.z); g.w = (s0.w + s1.w) + (s2.w + s3.w);
+    const long long j = ((long long)blockIdx.x * 64 + tid) * 4;
+    float q = 0.f;
+    if (j < a.P) {
+      mx_st4(a.grad + j, g);
+      q = (g.x * g.x + g.y * g.y) + (g.z * g.z + g.w * g.w);
+    }
+    q = mx_warp_sum(q);                       // per-block sum of squares: lets k_adam skip re-reading the whole gradient
+    if ((tid & 31) == 0) sq[tid >> 5] = q;
+  }
+  __syncthreads();
+  if (tid == 0 && a.normpart) a.normpart[blockIdx.x] = sq[0] + sq[1];
 }
 
 __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
@@ -83,15 +113,22 @@ __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
   const float denom = a.grad[a.P + 0];
   const float invd = 1.0f / denom;
   // ||g||^2 over the full vector, identical summation order in every CTA (no grid-wide barrier needed)
-  float sf = 0.f;
-  const long long P4 = a.P / 4;
+  double ds;
+  if (a.normpart) {       // single GPU: per-block sums of squares of the numerators left by k_grad_reduce
+    double sp = 0.0;
+    for (int i = tid; i < a.normpart_n; i += blockDim.x) sp += (double)a.normpart[i];
+    ds = mx_warp_sum_d(sp) * ((double)invd * (double)invd);
+  } else {                // data parallel: the gradient was all-reduced after k_grad_reduce
+    float sf = 0.f;
+    const long long P4 = a.P / 4;
 #pragma unroll 4
-  for (long long i = tid; i < P4; i += blockDim.x) {
-    const float4 g = mx_ld4(a.grad + 4 * i);
-    const float gx = g.x * invd, gy = g.y * invd, gz = g.z * invd, gw = g.w * invd;
-    sf += (gx * gx + gy * gy) + (gz * gz + gw * gw);
+    for (long long i = tid; i < P4; i += blockDim.x) {
+      const float4 g = mx_ld4(a.grad + 4 * i);
+      const float gx = g.x * invd, gy = g.y * invd, gz = g.z * invd, gw = g.w * invd;
+      sf += (gx * gx + gy * gy) + (gz * gz + gw * gw);
+    }
+    ds = mx_warp_sum_d((double)sf);
   }
-  double ds = mx_warp_sum_d((double)sf);
   if ((tid & 31) == 0) red[tid >> 5] = ds;
   __syncthreads();
   if (tid < 32) {
@@ -143,7 +180,7 @@ __global__ void __launch_bounds__(256) k_polyak(float* __restrict__ tgt, const f
 }
 
 int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s) {
-  const int grid = (int)((a.P + 255) / 256) + 1;
+  const int grid = mx_grad_reduce_blocks(a.P) + 1;
   MX_LAUNCH_PDL(k_grad_reduce, dim3(grid), dim3(256), 0, s, a);
   MX_COUNT();
   MX_MARK("k_grad_reduce", s);

@@ -136,6 +136,7 @@ static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W
   W->prio = tk(B);
   W->spart = tk((int64_t)npart * 8);
   W->adam_t = tk(8);
+  W->normpart = tk(mx_grad_reduce_blocks(P));
   W->tcimg[0] = tk((int64_t)mx_tc_image_floats(c->obs_dim)); W->tcimg[1] = tk((int64_t)mx_tc_image_floats(c->obs_dim));
   {
     const int64_t gH = mx_round_up(c->hyper_hidden, 4), gM = mx_round_up(c->mixer_hidden, 4), gP = mx_round_up(c->n_agents * c->mixer_hidden, 4);
@@ -250,6 +251,7 @@ static OptimArgs optim_args(mx_qmix* q, int B, const int parts[4]) {   // parts:
   o.prio = c.use_per ? ws + q->W.prio : nullptr;
   o.lr = c.lr; o.beta1 = c.adam_beta1; o.beta2 = c.adam_beta2; o.eps = c.adam_eps; o.max_grad_norm = c.max_grad_norm; o.tau = c.tau;
   o.world_size = c.world_size;
+  if (c.world_size == 1) { o.normpart = ws + q->W.normpart; o.normpart_n = mx_grad_reduce_blocks(q->P); }   // else: all-reduced in between
   return o;
 }
 
@@ -257,7 +259,13 @@ static OptimArgs optim_args(mx_qmix* q, int B, const int parts[4]) {   // parts:
 // `side` runs work that does not depend on the agent nets; events order it against the caller's stream.  While the caller's
 // stream is being captured the same calls fork / join the capture, i.e. the graph gets two parallel branches.
 #if !MX_EMU
-static inline bool use_overlap(const mx_qmix* q) { return g_mx_overlap && !g_mx_prof_on && q->side; }
+static inline bool want_overlap(const mx_qmix* q, int B) {     // the policy decision
+  if (!g_mx_overlap || !q->side) return false;
+  const long long rows = (long long)B * (q->cfg.episode_len + 1) * q->cfg.n_agents;
+  return g_mx_overlap >= 2 || rows <= g_mx_overlap_rows;     // large batches are throughput-bound: a second branch only adds contention
+}
+// per-kernel profiling (mx_profile_begin) times the same kernels back to back on one stream
+static inline bool use_overlap(const mx_qmix* q, int B) { return want_overlap(q, B) && !g_mx_prof_on; }
 static inline void fork_to_side(mx_qmix* q, cudaEvent_t ev, cudaStream_t s) { cudaEventRecord(ev, s); cudaStreamWaitEvent(q->side, ev, 0); }
 static inline void join_from_side(mx_qmix* q, cudaEvent_t ev, cudaStream_t s) { cudaEventRecord(ev, q->side); cudaStreamWaitEvent(s, ev, 0); }
 #endif
@@ -275,16 +283,16 @@ static int launch_prep(mx_qmix* q, cudaStream_t s) {
 
 // Parameter-only work of the coming step (TF32 hi/lo weight images of the front layers), started on the side branch so that it
 // overlaps the index draw and the gather.  Optional: mx_qmix_backward_only does it itself when this was not called.
-int mx_qmix_prefork(mx_qmix* q, void* stream) {
+int mx_qmix_prefork(mx_qmix* q, int B, void* stream) {
 #if !MX_EMU
-  if (!use_overlap(q) || !(g_mx_front_tc && q->cfg.obs_dim <= 64) || q->prep_pending) return 0;
+  if (!use_overlap(q, B) || !(g_mx_front_tc && q->cfg.obs_dim <= 64) || q->prep_pending) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   fork_to_side(q, q->ev_fork, s);
   if (launch_prep(q, q->side)) return 1;
   cudaEventRecord(q->ev_prep, q->side);
   q->prep_pending = 1;
 #else
-  (void)q; (void)stream;
+  (void)q; (void)B; (void)stream;
 #endif
   return 0;
 }
@@ -297,14 +305,15 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   const MxQmixWs& W = q->W;
   const int B = b->B, T = c.episode_len, N = c.n_agents;
   const int M = B * (T + 1) * N;
-  const bool split = g_mx_mixer_split && q->split_ok;
 #if !MX_EMU
-  const bool overlap = use_overlap(q);
+  const bool overlap = use_overlap(q, B), wanted = want_overlap(q, B);
   cudaStream_t side = overlap ? q->side : s;
 #else
-  const bool overlap = false;
+  const bool overlap = false, wanted = true;
   cudaStream_t side = s;
 #endif
+  // the split mixer only pays off when its hypernet kernels run beside the agent nets (serial, the fused k_mixer moves less data)
+  const bool split = q->split_ok && (g_mx_mixer_split >= 2 || (g_mx_mixer_split == 1 && wanted));
 
   MixerArgs mx;
   memset(&mx, 0, sizeof(mx));
@@ -431,7 +440,7 @@ extern "C" int mx_qmix_hard_update(mx_qmix* q, void* stream) {
 // whole-step CUDA graph
 // =====================================================================================================
 static int run_sequence(mx_replay* r, mx_qmix* q, int B, double beta, uint32_t flags, void* stream) {
-  if ((flags & 3u) && mx_qmix_prefork(q, stream)) return 1;      // weight-image prep overlaps the draw + gather
+  if ((flags & 3u) && mx_qmix_prefork(q, B, stream)) return 1;      // weight-image prep overlaps the draw + gather
   if (flags & 1u) { if (mx_replay_sample_uniform(r, B, stream)) return 1; }
   else if (flags & 2u) { if (mx_replay_sample_per(r, B, beta, stream)) return 1; }
   mx_batch b;

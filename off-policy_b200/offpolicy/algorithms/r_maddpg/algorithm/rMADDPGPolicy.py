@@ -135,40 +135,33 @@ class R_MADDPGPolicy(object):
         self.critic_vecs[1].copy_(self.critic_vecs[0])
         self._trainer = None
 
-    # -- rollout-time single step ------------------------------------------------------------------------------
-    def _actor_step(self, views, obs, h):
-        p, H = views, self.hidden_size
-        x = F.layer_norm(obs, (self.obs_dim,), p["rnn.feature_norm.weight"], p["rnn.feature_norm.bias"])
-        x = F.layer_norm(F.relu(F.linear(x, p["rnn.mlp.fc1.0.weight"], p["rnn.mlp.fc1.0.bias"])), (H,), p["rnn.mlp.fc1.2.weight"], p["rnn.mlp.fc1.2.bias"])
-        x = F.layer_norm(F.relu(F.linear(x, p["rnn.mlp.fc2.0.0.weight"], p["rnn.mlp.fc2.0.0.bias"])), (H,), p["rnn.mlp.fc2.0.2.weight"], p["rnn.mlp.fc2.0.2.bias"])
-        gi = F.linear(x, p["rnn.rnn.rnn.weight_ih_l0"], p["rnn.rnn.rnn.bias_ih_l0"])
-        gh = F.linear(h, p["rnn.rnn.rnn.weight_hh_l0"], p["rnn.rnn.rnn.bias_hh_l0"])
-        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
-        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
-        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
-        h2 = (1 - z) * n + z * h
-        y = F.layer_norm(h2, (H,), p["rnn.rnn.norm.weight"], p["rnn.rnn.norm.bias"])
-        return F.linear(y, p["act.action_out.weight"], p["act.action_out.bias"]), h2
+    # -- rollout-time single step: ONE launch of k_policy_step (csrc/rollout.cu) per env step -----------------------------
+    def _stepper(self):
+        if getattr(self, "_roll", None) is None:
+            from offpolicy._b200.rollout import PolicyStepper
+            self._roll = PolicyStepper(self.obs_dim, self.act_dim)
+        return self._roll
 
     def get_actions(self, obs, prev_actions, rnn_states, available_actions=None, t_env=None, explore=False, use_target=False, use_gumbel=False):
-        views = (self.target_actor if use_target else self.actor).views
-        o = torch.as_tensor(np.asarray(obs), dtype=torch.float32).to(self.dev)
-        h = torch.as_tensor(rnn_states, dtype=torch.float32).to(self.dev)
-        with torch.no_grad():
-            if o.dim() == 3:
-                outs = []
-                for t in range(o.shape[0]):
-                    a, h = self._actor_step(views, o[t], h)
-                    outs.append(a)
-                out = torch.stack(outs)
-            else:
-                out, h = self._actor_step(views, o, h)
+        theta = self.actor_vecs[1] if use_target else self.actor_vecs[0]
+        o = np.asarray(obs, dtype=np.float32)
+        st = self._stepper()
+        if o.ndim == 3:
+            outs, h = [], rnn_states
+            for t in range(o.shape[0]):
+                a, h, _, _ = st.step(theta, o[t], h, want_greedy=False)
+                outs.append(a)
+            out = torch.from_numpy(np.stack(outs))
+        else:
+            a, h, _, _ = st.step(theta, o, rnn_states, want_greedy=False)
+            out = torch.from_numpy(a)
+        h = torch.from_numpy(h)
         eps = None
         if self.discrete:                                                                   # rMADDPGPolicy.py:104-120
             if use_gumbel or (use_target and self.target_noise is not None):
                 out = gumbel_softmax_hard(out, available_actions)
             elif explore:
-                assert o.dim() == 2, "Cannot do exploration on a sequence!"
+                assert o.ndim == 2, "Cannot do exploration on a sequence!"
                 onehot_actions = gumbel_softmax_hard(out, available_actions)
                 batch_size = o.shape[0]
                 eps = self.exploration.eval(t_env)
@@ -183,7 +176,7 @@ class R_MADDPGPolicy(object):
                 out = onehot_from_logits(out, available_actions)
             return out, h, eps
         if explore:
-            assert o.dim() == 2, "Cannot do exploration on a sequence!"
+            assert o.ndim == 2, "Cannot do exploration on a sequence!"
             out = torch.empty(out.shape).normal_(mean=0, std=self.args.act_noise_std).to(out.device) + out     # util.py:217-218
         elif use_target and self.target_noise is not None:
             out = torch.empty(out.shape).normal_(mean=0, std=self.target_noise).to(out.device) + out
