@@ -97,6 +97,10 @@ int mx_replay_insert_async(mx_replay* r, const mx_episodes* ep, int32_t n_ep, in
  * mx_replay_insert_packed_layout (which returns the packed size in bytes for n_ep episodes). */
 int64_t mx_replay_insert_packed_layout(const mx_replay* r, int32_t n_ep, int64_t offsets[7], int64_t counts[7]);
 int mx_replay_insert_packed_async(mx_replay* r, const void* packed, int64_t nbytes, int32_t n_ep, int32_t* first_slot_out, void* stream);
+/* Checkpoint / resume (the reference saves network weights only, runner/rnn/base_runner.py:286-337):
+ * the blob IS the replay's whole state (episodes, PER trees, MT19937 key, ring position), so a snapshot is a copy of the blob;
+ * after copying one back, mx_replay_restore re-reads the host mirror of the ring position from it (synchronises). */
+int mx_replay_restore(mx_replay* r, void* stream);
 int32_t mx_replay_len(const mx_replay* r);      /* filled_i  (rec_buffer.py:36-37)  */
 int32_t mx_replay_cursor(const mx_replay* r);   /* current_i                         */
 

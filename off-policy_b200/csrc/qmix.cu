@@ -204,7 +204,7 @@ extern "C" int mx_qmix_ws_lookup(const mx_qmix* q, const char* name, int64_t* by
       {"st0", W.st0, M * 2}, {"st1", W.st1, M * 2}, {"st2", W.st2, M * 2}, {"sto", W.sto, M * 2}, {"gates", W.gates, M * MX_G},
       {"hn", W.hn, M * MX_H}, {"greedy", W.greedy, M}, {"q_taken", W.q_taken, E * N}, {"q_next", W.q_next, E * N}, {"qtot", W.qtot, E},
       {"qtot_next", W.qtot_next, E}, {"err", W.err, E}, {"dq_taken", W.dq_taken, E * N}, {"dh_out", W.dh_out, M * MX_H},
-      {"dgi", W.dgi, M * MX_G}, {"grad", W.grad, q->P + 8}, {"info", W.info, 8}, {"prio", W.prio, B}, {"gpart", W.gpart, (int64_t)q->npart * q->P},
+      {"dgi", W.dgi, M * MX_G}, {"grad", W.grad, q->P + 8}, {"info", W.info, 8}, {"adam_t", W.adam_t, 8}, {"prio", W.prio, B}, {"gpart", W.gpart, (int64_t)q->npart * q->P},
   };
   for (const Ent& e : tab)
     if (!strcmp(e.n, name)) { *byte_offset = e.off * 4; *n_elems = e.cnt; return 0; }

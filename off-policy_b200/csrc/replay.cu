@@ -467,6 +467,21 @@ extern "C" int mx_replay_create(const mx_replay_cfg* cfg, void* blob, void* stre
   return 0;
 }
 extern "C" void mx_replay_destroy(mx_replay* r) { delete r; }
+// Checkpoint restore: after the caller has copied a saved blob back into device memory, re-read the host mirror of the ring
+// position from the blob's device scalars (synchronises the stream).
+extern "C" int mx_replay_restore(mx_replay* r, void* stream) {
+  if (!r) { mx_set_error("mx_replay_restore: null handle"); return 1; }
+  MxReplayState st;
+  cudaMemcpyAsync(&st, r->blob + r->L.off_state, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  if (st.filled < 0 || st.filled > r->cfg.capacity || st.cursor < 0 || st.cursor > r->cfg.capacity) {
+    mx_set_error("mx_replay_restore: blob does not hold a replay of this shape (filled %d, cursor %d, capacity %d)", st.filled, st.cursor, r->cfg.capacity);
+    return 1;
+  }
+  r->filled = st.filled;
+  r->cursor = st.cursor;
+  return 0;
+}
 extern "C" int32_t mx_replay_len(const mx_replay* r) { return r->filled; }
 extern "C" int32_t mx_replay_cursor(const mx_replay* r) { return r->cursor; }
 

@@ -89,6 +89,7 @@ def _declare(lib):
         "mx_replay_insert_async": (C.c_int, [vp, C.POINTER(Episodes), i32, C.POINTER(i32), vp]),
         "mx_replay_insert_packed_layout": (i64, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
         "mx_replay_insert_packed_async": (C.c_int, [vp, vp, i64, i32, C.POINTER(i32), vp]),
+        "mx_replay_restore": (C.c_int, [vp, vp]),
         "mx_replay_len": (i32, [vp]),
         "mx_replay_cursor": (i32, [vp]),
         "mx_replay_seed": (C.c_int, [vp, u32, vp]),

@@ -216,6 +216,21 @@ class QMix(object):
             capi.lib().mx_graph_destroy(g)
         self._graphs = {}
 
+    # -- checkpoint / resume ------------------------------------------------------------------------
+    def state_dict(self):
+        """The whole learner: live + target parameters, Adam moments and step count.  (`policies[p].q_network.state_dict()` /
+        `mixer.state_dict()` remain the reference's per-network checkpoints, base_runner.py:286-337.)"""
+        return {"theta": self.theta.cpu().clone(), "theta_tgt": self.theta_tgt.cpu().clone(), "adam_m": self.adam_m.cpu().clone(),
+                "adam_v": self.adam_v.cpu().clone(), "adam_t": self.ws_view("adam_t", torch.float64).cpu().clone(),
+                "layout": [(n, int(o), int(r), int(c)) for n, o, r, c in self.entries]}
+
+    def load_state_dict(self, sd):
+        if [tuple(e) for e in sd["layout"]] != [(n, int(o), int(r), int(c)) for n, o, r, c in self.entries]:
+            raise ValueError("learner checkpoint was written for a different network configuration")
+        for name in ("theta", "theta_tgt", "adam_m", "adam_v"):
+            getattr(self, name).copy_(torch.as_tensor(sd[name]).to(self.dev))
+        self.ws_view("adam_t", torch.float64).copy_(torch.as_tensor(sd["adam_t"]).to(self.dev))
+
     def hard_target_updates(self):
         print("hard update targets")
         capi.check(capi.lib().mx_qmix_hard_update(self.handle, capi.stream_ptr()))

@@ -330,6 +330,31 @@ class RecPolicyBuffer(object):
         capi.check(capi.lib().mx_replay_get_rng_state(self.handle, key, C.byref(pos), capi.stream_ptr()))
         np.random.set_state(("MT19937", np.array(list(key), dtype=np.uint32), int(pos.value), 0, 0.0))
 
+    # -- checkpoint / resume (the reference checkpoints network weights only) -------------
+    def state_dict(self):
+        """Everything the replay is: the device blob holds the episodes, the PER trees, the device MT19937 key and the ring
+        position.  Only the persistent part is saved (the insert staging area and the sampled-batch region are scratch)."""
+        if self.dev.type == "cuda":
+            torch.cuda.current_stream(self.dev).synchronize()
+        n = int(self.L.off_stage)
+        return {"blob": self.blob[:n].cpu().clone(), "shape": self._shape_key()}
+
+    def _shape_key(self):
+        c = self.cfg
+        return [int(getattr(c, f)) for f in ("capacity", "episode_len", "n_agents", "obs_dim", "share_dim", "act_dim", "use_avail", "use_per",
+                                             "reward_norm")]
+
+    def load_state_dict(self, sd):
+        if list(sd["shape"]) != self._shape_key():
+            raise ValueError("replay checkpoint has shape %s, this buffer %s" % (list(sd["shape"]), self._shape_key()))
+        blob = torch.as_tensor(sd["blob"])
+        n = int(self.L.off_stage)
+        if blob.numel() != n:
+            raise ValueError("replay checkpoint holds %d bytes, expected %d" % (blob.numel(), n))
+        self.blob[:n].copy_(blob.to(self.dev))
+        capi.check(capi.lib().mx_replay_restore(self.handle, capi.stream_ptr()))
+        self.sample_serial += 1          # any batch sampled before the restore is stale
+
     # -- PER --------------------------------------------------------------------------------------------
     def tree_values(self):
         n = 2 * int(self.L.tree_cap)
@@ -392,6 +417,14 @@ class RecReplayBuffer(object):
         self.rng = "device"
         for b in self.policy_buffers.values():
             b.seed_device_rng(seed)
+
+    def state_dict(self):
+        return {"rng": self.rng, "policy_buffers": {p: b.state_dict() for p, b in self.policy_buffers.items()}}
+
+    def load_state_dict(self, sd):
+        self.rng = sd["rng"]
+        for p, b in self.policy_buffers.items():
+            b.load_state_dict(sd["policy_buffers"][p])
 
     def adopt_numpy_rng(self):
         self.rng = "device"
