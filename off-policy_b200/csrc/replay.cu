@@ -358,36 +358,53 @@ __global__ void __launch_bounds__(256) k_draw(DrawArgs a) {
 // =====================================================================================================
 // reward normalisation statistics (rec_buffer.py:209-220): nan-masked mean / population std over every
 // filled reward; a step is masked when the env was already done at the previous step.
+//
+// The reference rescans the whole buffer on every sample() (7 ms at 5 000 episodes).  Here the
+// masked sum / sum of squares / count are running fp64 totals in the blob, updated at insert time: the episodes an insert
+// evicts are subtracted (read from the SoA before the scatter overwrites them), the new ones added (read from the insert
+// staging area).  One CTA, fixed summation order -> deterministic; sample() only reads the two resulting scalars.
 // =====================================================================================================
-__global__ void k_reward_stats(const float* rew, const float* dones_env, long long ep_rew, long long ep_de, int T, int N,
-                               const MxReplayState* st, double* rstats) {
-  const int filled = st->filled;
-  const long long total = (long long)filled * T * N;
+struct RewStatArgs {
+  const float *rew_soa, *de_soa;     // [E][ep_rew], [E][ep_de]
+  long long ep_rew, ep_de;
+  const float *rew_stage, *de_stage; // raw time-major (T, n_ep, N), (T, n_ep)
+  int T, N, n_ep, first_slot, capacity, filled_before;
+  double* rstats;                    // [4]: sum, sum of squares, count
+  MxReplayState* state;
+};
+__global__ void __launch_bounds__(256) k_reward_stats_update(RewStatArgs a) {
+  __shared__ double red[3][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double s = 0, s2 = 0, c = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int n = (int)(i % N);
-    long long r = i / N;
-    int t = (int)(r % T);
-    long long e = r / T;
-    bool masked = t > 0 && dones_env[e * ep_de + t - 1] == 1.0f;
-    if (!masked) {
-      double v = (double)rew[e * ep_rew + t * N + n];
-      s += v; s2 += v * v; c += 1.0;
+  const int per = a.T * a.N;
+  for (int e = 0; e < a.n_ep; ++e) {
+    const int slot = (a.first_slot + e) % a.capacity;
+    const bool evict = slot < a.filled_before;
+    for (int i = tid; i < per; i += blockDim.x) {
+      const int t = i / a.N, n = i - t * a.N;
+      if (!(t > 0 && a.de_stage[(size_t)(t - 1) * a.n_ep + e] == 1.0f)) {
+        const double v = (double)a.rew_stage[((size_t)t * a.n_ep + e) * a.N + n];
+        s += v; s2 += v * v; c += 1.0;
+      }
+      if (evict && !(t > 0 && a.de_soa[(size_t)slot * a.ep_de + t - 1] == 1.0f)) {
+        const double v = (double)a.rew_soa[(size_t)slot * a.ep_rew + i];
+        s -= v; s2 -= v * v; c -= 1.0;
+      }
     }
   }
   s = mx_warp_sum_d(s); s2 = mx_warp_sum_d(s2); c = mx_warp_sum_d(c);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&rstats[0], s);
-    atomicAdd(&rstats[1], s2);
-    atomicAdd(&rstats[2], c);
-  }
-}
-__global__ void k_reward_stats_fin(double* rstats, MxReplayState* st) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double mean = rstats[0] / rstats[2];
-    double var = rstats[1] / rstats[2] - mean * mean;
-    st->reward_mean = (double)(float)mean;                      // the reference's statistics are np.float32 scalars
-    st->reward_std = (double)(float)sqrt(var > 0 ? var : 0.0);
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = s2; red[2][warp] = c; }
+  __syncthreads();
+  if (tid == 0) {
+    double t0 = a.rstats[0], t1 = a.rstats[1], t2 = a.rstats[2];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    a.rstats[0] = t0; a.rstats[1] = t1; a.rstats[2] = t2;
+    if (t2 > 0.0) {
+      const double mean = t0 / t2;
+      const double var = t1 / t2 - mean * mean;
+      a.state->reward_mean = (double)(float)mean;                      // the reference's statistics are np.float32 scalars
+      a.state->reward_std = (double)(float)sqrt(var > 0 ? var : 0.0);
+    }
   }
 }
 
@@ -535,6 +552,17 @@ static int insert_staged(mx_replay* r, int32_t n_ep, int32_t* first_slot_out, cu
   const int last = (first + n_ep - 1) % c.capacity;
   a.new_cursor = last + 1;                                     // rec_buffer.py:187 (not wrapped until the next insert)
   a.new_filled = r->filled + n_ep < c.capacity ? r->filled + n_ep : c.capacity;
+  if (c.reward_norm) {     // running reward statistics: must read the evicted episodes before the scatter overwrites them
+    RewStatArgs rs;
+    memset(&rs, 0, sizeof(rs));
+    rs.rew_soa = cat<float>(r, L.off_rew); rs.de_soa = cat<float>(r, L.off_dones_env); rs.ep_rew = L.ep_rew; rs.ep_de = L.ep_dones_env;
+    rs.rew_stage = reinterpret_cast<const float*>(stage + sf[3].offset); rs.de_stage = reinterpret_cast<const float*>(stage + sf[5].offset);
+    rs.T = T; rs.N = N; rs.n_ep = n_ep; rs.first_slot = first; rs.capacity = c.capacity; rs.filled_before = r->filled;
+    rs.rstats = at<double>(r, L.off_rstats); rs.state = a.state;
+    MX_LAUNCH(k_reward_stats_update, dim3(1), dim3(256), 0, s, rs);
+    MX_COUNT();
+    MX_MARK("k_reward_stats_update", s);
+  }
   int64_t work = a.f[0].count;
   int grid = (int)((work + 255) / 256);
   int maxg = mx_num_sms() * 8;
@@ -630,18 +658,6 @@ extern "C" int mx_replay_get_rng_state(mx_replay* r, uint32_t key[624], int32_t*
 static int launch_gather(mx_replay* r, const int64_t* idx_dev, int B, cudaStream_t s) {
   const mx_replay_cfg& c = r->cfg;
   const mx_replay_layout& L = r->L;
-  if (c.reward_norm) {
-    double* rs = at<double>(r, L.off_rstats);
-    cudaMemsetAsync(rs, 0, 32, s);
-    int g = mx_num_sms() * 2;
-    MX_LAUNCH(k_reward_stats, dim3(g), dim3(256), 0, s, cat<float>(r, L.off_rew), cat<float>(r, L.off_dones_env), (long long)L.ep_rew,
-              (long long)L.ep_dones_env, c.episode_len, c.n_agents, cat<MxReplayState>(r, L.off_state), rs);
-    MX_COUNT();
-    MX_MARK("k_reward_stats", s);
-    MX_LAUNCH(k_reward_stats_fin, dim3(1), dim3(32), 0, s, rs, at<MxReplayState>(r, L.off_state));
-    MX_COUNT();
-    MX_MARK("k_reward_stats_fin", s);
-  }
   GatherArgs g;
   memset(&g, 0, sizeof(g));
   int nf = 0;

@@ -333,10 +333,11 @@ class RecPolicyBuffer(object):
     # -- checkpoint / resume (the reference checkpoints network weights only) -------------
     def state_dict(self):
         """Everything the replay is: the device blob holds the episodes, the PER trees, the device MT19937 key and the ring
-        position.  Only the persistent part is saved (the insert staging area and the sampled-batch region are scratch)."""
+        position and the running reward statistics.  Only that persistent part is saved (the sampled-batch region and the insert
+        staging area behind it are scratch)."""
         if self.dev.type == "cuda":
             torch.cuda.current_stream(self.dev).synchronize()
-        n = int(self.L.off_stage)
+        n = int(self.L.off_b_obs)
         return {"blob": self.blob[:n].cpu().clone(), "shape": self._shape_key()}
 
     def _shape_key(self):
@@ -348,7 +349,7 @@ class RecPolicyBuffer(object):
         if list(sd["shape"]) != self._shape_key():
             raise ValueError("replay checkpoint has shape %s, this buffer %s" % (list(sd["shape"]), self._shape_key()))
         blob = torch.as_tensor(sd["blob"])
-        n = int(self.L.off_stage)
+        n = int(self.L.off_b_obs)
         if blob.numel() != n:
             raise ValueError("replay checkpoint holds %d bytes, expected %d" % (blob.numel(), n))
         self.blob[:n].copy_(blob.to(self.dev))

@@ -208,3 +208,31 @@ def check_uniform_vs_oracle_shapes(shape, seed=0):
                 assert got is None
             else:
                 assert np.array_equal(got, out[i]), name
+
+
+def check_reward_norm_running_stats(seed=3, E=7, B=5, inserts=40):
+    """Running reward statistics (updated at insert, evicted episodes subtracted) vs the oracle's full rescan
+    (rec_buffer.py:209-223) over many ring wraps: single-episode inserts like the RNN runners, a few multi-episode ones, episodes
+    that terminate early (masked steps), sampled rewards compared after every insert."""
+    N, O, A, S, T = 3, 4, 3, 5, 6
+    rs = np.random.RandomState(seed)
+    buf = make_buffers(N, O, A, S, T, E, norm=True, rng="numpy", max_batch=8)
+    ora = UniformReplay(E, T, N, O, S, A, reward_norm=True, rng=None)
+
+    def ep(n):
+        de = np.maximum.accumulate((rs.rand(T, n, 1) < 0.15).astype(np.float32), axis=0)
+        f = [rs.randn(T + 1, n, N, O), np.repeat(rs.randn(T + 1, n, 1, S), N, 2), np.eye(A)[rs.randint(0, A, (T, n, N))],
+             np.repeat(3.0 + 2.0 * rs.randn(T, n, 1, 1), N, 2), np.repeat(de[:, :, None], N, 2), de, np.ones((T + 1, n, N, A))]
+        return [x.astype(np.float32) for x in f]
+
+    for k in range(inserts):
+        n = 1 if k % 7 else int(rs.randint(2, 5))
+        e = ep(n)
+        buf.insert(n, *[d(x) for x in e])
+        ora.insert(n, *e)
+        st = np.random.get_state()
+        smp = buf.sample(B)
+        np.random.set_state(st)
+        out, inds = ora.sample(B)
+        got, want = smp[3]["policy_0"], out[3]
+        assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (k, np.abs(got - want).max())

@@ -23,3 +23,7 @@ def test_per_vs_oracle_random(emu_engine):
 @pytest.mark.parametrize("shape", [(3, 30, 9, 48, 5, 11, 4, True), (2, 5, 3, 7, 3, 6, 6, False), (1, 1, 2, 1, 1, 3, 2, True)])
 def test_uniform_vs_oracle(emu_engine, shape):
     rc.check_uniform_vs_oracle_shapes(shape)
+
+
+def test_reward_norm_running_statistics(emu_engine):
+    rc.check_reward_norm_running_stats()

@@ -33,6 +33,11 @@ def test_uniform_vs_oracle(gpu_engine, shape):
     rc.check_uniform_vs_oracle_shapes(shape)
 
 
+def test_reward_norm_running_statistics(gpu_engine):
+    rc.check_reward_norm_running_stats()
+    rc.check_reward_norm_running_stats(seed=8, E=50, B=16, inserts=130)
+
+
 def test_full_size_gather_properties(gpu_engine):
     """BASELINE config 4 shapes (8m: N=8, O=80, A=14, S=168, T=120, B=64): every sampled episode's bytes equal the
     stored bytes (round trip through insert -> sample), indices follow np.random.choice, duplicates allowed."""
