@@ -216,7 +216,7 @@ def check_reward_norm_running_stats(seed=3, E=7, B=5, inserts=40):
     that terminate early (masked steps), sampled rewards compared after every insert."""
     N, O, A, S, T = 3, 4, 3, 5, 6
     rs = np.random.RandomState(seed)
-    buf = make_buffers(N, O, A, S, T, E, norm=True, rng="numpy", max_batch=8)
+    buf = make_buffers(N, O, A, S, T, E, norm=True, rng="numpy", max_batch=max(B, 8))
     ora = UniformReplay(E, T, N, O, S, A, reward_norm=True, rng=None)
 
     def ep(n):
