@@ -425,27 +425,50 @@ struct GatherArgs {
   const MxReplayState* state;
 };
 
+// One float4 of the batch: flat index i -> (episode b, field, offset) -> source / destination addresses.
+MX_DEVINL void gather_addr(const GatherArgs& a, unsigned i, unsigned per_ep, const float*& src, float*& dst, bool& is_rew) {
+  const unsigned b = i / per_ep;
+  const unsigned r = i - b * per_ep;
+  int fi = 0;
+#pragma unroll
+  for (int k = 1; k < 8; ++k)
+    if (k < a.nf && r >= (unsigned)a.cum4[k]) fi = k;
+  const long long off = (long long)r - a.cum4[fi];
+  const long long e = a.idx[b];
+  src = a.f[fi].src + (e * a.f[fi].ep4 + off) * 4;
+  dst = a.f[fi].dst + ((long long)b * a.f[fi].ep4 + off) * 4;
+  is_rew = (fi == a.rew_field);
+}
+
+// HBM-bound copy: every thread keeps FOUR independent 16-byte loads in flight per iteration (8 resident CTAs x 256 threads x
+// 64 B = 128 KB in flight per SM), consecutive threads touch consecutive 16-byte words, 32-bit index arithmetic.
 __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
-  const long long per_ep = a.cum4[a.nf];
-  const long long total = per_ep * a.B;
+  const unsigned per_ep = (unsigned)a.cum4[a.nf];
+  const unsigned total = per_ep * (unsigned)a.B;            // < 2^31 float4 (checked by the launcher)
   float mean = 0.f, stdv = 1.f;
   MX_PDL_WAIT();
   if (a.rew_field >= 0) { mean = (float)a.state->reward_mean; stdv = (float)a.state->reward_std; }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int b = (int)(i / per_ep);
-    long long r = i - (long long)b * per_ep;
-    int fi = 0;
+  const unsigned step = gridDim.x * blockDim.x * 4u;
+  for (unsigned base = blockIdx.x * blockDim.x * 4u + threadIdx.x; base < total; base += step) {
+    const float* src[4];
+    float* dst[4];
+    bool rw[4], ok[4];
+    float4 v[4];
 #pragma unroll
-    for (int k = 1; k < 8; ++k)
-      if (k < a.nf && r >= a.cum4[k]) fi = k;
-    long long off = r - a.cum4[fi];
-    const GatherField f = a.f[fi];
-    long long e = a.idx[b];
-    float4 v = mx_ld4_stream(f.src + (e * f.ep4 + off) * 4);
-    if (fi == a.rew_field) {
-      v.x = (v.x - mean) / stdv; v.y = (v.y - mean) / stdv; v.z = (v.z - mean) / stdv; v.w = (v.w - mean) / stdv;
+    for (int j = 0; j < 4; ++j) {
+      const unsigned i = base + j * blockDim.x;
+      ok[j] = i < total;
+      if (ok[j]) gather_addr(a, i, per_ep, src[j], dst[j], rw[j]);
     }
-    mx_st4_stream(f.dst + ((long long)b * f.ep4 + off) * 4, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ok[j]) v[j] = mx_ld4_stream(src[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ok[j]) {
+        if (rw[j]) { v[j].x = (v[j].x - mean) / stdv; v[j].y = (v[j].y - mean) / stdv; v[j].z = (v[j].z - mean) / stdv; v[j].w = (v[j].w - mean) / stdv; }
+        mx_st4_stream(dst[j], v[j]);
+      }
   }
 }
 
@@ -686,8 +709,9 @@ static int launch_gather(mx_replay* r, const int64_t* idx_dev, int B, cudaStream
   g.idx = (const long long*)idx_dev;
   g.state = cat<MxReplayState>(r, L.off_state);
   long long total = cum * B;
-  // each thread moves >= 2 float4; grid is a multiple of the SM count (persistent-style, grid-stride)
-  long long want = (total + 511) / 512;
+  if (total >= (1ll << 31)) { mx_set_error("gather: batch of %lld 16-byte words exceeds the 32-bit index range", total); return 1; }
+  // each thread moves >= 4 float4 per iteration; grid is a multiple of the SM count (persistent-style, grid-stride)
+  long long want = (total + 1023) / 1024;
   int sms = mx_num_sms();
   int grid = (int)(want < 1 ? 1 : want);
   if (grid > sms * 8) grid = sms * 8;

@@ -1,0 +1,18 @@
+#!/bin/bash
+# GPU visit 7: new kernels (rollout, running reward stats, checkpoint, grad_reduce v2, mix_core) -- parity, sweep, bench, 2s3z decision
+set -u
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -n 15 gpurun_out/pytest_gpu.log
+{
+for o in "overlap=1" "overlap=0"; do
+  timeout 200 python bench.py --quick --steps 300 --warmup 20 --buffer 1024 --opt $o 2>gpurun_out/q.err | tail -n 1; tail -n 2 gpurun_out/q.err | grep -v "double Q"
+done
+for o in "overlap=2" "overlap=0"; do
+  timeout 200 python bench.py --quick --workload qmix_2s3z --steps 100 --warmup 10 --buffer 1024 --opt $o 2>gpurun_out/q.err | tail -n 1; tail -n 2 gpurun_out/q.err | grep -v "double Q"
+done
+} > gpurun_out/sweep.log 2>&1
+cat gpurun_out/sweep.log
+timeout 300 python bench.py --steps 300 --warmup 20 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cut -c1-300 gpurun_out/bench.json; tail -n 3 gpurun_out/bench.err
+timeout 120 python tools/rollout_bench.py > gpurun_out/rollout_bench.log 2>&1; tail -n 4 gpurun_out/rollout_bench.log
