@@ -261,6 +261,38 @@ __global__ void __launch_bounds__(256) k_draw(DrawArgs a) {
   __shared__ uint32_t s_half;   // PER: first word of a double already drawn
   __shared__ int s_havehalf;
   const int tid = threadIdx.x;
+  // ---- fast path (uniform draw, no regeneration needed within the next 256 words): the stream is consumed straight from
+  // global memory -- all 256 candidate words are tempered and rejection-tested in parallel, accepted ones are compacted in
+  // stream order with ballots, and only `rng_pos` is written back.  Falls through to the general path otherwise.
+  if (!a.per && blockDim.x == 256) {
+    __shared__ int s_wcnt[8], s_used;
+    const int pos0 = a.state->rng_pos, n0 = a.state->filled;
+    const uint32_t rng0 = (uint32_t)(n0 - 1);
+    if (rng0 != 0 && pos0 + 256 <= MT_N && a.B <= 256) {       // block-uniform condition
+      uint32_t mask0 = rng0;
+      mask0 |= mask0 >> 1; mask0 |= mask0 >> 2; mask0 |= mask0 >> 4; mask0 |= mask0 >> 8; mask0 |= mask0 >> 16;
+      const uint32_t v = mt_temper(a.rng[pos0 + tid]) & mask0;   // masked rejection (legacy randint)
+      const bool acc = v <= rng0;
+      const unsigned bal = __ballot_sync(0xffffffffu, acc);
+      const int lane = tid & 31, warp = tid >> 5;
+      if (lane == 0) s_wcnt[warp] = __popc(bal);
+      if (tid == 0) s_used = -1;
+      __syncthreads();
+      int before = 0, total_acc = 0;
+      for (int w = 0; w < 8; ++w) { if (w < warp) before += s_wcnt[w]; total_acc += s_wcnt[w]; }
+      if (total_acc >= a.B) {                                    // block-uniform
+        const int k = before + __popc(bal & ((1u << lane) - 1u));
+        if (acc && k < a.B) {
+          a.idx_out[k] = (long long)v;
+          if (k == a.B - 1) s_used = tid + 1;                    // words consumed = position of the B-th accepted word + 1
+        }
+        __syncthreads();
+        if (tid == 0) a.state->rng_pos = pos0 + s_used;
+        return;
+      }
+      __syncthreads();
+    }
+  }
   for (int i = tid; i < MT_N; i += blockDim.x) key[i] = a.rng[i];
   if (tid == 0) {
     s_pos = a.state->rng_pos;
