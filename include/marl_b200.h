@@ -206,6 +206,17 @@ const float* mx_qmix_info(mx_qmix* q);
 /* device fp32[B] new PER priorities (qmix.py:179-181) valid after a step with use_per */
 const float* mx_qmix_priorities(mx_qmix* q);
 
+/* Data-parallel exchange over NVLink peer memory instead of an NCCL call (no reference counterpart: the reference is single
+ * process).  Every rank allocates one SYMMETRIC block of mx_qmix_p2p_block_bytes() (zero-filled, mapped into
+ * every peer: torch.distributed._symmetric_memory / cudaIpc) and hands the world's block addresses, in rank order, to
+ * mx_qmix_set_peers together with a zeroed local uint32 counter.  From then on mx_qmix_step[_ex] with world_size > 1 is complete:
+ * backward -> publish (copy grad[P+4] into the own block, signal the peers) -> reduce (wait for every peer's signal, add all
+ * blocks in rank order: bit-identical on every rank) -> clip + Adam.  The two halves are exported for tests. */
+int64_t mx_qmix_p2p_block_bytes(const mx_qmix* q);
+int mx_qmix_set_peers(mx_qmix* q, int32_t rank, int32_t world, void* const* peer_blocks, uint32_t* counter_dev);
+int mx_qmix_p2p_publish(mx_qmix* q, void* stream);
+int mx_qmix_p2p_reduce(mx_qmix* q, void* stream);
+
 int mx_qmix_soft_update(mx_qmix* q, void* stream);   /* qmix.py:211-216 + util.py:123-134 (all registered params) */
 int mx_qmix_hard_update(mx_qmix* q, void* stream);   /* qmix.py:203-209 */
 

@@ -30,6 +30,11 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
   const int wtotal = gridDim.x * (blockDim.x >> 5);
   const int T1 = a.T + 1, N = a.N;
   float dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
+  // head-weight gradient of this warp's rows in registers (row k = action k; lane owns columns lane, lane + 32): no shared
+  // atomics, so the CTA's partial is summed in a fixed order (warp 0, 1, ... below) and the step is run-to-run deterministic
+  float dw0[32], dw1[32], dbk[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { dw0[k] = 0.f; dw1[k] = 0.f; dbk[k] = 0.f; }
   for (int m = wglobal; m < a.M; m += wtotal) {
     const int n = m % N;
     const int bt = m / N;
@@ -47,9 +52,9 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
     const float xh0 = (h[lane] - mean) * rstd, xh1 = (h[lane + 32] - mean) * rstd;
     const float y0 = xh0 * lg_s[lane] + lb_s[lane], y1 = xh1 * lg_s[lane + 32] + lb_s[lane + 32];
     const float dy0 = dqv * wq_s[act * MX_H + lane], dy1 = dqv * wq_s[act * MX_H + lane + 32];
-    atomicAdd(&dwq_s[act * MX_H + lane], dqv * y0);
-    atomicAdd(&dwq_s[act * MX_H + lane + 32], dqv * y1);
-    if (lane == 0) atomicAdd(&dbq_s[act], dqv);
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k == act) { dw0[k] += dqv * y0; dw1[k] += dqv * y1; dbk[k] += dqv; }
     dg0 += dy0 * xh0; dg1 += dy1 * xh1; db0 += dy0; db1 += dy1;
     // LayerNorm backward
     const float dx0 = dy0 * lg_s[lane], dx1 = dy1 * lg_s[lane + 32];
@@ -58,9 +63,19 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
     out[lane] = rstd * (dx0 - c1 - xh0 * c2);
     out[lane + 32] = rstd * (dx1 - c1 - xh1 * c2);
   }
-  atomicAdd(&dg_s[lane], dg0); atomicAdd(&dg_s[lane + 32], dg1);
-  atomicAdd(&db_s[lane], db0); atomicAdd(&db_s[lane + 32], db1);
-  __syncthreads();
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {       // warps add their partials one after the other
+    if ((tid >> 5) == w) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < A) {
+          dwq_s[k * MX_H + lane] += dw0[k]; dwq_s[k * MX_H + lane + 32] += dw1[k];
+          if (lane == 0) dbq_s[k] += dbk[k];
+        }
+      dg_s[lane] += dg0; dg_s[lane + 32] += dg1;
+      db_s[lane] += db0; db_s[lane + 32] += db1;
+    }
+    __syncthreads();
+  }
   float* gp = a.gpart + (size_t)blockIdx.x * a.P;
   for (int i = tid; i < A * MX_H; i += blockDim.x) gp[a.wq + i] = dwq_s[i];
   for (int i = tid; i < A; i += blockDim.x) gp[a.bq + i] = dbq_s[i];
@@ -415,6 +430,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
 #pragma unroll
           for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
         mx_mm_nn<RM>(da_s, sm.ld64, Wc, sm.ld64, v);
+        float cg[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int jx = 0; jx < 4; ++jx) {
           const int c = kb * 64 + 4 * tx + jx;
@@ -425,7 +441,19 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
               sg = fmaf(v[i][jx], xh0_s[(ty * RM + i) * sm.ldi + c], sg); sb += v[i][jx];
               if (a.dX) dx0_s[(ty * RM + i) * sm.ldi + c] = v[i][jx];
             }
-            if (wg && a.feature_norm) { atomicAdd(&col0g[c], sg); atomicAdd(&col0b[c], sb); }
+            cg[jx] = sg; cb[jx] = sb;
+          }
+        }
+        if (wg && a.feature_norm) {       // the 16 row groups add their column partials one after the other (deterministic)
+          for (int g = 0; g < MX_TILE_THREADS / 16; ++g) {
+            if (ty == g) {
+#pragma unroll
+              for (int jx = 0; jx < 4; ++jx) {
+                const int c = kb * 64 + 4 * tx + jx;
+                if (c < I) { col0g[c] += cg[jx]; col0b[c] += cb[jx]; }
+              }
+            }
+            __syncthreads();
           }
         }
       }
@@ -452,13 +480,17 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     }
   }
   // ---- LayerNorm gain / bias gradients: per-thread partials -> per-CTA column sums -> this CTA's gradient partial ----
+  for (int g = 0; g < MX_TILE_THREADS / 16; ++g) {       // row groups in turn: fixed summation order, no shared atomics
+    if (ty == g) {
 #pragma unroll
-  for (int jx = 0; jx < 4; ++jx) {
-    const int c = 4 * tx + jx;
-    atomicAdd(&col1g[c], dg1[jx]); atomicAdd(&col1b[c], db1[jx]);
-    atomicAdd(&col2g[c], dg2[jx]); atomicAdd(&col2b[c], db2[jx]);
+      for (int jx = 0; jx < 4; ++jx) {
+        const int c = 4 * tx + jx;
+        col1g[c] += dg1[jx]; col1b[c] += db1[jx];
+        col2g[c] += dg2[jx]; col2b[c] += db2[jx];
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (wg) {
     for (int c = tid; c < MX_H; c += MX_TILE_THREADS) {
       gp[L.ln2_g + c] = col2g[c]; gp[L.ln2_b + c] = col2b[c];

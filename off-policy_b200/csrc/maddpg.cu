@@ -127,22 +127,23 @@ __global__ void __launch_bounds__(256) k_head_bwd(HeadBwdArgs a) {
   __syncthreads();
   const int wglobal = blockIdx.x * (blockDim.x >> 5) + (tid >> 5), wtotal = gridDim.x * (blockDim.x >> 5);
   float dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
+  float dw0[8], dw1[8], dbo[8];      // this warp's head-weight gradient in registers: summed over warps in a fixed order below
+#pragma unroll
+  for (int o = 0; o < 8; ++o) { dw0[o] = 0.f; dw1[o] = 0.f; dbo[o] = 0.f; }
   for (int m = wglobal; m < a.M; m += wtotal) {
     const float* h = a.h + (size_t)m * MX_H;
     const float mean = a.sto[2 * (size_t)m], rstd = a.sto[2 * (size_t)m + 1];
     const float xh0 = (h[lane] - mean) * rstd, xh1 = (h[lane + 32] - mean) * rstd;
     const float y0 = xh0 * lg_s[lane] + lb_s[lane], y1 = xh1 * lg_s[lane + 32] + lb_s[lane + 32];
     float dy0 = 0.f, dy1 = 0.f;
-    for (int o = 0; o < a.OD; ++o) {
-      const float d = a.dout[(size_t)m * a.OD + o];
-      dy0 = fmaf(d, w_s[o * MX_H + lane], dy0);
-      dy1 = fmaf(d, w_s[o * MX_H + lane + 32], dy1);
-      if (a.gpart && d != 0.f) {
-        atomicAdd(&dw_s[o * MX_H + lane], d * y0);
-        atomicAdd(&dw_s[o * MX_H + lane + 32], d * y1);
-        if (lane == 0) atomicAdd(&db_s[o], d);
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o < a.OD) {
+        const float d = a.dout[(size_t)m * a.OD + o];
+        dy0 = fmaf(d, w_s[o * MX_H + lane], dy0);
+        dy1 = fmaf(d, w_s[o * MX_H + lane + 32], dy1);
+        dw0[o] = fmaf(d, y0, dw0[o]); dw1[o] = fmaf(d, y1, dw1[o]); dbo[o] += d;
       }
-    }
     dg0 += dy0 * xh0; dg1 += dy1 * xh1; db0 += dy0; db1 += dy1;
     const float dx0 = dy0 * lg_s[lane], dx1 = dy1 * lg_s[lane + 32];
     const float c1 = mx_warp_sum(dx0 + dx1) * (1.f / MX_H);
@@ -151,9 +152,19 @@ __global__ void __launch_bounds__(256) k_head_bwd(HeadBwdArgs a) {
     a.dh_out[(size_t)m * MX_H + lane + 32] = rstd * (dx1 - c1 - xh1 * c2);
   }
   if (!a.gpart) return;
-  atomicAdd(&dg_s[lane], dg0); atomicAdd(&dg_s[lane + 32], dg1);
-  atomicAdd(&dbb_s[lane], db0); atomicAdd(&dbb_s[lane + 32], db1);
-  __syncthreads();
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {       // warps in turn: deterministic, no shared atomics
+    if ((tid >> 5) == w) {
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o < a.OD) {
+          dw_s[o * MX_H + lane] += dw0[o]; dw_s[o * MX_H + lane + 32] += dw1[o];
+          if (lane == 0) db_s[o] += dbo[o];
+        }
+      dg_s[lane] += dg0; dg_s[lane + 32] += dg1;
+      dbb_s[lane] += db0; dbb_s[lane + 32] += db1;
+    }
+    __syncthreads();
+  }
   float* gp = a.gpart + (size_t)blockIdx.x * a.P;
   for (int i = tid; i < a.OD * MX_H; i += blockDim.x) gp[a.w + (i / MX_H) * a.w_stride + (i % MX_H)] = dw_s[i];
   for (int i = tid; i < a.OD; i += blockDim.x) gp[a.b + i * a.b_stride] = db_s[i];

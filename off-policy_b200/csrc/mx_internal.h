@@ -114,6 +114,10 @@ struct mx_qmix {
   int64_t ws_bytes;
   MxQmixWs W;
   int split_ok;            // the split mixer pipeline supports this configuration
+  // data-parallel exchange over peer memory (p2p.cu): symmetric blocks of every rank, set by mx_qmix_set_peers
+  int p2p_rank = 0, p2p_world = 0;
+  float* p2p_blocks[16] = {nullptr};
+  uint32_t* p2p_counter = nullptr;
 #if !MX_EMU
   // forked branch for the state-only kernels (weight-image prep, mixer hypernets): one non-blocking stream + fork/join events;
   // inside a stream capture the same record/wait calls turn into parallel graph branches

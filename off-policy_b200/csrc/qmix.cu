@@ -421,7 +421,10 @@ extern "C" int mx_qmix_apply(mx_qmix* q, void* stream) { return mx_qmix_apply_ex
 
 extern "C" int mx_qmix_step_ex(mx_qmix* q, const mx_batch* b, uint32_t flags, void* stream) {
   if (mx_qmix_backward_only(q, b, stream)) return 1;
-  if (q->cfg.world_size > 1) return 0;   // caller all-reduces mx_qmix_grad_buffer(), then mx_qmix_apply[_ex]()
+  if (q->cfg.world_size > 1) {
+    if (!q->p2p_world) return 0;         // NCCL path: the caller all-reduces mx_qmix_grad_buffer(), then mx_qmix_apply[_ex]()
+    if (mx_qmix_p2p_publish(q, stream) || mx_qmix_p2p_reduce(q, stream)) return 1;   // one-shot all-reduce over peer memory
+  }
   return mx_qmix_apply_ex(q, flags, stream);
 }
 extern "C" int mx_qmix_step(mx_qmix* q, const mx_batch* b, void* stream) { return mx_qmix_step_ex(q, b, 0, stream); }
@@ -445,7 +448,7 @@ static int run_sequence(mx_replay* r, mx_qmix* q, int B, double beta, uint32_t f
   else if (flags & 2u) { if (mx_replay_sample_per(r, B, beta, stream)) return 1; }
   mx_batch b;
   if (mx_replay_batch(r, B, &b)) return 1;
-  const bool fuse = (flags & 4u) && q->cfg.world_size == 1;
+  const bool fuse = (flags & 4u) && (q->cfg.world_size == 1 || q->p2p_world);
   if (mx_qmix_step_ex(q, &b, fuse ? MX_STEP_FUSE_SOFT_UPDATE : 0u, stream)) return 1;
   if (flags & 8u) {
     if (mx_replay_update_priorities(r, b.idx, mx_qmix_priorities(q), nullptr, nullptr, B, stream)) return 1;

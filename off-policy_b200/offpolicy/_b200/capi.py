@@ -114,6 +114,10 @@ def _declare(lib):
         "mx_qmix_grad_buffer": (vp, [vp, C.POINTER(i64)]),
         "mx_qmix_info": (vp, [vp]),
         "mx_qmix_priorities": (vp, [vp]),
+        "mx_qmix_p2p_block_bytes": (i64, [vp]),
+        "mx_qmix_set_peers": (C.c_int, [vp, i32, i32, C.POINTER(vp), vp]),
+        "mx_qmix_p2p_publish": (C.c_int, [vp, vp]),
+        "mx_qmix_p2p_reduce": (C.c_int, [vp, vp]),
         "mx_qmix_soft_update": (C.c_int, [vp, vp]),
         "mx_qmix_hard_update": (C.c_int, [vp, vp]),
         "mx_qmix_ws_lookup": (C.c_int, [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),

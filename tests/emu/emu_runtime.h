@@ -124,6 +124,7 @@ inline unsigned ballot(int pred) {
 #define __syncwarp(...) emu::warp_barrier()
 #define __threadfence() ((void)0)
 #define __threadfence_block() ((void)0)
+#define __threadfence_system() ((void)0)
 
 template <class T> inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
   int base = (emu::cur->lane / width) * width;
