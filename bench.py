@@ -376,7 +376,8 @@ def run_engine(args):
     graph = None
     tgraph = None
     run_stream = torch.cuda.current_stream()
-    if world == 1:
+    p2p = world > 1 and bool(getattr(tr, "_p2p", False))      # gradient exchange over NVLink peer memory inside the step (no NCCL)
+    if world == 1 or p2p:
         from offpolicy._b200.graph import StepGraph
         torch.cuda.synchronize()
         graph = StepGraph(buf, tr, B, beta=0.4)
@@ -540,6 +541,8 @@ def run_engine(args):
         ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload=args.workload, batch_per_gpu=B, episode_len=T, n_agents=N, obs_dim=O, act_dim=A, state_dim=S,
                     buffer_episodes_per_gpu=E, parallelism="dp%d" % world if world > 1 else "single",
+                    grad_exchange=("one-shot all-reduce over NVLink peer memory inside the step graph (k_p2p_publish/k_p2p_reduce)" if p2p
+                                   else "NCCL all-reduce of the flat gradient buffer") if world > 1 else None,
                     value_definition="batch-%d grad-steps/s summed over ranks (each rank samples its own shard; one flat all-reduce)" % B,
                     l2="inputs gathered from a replay larger than L2 (%.0f MB); the per-step working set is L2-resident by design" %
                        (pb.L.total_bytes / 1e6),

@@ -14,6 +14,8 @@ single all-reduce of one flat buffer, after which every rank applies the identic
 (the reference has no distributed path: utils/util.py:148-153 is dead code).
 """
 import ctypes as C
+import os
+import sys
 
 import numpy as np
 import torch
@@ -95,6 +97,8 @@ class QMix(object):
         lib = capi.lib()
         self.dev = capi.device()
         self.world_size = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        self.world_size = int(getattr(args, "dp_world_size", None) or self.world_size)     # (tests drive several "ranks" from one process)
+        self._p2p = False
         self.cfg = qmix_cfg_struct(args, num_agents, pol.obs_dim, pol.act_dim, pol.central_obs_dim, self.episode_length, self.max_batch,
                                    vdn=self.vdn, use_avail=True, world_size=self.world_size)
         entries, total = param_entries(self.cfg)
@@ -134,8 +138,35 @@ class QMix(object):
         gptr = lib.mx_qmix_grad_buffer(self.handle, C.byref(n))
         off = gptr - self.workspace.data_ptr()
         self._grad_buf = self.workspace[off:off + 4 * int(n.value)].view(torch.float32)
+        if self.world_size > 1 and self.dev.type == "cuda" and os.environ.get("MARL_B200_P2P", "1") != "0" and \
+                torch.distributed.is_available() and torch.distributed.is_initialized():
+            try:
+                self._setup_p2p()
+            except Exception as ex:       # no peer access / symmetric memory on this box: the NCCL all-reduce path stays in use
+                sys.stderr.write("marl_b200: peer-memory gradient exchange unavailable (%s); using the NCCL all-reduce\n" % (ex,))
         if getattr(args, "use_double_q", True):
             print("double Q learning will be used")
+
+    # -- data-parallel gradient exchange over NVLink peer memory (csrc/p2p.cu) ----------------------------------------
+    def _setup_p2p(self):
+        """One symmetric block per rank (torch.distributed._symmetric_memory: allocation + exchange of the peer mappings is
+        plumbing), handed to the library; from then on `mx_qmix_step` contains the whole exchange and NCCL is not called."""
+        import torch.distributed._symmetric_memory as symm
+        dist = torch.distributed
+        n = int(capi.lib().mx_qmix_p2p_block_bytes(self.handle)) // 4
+        block = symm.empty(n, dtype=torch.float32, device=self.dev)
+        block.zero_()
+        hdl = symm.rendezvous(block, dist.group.WORLD.group_name)
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()
+        self.attach_peer_blocks(dist.get_rank(), [int(p) for p in hdl.buffer_ptrs], keep=(block, hdl))
+
+    def attach_peer_blocks(self, rank, block_ptrs, keep=None):
+        ptrs = (C.c_void_p * len(block_ptrs))(*block_ptrs)
+        self._p2p_counter = torch.zeros(4, dtype=torch.int32, device=self.dev)
+        capi.check(capi.lib().mx_qmix_set_peers(self.handle, int(rank), len(block_ptrs), ptrs, capi.ptr(self._p2p_counter)))
+        self._p2p_keep = keep
+        self._p2p = True
 
     def __del__(self):
         try:
@@ -181,7 +212,7 @@ class QMix(object):
         lib = capi.lib()
         b = self._device_batch(batch)
         stream = capi.stream_ptr()
-        if self.world_size > 1:
+        if self.world_size > 1 and not self._p2p:
             capi.check(lib.mx_qmix_backward_only(self.handle, C.byref(b), stream))
             torch.distributed.all_reduce(self._grad_buf)
             capi.check(lib.mx_qmix_apply(self.handle, stream))
@@ -230,6 +261,14 @@ class QMix(object):
         for name in ("theta", "theta_tgt", "adam_m", "adam_v"):
             getattr(self, name).copy_(torch.as_tensor(sd[name]).to(self.dev))
         self.ws_view("adam_t", torch.float64).copy_(torch.as_tensor(sd["adam_t"]).to(self.dev))
+        if self._p2p and self._p2p_keep is not None and torch.distributed.is_initialized():
+            # the peers' "step reached" flags in the symmetric block belong to the run that wrote them: start over (every rank
+            # restores the same step count, so the exchange resumes in lock-step)
+            torch.cuda.synchronize(self.dev)
+            torch.distributed.barrier()
+            self._p2p_keep[0].zero_()
+            torch.cuda.synchronize(self.dev)
+            torch.distributed.barrier()
 
     def hard_target_updates(self):
         print("hard update targets")
