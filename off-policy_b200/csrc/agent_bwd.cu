@@ -14,27 +14,32 @@
 // =====================================================================================================
 // Q head backward (one warp per row-step)
 // =====================================================================================================
+// Shared memory: wq[A][64] | per-warp private accumulators dW[8][A][64], db[8][32], dgamma[8][64], dbeta[8][64].  Only the owning
+// warp touches its slice while rows are processed (no atomics); the CTA's partial is the sum over the 8 warps in fixed order,
+// so the step is run-to-run deterministic.
+static inline size_t qhead_bwd_smem(int A) { return (size_t)(A * MX_H * 9 + 8 * 32 + 2 * 8 * MX_H + 2 * MX_H) * sizeof(float); }
+
 __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
-  __shared__ float wq_s[32 * MX_H];
-  __shared__ float dwq_s[32 * MX_H];
-  __shared__ float dbq_s[32];
-  __shared__ float dg_s[MX_H], db_s[MX_H], lg_s[MX_H], lb_s[MX_H];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int A = a.A;
-  for (int i = tid; i < A * MX_H; i += blockDim.x) { wq_s[i] = a.theta[a.wq + i]; dwq_s[i] = 0.f; }
-  for (int i = tid; i < 32; i += blockDim.x) dbq_s[i] = 0.f;
-  for (int i = tid; i < MX_H; i += blockDim.x) { dg_s[i] = 0.f; db_s[i] = 0.f; lg_s[i] = a.theta[a.lno_g + i]; lb_s[i] = a.theta[a.lno_b + i]; }
+  MX_DYN_SMEM(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int A = a.A, AW = A * MX_H;
+  float* wq_s = smem;
+  float* dw_w = wq_s + AW;               // [8][A*64]
+  float* db_w = dw_w + 8 * AW;           // [8][32]
+  float* dg_w = db_w + 8 * 32;           // [8][64]
+  float* dbt_w = dg_w + 8 * MX_H;        // [8][64]
+  float* lg_s = dbt_w + 8 * MX_H;
+  float* lb_s = lg_s + MX_H;
+  for (int i = tid; i < AW; i += blockDim.x) wq_s[i] = a.theta[a.wq + i];
+  for (int i = tid; i < 8 * AW + 8 * 32; i += blockDim.x) dw_w[i] = 0.f;      // dw_w and db_w are contiguous
+  for (int i = tid; i < MX_H; i += blockDim.x) { lg_s[i] = a.theta[a.lno_g + i]; lb_s[i] = a.theta[a.lno_b + i]; }
   MX_PDL_WAIT();
   __syncthreads();
-  const int wglobal = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+  const int wglobal = blockIdx.x * (blockDim.x >> 5) + warp;
   const int wtotal = gridDim.x * (blockDim.x >> 5);
   const int T1 = a.T + 1, N = a.N;
   float dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
-  // head-weight gradient of this warp's rows in registers (row k = action k; lane owns columns lane, lane + 32): no shared
-  // atomics, so the CTA's partial is summed in a fixed order (warp 0, 1, ... below) and the step is run-to-run deterministic
-  float dw0[32], dw1[32], dbk[32];
-#pragma unroll
-  for (int k = 0; k < 32; ++k) { dw0[k] = 0.f; dw1[k] = 0.f; dbk[k] = 0.f; }
+  float* my_dw = dw_w + warp * AW;
   for (int m = wglobal; m < a.M; m += wtotal) {
     const int n = m % N;
     const int bt = m / N;
@@ -52,9 +57,9 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
     const float xh0 = (h[lane] - mean) * rstd, xh1 = (h[lane + 32] - mean) * rstd;
     const float y0 = xh0 * lg_s[lane] + lb_s[lane], y1 = xh1 * lg_s[lane + 32] + lb_s[lane + 32];
     const float dy0 = dqv * wq_s[act * MX_H + lane], dy1 = dqv * wq_s[act * MX_H + lane + 32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k)
-      if (k == act) { dw0[k] += dqv * y0; dw1[k] += dqv * y1; dbk[k] += dqv; }
+    my_dw[act * MX_H + lane] += dqv * y0;
+    my_dw[act * MX_H + lane + 32] += dqv * y1;
+    if (lane == 0) db_w[warp * 32 + act] += dqv;
     dg0 += dy0 * xh0; dg1 += dy1 * xh1; db0 += dy0; db1 += dy1;
     // LayerNorm backward
     const float dx0 = dy0 * lg_s[lane], dx1 = dy1 * lg_s[lane + 32];
@@ -63,23 +68,28 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
     out[lane] = rstd * (dx0 - c1 - xh0 * c2);
     out[lane + 32] = rstd * (dx1 - c1 - xh1 * c2);
   }
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {       // warps add their partials one after the other
-    if ((tid >> 5) == w) {
-#pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (k < A) {
-          dwq_s[k * MX_H + lane] += dw0[k]; dwq_s[k * MX_H + lane + 32] += dw1[k];
-          if (lane == 0) dbq_s[k] += dbk[k];
-        }
-      dg_s[lane] += dg0; dg_s[lane + 32] += dg1;
-      db_s[lane] += db0; db_s[lane + 32] += db1;
-    }
-    __syncthreads();
-  }
+  dg_w[warp * MX_H + lane] = dg0; dg_w[warp * MX_H + lane + 32] = dg1;
+  dbt_w[warp * MX_H + lane] = db0; dbt_w[warp * MX_H + lane + 32] = db1;
+  __syncthreads();
   float* gp = a.gpart + (size_t)blockIdx.x * a.P;
-  for (int i = tid; i < A * MX_H; i += blockDim.x) gp[a.wq + i] = dwq_s[i];
-  for (int i = tid; i < A; i += blockDim.x) gp[a.bq + i] = dbq_s[i];
-  for (int i = tid; i < MX_H; i += blockDim.x) { gp[a.lno_g + i] = dg_s[i]; gp[a.lno_b + i] = db_s[i]; }
+  for (int i = tid; i < AW; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += dw_w[w * AW + i];
+    gp[a.wq + i] = v;
+  }
+  for (int i = tid; i < A; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += db_w[w * 32 + i];
+    gp[a.bq + i] = v;
+  }
+  for (int i = tid; i < MX_H; i += blockDim.x) {
+    float g = 0.f, bb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { g += dg_w[w * MX_H + i]; bb += dbt_w[w * MX_H + i]; }
+    gp[a.lno_g + i] = g; gp[a.lno_b + i] = bb;
+  }
 }
 
 // =====================================================================================================
@@ -508,7 +518,15 @@ int mx_launch_qhead_bwd(const QHeadBwdArgs& a, int* nparts_used, cudaStream_t s)
   const int cap = mx_num_sms();
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  MX_LAUNCH_PDL(k_qhead_bwd, dim3(grid), dim3(256), 0, s, a);
+  const size_t smem = qhead_bwd_smem(a.A);
+#if !MX_EMU
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(k_qhead_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { mx_set_error("qhead_bwd: smem %zu too large", smem); return 1; }
+    configured = smem;
+  }
+#endif
+  MX_LAUNCH_PDL(k_qhead_bwd, dim3(grid), dim3(256), smem, s, a);
   MX_COUNT();
   MX_MARK("k_qhead_bwd", s);
   *nparts_used = grid;
