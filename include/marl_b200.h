@@ -293,7 +293,11 @@ typedef struct mx_policy_step_args {
   const float* avail;      /* device [rows][avail_ld]  available-action mask or NULL                   */
   int32_t* greedy;         /* device [rows] arg-max action under the mask, or NULL                     */
   float* greedy_q;         /* device [rows] its value (the reference's greedy_Qs), or NULL             */
+  float* h_copy;           /* optional second destination of the new state [rows][64] (e.g. mapped pinned host memory), or NULL */
 } mx_policy_step_args;
+/* x / avail / out / greedy / greedy_q / h_copy may point into MAPPED PINNED HOST memory (cudaHostAlloc; same address on the
+ * device under UVA): the kernel then reads the observation and writes the actions straight over PCIe and one env step costs one
+ * launch + one stream synchronisation, no memcpy calls. */
 int mx_policy_step(const mx_policy_step_args* args, void* stream);
 
 /* Debug / parity: look up a named fp32 (or int32) region of the workspace written by the last step.

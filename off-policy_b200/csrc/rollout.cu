@@ -22,6 +22,7 @@ struct RollArgs {
   const float* x; int x_ld;
   const float* h_in;       // [R][H] or null (zeros)
   float* h_out;            // [R][H]
+  float* h_copy;           // optional second copy of the new state (mapped host memory) or null
   float* out;              // [R][out_dim]
   const float* avail; int avail_ld;
   int32_t* greedy;         // [R] or null
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(MX_ROLL_THREADS) k_policy_step(RollArgs a) {
         const float hnew = (1.0f - zg) * ng + zg * hs[u];
         hn[u] = hnew;
         a.h_out[(size_t)r * MX_H + u] = hnew;                                             // carried state is the raw h' (rnn.py:21-23)
+        if (a.h_copy) a.h_copy[(size_t)r * MX_H + u] = hnew;
       }
     }
     __syncthreads();
@@ -129,7 +131,7 @@ extern "C" int mx_policy_step(const mx_policy_step_args* p, void* stream) {
   memset(&a, 0, sizeof(a));
   a.theta = p->theta;
   mx_net_layout(p->in_dim, p->out_dim, 0, &a.L);
-  a.x = p->x; a.x_ld = p->x_ld; a.h_in = p->h_in; a.h_out = p->h_out; a.out = p->out;
+  a.x = p->x; a.x_ld = p->x_ld; a.h_in = p->h_in; a.h_out = p->h_out; a.h_copy = p->h_copy; a.out = p->out;
   a.avail = p->avail; a.avail_ld = p->avail_ld; a.greedy = p->greedy; a.greedy_q = p->greedy_q; a.R = p->rows;
   int grid = p->rows;
   const int cap = mx_num_sms() * 4;

@@ -64,7 +64,7 @@ class Batch(C.Structure):
 
 class PolicyStepArgs(C.Structure):
     _fields_ = ([("theta", C.c_void_p)] + [(n, C.c_int32) for n in ("in_dim", "out_dim", "rows", "x_ld", "avail_ld")] +
-                [(n, C.c_void_p) for n in ("x", "h_in", "h_out", "out", "avail", "greedy", "greedy_q")])
+                [(n, C.c_void_p) for n in ("x", "h_in", "h_out", "out", "avail", "greedy", "greedy_q", "h_copy")])
 
 
 class MxError(RuntimeError):

@@ -1,10 +1,11 @@
 """Rollout-time policy step through `mx_policy_step` (csrc/rollout.cu): one launch per env step.
 
 Used by the drop-in policies' `get_actions` / `get_q_values` (reference: QMixPolicy.py:42-67, 95-174;
-rMADDPGPolicy.py:77-137).  Per call: ONE host->device copy of the packed inputs [obs | rnn_state | avail] from a pinned
-staging buffer, ONE kernel, ONE device->host copy of the packed outputs [out | new rnn_state | greedy index | greedy value].
-When the caller hands back the recurrent state it received from the previous call, the device copy is used directly
-(`rnn_states` stay resident in HBM across the episode).
+rMADDPGPolicy.py:77-137).  Inputs and outputs live in ONE block of mapped pinned host memory that the kernel addresses
+directly (UVA): per call the host writes [obs | avail | (rnn_state)] into the block, launches the kernel and synchronises the
+stream -- no memcpy calls; the kernel reads the observation over PCIe and writes [out | new rnn_state | greedy index | greedy
+value] back the same way.  The recurrent state is ALSO kept in device memory: when the caller hands back the state it received
+from the previous call (the runner does, smac_runner.py:86-98) the device copy is used and nothing is uploaded.
 """
 import ctypes as C
 
@@ -29,70 +30,65 @@ class PolicyStepper(object):
         self.in_dim, self.out_dim = int(in_dim), int(out_dim)
         self.dev = capi.device()
         self.rows = 0
-        self._last_h = None      # (host array handed out, device tensor it mirrors)
+        self._last_h = None      # (host array handed out, rows): its device copy is in self.d_h
 
     def _ensure(self, rows):
         if rows <= self.rows:
             return
         self.rows = rows
         cuda = self.dev.type == "cuda"
-        nin = rows * (self.in_dim + H + self.out_dim)
-        nout = rows * (self.out_dim + H + 2)
-        self.h_in_host = torch.zeros(nin, dtype=torch.float32, pin_memory=cuda)
-        self.h_out_host = torch.zeros(nout, dtype=torch.float32, pin_memory=cuda)
-        self.d_in = torch.zeros(nin, dtype=torch.float32, device=self.dev)
-        self.d_out = torch.zeros(nout, dtype=torch.float32, device=self.dev)
-        self._last_h = None      # the device-resident state lived in the old buffers
+        I, A = self.in_dim, self.out_dim
+        n = rows * (I + A + H) + rows * (A + H + 2)
+        # pinned (page-locked) host memory is mapped into the device address space by the CUDA allocator torch uses
+        self.block = torch.zeros(n, dtype=torch.float32, pin_memory=cuda)
+        self.block_np = self.block.numpy()
+        self.d_h = torch.zeros(rows * H, dtype=torch.float32, device=self.dev)     # recurrent state resident on the device
+        self._last_h = None
+        self._args = capi.PolicyStepArgs()
 
     def step(self, theta, obs, rnn_states, avail=None, want_greedy=True):
         """theta: flat device parameter vector; obs (R, in_dim); rnn_states (R, 64) array / tensor / None.
-        Returns (out (R,out_dim), h_new (R,64), greedy_idx (R,) int64, greedy_val (R,)) as NumPy arrays (views of one pinned
-        block, copied) -- one synchronisation per env step, which the CPU env loop needs anyway."""
+        Returns (out (R,out_dim), h_new (R,64), greedy_idx (R,) int64, greedy_val (R,)) as NumPy arrays -- one stream
+        synchronisation per env step, which the CPU env loop needs anyway."""
         obs = np.asarray(obs, dtype=np.float32)
         R = obs.shape[0]
         self._ensure(R)
         I, A = self.in_dim, self.out_dim
-        o_x, o_h, o_av = 0, R * I, R * (I + H)
-        hin = self.h_in_host.numpy()
-        hin[o_x:o_x + R * I] = obs.reshape(-1)
+        blk = self.block_np
+        o_x, o_av, o_h = 0, R * I, R * (I + A)
+        o_out = R * (I + A + H)
+        o_hn, o_gi, o_gq = o_out + R * A, o_out + R * (A + H), o_out + R * (A + H + 1)
+        blk[o_x:o_x + R * I] = obs.reshape(-1)
         resident = False
         if rnn_states is None:
-            hin[o_h:o_h + R * H] = 0.0
+            blk[o_h:o_h + R * H] = 0.0
         elif self._last_h is not None and self._last_h[1] == R and _host_ptr(rnn_states) == _host_ptr(self._last_h[0]):
-            # the very buffer we handed out last step (the runner passes it straight back, smac_runner.py:86-98; holding a
-            # reference keeps its memory from being reused): its device copy is still in the output block
+            # the very buffer we handed out last step (holding a reference keeps its memory from being reused)
             resident = True
         else:
             hs = rnn_states.detach().cpu().numpy() if isinstance(rnn_states, torch.Tensor) else np.asarray(rnn_states)
-            hin[o_h:o_h + R * H] = hs.astype(np.float32, copy=False).reshape(-1)
+            blk[o_h:o_h + R * H] = hs.astype(np.float32, copy=False).reshape(-1)
         if avail is not None:
             av = avail.detach().cpu().numpy() if isinstance(avail, torch.Tensor) else np.asarray(avail)
-            hin[o_av:o_av + R * A] = av.astype(np.float32, copy=False).reshape(-1)
-        n_in = R * (I + H + A)
-        self.d_in[:n_in].copy_(self.h_in_host[:n_in], non_blocking=True)
-        a = capi.PolicyStepArgs()
+            blk[o_av:o_av + R * A] = av.astype(np.float32, copy=False).reshape(-1)
+        a = self._args
+        base = self.block.data_ptr()
         a.theta = theta.data_ptr()
         a.in_dim, a.out_dim, a.rows, a.x_ld, a.avail_ld = I, A, R, I, A
-        base = self.d_in.data_ptr()
         a.x = base + 4 * o_x
-        ob = self.d_out.data_ptr()
-        # the new state is written into the packed output block; a resident state is read from that same place (the kernel
-        # reads a row's state completely before it writes it)
-        a.h_in = ob + 4 * R * A if resident else base + 4 * o_h
-        a.h_out = ob + 4 * R * A
-        a.out = ob
+        a.h_in = self.d_h.data_ptr() if resident else base + 4 * o_h
+        a.h_out = self.d_h.data_ptr()
+        a.h_copy = base + 4 * o_hn
+        a.out = base + 4 * o_out
         a.avail = base + 4 * o_av if avail is not None else None
-        a.greedy = ob + 4 * R * (A + H) if want_greedy else None
-        a.greedy_q = ob + 4 * R * (A + H + 1) if want_greedy else None
+        a.greedy = base + 4 * o_gi if want_greedy else None
+        a.greedy_q = base + 4 * o_gq if want_greedy else None
         capi.check(capi.lib().mx_policy_step(C.byref(a), capi.stream_ptr()))
-        n_out = R * (A + H + 2)
-        self.h_out_host[:n_out].copy_(self.d_out[:n_out], non_blocking=True)
         if self.dev.type == "cuda":
             torch.cuda.current_stream().synchronize()
-        res = self.h_out_host.numpy()
-        out = res[:R * A].reshape(R, A).copy()
-        h_new = res[R * A:R * (A + H)].reshape(R, H).copy()
-        gi = res[R * (A + H):R * (A + H) + R].view(np.int32).astype(np.int64) if want_greedy else None
-        gq = res[R * (A + H + 1):R * (A + H + 1) + R].copy() if want_greedy else None
+        out = blk[o_out:o_out + R * A].reshape(R, A).copy()
+        h_new = blk[o_hn:o_hn + R * H].reshape(R, H).copy()
+        gi = blk[o_gi:o_gi + R].view(np.int32).astype(np.int64) if want_greedy else None
+        gq = blk[o_gq:o_gq + R].copy() if want_greedy else None
         self._last_h = (h_new, R)
         return out, h_new, gi, gq
