@@ -112,7 +112,7 @@ def run_maddpg(args):
             if s >= args.warmup:
                 times.append(time.perf_counter() - t0)
         sps = 1.0 / float(np.median(times))
-        print(json.dumps(dict(metric="learner grad-steps/sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
+        emit((dict(metric="learner grad-steps/sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
                               warmup=args.warmup, ms_per_step=1e3 / sps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                               data="synthetic", config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=n),
                               cpu_baseline=dict(value=sps, unit="steps/s", cores=th, kind="port", sample="%d timed updates" % args.steps),
@@ -180,7 +180,7 @@ def run_maddpg(args):
         if s >= 2:
             tms.append(time.perf_counter() - t0)
     cpu = 1.0 / float(np.median(tms))
-    print(json.dumps(dict(metric="learner grad-steps/sec", value=1000.0 / ms, unit="steps/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3),
+    emit(dict(metric="learner grad-steps/sec", value=1000.0 / ms, unit="steps/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3),
                           ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                           config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim,
                                       buffer_episodes=E, step="CUDA graphs (one per update_actor variant): device MT19937 sample + mx_maddpg_step (+ soft update when the actor was updated); "
@@ -192,7 +192,7 @@ def run_maddpg(args):
                           roofline=dict(bound="tensor", kernel="(many small launches)", achieved=None, peak=peaks()["tflops_sustained"], unit="TFLOP/s",
                                         frac=None, traffic=None, note="launch/latency bound at B=32, T=25; see DESIGN.md"),
                           cpu_baseline=dict(value=cpu, unit="steps/s", cores=8, kind="port", sample="6 timed updates of the same workload (oracle port)"),
-                          clocks=clocks.summary())))
+                          clocks=clocks.summary()))
 
 
 def make_cfg(w):
@@ -307,7 +307,7 @@ def run_reference(args):
                 cpu_baseline=dict(value=sps, unit="steps/s", cores=cores, host_cores=os.cpu_count(), kind="port",
                                   sample="%d timed learner steps (sample+train+soft update) of the same workload, replay of %d episodes" % (args.steps, E)),
                 e2e=dict(value=sps, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -436,8 +436,8 @@ def run_engine(args):
 
     if args.quick:          # tuning sweeps: the device-resident number only (not a bench line)
         if rank == 0:
-            print(json.dumps(dict(quick=True, workload=args.workload, value=world * 1000.0 / ms_step, ms_per_step=ms_step, opts=args.opt,
-                                  kernels_per_step=kernels_per_step)))
+            emit(dict(quick=True, workload=args.workload, value=world * 1000.0 / ms_step, ms_per_step=ms_step, opts=args.opt,
+                      kernels_per_step=kernels_per_step))
             sys.stdout.flush()
         if graph is not None:
             graph.close()
@@ -476,6 +476,37 @@ def run_engine(args):
     if world > 1:
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
     e2e_sps = world * n_e2e / float(e2e_s)
+
+    # same loop with the loss read lagging ONE step (copied to pinned memory asynchronously, read after the next step has been
+    # enqueued): what a runner that logs train_info asynchronously sees.  Reported beside, not instead of, the synchronous number.
+    pins = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(2)]
+    evts = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_step_lagged(i):
+        buf.insert(1, *[rc.d(x) for x in fresh[i % 8]])
+        smp = buf.sample(B, 0.4, "policy_0") if cfg.use_per else buf.sample(B)
+        info, prio, idx = tr.train_policy_on_batch(smp)
+        if cfg.use_per:
+            buf.update_priorities(idx, prio, "policy_0")
+        tr.soft_target_updates()
+        k = i & 1
+        pins[k].copy_(tr._info[:4], non_blocking=True)
+        evts[k].record()
+        evts[k ^ 1].synchronize()
+        return float(pins[k ^ 1][0])                                                  # D2H result of the PREVIOUS step
+
+    evts[1].record()
+    for i in range(4):
+        e2e_step_lagged(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        e2e_step_lagged(i)
+    barrier()
+    lag_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(lag_s, op=torch.distributed.ReduceOp.MAX)
+    e2e_lagged_sps = world * n_e2e / float(lag_s)
 
     # ---------------- per-kernel timing (eager, CUDA events on the launch stream) ----------------
     # every rank runs this loop: the eager step contains the all-reduce, so the collective counts must match on all ranks
@@ -549,6 +580,7 @@ def run_engine(args):
                     step="CUDA graph: device MT19937 draw + gather + fused QMIX learner + Adam + Polyak; state-only kernels (weight images, mixer "
                          "hypernets) on a forked graph branch beside the agent-net kernels" if (graph or tgraph) else "eager"),
         e2e=dict(value=e2e_sps, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=n_e2e,
+                 lagged_read_value=e2e_lagged_sps,      # same loop, each step's loss read one step late (asynchronous logging)
                  path="RecReplayBuffer.insert(1 episode, pinned) + sample(np.random.choice) + QMix.train_policy_on_batch + soft_target_updates + D2H info"),
         gpu_launches=launches, kernels_per_step=kernels_per_step,
         roofline=roof, kernels=breakdown, kernel_sum_ms=round(ksum, 5),        # > ms_per_step when branches of the step graph overlap
@@ -557,7 +589,7 @@ def run_engine(args):
                           best_threads_steps_per_s=sps_all, one_thread_steps_per_s=sps_one,
                           sample="%d timed steps (sample+train+soft update) of the same workload on a %d-episode replay, oracle port of the reference learner" % (n_cpu, Ecpu)),
         clocks=clocks.summary())
-    print(json.dumps(line))
+    emit(line)
     sys.stdout.flush()
     if graph is not None:
         graph.close()
@@ -566,7 +598,25 @@ def run_engine(args):
         os._exit(0)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The bench contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner on communicator
+    creation, the drop-in classes' reference-style prints), so main() points fd 1 at stderr and the result goes to the saved fd."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

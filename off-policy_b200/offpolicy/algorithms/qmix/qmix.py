@@ -134,6 +134,8 @@ class QMix(object):
         self.use_step_graph = True          # replay the captured launch sequence for batches that live in a replay's batch region
         self._graphs, self._graph_keep, self._cap_stream = {}, [], None
         self._info = self.ws_view("info")
+        self._info_views = (self._info[0], self._info[1], self._info[2])       # 0-dim views, created once (they alias the workspace)
+        self._prio_view = self.ws_view("prio")
         n = C.c_int64()
         gptr = lib.mx_qmix_grad_buffer(self.handle, C.byref(n))
         off = gptr - self.workspace.data_ptr()
@@ -210,19 +212,27 @@ class QMix(object):
 
     def train_policy_on_batch(self, batch, update_policy_id=None):
         lib = capi.lib()
-        b = self._device_batch(batch)
         stream = capi.stream_ptr()
-        if self.world_size > 1 and not self._p2p:
-            capi.check(lib.mx_qmix_backward_only(self.handle, C.byref(b), stream))
-            torch.distributed.all_reduce(self._grad_buf)
-            capi.check(lib.mx_qmix_apply(self.handle, stream))
-        elif self.use_step_graph and isinstance(batch, SampledBatch) and self.dev.type == "cuda":
-            capi.check(lib.mx_graph_launch(self._step_graph(batch, b.B), stream))
+        sampled = isinstance(batch, SampledBatch)
+        if sampled and self.use_step_graph and self.dev.type == "cuda" and (self.world_size == 1 or self._p2p):
+            # fast path: the batch lives in a replay's batch region -> replay the captured launch sequence (one cudaGraphLaunch)
+            buf = batch.buffers["policy_0"]
+            if buf.sample_serial != batch.serial["policy_0"]:
+                raise RuntimeError("stale sample: the buffer has been sampled again since this batch was drawn")
+            B = batch.B
+            capi.check(lib.mx_graph_launch(self._step_graph(batch, B), stream))
         else:
-            capi.check(lib.mx_qmix_step(self.handle, C.byref(b), stream))
-        info = self._info
-        train_info = {"loss": info[0], "grad_norm": info[1], "Q_tot": info[2]}          # qmix.py:195-198 (0-dim device tensors)
-        new_priorities = DeviceArray(self.ws_view("prio")[:b.B]) if self.use_per else None
+            b = self._device_batch(batch)
+            B = b.B
+            if self.world_size > 1 and not self._p2p:
+                capi.check(lib.mx_qmix_backward_only(self.handle, C.byref(b), stream))
+                torch.distributed.all_reduce(self._grad_buf)
+                capi.check(lib.mx_qmix_apply(self.handle, stream))
+            else:
+                capi.check(lib.mx_qmix_step(self.handle, C.byref(b), stream))
+        v = self._info_views
+        train_info = {"loss": v[0], "grad_norm": v[1], "Q_tot": v[2]}                   # qmix.py:195-198 (0-dim device tensors)
+        new_priorities = DeviceArray(self._prio_view[:B]) if self.use_per else None
         return train_info, new_priorities, batch[8]
 
     def _step_graph(self, batch, B):

@@ -89,18 +89,34 @@ class _LazyField(dict):
         return k in self._p_ids
 
 
-class SampledBatch(tuple):
-    """The reference's 9-tuple (rec_buffer.py:82,304) + a handle on the device-side batch."""
+class SampledBatch(object):
+    """The reference's 9-tuple (rec_buffer.py:82,304) + a handle on the device-side batch.  Behaves like the tuple (len 9,
+    indexing, unpacking); the seven field entries are created on first access (a B200 trainer never touches them)."""
 
-    def __new__(cls, buffers, B, weights, idxes, p_ids):
-        fields = [_LazyField(None, f, p_ids) for f in FIELDS]
-        self = super().__new__(cls, tuple(fields) + (weights, idxes))
-        for f in fields:
-            f._owner = self
+    __slots__ = ("buffers", "B", "serial", "_p_ids", "_items")
+
+    def __init__(self, buffers, B, weights, idxes, p_ids):
         self.buffers = buffers
         self.B = B
+        self._p_ids = p_ids
         self.serial = {p: buffers[p].sample_serial for p in p_ids}
-        return self
+        self._items = [None] * 7 + [weights, idxes]
+
+    def __len__(self):
+        return 9
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return tuple(self[k] for k in range(*i.indices(9)))
+        if i < 0:
+            i += 9
+        v = self._items[i]
+        if v is None and i < 7:
+            v = self._items[i] = _LazyField(self, FIELDS[i], self._p_ids)
+        return v
+
+    def __iter__(self):
+        return (self[k] for k in range(9))
 
     def materialize(self, p_id, field):
         buf = self.buffers[p_id]
@@ -147,6 +163,8 @@ class RecPolicyBuffer(object):
         self._stage_evt = [None, None]
         self._stage_i = 0
         self._pack_cache = {}
+        self._view_cache = {}
+        self._first_slot = C.c_int32()
         self._idx_dev = torch.zeros(self.max_batch, dtype=torch.int64, device=self.dev)
         self._idx_pin = None
         self._idx_ring, self._idx_k = None, 0
@@ -230,6 +248,21 @@ class RecPolicyBuffer(object):
             self._pack_cache[n_ep] = lay
         return lay
 
+    def _stage_views(self, si, stage, n_ep):
+        """float32 views of staging buffer `si`, one per field of an n_ep-episode insert (cached: the pinned buffers are reused)."""
+        key = (si, n_ep, stage.data_ptr())
+        v = self._view_cache.get(key)
+        if v is None:
+            offs, cnts, total = self._packed_layout(n_ep)
+            host = stage.numpy()
+            T, N = self.episode_length, self.num_agents
+            shapes = [(T + 1, n_ep, N, self.obs_dim), (T + 1, n_ep, self.share_dim), (T, n_ep, N, self.act_dim), (T, n_ep, N, 1),
+                      (T, n_ep, N, 1), (T, n_ep, 1), (T + 1, n_ep, N, self.act_dim)]
+            v = [host[o:o + 4 * n].view(np.float32).reshape(sh) if n else None for o, n, sh in zip(offs, cnts, shapes)]
+            self._view_cache = {k: w for k, w in self._view_cache.items() if k[0] != si or k[2] == stage.data_ptr()}
+            self._view_cache[key] = v
+        return v
+
     def insert(self, num_insert_episodes, obs, share_obs, acts, rewards, dones, dones_env, avail_acts=None):
         n_ep = int(num_insert_episodes)
         acts = np.asarray(acts)
@@ -239,22 +272,21 @@ class RecPolicyBuffer(object):
         share_obs = np.asarray(share_obs)
         if share_obs.ndim == 4:
             share_obs = share_obs[:, :, 0]                                               # rec_buffer.py:173-175
-        arrs = [obs, share_obs, acts, rewards, dones, dones_env, avail_acts if self.use_avail_acts else None]
-        offs, cnts, total = self._packed_layout(n_ep)
+        arrs = (obs, share_obs, acts, rewards, dones, dones_env, avail_acts if self.use_avail_acts else None)
+        total = self._packed_layout(n_ep)[2]
         si, stage = self._staging(total)
-        host = stage.numpy()
-        for a, o, n in zip(arrs, offs, cnts):
-            if n:
+        for a, view in zip(arrs, self._stage_views(si, stage, n_ep)):
+            if view is not None:
                 a = np.asarray(a)
-                if a.size != n:
-                    raise ValueError("insert: a field has %d elements, expected %d" % (a.size, n))
-                np.copyto(host[o:o + 4 * n].view(np.float32), a.reshape(-1), casting="same_kind")
-        first = C.c_int32()
+                if a.size != view.size:
+                    raise ValueError("insert: a field has %d elements, expected %d" % (a.size, view.size))
+                np.copyto(view, a.reshape(view.shape), casting="same_kind")      # one (possibly strided) pass into pinned memory
+        first = self._first_slot
         capi.check(capi.lib().mx_replay_insert_packed_async(self.handle, C.c_void_p(stage.data_ptr()), total, n_ep, C.byref(first),
                                                             capi.stream_ptr()))
         if self.dev.type == "cuda":
             evt = self._stage_evt[si] or torch.cuda.Event()
-            evt.record(torch.cuda.current_stream(self.dev))
+            evt.record()
             self._stage_evt[si] = evt
         return (first.value + np.arange(n_ep)) % self.buffer_size
 
