@@ -1,4 +1,5 @@
 """QMIX learner kernels' logic on the CPU fiber emulator vs the reference goldens (and the oracle's trace)."""
+import numpy as np
 import pytest
 
 import qmix_checks as qc
@@ -38,3 +39,23 @@ def test_fused_mixer_kernel_matches_reference_golden(emu_engine, name):
     g = qc.load_golden(name)
     steps = int(g["meta.steps"]) if "meta.steps" in g else None
     assert split > fused and (split - fused) % 2 == 0, (split, fused, steps)      # two extra launches per learner step
+
+
+@pytest.mark.parametrize("split", [1, 0])
+@pytest.mark.parametrize("mixer_hidden,hyper_hidden,n_agents,layers", [(48, 40, 4, 2), (64, 64, 2, 1), (20, 64, 3, 2)])
+def test_mixer_shapes_vs_oracle(emu_engine, split, mixer_hidden, hyper_hidden, n_agents, layers):
+    """Mixer widths that are not the defaults (mixer_hidden not a multiple of 32 / equal to 64 = two units per lane in k_mix_core,
+    hypernet_hidden != 64, one hypernet layer), split and fused kernels, PER weights + Huber, against the oracle in lock-step."""
+    from oracle.qmix import QmixConfig, synth_batch
+    lib = emu_engine.lib()
+    cfg = QmixConfig(n_agents=n_agents, obs_dim=7, act_dim=4, state_dim=10, mixer_hidden=mixer_hidden, hyper_hidden=hyper_hidden,
+                     hyper_layers=layers, gain=1.0, use_per=True, huber=True, huber_delta=0.7)
+    B, T = 5, 6
+    lib.mx_set_option(b"mixer_split", split)
+    try:
+        L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T)
+        w = np.random.RandomState(3).rand(B) * 0.9 + 0.1
+        batch = synth_batch(cfg, B, T, seed=9, avail_p=0.8, var_len=True) + (w, np.arange(B))
+        qc.compare_step(L, pol, tr, batch, cfg, steps=2)
+    finally:
+        lib.mx_set_option(b"mixer_split", 1)

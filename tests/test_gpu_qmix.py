@@ -54,6 +54,41 @@ def test_config5_2s3z_vs_oracle(gpu_engine):
     _compare_step(L, pol, tr, batch, cfg, steps=1)
 
 
+@pytest.mark.parametrize("mode", ["forked", "fused"])
+def test_config5_2s3z_branch_modes_vs_oracle(gpu_engine, mode):
+    """2s3z sizes with the forked branch forced on (split mixer beside the agent nets; the default at this size is the in-line
+    fused k_mixer) and forced off: both against the oracle."""
+    from oracle.qmix import QmixConfig, synth_batch
+    torch.set_num_threads(8)
+    lib = gpu_engine.lib()
+    lib.mx_set_option(b"overlap", 2 if mode == "forked" else 0)
+    try:
+        cfg = QmixConfig(n_agents=5, obs_dim=80, act_dim=11, state_dim=120)
+        L, args, pol, tr = _oracle_and_trainer(cfg, 32, 120)
+        batch = synth_batch(cfg, 32, 120, seed=7, avail_p=0.8, var_len=False) + (None, None)
+        _compare_step(L, pol, tr, batch, cfg, steps=2)
+    finally:
+        lib.mx_set_option(b"overlap", 1)
+
+
+@pytest.mark.parametrize("mode", ["forked", "fused"])
+@pytest.mark.parametrize("mixer_hidden,hyper_hidden,n_agents,layers", [(48, 40, 4, 2), (64, 64, 2, 1), (20, 64, 3, 2)])
+def test_mixer_shapes_vs_oracle(gpu_engine, mode, mixer_hidden, hyper_hidden, n_agents, layers):
+    from oracle.qmix import QmixConfig, synth_batch
+    lib = gpu_engine.lib()
+    cfg = QmixConfig(n_agents=n_agents, obs_dim=7, act_dim=4, state_dim=10, mixer_hidden=mixer_hidden, hyper_hidden=hyper_hidden,
+                     hyper_layers=layers, gain=1.0, use_per=True, huber=True, huber_delta=0.7)
+    B, T = 5, 6
+    lib.mx_set_option(b"overlap", 2 if mode == "forked" else 0)
+    try:
+        L, args, pol, tr = _oracle_and_trainer(cfg, B, T)
+        w = np.random.RandomState(3).rand(B) * 0.9 + 0.1
+        batch = synth_batch(cfg, B, T, seed=9, avail_p=0.8, var_len=True) + (w, np.arange(B))
+        _compare_step(L, pol, tr, batch, cfg, steps=2)
+    finally:
+        lib.mx_set_option(b"overlap", 1)
+
+
 def test_vdn_vs_oracle(gpu_engine):
     """VDN = sum mixer (reference is shape-broken, App. D-1: pinned against the oracle's intent restatement)."""
     from oracle.qmix import QmixConfig, synth_batch
