@@ -78,6 +78,22 @@ int mx_launch_mix_hyper_fwd(const MixerArgs& a, cudaStream_t s);
 int mx_launch_mix_core(const MixerArgs& a, int* scalar_parts_used, cudaStream_t s);
 int mx_launch_mix_hyper_bwd(const MixerArgs& a, int* nparts_used, cudaStream_t s);
 
+// k_qhead + k_mix_core + k_qhead_bwd in one launch (mid.cu); `mix` carries the hypernet outputs / mixer scalars, the rest is the head
+struct MidArgs {
+  MixerArgs mix;
+  int wq, bq, lno_g, lno_b;
+  const float* hall[2];    // live, target [M][H]
+  const int32_t* act_idx;  // [B][T][N]
+  const float* avail;      // [M][act_ld] or null
+  int act_ld;
+  int T, N, A, double_q;
+  float* dh_out;           // [M][H]
+  float* gpart;            // head + post-GRU LayerNorm gradient partial of CTA blockIdx.x
+  long long P;
+};
+int mx_mid_supported(const MidArgs& a);
+int mx_launch_mid(const MidArgs& a, int* parts_used, cudaStream_t s);   // parts_used: gradient partials == scalar partials
+
 struct QHeadBwdArgs {
   const float* theta;
   int wq, bq, lno_g, lno_b;

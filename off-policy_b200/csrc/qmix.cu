@@ -366,34 +366,55 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   qh.q_taken = ws + W.q_taken; qh.q_next = ws + W.q_next;
   qh.greedy = q->debug ? reinterpret_cast<int32_t*>(ws + W.greedy) : nullptr;
   qh.qall0 = q->debug ? ws + W.qall[0] : nullptr; qh.qall1 = q->debug ? ws + W.qall[1] : nullptr;
-  if (mx_launch_qhead(qh, s)) return 1;
 
   int parts[4] = {0, 0, 0, 0};
-  if (split) {
+  MidArgs md;
+  memset(&md, 0, sizeof(md));
+  md.mix = mx;
+  md.wq = qh.wq; md.bq = qh.bq; md.lno_g = qh.lno_g; md.lno_b = qh.lno_b; md.hall[0] = qh.hall[0]; md.hall[1] = qh.hall[1];
+  md.act_idx = qh.act_idx; md.avail = qh.avail; md.act_ld = qh.act_ld; md.T = T; md.N = N; md.A = c.act_dim; md.double_q = c.double_q;
+  md.dh_out = ws + W.dh_out; md.gpart = mx.gpart; md.P = q->P;
+  // the three latency-bound launches between the recurrences (Q head, mixer core, Q head backward) as one kernel; the debug mode
+  // of the parity tests keeps the separate kernels because it materialises every per-action Q value
+  const bool mid = split && g_mx_mid_fused && !q->debug && mx_mid_supported(md);
+  if (mid) {
     if (!overlap) { if (mx_launch_mix_hyper_fwd(mx, s)) return 1; }
 #if !MX_EMU
     else join_from_side(q, q->ev_hyper, s);
 #endif
-    if (mx_launch_mix_core(mx, &parts[3], s)) return 1;
+    if (mx_launch_mid(md, &parts[1], s)) return 1;
+    parts[3] = parts[1];
 #if !MX_EMU
     if (overlap) fork_to_side(q, q->ev_core, s);
 #endif
-    if (mx_launch_mix_hyper_bwd(mx, &parts[2], side)) return 1;      // beside k_qhead_bwd / k_gru_bwd / k_front_bwd when forked
+    if (mx_launch_mix_hyper_bwd(mx, &parts[2], side)) return 1;
   } else {
-    if (mx_launch_mixer(mx, &parts[2], s)) return 1;
-    parts[3] = parts[2];
+    if (mx_launch_qhead(qh, s)) return 1;
+    if (split) {
+      if (!overlap) { if (mx_launch_mix_hyper_fwd(mx, s)) return 1; }
+#if !MX_EMU
+      else join_from_side(q, q->ev_hyper, s);
+#endif
+      if (mx_launch_mix_core(mx, &parts[3], s)) return 1;
+#if !MX_EMU
+      if (overlap) fork_to_side(q, q->ev_core, s);
+#endif
+      if (mx_launch_mix_hyper_bwd(mx, &parts[2], side)) return 1;      // beside k_qhead_bwd / k_gru_bwd / k_front_bwd when forked
+    } else {
+      if (mx_launch_mixer(mx, &parts[2], s)) return 1;
+      parts[3] = parts[2];
+    }
+    QHeadBwdArgs hb;
+    memset(&hb, 0, sizeof(hb));
+    hb.theta = q->theta; hb.wq = q->agent.wq; hb.bq = q->agent.bq; hb.lno_g = q->agent.lno_g; hb.lno_b = q->agent.lno_b;
+    hb.hall = gf.hall[0]; hb.sto = qh.sto; hb.act_idx = b->act_idx; hb.dq_taken = mx.dq_taken;
+    hb.M = M; hb.T = T; hb.N = N; hb.A = c.act_dim; hb.dh_out = ws + W.dh_out; hb.gpart = mx.gpart; hb.P = q->P;
+    if (mx_launch_qhead_bwd(hb, &parts[1], s)) return 1;
   }
-
-  QHeadBwdArgs hb;
-  memset(&hb, 0, sizeof(hb));
-  hb.theta = q->theta; hb.wq = q->agent.wq; hb.bq = q->agent.bq; hb.lno_g = q->agent.lno_g; hb.lno_b = q->agent.lno_b;
-  hb.hall = gf.hall[0]; hb.sto = qh.sto; hb.act_idx = b->act_idx; hb.dq_taken = mx.dq_taken;
-  hb.M = M; hb.T = T; hb.N = N; hb.A = c.act_dim; hb.dh_out = ws + W.dh_out; hb.gpart = mx.gpart; hb.P = q->P;
-  if (mx_launch_qhead_bwd(hb, &parts[1], s)) return 1;
 
   GruBwdArgs gb;
   memset(&gb, 0, sizeof(gb));
-  gb.theta = q->theta; gb.whh = q->agent.whh; gb.hall = gf.hall[0]; gb.gates = gf.gates; gb.hn = gf.hn; gb.dh_out = hb.dh_out;
+  gb.theta = q->theta; gb.whh = q->agent.whh; gb.hall = gf.hall[0]; gb.gates = gf.gates; gb.hn = gf.hn; gb.dh_out = ws + W.dh_out;
   gb.dgi = ws + W.dgi; gb.R = B * N; gb.T = T; gb.N = N;
   if (mx_launch_gru_bwd(gb, s)) return 1;
 

@@ -29,7 +29,7 @@ def make_args(cfg, B, **over):
     return a
 
 
-def build_trainer(cfg, B, T, vdn=False, **over):
+def build_trainer(cfg, B, T, vdn=False, debug=True, **over):
     from offpolicy.algorithms.qmix.algorithm.QMixPolicy import QMixPolicy
     from offpolicy.algorithms.qmix.qmix import QMix
     from offpolicy._b200 import capi
@@ -38,7 +38,9 @@ def build_trainer(cfg, B, T, vdn=False, **over):
                 cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
     pol = QMixPolicy({"args": args, "device": capi.device()}, info)
     tr = QMix(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=capi.device(), episode_length=T, vdn=vdn)
-    capi.lib().mx_qmix_set_debug(tr.handle, 1)      # also materialise per-action Q values for the intermediate checks
+    # debug: also materialise per-action Q values for the intermediate checks (and keep k_qhead / k_mix_core / k_qhead_bwd as
+    # separate launches); debug=False runs the product configuration (the fused k_mid between the recurrences)
+    capi.lib().mx_qmix_set_debug(tr.handle, 1 if debug else 0)
     return args, pol, tr
 
 
@@ -107,10 +109,11 @@ def check_forward_intermediates(tr, L, batch, cfg, B, T):
     return bad
 
 
-def check_step_against(g_or_none, name=None, intermediates=True):
+def check_step_against(g_or_none, name=None, intermediates=True, debug=True):
     g = load_golden(name)
     L, cfg, B, T, steps = oracle_from_golden(g)
-    args, pol, tr = build_trainer(cfg, B, T)
+    args, pol, tr = build_trainer(cfg, B, T, debug=debug)
+    intermediates = intermediates and debug
     load_state(pol, tr, sub(g, "init.agent."), sub(g, "init.mixer."), sub(g, "init.tgt_agent."), sub(g, "init.tgt_mixer."))
     problems = []
     for s in range(steps):

@@ -59,3 +59,33 @@ def test_mixer_shapes_vs_oracle(emu_engine, split, mixer_hidden, hyper_hidden, n
         qc.compare_step(L, pol, tr, batch, cfg, steps=2)
     finally:
         lib.mx_set_option(b"mixer_split", 1)
+
+
+@pytest.mark.parametrize("name", ["qmix_small", "qmix_small_huber_nodq", "qmix_small_per", "qmix_small_hyper1", "qmix_5ag"])
+def test_product_configuration_matches_reference_golden(emu_engine, name):
+    """debug outputs off = what bench.py / the runner execute: k_qhead + k_mix_core + k_qhead_bwd run as the single k_mid."""
+    lib = emu_engine.lib()
+    c0 = lib.mx_launch_count()
+    qc.check_step_against(None, name, debug=False)
+    fused = lib.mx_launch_count() - c0
+    lib.mx_set_option(b"mid_fused", 0)
+    try:
+        c0 = lib.mx_launch_count()
+        qc.check_step_against(None, name, debug=False)
+        separate = lib.mx_launch_count() - c0
+    finally:
+        lib.mx_set_option(b"mid_fused", 1)
+    assert separate > fused and (separate - fused) % 2 == 0, (separate, fused)      # two launches fewer per learner step
+
+
+@pytest.mark.parametrize("mixer_hidden,hyper_hidden,n_agents,act_dim", [(48, 40, 4, 4), (64, 64, 2, 20), (20, 64, 8, 17)])
+def test_product_configuration_shapes_vs_oracle(emu_engine, mixer_hidden, hyper_hidden, n_agents, act_dim):
+    """k_mid at other widths: more than 16 actions (one lane per action instead of two half dot products), 8 agents, wide mixer."""
+    from oracle.qmix import QmixConfig, synth_batch
+    cfg = QmixConfig(n_agents=n_agents, obs_dim=7, act_dim=act_dim, state_dim=10, mixer_hidden=mixer_hidden, hyper_hidden=hyper_hidden,
+                     gain=1.0, use_per=True, huber=True, huber_delta=0.7)
+    B, T = 5, 6
+    L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T, debug=False)
+    w = np.random.RandomState(3).rand(B) * 0.9 + 0.1
+    batch = synth_batch(cfg, B, T, seed=9, avail_p=0.6, var_len=True) + (w, np.arange(B))
+    qc.compare_step(L, pol, tr, batch, cfg, steps=2)
