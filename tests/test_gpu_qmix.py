@@ -20,6 +20,34 @@ def test_step_matches_reference_golden(gpu_engine, name):
     qc.check_step_against(None, name)
 
 
+@pytest.mark.parametrize("name", GOLDENS)
+def test_product_configuration_matches_reference_golden(gpu_engine, name):
+    """debug outputs off = what bench.py / the runner execute (k_mid between the recurrences, forked hypernet branch)."""
+    qc.check_step_against(None, name, debug=False)
+
+
+@pytest.mark.parametrize("mixer_hidden,hyper_hidden,n_agents,act_dim", [(48, 40, 4, 4), (64, 64, 2, 20), (20, 64, 8, 17)])
+def test_product_configuration_shapes_vs_oracle(gpu_engine, mixer_hidden, hyper_hidden, n_agents, act_dim):
+    from oracle.qmix import QmixConfig, synth_batch
+    cfg = QmixConfig(n_agents=n_agents, obs_dim=7, act_dim=act_dim, state_dim=10, mixer_hidden=mixer_hidden, hyper_hidden=hyper_hidden,
+                     gain=1.0, use_per=True, huber=True, huber_delta=0.7)
+    B, T = 5, 6
+    L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T, debug=False)
+    w = np.random.RandomState(3).rand(B) * 0.9 + 0.1
+    batch = synth_batch(cfg, B, T, seed=9, avail_p=0.6, var_len=True) + (w, np.arange(B))
+    qc.compare_step(L, pol, tr, batch, cfg, steps=2)
+
+
+def test_config2_3m_full_size_product_configuration_vs_oracle(gpu_engine):
+    """BASELINE config 2 exactly as benchmarked: 14-launch two-branch step with k_mid, three consecutive steps."""
+    from oracle.qmix import QmixConfig, synth_batch
+    torch.set_num_threads(8)
+    cfg = QmixConfig(gain=1.0)
+    L, args, pol, tr = qc.oracle_and_trainer(cfg, 32, 60, debug=False)
+    batch = synth_batch(cfg, 32, 60, seed=5, avail_p=0.8, var_len=True) + (None, None)
+    qc.compare_step(L, pol, tr, batch, cfg, steps=3)
+
+
 _oracle_and_trainer = qc.oracle_and_trainer
 _compare_step = qc.compare_step
 
