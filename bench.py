@@ -324,6 +324,7 @@ def kernel_work(cfg, T, B, P):
         "k_mixer": 2.0 * E * mix * 4,                    # target fwd + live fwd + live bwd (dgrad + wgrad)
         "k_mix_hyper_fwd": 2.0 * E * (mix - N * ME - ME) * 2,         # split pipeline: hypernet layers of the live + target mixers
         "k_mix_core": 2.0 * E * (N * ME + ME) * 4,                    # q-dependent part: both forwards + backward
+        "k_mid": 2.0 * E * (N * ME + ME) * 4 + 2.0 * E * N * H * A * 3 + 2.0 * E * N * 3 * H,    # 3 head evaluations per row + core + head backward
         "k_mix_hyper_bwd": 2.0 * E * (mix - N * ME - ME) * 2,         # dgrad + wgrad of the live hypernets
         "k_qhead_bwd": 2.0 * M * 3 * H,
         "k_gru_bwd": 2.0 * M * 3 * H * H,
@@ -361,7 +362,7 @@ def run_engine(args):
     torch.manual_seed(1)
     np.random.seed(1)
     with contextlib.redirect_stdout(sys.stderr):        # the drop-in QMix mirrors the reference's "double Q learning will be used" print
-        args_ns, pol, tr = qc.build_trainer(cfg, B, T)
+        args_ns, pol, tr = qc.build_trainer(cfg, B, T, debug=False)      # product configuration: no debug outputs, k_mid
     pb = buf.policy_buffers["policy_0"]
     buf.seed_device_rng(1 + rank)
     stream = torch.cuda.current_stream()

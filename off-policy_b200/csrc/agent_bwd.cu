@@ -537,6 +537,7 @@ int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
   const int sms = mx_num_sms();
   int rpc = 1;
   while (rpc < 4 && mx_ceil_div(a.R, rpc) > 2 * sms) rpc *= 2;
+  if (g_mx_gru_bwd_rpc == 1 || g_mx_gru_bwd_rpc == 2 || g_mx_gru_bwd_rpc == 4) rpc = g_mx_gru_bwd_rpc;
   dim3 grid(mx_ceil_div(a.R, rpc));
   if (rpc == 1) MX_LAUNCH_PDL(k_gru_bwd<1>, grid, dim3(BWD_THREADS), 0, s, a);
   else if (rpc == 2) MX_LAUNCH_PDL(k_gru_bwd<2>, grid, dim3(BWD_THREADS), 0, s, a);

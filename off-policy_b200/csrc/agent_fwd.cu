@@ -392,6 +392,7 @@ int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s) {
   const int sms = mx_num_sms();
   int rpc = 1;     // one resident CTA per SM (the kernel is register heavy): grow rows-per-CTA until the grid fits one wave
   while (rpc < 4 && mx_ceil_div(a.R, rpc) * nets > 2 * sms) rpc *= 2;   // two CTAs fit per SM (<= 128 registers): co-resident CTAs hide each other's latencies
+  if (g_mx_gru_fwd_rpc == 1 || g_mx_gru_fwd_rpc == 2 || g_mx_gru_fwd_rpc == 4) rpc = g_mx_gru_fwd_rpc;
   dim3 grid(mx_ceil_div(a.R, rpc), nets);
   if (rpc == 1) MX_LAUNCH_PDL(k_gru_fwd<1>, grid, dim3(GRU_THREADS), 0, s, a);
   else if (rpc == 2) MX_LAUNCH_PDL(k_gru_fwd<2>, grid, dim3(GRU_THREADS), 0, s, a);

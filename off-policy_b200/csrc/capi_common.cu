@@ -20,6 +20,8 @@ int g_mx_overlap = 1;          // state-only kernels (weight-image prep, mixer h
                                // kernels: 1 = when the step is latency-bound (rows <= g_mx_overlap_rows), 2 = always, 0 = never
 int g_mx_mid_fused = 1;        // 1: k_qhead + k_mix_core + k_qhead_bwd as ONE kernel (k_mid) when the split mixer is in use and no debug
                                //    outputs are requested; 0: three launches
+int g_mx_gru_fwd_rpc = 0;      // tuning overrides: sequence rows per CTA of the recurrence kernels (0 = automatic; 1, 2 or 4)
+int g_mx_gru_bwd_rpc = 0;
 int g_mx_overlap_rows = 12288; // measured on B200 (profiles/r01l_overlap_sweep.log): 3m (5 856 rows) +16 %, 8m (61 952 rows) -8 %
 int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "mixer_split")) { g_mx_mixer_split = value; return 0; }
@@ -27,6 +29,8 @@ int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "overlap")) { g_mx_overlap = value; return 0; }
   if (!strcmp(name, "overlap_rows")) { g_mx_overlap_rows = value; return 0; }
   if (!strcmp(name, "mid_fused")) { g_mx_mid_fused = value; return 0; }
+  if (!strcmp(name, "gru_fwd_rpc")) { g_mx_gru_fwd_rpc = value; return 0; }
+  if (!strcmp(name, "gru_bwd_rpc")) { g_mx_gru_bwd_rpc = value; return 0; }
   return -1;
 }
 

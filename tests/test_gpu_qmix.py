@@ -94,7 +94,7 @@ def test_config5_2s3z_branch_modes_vs_oracle(gpu_engine, mode):
         cfg = QmixConfig(n_agents=5, obs_dim=80, act_dim=11, state_dim=120)
         L, args, pol, tr = _oracle_and_trainer(cfg, 32, 120)
         batch = synth_batch(cfg, 32, 120, seed=7, avail_p=0.8, var_len=False) + (None, None)
-        _compare_step(L, pol, tr, batch, cfg, steps=2)
+        _compare_step(L, pol, tr, batch, cfg, steps=1)      # (a second step would compare gradients at parameters that already differ by the Adam-step tolerance)
     finally:
         lib.mx_set_option(b"overlap", 1)
 
