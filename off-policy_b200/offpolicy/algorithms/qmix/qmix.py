@@ -146,6 +146,11 @@ class QMix(object):
                 self._setup_p2p()
             except Exception as ex:       # no peer access / symmetric memory on this box: the NCCL all-reduce path stays in use
                 sys.stderr.write("marl_b200: peer-memory gradient exchange unavailable (%s); using the NCCL all-reduce\n" % (ex,))
+            # every rank must use the same exchange: fall back everywhere if any rank could not map its peers
+            agree = torch.tensor([1 if self._p2p else 0], dtype=torch.int32, device=self.dev)
+            torch.distributed.all_reduce(agree, op=torch.distributed.ReduceOp.MIN)
+            if int(agree) == 0:
+                self._p2p = False
         if getattr(args, "use_double_q", True):
             print("double Q learning will be used")
 
