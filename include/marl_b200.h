@@ -147,7 +147,7 @@ typedef struct mx_qmix_cfg {
   int32_t double_q;          /* use_double_q                                       */
   int32_t use_huber;         /* use_huber_loss                                     */
   int32_t use_per;           /* importance weights + new priorities                */
-  int32_t use_avail;         /* avail_acts present in the batch                    */
+  int32_t use_avail;         /* (informational) masks follow the batch: batch->avail may be NULL, e.g. MPE */
   int32_t world_size;        /* data-parallel ranks (1 = single GPU)               */
   float gamma, huber_delta, per_nu, per_eps;
   float lr, adam_beta1, adam_beta2, adam_eps, max_grad_norm, tau;
@@ -182,6 +182,9 @@ typedef struct mx_batch {
   const float* dones_env;  /* [B][T]               */
   const float* weights;    /* [B] fp32 PER importance weights or NULL */
   const int64_t* idx;      /* [B] or NULL */
+  /* floats between consecutive episodes of the per-step fields: rewards / dones / act_idx (>= T*N) and dones_env (>= T).
+   * 0 = dense.  The replay's batch region pads every episode row to 16 bytes, so it reports round_up(T*N, 4) / round_up(T, 4). */
+  int32_t ep_tn_ld, ep_t_ld;
 } mx_batch;
 int mx_replay_batch(const mx_replay* r, int32_t B, mx_batch* out);   /* view of the replay's batch region */
 

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
       continue;
     }
     const size_t e = (size_t)b * a.T + t;
-    const int act = a.act_idx[e * N + n];
+    const int act = a.act_idx[(size_t)b * a.ld_tn + (size_t)t * N + n];
     const float dqv = a.dq_taken[e * N + n];
     const float* h = a.hall + (size_t)m * MX_H;
     const float mean = a.sto[2 * (size_t)m], rstd = a.sto[2 * (size_t)m + 1];

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) k_qhead(QHeadArgs a) {
     const float* hl = a.hall[0] + (size_t)m * MX_H;
     const float* ht = a.hall[1] + (size_t)m * MX_H;
     const float hl0 = hl[lane], hl1 = hl[lane + 32], ht0 = ht[lane], ht1 = ht[lane + 32];
-    const int act = (t < a.T) ? a.act_idx[((size_t)b * a.T + t) * N + n] : 0;
+    const int act = (t < a.T) ? a.act_idx[(size_t)b * a.ld_tn + (size_t)t * N + n] : 0;
     float av = 1.f;
     if (a.avail && lane < A) av = a.avail[(size_t)m * a.act_ld + lane];
     const unsigned avail_mask = __ballot_sync(0xffffffffu, av != 0.f);

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(256) k_head_bwd(HeadBwdArgs a) {
 
 struct CriticLossArgs {
   int B, T, N, K;
+  int ld_tn, ld_t;          // floats between consecutive episodes of rewards (>= T*N) and dones_env (>= T)
   const float* qpred;       // [B*T][K]
   const float* qnext_min;   // [B*T]
   const float* rewards;     // [B][T][N]
@@ -192,9 +193,9 @@ __global__ void __launch_bounds__(256) k_critic_loss(CriticLossArgs a) {   // ON
   float den = 0.f, ls = 0.f;
   for (int e = tid; e < E; e += blockDim.x) {
     const int b = e / a.T, t = e % a.T;
-    const float rew = a.rewards[((size_t)b * a.T + t) * a.N];
-    const float de = a.dones_env[(size_t)b * a.T + t];
-    const float bad = t > 0 ? a.dones_env[(size_t)b * a.T + t - 1] : 0.f;
+    const float rew = a.rewards[(size_t)b * a.ld_tn + (size_t)t * a.N];
+    const float de = a.dones_env[(size_t)b * a.ld_t + t];
+    const float bad = t > 0 ? a.dones_env[(size_t)b * a.ld_t + t - 1] : 0.f;
     const float keep = 1.f - bad;
     const float y = rew + a.gamma * (1.f - de) * a.qnext_min[e];
     const float w = a.weights ? a.weights[b] : 1.f;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(256) k_critic_loss(CriticLossArgs a) {   // ON
 
 struct ActorLossArgs {
   int B, T, N, K;
+  int ld_tn;                // floats between consecutive episodes of dones (>= T*N)
   const float* qa;          // [N*B*T][K] critic outputs on the agent-replaced copies (head 0 is used)
   const float* dones;       // [B][T][N]
   float* dout;              // [N*B*T][K]
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(256) k_actor_loss(ActorLossArgs a) {   // ONE 
   for (int row = tid; row < rows; row += blockDim.x) {
     const int i = row / (a.B * a.T), bt = row % (a.B * a.T);
     const int b = bt / a.T, t = bt % a.T;
-    const float dm = t > 0 ? a.dones[((size_t)b * a.T + t - 1) * a.N + i] : 0.f;    // r_maddpg.py:268-272
+    const float dm = t > 0 ? a.dones[(size_t)b * a.ld_tn + (size_t)(t - 1) * a.N + i] : 0.f;    // r_maddpg.py:268-272
     const float keep = 1.f - dm;
     den += keep;
     ls -= a.qa[(size_t)row * a.K] * keep;
@@ -614,7 +616,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   // ---------- D. TD target, critic loss ----------
   CriticLossArgs cl;
   memset(&cl, 0, sizeof(cl));
-  cl.B = B; cl.T = T; cl.N = N; cl.K = K; cl.qpred = ws + W.c_q; cl.qnext_min = ws + W.t_qmin; cl.rewards = b->rewards; cl.dones_env = b->dones_env;
+  cl.B = B; cl.T = T; cl.N = N; cl.K = K; cl.ld_tn = b->ep_tn_ld > 0 ? b->ep_tn_ld : T * N; cl.ld_t = b->ep_t_ld > 0 ? b->ep_t_ld : T; cl.qpred = ws + W.c_q; cl.qnext_min = ws + W.t_qmin; cl.rewards = b->rewards; cl.dones_env = b->dones_env;
   cl.weights = c.use_per ? b->weights : nullptr; cl.gamma = c.gamma; cl.huber_delta = c.huber_delta; cl.per_nu = c.per_nu; cl.per_eps = c.per_eps;
   cl.use_huber = c.use_huber; cl.dq = ws + W.c_dq; cl.err = ws + W.c_err; cl.scal = ws + W.scal_c; cl.prio = c.use_per ? ws + W.prio : nullptr;
   MX_LAUNCH(k_critic_loss, dim3(1), dim3(256), 0, s, cl); MX_COUNT(); MX_MARK("k_critic_loss", s);
@@ -676,7 +678,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
     MX_LAUNCH(k_head_fwd, dim3(launch1d((long long)Mr * 32)), dim3(256), 0, s, hr); MX_COUNT(); MX_MARK("k_head_fwd", s);
     ActorLossArgs al;
     memset(&al, 0, sizeof(al));
-    al.B = B; al.T = T; al.N = N; al.K = K; al.qa = ws + W.r_q; al.dones = b->dones; al.dout = ws + W.r_dout; al.scal = ws + W.scal_a;
+    al.B = B; al.T = T; al.N = N; al.K = K; al.ld_tn = b->ep_tn_ld > 0 ? b->ep_tn_ld : T * N; al.qa = ws + W.r_q; al.dones = b->dones; al.dout = ws + W.r_dout; al.scal = ws + W.scal_a;
     MX_LAUNCH(k_actor_loss, dim3(1), dim3(256), 0, s, al); MX_COUNT(); MX_MARK("k_actor_loss", s);
     // back through the (frozen) critic to its action inputs
     HeadBwdArgs hbr = hb;

@@ -16,7 +16,12 @@
 
 #define MID_WARPS 16
 #define MID_THREADS (32 * MID_WARPS)
-#define MID_WLD 65          // padded head-weight row: lane k reads row k, conflict-free
+// Head-weight row k lives at k * 66 with column j at j + (j >= 32): the two half-warps of the A <= 16 path (columns 0..31 and
+// 32..63 of the same rows) then read banks 2k + j and 2k + 1 + j -- all 32 lanes conflict-free; the LayerNorm output row uses the
+// same one-float gap, so its two broadcast reads per step also hit different banks.
+#define MID_WLD 66
+#define MID_YLD 66
+MX_DEVINL int mid_col(int j) { return j + (j >> 5); }
 
 struct MidSmem { int o_wq, o_bq, o_ln, o_y, o_dw, o_db, o_dg, total; };
 static MidSmem mid_smem(int A) {
@@ -25,7 +30,7 @@ static MidSmem mid_smem(int A) {
   s.o_wq = o; o += 2 * 32 * MID_WLD;            // [net][32][65]
   s.o_bq = o; o += 2 * 32;
   s.o_ln = o; o += 4 * MX_H;                    // live gamma, beta, target gamma, beta
-  s.o_y = o; o += MID_WARPS * MX_H;             // per-warp LayerNorm output row
+  s.o_y = o; o += MID_WARPS * MID_YLD;          // per-warp LayerNorm output row (gapped)
   s.o_dw = o; o += MID_WARPS * A * MX_H;        // per-warp private dWq
   s.o_db = o; o += MID_WARPS * 32;              // per-warp private dbq
   s.o_dg = o; o += 2 * MID_WARPS * MX_H;        // per-warp d gamma, d beta
@@ -46,7 +51,7 @@ MX_DEVINL void mid_ln(float v0, float v1, const float* g, const float* b, int la
 MX_DEVINL float mid_head(const float* ys, const float* wq, const float* bq, int A, int lane) {
   float q;
   if (A <= 16) {
-    const int k = lane & 15, j0 = (lane >> 4) * 32;
+    const int k = lane & 15, j0 = (lane >> 4) * 33;         // second half starts one float later (mid_col)
     const float* w = wq + (k < A ? k : 0) * MID_WLD + j0;
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -59,7 +64,7 @@ MX_DEVINL float mid_head(const float* ys, const float* wq, const float* bq, int 
     const float* w = wq + (k < A ? k : 0) * MID_WLD;
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < MX_H; j += 2) { s0 = fmaf(ys[j], w[j], s0); s1 = fmaf(ys[j + 1], w[j + 1], s1); }
+    for (int j = 0; j < MX_H; j += 2) { s0 = fmaf(ys[mid_col(j)], w[mid_col(j)], s0); s1 = fmaf(ys[mid_col(j + 1)], w[mid_col(j + 1)], s1); }
     q = k < A ? (s0 + s1) + bq[k] : 0.f;
   }
   return q;
@@ -85,12 +90,12 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
   const int A = a.A, N = a.N, T = a.T, T1 = a.T + 1, ME = L.ME;
   const int E = a.mix.B * T;
   float* wq_s = smem + sm.o_wq; float* bq_s = smem + sm.o_bq; float* ln_s = smem + sm.o_ln;
-  float* ys = smem + sm.o_y + warp * MX_H;
+  float* ys = smem + sm.o_y + warp * MID_YLD;
   float* my_dw = smem + sm.o_dw + warp * A * MX_H;
   float* my_db = smem + sm.o_db + warp * 32;
   for (int net = 0; net < 2; ++net) {
     const float* th = net ? a.mix.theta_tgt : a.mix.theta;
-    for (int i = tid; i < A * MX_H; i += MID_THREADS) wq_s[net * 32 * MID_WLD + (i / MX_H) * MID_WLD + (i % MX_H)] = th[a.wq + i];
+    for (int i = tid; i < A * MX_H; i += MID_THREADS) wq_s[net * 32 * MID_WLD + (i / MX_H) * MID_WLD + mid_col(i % MX_H)] = th[a.wq + i];
     for (int i = tid; i < 32; i += MID_THREADS) bq_s[net * 32 + i] = i < A ? th[a.bq + i] : 0.f;
     for (int i = tid; i < MX_H; i += MID_THREADS) { ln_s[net * 2 * MX_H + i] = th[a.lno_g + i]; ln_s[net * 2 * MX_H + MX_H + i] = th[a.lno_b + i]; }
   }
@@ -107,9 +112,9 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
     const int b = e / T, t = e - b * T;
     const size_t m0 = ((size_t)b * T1 + t) * N;          // rows of step t;  rows of step t+1 start at m0 + N
     // independent scalar loads first
-    const float rew = a.mix.rewards[((size_t)b * T + t) * N];
-    const float de = a.mix.dones_env[(size_t)b * T + t];
-    const float bad = t > 0 ? a.mix.dones_env[(size_t)b * T + t - 1] : 0.f;
+    const float rew = a.mix.rewards[(size_t)b * a.mix.ld_tn + (size_t)t * N];
+    const float de = a.mix.dones_env[(size_t)b * a.mix.ld_t + t];
+    const float bad = t > 0 ? a.mix.dones_env[(size_t)b * a.mix.ld_t + t - 1] : 0.f;
     const float w = a.mix.weights ? a.mix.weights[b] : 1.f;
     const float b2v[2] = {a.mix.hyp_b2[0][e], a.mix.hyp_b2[1][e]};
     float qt_reg = 0.f, qn_reg = 0.f;                     // lane n: q_taken[n], q_next[n]
@@ -119,25 +124,25 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
       const float* hl1 = a.hall[0] + (m0 + N + n) * MX_H;
       const float* ht1 = a.hall[1] + (m0 + N + n) * MX_H;
       const float h0a = hl[lane], h0b = hl[lane + 32], h1a = hl1[lane], h1b = hl1[lane + 32], g1a = ht1[lane], g1b = ht1[lane + 32];
-      const int act = a.act_idx[(size_t)e * N + n];
+      const int act = a.act_idx[(size_t)b * a.ld_tn + (size_t)t * N + n];
       float av = 1.f;
       if (a.avail && lane < A) av = a.avail[(m0 + N + n) * a.act_ld + lane];
       float xh0, xh1, y0, y1, rstd;
       mid_ln(h0a, h0b, lg, lb, lane, xh0, xh1, y0, y1, rstd);
-      ys[lane] = y0; ys[lane + 32] = y1;
+      ys[lane] = y0; ys[lane + 33] = y1;
       __syncwarp();
       const float q_t = mid_head(ys, wq0, bq_s, A, lane);
       const float q_taken = __shfl_sync(0xffffffffu, q_t, act);
       __syncwarp();
       mid_ln(h1a, h1b, lg, lb, lane, xh0, xh1, y0, y1, rstd);
-      ys[lane] = y0; ys[lane + 32] = y1;
+      ys[lane] = y0; ys[lane + 33] = y1;
       __syncwarp();
       const float q_t1 = mid_head(ys, wq0, bq_s, A, lane);
       float gbest; int greedy;
       mid_argmax(av != 0.f ? q_t1 : -1e10f, A, lane, gbest, greedy);          // util.py:297-302, first maximum wins
       __syncwarp();
       mid_ln(g1a, g1b, tg, tb, lane, xh0, xh1, y0, y1, rstd);
-      ys[lane] = y0; ys[lane + 32] = y1;
+      ys[lane] = y0; ys[lane + 33] = y1;
       __syncwarp();
       const float tq = mid_head(ys, wq1, bq_s + 32, A, lane);
       float q_next;
@@ -218,11 +223,11 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
     // ---------------- Q head backward for the rows of step t ----------------
     for (int n = 0; n < N; ++n) {
       const float dqv = __shfl_sync(0xffffffffu, dqt_reg, n);
-      const int act = a.act_idx[(size_t)e * N + n];
+      const int act = a.act_idx[(size_t)b * a.ld_tn + (size_t)t * N + n];
       const float* hl = a.hall[0] + (m0 + n) * MX_H;
       float xh0, xh1, y0, y1, rstd;
       mid_ln(hl[lane], hl[lane + 32], lg, lb, lane, xh0, xh1, y0, y1, rstd);
-      const float dy0 = dqv * wq0[act * MID_WLD + lane], dy1 = dqv * wq0[act * MID_WLD + lane + 32];
+      const float dy0 = dqv * wq0[act * MID_WLD + lane], dy1 = dqv * wq0[act * MID_WLD + lane + 33];
       my_dw[act * MX_H + lane] += dqv * y0;
       my_dw[act * MX_H + lane + 32] += dqv * y1;
       if (lane == 0) my_db[act] += dqv;

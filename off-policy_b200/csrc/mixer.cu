@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_mixer(MixerArgs a, MixSmem 
       float dq = 0.f, den = 0.f, ls = 0.f, qs = 0.f;
       if (e < E) {
         const int b = e / a.T, t = e % a.T;
-        const float rew = a.rewards[((size_t)b * a.T + t) * L.N];              // agent 0 (qmix.py:159)
-        const float de = a.dones_env[(size_t)b * a.T + t];
-        const float bad = t > 0 ? a.dones_env[(size_t)b * a.T + t - 1] : 0.f;     // qmix.py:161
+        const float rew = a.rewards[(size_t)b * a.ld_tn + (size_t)t * L.N];              // agent 0 (qmix.py:159)
+        const float de = a.dones_env[(size_t)b * a.ld_t + t];
+        const float bad = t > 0 ? a.dones_env[(size_t)b * a.ld_t + t - 1] : 0.f;     // qmix.py:161
         const float y = rew + (1.f - de) * a.gamma * Qn_s[tid];
         const float keep = 1.f - bad;
         const float err = (Q_s[tid] - y) * keep;
@@ -348,9 +348,9 @@ __global__ void __launch_bounds__(256) k_vdn_mix(MixerArgs a) {
     float Q = 0.f, Qn = 0.f;
     for (int n = 0; n < N; ++n) { Q += a.q_taken[(size_t)e * N + n]; Qn += a.q_next[(size_t)e * N + n]; }
     const int b = e / a.T, t = e % a.T;
-    const float rew = a.rewards[((size_t)b * a.T + t) * N];
-    const float de = a.dones_env[(size_t)b * a.T + t];
-    const float bad = t > 0 ? a.dones_env[(size_t)b * a.T + t - 1] : 0.f;
+    const float rew = a.rewards[(size_t)b * a.ld_tn + (size_t)t * N];
+    const float de = a.dones_env[(size_t)b * a.ld_t + t];
+    const float bad = t > 0 ? a.dones_env[(size_t)b * a.ld_t + t - 1] : 0.f;
     const float y = rew + (1.f - de) * a.gamma * Qn;
     const float keep = 1.f - bad;
     const float err = (Q - y) * keep;
@@ -481,9 +481,9 @@ __global__ void __launch_bounds__(512) k_mix_core(MixerArgs a) {
     float hp[MX_MIX_MAXK], hvv[MX_MIX_MAXK], p2v[MX_MIX_MAXK];
     // independent scalar loads first: their latency overlaps the two mixing passes
     const int b = e / a.T, t = e % a.T;
-    const float rew = a.rewards[((size_t)b * a.T + t) * N];              // agent 0 (qmix.py:159)
-    const float de = a.dones_env[(size_t)b * a.T + t];
-    const float bad = t > 0 ? a.dones_env[(size_t)b * a.T + t - 1] : 0.f;     // qmix.py:161
+    const float rew = a.rewards[(size_t)b * a.ld_tn + (size_t)t * N];              // agent 0 (qmix.py:159)
+    const float de = a.dones_env[(size_t)b * a.ld_t + t];
+    const float bad = t > 0 ? a.dones_env[(size_t)b * a.ld_t + t - 1] : 0.f;     // qmix.py:161
     const float w = a.weights ? a.weights[b] : 1.f;
     const float b2v[2] = {a.hyp_b2[0][e], a.hyp_b2[1][e]};
 #pragma unroll

@@ -39,6 +39,7 @@ struct QHeadArgs {
   const float* avail;      // [M][act_ld] or null
   int act_ld;
   int M, T, N, A, double_q;
+  int ld_tn;               // floats between consecutive episodes of act_idx (>= T*N)
   float *q_taken, *q_next; // [B*T][N]
   int32_t* greedy;         // [M] (debug)
   float *qall0, *qall1;    // [M][A] (debug) or null
@@ -56,6 +57,7 @@ struct MixerArgs {
   const float* dones_env;  // [B][T]
   const float* weights;    // [B] or null
   int B, T, N;
+  int ld_tn, ld_t;         // floats between consecutive episodes of rewards (>= T*N) and dones_env (>= T)
   float gamma, huber_delta;
   int use_huber;
   float *qtot, *qtot_next, *err;   // [E]
@@ -87,6 +89,7 @@ struct MidArgs {
   const float* avail;      // [M][act_ld] or null
   int act_ld;
   int T, N, A, double_q;
+  int ld_tn;               // episode stride of act_idx (rewards / dones_env strides are in `mix`)
   float* dh_out;           // [M][H]
   float* gpart;            // head + post-GRU LayerNorm gradient partial of CTA blockIdx.x
   long long P;
@@ -102,6 +105,7 @@ struct QHeadBwdArgs {
   const int32_t* act_idx;
   const float* dq_taken;   // [E][N]
   int M, T, N, A;
+  int ld_tn;               // episode stride of act_idx
   float* dh_out;           // [M][H]
   float* gpart;
   long long P;

@@ -226,9 +226,12 @@ static int check_batch(const mx_qmix* q, const mx_batch* b) {
   const mx_qmix_cfg& c = q->cfg;
   if (!b || b->B <= 0 || b->B > c.max_batch) { mx_set_error("qmix step: batch size outside [1, max_batch=%d]", c.max_batch); return 1; }
   if (!b->obs || !b->share || !b->act_idx || !b->rewards || !b->dones_env) { mx_set_error("qmix step: missing batch field"); return 1; }
-  if (c.use_avail && !b->avail) { mx_set_error("qmix step: use_avail set but batch has no avail"); return 1; }
+  // b->avail may be NULL: MPE has no available-action masks (runner/rnn/mpe_runner.py:62; qmix.py:141-147 masks only when given)
   if (c.use_per && !b->weights) { mx_set_error("qmix step: use_per set but batch has no importance weights"); return 1; }
   if (b->obs_ld < c.obs_dim || b->share_ld < c.state_dim) { mx_set_error("qmix step: batch strides smaller than dims"); return 1; }
+  if ((b->ep_tn_ld > 0 && b->ep_tn_ld < c.episode_len * c.n_agents) || (b->ep_t_ld > 0 && b->ep_t_ld < c.episode_len)) {
+    mx_set_error("qmix step: episode strides smaller than the episode"); return 1;
+  }
   return 0;
 }
 
@@ -321,6 +324,8 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   mx.share = b->share; mx.share_ld = b->share_ld;
   mx.q_taken = ws + W.q_taken; mx.q_next = ws + W.q_next;
   mx.rewards = b->rewards; mx.dones_env = b->dones_env; mx.weights = c.use_per ? b->weights : nullptr;
+  const int ld_tn = b->ep_tn_ld > 0 ? b->ep_tn_ld : T * N, ld_t = b->ep_t_ld > 0 ? b->ep_t_ld : T;
+  mx.ld_tn = ld_tn; mx.ld_t = ld_t;
   mx.B = B; mx.T = T; mx.N = N; mx.gamma = c.gamma; mx.huber_delta = c.huber_delta; mx.use_huber = c.use_huber;
   mx.qtot = ws + W.qtot; mx.qtot_next = ws + W.qtot_next; mx.err = ws + W.err; mx.dq_taken = ws + W.dq_taken;
   mx.gpart = ws + W.gpart; mx.P = q->P; mx.spart = ws + W.spart;
@@ -361,8 +366,8 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   qh.theta[0] = q->theta; qh.theta[1] = q->theta_tgt;
   qh.wq = q->agent.wq; qh.bq = q->agent.bq; qh.lno_g = q->agent.lno_g; qh.lno_b = q->agent.lno_b;
   qh.hall[0] = gf.hall[0]; qh.hall[1] = gf.hall[1]; qh.sto = ws + W.sto;
-  qh.act_idx = b->act_idx; qh.avail = c.use_avail ? b->avail : nullptr; qh.act_ld = b->act_ld;
-  qh.M = M; qh.T = T; qh.N = N; qh.A = c.act_dim; qh.double_q = c.double_q;
+  qh.act_idx = b->act_idx; qh.avail = b->avail; qh.act_ld = b->act_ld;
+  qh.M = M; qh.T = T; qh.N = N; qh.A = c.act_dim; qh.double_q = c.double_q; qh.ld_tn = ld_tn;
   qh.q_taken = ws + W.q_taken; qh.q_next = ws + W.q_next;
   qh.greedy = q->debug ? reinterpret_cast<int32_t*>(ws + W.greedy) : nullptr;
   qh.qall0 = q->debug ? ws + W.qall[0] : nullptr; qh.qall1 = q->debug ? ws + W.qall[1] : nullptr;
@@ -372,7 +377,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   memset(&md, 0, sizeof(md));
   md.mix = mx;
   md.wq = qh.wq; md.bq = qh.bq; md.lno_g = qh.lno_g; md.lno_b = qh.lno_b; md.hall[0] = qh.hall[0]; md.hall[1] = qh.hall[1];
-  md.act_idx = qh.act_idx; md.avail = qh.avail; md.act_ld = qh.act_ld; md.T = T; md.N = N; md.A = c.act_dim; md.double_q = c.double_q;
+  md.act_idx = qh.act_idx; md.avail = qh.avail; md.act_ld = qh.act_ld; md.T = T; md.N = N; md.A = c.act_dim; md.double_q = c.double_q; md.ld_tn = ld_tn;
   md.dh_out = ws + W.dh_out; md.gpart = mx.gpart; md.P = q->P;
   // the three latency-bound launches between the recurrences (Q head, mixer core, Q head backward) as one kernel; the debug mode
   // of the parity tests keeps the separate kernels because it materialises every per-action Q value
@@ -408,7 +413,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
     memset(&hb, 0, sizeof(hb));
     hb.theta = q->theta; hb.wq = q->agent.wq; hb.bq = q->agent.bq; hb.lno_g = q->agent.lno_g; hb.lno_b = q->agent.lno_b;
     hb.hall = gf.hall[0]; hb.sto = qh.sto; hb.act_idx = b->act_idx; hb.dq_taken = mx.dq_taken;
-    hb.M = M; hb.T = T; hb.N = N; hb.A = c.act_dim; hb.dh_out = ws + W.dh_out; hb.gpart = mx.gpart; hb.P = q->P;
+    hb.M = M; hb.T = T; hb.N = N; hb.A = c.act_dim; hb.ld_tn = ld_tn; hb.dh_out = ws + W.dh_out; hb.gpart = mx.gpart; hb.P = q->P;
     if (mx_launch_qhead_bwd(hb, &parts[1], s)) return 1;
   }
 

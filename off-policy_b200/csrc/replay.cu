@@ -849,5 +849,7 @@ extern "C" int mx_replay_batch(const mx_replay* r, int32_t B, mx_batch* out) {
   out->dones_env = cat<float>(r, L.off_b_dones_env);
   out->weights = r->cfg.use_per ? cat<float>(r, L.off_b_wf32) : nullptr;
   out->idx = cat<int64_t>(r, L.off_b_idx);
+  out->ep_tn_ld = (int32_t)L.ep_rew;          // == ep_dones == ep_actidx: round_up(T * N, 4)
+  out->ep_t_ld = (int32_t)L.ep_dones_env;     // round_up(T, 4)
   return 0;
 }

@@ -59,7 +59,8 @@ class ParamEntry(C.Structure):
 
 class Batch(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("B", "obs_ld", "share_ld", "act_ld")] +
-                [(n, C.c_void_p) for n in ("obs", "share", "acts", "act_idx", "avail", "rewards", "dones", "dones_env", "weights", "idx")])
+                [(n, C.c_void_p) for n in ("obs", "share", "acts", "act_idx", "avail", "rewards", "dones", "dones_env", "weights", "idx")] +
+                [("ep_tn_ld", C.c_int32), ("ep_t_ld", C.c_int32)])
 
 
 class PolicyStepArgs(C.Structure):

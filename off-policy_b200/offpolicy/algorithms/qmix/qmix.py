@@ -211,9 +211,7 @@ class QMix(object):
         if self._host_batch is None:
             self._host_batch = _HostBatch(self.cfg, self.dev)
         avail = batch[6]["policy_0"] if batch[6] is not None else None
-        if avail is None:
-            raise NotImplementedError("B200 QMIX path: batches without avail_acts must come from the B200 replay buffer")
-        return self._host_batch.pack(batch, "policy_0", True, self.use_per)
+        return self._host_batch.pack(batch, "policy_0", avail is not None, self.use_per)      # MPE: no masks (mpe_runner.py:62)
 
     def train_policy_on_batch(self, batch, update_policy_id=None):
         lib = capi.lib()

@@ -184,3 +184,39 @@ def check_graph_matches_eager(td3, disc, B=4, T=6, E=16, steps=4):
     assert results[0][1] == results[1][1]
     for x, y in zip(results[0][0], results[1][0]):
         assert float((x - y).abs().max()) <= 1e-6 * float(x.abs().max()) + 1e-7
+
+
+def check_replay_batch_equals_host_batch(T=5, B=4, E=9):
+    """The replay's batch region pads every episode row of the per-step fields (rewards / dones / dones_env) to 16 bytes; the
+    learner must index them with the reported episode strides.  T * N = 15 and T = 5 are not multiples of 4 here: training on the
+    device-side sample and on the same sample handed over as NumPy arrays (dense host layout) must give the same update."""
+    import replay_checks as rc
+    from offpolicy.utils.rec_buffer import RecReplayBuffer
+    from oracle.maddpg import MaddpgConfig
+    cfg = MaddpgConfig(act_dim=2, discrete=False, td3=False, actor_update_interval=1, gain=1.0)
+    n, o, a, sdim = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    rs = np.random.RandomState(3)
+    info = {"policy_0": dict(obs_space=[o], share_obs_space=[sdim], act_space=Box(a))}
+    buf = RecReplayBuffer(info, {"policy_0": list(range(n))}, E, T, True, False, rng="numpy", max_batch=max(B, E))
+    de = np.maximum.accumulate((rs.rand(T, E, 1) < 0.2).astype(np.float32), axis=0)
+    ep = [rs.randn(T + 1, E, n, o).astype(np.float32), np.repeat(rs.randn(T + 1, E, 1, sdim).astype(np.float32), n, 2),
+          rs.uniform(-1, 1, (T, E, n, a)).astype(np.float32), np.repeat(rs.randn(T, E, 1, 1).astype(np.float32), n, 2),
+          np.repeat(de[:, :, None], n, 2), de]
+    buf.insert(E, *[rc.d(x) for x in ep], None)
+    outs = []
+    for mode in ("device", "host"):
+        torch.manual_seed(1)
+        args, pol, tr = build(cfg, B, T)
+        init = torch.Generator().manual_seed(11)
+        for vec in (pol.actor_vecs[0], pol.critic_vecs[0]):
+            vec.add_((0.05 * torch.randn(vec.shape, generator=init)).to(vec.device))
+        pol.hard_target_updates()
+        np.random.seed(7)
+        smp = buf.sample(B)
+        if mode == "host":
+            smp = tuple({"policy_0": smp[i]["policy_0"]} for i in range(6)) + (None, None, None)
+        info_t, _, _ = tr.shared_train_policy_on_batch("policy_0", smp)
+        outs.append(([float(info_t["critic_loss"]), float(info_t["actor_loss"])], [v.clone().cpu() for v in pol.actor_vecs[:1] + pol.critic_vecs[:1]]))
+    assert outs[0][0] == outs[1][0], (outs[0][0], outs[1][0])
+    for x, y in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(x, y)

@@ -214,3 +214,41 @@ def compare_step(L, pol, tr, batch, cfg, steps=1, tol=1e-4):
             assert float((v.cpu() - L.tgt_agent.state_dict()[k]).abs().max()) <= 1e-6, (s, k)
 
 
+
+
+def check_mpe_shapes_without_avail_masks(steps=2):
+    """BASELINE configs[0]: scripts/train_mpe_qmix.sh = recurrent QMIX on MPE simple_spread (3 agents, obs 18, Discrete(5), state 54,
+    episode_length 25, batch 32, --use_reward_normalization) -- no available-action masks (runner/rnn/mpe_runner.py:62 passes
+    avail_acts = None).  Replay (reward normalisation on, use_avail_acts False) -> sample -> train, against the oracle replay +
+    oracle learner fed the same episodes and the same NumPy index stream."""
+    import replay_checks as rc
+    from oracle.qmix import QmixConfig, QmixLearner, randomize_all
+    from oracle.replay import UniformReplay
+    N, O, A, S, T, B, E = 3, 18, 5, 54, 25, 32, 48
+    cfg = QmixConfig(n_agents=N, obs_dim=O, act_dim=A, state_dim=S, gain=1.0)
+    L, args, pol, tr = oracle_and_trainer(cfg, B, T, debug=False)
+    buf = rc.make_buffers(N, O, A, S, T, E, norm=True, rng="numpy", max_batch=B, avail=False)
+    ora = UniformReplay(E, T, N, O, S, A, use_avail=False, reward_norm=True, rng=None)
+    rs = np.random.RandomState(4)
+    for n in (30, 10, 20):                      # the third insert wraps the ring: running reward statistics evict
+        de = np.maximum.accumulate((rs.rand(T, n, 1) < 0.05).astype(np.float32), axis=0)
+        ep = [rs.randn(T + 1, n, N, O), np.repeat(rs.randn(T + 1, n, 1, S), N, 2), np.eye(A)[rs.randint(0, A, (T, n, N))],
+              np.repeat(2.0 + rs.randn(T, n, 1, 1), N, 2), np.repeat(de[:, :, None], N, 2), de]
+        ep = [x.astype(np.float32) for x in ep]
+        buf.insert(n, *[rc.d(x) for x in ep], None)
+        ora.insert(n, *ep, None)
+    np.random.seed(21)
+    for s in range(steps):
+        st = np.random.get_state()
+        smp = buf.sample(B)
+        np.random.set_state(st)
+        out, inds = ora.sample(B)
+        assert smp[6]["policy_0"] is None and out[6] is None
+        info, _, _ = tr.train_policy_on_batch(smp)
+        tr.soft_target_updates()
+        ref, _, _ = L.step(tuple(out))
+        L.soft_update()
+        for k in ("loss", "grad_norm", "Q_tot"):
+            assert rel_err(info[k].cpu(), ref[k]) < 1e-4, (s, k, float(info[k]), float(ref[k]))
+    for k, v in pol.q_network.state_dict().items():
+        assert float((v.cpu() - L.agent.state_dict()[k]).abs().max()) <= 5e-3 * cfg.lr * steps + 1e-7, k

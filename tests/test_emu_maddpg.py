@@ -17,3 +17,7 @@ def test_rollout_actions_match_reference(emu_engine, name):
 @pytest.mark.parametrize("td3,disc", [(False, False), (True, True)])
 def test_whole_update_graph_matches_eager(emu_engine, td3, disc):
     mc.check_graph_matches_eager(td3, disc)
+
+
+def test_replay_batch_equals_host_batch_odd_episode_length(emu_engine):
+    mc.check_replay_batch_equals_host_batch()

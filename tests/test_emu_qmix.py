@@ -89,3 +89,7 @@ def test_product_configuration_shapes_vs_oracle(emu_engine, mixer_hidden, hyper_
     w = np.random.RandomState(3).rand(B) * 0.9 + 0.1
     batch = synth_batch(cfg, B, T, seed=9, avail_p=0.6, var_len=True) + (w, np.arange(B))
     qc.compare_step(L, pol, tr, batch, cfg, steps=2)
+
+
+def test_mpe_shapes_without_avail_masks(emu_engine):
+    qc.check_mpe_shapes_without_avail_masks()

@@ -320,3 +320,13 @@ def test_maddpg_rollout_actions_match_reference(gpu_engine, name):
 def test_maddpg_whole_update_graph_matches_eager(gpu_engine, td3, disc):
     import maddpg_checks as mc
     mc.check_graph_matches_eager(td3, disc, B=32, T=25, E=64, steps=4)
+
+
+def test_maddpg_replay_batch_equals_host_batch_odd_episode_length(gpu_engine):
+    mc.check_replay_batch_equals_host_batch()
+
+
+def test_mpe_shapes_without_avail_masks(gpu_engine):
+    """BASELINE configs[0] shapes (train_mpe_qmix.sh): T = 25, 3 agents -> padded episode rows in the batch region, no avail masks,
+    reward normalisation."""
+    qc.check_mpe_shapes_without_avail_masks()
