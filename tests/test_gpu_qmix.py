@@ -323,6 +323,7 @@ def test_maddpg_whole_update_graph_matches_eager(gpu_engine, td3, disc):
 
 
 def test_maddpg_replay_batch_equals_host_batch_odd_episode_length(gpu_engine):
+    import maddpg_checks as mc
     mc.check_replay_batch_equals_host_batch()
 
 
