@@ -175,9 +175,9 @@ typedef struct mx_batch {
   const float* obs;        /* [B][T+1][N][obs_ld]  */
   const float* share;      /* [B][T+1][share_ld]   */
   const float* acts;       /* [B][T][N][act_ld]  one-hot (unused by QMIX when act_idx given) */
-  const int32_t* act_idx;  /* [B][T][N]            argmax of the one-hot action (QMixPolicy.py:89) */
+  const int32_t* act_idx;  /* [B][T][N]            argmax of the one-hot action (QMixPolicy.py:89); episode stride ep_tn_ld */
   const float* avail;      /* [B][T+1][N][act_ld]  or NULL */
-  const float* rewards;    /* [B][T][N]            agent 0's stream is used (qmix.py:159) */
+  const float* rewards;    /* [B][T][N]            agent 0's stream is used (qmix.py:159); episode stride ep_tn_ld */
   const float* dones;      /* [B][T][N]            (unused by QMIX) */
   const float* dones_env;  /* [B][T]               */
   const float* weights;    /* [B] fp32 PER importance weights or NULL */
