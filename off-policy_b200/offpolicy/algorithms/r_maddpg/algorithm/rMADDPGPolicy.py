@@ -131,6 +131,13 @@ class R_MADDPGPolicy(object):
                   self.args.use_orthogonal)
         _init_net(self.critic, self.central_obs_dim + self.central_act_dim, self.hidden_size,
                   [("q_outs.%d" % k, 1, 1.0) for k in range(2 if td3 else 1)], 1.0, self.args.use_orthogonal)
+        # the reference constructs the two target networks like the live ones (rMADDPGPolicy.py:45-46) before overwriting them with
+        # the live weights (:49-50): their initialisation consumes torch's generator, so it is replayed here -- a seeded run then
+        # draws the same warm-up / exploration actions as the reference
+        _init_net(self.target_actor, self.obs_dim, self.hidden_size, [("act.action_out", self.act_dim, self.args.gain)], self.args.gain,
+                  self.args.use_orthogonal)
+        _init_net(self.target_critic, self.central_obs_dim + self.central_act_dim, self.hidden_size,
+                  [("q_outs.%d" % k, 1, 1.0) for k in range(2 if td3 else 1)], 1.0, self.args.use_orthogonal)
         self.actor_vecs[1].copy_(self.actor_vecs[0])          # rMADDPGPolicy.py:49-50
         self.critic_vecs[1].copy_(self.critic_vecs[0])
         self._trainer = None
