@@ -24,6 +24,7 @@ RUNS = {
     "qmix_reward_norm": ("qmix", 150, ["--use_reward_normalization"], True),            # scripts/train_mpe_qmix.sh:14
     "rmaddpg": ("rmaddpg", 150, ["--actor_train_interval_step", "1"], True),
     "rmatd3": ("rmatd3", 150, ["--actor_train_interval_step", "1"], True),
+    "qmix_per": ("qmix", 150, ["--use_per"], False),   # the reference's PER insert raises IndexError for 1-episode inserts (App. D-2): drop-in only
     "vdn": ("vdn", 150, [], False),          # the reference's recurrent VDN mixer is shape-broken: drop-in only
 }
 
