@@ -470,7 +470,9 @@ class RecReplayBuffer(object):
         if self.rng == "device":
             buf.sample_device_uniform(batch_size)
         else:
-            inds = np.random.choice(self.__len__(), batch_size)                              # rec_buffer.py:76
+            # rec_buffer.py:76 draws np.random.choice(len, B); randint(0, len, B) is the same call underneath (same masked-rejection
+            # draws from the global MT19937 stream, same int64 result: tests/test_oracle_rng.py) without choice()'s argument checks
+            inds = np.random.randint(0, self.__len__(), batch_size)
             buf.gather(inds)
         return SampledBatch(self.policy_buffers, batch_size, None, None, p_ids)
 

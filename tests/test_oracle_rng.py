@@ -31,3 +31,17 @@ def test_adopt_numpy_global_state():
     np.random.random(size=17)
     g = LegacyMT19937.from_numpy_global()
     assert np.array_equal(g.choice(5000, 64), np.random.choice(5000, 64))
+
+
+@pytest.mark.parametrize("n", [1, 2, 37, 64, 4096, 5000, 100000])
+def test_randint_is_the_same_draw_as_choice(n):
+    """The drop-in buffer draws `np.random.randint(0, len, B)` where the reference writes `np.random.choice(len, B)`
+    (rec_buffer.py:76): same values, same dtype, same generator state afterwards."""
+    np.random.seed(11)
+    a = np.random.choice(n, 32)
+    sa = np.random.get_state()
+    np.random.seed(11)
+    b = np.random.randint(0, n, 32)
+    sb = np.random.get_state()
+    assert a.dtype == b.dtype and np.array_equal(a, b)
+    assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
