@@ -36,7 +36,11 @@ WORKLOADS = {
     "qmix_3m": (3, 30, 9, 48, 60, 32, False),          # configs[1]: the configuration the metric is quoted on
     "qmix_8m_per": (8, 80, 14, 168, 120, 64, True),    # configs[3]
     "qmix_2s3z": (5, 80, 11, 120, 120, 32, False),     # configs[4]
+    # configs[0]: scripts/train_mpe_qmix.sh = recurrent QMIX on MPE simple_spread (obs 18, Discrete(5), state 54, episode_length 25,
+    # --use_reward_normalization, no available-action masks) -- the reference's own CPU-runnable case
+    "qmix_mpe_spread": (3, 18, 5, 54, 25, 32, False),
 }
+NO_AVAIL = {"qmix_mpe_spread"}       # MPE passes avail_acts = None (runner/rnn/mpe_runner.py:62) and normalises rewards
 
 
 def ncu_traffic(kernel):
@@ -201,11 +205,11 @@ def make_cfg(w):
     return QmixConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, use_per=per, gain=1.0), T, B
 
 
-def synth_episodes(cfg, T, n, rs):
+def synth_episodes(cfg, T, n, rs, avail=True):
     N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
     f = [rs.standard_normal((T + 1, n, N, O), dtype=np.float32), np.repeat(rs.standard_normal((T + 1, n, 1, S), dtype=np.float32), N, 2),
          np.eye(A, dtype=np.float32)[rs.integers(0, A, (T, n, N))], np.repeat(rs.standard_normal((T, n, 1, 1), dtype=np.float32), N, 2),
-         np.zeros((T, n, N, 1), np.float32), np.zeros((T, n, 1), np.float32), np.ones((T + 1, n, N, A), np.float32)]
+         np.zeros((T, n, N, 1), np.float32), np.zeros((T, n, 1), np.float32), np.ones((T + 1, n, N, A), np.float32) if avail else None]
     return f
 
 
@@ -248,7 +252,7 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference learner on the host cores
 # ---------------------------------------------------------------------------------------------------------
-def best_cpu_threads(cfg, T, B, E):
+def best_cpu_threads(cfg, T, B, E, avail=True):
     """The reference sets torch.set_num_threads(n_training_threads); on a many-core host more threads are SLOWER for
     these tiny ops, so the baseline uses the fastest of a few thread counts (probed with 3 timed steps each)."""
     cores = os.cpu_count() or 1
@@ -256,22 +260,22 @@ def best_cpu_threads(cfg, T, B, E):
     for th in sorted({1, 4, 8, 16, min(32, cores)}):
         if th > cores:
             continue
-        sps, _ = cpu_learner_steps_per_s(cfg, T, B, E, 3, 1, th)
+        sps, _ = cpu_learner_steps_per_s(cfg, T, B, E, 3, 1, th, avail)
         if sps > best_sps:
             best, best_sps = th, sps
     return best
 
 
-def cpu_learner_steps_per_s(cfg, T, B, E, steps, warmup, threads):
+def cpu_learner_steps_per_s(cfg, T, B, E, steps, warmup, threads, avail=True):
     from oracle.qmix import QmixLearner
     from oracle.replay import UniformReplay, PrioritizedReplay
     torch.set_num_threads(threads)
     rs = np.random.default_rng(0)
     N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
-    buf = (PrioritizedReplay(0.6, E, T, N, O, S, A) if cfg.use_per else UniformReplay(E, T, N, O, S, A))
+    buf = (PrioritizedReplay(0.6, E, T, N, O, S, A) if cfg.use_per else UniformReplay(E, T, N, O, S, A, use_avail=avail, reward_norm=not avail))
     for c in range(0, E, 64):
         n = min(64, E - c)
-        buf.insert(n, *synth_episodes(cfg, T, n, rs))
+        buf.insert(n, *synth_episodes(cfg, T, n, rs, avail))
     torch.manual_seed(1)
     np.random.seed(1)
     L = QmixLearner(cfg, seed=1)
@@ -298,8 +302,9 @@ def run_reference(args):
         return
     cfg, T, B = make_cfg(args.workload)
     E = min(args.buffer, 1024)
-    cores = best_cpu_threads(cfg, T, B, E)
-    sps, ms = cpu_learner_steps_per_s(cfg, T, B, E, args.steps, args.warmup, cores)
+    avail = args.workload not in NO_AVAIL
+    cores = best_cpu_threads(cfg, T, B, E, avail)
+    sps, ms = cpu_learner_steps_per_s(cfg, T, B, E, args.steps, args.warmup, cores, avail)
     line = dict(metric="learner grad-steps/sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=cfg.n_agents, obs_dim=cfg.obs_dim, act_dim=cfg.act_dim,
@@ -355,10 +360,14 @@ def run_engine(args):
     N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
     E = args.buffer // world if world > 1 else args.buffer            # replay sharded by episode across ranks
     rs = np.random.default_rng(rank)
-    buf = rc.make_buffers(N, O, A, S, T, E, per_alpha=0.6 if cfg.use_per else None, rng="device", max_batch=max(B, 128))
+    avail = args.workload not in NO_AVAIL
+    buf = rc.make_buffers(N, O, A, S, T, E, per_alpha=0.6 if cfg.use_per else None, norm=not avail, rng="device", max_batch=max(B, 128), avail=avail)
+
+    def wrap(ep):
+        return [rc.d(x) if x is not None else None for x in ep]
     for c in range(0, E, 128):
         n = min(128, E - c)
-        buf.insert(n, *[rc.d(x) for x in synth_episodes(cfg, T, n, rs)])
+        buf.insert(n, *wrap(synth_episodes(cfg, T, n, rs, avail)))
     torch.manual_seed(1)
     np.random.seed(1)
     with contextlib.redirect_stdout(sys.stderr):        # the drop-in QMix mirrors the reference's "double Q learning will be used" print
@@ -449,12 +458,12 @@ def run_engine(args):
 
     # ---------------- e2e: host inputs through the drop-in API ----------------
     buf.rng = "numpy"
-    fresh = [synth_episodes(cfg, T, 1, rs) for _ in range(8)]
-    h2d = sum(x.nbytes for x in fresh[0]) + B * 8
+    fresh = [synth_episodes(cfg, T, 1, rs, avail) for _ in range(8)]
+    h2d = sum(x.nbytes for x in fresh[0] if x is not None) + B * 8
     d2h = 4
 
     def e2e_step(i):
-        buf.insert(1, *[rc.d(x) for x in fresh[i % 8]])
+        buf.insert(1, *wrap(fresh[i % 8]))
         if cfg.use_per:
             smp = buf.sample(B, 0.4, "policy_0")
         else:
@@ -484,7 +493,7 @@ def run_engine(args):
     evts = [torch.cuda.Event(), torch.cuda.Event()]
 
     def e2e_step_lagged(i):
-        buf.insert(1, *[rc.d(x) for x in fresh[i % 8]])
+        buf.insert(1, *wrap(fresh[i % 8]))
         smp = buf.sample(B, 0.4, "policy_0") if cfg.use_per else buf.sample(B)
         info, prio, idx = tr.train_policy_on_batch(smp)
         if cfg.use_per:
@@ -562,9 +571,9 @@ def run_engine(args):
     # ---------------- CPU baseline (bounded sample) ----------------
     Ecpu = min(args.buffer, 1024)
     n_cpu = 20 if args.workload == "qmix_3m" else 5
-    cores = best_cpu_threads(cfg, T, B, Ecpu)
-    sps_all, ms_all = cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, cores)
-    sps_one, ms_one = (sps_all, ms_all) if cores == 1 else cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, 1)
+    cores = best_cpu_threads(cfg, T, B, Ecpu, avail)
+    sps_all, ms_all = cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, cores, avail)
+    sps_one, ms_one = (sps_all, ms_all) if cores == 1 else cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, 1, avail)
     best = max(sps_all, sps_one)
 
     value = world * 1000.0 / ms_step
