@@ -20,9 +20,10 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "offpolicy",
 
 RUNS = {
     # name: (algorithm, env steps, extra reference flags, compare against the pure reference?)
-    "qmix": ("qmix", 200, [], True),
+    # also exercises the runner's periodic evaluation (greedy rollouts) and checkpoint saving (state_dict -> torch.save)
+    "qmix": ("qmix", 200, ["--save_interval", "50", "--use_eval", "--eval_interval", "75", "--num_eval_episodes", "2"], True),
     "qmix_reward_norm": ("qmix", 150, ["--use_reward_normalization"], True),            # scripts/train_mpe_qmix.sh:14
-    "rmaddpg": ("rmaddpg", 150, ["--actor_train_interval_step", "1"], True),
+    "rmaddpg": ("rmaddpg", 150, ["--actor_train_interval_step", "1", "--save_interval", "50"], True),
     "rmatd3": ("rmatd3", 150, ["--actor_train_interval_step", "1"], True),
     "qmix_per": ("qmix", 150, ["--use_per"], False),   # the reference's PER insert raises IndexError for 1-episode inserts (App. D-2): drop-in only
     "vdn": ("vdn", 150, [], False),          # the reference's recurrent VDN mixer is shape-broken: drop-in only
