@@ -22,7 +22,9 @@ RUNS = {
     # name: (algorithm, env steps, extra reference flags, compare against the pure reference?)
     # also exercises the runner's periodic evaluation (greedy rollouts) and checkpoint saving (state_dict -> torch.save)
     "qmix": ("qmix", 200, ["--save_interval", "50", "--use_eval", "--eval_interval", "75", "--num_eval_episodes", "2"], True),
-    "qmix_reward_norm": ("qmix", 150, ["--use_reward_normalization"], True),            # scripts/train_mpe_qmix.sh:14
+    # scripts/train_mpe_qmix.sh:14 normalises rewards; `--use_soft_update` is a store_false flag, i.e. HARD target updates every
+    # hard_update_interval_episode episodes like the shipped train_smac_qmix.sh
+    "qmix_reward_norm": ("qmix", 150, ["--use_reward_normalization", "--use_soft_update", "--hard_update_interval_episode", "2"], True),
     "rmaddpg": ("rmaddpg", 150, ["--actor_train_interval_step", "1", "--save_interval", "50"], True),
     "rmatd3": ("rmatd3", 150, ["--actor_train_interval_step", "1"], True),
     "qmix_per": ("qmix", 150, ["--use_per"], False),   # the reference's PER insert raises IndexError for 1-episode inserts (App. D-2): drop-in only
