@@ -176,7 +176,7 @@ def test_sample_train_end_to_end_and_graph_replay(gpu_engine):
             g.synchronize()
             g.close()
         results.append((tr.theta.clone(), tr.theta_tgt.clone(), tr.adam_m.clone()))
-    # same kernels, same order; shared-memory float atomics inside two kernels make the last bits scheduling-dependent
+    # same kernels, same order (the step is deterministic since r01m; the bound predates that and is kept loose on purpose)
     for a, b in zip(results[0], results[1]):
         assert float((a - b).abs().max()) <= 1e-6 * float(a.abs().max()) + 1e-7
 
