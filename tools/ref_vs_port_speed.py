@@ -12,7 +12,6 @@ from oracle.qmix import QmixConfig
 threads = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 cfg, T, B = bench.make_cfg("qmix_3m")
 E, steps, warm = 256, 12, 3
-port_sps, _ = bench.cpu_learner_steps_per_s(cfg, T, B, E, steps, warm, threads)
 
 import ref_harness as rh
 rh.import_reference()
@@ -28,14 +27,23 @@ rs = np.random.default_rng(0)
 d = lambda x: {"policy_0": x}
 for c in range(0, E, 64):
     buf.insert(64, *[d(x) for x in bench.synth_episodes(cfg, T, 64, rs)])
-times = []
-for s in range(warm + steps):
-    t0 = time.perf_counter()
-    smp = buf.sample(B)
-    info_t, _, _ = tr.train_policy_on_batch(smp)
-    tr.soft_target_updates()
-    float(info_t["loss"])
-    if s >= warm:
-        times.append(time.perf_counter() - t0)
-ref_sps = 1.0 / float(np.median(times))
+def ref_run():
+    times = []
+    for s in range(warm + steps):
+        t0 = time.perf_counter()
+        smp = buf.sample(B)
+        info_t, _, _ = tr.train_policy_on_batch(smp)
+        tr.soft_target_updates()
+        float(info_t["loss"])
+        if s >= warm:
+            times.append(time.perf_counter() - t0)
+    return 1.0 / float(np.median(times))
+
+
+# the container is shared and noisy: alternate the two arms three times and keep each arm's best median
+ref_sps = port_sps = 0.0
+for rep in range(3):
+    port_sps = max(port_sps, bench.cpu_learner_steps_per_s(cfg, T, B, E, steps, warm, threads)[0])
+    torch.set_num_threads(threads)
+    ref_sps = max(ref_sps, ref_run())
 print(json.dumps(dict(workload="qmix_3m", threads=threads, reference_steps_per_s=ref_sps, oracle_port_steps_per_s=port_sps, port_over_reference=port_sps / ref_sps)))
