@@ -151,6 +151,8 @@ typedef struct mx_qmix_cfg {
   int32_t world_size;        /* data-parallel ranks (1 = single GPU)               */
   float gamma, huber_delta, per_nu, per_eps;
   float lr, adam_beta1, adam_beta2, adam_eps, max_grad_norm, tau;
+  int32_t prev_act_inp;      /* --prev_act_inp (config.py:81): the agent net's input is [obs | previous one-hot action]
+                                (QMixPolicy.py:29,54-58; qmix.py:122-127: zeros at t = 0, then the buffer's actions) */
 } mx_qmix_cfg;
 
 typedef struct mx_param_entry {

@@ -351,6 +351,39 @@ __global__ void __launch_bounds__(256) k_qhead(QHeadArgs a) {
 }
 
 // =====================================================================================================
+// --prev_act_inp: network input rows [obs | previous one-hot action]
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_pack_prev_act(const float* __restrict__ obs, int obs_ld, const float* __restrict__ acts, int act_ld,
+                                                       float* __restrict__ X, int ldx, int B, int T, int N, int O, int A) {
+  const long long total = (long long)B * (T + 1) * N * ldx;
+  MX_PDL_WAIT();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ldx);
+    const long long m = i / ldx;
+    const int n = (int)(m % N);
+    const long long bt = m / N;
+    const int t = (int)(bt % (T + 1));
+    const long long b = bt / (T + 1);
+    float v = 0.f;
+    if (c < O) v = obs[m * obs_ld + c];
+    else if (c < O + A && t > 0) v = acts[((b * T + (t - 1)) * N + n) * act_ld + (c - O)];     // zeros at t = 0 (qmix.py:122)
+    X[i] = v;
+  }
+}
+
+int mx_launch_pack_prev_act(const float* obs, int obs_ld, const float* acts, int act_ld, float* X, int ldx, int B, int T, int N, int O, int A,
+                            cudaStream_t s) {
+  const long long total = (long long)B * (T + 1) * N * ldx;
+  int grid = (int)((total + 255) / 256);
+  const int cap = mx_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  MX_LAUNCH_PDL(k_pack_prev_act, dim3(grid), dim3(256), 0, s, obs, obs_ld, acts, act_ld, X, ldx, B, T, N, O, A);
+  MX_COUNT();
+  MX_MARK("k_pack_prev_act", s);
+  return MX_CHECK_LAUNCH("pack_prev_act");
+}
+
+// =====================================================================================================
 // launchers
 // =====================================================================================================
 size_t mx_front_fwd_smem(int in_dim, int RM) {

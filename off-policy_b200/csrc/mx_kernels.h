@@ -18,6 +18,10 @@ int mx_launch_tc_prep_weights(const float* const theta[2], const MxNetLayout& L,
 size_t mx_front_fwd_smem(int in_dim, int RM);
 int mx_launch_front_fwd(const FrontFwdArgs& a, int nets, cudaStream_t s);
 
+// prev_act_inp: X[m] = [obs[m] | acts[b][t-1][n]] (zeros at t = 0) for m = (b (T+1) + t) N + n   (qmix.py:122-127)
+int mx_launch_pack_prev_act(const float* obs, int obs_ld, const float* acts, int act_ld, float* X, int ldx, int B, int T, int N, int O, int A,
+                            cudaStream_t s);
+
 struct GruFwdArgs {
   const float* theta[2];
   int whh, bhh;

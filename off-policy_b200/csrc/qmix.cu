@@ -59,8 +59,10 @@ static int check_cfg(const mx_qmix_cfg* c) {
   return 0;
 }
 
+static inline int agent_in_dim(const mx_qmix_cfg* c) { return c->obs_dim + (c->prev_act_inp ? c->act_dim : 0); }
+
 static void layouts(const mx_qmix_cfg* c, MxNetLayout* A, MxMixLayout* M, int64_t* P) {
-  mx_net_layout(c->obs_dim, c->act_dim, 0, A);
+  mx_net_layout(agent_in_dim(c), c->act_dim, 0, A);
   memset(M, 0, sizeof(*M));
   M->size = 0;
   if (!c->vdn) mx_mix_layout(c->state_dim, c->n_agents, c->mixer_hidden, c->hyper_hidden, c->hyper_layers, A->size, M);
@@ -79,7 +81,7 @@ extern "C" int mx_qmix_param_layout(const mx_qmix_cfg* c, mx_param_entry* out, i
     e.offset = off; e.rows = rows; e.cols = cols;
     v.push_back(e);
   };
-  const int H = MX_H, I = c->obs_dim, Aq = c->act_dim;
+  const int H = MX_H, I = agent_in_dim(c), Aq = c->act_dim;
   add("agent.rnn.feature_norm.weight", A.fn_g, I, 0); add("agent.rnn.feature_norm.bias", A.fn_b, I, 0);
   add("agent.rnn.mlp.fc1.0.weight", A.w1, H, I); add("agent.rnn.mlp.fc1.0.bias", A.b1, H, 0);
   add("agent.rnn.mlp.fc1.2.weight", A.ln1_g, H, 0); add("agent.rnn.mlp.fc1.2.bias", A.ln1_b, H, 0);
@@ -137,7 +139,8 @@ static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W
   W->spart = tk((int64_t)npart * 8);
   W->adam_t = tk(8);
   W->normpart = tk(mx_grad_reduce_blocks(P));
-  W->tcimg[0] = tk((int64_t)mx_tc_image_floats(c->obs_dim)); W->tcimg[1] = tk((int64_t)mx_tc_image_floats(c->obs_dim));
+  W->tcimg[0] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c))); W->tcimg[1] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c)));
+  W->xin = tk(c->prev_act_inp ? M * mx_round_up(agent_in_dim(c), 4) : 0);
   {
     const int64_t gH = mx_round_up(c->hyper_hidden, 4), gM = mx_round_up(c->mixer_hidden, 4), gP = mx_round_up(c->n_agents * c->mixer_hidden, 4);
     const int64_t En = c->vdn ? 0 : E;
@@ -288,7 +291,7 @@ static int launch_prep(mx_qmix* q, cudaStream_t s) {
 // overlaps the index draw and the gather.  Optional: mx_qmix_backward_only does it itself when this was not called.
 int mx_qmix_prefork(mx_qmix* q, int B, void* stream) {
 #if !MX_EMU
-  if (!use_overlap(q, B) || !(g_mx_front_tc && q->cfg.obs_dim <= 64) || q->prep_pending) return 0;
+  if (!use_overlap(q, B) || !(g_mx_front_tc && q->agent.in_dim <= 64) || q->prep_pending) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   fork_to_side(q, q->ev_fork, s);
   if (launch_prep(q, q->side)) return 1;
@@ -334,14 +337,22 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   mx.d_q = ws + W.d_q; mx.d_hp = ws + W.d_hp; mx.d_p2 = ws + W.d_p2; mx.d_p1 = ws + W.d_p1;
   mx.gH = mx_round_up(c.hyper_hidden, 4); mx.gM = mx_round_up(c.mixer_hidden, 4); mx.gP = mx_round_up(c.n_agents * c.mixer_hidden, 4);
 
+  const float* X = b->obs;
+  int ldx = b->obs_ld;
+  if (c.prev_act_inp) {       // network input = [obs | previous action]: packed once per step into the workspace
+    if (!b->acts) { mx_set_error("qmix step: prev_act_inp needs the batch's one-hot actions"); return 1; }
+    ldx = mx_round_up(c.obs_dim + c.act_dim, 4);
+    if (mx_launch_pack_prev_act(b->obs, b->obs_ld, b->acts, b->act_ld, ws + W.xin, ldx, B, T, N, c.obs_dim, c.act_dim, s)) return 1;
+    X = ws + W.xin;
+  }
   FrontFwdArgs ff;
   memset(&ff, 0, sizeof(ff));
-  ff.X = b->obs; ff.ldx = b->obs_ld; ff.M = M; ff.feature_norm = 1;
+  ff.X = X; ff.ldx = ldx; ff.M = M; ff.feature_norm = 1;
   ff.theta[0] = q->theta; ff.theta[1] = q->theta_tgt; ff.L = q->agent;
   ff.gi[0] = ws + W.gi[0]; ff.gi[1] = ws + W.gi[1];
   ff.u1 = ws + W.u1; ff.u2 = ws + W.u2; ff.st0 = ws + W.st0; ff.st1 = ws + W.st1; ff.st2 = ws + W.st2;
 #if !MX_EMU
-  if (g_mx_front_tc && c.obs_dim <= 64) {       // weights changed in the last Adam / Polyak: rebuild the TF32 hi/lo images (18k elements per net)
+  if (g_mx_front_tc && q->agent.in_dim <= 64) {       // weights changed in the last Adam / Polyak: rebuild the TF32 hi/lo images (18k elements per net)
     if (q->prep_pending) {                      // mx_qmix_prefork() launched it on the side branch before the batch was sampled
       cudaStreamWaitEvent(s, q->ev_prep, 0);
       q->prep_pending = 0;
@@ -425,7 +436,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
 
   FrontBwdArgs fb;
   memset(&fb, 0, sizeof(fb));
-  fb.X = b->obs; fb.ldx = b->obs_ld; fb.M = M; fb.T = T; fb.N = N; fb.feature_norm = 1;
+  fb.X = X; fb.ldx = ldx; fb.M = M; fb.T = T; fb.N = N; fb.feature_norm = 1;
   fb.theta = q->theta; fb.L = q->agent; fb.u1 = ff.u1; fb.u2 = ff.u2; fb.st0 = ff.st0; fb.st1 = ff.st1; fb.st2 = ff.st2;
   fb.dgi = gb.dgi; fb.gates = gf.gates; fb.hall = gf.hall[0]; fb.gpart = mx.gpart; fb.P = q->P;
   if (mx_launch_front_bwd(fb, &parts[0], s)) return 1;

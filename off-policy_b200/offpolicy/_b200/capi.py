@@ -42,7 +42,7 @@ class QmixCfg(C.Structure):
                                           "hyper_layers", "episode_len", "max_batch", "vdn", "double_q", "use_huber", "use_per",
                                           "use_avail", "world_size")] +
                 [(n, C.c_float) for n in ("gamma", "huber_delta", "per_nu", "per_eps", "lr", "adam_beta1", "adam_beta2", "adam_eps",
-                                          "max_grad_norm", "tau")])
+                                          "max_grad_norm", "tau")] + [("prev_act_inp", C.c_int32)])
 
 
 class MaddpgCfg(C.Structure):

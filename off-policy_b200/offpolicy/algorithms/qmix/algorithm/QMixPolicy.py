@@ -25,7 +25,8 @@ def qmix_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, ma
         episode_len=episode_len, max_batch=max_batch, vdn=int(vdn), double_q=int(args.use_double_q),
         use_huber=int(args.use_huber_loss), use_per=int(args.use_per), use_avail=int(use_avail), world_size=world_size,
         gamma=args.gamma, huber_delta=args.huber_delta, per_nu=args.per_nu, per_eps=args.per_eps, lr=args.lr,
-        adam_beta1=0.9, adam_beta2=0.999, adam_eps=args.opti_eps, max_grad_norm=args.max_grad_norm, tau=args.tau)
+        adam_beta1=0.9, adam_beta2=0.999, adam_eps=args.opti_eps, max_grad_norm=args.max_grad_norm, tau=args.tau,
+        prev_act_inp=int(bool(getattr(args, "prev_act_inp", False))))
 
 
 def param_entries(cfg):
@@ -52,14 +53,13 @@ class QMixPolicy(object):
         self.central_obs_dim = policy_config["cent_obs_dim"]
         self.discrete = is_discrete(self.act_space)
         self.multidiscrete = False
-        if getattr(self.args, "prev_act_inp", False):
-            raise NotImplementedError("B200 QMIX path: --prev_act_inp is not implemented")
+        self.prev_act_inp = bool(getattr(self.args, "prev_act_inp", False))
         for flag, want in (("use_rnn_layer", True), ("use_feature_normalization", True), ("use_ReLU", True), ("use_conv1d", False)):
             if getattr(self.args, flag, want) != want:
                 raise NotImplementedError("B200 QMIX path requires %s=%s" % (flag, want))
         if getattr(self.args, "layer_N", 1) != 1 or getattr(self.args, "recurrent_N", 1) != 1:
             raise NotImplementedError("B200 QMIX path requires layer_N=1, recurrent_N=1")
-        self.q_network_input_dim = self.obs_dim
+        self.q_network_input_dim = self.obs_dim + self.act_dim if self.prev_act_inp else self.obs_dim       # QMixPolicy.py:29-32
 
         capi.lib()
         self.dev = capi.device()
@@ -69,7 +69,7 @@ class QMixPolicy(object):
         self._entries = entries
         flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.q_network = FlatModule(flat, entries, "agent.")
-        init = reference_style_init(entries, dict(hidden=self.hidden_size, obs_dim=self.obs_dim, act_dim=self.act_dim),
+        init = reference_style_init(entries, dict(hidden=self.hidden_size, obs_dim=self.q_network_input_dim, act_dim=self.act_dim),
                                     gain=self.args.gain, use_orthogonal=self.args.use_orthogonal)
         self.q_network.load_state_dict({k[len("agent."):]: v for k, v in init.items()})
         self._roll = None
@@ -84,10 +84,12 @@ class QMixPolicy(object):
     def _stepper(self):
         if self._roll is None:
             from offpolicy._b200.rollout import PolicyStepper
-            self._roll = PolicyStepper(self.obs_dim, self.act_dim)
+            self._roll = PolicyStepper(self.q_network_input_dim, self.act_dim)
         return self._roll
 
-    def _step(self, obs, rnn_states, available_actions=None):
+    def _step(self, obs, rnn_states, available_actions=None, prev_actions=None):
+        if self.prev_act_inp:                                                          # QMixPolicy.py:54-58
+            obs = np.concatenate((obs, np.asarray(prev_actions, dtype=np.float32)), axis=-1)
         return self._stepper().step(self._theta(), obs, rnn_states, available_actions)
 
     def get_q_values(self, obs_batch, prev_action_batch, rnn_states, action_batch=None):
@@ -95,12 +97,13 @@ class QMixPolicy(object):
         obs = np.asarray(obs_batch, dtype=np.float32)
         if obs.ndim == 3:
             qs, h = [], rnn_states
+            pa = None if prev_action_batch is None else np.asarray(prev_action_batch, dtype=np.float32)
             for t in range(obs.shape[0]):
-                q, h, _, _ = self._step(obs[t], h)
+                q, h, _, _ = self._step(obs[t], h, prev_actions=None if pa is None else pa[t])
                 qs.append(q)
             q = torch.from_numpy(np.stack(qs))
         else:
-            q, h, _, _ = self._step(obs, rnn_states)
+            q, h, _, _ = self._step(obs, rnn_states, prev_actions=prev_action_batch)
             q = torch.from_numpy(q)
         if action_batch is not None:
             q = self.q_values_from_actions(q, action_batch)
@@ -118,7 +121,7 @@ class QMixPolicy(object):
             q, h = self.get_q_values(obs, prev_actions, rnn_states)
             onehot_actions, greedy_Qs = self.actions_from_q(q, available_actions=available_actions, explore=explore, t_env=t_env)
             return onehot_actions, h, greedy_Qs
-        _, h, greedy, greedy_q = self._step(obs, rnn_states, available_actions)
+        _, h, greedy, greedy_q = self._step(obs, rnn_states, available_actions, prev_actions)
         greedy_Qs = torch.from_numpy(greedy_q)
         if explore:
             actions = self._eps_greedy(greedy, available_actions, t_env)

@@ -113,7 +113,7 @@ class QMix(object):
         if not self.vdn:
             init = reference_style_init([e for e in entries if e[0].startswith("mixer.")],
                                         dict(state_dim=pol.central_obs_dim, n_agents=num_agents, mixer_hidden=args.mixer_hidden_dim,
-                                             hyper_hidden=args.hypernet_hidden_dim, hidden=args.hidden_size, obs_dim=pol.obs_dim,
+                                             hyper_hidden=args.hypernet_hidden_dim, hidden=args.hidden_size, obs_dim=pol.q_network_input_dim,
                                              act_dim=pol.act_dim), gain=1.0, use_orthogonal=args.use_orthogonal,
                                         hyper_layers=args.hypernet_layers)
             self.mixer.load_state_dict({k[len("mixer."):]: v for k, v in init.items()})

@@ -49,6 +49,7 @@ class QmixConfig:
     per_eps: float = 1e-6
     vdn: bool = False
     feature_norm: bool = True
+    prev_act_inp: bool = False     # config.py:81: agent-net input = [obs | previous one-hot action] (QMixPolicy.py:29,54-58)
     gain: float = 0.01
 
 
@@ -204,7 +205,8 @@ class QmixLearner(object):
 
     def __init__(self, cfg, seed=1):
         self.cfg = cfg
-        self.agent = init_like_reference(AgentNet(cfg), cfg, seed)
+        in_dim = cfg.obs_dim + cfg.act_dim if cfg.prev_act_inp else cfg.obs_dim
+        self.agent = init_like_reference(AgentNet(cfg, in_dim=in_dim), cfg, seed)
         self.mixer = VDNMixerNet() if cfg.vdn else init_like_reference(QMixerNet(cfg), cfg, seed + 1)
         self.sync_targets()
         self.params = list(self.agent.parameters()) + list(self.mixer.parameters())   # qmix.py:66-72
@@ -231,6 +233,8 @@ class QmixLearner(object):
         x = self.stack_agents(obs)
         a = self.stack_agents(acts)
         av = self.stack_agents(avail) if avail is not None else None
+        if cfg.prev_act_inp:        # zeros at t = 0, then the buffer's actions (qmix.py:122-127)
+            x = torch.cat((x, torch.cat((torch.zeros(1, a.shape[1], a.shape[2]), a), 0)), -1)
 
         q_all, _ = self.agent(x)                                   # (T+1, N*B, A)
         a_idx = a.max(dim=-1)[1]

@@ -93,3 +93,9 @@ def test_product_configuration_shapes_vs_oracle(emu_engine, mixer_hidden, hyper_
 
 def test_mpe_shapes_without_avail_masks(emu_engine):
     qc.check_mpe_shapes_without_avail_masks()
+
+
+@pytest.mark.parametrize("debug", [True, False])
+def test_prev_act_inp_matches_reference_golden(emu_engine, debug):
+    """--prev_act_inp (config.py:81): the agent net reads [obs | previous one-hot action]; golden made by the reference with the flag."""
+    qc.check_step_against(None, "qmix_small_prev_act", intermediates=False, debug=debug)

@@ -26,6 +26,9 @@ RUNS = {
     # scripts/train_mpe_qmix.sh:14 normalises rewards; `--use_soft_update` is a store_false flag, i.e. HARD target updates every
     # hard_update_interval_episode episodes like the shipped train_smac_qmix.sh
     "qmix_reward_norm": ("qmix", 150, ["--use_reward_normalization", "--use_soft_update", "--hard_update_interval_episode", "2"], True),
+    # network input [obs | previous action]; the reference's own rollout path raises with this flag (QMixPolicy.py:54-58 concatenates a
+    # NumPy observation with a tensor), so only its learner is pinned (golden qmix_small_prev_act) and the runner runs on the drop-in
+    "qmix_prev_act": ("qmix", 150, ["--prev_act_inp"], False),
     "rmaddpg": ("rmaddpg", 150, ["--actor_train_interval_step", "1", "--save_interval", "50"], True),
     "rmatd3": ("rmatd3", 150, ["--actor_train_interval_step", "1"], True),
     "qmix_per": ("qmix", 150, ["--use_per"], False),   # the reference's PER insert raises IndexError for 1-episode inserts (App. D-2): drop-in only
