@@ -216,7 +216,7 @@ def compare_step(L, pol, tr, batch, cfg, steps=1, tol=1e-4):
 
 
 
-def check_mpe_shapes_without_avail_masks(steps=2):
+def check_mpe_shapes_without_avail_masks(steps=2, B=32):
     """BASELINE configs[0]: scripts/train_mpe_qmix.sh = recurrent QMIX on MPE simple_spread (3 agents, obs 18, Discrete(5), state 54,
     episode_length 25, batch 32, --use_reward_normalization) -- no available-action masks (runner/rnn/mpe_runner.py:62 passes
     avail_acts = None).  Replay (reward normalisation on, use_avail_acts False) -> sample -> train, against the oracle replay +
@@ -224,10 +224,10 @@ def check_mpe_shapes_without_avail_masks(steps=2):
     import replay_checks as rc
     from oracle.qmix import QmixConfig, QmixLearner, randomize_all
     from oracle.replay import UniformReplay
-    N, O, A, S, T, B, E = 3, 18, 5, 54, 25, 32, 48
+    N, O, A, S, T, E = 3, 18, 5, 54, 25, 48
     cfg = QmixConfig(n_agents=N, obs_dim=O, act_dim=A, state_dim=S, gain=1.0)
     L, args, pol, tr = oracle_and_trainer(cfg, B, T, debug=False)
-    buf = rc.make_buffers(N, O, A, S, T, E, norm=True, rng="numpy", max_batch=B, avail=False)
+    buf = rc.make_buffers(N, O, A, S, T, E, norm=True, rng="numpy", max_batch=max(B, 32), avail=False)
     ora = UniformReplay(E, T, N, O, S, A, use_avail=False, reward_norm=True, rng=None)
     rs = np.random.RandomState(4)
     for n in (30, 10, 20):                      # the third insert wraps the ring: running reward statistics evict

@@ -92,7 +92,7 @@ def test_product_configuration_shapes_vs_oracle(emu_engine, mixer_hidden, hyper_
 
 
 def test_mpe_shapes_without_avail_masks(emu_engine):
-    qc.check_mpe_shapes_without_avail_masks()
+    qc.check_mpe_shapes_without_avail_masks(steps=1, B=8)       # (the GPU test runs the script's batch of 32, two steps)
 
 
 @pytest.mark.parametrize("debug", [True, False])

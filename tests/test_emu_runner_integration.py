@@ -22,21 +22,21 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "offpolicy",
 RUNS = {
     # name: (algorithm, env steps, extra reference flags, compare against the pure reference?)   [name smac_*: run_smac_like.py]
     # also exercises the runner's periodic evaluation (greedy rollouts) and checkpoint saving (state_dict -> torch.save)
-    "qmix": ("qmix", 200, ["--save_interval", "50", "--use_eval", "--eval_interval", "75", "--num_eval_episodes", "2"], True),
+    "qmix": ("qmix", 150, ["--save_interval", "50", "--use_eval", "--eval_interval", "75", "--num_eval_episodes", "2"], True),
     # scripts/train_mpe_qmix.sh:14 normalises rewards; `--use_soft_update` is a store_false flag, i.e. HARD target updates every
     # hard_update_interval_episode episodes like the shipped train_smac_qmix.sh
-    "qmix_reward_norm": ("qmix", 150, ["--use_reward_normalization", "--use_soft_update", "--hard_update_interval_episode", "2"], True),
+    "qmix_reward_norm": ("qmix", 125, ["--use_reward_normalization", "--use_soft_update", "--hard_update_interval_episode", "2"], True),
     # network input [obs | previous action]; the reference's own rollout path raises with this flag (QMixPolicy.py:54-58 concatenates a
     # NumPy observation with a tensor), so only its learner is pinned (golden qmix_small_prev_act) and the runner runs on the drop-in
-    "qmix_prev_act": ("qmix", 150, ["--prev_act_inp"], False),
-    "rmaddpg": ("rmaddpg", 150, ["--actor_train_interval_step", "1", "--save_interval", "50"], True),
-    "rmatd3": ("rmatd3", 150, ["--actor_train_interval_step", "1"], True),
-    "qmix_per": ("qmix", 150, ["--use_per"], False),   # the reference's PER insert raises IndexError for 1-episode inserts (App. D-2): drop-in only
-    "vdn": ("vdn", 150, [], False),          # the reference's recurrent VDN mixer is shape-broken: drop-in only
+    "qmix_prev_act": ("qmix", 100, ["--prev_act_inp"], False),
+    "rmaddpg": ("rmaddpg", 125, ["--actor_train_interval_step", "1", "--save_interval", "50"], True),
+    "rmatd3": ("rmatd3", 125, ["--actor_train_interval_step", "1"], True),
+    "qmix_per": ("qmix", 100, ["--use_per"], False),   # the reference's PER insert raises IndexError for 1-episode inserts (App. D-2): drop-in only
+    "vdn": ("vdn", 100, [], False),          # the reference's recurrent VDN mixer is shape-broken: drop-in only
     # offpolicy/runner/rnn/smac_runner.py (scripts/train_smac_qmix.sh) on a synthetic env with the 3m interface: availability masks
     # that change every step (the env asserts no unavailable action is ever chosen), early termination, episode limit 60
-    "smac_qmix": ("qmix", 300, [], True),
-    "smac_qmix_per_hard": ("qmix", 250, ["--use_per", "--use_soft_update", "--hard_update_interval_episode", "2"], False),
+    "smac_qmix": ("qmix", 220, [], True),
+    "smac_qmix_per_hard": ("qmix", 200, ["--use_per", "--use_soft_update", "--hard_update_interval_episode", "2"], False),
 }
 
 
