@@ -20,7 +20,7 @@ def _episodes(cfg, T, n, rs):
 
 def _build(cfg, B, T, E, per, device_rng):
     buf = rc.make_buffers(cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, T, E, per_alpha=0.6 if per else None,
-                          rng="numpy", max_batch=max(B, 8))
+                          rng="numpy", max_batch=max(B, 12))
     torch.manual_seed(2)
     args, pol, tr = qc.build_trainer(cfg, B, T)
     return buf, pol, tr
@@ -39,21 +39,21 @@ def _steps(buf, tr, cfg, B, n, rs, T):
     return out
 
 
-def check_resume(per=False, device_rng=False):
+def check_resume(per=False, device_rng=False, n=3):
     from offpolicy._b200.checkpoint import save_checkpoint, load_checkpoint
     cfg = QmixConfig(n_agents=3, obs_dim=9, act_dim=5, state_dim=11, use_per=per, gain=1.0)
     B, T, E = 4, 6, 12
     buf, pol, tr = _build(cfg, B, T, E, per, device_rng)
     rs = np.random.RandomState(5)
-    buf.insert(8, *_episodes(cfg, T, 8, rs))
+    buf.insert(12 - n, *_episodes(cfg, T, 12 - n, rs))      # so that the steps after the checkpoint wrap the 12-slot ring
     np.random.seed(11)
     if device_rng:
         buf.seed_device_rng(11)
-    _steps(buf, tr, cfg, B, 3, rs, T)                       # ring wraps during these + the next steps (12 slots)
+    _steps(buf, tr, cfg, B, n, rs, T)                       # ring wraps during these + the next steps (12 slots)
     with tempfile.TemporaryDirectory() as d:
         path = save_checkpoint(os.path.join(d, "ck.pt"), tr, buf, extra={"episode": 3})
         rs_state = rs.get_state()
-        want = _steps(buf, tr, cfg, B, 3, rs, T)
+        want = _steps(buf, tr, cfg, B, n, rs, T)
         want_theta = tr.theta.cpu().clone()
         want_tgt = tr.theta_tgt.cpu().clone()
         want_len = len(buf)
@@ -64,7 +64,7 @@ def check_resume(per=False, device_rng=False):
         assert extra == {"episode": 3}
         rs2 = np.random.RandomState(0)
         rs2.set_state(rs_state)
-        got = _steps(buf2, tr2, cfg, B, 3, rs2, T)
+        got = _steps(buf2, tr2, cfg, B, n, rs2, T)
     assert got == want, (got, want)                                   # bit-identical scalars
     assert torch.equal(tr2.theta.cpu(), want_theta) and torch.equal(tr2.theta_tgt.cpu(), want_tgt)
     assert len(buf2) == want_len
