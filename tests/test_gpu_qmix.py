@@ -48,12 +48,6 @@ def test_config2_3m_full_size_product_configuration_vs_oracle(gpu_engine):
     qc.compare_step(L, pol, tr, batch, cfg, steps=3)
 
 
-@pytest.mark.parametrize("debug", [True, False])
-def test_prev_act_inp_matches_reference_golden(gpu_engine, debug):
-    """--prev_act_inp: input width 30 + 9 = 39 (tcgen05 front kernel with K padded to 40)."""
-    qc.check_step_against(None, "qmix_small_prev_act", intermediates=False, debug=debug)
-
-
 _oracle_and_trainer = qc.oracle_and_trainer
 _compare_step = qc.compare_step
 
