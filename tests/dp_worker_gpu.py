@@ -24,7 +24,7 @@ def main():
     g = load_golden("qmix_small")
     L, cfg, B, T, steps = oracle_from_golden(g)
     Bl = B // world
-    args, pol, tr = qc.build_trainer(cfg, Bl, T)
+    args, pol, tr = qc.build_trainer(cfg, Bl, T, debug=False)      # product configuration (k_mid), like bench.py --gpus N
     assert tr.world_size == world
     qc.load_state(pol, tr, sub(g, "init.agent."), sub(g, "init.mixer."), sub(g, "init.tgt_agent."), sub(g, "init.tgt_mixer."))
     res = dict(p2p=int(tr._p2p))

@@ -11,7 +11,11 @@ import qmix_checks as qc
 from helpers import load_golden, oracle_from_golden, golden_batch, sub
 
 
-def test_two_rank_peer_memory_exchange_equals_single_batch_reference(emu_engine):
+import pytest
+
+
+@pytest.mark.parametrize("debug", [True, False])      # False = the product configuration (k_mid), what bench.py --gpus N runs
+def test_two_rank_peer_memory_exchange_equals_single_batch_reference(emu_engine, debug):
     capi = emu_engine
     lib = capi.lib()
     g = load_golden("qmix_small")
@@ -19,7 +23,7 @@ def test_two_rank_peer_memory_exchange_equals_single_batch_reference(emu_engine)
     world, Bl = 2, B // 2
     ranks = []
     for r in range(world):
-        args, pol, tr = qc.build_trainer(cfg, Bl, T, dp_world_size=world)
+        args, pol, tr = qc.build_trainer(cfg, Bl, T, debug=debug, dp_world_size=world)
         assert tr.world_size == world and not tr._p2p
         qc.load_state(pol, tr, sub(g, "init.agent."), sub(g, "init.mixer."), sub(g, "init.tgt_agent."), sub(g, "init.tgt_mixer."))
         ranks.append((pol, tr))
