@@ -11,8 +11,12 @@
  *   - every function returns 0 on success, non-zero on error; mx_last_error() gives the message
  *     (the reference signals errors with Python asserts/exceptions; the Python mirror re-raises).
  *   - nothing here allocates device memory: the caller owns every device buffer (sizes come from the
- *     *_layout / *_bytes queries, which need no GPU) and passes raw device pointers.
- *   - every launch goes to the cudaStream_t given (as void*), is asynchronous and never synchronises.
+ *     *_layout / *_bytes queries, which need no GPU) and passes raw device pointers.  (A learner handle
+ *     owns one non-blocking CUDA stream + a few events: kernels that do not depend on the agent nets run
+ *     on that forked branch, ordered against the caller's stream by events -- parallel graph branches
+ *     under stream capture.)
+ *   - every launch is ordered on the cudaStream_t given (as void*), is asynchronous and never synchronises,
+ *     except the calls documented as synchronising (mx_replay_restore, mx_replay_get_rng_state, mx_profile_end).
  *     Host pointers given to *_async calls must stay valid until the stream reaches that point
  *     (cudaMemcpyAsync rules); use pinned memory for real asynchrony.
  *   - all floating-point data is fp32 unless stated; PER trees are fp64 like the reference
