@@ -167,6 +167,40 @@ class QMix(object):
         torch.cuda.synchronize(self.dev)
         dist.barrier()
         self.attach_peer_blocks(dist.get_rank(), [int(p) for p in hdl.buffer_ptrs], keep=(block, hdl))
+        self._p2p = self._p2p_selftest(block)
+
+    def _p2p_selftest(self, block):
+        """One exchange of a known pattern before the first real step: rank r publishes r + 1 in every element, the reduce must
+        return G (G + 1) / 2 everywhere without a time-out.  Every rank always reaches both barriers (local failures are only
+        recorded), and the caller combines the verdicts with an all-reduce, so a box on which peer loads misbehave falls back to
+        the NCCL exchange on ALL ranks instead of training on garbage."""
+        dist = torch.distributed
+        lib, stream = capi.lib(), capi.stream_ptr()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ok = True
+        adam_t = self.ws_view("adam_t", torch.float64)
+        saved = adam_t.clone()
+        try:
+            self._grad_buf.fill_(float(rank + 1))
+            self._info[7] = 0.0
+            adam_t[0] = 1.0                                   # the kernels take the step number (slot parity, flag value) from here
+            capi.check(lib.mx_qmix_p2p_publish(self.handle, stream))
+            capi.check(lib.mx_qmix_p2p_reduce(self.handle, stream))
+            torch.cuda.synchronize(self.dev)
+            want = world * (world + 1) / 2.0
+            ok = bool((self._grad_buf == want).all().item()) and float(self._info[7]) == 0.0
+        except Exception as ex:
+            sys.stderr.write("marl_b200: peer-memory self-test raised %s\n" % (ex,))
+            ok = False
+        adam_t.copy_(saved)
+        self._grad_buf.zero_()
+        self._info[7] = 0.0
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()                                        # nobody is reading a slot any more
+        block.zero_()                                         # flags back to 0: the first real step is step 1 again
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()
+        return ok
 
     def attach_peer_blocks(self, rank, block_ptrs, keep=None):
         ptrs = (C.c_void_p * len(block_ptrs))(*block_ptrs)
