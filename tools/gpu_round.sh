@@ -1,22 +1,24 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list + full capture of the top kernels.
-# Usage (from the build container):  gpurun --timeout 1700 -- 'bash tools/gpu_round.sh [quick]'
+# One standard GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list + full capture, summaries.
+# Usage (from the build container):  gpurun --timeout 1500 -- 'bash tools/gpu_round.sh <tag> [quick]'
+#   then:  python tools/ncu_summary.py <tag> gpurun_out/launches.csv gpurun_out/prof_<tag>.ncu-rep   (writes profiles/<tag>_ncu_*)
 set -u
+TAG=${1:-rXX}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+timeout 600 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -n 30 gpurun_out/pytest_gpu.log
-python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -n 3 gpurun_out/smoke.log
-python bench.py --steps 300 --warmup 20 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
-python bench.py --workload qmix_8m_per --steps 100 --warmup 10 --buffer 2000 > gpurun_out/bench_8m.json 2> gpurun_out/bench_8m.err; cat gpurun_out/bench_8m.json; tail -n 3 gpurun_out/bench_8m.err
-if [ "${1:-}" != "quick" ]; then
-  python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+tail -n 12 gpurun_out/pytest_gpu.log
+timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -n 2 gpurun_out/smoke.log
+timeout 300 python bench.py --steps 300 --warmup 20 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cut -c1-300 gpurun_out/bench.json; tail -n 3 gpurun_out/bench.err
+if [ "${2:-}" != "quick" ]; then
+  timeout 200 python bench.py --workload qmix_8m_per --steps 50 --warmup 5 --buffer 2000 > gpurun_out/bench_8m.json 2> gpurun_out/bench_8m.err; cut -c1-200 gpurun_out/bench_8m.json
+  timeout 200 python bench.py --workload qmix_mpe_spread --steps 300 --warmup 20 > gpurun_out/bench_mpe.json 2> gpurun_out/bench_mpe.err; cut -c1-200 gpurun_out/bench_mpe.json
+  timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-200 gpurun_out/bench_ref.json
+  timeout 200 python tools/gather_sweep.py > gpurun_out/gather_sweep.log 2> gpurun_out/gather_sweep.err; cut -c1-200 gpurun_out/gather_sweep.log
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 3 --warmup 3 --buffer 512 > gpurun_out/ncu_launch.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_front_bwd|k_gru_fwd|k_gru_bwd|k_mixer|k_front_fwd|k_gather' -s 20 -c 12 \
-      -o gpurun_out/prof_r01 -f python bench.py --steps 3 --warmup 3 --buffer 512 > gpurun_out/ncu_full.log 2>&1
-  timeout 600 compute-sanitizer --tool memcheck python __graft_entry__.py smoke > gpurun_out/memcheck.log 2>&1; tail -n 5 gpurun_out/memcheck.log
-  timeout 600 compute-sanitizer --tool racecheck python __graft_entry__.py smoke > gpurun_out/racecheck.log 2>&1; tail -n 5 gpurun_out/racecheck.log
+  timeout 500 ncu --set full --clock-control none --import-source on -k regex:'k_' -s 40 -c 16 \
+      -o gpurun_out/prof_$TAG -f python bench.py --steps 3 --warmup 3 --buffer 512 > gpurun_out/ncu_full.log 2>&1
 fi
-ls -la gpurun_out
+ls -la gpurun_out | head -30
