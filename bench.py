@@ -296,6 +296,36 @@ def cpu_learner_steps_per_s(cfg, T, B, E, steps, warmup, threads, avail=True):
     return 1.0 / float(np.median(times)), float(np.median(times)) * 1e3
 
 
+def torch_eager_gpu_steps_per_s(cfg, T, B, E, steps, warmup, avail=True):
+    """Secondary baseline: the reference learner's own eager PyTorch ops on the SAME B200 (what
+    `--cuda` gives the reference): the oracle port with its networks on cuda:0, batches sampled by the NumPy replay on the host and
+    copied up per step like the reference's to_torch(...).to(device).  ~10^4 small ATen launches per step."""
+    from oracle.qmix import QmixLearner
+    from oracle.replay import UniformReplay, PrioritizedReplay
+    rs = np.random.default_rng(0)
+    N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    buf = (PrioritizedReplay(0.6, E, T, N, O, S, A) if cfg.use_per else UniformReplay(E, T, N, O, S, A, use_avail=avail, reward_norm=not avail))
+    for c in range(0, E, 64):
+        n = min(64, E - c)
+        buf.insert(n, *synth_episodes(cfg, T, n, rs, avail))
+    torch.manual_seed(1)
+    np.random.seed(1)
+    L = QmixLearner(cfg, seed=1, device="cuda")
+    times = []
+    for s in range(warmup + steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out, inds = buf.sample(B, 0.4) if cfg.use_per else buf.sample(B)
+        info, prio, _ = L.step(out)
+        if cfg.use_per:
+            buf.update_priorities(inds, prio)
+        L.soft_update()
+        float(info["loss"])
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return 1.0 / float(np.median(times))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -575,6 +605,12 @@ def run_engine(args):
     sps_all, ms_all = cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, cores, avail)
     sps_one, ms_one = (sps_all, ms_all) if cores == 1 else cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, 1, avail)
     best = max(sps_all, sps_one)
+    eager_gpu = None
+    try:        # never let the secondary baseline break the bench line
+        torch.set_num_threads(1)
+        eager_gpu = torch_eager_gpu_steps_per_s(cfg, T, B, Ecpu, 10, 3, avail)
+    except Exception as ex:
+        sys.stderr.write("torch eager GPU baseline skipped: %r\n" % (ex,))
 
     value = world * 1000.0 / ms_step
     line = dict(
@@ -598,6 +634,9 @@ def run_engine(args):
         cpu_baseline=dict(value=best, unit="steps/s", cores=cores if sps_all >= sps_one else 1, host_cores=os.cpu_count(), kind="port",
                           best_threads_steps_per_s=sps_all, one_thread_steps_per_s=sps_one,
                           sample="%d timed steps (sample+train+soft update) of the same workload on a %d-episode replay, oracle port of the reference learner" % (n_cpu, Ecpu)),
+        torch_eager_gpu_baseline=dict(value=eager_gpu, unit="steps/s", kind="port",
+                                      sample="10 timed steps of the oracle port of the reference learner with its networks on cuda:0 (eager PyTorch, "
+                                             "host-side NumPy replay + H2D per step): the reference's own `--cuda` mode on this GPU"),
         clocks=clocks.summary())
     emit(line)
     sys.stdout.flush()

@@ -117,7 +117,7 @@ class AgentNet(nn.Module):
 
     def forward(self, x, h0=None):
         if h0 is None:
-            h0 = torch.zeros(1, x.shape[1], self.hidden, dtype=x.dtype)
+            h0 = torch.zeros(1, x.shape[1], self.hidden, dtype=x.dtype, device=x.device)
         y, hT = self.rnn(x, h0)
         return self.q.action_out(y), hT
 
@@ -203,11 +203,14 @@ class QmixLearner(object):
     as arrays: obs (N,T+1,B,O), share (T+1,B,S), acts (N,T,B,A), rewards (N,T,B,1),
     dones (N,T,B,1), dones_env (T,B,1), avail (N,T+1,B,A) | None, weights (B,) | None, idx | None."""
 
-    def __init__(self, cfg, seed=1):
+    def __init__(self, cfg, seed=1, device="cpu"):
+        """device: "cpu" (parity oracle, CPU baseline) or a CUDA device -- the same eager PyTorch ops the reference issues with
+        `--cuda` (bench.py's secondary baseline)."""
         self.cfg = cfg
+        self.device = torch.device(device)
         in_dim = cfg.obs_dim + cfg.act_dim if cfg.prev_act_inp else cfg.obs_dim
-        self.agent = init_like_reference(AgentNet(cfg, in_dim=in_dim), cfg, seed)
-        self.mixer = VDNMixerNet() if cfg.vdn else init_like_reference(QMixerNet(cfg), cfg, seed + 1)
+        self.agent = init_like_reference(AgentNet(cfg, in_dim=in_dim), cfg, seed).to(self.device)
+        self.mixer = (VDNMixerNet() if cfg.vdn else init_like_reference(QMixerNet(cfg), cfg, seed + 1)).to(self.device)
         self.sync_targets()
         self.params = list(self.agent.parameters()) + list(self.mixer.parameters())   # qmix.py:66-72
         self.opt = torch.optim.Adam(self.params, lr=cfg.lr, eps=cfg.opti_eps)
@@ -217,10 +220,9 @@ class QmixLearner(object):
         self.tgt_mixer = copy.deepcopy(self.mixer)
 
     # -- forward pieces ----------------------------------------------------------
-    @staticmethod
-    def stack_agents(x):
+    def stack_agents(self, x):
         """(N,T,B,D) -> (T, N*B, D), row = n*B + b (qmix.py:108-109)."""
-        x = torch.as_tensor(x, dtype=torch.float32)
+        x = torch.as_tensor(x, dtype=torch.float32).to(getattr(self, "device", "cpu"))
         return torch.cat(list(x), dim=-2)
 
     def loss_terms(self, batch):
@@ -228,13 +230,14 @@ class QmixLearner(object):
         obs, share, acts, rew, _dones, dones_env, avail, weights, _idx = batch
         B = obs.shape[2]
         T = acts.shape[1]
-        s = torch.as_tensor(share, dtype=torch.float32)
-        de = torch.as_tensor(dones_env, dtype=torch.float32)
+        dev = self.device
+        s = torch.as_tensor(share, dtype=torch.float32).to(dev)
+        de = torch.as_tensor(dones_env, dtype=torch.float32).to(dev)
         x = self.stack_agents(obs)
         a = self.stack_agents(acts)
         av = self.stack_agents(avail) if avail is not None else None
         if cfg.prev_act_inp:        # zeros at t = 0, then the buffer's actions (qmix.py:122-127)
-            x = torch.cat((x, torch.cat((torch.zeros(1, a.shape[1], a.shape[2]), a), 0)), -1)
+            x = torch.cat((x, torch.cat((torch.zeros(1, a.shape[1], a.shape[2], device=dev), a), 0)), -1)
 
         q_all, _ = self.agent(x)                                   # (T+1, N*B, A)
         a_idx = a.max(dim=-1)[1]
@@ -250,17 +253,17 @@ class QmixLearner(object):
             tq = torch.cat(tq[1:].split(B, dim=-2), dim=-1)        # (T, B, N)
             q_tot_next = self.tgt_mixer(tq, s[1:])
         q_tot = self.mixer(q_taken, s[:-1])                        # (T, B, 1)
-        r = torch.as_tensor(rew[0], dtype=torch.float32)           # agent 0's stream (qmix.py:159)
-        bad = torch.cat([torch.zeros(1, B, 1), de[:T - 1]], 0)     # qmix.py:161
+        r = torch.as_tensor(rew[0], dtype=torch.float32).to(dev)   # agent 0's stream (qmix.py:159)
+        bad = torch.cat([torch.zeros(1, B, 1, device=dev), de[:T - 1]], 0)     # qmix.py:161
         y = r + (1 - de) * cfg.gamma * q_tot_next
         err = (q_tot - y.detach()) * (1 - bad)
         per_elem = self._huber(err) if cfg.huber else err ** 2
         denom = (1 - bad).sum()
         prio = None
         if cfg.use_per:
-            w = torch.as_tensor(weights, dtype=torch.float32)
+            w = torch.as_tensor(weights, dtype=torch.float32).to(dev)
             loss = (per_elem.sum(dim=0).flatten() * w).sum() / denom
-            td = err.abs().detach().numpy()
+            td = err.abs().detach().cpu().numpy()
             prio = ((1 - cfg.per_nu) * td.mean(axis=0) + cfg.per_nu * td.max(axis=0)).flatten() + cfg.per_eps
         else:
             loss = per_elem.sum() / denom
