@@ -157,6 +157,10 @@ typedef struct mx_qmix_cfg {
   float lr, adam_beta1, adam_beta2, adam_eps, max_grad_norm, tau;
   int32_t prev_act_inp;      /* --prev_act_inp (config.py:81): the agent net's input is [obs | previous one-hot action]
                                 (QMixPolicy.py:29,54-58; qmix.py:122-127: zeros at t = 0, then the buffer's actions) */
+  int32_t mlp;               /* 1: the transition-level (non-recurrent) variant M_QMix / M_VDN (algorithms/mqmix/mqmix.py:67-216): the agent
+                                net is MLPBase + Linear head without a GRU (mqmix/algorithm/agent_q_function.py), a "batch" is B single
+                                transitions stored as episodes of length 1 (step 0 = obs, step 1 = next_obs), episode_len must be 1.
+                                The head occupies the first act_dim rows of the (otherwise zero) weight_ih slot of the flat vector. */
 } mx_qmix_cfg;
 
 typedef struct mx_param_entry {
@@ -303,6 +307,8 @@ typedef struct mx_policy_step_args {
   int32_t* greedy;         /* device [rows] arg-max action under the mask, or NULL                     */
   float* greedy_q;         /* device [rows] its value (the reference's greedy_Qs), or NULL             */
   float* h_copy;           /* optional second destination of the new state [rows][64] (e.g. mapped pinned host memory), or NULL */
+  int32_t mlp;             /* 1: non-recurrent net (M_QMixPolicy.get_actions, mQMixPolicy.py:60-110): MLPBase -> head stored in the
+                              weight_ih slot (see mx_qmix_cfg.mlp); h_in / h_out are ignored (h_out may be NULL) */
 } mx_policy_step_args;
 /* x / avail / out / greedy / greedy_q / h_copy may point into MAPPED PINNED HOST memory (cudaHostAlloc; same address on the
  * device under UVA): the kernel then reads the observation and writes the actions straight over PCIe and one env step costs one

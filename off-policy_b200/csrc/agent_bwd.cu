@@ -329,11 +329,12 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     __syncthreads();
     // ---- stage the tile's raw operands with cp.async: dgi, r gate, u2, u1?, h_{t-1}, the input rows, LN statistics ----
     mx_stage_rows(dgi_s, sm.ldg, a.dgi, MX_G, m0, a.M, TM, MX_G);
-    mx_stage_rows(x_s, sm.ld64, a.gates, MX_G, m0, a.M, TM, MX_H);          // r gate = first 64 columns of the gates row
+    if (!a.no_gru) mx_stage_rows(x_s, sm.ld64, a.gates, MX_G, m0, a.M, TM, MX_H);          // r gate = first 64 columns of the gates row
+    else for (int i = tid; i < TM * sm.ld64; i += MX_TILE_THREADS) x_s[i] = 0.f;
     mx_stage_rows(u_s, sm.ld64, a.u2, MX_H, m0, a.M, TM, MX_H);
     for (int r = tid >> 4; r < TM; r += MX_TILE_THREADS / 16) {
       const int m = m0 + r;
-      const bool has = m < a.M && ((m / N) % T1) > 0;
+      const bool has = !a.no_gru && m < a.M && ((m / N) % T1) > 0;
       float* d = hp_s + r * sm.ld64 + 4 * tx;
       if (has) mx_cp16(d, a.hall + (size_t)(m - N) * MX_H + 4 * tx);
       else if (m < a.M && a.h0) mx_cp16(d, a.h0 + (size_t)m * MX_H + 4 * tx);
@@ -360,13 +361,16 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     if (wg) {
       for (int nb = 0; nb < 3; ++nb) {
         mx_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
+        if (a.no_gru) continue;
         const float* dgh = nb < 2 ? dgi_s + nb * 64 : dgn_s;
         const int ldd = nb < 2 ? sm.ldg : sm.ld64;
         mx_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
       }
       mx_colsum(dgi_s, sm.ldg, TM, MX_G, gp + L.bih, accum);
-      mx_colsum(dgi_s, sm.ldg, TM, 2 * MX_H, gp + L.bhh, accum);
-      mx_colsum(dgn_s, sm.ld64, TM, MX_H, gp + L.bhh + 2 * MX_H, accum);
+      if (!a.no_gru) {
+        mx_colsum(dgi_s, sm.ldg, TM, 2 * MX_H, gp + L.bhh, accum);
+        mx_colsum(dgn_s, sm.ld64, TM, MX_H, gp + L.bhh + 2 * MX_H, accum);
+      }
     }
     // ---- dx2 = dgi . W_ih  (three 64-row chunks) ----
     float v[RM][4];
@@ -531,6 +535,34 @@ int mx_launch_qhead_bwd(const QHeadBwdArgs& a, int* nparts_used, cudaStream_t s)
   MX_MARK("k_qhead_bwd", s);
   *nparts_used = grid;
   return MX_CHECK_LAUNCH("qhead_bwd");
+}
+
+// MLP variant: gradient w.r.t. the "gi" rows = the Q-head outputs: only the taken action of the step-0 rows receives dL/dq
+__global__ void __launch_bounds__(256) k_mlp_dgi(const float* __restrict__ dq_taken, const int32_t* __restrict__ act_idx, int ld_tn,
+                                                 float* __restrict__ dgi, int B, int N) {
+  const long long total = (long long)B * 2 * N * MX_G;
+  MX_PDL_WAIT();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % MX_G);
+    const long long m = i / MX_G;
+    const int n = (int)(m % N);
+    const long long bt = m / N;
+    const int t = (int)(bt & 1);
+    const long long b = bt >> 1;
+    float v = 0.f;
+    if (t == 0 && c == act_idx[b * ld_tn + n]) v = dq_taken[b * N + n];
+    dgi[i] = v;
+  }
+}
+int mx_launch_mlp_dgi(const float* dq_taken, const int32_t* act_idx, int ld_tn, float* dgi, int B, int N, cudaStream_t s) {
+  const long long total = (long long)B * 2 * N * MX_G;
+  int grid = (int)((total + 255) / 256);
+  const int cap = mx_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  MX_LAUNCH_PDL(k_mlp_dgi, dim3(grid), dim3(256), 0, s, dq_taken, act_idx, ld_tn, dgi, B, N);
+  MX_COUNT();
+  MX_MARK("k_mlp_dgi", s);
+  return MX_CHECK_LAUNCH("mlp_dgi");
 }
 
 int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {

@@ -351,6 +351,49 @@ __global__ void __launch_bounds__(256) k_qhead(QHeadArgs a) {
 }
 
 // =====================================================================================================
+// MLP variant (M_QMix, mqmix.py:101-176): Q values are columns [0, A) of the "gi" rows; one thread per (b, n):
+// taken-action Q at step 0, greedy action of the LIVE net at step 1 under next_avail (first maximum), target Q there (double-Q),
+// or the target net's own masked maximum.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_mlp_qselect(MlpQSelArgs a) {
+  const int total = a.B * a.N;
+  MX_PDL_WAIT();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i % a.N, b = i / a.N;
+    const size_t m0 = ((size_t)b * 2) * a.N + n, m1 = m0 + a.N;
+    const float* q0 = a.gi[0] + m0 * MX_G;
+    const float* q1 = a.gi[0] + m1 * MX_G;
+    const float* t1 = a.gi[1] + m1 * MX_G;
+    const int act = a.act_idx[(size_t)b * a.ld_tn + n];
+    int greedy = 0;
+    float best = 0.f, tbest = 0.f;
+    for (int k = 0; k < a.A; ++k) {
+      const bool off = a.avail && a.avail[m1 * a.act_ld + k] == 0.f;
+      const float qm = off ? -1e10f : q1[k];                                                // mqmix.py:147-149
+      if (k == 0 || qm > best) { best = qm; greedy = k; }
+      const float tm = off ? -1e10f : t1[k];               // not double-Q: target_policy.get_actions masks too (mqmix.py:155-160)
+      if (k == 0 || tm > tbest) tbest = tm;
+    }
+    a.q_taken[i] = q0[act];
+    a.q_next[i] = a.double_q ? t1[greedy] : tbest;
+    if (a.greedy) { a.greedy[m0] = 0; a.greedy[m1] = greedy; }
+    if (a.qall0)
+      for (int k = 0; k < a.A; ++k) {
+        a.qall0[m0 * a.A + k] = q0[k]; a.qall0[m1 * a.A + k] = q1[k];
+        a.qall1[m0 * a.A + k] = a.gi[1][m0 * MX_G + k]; a.qall1[m1 * a.A + k] = t1[k];
+      }
+  }
+}
+int mx_launch_mlp_qselect(const MlpQSelArgs& a, cudaStream_t s) {
+  int grid = mx_ceil_div(a.B * a.N, 256);
+  if (grid > mx_num_sms() * 4) grid = mx_num_sms() * 4;
+  MX_LAUNCH_PDL(k_mlp_qselect, dim3(grid), dim3(256), 0, s, a);
+  MX_COUNT();
+  MX_MARK("k_mlp_qselect", s);
+  return MX_CHECK_LAUNCH("mlp_qselect");
+}
+
+// =====================================================================================================
 // --prev_act_inp: network input rows [obs | previous one-hot action]
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k_pack_prev_act(const float* __restrict__ obs, int obs_ld, const float* __restrict__ acts, int act_ld,

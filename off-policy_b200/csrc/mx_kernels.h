@@ -101,6 +101,21 @@ struct MidArgs {
 int mx_mid_supported(const MidArgs& a);
 int mx_launch_mid(const MidArgs& a, int* parts_used, cudaStream_t s);   // parts_used: gradient partials == scalar partials
 
+// ---- transition-level MLP variant (cfg.mlp): the Q head is the first A rows of the W_ih slot, so Q[m][k] = gi[m][k] ----
+struct MlpQSelArgs {
+  const float* gi[2];      // live, target [M][3H]: columns [0, A) are the Q values of row m = (b*2 + t)*N + n
+  const int32_t* act_idx;  // [B][1][N] (episode stride ld_tn)
+  const float* avail;      // [M][act_ld] or null (rows t = 1 = next_avail)
+  int act_ld, ld_tn;
+  int B, N, A, double_q;
+  float *q_taken, *q_next; // [B][N]
+  float *qall0, *qall1;    // debug [M][A] or null
+  int32_t* greedy;         // debug [M] or null
+};
+int mx_launch_mlp_qselect(const MlpQSelArgs& a, cudaStream_t s);
+// dgi[M][3H] = 0 except (row of step 0, column act) = dq_taken[b][n]
+int mx_launch_mlp_dgi(const float* dq_taken, const int32_t* act_idx, int ld_tn, float* dgi, int B, int N, cudaStream_t s);
+
 struct QHeadBwdArgs {
   const float* theta;
   int wq, bq, lno_g, lno_b;
@@ -144,6 +159,7 @@ struct FrontBwdArgs {
   const float* hall;       // [M][H]
   float* gpart;
   long long P;
+  int no_gru;              // 1: MLP variant -- no recurrent weights: gates / hall are not read, dW_hh / db_hh are not produced
   float* dX;               // optional: gradient w.r.t. the input rows [M][ldx] (through the feature LayerNorm)
   int skip_wgrad;          // 1: data gradient only (frozen network)
 };

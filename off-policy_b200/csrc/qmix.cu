@@ -56,6 +56,8 @@ static int check_cfg(const mx_qmix_cfg* c) {
   }
   if (c->act_dim > 32 || c->n_agents > 32) { mx_set_error("mx_qmix: act_dim and n_agents must be <= 32"); return 1; }
   if (!c->vdn && c->hyper_layers != 1 && c->hyper_layers != 2) { mx_set_error("hypernet_layers must be 1 or 2"); return 1; }
+  if (c->mlp && c->episode_len != 1) { mx_set_error("mx_qmix: the MLP (transition-level) variant stores transitions as episodes of length 1"); return 1; }
+  if (c->mlp && c->prev_act_inp) { mx_set_error("mx_qmix: prev_act_inp is a recurrent-policy option"); return 1; }
   return 0;
 }
 
@@ -82,6 +84,17 @@ extern "C" int mx_qmix_param_layout(const mx_qmix_cfg* c, mx_param_entry* out, i
     v.push_back(e);
   };
   const int H = MX_H, I = agent_in_dim(c), Aq = c->act_dim;
+  if (c->mlp) {     // M_QMixPolicy.q_network = AgentQFunction(MLPBase + ACTLayer) (mqmix/algorithm/agent_q_function.py): reference key names;
+                    // the head lives in the first act_dim rows of the weight_ih slot, the remaining recurrent slots stay zero
+    add("agent.mlp.feature_norm.weight", A.fn_g, I, 0); add("agent.mlp.feature_norm.bias", A.fn_b, I, 0);
+    add("agent.mlp.mlp.fc1.0.weight", A.w1, H, I); add("agent.mlp.mlp.fc1.0.bias", A.b1, H, 0);
+    add("agent.mlp.mlp.fc1.2.weight", A.ln1_g, H, 0); add("agent.mlp.mlp.fc1.2.bias", A.ln1_b, H, 0);
+    add("agent.mlp.mlp.fc_h.0.weight", A.wh, H, H); add("agent.mlp.mlp.fc_h.0.bias", A.bh, H, 0);
+    add("agent.mlp.mlp.fc_h.2.weight", A.lnh_g, H, 0); add("agent.mlp.mlp.fc_h.2.bias", A.lnh_b, H, 0);
+    add("agent.mlp.mlp.fc2.0.0.weight", A.w2, H, H); add("agent.mlp.mlp.fc2.0.0.bias", A.b2, H, 0);
+    add("agent.mlp.mlp.fc2.0.2.weight", A.ln2_g, H, 0); add("agent.mlp.mlp.fc2.0.2.bias", A.ln2_b, H, 0);
+    add("agent.q.action_out.weight", A.wih, Aq, H); add("agent.q.action_out.bias", A.bih, Aq, 0);
+  } else {
   add("agent.rnn.feature_norm.weight", A.fn_g, I, 0); add("agent.rnn.feature_norm.bias", A.fn_b, I, 0);
   add("agent.rnn.mlp.fc1.0.weight", A.w1, H, I); add("agent.rnn.mlp.fc1.0.bias", A.b1, H, 0);
   add("agent.rnn.mlp.fc1.2.weight", A.ln1_g, H, 0); add("agent.rnn.mlp.fc1.2.bias", A.ln1_b, H, 0);
@@ -93,6 +106,7 @@ extern "C" int mx_qmix_param_layout(const mx_qmix_cfg* c, mx_param_entry* out, i
   add("agent.rnn.rnn.rnn.bias_ih_l0", A.bih, 3 * H, 0); add("agent.rnn.rnn.rnn.bias_hh_l0", A.bhh, 3 * H, 0);
   add("agent.rnn.rnn.norm.weight", A.lno_g, H, 0); add("agent.rnn.rnn.norm.bias", A.lno_b, H, 0);
   add("agent.q.action_out.weight", A.wq, Aq, H); add("agent.q.action_out.bias", A.bq, Aq, 0);
+  }
   if (!c->vdn) {
     const int S = c->state_dim, N = c->n_agents, ME = c->mixer_hidden, HY = c->hyper_hidden;
     if (c->hyper_layers == 2) {
@@ -364,6 +378,43 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
 #endif
   if (split && overlap) { if (mx_launch_mix_hyper_fwd(mx, side)) return 1; }
   if (mx_launch_front_fwd(ff, 2, s)) return 1;
+
+  if (c.mlp) {      // ---- transition-level variant (M_QMix / M_VDN): no recurrence, Q = columns [0, A) of the "gi" rows ----
+    int parts[4] = {0, 0, 0, 0};
+    MlpQSelArgs qs;
+    memset(&qs, 0, sizeof(qs));
+    qs.gi[0] = ff.gi[0]; qs.gi[1] = ff.gi[1]; qs.act_idx = b->act_idx; qs.avail = b->avail; qs.act_ld = b->act_ld; qs.ld_tn = ld_tn;
+    qs.B = B; qs.N = N; qs.A = c.act_dim; qs.double_q = c.double_q; qs.q_taken = ws + W.q_taken; qs.q_next = ws + W.q_next;
+    qs.qall0 = q->debug ? ws + W.qall[0] : nullptr; qs.qall1 = q->debug ? ws + W.qall[1] : nullptr;
+    qs.greedy = q->debug ? reinterpret_cast<int32_t*>(ws + W.greedy) : nullptr;
+    if (mx_launch_mlp_qselect(qs, s)) return 1;
+    if (split) {
+      if (!overlap) { if (mx_launch_mix_hyper_fwd(mx, s)) return 1; }
+#if !MX_EMU
+      else join_from_side(q, q->ev_hyper, s);
+#endif
+      if (mx_launch_mix_core(mx, &parts[3], s)) return 1;
+#if !MX_EMU
+      if (overlap) fork_to_side(q, q->ev_core, s);
+#endif
+      if (mx_launch_mix_hyper_bwd(mx, &parts[2], side)) return 1;
+    } else {
+      if (mx_launch_mixer(mx, &parts[2], s)) return 1;
+      parts[3] = parts[2];
+    }
+    if (mx_launch_mlp_dgi(mx.dq_taken, b->act_idx, ld_tn, ws + W.dgi, B, N, s)) return 1;
+    FrontBwdArgs fbm;
+    memset(&fbm, 0, sizeof(fbm));
+    fbm.X = X; fbm.ldx = ldx; fbm.M = M; fbm.T = T; fbm.N = N; fbm.feature_norm = 1; fbm.no_gru = 1;
+    fbm.theta = q->theta; fbm.L = q->agent; fbm.u1 = ff.u1; fbm.u2 = ff.u2; fbm.st0 = ff.st0; fbm.st1 = ff.st1; fbm.st2 = ff.st2;
+    fbm.dgi = ws + W.dgi; fbm.gpart = mx.gpart; fbm.P = q->P;
+    if (mx_launch_front_bwd(fbm, &parts[0], s)) return 1;
+#if !MX_EMU
+    if (split && overlap) join_from_side(q, q->ev_hbwd, s);
+#endif
+    OptimArgs om = optim_args(q, B, parts);
+    return mx_launch_grad_reduce(om, s);
+  }
 
   GruFwdArgs gf;
   memset(&gf, 0, sizeof(gf));

@@ -28,6 +28,7 @@ struct RollArgs {
   int32_t* greedy;         // [R] or null
   float* greedy_q;         // [R] or null
   int R;
+  int mlp;                 // non-recurrent net: head = first out_dim rows of the W_ih slot applied to the MLPBase output
 };
 
 // LayerNorm of v[0..n) in shared memory, in place (two-pass, biased variance, eps inside the sqrt like ATen); warp 0 only
@@ -79,6 +80,14 @@ __global__ void __launch_bounds__(MX_ROLL_THREADS) k_policy_step(RollArgs a) {
     }
     __syncthreads();
     roll_layer_norm(v2, MX_H, th + L.ln2_g, th + L.ln2_b);
+    if (a.mlp) {   // M_QMixPolicy: Q = Linear(H, A)(MLPBase(x)); the head sits in the W_ih slot (agent_q_function.py:24-33)
+      const float d = roll_dot4(th + L.wih + (size_t)(u < A ? u : 0) * MX_H, v2, MX_H, q);
+      if (q == 0 && u < A) {
+        const float o = d + th[L.bih + u];
+        qs[u] = o;
+        a.out[(size_t)r * A + u] = o;
+      }
+    } else {
     {   // GRU cell, PyTorch gate order [r; z; n]                                          rnn.py:8, 33-47
       float gi[3], gh[3];
 #pragma unroll
@@ -106,6 +115,7 @@ __global__ void __launch_bounds__(MX_ROLL_THREADS) k_policy_step(RollArgs a) {
         a.out[(size_t)r * A + u] = o;
       }
     }
+    }
     __syncthreads();
     if (tid == 0 && a.greedy) {   // greedy action: unavailable actions forced to -1e10, first maximum wins (util.py:297-302, torch.max)
       int best = 0;
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(MX_ROLL_THREADS) k_policy_step(RollArgs a) {
 }
 
 extern "C" int mx_policy_step(const mx_policy_step_args* p, void* stream) {
-  if (!p || !p->theta || !p->x || !p->h_out || !p->out) { mx_set_error("mx_policy_step: null argument"); return 1; }
+  if (!p || !p->theta || !p->x || (!p->h_out && !p->mlp) || !p->out) { mx_set_error("mx_policy_step: null argument"); return 1; }
   if (p->rows <= 0) { mx_set_error("mx_policy_step: rows must be positive"); return 1; }
   if (p->in_dim <= 0 || p->in_dim > MX_ROLL_MAX_IN) { mx_set_error("mx_policy_step: in_dim %d outside [1, %d]", p->in_dim, MX_ROLL_MAX_IN); return 1; }
   if (p->out_dim <= 0 || p->out_dim > 64) { mx_set_error("mx_policy_step: out_dim %d outside [1, 64]", p->out_dim); return 1; }
@@ -132,7 +142,7 @@ extern "C" int mx_policy_step(const mx_policy_step_args* p, void* stream) {
   a.theta = p->theta;
   mx_net_layout(p->in_dim, p->out_dim, 0, &a.L);
   a.x = p->x; a.x_ld = p->x_ld; a.h_in = p->h_in; a.h_out = p->h_out; a.h_copy = p->h_copy; a.out = p->out;
-  a.avail = p->avail; a.avail_ld = p->avail_ld; a.greedy = p->greedy; a.greedy_q = p->greedy_q; a.R = p->rows;
+  a.avail = p->avail; a.avail_ld = p->avail_ld; a.greedy = p->greedy; a.greedy_q = p->greedy_q; a.R = p->rows; a.mlp = p->mlp;
   int grid = p->rows;
   const int cap = mx_num_sms() * 4;
   if (grid > cap) grid = cap;

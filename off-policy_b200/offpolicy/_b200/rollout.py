@@ -26,8 +26,9 @@ def _host_ptr(x):
 
 
 class PolicyStepper(object):
-    def __init__(self, in_dim, out_dim):
+    def __init__(self, in_dim, out_dim, mlp=False):
         self.in_dim, self.out_dim = int(in_dim), int(out_dim)
+        self.mlp = bool(mlp)      # non-recurrent net (M_QMixPolicy): no state is carried
         self.dev = capi.device()
         self.rows = 0
         self._last_h = None      # (host array handed out, rows): its device copy is in self.d_h
@@ -76,9 +77,10 @@ class PolicyStepper(object):
         a.theta = theta.data_ptr()
         a.in_dim, a.out_dim, a.rows, a.x_ld, a.avail_ld = I, A, R, I, A
         a.x = base + 4 * o_x
-        a.h_in = self.d_h.data_ptr() if resident else base + 4 * o_h
-        a.h_out = self.d_h.data_ptr()
-        a.h_copy = base + 4 * o_hn
+        a.mlp = int(self.mlp)
+        a.h_in = None if self.mlp else (self.d_h.data_ptr() if resident else base + 4 * o_h)
+        a.h_out = None if self.mlp else self.d_h.data_ptr()
+        a.h_copy = None if self.mlp else base + 4 * o_hn
         a.out = base + 4 * o_out
         a.avail = base + 4 * o_av if avail is not None else None
         a.greedy = base + 4 * o_gi if want_greedy else None

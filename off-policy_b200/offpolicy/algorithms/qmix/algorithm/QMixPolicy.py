@@ -18,7 +18,7 @@ from offpolicy._b200.flat import FlatModule, reference_style_init
 from offpolicy._b200.host_util import LinearDecay, space_dim, is_discrete, onehot
 
 
-def qmix_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, max_batch, vdn=False, use_avail=True, world_size=1):
+def qmix_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, max_batch, vdn=False, use_avail=True, world_size=1, mlp=False):
     return capi.QmixCfg(
         n_agents=n_agents, obs_dim=obs_dim, act_dim=act_dim, state_dim=state_dim, hidden=args.hidden_size,
         mixer_hidden=args.mixer_hidden_dim, hyper_hidden=args.hypernet_hidden_dim, hyper_layers=args.hypernet_layers,
@@ -26,7 +26,7 @@ def qmix_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, ma
         use_huber=int(args.use_huber_loss), use_per=int(args.use_per), use_avail=int(use_avail), world_size=world_size,
         gamma=args.gamma, huber_delta=args.huber_delta, per_nu=args.per_nu, per_eps=args.per_eps, lr=args.lr,
         adam_beta1=0.9, adam_beta2=0.999, adam_eps=args.opti_eps, max_grad_norm=args.max_grad_norm, tau=args.tau,
-        prev_act_inp=int(bool(getattr(args, "prev_act_inp", False))))
+        prev_act_inp=0 if mlp else int(bool(getattr(args, "prev_act_inp", False))), mlp=int(bool(mlp)))
 
 
 def param_entries(cfg):

@@ -99,8 +99,7 @@ class QMix(object):
         self.world_size = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
         self.world_size = int(getattr(args, "dp_world_size", None) or self.world_size)     # (tests drive several "ranks" from one process)
         self._p2p = False
-        self.cfg = qmix_cfg_struct(args, num_agents, pol.obs_dim, pol.act_dim, pol.central_obs_dim, self.episode_length, self.max_batch,
-                                   vdn=self.vdn, use_avail=True, world_size=self.world_size)
+        self.cfg = self._cfg_struct(args, num_agents, pol)
         entries, total = param_entries(self.cfg)
         self.entries, self.P = entries, total
         z = lambda: torch.zeros(total, dtype=torch.float32, device=self.dev)
@@ -113,7 +112,7 @@ class QMix(object):
         if not self.vdn:
             init = reference_style_init([e for e in entries if e[0].startswith("mixer.")],
                                         dict(state_dim=pol.central_obs_dim, n_agents=num_agents, mixer_hidden=args.mixer_hidden_dim,
-                                             hyper_hidden=args.hypernet_hidden_dim, hidden=args.hidden_size, obs_dim=pol.q_network_input_dim,
+                                             hyper_hidden=args.hypernet_hidden_dim, hidden=args.hidden_size, obs_dim=getattr(pol, "q_network_input_dim", pol.obs_dim),
                                              act_dim=pol.act_dim), gain=1.0, use_orthogonal=args.use_orthogonal,
                                         hyper_layers=args.hypernet_layers)
             self.mixer.load_state_dict({k[len("mixer."):]: v for k, v in init.items()})
@@ -153,6 +152,10 @@ class QMix(object):
                 self._p2p = False
         if getattr(args, "use_double_q", True):
             print("double Q learning will be used")
+
+    def _cfg_struct(self, args, num_agents, pol):
+        return qmix_cfg_struct(args, num_agents, pol.obs_dim, pol.act_dim, pol.central_obs_dim, self.episode_length, self.max_batch,
+                               vdn=self.vdn, use_avail=True, world_size=self.world_size)
 
     # -- data-parallel gradient exchange over NVLink peer memory (csrc/p2p.cu) ----------------------------------------
     def _setup_p2p(self):

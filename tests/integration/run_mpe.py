@@ -60,6 +60,7 @@ def main():
     ap.add_argument("--algo", default="qmix")
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--runner", default="rnn", choices=["rnn", "mlp"], help="runner/rnn/mpe_runner.py (recurrent algorithms) or runner/mlp/mpe_runner.py")
     a, extra = ap.parse_known_args()          # unknown flags go to the reference's own parser (config.py)
     a.extra = extra
     rh = install_shims()
@@ -83,8 +84,12 @@ def main():
     from offpolicy.utils.util import get_cent_act_dim, get_dim_from_space
     from offpolicy.envs.mpe.MPE_Env import MPEEnv
     from offpolicy.envs.env_wrappers import DummyVecEnv
-    from offpolicy.runner.rnn.mpe_runner import MPERunner
-    import offpolicy.utils.rec_buffer as rb
+    if a.runner == "mlp":
+        from offpolicy.runner.mlp.mpe_runner import MPERunner
+        import offpolicy.utils.mlp_buffer as rb
+    else:
+        from offpolicy.runner.rnn.mpe_runner import MPERunner
+        import offpolicy.utils.rec_buffer as rb
     parser = get_config()
     parser.add_argument('--scenario_name', type=str, default='simple_spread')          # train_mpe.py:49-57
     parser.add_argument("--num_landmarks", type=int, default=3)
@@ -92,7 +97,8 @@ def main():
     parser.add_argument('--use_same_share_obs', action='store_false', default=True)
     argv = ["--env_name", "MPE", "--algorithm_name", a.algo, "--experiment_name", "b200", "--scenario_name", "simple_spread", "--num_agents", "3",
             "--num_landmarks", "3", "--seed", str(a.seed), "--episode_length", "25", "--tau", "0.005", "--lr", "7e-4",
-            "--num_env_steps", str(a.steps), "--batch_size", "4", "--buffer_size", "64", "--num_random_episodes", "2",
+            "--num_env_steps", str(a.steps), "--batch_size", "4" if a.runner == "rnn" else "16", "--buffer_size", "64" if a.runner == "rnn" else "512",
+            "--num_random_episodes", "2", "--train_interval", "25",
             "--log_interval", "100000", "--eval_interval", "10000000", "--save_interval", "10000000"] + list(a.extra)
     all_args = parser.parse_known_args(argv)[0]
     all_args.use_wandb = False
@@ -121,7 +127,7 @@ def main():
         rewards.append(float(info["average_episode_rewards"]))
         return info
     runner.collecter = recording_collect
-    q_learning = a.algo in ("qmix", "vdn")
+    q_learning = a.algo in ("qmix", "vdn", "mqmix", "mvdn")
     name = "train_policy_on_batch" if q_learning else "shared_train_policy_on_batch"
     train = getattr(runner.trainer, name)
 
