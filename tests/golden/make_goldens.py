@@ -170,7 +170,7 @@ def gen_replay(name="replay_small"):
     print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
-if __name__ == "__main__" and "maddpg" not in sys.argv[1:] and "rollout" not in sys.argv[1:] and "prev_act" not in sys.argv[1:]:
+if __name__ == "__main__" and "maddpg" not in sys.argv[1:] and "rollout" not in sys.argv[1:] and "prev_act" not in sys.argv[1:] and "mqmix" not in sys.argv[1:]:
     torch.set_num_threads(1)
     small = QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48)
     gen_qmix("qmix_small", small)
@@ -337,3 +337,96 @@ if __name__ == "__main__" and "rollout" in sys.argv[1:]:
 if __name__ == "__main__" and "prev_act" in sys.argv[1:]:
     torch.set_num_threads(1)
     gen_qmix("qmix_small_prev_act", QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48), flags=["--prev_act_inp"], steps=2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MLP (transition-level) QMIX: M_QMixPolicy + M_QMix (algorithms/mqmix/*), batches of single transitions
+# ---------------------------------------------------------------------------------------------------------------
+def synth_transitions(cfg, B, seed, avail=True):
+    rs = np.random.RandomState(seed)
+    N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    av = (rs.rand(N, B, A) < 0.6).astype(np.float32); av[..., 0] = 1.0
+    nav = (rs.rand(N, B, A) < 0.6).astype(np.float32); nav[..., 0] = 1.0
+    logits = rs.rand(N, B, A) + 10.0 * av
+    acts = np.eye(A, dtype=np.float32)[logits.argmax(-1)]
+    rew = np.repeat(rs.randn(1, B, 1).astype(np.float32), N, 0)
+    return dict(obs=rs.randn(N, B, O).astype(np.float32), share=rs.randn(B, S).astype(np.float32), acts=acts, rew=rew,
+                nobs=rs.randn(N, B, O).astype(np.float32), nshare=rs.randn(B, S).astype(np.float32), dones=np.zeros((N, B, 1), np.float32),
+                dones_env=(rs.rand(B, 1) < 0.3).astype(np.float32), valid=np.ones((N, B, 1), np.float32),
+                avail=av if avail else None, navail=nav if avail else None)
+
+
+def gen_mqmix(name, cfg, flags=(), B=8, steps=2, per=False, avail=True):
+    rh.import_reference()
+    from offpolicy.algorithms.mqmix.mqmix import M_QMix
+    from offpolicy.algorithms.mqmix.algorithm.mQMixPolicy import M_QMixPolicy
+    sp = rh.gym_spaces()
+    args = rh.make_args(["--algorithm_name", "mqmix", "--hidden_size", str(cfg.hidden), "--gain", str(cfg.gain),
+                         "--hypernet_layers", str(cfg.hyper_layers), "--lr", str(cfg.lr)] + list(flags))
+    torch.manual_seed(1); np.random.seed(1)
+    info = dict(obs_space=sp.Box(-np.inf, np.inf, (cfg.obs_dim,)), share_obs_space=sp.Box(-np.inf, np.inf, (cfg.state_dim,)),
+                act_space=sp.Discrete(cfg.act_dim), cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
+    dev = torch.device("cpu")
+    pol = M_QMixPolicy({"args": args, "device": dev}, info)
+    tr = M_QMix(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=dev)
+    randomize_all(pol.q_network, 31); randomize_all(tr.mixer, 32)
+    tr.hard_target_updates()
+    randomize_all(tr.target_policies["policy_0"].q_network, 33, scale=0.05); randomize_all(tr.target_mixer, 34, scale=0.05)
+    out = {}
+    out.update(sd_np("init.agent.", pol.q_network)); out.update(sd_np("init.mixer.", tr.mixer))
+    out.update(sd_np("init.tgt_agent.", tr.target_policies["policy_0"].q_network)); out.update(sd_np("init.tgt_mixer.", tr.target_mixer))
+    d = lambda x: {"policy_0": x}
+    for s in range(steps):
+        b = synth_transitions(cfg, B, 400 + s, avail)
+        for k, v in b.items():
+            if v is not None:
+                out["s%d.in.%s" % (s, k)] = v
+        w = idx = None
+        if per:
+            w = np.random.RandomState(17 + s).rand(B) * 0.9 + 0.1
+            idx = np.arange(B)
+            out["s%d.in.weights" % s] = w
+        batch = (d(b["obs"]), d(b["share"]), d(b["acts"]), d(b["rew"]), d(b["nobs"]), d(b["nshare"]), d(b["dones"]), d(b["dones_env"]),
+                 d(b["valid"]), d(b["avail"]), d(b["navail"]), w, idx)
+        info_t, prio, _ = tr.train_policy_on_batch(batch, True)
+        out["s%d.loss" % s] = info_t["loss"].detach().numpy()
+        out["s%d.grad_norm" % s] = np.asarray(float(info_t["grad_norm"]), np.float32)
+        out["s%d.Q_tot" % s] = info_t["Q_tot"].detach().numpy()
+        if prio is not None:
+            out["s%d.prio" % s] = np.asarray(prio)
+        for k, p in pol.q_network.named_parameters():
+            if p.grad is not None:
+                out["s%d.grad.agent.%s" % (s, k)] = p.grad.numpy().copy()
+        for k, p in tr.mixer.named_parameters():
+            out["s%d.grad.mixer.%s" % (s, k)] = p.grad.numpy().copy()
+        tr.soft_target_updates()
+        out.update(sd_np("s%d.agent." % s, pol.q_network)); out.update(sd_np("s%d.mixer." % s, tr.mixer))
+        out.update(sd_np("s%d.tgt_agent." % s, tr.target_policies["policy_0"].q_network)); out.update(sd_np("s%d.tgt_mixer." % s, tr.target_mixer))
+    # rollout surface (one env step): greedy and exploring under fixed seeds
+    rs = np.random.RandomState(5)
+    r_obs = rs.randn(cfg.n_agents, cfg.obs_dim).astype(np.float32)
+    r_av = (rs.rand(cfg.n_agents, cfg.act_dim) < 0.6).astype(np.float32); r_av[:, 0] = 1.0
+    out["roll.obs"], out["roll.avail"] = r_obs, r_av
+    with torch.no_grad():
+        a, q = pol.get_actions(r_obs, r_av)
+        out["roll.greedy"], out["roll.greedy_q"] = np.asarray(a, np.float32), q.numpy().copy()
+        torch.manual_seed(5); np.random.seed(5)
+        a, q = pol.get_actions(r_obs, r_av, t_env=20000, explore=True)
+        out["roll.explore"] = np.asarray(a, np.float32)
+        out["roll.q_all"] = pol.get_q_values(torch.from_numpy(r_obs)).numpy().copy()
+    out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, cfg.hidden, cfg.mixer_hidden, cfg.hyper_hidden,
+                                cfg.hyper_layers, B, 1, steps])
+    out["meta.flags"] = np.array([args.use_double_q, args.use_huber_loss, per, False], dtype=np.int64)
+    out["meta.hparams"] = np.array([args.gamma, args.lr, args.opti_eps, args.max_grad_norm, args.tau, args.huber_delta, args.per_nu, args.per_eps],
+                                   dtype=np.float64)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024), "loss", out["s0.loss"])
+
+
+if __name__ == "__main__" and "mqmix" in sys.argv[1:]:
+    torch.set_num_threads(1)
+    small = QmixConfig(n_agents=3, obs_dim=18, act_dim=5, state_dim=54)
+    gen_mqmix("mqmix_small", small)
+    gen_mqmix("mqmix_small_per_huber_nodq", small, flags=["--use_per", "--use_huber_loss", "--use_double_q", "--huber_delta", "0.5"], per=True, steps=1)
+    gen_mqmix("mqmix_small_noavail", small, avail=False, steps=1)

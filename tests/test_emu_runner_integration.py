@@ -37,6 +37,11 @@ RUNS = {
     # that change every step (the env asserts no unavailable action is ever chosen), early termination, episode limit 60
     "smac_qmix": ("qmix", 220, [], True),
     "smac_qmix_per_hard": ("qmix", 200, ["--use_per", "--use_soft_update", "--hard_update_interval_episode", "2"], False),
+    # offpolicy/runner/mlp/mpe_runner.py (the transition-level algorithms): M_QMix on MlpReplayBuffer
+    "mlp_mqmix": ("mqmix", 150, ["--runner", "mlp"], True),
+    "mlp_mqmix_reward_norm": ("mqmix", 125, ["--runner", "mlp", "--use_reward_normalization"], True),
+    "mlp_mqmix_per": ("mqmix", 100, ["--runner", "mlp", "--use_per"], False),       # reference PER insert bug (mlp_buffer.py:282)
+    "mlp_mvdn": ("mvdn", 100, ["--runner", "mlp"], False),                         # reference M_VDNMixer is broken (App. D-5)
 }
 
 
