@@ -13,25 +13,33 @@ SAMPLE_UNIFORM, SAMPLE_PER, SOFT_UPDATE, PER_WRITEBACK = 1, 2, 4, 8
 
 
 class StepGraph(object):
+    """`buffer`: RecReplayBuffer / PrioritizedRecReplayBuffer with a recurrent trainer, or MlpReplayBuffer / PrioritizedMlpReplayBuffer with
+    M_QMix / M_VDN (transitions are length-1 episodes of the same HBM replay, so the captured sequence is the same)."""
+
     def __init__(self, buffer, trainer, batch_size, beta=0.4, soft_update=True, p_id="policy_0"):
         lib = capi.lib()
         pb = buffer.policy_buffers[p_id]
+        pb = getattr(pb, "rep", pb)               # MlpPolicyBuffer wraps the episode replay
         per = bool(getattr(trainer, "use_per", False))
         self.flags = (SAMPLE_PER | PER_WRITEBACK if per else SAMPLE_UNIFORM) | (SOFT_UPDATE if soft_update else 0)
-        self.stream = torch.cuda.Stream(device=capi.device())
-        self.stream.wait_stream(torch.cuda.current_stream(capi.device()))
+        dev = capi.device()
+        self.cuda = dev.type == "cuda"            # (the CPU-emulated unit-test build re-runs the sequence instead of a graph)
+        self.stream = torch.cuda.Stream(device=dev) if self.cuda else None
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream(dev))
+        self._sp = C.c_void_p(self.stream.cuda_stream if self.cuda else 0)
         g = C.c_void_p()
-        capi.check(lib.mx_graph_capture(pb.handle, trainer.handle, int(batch_size), float(beta), self.flags,
-                                        C.c_void_p(self.stream.cuda_stream), C.byref(g)))
+        capi.check(lib.mx_graph_capture(pb.handle, trainer.handle, int(batch_size), float(beta), self.flags, self._sp, C.byref(g)))
         self.handle = g
         self.num_kernels = int(lib.mx_graph_num_kernels(g))
         self._keep = (buffer, trainer)
 
     def launch(self):
-        capi.check(capi.lib().mx_graph_launch(self.handle, C.c_void_p(self.stream.cuda_stream)))
+        capi.check(capi.lib().mx_graph_launch(self.handle, self._sp))
 
     def synchronize(self):
-        self.stream.synchronize()
+        if self.cuda:
+            self.stream.synchronize()
 
     def close(self):
         if self.handle:

@@ -170,7 +170,7 @@ def gen_replay(name="replay_small"):
     print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
-if __name__ == "__main__" and "maddpg" not in sys.argv[1:] and "rollout" not in sys.argv[1:] and "prev_act" not in sys.argv[1:] and "mqmix" not in sys.argv[1:]:
+if __name__ == "__main__" and "maddpg" not in sys.argv[1:] and "rollout" not in sys.argv[1:] and "prev_act" not in sys.argv[1:] and "mqmix" not in sys.argv[1:] and "mlp_replay" not in sys.argv[1:]:
     torch.set_num_threads(1)
     small = QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48)
     gen_qmix("qmix_small", small)
@@ -430,3 +430,42 @@ if __name__ == "__main__" and "mqmix" in sys.argv[1:]:
     gen_mqmix("mqmix_small", small)
     gen_mqmix("mqmix_small_per_huber_nodq", small, flags=["--use_per", "--use_huber_loss", "--use_double_q", "--huber_delta", "0.5"], per=True, steps=1)
     gen_mqmix("mqmix_small_noavail", small, avail=False, steps=1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# transition replay: the reference's MlpReplayBuffer (utils/mlp_buffer.py) driven with seeded inserts and samples
+# ---------------------------------------------------------------------------------------------------------------
+from oracle.mqmix import transition_replay_script as mlp_replay_script  # noqa: E402
+
+
+def gen_mlp_replay():
+    rh.import_reference()
+    from offpolicy.utils.mlp_buffer import MlpReplayBuffer
+    N, O, A, S, E = 3, 6, 4, 7, 20
+    out = {"meta.shape": np.array([N, O, A, S, E])}
+    for tag, norm, avail in (("plain", False, True), ("norm", True, False)):
+        info = {"policy_0": dict(obs_space=[O], share_obs_space=[S], act_space=rh.gym_spaces().Discrete(A))}
+        buf = MlpReplayBuffer(info, {"policy_0": list(range(N))}, E, True, avail, use_reward_normalization=norm)
+        np.random.seed(11)
+        d = lambda x: {"policy_0": x}
+        ns = ni = 0
+        for op, n, f in mlp_replay_script():
+            if op == "insert":
+                idx = buf.insert(n, d(f["obs"]), d(f["share"]), d(f["acts"]), d(f["rew"]), d(f["nobs"]), d(f["nshare"]), d(f["dones"]), d(f["dones_env"]),
+                                 d(f["valid"]), d(f["avail"]), d(f["navail"]))
+                out["%s.idx%d" % (tag, ni)] = np.asarray(idx)
+                ni += 1
+            else:
+                smp = buf.sample(n)
+                for i, name in enumerate(["obs", "share", "acts", "rew", "nobs", "nshare", "dones", "dones_env", "valid", "avail", "navail"]):
+                    if smp[i]["policy_0"] is not None:
+                        out["%s.s%d.%s" % (tag, ns, name)] = np.asarray(smp[i]["policy_0"])
+                ns += 1
+        out["%s.n_samples" % tag] = np.array(ns)
+    path = os.path.join(HERE, "mlp_replay_small.npz")
+    np.savez_compressed(path, **out)
+    print("mlp_replay_small ->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__" and "mlp_replay" in sys.argv[1:]:
+    gen_mlp_replay()

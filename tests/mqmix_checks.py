@@ -150,3 +150,153 @@ def check_buffer_vs_reference_layout(seed=0):
                     assert np.abs(got - w).max() <= 2e-5 * max(1.0, np.abs(w).max()), (k, i)
                 else:
                     assert np.array_equal(got, w), (k, i)
+
+
+def _to_dicts(b, w=None):
+    d = lambda x: {"policy_0": x}
+    B = b[0].shape[1]
+    return tuple(d(x) for x in b) + (w, np.arange(B) if w is not None else None)
+
+
+def check_vs_oracle(N=3, O=18, A=5, S=54, B=64, steps=2, avail=False, per=False, huber=False, double_q=True, vdn=False, hyper_layers=2, debug=False):
+    """Any size: the MLP learner in lock-step with the pinned oracle (oracle/mqmix.py).  Defaults = scripts/train_mpe_mqmix.sh shapes
+    (simple_spread: 3 agents, obs 18, Discrete(5), state 54, no availability masks)."""
+    from oracle.qmix import QmixConfig, randomize_all
+    from oracle.mqmix import MqmixLearner, synth_transitions
+    cfg = QmixConfig(n_agents=N, obs_dim=O, act_dim=A, state_dim=S, gain=1.0, use_per=per, huber=huber, huber_delta=0.7, double_q=double_q, vdn=vdn,
+                     hyper_layers=hyper_layers)
+    L = MqmixLearner(cfg, seed=3)
+    randomize_all(L.agent, 1)
+    if not vdn:
+        randomize_all(L.mixer, 2)
+    L.sync_targets()
+    randomize_all(L.tgt_agent, 3, 0.05)
+    if not vdn:
+        randomize_all(L.tgt_mixer, 4, 0.05)
+    if vdn:
+        from offpolicy.algorithms.mvdn.algorithm.mVDNPolicy import M_VDNPolicy as Pol
+        from offpolicy.algorithms.mvdn.mvdn import M_VDN as Tr
+    else:
+        from offpolicy.algorithms.mqmix.algorithm.mQMixPolicy import M_QMixPolicy as Pol
+        from offpolicy.algorithms.mqmix.mqmix import M_QMix as Tr
+    from offpolicy._b200 import capi
+    args = qc.make_args(cfg, B)
+    info = dict(obs_space=[O], share_obs_space=[S], act_space=Discrete(A), cent_obs_dim=S, cent_act_dim=A * N)
+    pol = Pol({"args": args, "device": capi.device()}, info)
+    tr = Tr(args, N, {"policy_0": pol}, lambda a: "policy_0", device=capi.device())
+    capi.lib().mx_qmix_set_debug(tr.handle, 1 if debug else 0)
+    pol.q_network.load_state_dict(L.agent.state_dict())
+    tr.target_q_network.load_state_dict(L.tgt_agent.state_dict())
+    if not vdn:
+        tr.mixer.load_state_dict(L.mixer.state_dict())
+        tr.target_mixer.load_state_dict(L.tgt_mixer.state_dict())
+    for s in range(steps):
+        b = synth_transitions(cfg, B, seed=50 + s, avail=avail)
+        w = (np.random.RandomState(60 + s).rand(B) * 0.9 + 0.1) if per else None
+        info_t, prio, _ = tr.train_policy_on_batch(_to_dicts(b, w), True)
+        gv = {k: v.clone() for k, v in tr.grad_views().items()}
+        tr.soft_target_updates()
+        ref, rprio, _ = L.step(b + (w, None))
+        coef = min(1.0, cfg.max_grad_norm / (float(ref["grad_norm"]) + 1e-6))
+        L.soft_update()
+        for k in ("loss", "grad_norm", "Q_tot"):
+            assert rel_err(info_t[k].cpu(), ref[k]) < 1e-4, (s, k, float(info_t[k]), float(ref[k]))
+        if per:
+            assert rel_err(np.asarray(prio), rprio) < 1e-4
+        named = dict(("agent." + k, p) for k, p in L.agent.named_parameters())
+        if not vdn:
+            named.update(("mixer." + k, p) for k, p in L.mixer.named_parameters())
+        for k, p in named.items():
+            if p.grad is None:
+                assert float(gv[k].abs().max()) == 0.0, k
+                continue
+            ok, err, lim = qc.close(gv[k] * coef, p.grad, 1e-4)
+            assert ok, (s, k, err, lim)
+        for k, v in pol.q_network.state_dict().items():
+            assert float((v.cpu() - L.agent.state_dict()[k]).abs().max()) <= 5e-3 * cfg.lr * (s + 1) + 1e-7, (s, k)
+        for k, v in tr.target_q_network.state_dict().items():
+            assert float((v.cpu() - L.tgt_agent.state_dict()[k]).abs().max()) <= 1e-6, (s, k)
+
+
+def fill_mlp_buffer(N, O, A, S, E, B, avail=False, per=False, norm=False, seed=0):
+    from offpolicy.utils.mlp_buffer import MlpReplayBuffer, PrioritizedMlpReplayBuffer
+    info = {"policy_0": dict(obs_space=[O], share_obs_space=[S], act_space=Discrete(A))}
+    ag = {"policy_0": list(range(N))}
+    buf = (PrioritizedMlpReplayBuffer(0.6, info, ag, E, True, avail, norm, max_batch=max(B, 256)) if per else
+           MlpReplayBuffer(info, ag, E, True, avail, norm, max_batch=max(B, 256)))
+    rs = np.random.RandomState(seed)
+    d = lambda x: {"policy_0": None if x is None else x.astype(np.float32)}
+    for c in range(0, E, 256):
+        n = min(256, E - c)
+        av = (rs.rand(n, N, A) < 0.6) * 1.0
+        av[..., 0] = 1.0
+        buf.insert(n, d(rs.randn(n, N, O)), d(rs.randn(n, S)), d(np.eye(A)[rs.randint(0, A, (n, N))]), d(np.repeat(rs.randn(n, 1, 1), N, 1)), d(rs.randn(n, N, O)),
+                   d(rs.randn(n, S)), d(np.zeros((n, N, 1))), d((rs.rand(n, 1) < 0.2) * 1.0), d(np.ones((n, N, 1))), d(av if avail else None), d(av if avail else None))
+    return buf
+
+
+def check_step_graph_vs_eager(per=False, steps=3, B=32, E=300):
+    """sample (device MT19937) -> M_QMix step [-> priority write-back] -> soft update: the captured whole-step sequence
+    (StepGraph; on the emulator the same launch sequence re-run) leaves exactly the state the drop-in calls leave."""
+    from oracle.qmix import QmixConfig
+    from offpolicy._b200.graph import StepGraph
+    N, O, A, S = 3, 18, 5, 54
+    cfg = QmixConfig(n_agents=N, obs_dim=O, act_dim=A, state_dim=S, gain=1.0, use_per=per)
+    outs = []
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0); np.random.seed(0)
+        buf = fill_mlp_buffer(N, O, A, S, E, B, avail=per, per=per)
+        args, pol, tr = build(cfg, B, debug=False)
+        buf.seed_device_rng(77)
+        if mode == "eager":
+            for s in range(steps):
+                smp = buf.sample(B, 0.4) if per else buf.sample(B)
+                info, prio, idx = tr.train_policy_on_batch(smp, True)
+                if per:
+                    buf.update_priorities(idx, prio, "policy_0")
+                tr.soft_target_updates()
+        else:
+            g = StepGraph(buf, tr, B, beta=0.4)
+            for s in range(steps):
+                g.launch()
+            g.synchronize()
+            g.close()
+        outs.append((tr.theta.clone().cpu(), tr.theta_tgt.clone().cpu(), tr.adam_m.clone().cpu()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert float((outs[0][0] - outs[0][1]).abs().max()) > 0.0
+
+
+def check_buffer_vs_reference_golden():
+    """MlpReplayBuffer (HBM replay, length-1 episodes) driven with the schedule of tests/golden/mlp_replay_small.npz = the reference's own
+    MlpReplayBuffer under the same inserts and the same NumPy seed: ring indices and every sampled array bit-equal; normalised rewards to
+    2e-5 (running statistics kept in fp64 on the device instead of a rescan of all stored rewards)."""
+    from oracle.mqmix import transition_replay_script
+    from offpolicy.utils.mlp_buffer import MlpReplayBuffer
+    g = load_golden("mlp_replay_small")
+    N, O, A, S, E = [int(v) for v in g["meta.shape"]]
+    names = ["obs", "share", "acts", "rew", "nobs", "nshare", "dones", "dones_env", "valid", "avail", "navail"]
+    d = lambda x: {"policy_0": x}
+    for tag, norm, avail in (("plain", False, True), ("norm", True, False)):
+        info = {"policy_0": dict(obs_space=[O], share_obs_space=[S], act_space=Discrete(A))}
+        buf = MlpReplayBuffer(info, {"policy_0": list(range(N))}, E, True, avail, use_reward_normalization=norm, max_batch=16)
+        np.random.seed(11)
+        ns = ni = 0
+        for op, n, f in transition_replay_script():
+            if op == "insert":
+                idx = buf.insert(n, *[d(f[k]) for k in names])
+                assert np.array_equal(idx, g["%s.idx%d" % (tag, ni)]), (tag, ni)
+                ni += 1
+                continue
+            smp = buf.sample(n)
+            for i, name in enumerate(names):
+                key = "%s.s%d.%s" % (tag, ns, name)
+                got = smp[i]["policy_0"]
+                if key not in g:
+                    assert got is None, key
+                elif name == "rew" and norm:
+                    assert np.abs(got - g[key]).max() <= 2e-5 * max(1.0, np.abs(g[key]).max()), key
+                else:
+                    assert np.array_equal(got, g[key]), key
+            ns += 1
+        assert ns == int(g["%s.n_samples" % tag])

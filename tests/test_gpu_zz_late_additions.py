@@ -24,3 +24,24 @@ def test_mqmix_matches_reference_golden(gpu_engine, name, debug):
 def test_mlp_buffer_sample_layout(gpu_engine):
     import mqmix_checks as mc
     mc.check_buffer_vs_reference_layout()
+
+
+@pytest.mark.parametrize("kw", [dict(B=1000), dict(B=1000, avail=True, per=True, huber=True), dict(B=256, avail=True, double_q=False), dict(B=1000, vdn=True),
+                                dict(B=320, hyper_layers=1, N=5, O=80, A=11, S=120)],
+                         ids=["mpe_b1000", "avail_per_huber", "avail_nodq", "vdn", "hyper1_2s3z_shapes"])
+def test_mlp_learner_vs_oracle(gpu_engine, kw):
+    """scripts/train_mpe_mqmix.sh sizes (batch 1000 transitions) in lock-step with the pinned oracle (oracle/mqmix.py); obs 80 takes the
+    FFMA front kernel (obs_dim > 64), obs 18 the tcgen05 one."""
+    import mqmix_checks as mc
+    mc.check_vs_oracle(steps=2, **kw)
+
+
+def test_mlp_buffer_vs_reference_golden(gpu_engine):
+    import mqmix_checks as mc
+    mc.check_buffer_vs_reference_golden()
+
+
+@pytest.mark.parametrize("per", [False, True], ids=["uniform", "per"])
+def test_mlp_step_graph_vs_eager(gpu_engine, per):
+    import mqmix_checks as mc
+    mc.check_step_graph_vs_eager(per=per, B=1000, E=4096)
