@@ -40,6 +40,7 @@ WORKLOADS = {
     # --use_reward_normalization, no available-action masks) -- the reference's own CPU-runnable case
     "qmix_mpe_spread": (3, 18, 5, 54, 25, 32, False),
 }
+PROFILE_REPS, PROFILE_INNER, E2E_MIN_STEPS, CPU_STEPS = 6, 8, 20, 20     # loop lengths (tests/test_bench_dryrun.py shrinks them)
 NO_AVAIL = {"qmix_mpe_spread"}       # MPE passes avail_acts = None (runner/rnn/mpe_runner.py:62) and normalises rewards
 
 
@@ -507,7 +508,7 @@ def run_engine(args):
     for i in range(5):
         e2e_step(i)
     barrier()
-    n_e2e = max(20, min(args.steps, 200))
+    n_e2e = max(E2E_MIN_STEPS, min(args.steps, 200))
     t0 = time.perf_counter()
     for i in range(n_e2e):
         e2e_step(i)
@@ -553,7 +554,7 @@ def run_engine(args):
     buf.rng = "device"
     tr.use_step_graph = False       # individual launches (with event marks between them), not the captured graph
     kern = {}
-    reps, inner = 6, 8
+    reps, inner = PROFILE_REPS, PROFILE_INNER
     for rep in range(reps + 1):
         # `inner` eager steps are queued back to back (no host sync) so the GPU never waits for a launch: the
         # event-to-event intervals are then kernel durations, not host launch gaps; the first step of each burst is dropped
@@ -600,7 +601,7 @@ def run_engine(args):
 
     # ---------------- CPU baseline (bounded sample) ----------------
     Ecpu = min(args.buffer, 1024)
-    n_cpu = 20 if args.workload == "qmix_3m" else 5
+    n_cpu = min(CPU_STEPS, 20 if args.workload == "qmix_3m" else 5)
     cores = best_cpu_threads(cfg, T, B, Ecpu, avail)
     sps_all, ms_all = cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, cores, avail)
     sps_one, ms_one = (sps_all, ms_all) if cores == 1 else cpu_learner_steps_per_s(cfg, T, B, Ecpu, n_cpu, 2, 1, avail)
@@ -647,6 +648,201 @@ def run_engine(args):
         os._exit(0)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# MLP (transition-level) QMIX: SURVEY.md section 8(f).4 -- batches of single transitions from a large transition replay
+# ---------------------------------------------------------------------------------------------------------
+MLP_WORKLOADS = {
+    # name: (n_agents, obs, act, state, B, transitions): MPE simple_spread shapes at the MLP scripts' batch / buffer sizes
+    # (scripts/train_mpe_maddpg.sh:14: batch 1000, buffer 500 000; there is no recurrence, a transition is one replay row)
+    "mqmix_mpe_spread": (3, 18, 5, 54, 1000, 500000),
+}
+
+
+def mlp_cfg(w):
+    from oracle.qmix import QmixConfig
+    n, o, a, s, B, E = MLP_WORKLOADS[w]
+    return QmixConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, gain=1.0), B, E
+
+
+def synth_steps(cfg, n, rs):
+    N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    f32 = np.float32
+    return [rs.standard_normal((n, N, O), dtype=f32), rs.standard_normal((n, S), dtype=f32), np.eye(A, dtype=f32)[rs.integers(0, A, (n, N))],
+            np.repeat(rs.standard_normal((n, 1, 1), dtype=f32), N, 1), rs.standard_normal((n, N, O), dtype=f32), rs.standard_normal((n, S), dtype=f32),
+            np.zeros((n, N, 1), f32), (rs.random((n, 1)) < 0.04).astype(f32), np.ones((n, N, 1), f32), None, None]
+
+
+def mlp_cpu_steps_per_s(cfg, B, E, steps, warmup, threads):
+    from oracle.mqmix import MqmixLearner, TransitionReplay
+    torch.set_num_threads(threads)
+    rs = np.random.default_rng(0)
+    buf = TransitionReplay(E, cfg.n_agents, cfg.obs_dim, cfg.state_dim, cfg.act_dim, use_avail=False, reward_norm=False)
+    for c in range(0, E, 8192):
+        n = min(8192, E - c)
+        buf.insert(n, *synth_steps(cfg, n, rs))
+    torch.manual_seed(1)
+    np.random.seed(1)
+    L = MqmixLearner(cfg, seed=1)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        out, inds = buf.sample(B)
+        info, prio, _ = L.step(out)
+        L.soft_update()
+        float(info["loss"])
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return 1.0 / float(np.median(times)), float(np.median(times)) * 1e3
+
+
+def mlp_best_threads(cfg, B, E):
+    cores = os.cpu_count() or 1
+    best, best_sps = 1, 0.0
+    for th in sorted({1, 4, 8, 16, min(32, cores)}):
+        if th <= cores:
+            sps, _ = mlp_cpu_steps_per_s(cfg, B, E, 5, 2, th)
+            if sps > best_sps:
+                best, best_sps = th, sps
+    return best
+
+
+def run_mlp(args):
+    """M_QMix learner: sample(B transitions) -> train_policy_on_batch -> soft_target_updates (runner/mlp/base_runner.py batch_train)."""
+    cfg, B, E_full = mlp_cfg(args.workload)
+    N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if args.impl == "reference":
+        E = min(E_full, 65536)
+        cores = mlp_best_threads(cfg, B, E)
+        sps, ms = mlp_cpu_steps_per_s(cfg, B, E, args.steps, args.warmup, cores)
+        emit(dict(metric="learner grad-steps/sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                  ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                  config=dict(workload=args.workload, batch=B, n_agents=N, obs_dim=O, act_dim=A, state_dim=S, buffer_transitions=E),
+                  cpu_baseline=dict(value=sps, unit="steps/s", cores=cores, host_cores=os.cpu_count(), kind="port",
+                                    sample="%d timed learner steps (sample+train+soft update), transition replay of %d" % (args.steps, E)),
+                  e2e=dict(value=sps, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0))
+        return
+    from offpolicy._b200 import capi
+    from offpolicy._b200.graph import StepGraph
+    from offpolicy.utils.mlp_buffer import MlpReplayBuffer
+    import mqmix_checks as mc
+    torch.cuda.set_device(0)
+    torch.set_num_threads(1)
+    lib, dev = capi.lib(), capi.device()
+    E = min(E_full, args.buffer * 100) if args.buffer != 5000 else E_full          # --buffer N (non-default) = N*100 transitions for quick runs
+    info = {"policy_0": dict(obs_space=[O], share_obs_space=[S], act_space=mc.Discrete(A))}
+    buf = MlpReplayBuffer(info, {"policy_0": list(range(N))}, E, True, False, max_batch=1024)        # the replay's batch limit (B = 1000 fits)
+    rs = np.random.default_rng(0)
+    d = lambda x: {"policy_0": x}
+    for c in range(0, E, 1024):
+        n = min(1024, E - c)
+        buf.insert(n, *[d(x) for x in synth_steps(cfg, n, rs)])
+    torch.manual_seed(1)
+    np.random.seed(1)
+    with contextlib.redirect_stdout(sys.stderr):
+        margs, pol, tr = mc.build(cfg, B, debug=False)
+    rep = buf.policy_buffers["policy_0"].rep
+    buf.seed_device_rng(1)
+    sp = capi.stream_ptr
+    torch.cuda.synchronize()
+    graph = StepGraph(buf, tr, B)
+    for _ in range(max(args.warmup, 3)):
+        graph.launch()
+    graph.synchronize()
+    launches0 = lib.mx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        e0.record(graph.stream)
+        for _ in range(args.steps):
+            graph.launch()
+        e1.record(graph.stream)
+        torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    launches = int(lib.mx_launch_count() - launches0)
+    if args.quick:
+        emit(dict(quick=True, workload=args.workload, value=1000.0 / ms_step, ms_per_step=ms_step, opts=args.opt, kernels_per_step=graph.num_kernels))
+        graph.close()
+        return
+
+    # e2e: the runner's per-step sequence with host inputs: one freshly collected transition inserted (H2D), indices drawn on the host
+    # (np.random.randint == np.random.choice, H2D), train, soft update, loss read back (D2H)
+    buf.rng = "numpy"
+    fresh = [synth_steps(cfg, 1, rs) for _ in range(8)]
+    h2d = sum(x.nbytes for x in fresh[0] if x is not None) + B * 8
+
+    def e2e_step(i):
+        buf.insert(1, *[d(x) for x in fresh[i % 8]])
+        info_t, _, _ = tr.train_policy_on_batch(buf.sample(B), True)
+        tr.soft_target_updates()
+        return float(info_t["loss"])
+
+    for i in range(5):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    n_e2e = max(E2E_MIN_STEPS, min(args.steps, 200))
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_sps = n_e2e / (time.perf_counter() - t0)
+
+    # per-kernel timing (eager launches, CUDA events on the launch stream)
+    buf.seed_device_rng(2)
+    tr.use_step_graph = False
+    kern, reps, inner = {}, PROFILE_REPS, PROFILE_INNER
+    for rep_i in range(reps + 1):
+        lib.mx_profile_begin(sp())
+        for _ in range(inner):
+            tr.train_policy_on_batch(buf.sample(B), True)
+            tr.soft_target_updates()
+        names = C.create_string_buffer(16384)
+        ms = (C.c_float * 512)()
+        n = lib.mx_profile_end(sp(), names, 16384, ms, 512)
+        if rep_i >= 1:
+            per = n // inner
+            for k, (nm, t) in enumerate(zip(names.value.decode().split(";"), list(ms)[:n])):
+                if k >= per:
+                    kern.setdefault(nm, []).append(t)
+    kavg = {k: float(np.median(v)) for k, v in kern.items()}
+    ksum = sum(kavg.values())
+    H, ME, HY = 64, cfg.mixer_hidden, cfg.hyper_hidden
+    M = 2 * B * N                                         # agent-net rows: obs and next obs of every agent
+    mix = (S * HY + HY * N * ME) + (S * HY + HY * ME) + S * ME + (S * HY + HY) + N * ME + ME
+    fl = {"k_front_fwd": 2 * 2.0 * M * (O * H + H * H + H * A), "k_front_fwd_tc": 2 * 2.0 * M * (O * H + H * H + H * A),
+          "k_front_bwd": 2.0 * M * (2 * H * A + 3 * H * H + 3 * O * H) / 2, "k_mixer": 2.0 * B * mix * 4,
+          "k_mix_hyper_fwd": 2.0 * B * (mix - N * ME - ME) * 2, "k_mix_hyper_bwd": 2.0 * B * (mix - N * ME - ME) * 2, "k_mix_core": 2.0 * B * (N * ME + ME) * 4}
+    fields = 4.0 * B * (N * 2 * O + 2 * S + N * A + 3 * N + 1)
+    by = {"k_gather": 2 * fields, "k_adam": 4.0 * tr.P * 7, "k_polyak": 4.0 * tr.P * 3, "k_grad_reduce": 4.0 * tr.P * 2}
+    top = max(kavg, key=kavg.get)
+    pk = peaks()
+    if top in by:
+        ach = by[top] / (kavg[top] * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel=top, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=None, peak_source=pk["src"])
+    else:
+        ach = fl.get(top, 0.0) / (kavg[top] * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel=top, achieved=ach, peak=pk["tflops_sustained"], unit="TFLOP/s", frac=ach / pk["tflops_sustained"], traffic=None,
+                    peak_source=pk["src"] + " bf16 sustained (kernel timed inside the step)",
+                    note="FP32 kernel (1e-4 parity budget); ~6000 agent-net rows per step: latency / occupancy bound, see DESIGN.md")
+    Ecpu = min(E, 65536)
+    cores = mlp_best_threads(cfg, B, Ecpu)
+    sps_cpu, _ = mlp_cpu_steps_per_s(cfg, B, Ecpu, CPU_STEPS, 3, cores)
+    emit(dict(metric="learner grad-steps/sec", value=1000.0 / ms_step, unit="steps/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3),
+              ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+              config=dict(workload=args.workload, batch_transitions=B, n_agents=N, obs_dim=O, act_dim=A, state_dim=S, buffer_transitions=E,
+                          l2="transitions gathered from a replay of %.0f MB (> L2)" % (rep.L.total_bytes / 1e6),
+                          step="CUDA graph: device MT19937 draw + gather + fused MLP-QMIX learner + Adam + Polyak"),
+              e2e=dict(value=e2e_sps, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4, steps=n_e2e,
+                       path="MlpReplayBuffer.insert(1 transition) + sample(np.random.choice) + M_QMix.train_policy_on_batch + soft_target_updates + D2H loss"),
+              gpu_launches=launches, kernels_per_step=graph.num_kernels, roofline=roof,
+              kernels={k: dict(ms=round(v, 5), share=round(v / ksum, 4)) for k, v in sorted(kavg.items(), key=lambda kv: -kv[1])}, kernel_sum_ms=round(ksum, 5),
+              gather_gbs=by["k_gather"] / (kavg.get("k_gather", 1e9) * 1e-3) / 1e9,
+              cpu_baseline=dict(value=sps_cpu, unit="steps/s", cores=cores, host_cores=os.cpu_count(), kind="port",
+                                sample="%d timed steps (sample+train+soft update) on a %d-transition replay, oracle port of the reference M_QMix learner" % (CPU_STEPS, Ecpu)),
+              clocks=clocks.summary()))
+    graph.close()
+
+
 _REAL_STDOUT = None
 
 
@@ -671,7 +867,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="qmix_3m", choices=sorted(WORKLOADS) + sorted(MADDPG_WORKLOADS))
+    ap.add_argument("--workload", default="qmix_3m", choices=sorted(WORKLOADS) + sorted(MADDPG_WORKLOADS) + sorted(MLP_WORKLOADS))
     ap.add_argument("--buffer", type=int, default=5000, help="replay episodes (scripts/train_smac_qmix.sh default 5000)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning sweeps; not the bench contract line)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=int (mx_set_option), e.g. --opt pdl=0 --opt front_tc=0")
@@ -684,6 +880,9 @@ def main():
     if a.workload in MADDPG_WORKLOADS:
         if int(os.environ.get("RANK", "0")) == 0:
             run_maddpg(a)
+        return
+    if a.workload in MLP_WORKLOADS:
+        run_mlp(a)
         return
     if a.impl == "reference":
         run_reference(a)

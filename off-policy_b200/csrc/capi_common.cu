@@ -47,13 +47,40 @@ extern "C" int mx_is_cuda_build(void) { return MX_EMU ? 0 : 1; }
 extern "C" int64_t mx_launch_count(void) { return g_mx_launches; }
 
 int g_mx_prof_on = 0;
-#if MX_EMU
-void mx_prof_mark(const char*, cudaStream_t) {}
-extern "C" int mx_profile_begin(void*) { return 0; }
-extern "C" int mx_profile_end(void*, char*, int32_t, float*, int32_t) { return 0; }
-#else
 #include <string>
 #include <vector>
+#if MX_EMU
+// CPU-emulated unit-test build: the same marks, stamped with the host clock (kernels run synchronously there)
+#include <chrono>
+static std::vector<std::pair<std::string, double>> g_marks;
+static double g_prof_start;
+static double emu_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+void mx_prof_mark(const char* name, cudaStream_t) { g_marks.emplace_back(name, emu_now_ms()); }
+extern "C" int mx_profile_begin(void*) {
+  g_marks.clear();
+  g_prof_start = emu_now_ms();
+  g_mx_prof_on = 1;
+  return 0;
+}
+extern "C" int mx_profile_end(void*, char* names_buf, int32_t buf_len, float* ms, int32_t max_n) {
+  g_mx_prof_on = 0;
+  std::string names;
+  double prev = g_prof_start;
+  int n = 0;
+  for (auto& m : g_marks) {
+    if (n < max_n) {
+      ms[n] = (float)(m.second - prev);
+      if (n) names += ";";
+      names += m.first;
+      ++n;
+    }
+    prev = m.second;
+  }
+  if (names_buf && buf_len > 0) snprintf(names_buf, buf_len, "%s", names.c_str());
+  g_marks.clear();
+  return n;
+}
+#else
 static std::vector<std::pair<std::string, cudaEvent_t>> g_marks;
 static cudaEvent_t g_prof_start;
 void mx_prof_mark(const char* name, cudaStream_t s) {
