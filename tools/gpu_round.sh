@@ -14,6 +14,7 @@ timeout 300 python bench.py --steps 300 --warmup 20 > gpurun_out/bench.json 2> g
 if [ "${2:-}" != "quick" ]; then
   timeout 200 python bench.py --workload qmix_8m_per --steps 50 --warmup 5 --buffer 2000 > gpurun_out/bench_8m.json 2> gpurun_out/bench_8m.err; cut -c1-200 gpurun_out/bench_8m.json
   timeout 200 python bench.py --workload qmix_mpe_spread --steps 300 --warmup 20 > gpurun_out/bench_mpe.json 2> gpurun_out/bench_mpe.err; cut -c1-200 gpurun_out/bench_mpe.json
+  timeout 300 python bench.py --workload mqmix_mpe_spread --steps 300 --warmup 20 > gpurun_out/bench_mlp.json 2> gpurun_out/bench_mlp.err; cut -c1-200 gpurun_out/bench_mlp.json
   timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-200 gpurun_out/bench_ref.json
   timeout 200 python tools/gather_sweep.py > gpurun_out/gather_sweep.log 2> gpurun_out/gather_sweep.err; cut -c1-200 gpurun_out/gather_sweep.log
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv \
