@@ -436,14 +436,10 @@ size_t mx_front_fwd_smem(int in_dim, int RM) {
 }
 
 extern int g_mx_front_tc;
-#if !MX_EMU
 int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s);
-#endif
 
 int mx_launch_front_fwd(const FrontFwdArgs& a, int nets, cudaStream_t s) {
-#if !MX_EMU
   if (g_mx_front_tc && a.L.in_dim <= 64 && (a.ldx & 3) == 0) return mx_launch_front_fwd_tc(a, nets, s);
-#endif
   const int RM = 2;
   const int ntiles = mx_ceil_div(a.M, 16 * RM);
   int gx = mx_num_sms() / nets;

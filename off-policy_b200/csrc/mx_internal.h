@@ -124,7 +124,7 @@ struct mx_qmix {
   // inside a stream capture the same record/wait calls turn into parallel graph branches
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_prep = nullptr, ev_batch = nullptr, ev_hyper = nullptr, ev_core = nullptr, ev_hbwd = nullptr;
-  int prep_pending = 0;    // mx_qmix_prefork() already launched the weight-image prep for the coming step
 #endif
+  int prep_pending = 0;    // mx_qmix_prefork() already launched the weight-image prep for the coming step
 };
 int mx_qmix_prefork(mx_qmix* q, int B, void* stream);   // optional: start the parameter-only work of the next step before its batch is sampled

@@ -291,14 +291,9 @@ static inline void join_from_side(mx_qmix* q, cudaEvent_t ev, cudaStream_t s) { 
 #endif
 
 static int launch_prep(mx_qmix* q, cudaStream_t s) {
-#if !MX_EMU
   const float* const th2[2] = {q->theta, q->theta_tgt};
   float* const img2[2] = {q->ws + q->W.tcimg[0], q->ws + q->W.tcimg[1]};
   return mx_launch_tc_prep_weights(th2, q->agent, img2, 2, s);
-#else
-  (void)q; (void)s;
-  return 0;
-#endif
 }
 
 // Parameter-only work of the coming step (TF32 hi/lo weight images of the front layers), started on the side branch so that it
@@ -365,14 +360,16 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   ff.theta[0] = q->theta; ff.theta[1] = q->theta_tgt; ff.L = q->agent;
   ff.gi[0] = ws + W.gi[0]; ff.gi[1] = ws + W.gi[1];
   ff.u1 = ws + W.u1; ff.u2 = ws + W.u2; ff.st0 = ws + W.st0; ff.st1 = ws + W.st1; ff.st2 = ws + W.st2;
-#if !MX_EMU
   if (g_mx_front_tc && q->agent.in_dim <= 64) {       // weights changed in the last Adam / Polyak: rebuild the TF32 hi/lo images (18k elements per net)
     if (q->prep_pending) {                      // mx_qmix_prefork() launched it on the side branch before the batch was sampled
+#if !MX_EMU
       cudaStreamWaitEvent(s, q->ev_prep, 0);
+#endif
       q->prep_pending = 0;
     } else if (launch_prep(q, s)) return 1;
     ff.tc_img[0] = ws + W.tcimg[0]; ff.tc_img[1] = ws + W.tcimg[1];
   }
+#if !MX_EMU
   // the mixer's hypernetworks depend on the sampled states and the parameters only: forked branch beside the agent nets
   if (split && overlap) fork_to_side(q, q->ev_batch, s);
 #endif
