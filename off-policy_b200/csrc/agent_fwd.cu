@@ -437,9 +437,10 @@ size_t mx_front_fwd_smem(int in_dim, int RM) {
 
 extern int g_mx_front_tc;
 int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s);
+bool mx_front_tc_usable(int in_dim, bool have_image);
 
 int mx_launch_front_fwd(const FrontFwdArgs& a, int nets, cudaStream_t s) {
-  if (g_mx_front_tc && a.L.in_dim <= 64 && (a.ldx & 3) == 0) return mx_launch_front_fwd_tc(a, nets, s);
+  if (mx_front_tc_usable(a.L.in_dim, a.tc_img[0] != nullptr) && (a.ldx & 3) == 0) return mx_launch_front_fwd_tc(a, nets, s);
   const int RM = 2;
   const int ntiles = mx_ceil_div(a.M, 16 * RM);
   int gx = mx_num_sms() / nets;

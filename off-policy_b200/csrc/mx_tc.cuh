@@ -156,6 +156,25 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, const char* a_hi, c
   commit(bar);
 }
 
+// Same, for a layer whose K dimension is fed in chunks (the operand tiles are refilled between calls): acc0 = 0 starts the
+// accumulator, acc0 = 1 adds this chunk's products to what the previous calls left in TMEM.  The caller waits on `bar` after each call.
+__device__ __forceinline__ void issue_layer_acc(uint32_t tmem_d, const char* a_hi, const char* a_lo, const char* b_hi, const char* b_lo, int N, int K,
+                                                int swap_ls, uint32_t acc0, uint32_t bar) {
+  const uint32_t kstride = 128, mstride = (uint32_t)(K >> 2) * 128;
+  const uint32_t lbo = swap_ls ? mstride : kstride, sbo = swap_ls ? kstride : mstride;
+  const uint32_t idesc = make_idesc_tf32(128, N);
+  uint32_t acc = acc0;
+  for (int p = 0; p < 3; ++p) {
+    const char* a = (p == 1) ? a_lo : a_hi;      // hi*hi, lo*hi, hi*lo
+    const char* b = (p == 2) ? b_lo : b_hi;
+    for (int k8 = 0; k8 < K / 8; ++k8) {
+      mma_tf32(tmem_d, make_desc(op_addr(a) + k8 * 256, lbo, sbo), make_desc(op_addr(b) + k8 * 256, lbo, sbo), idesc, acc);
+      acc = 1;
+    }
+  }
+  commit(bar);
+}
+
 }  // namespace tc
 
 namespace tc {
@@ -260,6 +279,25 @@ inline void issue_layer(uint32_t tmem_d, const char* a_hi, const char* a_lo, con
   uint32_t acc = 0;
   for (int p = 0; p < passes; ++p) {
     const char* a = (p == 1) ? a_lo : a_hi;
+    const char* b = (p == 2) ? b_lo : b_hi;
+    for (int k8 = 0; k8 < K / 8; ++k8) {
+      mma_tf32(tmem_d, make_desc(op_addr(a) + k8 * 256, lbo, sbo), make_desc(op_addr(b) + k8 * 256, lbo, sbo), idesc, acc);
+      acc = 1;
+    }
+  }
+  commit(bar);
+}
+
+// Same, for a layer whose K dimension is fed in chunks (the operand tiles are refilled between calls): acc0 = 0 starts the
+// accumulator, acc0 = 1 adds this chunk's products to what the previous calls left in TMEM.  The caller waits on `bar` after each call.
+inline void issue_layer_acc(uint32_t tmem_d, const char* a_hi, const char* a_lo, const char* b_hi, const char* b_lo, int N, int K,
+                                                int swap_ls, uint32_t acc0, uint32_t bar) {
+  const uint32_t kstride = 128, mstride = (uint32_t)(K >> 2) * 128;
+  const uint32_t lbo = swap_ls ? mstride : kstride, sbo = swap_ls ? kstride : mstride;
+  const uint32_t idesc = make_idesc_tf32(128, N);
+  uint32_t acc = acc0;
+  for (int p = 0; p < 3; ++p) {
+    const char* a = (p == 1) ? a_lo : a_hi;      // hi*hi, lo*hi, hi*lo
     const char* b = (p == 2) ? b_lo : b_hi;
     for (int k8 = 0; k8 < K / 8; ++k8) {
       mma_tf32(tmem_d, make_desc(op_addr(a) + k8 * 256, lbo, sbo), make_desc(op_addr(b) + k8 * 256, lbo, sbo), idesc, acc);

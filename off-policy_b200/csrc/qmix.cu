@@ -10,6 +10,7 @@
 #include "mx_kernels.h"
 
 extern int g_mx_front_tc;
+bool mx_front_tc_usable(int in_dim, bool have_image);
 
 // =====================================================================================================
 // parameter layouts (names = the reference's state_dict keys)
@@ -300,7 +301,7 @@ static int launch_prep(mx_qmix* q, cudaStream_t s) {
 // overlaps the index draw and the gather.  Optional: mx_qmix_backward_only does it itself when this was not called.
 int mx_qmix_prefork(mx_qmix* q, int B, void* stream) {
 #if !MX_EMU
-  if (!use_overlap(q, B) || !(g_mx_front_tc && q->agent.in_dim <= 64) || q->prep_pending) return 0;
+  if (!use_overlap(q, B) || !mx_front_tc_usable(q->agent.in_dim, true) || q->prep_pending) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   fork_to_side(q, q->ev_fork, s);
   if (launch_prep(q, q->side)) return 1;
@@ -360,7 +361,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   ff.theta[0] = q->theta; ff.theta[1] = q->theta_tgt; ff.L = q->agent;
   ff.gi[0] = ws + W.gi[0]; ff.gi[1] = ws + W.gi[1];
   ff.u1 = ws + W.u1; ff.u2 = ws + W.u2; ff.st0 = ws + W.st0; ff.st1 = ws + W.st1; ff.st2 = ws + W.st2;
-  if (g_mx_front_tc && q->agent.in_dim <= 64) {       // weights changed in the last Adam / Polyak: rebuild the TF32 hi/lo images (18k elements per net)
+  if (mx_front_tc_usable(q->agent.in_dim, true)) {       // weights changed in the last Adam / Polyak: rebuild the TF32 hi/lo images (18k elements per net)
     if (q->prep_pending) {                      // mx_qmix_prefork() launched it on the side branch before the batch was sampled
 #if !MX_EMU
       cudaStreamWaitEvent(s, q->ev_prep, 0);

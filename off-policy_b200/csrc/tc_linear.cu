@@ -48,6 +48,15 @@ __device__ __forceinline__ void tc_stage_weight(char* hi, char* lo, const float*
 // Weight images: [w1 hi | w1 lo | w2 hi | w2 lo | w_ih hi | w_ih lo], each already in the UMMA core-matrix layout, so a CTA
 // stages all three layers with straight 16-byte cp.async copies (no per-CTA conversion).  Rebuilt once per step.
 struct TcPrepArgs { const float* th[2]; float* img[2]; };
+// fc1 image: in_dim <= 64: one [64][Kp] tile.  64 < in_dim <= 128 ("wide"): K is fed in chunks of 64 columns, each chunk its own
+// [64][Kc] hi | lo tile pair (Kc = 64, then round_up(in_dim - 64, 8)); the floats add up to 64 * Kp either way.
+__device__ __forceinline__ void tc_w1_image_slot(int n, int k, int Kp, char* base, char** hi, char** lo, int* kk, int* Kd) {
+  if (Kp <= 64) { *hi = base; *lo = base + 64 * Kp * 4; *kk = k; *Kd = Kp; return; }
+  const int c = k >> 6, Kc = c == 0 ? 64 : Kp - 64;
+  char* chunk = base + (c == 0 ? 0 : 2 * 64 * 64 * 4);
+  *hi = chunk; *lo = chunk + 64 * Kc * 4; *kk = k & 63; *Kd = Kc;
+  (void)n;
+}
 __global__ void __launch_bounds__(256) k_tc_prep_weights(TcPrepArgs p, MxNetLayout L) {
   const float* __restrict__ th = p.th[blockIdx.y];
   const int I = L.in_dim, Kp = (I + 7) & ~7;
@@ -58,7 +67,14 @@ __global__ void __launch_bounds__(256) k_tc_prep_weights(TcPrepArgs p, MxNetLayo
     int n, k, K, Kd;
     const float* W;
     char *hi, *lo;
-    if (idx < n1) { n = idx / Kp; k = idx - n * Kp; K = I; Kd = Kp; W = th + L.w1; hi = base; lo = base + n1 * 4; }
+    if (idx < n1) {
+      n = idx / Kp; k = idx - n * Kp; K = I; W = th + L.w1;
+      const float x = k < K ? W[(size_t)n * K + k] : 0.f;
+      int kk;
+      tc_w1_image_slot(n, k, Kp, base, &hi, &lo, &kk, &Kd);
+      tc::put_split(hi, lo, n, kk, Kd, x);
+      continue;
+    }
     else if (idx < n1 + n2) { const int j = idx - n1; n = j / MX_H; k = j % MX_H; K = MX_H; Kd = MX_H; W = th + L.w2; hi = base + 2 * n1 * 4; lo = hi + n2 * 4; }
     else { const int j = idx - n1 - n2; n = j / MX_H; k = j % MX_H; K = MX_H; Kd = MX_H; W = th + L.wih; hi = base + (2 * n1 + 2 * n2) * 4; lo = hi + n3 * 4; }
     tc::put_split(hi, lo, n, k, Kd, k < K ? W[(size_t)n * K + k] : 0.f);
@@ -263,15 +279,216 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
   if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
 }
 
+
+// =====================================================================================================
+// Wide inputs (64 < in_dim <= 128: SMAC 8m / 2s3z observations): same pipeline, but fc1's K dimension is fed in chunks of 64
+// columns that accumulate in TMEM -- the A tile stays [128][64] and only one fc1 weight chunk is resident (restaged per tile from
+// the L2-resident image), so that fc2 and W_ih (96 KB as hi / lo) still fit beside them: 224 KB of dynamic shared memory.
+// =====================================================================================================
+__global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, FrontTcSmem sm, int swap_ls) {
+  MX_DYN_SMEM_RAW(smem_raw);
+  __shared__ __align__(8) tc::Bar bar_s;
+  __shared__ uint32_t tmem_s;
+  __shared__ float par_s[6 * MX_H + MX_G];      // b1,g1,be1,b2,g2,be2 | b_ih   (the feature-norm rows are read through L1: no room)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int net = blockIdx.y;
+  const float* __restrict__ th = a.theta[net];
+  const MxNetLayout L = a.L;
+  const bool live = (net == 0);
+  const int I = L.in_dim, Kp = (I + 7) & ~7, Kc1 = Kp - 64;
+  char* base = reinterpret_cast<char*>(smem_raw);
+  char *a_hi = base + sm.o_ahi, *a_lo = base + sm.o_alo;
+  char *w1h = base + sm.o_w1h, *w2h = base + sm.o_w2h, *w2l = base + sm.o_w2l, *wih = base + sm.o_wih, *wil = base + sm.o_wil;
+  const uint32_t bar = tc::bar_addr(&bar_s);
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_s);
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::mbar_init_fence();
+  }
+  for (int i = tid; i < MX_H; i += blockDim.x) {
+    par_s[i] = th[L.b1 + i]; par_s[MX_H + i] = th[L.ln1_g + i]; par_s[2 * MX_H + i] = th[L.ln1_b + i];
+    par_s[3 * MX_H + i] = th[L.b2 + i]; par_s[4 * MX_H + i] = th[L.ln2_g + i]; par_s[5 * MX_H + i] = th[L.ln2_b + i];
+  }
+  for (int i = tid; i < MX_G; i += blockDim.x) par_s[6 * MX_H + i] = th[L.bih + i];
+  MX_PDL_WAIT();
+  const float* img = a.tc_img[net];
+  const float* img_w1c[2] = {img, img + 2 * 64 * 64};
+  {   // resident layers: fc2 and W_ih (contiguous in the image after the two fc1 chunks, contiguous in shared memory from o_w2h)
+    const float* src = img + 2 * 64 * Kp;
+    float* dst = reinterpret_cast<float*>(w2h);
+    const int nvec = (sm.total - sm.o_w2h) >> 4;
+    for (int v = tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
+    mx_cp_commit();
+  }
+  const float* bih_s = par_s + 6 * MX_H;
+  const float* fng = th + L.fn_g;
+  const float* fnb = th + L.fn_b;
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = tmem_s;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  uint32_t phase = 0;
+  const int ntiles = (a.M + 127) / 128;
+  const int I4 = (I + 3) >> 2;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m = tile * 128 + tid;
+    const bool ok = m < a.M;
+    const float* xrow = a.X + (size_t)(ok ? m : 0) * a.ldx;
+    // ---- row statistics over all I features (two reads of the row; the second pass and the chunk loads below hit L1) ----
+    float mean = 0.f, rstd = 1.f;
+    {
+      float p[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c4 = 0; c4 < I4; ++c4) {
+        const float4 v = ok ? *reinterpret_cast<const float4*>(xrow + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        p[0] += (4 * c4 < I) ? v.x : 0.f; p[1] += (4 * c4 + 1 < I) ? v.y : 0.f; p[2] += (4 * c4 + 2 < I) ? v.z : 0.f; p[3] += (4 * c4 + 3 < I) ? v.w : 0.f;
+      }
+      mean = ((p[0] + p[1]) + (p[2] + p[3])) / (float)I;
+      float q[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c4 = 0; c4 < I4; ++c4) {
+        const float4 v = ok ? *reinterpret_cast<const float4*>(xrow + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float d0 = (4 * c4 < I) ? v.x - mean : 0.f, d1 = (4 * c4 + 1 < I) ? v.y - mean : 0.f, d2 = (4 * c4 + 2 < I) ? v.z - mean : 0.f,
+                    d3 = (4 * c4 + 3 < I) ? v.w - mean : 0.f;
+        q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
+      }
+      rstd = rsqrtf(((q[0] + q[1]) + (q[2] + q[3])) / (float)I + MX_LN_EPS);
+      if (live && ok && a.st0) { a.st0[2 * (size_t)m] = mean; a.st0[2 * (size_t)m + 1] = rstd; }
+    }
+    // ---- fc1 in two K chunks: stage the weight chunk, write the normalised input chunk as the A tile, accumulate ----
+    for (int ch = 0; ch < 2; ++ch) {
+      const int Kc = ch == 0 ? 64 : Kc1;
+      {
+        const float* src = img_w1c[ch];
+        float* dst = reinterpret_cast<float*>(w1h);
+        const int nvec = (2 * 64 * Kc * 4) >> 4;          // hi tile then lo tile, contiguous in the image
+        for (int v = tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
+        mx_cp_commit();
+      }
+      for (int c4 = 0; 4 * c4 < Kc; ++c4) {
+        const int c0 = 64 * ch + 4 * c4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && c0 < I) v = *reinterpret_cast<const float4*>(xrow + c0);
+        float x[4] = {v.x, v.y, v.z, v.w};
+        float4 h, l;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j;
+          x[j] = (ok && c < I) ? (a.feature_norm ? ((x[j] - mean) * rstd * fng[c] + fnb[c]) : x[j]) : 0.f;
+        }
+        h.x = tc::to_tf32(x[0]); h.y = tc::to_tf32(x[1]); h.z = tc::to_tf32(x[2]); h.w = tc::to_tf32(x[3]);
+        l.x = x[0] - h.x; l.y = x[1] - h.y; l.z = x[2] - h.z; l.w = x[3] - h.w;
+        const uint32_t o = tc::core_off_bytes(tid, 4 * c4, Kc);
+        *reinterpret_cast<float4*>(a_hi + o) = h;
+        *reinterpret_cast<float4*>(a_lo + o) = l;
+      }
+      mx_cp_wait<0>();
+      tc::fence_async_smem();
+      tc::fence_before();
+      __syncthreads();
+      tc::fence_after();
+      if (tid == 0) tc::issue_layer_acc(tmem_base, a_hi, a_lo, w1h, w1h + 64 * Kc * 4, MX_H, Kc, swap_ls, ch > 0 ? 1u : 0u, bar);
+      tc::mbar_wait(bar, phase);        // the MMAs have read the A tile and the weight chunk: both may be refilled
+      phase ^= 1;
+      tc::fence_after();
+    }
+    // ---- fc1 epilogue, then fc2 (weights resident) ----
+    for (int layer = 0; layer < 2; ++layer) {
+      if (layer == 1) {
+        tc::fence_async_smem();
+        tc::fence_before();
+        __syncthreads();
+        tc::fence_after();
+        if (tid == 0) tc::issue_layer(tmem_base, a_hi, a_lo, w2h, w2l, MX_H, MX_H, 3, swap_ls, bar);
+        tc::mbar_wait(bar, phase);
+        phase ^= 1;
+        tc::fence_after();
+      }
+      float v[64];
+      tc::tmem_ld64(tmem_row, v);
+      const float* bs = par_s + layer * 3 * MX_H;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) v[c] = fmaxf(v[c] + bs[c], 0.f);
+      const float mu = tc_sum64(v) * (1.f / 64.f);
+      const float rs = rsqrtf(tc_sumsq64(v, mu, 64) * (1.f / 64.f) + MX_LN_EPS);
+      float* u_out = layer == 0 ? a.u1 : a.u2;
+      float* st_out = layer == 0 ? a.st1 : a.st2;
+      if (live && ok && u_out) {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) *reinterpret_cast<float4*>(u_out + (size_t)m * MX_H + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        if (st_out) { st_out[2 * (size_t)m] = mu; st_out[2 * (size_t)m + 1] = rs; }
+      }
+#pragma unroll
+      for (int c = 0; c < 64; ++c) v[c] = (v[c] - mu) * rs * bs[MX_H + c] + bs[2 * MX_H + c];
+      tc::fence_before();
+      __syncthreads();          // every thread has drained its TMEM reads before the next layer's MMAs overwrite the accumulator
+      tc::fence_after();
+      tc_put_row64(a_hi, a_lo, tid, v);
+    }
+    // ---- gi = x2 . W_ih^T + b_ih ----
+    tc::fence_async_smem();
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    if (tid == 0) tc::issue_layer(tmem_base, a_hi, a_lo, wih, wil, MX_G, MX_H, 3, swap_ls, bar);
+    tc::mbar_wait(bar, phase);
+    phase ^= 1;
+    tc::fence_after();
+    float* gi = a.gi[net];
+#pragma unroll 1
+    for (int c0 = 0; c0 < MX_G; c0 += 64) {
+      float t0[64];
+      tc::tmem_ld64(tmem_row + c0, t0);
+      if (ok) {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4)
+          *reinterpret_cast<float4*>(gi + (size_t)m * MX_G + c0 + 4 * c4) =
+              make_float4(t0[4 * c4] + bih_s[c0 + 4 * c4], t0[4 * c4 + 1] + bih_s[c0 + 4 * c4 + 1], t0[4 * c4 + 2] + bih_s[c0 + 4 * c4 + 2],
+                          t0[4 * c4 + 3] + bih_s[c0 + 4 * c4 + 3]);
+      }
+    }
+    tc::fence_before();
+    __syncthreads();     // TMEM reads drained; the A tile and the fc1 chunk buffer are free for the next tile
+    tc::fence_after();
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
+}
+
 int g_mx_front_tc = 1;        // 1: tcgen05 3xTF32 kernel (default), 0: FFMA kernel (mx_set_option("front_tc", 0))
+int g_mx_front_tc_wide = 0;   // 1: 64 < in_dim <= 128 also runs on tcgen05 (k_front_fwd_tc_wide); off until it has been timed on a B200
 int g_mx_tc_swap = 0;
 int g_mx_mixer_rm = 0;        // tuning overrides (0 = automatic): rows per thread of the mixer / backward front tiles
 int g_mx_front_bwd_rm = 0;
 
+bool mx_front_tc_usable(int in_dim, bool have_image) {
+  if (!g_mx_front_tc) return false;
+  return in_dim <= 64 || (g_mx_front_tc_wide && in_dim <= 128 && have_image);
+}
+
 int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
+  const bool wide = a.L.in_dim > 64;
   const int Kp = mx_round_up(a.L.in_dim, 8);
-  FrontTcSmem sm = front_tc_smem(Kp);
+  FrontTcSmem sm = front_tc_smem(wide ? 64 : Kp);
   const size_t smem = (size_t)sm.total;
+  const int ntiles = mx_ceil_div(a.M, 128);
+  int gx = mx_num_sms() / nets;
+  if (gx > ntiles) gx = ntiles;
+  if (gx < 1) gx = 1;
+  if (wide) {
+    if (!a.tc_img[0] || (nets > 1 && !a.tc_img[1])) { mx_set_error("front_fwd_tc_wide: weight images missing"); return 1; }
+#if !MX_EMU
+    static bool configured_w = false;
+    if (!configured_w) {
+      if (cudaFuncSetAttribute(k_front_fwd_tc_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { mx_set_error("front_fwd_tc_wide: smem %zu too large", smem); return 1; }
+      configured_w = true;
+    }
+#endif
+    MX_LAUNCH_PDL(k_front_fwd_tc_wide, dim3(gx, nets), dim3(128), smem, s, a, sm, g_mx_tc_swap);
+    MX_COUNT();
+    MX_MARK("k_front_fwd_tc_wide", s);
+    return MX_CHECK_LAUNCH("front_fwd_tc_wide");
+  }
 #if !MX_EMU
   static size_t configured = 0;
   if (smem > configured) {
@@ -279,10 +496,6 @@ int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
     configured = smem;
   }
 #endif
-  const int ntiles = mx_ceil_div(a.M, 128);
-  int gx = mx_num_sms() / nets;
-  if (gx > ntiles) gx = ntiles;
-  if (gx < 1) gx = 1;
   MX_LAUNCH_PDL(k_front_fwd_tc, dim3(gx, nets), dim3(128), smem, s, a, sm, g_mx_tc_swap);
   MX_COUNT();
   MX_MARK("k_front_fwd_tc", s);
@@ -292,6 +505,7 @@ int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
 extern "C" int mx_set_option(const char* name, int32_t value) {
   if (mx_set_option_common(name, value) == 0) return 0;
   if (!strcmp(name, "front_tc")) { g_mx_front_tc = value; return 0; }
+  if (!strcmp(name, "front_tc_wide")) { g_mx_front_tc_wide = value; return 0; }
   if (!strcmp(name, "tc_swap_ls")) { g_mx_tc_swap = value; return 0; }
   if (!strcmp(name, "mixer_rm")) { g_mx_mixer_rm = value; return 0; }
   if (!strcmp(name, "front_bwd_rm")) { g_mx_front_bwd_rm = value; return 0; }

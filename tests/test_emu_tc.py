@@ -36,3 +36,44 @@ def test_qmix_step_front_paths_match_reference_golden(emu_engine, front_tc):
         qc.check_step_against(None, "qmix_5ag")
     finally:
         lib.mx_set_option(b"front_tc", 1)
+
+
+@pytest.mark.parametrize("obs_dim", [65, 80, 100, 128])
+def test_wide_input_front_kernel_vs_oracle(emu_engine, obs_dim):
+    """64 < obs_dim <= 128 (SMAC 8m / 2s3z observations are 80 wide): fc1's K dimension fed to the tensor core in two chunks that
+    accumulate in TMEM (k_front_fwd_tc_wide, option front_tc_wide).  More than 128 rows so a CTA runs several tiles."""
+    from oracle.qmix import QmixConfig, synth_batch
+    lib = emu_engine.lib()
+    cfg = QmixConfig(n_agents=5, obs_dim=obs_dim, act_dim=6, state_dim=20, gain=1.0)
+    B, T = 24, 5           # 24 * 6 * 5 = 720 rows: 6 tiles on the emulator's 4 "SMs" / 2 nets
+    lib.mx_set_option(b"front_tc_wide", 1)
+    try:
+        L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T, debug=False)
+        batch = synth_batch(cfg, B, T, seed=4, avail_p=0.7, var_len=True) + (None, None)
+        # parameter bound 1e-2 * lr: an element with |g| ~ eps sees Adam amplify a 1e-6-relative gradient difference (measured 5.3e-3 * lr
+        # at obs 100, with the gradients themselves equal to 9e-7 of their maximum)
+        qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
+    finally:
+        lib.mx_set_option(b"front_tc_wide", 0)
+
+
+def test_wide_input_kernel_is_what_runs(emu_engine):
+    from oracle.qmix import QmixConfig, synth_batch
+    lib = emu_engine.lib()
+    cfg = QmixConfig(n_agents=2, obs_dim=80, act_dim=4, state_dim=10, gain=1.0)
+    names = {}
+    for opt in (0, 1):
+        lib.mx_set_option(b"front_tc_wide", opt)
+        try:
+            L, args, pol, tr = qc.oracle_and_trainer(cfg, 3, 2, debug=False)
+            import ctypes as C
+            lib.mx_profile_begin(None)
+            tr.train_policy_on_batch(qc.ref_tuple(synth_batch(cfg, 3, 2, seed=1) + (None, None)))
+            buf = C.create_string_buffer(8192)
+            ms = (C.c_float * 128)()
+            n = lib.mx_profile_end(None, buf, 8192, ms, 128)
+            names[opt] = buf.value.decode().split(";")[:n]
+        finally:
+            lib.mx_set_option(b"front_tc_wide", 0)
+    assert "k_front_fwd" in names[0] and "k_front_fwd_tc_wide" not in names[0]
+    assert "k_front_fwd_tc_wide" in names[1] and "k_front_fwd" not in names[1] and "k_tc_prep_weights" in names[1]

@@ -45,3 +45,28 @@ def test_mlp_buffer_vs_reference_golden(gpu_engine):
 def test_mlp_step_graph_vs_eager(gpu_engine, per):
     import mqmix_checks as mc
     mc.check_step_graph_vs_eager(per=per, B=1000, E=4096)
+
+
+@pytest.mark.parametrize("obs_dim,n_agents,B,T", [(80, 8, 8, 20), (128, 3, 16, 12), (72, 5, 32, 10)])
+def test_wide_input_tcgen05_front_kernel_vs_oracle(gpu_engine, obs_dim, n_agents, B, T):
+    """k_front_fwd_tc_wide (64 < obs_dim <= 128, option front_tc_wide, off by default until timed): emulator-verified indexing; this is its
+    first run on real tensor cores.  Runs under a launch-count check that the wide kernel, not the FFMA one, executed."""
+    import ctypes as C
+    import numpy as np
+    from oracle.qmix import QmixConfig, synth_batch
+    lib = gpu_engine.lib()
+    cfg = QmixConfig(n_agents=n_agents, obs_dim=obs_dim, act_dim=7, state_dim=40, gain=1.0)
+    lib.mx_set_option(b"front_tc_wide", 1)
+    try:
+        L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T, debug=False)
+        tr.use_step_graph = False
+        batch = synth_batch(cfg, B, T, seed=4, avail_p=0.7, var_len=True) + (None, None)
+        lib.mx_profile_begin(gpu_engine.stream_ptr())
+        qc.compare_step(L, pol, tr, batch, cfg, steps=1, param_tol=1e-2)
+        buf = C.create_string_buffer(8192)
+        ms = (C.c_float * 256)()
+        n = lib.mx_profile_end(gpu_engine.stream_ptr(), buf, 8192, ms, 256)
+        assert "k_front_fwd_tc_wide" in buf.value.decode().split(";")[:n]
+        qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
+    finally:
+        lib.mx_set_option(b"front_tc_wide", 0)

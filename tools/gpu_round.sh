@@ -15,6 +15,10 @@ if [ "${2:-}" != "quick" ]; then
   timeout 200 python bench.py --workload qmix_8m_per --steps 50 --warmup 5 --buffer 2000 > gpurun_out/bench_8m.json 2> gpurun_out/bench_8m.err; cut -c1-200 gpurun_out/bench_8m.json
   timeout 200 python bench.py --workload qmix_mpe_spread --steps 300 --warmup 20 > gpurun_out/bench_mpe.json 2> gpurun_out/bench_mpe.err; cut -c1-200 gpurun_out/bench_mpe.json
   timeout 300 python bench.py --workload mqmix_mpe_spread --steps 300 --warmup 20 > gpurun_out/bench_mlp.json 2> gpurun_out/bench_mlp.err; cut -c1-200 gpurun_out/bench_mlp.json
+  # option candidates prepared without a GPU (off by default until timed): wide-input tcgen05 front kernel on the obs-80 workloads
+  for o in 0 1; do for w in qmix_8m_per qmix_2s3z; do
+    timeout 200 python bench.py --workload $w --quick --steps 50 --warmup 5 --buffer 2000 --opt front_tc_wide=$o >> gpurun_out/sweep_wide.log 2>> gpurun_out/sweep_wide.err
+  done; done; cat gpurun_out/sweep_wide.log
   timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-200 gpurun_out/bench_ref.json
   timeout 200 python tools/gather_sweep.py > gpurun_out/gather_sweep.log 2> gpurun_out/gather_sweep.err; cut -c1-200 gpurun_out/gather_sweep.log
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv \
