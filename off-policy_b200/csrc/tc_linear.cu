@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
   MX_DYN_SMEM_RAW(smem_raw);
   __shared__ __align__(8) tc::Bar bar_s;
   __shared__ uint32_t tmem_s;
-  __shared__ float par_s[6 * MX_H + MX_G];      // b1,g1,be1,b2,g2,be2 | b_ih   (the feature-norm rows are read through L1: no room)
+  __shared__ float par_s[6 * MX_H];             // b1,g1,be1,b2,g2,be2   (b_ih and the feature-norm rows are read through L1: the dynamic
+                                                // 224 KB leave ~3 KB of static shared memory under the 227 KB per-CTA limit)
   const int tid = threadIdx.x, warp = tid >> 5;
   const int net = blockIdx.y;
   const float* __restrict__ th = a.theta[net];
@@ -309,7 +310,6 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
     par_s[i] = th[L.b1 + i]; par_s[MX_H + i] = th[L.ln1_g + i]; par_s[2 * MX_H + i] = th[L.ln1_b + i];
     par_s[3 * MX_H + i] = th[L.b2 + i]; par_s[4 * MX_H + i] = th[L.ln2_g + i]; par_s[5 * MX_H + i] = th[L.ln2_b + i];
   }
-  for (int i = tid; i < MX_G; i += blockDim.x) par_s[6 * MX_H + i] = th[L.bih + i];
   MX_PDL_WAIT();
   const float* img = a.tc_img[net];
   const float* img_w1c[2] = {img, img + 2 * 64 * 64};
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
     for (int v = tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
     mx_cp_commit();
   }
-  const float* bih_s = par_s + 6 * MX_H;
+  const float* bih_s = th + L.bih;
   const float* fng = th + L.fn_g;
   const float* fnb = th + L.fn_b;
   tc::fence_before();
