@@ -20,6 +20,8 @@ def main():
     capi._install_for_tests(LIB)
     import qmix_checks as qc
     from helpers import load_golden, oracle_from_golden, golden_batch, sub
+    if len(sys.argv) > 2 and sys.argv[2] == "mlp":
+        return main_mlp(out_dir, rank, world)
     g = load_golden("qmix_small")
     L, cfg, B, T, steps = oracle_from_golden(g)
     Bl = B // world
@@ -30,6 +32,30 @@ def main():
     sl = slice(rank * Bl, (rank + 1) * Bl)
     shard = tuple(x[..., sl, :] if x.ndim == 4 else x[:, sl] for x in full[:7]) + (None, None)
     info, _, _ = tr.train_policy_on_batch(qc.ref_tuple(shard))
+    tr.soft_target_updates()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), loss=float(info["loss"]), grad_norm=float(info["grad_norm"]),
+             Q_tot=float(info["Q_tot"]), theta=tr.theta.numpy(), theta_tgt=tr.theta_tgt.numpy())
+    dist.destroy_process_group()
+
+
+def main_mlp(out_dir, rank, world):
+    """M_QMix (transition-level path): each rank trains on its slice of the golden transition batch."""
+    import mqmix_checks as mc
+    from helpers import load_golden, golden_cfg, sub
+    g = load_golden("mqmix_small")
+    cfg, B, T, steps = golden_cfg(g)
+    Bl = B // world
+    args, pol, tr = mc.build(cfg, Bl, debug=False)
+    assert tr.world_size == world
+    pol.q_network.load_state_dict(sub(g, "init.agent."))
+    tr.target_q_network.load_state_dict(sub(g, "init.tgt_agent."))
+    tr.mixer.load_state_dict(sub(g, "init.mixer."))
+    tr.target_mixer.load_state_dict(sub(g, "init.tgt_mixer."))
+    full = mc.golden_transitions(g, 0)
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    cut = lambda d: {"policy_0": None if d["policy_0"] is None else (d["policy_0"][:, sl] if d["policy_0"].ndim == 3 else d["policy_0"][sl])}
+    shard = tuple(cut(d) for d in full[:11]) + (None, None)
+    info, _, _ = tr.train_policy_on_batch(shard, True)
     tr.soft_target_updates()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), loss=float(info["loss"]), grad_norm=float(info["grad_norm"]),
              Q_tot=float(info["Q_tot"]), theta=tr.theta.numpy(), theta_tgt=tr.theta_tgt.numpy())

@@ -7,20 +7,22 @@ import sys
 import tempfile
 
 import numpy as np
+import pytest
 
 from helpers import load_golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_rank_step_equals_single_batch_reference(emu_engine):
-    g = load_golden("qmix_small")
+@pytest.mark.parametrize("mode,golden", [("rnn", "qmix_small"), ("mlp", "mqmix_small")])
+def test_two_rank_step_equals_single_batch_reference(emu_engine, mode, golden):
+    g = load_golden(golden)
     with tempfile.TemporaryDirectory() as td:
-        port = 29500 + os.getpid() % 1000
+        port = 29500 + (os.getpid() + (7 if mode == "mlp" else 0)) % 1000
         procs = []
         for r in range(2):
             env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
-            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dp_worker.py"), td], env=env,
+            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dp_worker.py"), td, mode], env=env,
                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
         outs = [p.communicate(timeout=600)[0].decode() for p in procs]
         assert all(p.returncode == 0 for p in procs), "\n".join(outs)
