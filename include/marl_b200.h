@@ -331,8 +331,14 @@ void mx_graph_destroy(mx_graph* g);
  * carries the K-direction core-matrix stride.  N % 16 == 0, N <= 256, K % 8 == 0, K <= 64. */
 int mx_tc_linear_probe(const float* X, const float* W, float* Y, int32_t M, int32_t N, int32_t K, int32_t passes, int32_t swap_ls, void* stream);
 
-/* runtime options: "front_tc" = 1 routes the time-batched front layers through the tcgen05 3xTF32 kernel (k_front_fwd_tc)
- * instead of the FFMA kernel; "tc_swap_ls" selects the shared-memory descriptor stride convention (see mx_tc_linear_probe). */
+/* Runtime options (process-wide tuning switches; defaults = the configuration measured on the B200).  Returns 1 for an unknown name.
+ *   front_tc (1)        time-batched front layers on the tcgen05 3xTF32 kernel (input width <= 64); 0 = the FFMA kernel
+ *   front_tc_wide (0)   64 < input width <= 128 on tcgen05 too (k_front_fwd_tc_wide; emulator-verified, off until timed on a B200)
+ *   tc_swap_ls (0)      shared-memory descriptor stride convention (see mx_tc_linear_probe)
+ *   overlap (1) / overlap_rows (12288)   state-only kernels on a forked stream / graph branch: 0 off, 1 when B*(T+1)*N <= overlap_rows, 2 always
+ *   mixer_split (1), mid_fused (1)       split hypernet / core mixer kernels; k_mid between the recurrences (0 = separate kernels)
+ *   mixer_rm, mixer_split_rm, front_bwd_rm, gru_fwd_rpc, gru_bwd_rpc (0 = automatic)   tile heights / rows per CTA
+ *   pdl (0)             programmatic dependent launch for eager (non-graph) launches */
 int mx_set_option(const char* name, int32_t value);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches counter) */
