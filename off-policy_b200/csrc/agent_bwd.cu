@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
   const int T1 = a.T1 > 0 ? a.T1 : a.T + 1, N = a.N;
   const bool ldx_vec = (a.ldx & 3) == 0;
   const bool wg = !a.skip_wgrad;
+  const bool wgemm = wg && !a.wgrad_external;      // the weight-gradient GEMMs and bias column sums run here (else: k_wgrad_tc)
   float* dx0_s = smem + sm.o_dx0;
   float* gp = a.gpart + (size_t)blockIdx.x * a.P;
   for (int i = tid; i < 2 * I64 + 4 * 64; i += MX_TILE_THREADS) col0g[i] = 0.f;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     }
     __syncthreads();
     // ---- GRU weight gradients: dW_ih = dgi^T x2 ; dW_hh = [dgi_r, dgi_z, dgi_n*r]^T h_{t-1} ----
-    if (wg) {
+    if (wgemm) {
       for (int nb = 0; nb < 3; ++nb) {
         mx_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
         if (a.no_gru) continue;
@@ -389,6 +390,13 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     __syncthreads();     // x_s (x2), u_s (u2) no longer needed by anyone
 #pragma unroll
     for (int i = 0; i < RM; ++i) mx_st4(da_s + (ty * RM + i) * sm.ld64 + 4 * tx, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+    if (a.wgrad_external) {
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        const int m = m0 + ty * RM + i;
+        if (m < a.M) mx_st4(a.da2_out + (size_t)m * MX_H + 4 * tx, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+      }
+    }
     mx_stage_rows(u_s, sm.ld64, a.u1, MX_H, m0, a.M, TM, MX_H);
     mx_cp_commit();
     mx_cp_wait<0>();
@@ -400,7 +408,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     }
     __syncthreads();
     // ---- fc2: dW2 = da2^T x1, db2 ; dx1 = da2 . W2 ----
-    if (wg) {
+    if (wgemm) {
       mx_wgrad_block(da_s, sm.ld64, x_s, sm.ld64, TM, gp + L.w2, MX_H, MX_H, 0, 0, accum);
       mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b2, accum);
     }
@@ -415,6 +423,13 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     __syncthreads();     // da_s (da2) consumed by everyone
 #pragma unroll
     for (int i = 0; i < RM; ++i) mx_st4(da_s + (ty * RM + i) * sm.ld64 + 4 * tx, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+    if (a.wgrad_external) {
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        const int m = m0 + ty * RM + i;
+        if (m < a.M) mx_st4(a.da1_out + (size_t)m * MX_H + 4 * tx, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+      }
+    }
     // x0 = LN0(x) and the normalised input, in place over the staged raw rows
     for (int idx = tid; idx < TM * I64; idx += MX_TILE_THREADS) {
       const int r = idx / I64, c = idx - r * I64, m = m0 + r;
@@ -430,7 +445,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     }
     __syncthreads();
     // ---- fc1: dW1 = da1^T x0, db1 ; dx0 = da1 . W1 (only for the LN0 gain/bias) ----
-    if (wg) {
+    if (wgemm) {
       for (int kb = 0; kb * 64 < I; ++kb) mx_wgrad_block(da_s, sm.ld64, x0_s + kb * 64, sm.ldi, TM, gp + L.w1, MX_H, I, 0, kb * 64, accum);
       mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b1, accum);
     }
@@ -616,9 +631,14 @@ static int front_bwd_launch(const FrontBwdArgs& a, int* nparts_used, cudaStream_
 }
 
 extern int g_mx_front_bwd_rm;
-int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
+int mx_launch_front_bwd(const FrontBwdArgs& a_in, int* nparts_used, cudaStream_t s) {
+  FrontBwdArgs a = a_in;
+  a.wgrad_external = mx_wgrad_tc_usable(a) ? 1 : 0;
   const int rm = g_mx_front_bwd_rm ? g_mx_front_bwd_rm : front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms());
-  if (rm == 3) return front_bwd_launch<3>(a, nparts_used, s);
-  if (rm == 4) return front_bwd_launch<4>(a, nparts_used, s);
-  return front_bwd_launch<2>(a, nparts_used, s);
+  int rc;
+  if (rm == 3) rc = front_bwd_launch<3>(a, nparts_used, s);
+  else if (rm == 4) rc = front_bwd_launch<4>(a, nparts_used, s);
+  else rc = front_bwd_launch<2>(a, nparts_used, s);
+  if (rc || !a.wgrad_external) return rc;
+  return mx_launch_wgrad_tc(a, *nparts_used, s);      // one gradient partial per k_front_bwd CTA: the same rows of gpart
 }

@@ -162,8 +162,15 @@ struct FrontBwdArgs {
   int no_gru;              // 1: MLP variant -- no recurrent weights: gates / hall are not read, dW_hh / db_hh are not produced
   float* dX;               // optional: gradient w.r.t. the input rows [M][ldx] (through the feature LayerNorm)
   int skip_wgrad;          // 1: data gradient only (frozen network)
+  // tensor-core weight gradients (tc_bwd.cu, option wgrad_tc): when both buffers are given and the option is on, k_front_bwd keeps
+  // the data-gradient chain and the LayerNorm gain / bias gradients, writes the two intermediate row gradients here, and
+  // k_wgrad_tc produces every dW / db of the front layers and the GRU input / recurrent matrices from them
+  float *da2_out, *da1_out;   // [M][H] each: gradient at the fc2 / fc1 pre-activation outputs (after the ReLU mask)
+  int wgrad_external;      // set by the launcher, not by callers
 };
 int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s);
+int mx_launch_wgrad_tc(const FrontBwdArgs& a, int nparts, cudaStream_t s);
+bool mx_wgrad_tc_usable(const FrontBwdArgs& a);
 
 struct OptimArgs {
   float *theta, *theta_tgt, *adam_m, *adam_v;

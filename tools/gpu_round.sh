@@ -19,6 +19,10 @@ if [ "${2:-}" != "quick" ]; then
   for o in 0 1; do for w in qmix_8m_per qmix_2s3z; do
     timeout 200 python bench.py --workload $w --quick --steps 50 --warmup 5 --buffer 2000 --opt front_tc_wide=$o >> gpurun_out/sweep_wide.log 2>> gpurun_out/sweep_wide.err
   done; done; cat gpurun_out/sweep_wide.log
+  # tensor-core weight-gradient kernel (k_wgrad_tc) on the headline workload and on 8m
+  for o in 0 1; do for w in qmix_3m qmix_8m_per; do
+    timeout 200 python bench.py --workload $w --quick --steps 100 --warmup 10 --buffer 2000 --opt wgrad_tc=$o >> gpurun_out/sweep_wgrad.log 2>> gpurun_out/sweep_wgrad.err
+  done; done; cat gpurun_out/sweep_wgrad.log
   timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-200 gpurun_out/bench_ref.json
   timeout 200 python tools/gather_sweep.py > gpurun_out/gather_sweep.log 2> gpurun_out/gather_sweep.err; cut -c1-200 gpurun_out/gather_sweep.log
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv \
