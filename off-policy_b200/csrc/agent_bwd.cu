@@ -631,7 +631,10 @@ static int front_bwd_launch(const FrontBwdArgs& a, int* nparts_used, cudaStream_
 }
 
 extern int g_mx_front_bwd_rm;
+bool mx_front_bwd_tc_usable(const FrontBwdArgs& a);
+int mx_launch_front_bwd_tc(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s);
 int mx_launch_front_bwd(const FrontBwdArgs& a_in, int* nparts_used, cudaStream_t s) {
+  if (mx_front_bwd_tc_usable(a_in)) return mx_launch_front_bwd_tc(a_in, nparts_used, s);
   FrontBwdArgs a = a_in;
   a.wgrad_external = mx_wgrad_tc_usable(a) ? 1 : 0;
   const int rm = g_mx_front_bwd_rm ? g_mx_front_bwd_rm : front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms());

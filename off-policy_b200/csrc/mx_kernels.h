@@ -167,7 +167,9 @@ struct FrontBwdArgs {
   // k_wgrad_tc produces every dW / db of the front layers and the GRU input / recurrent matrices from them
   float *da2_out, *da1_out;   // [M][H] each: gradient at the fc2 / fc1 pre-activation outputs (after the ReLU mask)
   int wgrad_external;      // set by the launcher, not by callers
+  float* tc_imgT;          // scratch for the transposed TF32 weight images of the all-tensor-core backward (option wgrad_tc = 2)
 };
+size_t mx_tc_imageT_floats(int in_dim);
 int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s);
 int mx_launch_wgrad_tc(const FrontBwdArgs& a, int nparts, cudaStream_t s);
 bool mx_wgrad_tc_usable(const FrontBwdArgs& a);

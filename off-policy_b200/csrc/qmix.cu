@@ -157,6 +157,7 @@ static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W
   W->tcimg[0] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c))); W->tcimg[1] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c)));
   W->xin = tk(c->prev_act_inp ? M * mx_round_up(agent_in_dim(c), 4) : 0);
   W->da2 = tk(c->mlp ? 0 : M * MX_H); W->da1 = tk(c->mlp ? 0 : M * MX_H);
+  W->tcimgT = tk((int64_t)mx_tc_imageT_floats(agent_in_dim(c)));
   {
     const int64_t gH = mx_round_up(c->hyper_hidden, 4), gM = mx_round_up(c->mixer_hidden, 4), gP = mx_round_up(c->n_agents * c->mixer_hidden, 4);
     const int64_t En = c->vdn ? 0 : E;
@@ -489,7 +490,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   fb.X = X; fb.ldx = ldx; fb.M = M; fb.T = T; fb.N = N; fb.feature_norm = 1;
   fb.theta = q->theta; fb.L = q->agent; fb.u1 = ff.u1; fb.u2 = ff.u2; fb.st0 = ff.st0; fb.st1 = ff.st1; fb.st2 = ff.st2;
   fb.dgi = gb.dgi; fb.gates = gf.gates; fb.hall = gf.hall[0]; fb.gpart = mx.gpart; fb.P = q->P;
-  fb.da2_out = ws + W.da2; fb.da1_out = ws + W.da1;      // used when the tensor-core weight-gradient kernel is enabled (option wgrad_tc)
+  fb.da2_out = ws + W.da2; fb.da1_out = ws + W.da1; fb.tc_imgT = ws + W.tcimgT;      // used when the tensor-core weight-gradient kernel is enabled (option wgrad_tc)
   if (mx_launch_front_bwd(fb, &parts[0], s)) return 1;
 
 #if !MX_EMU

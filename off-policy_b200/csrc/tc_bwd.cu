@@ -55,6 +55,7 @@ __device__ __forceinline__ void wg_pair(int p, int* feat, int* kq) {
 struct WgradArgs {
   FrontBwdArgs f;
   int nchunks, Kp16;
+  int ln_zero_from;      // CTAs from this index on also zero the LayerNorm ranges of their partial (k_front_bwd_tc ran fewer CTAs); -1: none
 };
 
 #define WG_THREADS 512        // staging is load-latency bound: 16 warps keep enough loads in flight; warps 0-3 own the TMEM lanes in the epilogue
@@ -232,6 +233,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
   if (any) tc::tmem_ld32(trow + 2 * WG_DSTRIDE + ones3, t);      // 32 columns from the ones column on (inside this accumulator's stride)
   gp[(r < 64 ? L.b2 : L.b1) + (r & 63)] = any ? t[0] : 0.f;
   }
+  if (w.ln_zero_from >= 0 && (int)blockIdx.x >= w.ln_zero_from) {
+    for (int c = tid; c < MX_H; c += blockDim.x) { gp[L.ln2_g + c] = 0.f; gp[L.ln2_b + c] = 0.f; gp[L.ln1_g + c] = 0.f; gp[L.ln1_b + c] = 0.f; }
+    for (int c = tid; c < I; c += blockDim.x) { gp[L.fn_g + c] = 0.f; gp[L.fn_b + c] = 0.f; }
+  }
   tc::fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
@@ -242,9 +247,12 @@ bool mx_wgrad_tc_usable(const FrontBwdArgs& a) {
 }
 
 extern int g_mx_tc_swap;
-int mx_launch_wgrad_tc(const FrontBwdArgs& a, int nparts, cudaStream_t s) {
+static int launch_wgrad_tc(const FrontBwdArgs& a, int nparts, int ln_zero_from, cudaStream_t s);
+int mx_launch_wgrad_tc(const FrontBwdArgs& a, int nparts, cudaStream_t s) { return launch_wgrad_tc(a, nparts, -1, s); }
+static int launch_wgrad_tc(const FrontBwdArgs& a, int nparts, int ln_zero_from, cudaStream_t s) {
   WgradArgs w;
   w.f = a;
+  w.ln_zero_from = ln_zero_from;
   w.nchunks = mx_ceil_div(a.M, WG_ROWS);
   w.Kp16 = mx_round_up(a.L.in_dim, 16);
   WgradSmem sm = wgrad_smem();
@@ -259,4 +267,271 @@ int mx_launch_wgrad_tc(const FrontBwdArgs& a, int nparts, cudaStream_t s) {
   MX_COUNT();
   MX_MARK("k_wgrad_tc", s);
   return MX_CHECK_LAUNCH("wgrad_tc");
+}
+
+
+// =====================================================================================================
+// k_front_bwd_tc: the data-gradient chain of the front layers on tcgen05 (option wgrad_tc = 2; with k_wgrad_tc it replaces
+// k_front_bwd for input widths <= 64).  Mirror image of k_front_fwd_tc: a 128-row tile per CTA, thread r owns row r, so the three
+// LayerNorm backward passes and ReLU masks run on registers after tcgen05.ld:
+//   dx2 = dgi . W_ih (K = 192 fed as three gate chunks that accumulate in TMEM) -> LN2' , ReLU' -> da2
+//   dx1 = da2 . W2 -> LN1', ReLU' -> da1 ;  dx0 = da1 . W1 -> the feature LayerNorm's gain / bias gradients
+// B operands are TRANSPOSED weight images (k_tc_prep_weights_T).  da2 / da1 go to global memory for k_wgrad_tc.  LayerNorm gain / bias
+// gradients are column sums over rows = over threads: each tile writes [dy * xhat | dy] through an XOR-swizzled scratch (the A
+// tile's shared memory, free between MMAs) and threads 0-63 / 64-127 keep running sums of one column each.
+// =====================================================================================================
+struct BwdTcSmem { int o_ahi, o_alo, o_wih, o_w2, o_w1, total; };
+static BwdTcSmem bwd_tc_smem(int Kp16) {
+  BwdTcSmem s;
+  int o = 0;
+  s.o_ahi = o; o += 128 * 64 * 4;
+  s.o_alo = o; o += 128 * 64 * 4;
+  s.o_wih = o; o += 3 * 2 * 64 * 64 * 4;      // three gate chunks, each [64][64] hi | lo
+  s.o_w2 = o; o += 2 * 64 * 64 * 4;
+  s.o_w1 = o; o += 2 * Kp16 * 64 * 4;
+  s.total = o;
+  return s;
+}
+size_t mx_tc_imageT_floats(int in_dim) { return (size_t)2 * (3 * 64 * 64 + 64 * 64 + mx_round_up(in_dim, 16) * 64); }
+
+// transposed images: B[n][k] with n = the layer's INPUT feature, k = its output feature (what the data gradient contracts over)
+__global__ void __launch_bounds__(256) k_tc_prep_weights_T(const float* __restrict__ th, MxNetLayout L, float* img) {
+  const int I = L.in_dim, Kp16 = (I + 15) & ~15;
+  const int n_ih = 3 * 64 * 64, n_2 = 64 * 64, n_1 = Kp16 * 64;
+  char* base = reinterpret_cast<char*>(img);
+  MX_PDL_WAIT();
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_ih + n_2 + n_1; idx += gridDim.x * blockDim.x) {
+    if (idx < n_ih) {
+      const int c = idx / 4096, j = idx - c * 4096, n = j >> 6, k = j & 63;          // chunk c: gates 64c .. 64c+63
+      char* hi = base + (size_t)c * 2 * 4096 * 4;
+      tc::put_split(hi, hi + 4096 * 4, n, k, 64, th[L.wih + (size_t)(64 * c + k) * MX_H + n]);
+    } else if (idx < n_ih + n_2) {
+      const int j = idx - n_ih, n = j >> 6, k = j & 63;
+      char* hi = base + (size_t)2 * n_ih * 4;
+      tc::put_split(hi, hi + 4096 * 4, n, k, 64, th[L.w2 + (size_t)k * MX_H + n]);
+    } else {
+      const int j = idx - n_ih - n_2, n = j >> 6, k = j & 63;
+      char* hi = base + (size_t)2 * (n_ih + n_2) * 4;
+      tc::put_split(hi, hi + (size_t)n_1 * 4, n, k, 64, n < I ? th[L.w1 + (size_t)k * I + n] : 0.f);
+    }
+  }
+}
+
+__device__ __forceinline__ void bt_put_row64(char* hi, char* lo, int r, const float (&x)[64]) {
+#pragma unroll
+  for (int k4 = 0; k4 < 16; ++k4) {
+    float4 h, l;
+    h.x = tc::to_tf32(x[4 * k4]); h.y = tc::to_tf32(x[4 * k4 + 1]); h.z = tc::to_tf32(x[4 * k4 + 2]); h.w = tc::to_tf32(x[4 * k4 + 3]);
+    l.x = x[4 * k4] - h.x; l.y = x[4 * k4 + 1] - h.y; l.z = x[4 * k4 + 2] - h.z; l.w = x[4 * k4 + 3] - h.w;
+    const uint32_t o = tc::core_off_bytes(r, 4 * k4, 64);
+    *reinterpret_cast<float4*>(hi + o) = h;
+    *reinterpret_cast<float4*>(lo + o) = l;
+  }
+}
+// Column sums over the tile's 128 rows of two [128][64] arrays, one row per thread.  The rows are written into two 32 KB scratch
+// arrays (element (r, c) at r * 64 + (c ^ (r & 31)): conflict-free for the row writes and for the column reads); then threads 0-63
+// add column t of the first array to their running sum, threads 64-127 column t - 64 of the second.
+#define BT_SC(r, c) ((r) * 64 + ((c) ^ ((r) & 31)))
+__device__ __forceinline__ void bt_colsum_read(const float* sc0, const float* sc1, int tid, float* acc) {
+  __syncthreads();
+  const float* sc = tid < 64 ? sc0 : sc1;
+  const int col = tid & 63;
+  float s = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 128; ++r) s += sc[BT_SC(r, col)];
+  *acc += s;
+  __syncthreads();
+}
+// LayerNorm backward + ReLU mask for one row held in registers: dy -> da (in place); the products for the gain / bias gradients go
+// straight into the scratch rows (sc0: dy * xhat, sc1: dy)
+__device__ __forceinline__ void bt_ln_bwd_relu(float (&dy)[64], const float* __restrict__ urow, bool ok, float mean, float rstd, const float* gamma_s,
+                                               float* sc0, float* sc1, int tid) {
+  float u[64];
+#pragma unroll
+  for (int c4 = 0; c4 < 16; ++c4) {
+    const float4 q = ok ? *reinterpret_cast<const float4*>(urow + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    u[4 * c4] = q.x; u[4 * c4 + 1] = q.y; u[4 * c4 + 2] = q.z; u[4 * c4 + 3] = q.w;
+  }
+  float p1[8], p2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { p1[i] = 0.f; p2[i] = 0.f; }
+#pragma unroll
+  for (int c = 0; c < 64; ++c) {
+    const float xh = ok ? (u[c] - mean) * rstd : 0.f;
+    sc0[BT_SC(tid, c)] = dy[c] * xh;
+    sc1[BT_SC(tid, c)] = dy[c];
+    const float dxh = dy[c] * gamma_s[c];
+    dy[c] = dxh;
+    p1[c & 7] += dxh;
+    p2[c & 7] = fmaf(dxh, xh, p2[c & 7]);
+  }
+  const float s1 = (((p1[0] + p1[1]) + (p1[2] + p1[3])) + ((p1[4] + p1[5]) + (p1[6] + p1[7]))) * (1.f / 64.f);
+  const float s2 = (((p2[0] + p2[1]) + (p2[2] + p2[3])) + ((p2[4] + p2[5]) + (p2[6] + p2[7]))) * (1.f / 64.f);
+#pragma unroll
+  for (int c = 0; c < 64; ++c) {
+    const float xh = ok ? (u[c] - mean) * rstd : 0.f;
+    const float du = rstd * (dy[c] - s1 - xh * s2);
+    dy[c] = u[c] > 0.f ? du : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSmem sm, int swap_ls) {
+  MX_DYN_SMEM_RAW(smem_raw);
+  __shared__ __align__(8) tc::Bar bar_s;
+  __shared__ uint32_t tmem_s;
+  __shared__ float par_s[3 * 64];            // gains: ln2 | ln1 | feature norm
+  const MxNetLayout L = a.L;
+  const float* __restrict__ th = a.theta;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int I = L.in_dim, Kp16 = (I + 15) & ~15;
+  char* base = reinterpret_cast<char*>(smem_raw);
+  char *a_hi = base + sm.o_ahi, *a_lo = base + sm.o_alo, *wih = base + sm.o_wih, *w2 = base + sm.o_w2, *w1 = base + sm.o_w1;
+  float* sc0 = reinterpret_cast<float*>(a_hi);
+  float* sc1 = reinterpret_cast<float*>(a_lo);
+  const uint32_t bar = tc::bar_addr(&bar_s);
+  if (warp == 0) tc::tmem_alloc<64>(&tmem_s);
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::mbar_init_fence();
+  }
+  for (int i = tid; i < 64; i += blockDim.x) {
+    par_s[i] = th[L.ln2_g + i]; par_s[64 + i] = th[L.ln1_g + i]; par_s[128 + i] = (a.feature_norm && i < I) ? th[L.fn_g + i] : 1.f;
+  }
+  MX_PDL_WAIT();
+  {   // the transposed weight images are byte-identical to the shared-memory weight region
+    const float* src = a.tc_imgT;
+    float* dst = reinterpret_cast<float*>(wih);
+    const int nvec = (sm.total - sm.o_wih) >> 4;
+    for (int v = tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
+    mx_cp_commit();
+  }
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = tmem_s;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  uint32_t phase = 0;
+  float acc2 = 0.f, acc1 = 0.f, acc0 = 0.f;      // running column sums: threads 0-63 gain gradients, 64-127 bias gradients
+  const int ntiles = (a.M + 127) / 128;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m = tile * 128 + tid;
+    const bool ok = m < a.M;
+    const size_t mm = ok ? (size_t)m : 0;
+    // ---- dx2 = dgi . W_ih : three gate chunks ----
+    for (int ch = 0; ch < 3; ++ch) {
+      float x[64];
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 q = ok ? *reinterpret_cast<const float4*>(a.dgi + mm * MX_G + 64 * ch + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[4 * c4] = q.x; x[4 * c4 + 1] = q.y; x[4 * c4 + 2] = q.z; x[4 * c4 + 3] = q.w;
+      }
+      bt_put_row64(a_hi, a_lo, tid, x);
+      mx_cp_wait<0>();
+      tc::fence_async_smem();
+      tc::fence_before();
+      __syncthreads();
+      tc::fence_after();
+      if (tid == 0) tc::issue_layer_acc(tmem_base, a_hi, a_lo, wih + ch * 2 * 4096 * 4, wih + ch * 2 * 4096 * 4 + 4096 * 4, 64, 64, swap_ls, ch > 0 ? 1u : 0u, bar);
+      tc::mbar_wait(bar, phase);
+      phase ^= 1;
+      tc::fence_after();
+    }
+    // ---- LN2', ReLU' -> da2 ; then fc2 and LN1', ReLU' -> da1 ----
+    for (int layer = 0; layer < 2; ++layer) {
+      float v[64];
+      tc::tmem_ld64(tmem_row, v);
+      const float* st = layer == 0 ? a.st2 : a.st1;
+      const float* uu = layer == 0 ? a.u2 : a.u1;
+      // (the MMAs that read the A tile have completed: its shared memory is the scratch until the next operand is written)
+      bt_ln_bwd_relu(v, uu + mm * MX_H, ok, ok ? st[2 * mm] : 0.f, ok ? st[2 * mm + 1] : 0.f, par_s + 64 * layer, sc0, sc1, tid);
+      bt_colsum_read(sc0, sc1, tid, layer == 0 ? &acc2 : &acc1);
+      float* da_out = layer == 0 ? a.da2_out : a.da1_out;
+      if (ok) {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) *reinterpret_cast<float4*>(da_out + mm * MX_H + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+      }
+      bt_put_row64(a_hi, a_lo, tid, v);
+      tc::fence_async_smem();
+      tc::fence_before();
+      __syncthreads();
+      tc::fence_after();
+      if (tid == 0) {
+        if (layer == 0) tc::issue_layer(tmem_base, a_hi, a_lo, w2, w2 + 4096 * 4, 64, 64, 3, swap_ls, bar);
+        else tc::issue_layer(tmem_base, a_hi, a_lo, w1, w1 + Kp16 * 64 * 4, Kp16, 64, 3, swap_ls, bar);
+      }
+      tc::mbar_wait(bar, phase);
+      phase ^= 1;
+      tc::fence_after();
+    }
+    // ---- dx0 -> gain / bias gradients of the feature LayerNorm ----
+    {
+      float v[64];
+      tc::tmem_ld64(tmem_row, v);         // columns >= Kp16 hold leftovers of the previous layer: masked below
+      const float mean = (ok && a.feature_norm) ? a.st0[2 * mm] : 0.f, rstd = (ok && a.feature_norm) ? a.st0[2 * mm + 1] : 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && 4 * c4 < I) q = *reinterpret_cast<const float4*>(a.X + mm * a.ldx + 4 * c4);
+        const float xr[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 4 * c4 + j;
+          const float d = (ok && c < I) ? v[c] : 0.f;
+          sc0[BT_SC(tid, c)] = d * (xr[j] - mean) * rstd;
+          sc1[BT_SC(tid, c)] = d;
+        }
+      }
+      bt_colsum_read(sc0, sc1, tid, &acc0);
+    }
+    tc::fence_before();
+    __syncthreads();     // TMEM reads drained before the next tile's MMAs
+    tc::fence_after();
+  }
+  // ---- this CTA's partial of the LayerNorm gain / bias gradients ----
+  float* gp = a.gpart + (size_t)blockIdx.x * a.P;
+  const int col = tid & 63;
+  if (tid < 64) {
+    gp[L.ln2_g + col] = acc2; gp[L.ln1_g + col] = acc1;
+    if (col < I) gp[L.fn_g + col] = a.feature_norm ? acc0 : 0.f;
+  } else {
+    gp[L.ln2_b + col] = acc2; gp[L.ln1_b + col] = acc1;
+    if (col < I) gp[L.fn_b + col] = a.feature_norm ? acc0 : 0.f;
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<64>(tmem_base);
+}
+
+bool mx_front_bwd_tc_usable(const FrontBwdArgs& a) {
+  return g_mx_wgrad_tc >= 2 && mx_wgrad_tc_usable(a) && a.tc_imgT && !a.dX && !a.h0 && (a.ldx & 3) == 0;
+}
+
+// k_tc_prep_weights_T -> k_front_bwd_tc -> k_wgrad_tc ; *nparts_used = the number of gradient partials written
+int mx_launch_front_bwd_tc(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
+  const int Kp16 = mx_round_up(a.L.in_dim, 16);
+  const int n = 3 * 4096 + 4096 + Kp16 * 64;
+  MX_LAUNCH_PDL(k_tc_prep_weights_T, dim3((n + 255) / 256), dim3(256), 0, s, a.theta, a.L, a.tc_imgT);
+  MX_COUNT();
+  MX_MARK("k_tc_prep_weights_T", s);
+  if (MX_CHECK_LAUNCH("tc_prep_weights_T")) return 1;
+  BwdTcSmem sm = bwd_tc_smem(Kp16);
+#if !MX_EMU
+  static int configured = 0;
+  if (sm.total > configured) {
+    if (cudaFuncSetAttribute(k_front_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total) != cudaSuccess) { mx_set_error("front_bwd_tc: smem %d too large", sm.total); return 1; }
+    configured = sm.total;
+  }
+#endif
+  const int ntiles = mx_ceil_div(a.M, 128), nchunks = mx_ceil_div(a.M, WG_ROWS);
+  int ga = mx_num_sms(), gb = mx_num_sms();
+  if (ga > ntiles) ga = ntiles;
+  if (gb > nchunks) gb = nchunks;
+  FrontBwdArgs b = a;
+  b.wgrad_external = 1;
+  MX_LAUNCH_PDL(k_front_bwd_tc, dim3(ga), dim3(128), (size_t)sm.total, s, b, sm, g_mx_tc_swap);
+  MX_COUNT();
+  MX_MARK("k_front_bwd_tc", s);
+  if (MX_CHECK_LAUNCH("front_bwd_tc")) return 1;
+  *nparts_used = gb;
+  return launch_wgrad_tc(b, gb, ga < gb ? ga : -1, s);
 }

@@ -79,26 +79,29 @@ def test_wide_input_kernel_is_what_runs(emu_engine):
     assert "k_front_fwd_tc_wide" in names[1] and "k_front_fwd" not in names[1] and "k_tc_prep_weights" in names[1]
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", ["qmix_small", "qmix_5ag", "qmix_small_prev_act", "qmix_small_per"])
-def test_tensor_core_weight_gradients_match_reference_golden(emu_engine, name):
-    """k_wgrad_tc (option wgrad_tc): every dW / db of the front layers and the GRU matrices from the tensor-core kernel, the
-    LayerNorm gradients and the data-gradient chain still from k_front_bwd -- all gradient tensors against the reference's."""
+def test_tensor_core_weight_gradients_match_reference_golden(emu_engine, name, mode):
+    """Option wgrad_tc.  1: k_wgrad_tc produces every dW / db of the front layers and the GRU matrices, the LayerNorm gradients and the
+    data-gradient chain still come from k_front_bwd.  2: k_front_bwd_tc (data-gradient chain + LayerNorm gradients on tcgen05) replaces
+    k_front_bwd altogether.  All gradient tensors against the reference's."""
     lib = emu_engine.lib()
-    lib.mx_set_option(b"wgrad_tc", 1)
+    lib.mx_set_option(b"wgrad_tc", mode)
     try:
         qc.check_step_against(None, name, intermediates=False, debug=False)
     finally:
         lib.mx_set_option(b"wgrad_tc", 0)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("B,T,N,obs", [(24, 5, 5, 30), (7, 9, 3, 64), (3, 2, 2, 17)])
-def test_tensor_core_weight_gradients_vs_oracle(emu_engine, B, T, N, obs):
+def test_tensor_core_weight_gradients_vs_oracle(emu_engine, B, T, N, obs, mode):
     """Row counts that are not multiples of the 64-row chunks, more chunks than CTAs (several accumulation rounds per CTA) and fewer
     (CTAs without rows write zero partials), input widths up to 64."""
     from oracle.qmix import QmixConfig, synth_batch
     lib = emu_engine.lib()
     cfg = QmixConfig(n_agents=N, obs_dim=obs, act_dim=6, state_dim=20, gain=1.0)
-    lib.mx_set_option(b"wgrad_tc", 1)
+    lib.mx_set_option(b"wgrad_tc", mode)
     try:
         L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T, debug=False)
         batch = synth_batch(cfg, B, T, seed=4, avail_p=0.7, var_len=True) + (None, None)

@@ -72,25 +72,28 @@ def test_wide_input_tcgen05_front_kernel_vs_oracle(gpu_engine, obs_dim, n_agents
         lib.mx_set_option(b"front_tc_wide", 0)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", ["qmix_small", "qmix_5ag", "qmix_small_per"])
-def test_tensor_core_weight_gradients_match_reference_golden(gpu_engine, name):
-    """k_wgrad_tc (option wgrad_tc, off by default until timed): dW / db of the front layers and the GRU matrices on tcgen05 with
-    transposed operand staging; emulator-verified indexing, first run on real tensor cores here."""
+def test_tensor_core_weight_gradients_match_reference_golden(gpu_engine, name, mode):
+    """Option wgrad_tc (off by default until timed).  1: k_wgrad_tc -- dW / db of the front layers and the GRU matrices on tcgen05 with
+    transposed operand staging, beside k_front_bwd's data-gradient chain.  2: k_front_bwd_tc replaces k_front_bwd as well.
+    Emulator-verified indexing; first run on real tensor cores here."""
     lib = gpu_engine.lib()
-    lib.mx_set_option(b"wgrad_tc", 1)
+    lib.mx_set_option(b"wgrad_tc", mode)
     try:
         qc.check_step_against(None, name, intermediates=False, debug=False)
     finally:
         lib.mx_set_option(b"wgrad_tc", 0)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("B,T,N,obs", [(32, 60, 3, 30), (24, 5, 5, 30), (3, 2, 2, 17)])
-def test_tensor_core_weight_gradients_vs_oracle(gpu_engine, B, T, N, obs):
+def test_tensor_core_weight_gradients_vs_oracle(gpu_engine, B, T, N, obs, mode):
     """BASELINE config-2 size (5 856 rows = 92 chunks on 122 CTAs), several chunks per CTA, fewer chunks than CTAs."""
     from oracle.qmix import QmixConfig, synth_batch
     lib = gpu_engine.lib()
     cfg = QmixConfig(n_agents=N, obs_dim=obs, act_dim=9, state_dim=48, gain=1.0)
-    lib.mx_set_option(b"wgrad_tc", 1)
+    lib.mx_set_option(b"wgrad_tc", mode)
     try:
         L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T, debug=False)
         tr.use_step_graph = False
