@@ -156,7 +156,7 @@ static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W
   W->normpart = tk(mx_grad_reduce_blocks(P));
   W->tcimg[0] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c))); W->tcimg[1] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c)));
   W->xin = tk(c->prev_act_inp ? M * mx_round_up(agent_in_dim(c), 4) : 0);
-  W->da2 = tk(c->mlp ? 0 : M * MX_H); W->da1 = tk(c->mlp ? 0 : M * MX_H);
+  W->da2 = tk(M * MX_H); W->da1 = tk(M * MX_H);
   W->tcimgT = tk((int64_t)mx_tc_imageT_floats(agent_in_dim(c)));
   {
     const int64_t gH = mx_round_up(c->hyper_hidden, 4), gM = mx_round_up(c->mixer_hidden, 4), gP = mx_round_up(c->n_agents * c->mixer_hidden, 4);
@@ -408,6 +408,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
     fbm.X = X; fbm.ldx = ldx; fbm.M = M; fbm.T = T; fbm.N = N; fbm.feature_norm = 1; fbm.no_gru = 1;
     fbm.theta = q->theta; fbm.L = q->agent; fbm.u1 = ff.u1; fbm.u2 = ff.u2; fbm.st0 = ff.st0; fbm.st1 = ff.st1; fbm.st2 = ff.st2;
     fbm.dgi = ws + W.dgi; fbm.gpart = mx.gpart; fbm.P = q->P;
+    fbm.da2_out = ws + W.da2; fbm.da1_out = ws + W.da1; fbm.tc_imgT = ws + W.tcimgT;      // (option wgrad_tc)
     if (mx_launch_front_bwd(fbm, &parts[0], s)) return 1;
 #if !MX_EMU
     if (split && overlap) join_from_side(q, q->ev_hbwd, s);

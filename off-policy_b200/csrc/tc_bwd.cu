@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
         if (m < a.M) {
           if (n < 64) v = (a.u2[(size_t)m * MX_H + n] - a.st2[2 * (size_t)m]) * a.st2[2 * (size_t)m + 1] * par_s[n] + par_s[64 + n];
           else if (n < 128) {
-            if (((m / N) % T1) > 0) v = a.hall[(size_t)(m - N) * MX_H + (n - 64)];
+            if (a.no_gru) v = 0.f;                     // MLP variant: no recurrent matrix
+            else if (((m / N) % T1) > 0) v = a.hall[(size_t)(m - N) * MX_H + (n - 64)];
             else if (a.h0) v = a.h0[(size_t)m * MX_H + (n - 64)];
           } else if (n == 128) v = 1.f;
         }
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
             if (pass == 0) v = a.dgi[(size_t)m * MX_G + f];
             else {
               v = a.dgi[(size_t)m * MX_G + 2 * MX_H + (f & 63)];
-              if (f >= 64) v *= a.gates[(size_t)m * MX_G + (f - 64)];
+              if (f >= 64) v = a.no_gru ? 0.f : v * a.gates[(size_t)m * MX_G + (f - 64)];
             }
           }
           x[j] = v;
@@ -201,23 +202,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
 #pragma unroll
   for (int c4 = 0; c4 < 16; ++c4)
     *reinterpret_cast<float4*>(gp + L.wih + (size_t)r * MX_H + 4 * c4) = any ? make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool gru = !a.no_gru;       // MLP variant: the recurrent slots of the partial are never written (they stay at their initial zeros)
   if (any) tc::tmem_ld64(trow + 64, v);
+  if (gru) {
 #pragma unroll
-  for (int c4 = 0; c4 < 16; ++c4)
-    *reinterpret_cast<float4*>(gp + L.whh + (size_t)r * MX_H + 4 * c4) = any ? make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c4 = 0; c4 < 16; ++c4)
+      *reinterpret_cast<float4*>(gp + L.whh + (size_t)r * MX_H + 4 * c4) = any ? make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (any) tc::tmem_ld32(trow + 128, t);
   gp[L.bih + r] = any ? t[0] : 0.f;
-  gp[L.bhh + r] = any ? t[0] : 0.f;
+  if (gru) gp[L.bhh + r] = any ? t[0] : 0.f;
   // D2: n gate.  rows 0-63: dW_ih[128 + r] = cols 0-63, db_ih ; rows 64-127: dW_hh[128 + r - 64] = cols 64-127, db_hh
   if (any) tc::tmem_ld64(trow + WG_DSTRIDE + (r < 64 ? 0 : 64), v);
-  {
+  if (r < 64 || gru) {
     float* dst = gp + (r < 64 ? L.wih : L.whh) + (size_t)(128 + (r & 63)) * MX_H;
 #pragma unroll
     for (int c4 = 0; c4 < 16; ++c4)
       *reinterpret_cast<float4*>(dst + 4 * c4) = any ? make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (any) tc::tmem_ld32(trow + WG_DSTRIDE + 128, t);
-  gp[(r < 64 ? L.bih : L.bhh) + 128 + (r & 63)] = any ? t[0] : 0.f;
+  if (r < 64 || gru) gp[(r < 64 ? L.bih : L.bhh) + 128 + (r & 63)] = any ? t[0] : 0.f;
   // D3: rows 0-63: dW2[r] = cols 0-63, db2 ; rows 64-127: dW1[r - 64][0:I] = cols 64.., db1
   if (any) tc::tmem_ld64(trow + 2 * WG_DSTRIDE + (r < 64 ? 0 : 64), v);
   if (r < 64) {
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
 }
 
 bool mx_wgrad_tc_usable(const FrontBwdArgs& a) {
-  return g_mx_wgrad_tc && a.da2_out && a.da1_out && !a.no_gru && !a.skip_wgrad && a.L.in_dim <= 64 && a.M >= 1;
+  return g_mx_wgrad_tc && a.da2_out && a.da1_out && !a.skip_wgrad && a.L.in_dim <= 64 && a.M >= 1;
 }
 
 extern int g_mx_tc_swap;

@@ -108,3 +108,18 @@ def test_tensor_core_weight_gradients_vs_oracle(emu_engine, B, T, N, obs, mode):
         qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
     finally:
         lib.mx_set_option(b"wgrad_tc", 0)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name", ["mqmix_small", "mqmix_small_per_huber_nodq"])
+def test_tensor_core_backward_mlp_variant_matches_reference_golden(emu_engine, name, mode):
+    """The MLP (transition-level) learner through the tensor-core backward: no recurrent matrix -- its slots of the gradient partials are
+    never written and stay zero (mqmix_checks asserts that the unused slots of the parameter vector do not move)."""
+    import mqmix_checks as mc
+    lib = emu_engine.lib()
+    lib.mx_set_option(b"wgrad_tc", mode)
+    try:
+        mc.check_golden(name, debug=False)
+        mc.check_vs_oracle(B=200, steps=1, avail=True)        # 1 200 rows: more 64-row chunks than the emulator's 4 "SMs"
+    finally:
+        lib.mx_set_option(b"wgrad_tc", 0)

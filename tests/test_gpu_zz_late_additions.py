@@ -101,3 +101,16 @@ def test_tensor_core_weight_gradients_vs_oracle(gpu_engine, B, T, N, obs, mode):
         qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
     finally:
         lib.mx_set_option(b"wgrad_tc", 0)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_tensor_core_backward_mlp_variant(gpu_engine, mode):
+    """M_QMix (1 000 transitions = 6 000 agent-net rows) through k_wgrad_tc / k_front_bwd_tc."""
+    import mqmix_checks as mc
+    lib = gpu_engine.lib()
+    lib.mx_set_option(b"wgrad_tc", mode)
+    try:
+        mc.check_golden("mqmix_small", debug=False)
+        mc.check_vs_oracle(B=1000, steps=2, avail=True)
+    finally:
+        lib.mx_set_option(b"wgrad_tc", 0)

@@ -20,7 +20,7 @@ if [ "${2:-}" != "quick" ]; then
     timeout 200 python bench.py --workload $w --quick --steps 50 --warmup 5 --buffer 2000 --opt front_tc_wide=$o >> gpurun_out/sweep_wide.log 2>> gpurun_out/sweep_wide.err
   done; done; cat gpurun_out/sweep_wide.log
   # tensor-core backward of the front layers (1: k_wgrad_tc beside k_front_bwd, 2: k_front_bwd_tc + k_wgrad_tc) -- input widths <= 64
-  for o in 0 1 2; do for w in qmix_3m qmix_mpe_spread; do
+  for o in 0 1 2; do for w in qmix_3m qmix_mpe_spread mqmix_mpe_spread; do
     timeout 200 python bench.py --workload $w --quick --steps 100 --warmup 10 --buffer 2000 --opt wgrad_tc=$o >> gpurun_out/sweep_wgrad.log 2>> gpurun_out/sweep_wgrad.err
   done; done; cat gpurun_out/sweep_wgrad.log
   timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-200 gpurun_out/bench_ref.json
