@@ -20,18 +20,21 @@
 #include <string.h>
 
 int g_mx_wgrad_tc = 0;        // off until timed on a B200 (emulator-verified): mx_set_option("wgrad_tc", 1)
+int g_mx_wgrad_tc_wide = 1;   // with wgrad_tc: input widths 65 .. 112 too (SMAC 8m / 2s3z observations are 80 wide)
 
 #define WG_ROWS 64            // rows per MMA group (the K extent of one staged tile)
 #define WG_DSTRIDE 160        // TMEM column stride between the three accumulators
 
+#define WG_MAX_IN 112          // input widths up to here: D3 = [x1 | x0 | 1] is 64 + round_up(I, 16) + 16 <= 192 columns, the rest of TMEM
 struct WgradSmem { int o_ahi, o_alo, o_bhi, o_blo, total; };
-static WgradSmem wgrad_smem() {
+static WgradSmem wgrad_smem(int n3) {
+  const int nb = n3 > 144 ? n3 : 144;
   WgradSmem s;
   int o = 0;
   s.o_ahi = o; o += 128 * WG_ROWS * 4;
   s.o_alo = o; o += 128 * WG_ROWS * 4;
-  s.o_bhi = o; o += 144 * WG_ROWS * 4;
-  s.o_blo = o; o += 144 * WG_ROWS * 4;
+  s.o_bhi = o; o += nb * WG_ROWS * 4;
+  s.o_blo = o; o += nb * WG_ROWS * 4;
   s.total = o;
   return s;
 }
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
   MX_DYN_SMEM_RAW(smem_raw);
   __shared__ __align__(8) tc::Bar bar_s;
   __shared__ uint32_t tmem_s;
-  __shared__ float par_s[6 * 64];            // ln2 g,b | ln1 g,b | fn g,b
+  __shared__ float par_s[4 * 64 + 2 * 128];  // ln2 g,b | ln1 g,b | fn g (128), fn b (128)
   const FrontBwdArgs& a = w.f;
   const MxNetLayout L = a.L;
   const float* __restrict__ th = a.theta;
@@ -80,8 +83,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
   }
   for (int i = tid; i < 64; i += blockDim.x) {
     par_s[i] = th[L.ln2_g + i]; par_s[64 + i] = th[L.ln2_b + i]; par_s[128 + i] = th[L.ln1_g + i]; par_s[192 + i] = th[L.ln1_b + i];
-    par_s[256 + i] = i < I ? th[L.fn_g + i] : 0.f; par_s[320 + i] = i < I ? th[L.fn_b + i] : 0.f;
   }
+  for (int i = tid; i < 128; i += blockDim.x) { par_s[256 + i] = i < I ? th[L.fn_g + i] : 0.f; par_s[384 + i] = i < I ? th[L.fn_b + i] : 0.f; }
   MX_PDL_WAIT();
   tc::fence_before();
   __syncthreads();
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
           else if (n < 64 + I) {
             const int c = n - 64;
             const float xr = a.X[(size_t)m * a.ldx + c];
-            v = a.feature_norm ? (xr - a.st0[2 * (size_t)m]) * a.st0[2 * (size_t)m + 1] * par_s[256 + c] + par_s[320 + c] : xr;
+            v = a.feature_norm ? (xr - a.st0[2 * (size_t)m]) * a.st0[2 * (size_t)m + 1] * par_s[256 + c] + par_s[384 + c] : xr;
           } else if (n == ones3) v = 1.f;
         }
         x[j] = v;
@@ -230,12 +233,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
       *reinterpret_cast<float4*>(gp + L.w2 + (size_t)r * MX_H + 4 * c4) = any ? make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
     float* dst = gp + L.w1 + (size_t)(r - 64) * I;
+    for (int cb = 0; 64 * cb < I; ++cb) {        // (warp-uniform trip count)
+      if (cb > 0 && any) tc::tmem_ld64(trow + 2 * WG_DSTRIDE + 64 + 64 * cb, v);
 #pragma unroll
-    for (int c = 0; c < 64; ++c)
-      if (c < I) dst[c] = any ? v[c] : 0.f;
+      for (int c = 0; c < 64; ++c)
+        if (64 * cb + c < I) dst[64 * cb + c] = any ? v[c] : 0.f;
+    }
   }
-  if (any) tc::tmem_ld32(trow + 2 * WG_DSTRIDE + ones3, t);      // 32 columns from the ones column on (inside this accumulator's stride)
-  gp[(r < 64 ? L.b2 : L.b1) + (r & 63)] = any ? t[0] : 0.f;
+  if (any) tc::tmem_ld32(trow + 2 * WG_DSTRIDE + ones3 - 16, t);      // 32 columns around the ones column (inside this accumulator)
+  gp[(r < 64 ? L.b2 : L.b1) + (r & 63)] = any ? t[16] : 0.f;
   }
   if (w.ln_zero_from >= 0 && (int)blockIdx.x >= w.ln_zero_from) {
     for (int c = tid; c < MX_H; c += blockDim.x) { gp[L.ln2_g + c] = 0.f; gp[L.ln2_b + c] = 0.f; gp[L.ln1_g + c] = 0.f; gp[L.ln1_b + c] = 0.f; }
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
 }
 
 bool mx_wgrad_tc_usable(const FrontBwdArgs& a) {
-  return g_mx_wgrad_tc && a.da2_out && a.da1_out && !a.skip_wgrad && a.L.in_dim <= 64 && a.M >= 1;
+  return g_mx_wgrad_tc && a.da2_out && a.da1_out && !a.skip_wgrad && a.L.in_dim <= (g_mx_wgrad_tc_wide ? WG_MAX_IN : 64) && a.M >= 1;
 }
 
 extern int g_mx_tc_swap;
@@ -259,12 +265,12 @@ static int launch_wgrad_tc(const FrontBwdArgs& a, int nparts, int ln_zero_from, 
   w.ln_zero_from = ln_zero_from;
   w.nchunks = mx_ceil_div(a.M, WG_ROWS);
   w.Kp16 = mx_round_up(a.L.in_dim, 16);
-  WgradSmem sm = wgrad_smem();
+  WgradSmem sm = wgrad_smem(64 + w.Kp16 + 16);
 #if !MX_EMU
-  static bool configured = false;
-  if (!configured) {
+  static int configured = 0;
+  if (sm.total > configured) {
     if (cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total) != cudaSuccess) { mx_set_error("wgrad_tc: smem %d too large", sm.total); return 1; }
-    configured = true;
+    configured = sm.total;
   }
 #endif
   MX_LAUNCH_PDL(k_wgrad_tc, dim3(nparts), dim3(WG_THREADS), (size_t)sm.total, s, w, sm, g_mx_tc_swap);
@@ -291,8 +297,13 @@ static BwdTcSmem bwd_tc_smem(int Kp16) {
   s.o_ahi = o; o += 128 * 64 * 4;
   s.o_alo = o; o += 128 * 64 * 4;
   s.o_wih = o; o += 3 * 2 * 64 * 64 * 4;      // three gate chunks, each [64][64] hi | lo
-  s.o_w2 = o; o += 2 * 64 * 64 * 4;
-  s.o_w1 = o; o += 2 * Kp16 * 64 * 4;
+  s.o_w2 = o;
+  if (Kp16 <= 64) {                           // everything resident: 224 KB at obs 64
+    o += 2 * 64 * 64 * 4;
+    s.o_w1 = o; o += 2 * Kp16 * 64 * 4;
+  } else {                                    // wide inputs: W2^T and W1^T take turns in one region, restaged per tile from the image
+    s.o_w1 = o; o += 2 * Kp16 * 64 * 4;
+  }
   s.total = o;
   return s;
 }
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
   MX_DYN_SMEM_RAW(smem_raw);
   __shared__ __align__(8) tc::Bar bar_s;
   __shared__ uint32_t tmem_s;
-  __shared__ float par_s[3 * 64];            // gains: ln2 | ln1 | feature norm
+  __shared__ float par_s[2 * 64];            // gains: ln2 | ln1
   const MxNetLayout L = a.L;
   const float* __restrict__ th = a.theta;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -393,19 +404,20 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
   float* sc0 = reinterpret_cast<float*>(a_hi);
   float* sc1 = reinterpret_cast<float*>(a_lo);
   const uint32_t bar = tc::bar_addr(&bar_s);
-  if (warp == 0) tc::tmem_alloc<64>(&tmem_s);
+  const bool restage = sm.o_w1 == sm.o_w2;
+  const float* img_w2 = a.tc_imgT + 2 * 3 * 4096;
+  const float* img_w1 = img_w2 + 2 * 4096;
+  if (warp == 0) tc::tmem_alloc<128>(&tmem_s);
   if (tid == 0) {
     tc::mbar_init(bar, 1);
     tc::mbar_init_fence();
   }
-  for (int i = tid; i < 64; i += blockDim.x) {
-    par_s[i] = th[L.ln2_g + i]; par_s[64 + i] = th[L.ln1_g + i]; par_s[128 + i] = (a.feature_norm && i < I) ? th[L.fn_g + i] : 1.f;
-  }
+  for (int i = tid; i < 64; i += blockDim.x) { par_s[i] = th[L.ln2_g + i]; par_s[64 + i] = th[L.ln1_g + i]; }
   MX_PDL_WAIT();
-  {   // the transposed weight images are byte-identical to the shared-memory weight region
+  {   // the transposed weight images are byte-identical to the shared-memory weight region (resident part)
     const float* src = a.tc_imgT;
     float* dst = reinterpret_cast<float*>(wih);
-    const int nvec = (sm.total - sm.o_wih) >> 4;
+    const int nvec = ((restage ? sm.o_w2 : sm.total) - sm.o_wih) >> 4;
     for (int v = tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
     mx_cp_commit();
   }
@@ -415,7 +427,7 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
   const uint32_t tmem_base = tmem_s;
   const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
   uint32_t phase = 0;
-  float acc2 = 0.f, acc1 = 0.f, acc0 = 0.f;      // running column sums: threads 0-63 gain gradients, 64-127 bias gradients
+  float acc2 = 0.f, acc1 = 0.f, acc0a = 0.f, acc0b = 0.f;      // running column sums: threads 0-63 gain gradients, 64-127 bias gradients
   const int ntiles = (a.M + 127) / 128;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int m = tile * 128 + tid;
@@ -455,6 +467,14 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
         for (int c4 = 0; c4 < 16; ++c4) *reinterpret_cast<float4*>(da_out + mm * MX_H + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
       }
       bt_put_row64(a_hi, a_lo, tid, v);
+      if (restage) {      // the previous MMAs that read this region have completed (every issue is waited for)
+        const float* src = layer == 0 ? img_w2 : img_w1;
+        float* dst = reinterpret_cast<float*>(w2);
+        const int nvec = (layer == 0 ? 2 * 4096 * 4 : 2 * Kp16 * 64 * 4) >> 4;
+        for (int q = tid; q < nvec; q += blockDim.x) mx_cp16(dst + 4 * q, src + 4 * q);
+        mx_cp_commit();
+        mx_cp_wait<0>();
+      }
       tc::fence_async_smem();
       tc::fence_before();
       __syncthreads();
@@ -467,25 +487,29 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
       phase ^= 1;
       tc::fence_after();
     }
-    // ---- dx0 -> gain / bias gradients of the feature LayerNorm ----
+    // ---- dx0 -> gain / bias gradients of the feature LayerNorm (64 input columns per round) ----
     {
-      float v[64];
-      tc::tmem_ld64(tmem_row, v);         // columns >= Kp16 hold leftovers of the previous layer: masked below
       const float mean = (ok && a.feature_norm) ? a.st0[2 * mm] : 0.f, rstd = (ok && a.feature_norm) ? a.st0[2 * mm + 1] : 0.f;
+      for (int cb = 0; 64 * cb < I; ++cb) {
+        float v[64];
+        tc::tmem_ld64(tmem_row + 64 * cb, v);         // columns >= Kp16 hold leftovers of the previous layer: masked below
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && 4 * c4 < I) q = *reinterpret_cast<const float4*>(a.X + mm * a.ldx + 4 * c4);
-        const float xr[4] = {q.x, q.y, q.z, q.w};
+        for (int c4 = 0; c4 < 16; ++c4) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && 64 * cb + 4 * c4 < I) q = *reinterpret_cast<const float4*>(a.X + mm * a.ldx + 64 * cb + 4 * c4);
+          const float xr[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = 4 * c4 + j;
-          const float d = (ok && c < I) ? v[c] : 0.f;
-          sc0[BT_SC(tid, c)] = d * (xr[j] - mean) * rstd;
-          sc1[BT_SC(tid, c)] = d;
+          for (int j = 0; j < 4; ++j) {
+            const int c = 4 * c4 + j;
+            const float d = (ok && 64 * cb + c < I) ? v[c] : 0.f;
+            sc0[BT_SC(tid, c)] = d * (xr[j] - mean) * rstd;
+            sc1[BT_SC(tid, c)] = d;
+          }
         }
+        float part = 0.f;
+        bt_colsum_read(sc0, sc1, tid, &part);
+        if (cb == 0) acc0a += part; else acc0b += part;
       }
-      bt_colsum_read(sc0, sc1, tid, &acc0);
     }
     tc::fence_before();
     __syncthreads();     // TMEM reads drained before the next tile's MMAs
@@ -496,14 +520,16 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
   const int col = tid & 63;
   if (tid < 64) {
     gp[L.ln2_g + col] = acc2; gp[L.ln1_g + col] = acc1;
-    if (col < I) gp[L.fn_g + col] = a.feature_norm ? acc0 : 0.f;
+    if (col < I) gp[L.fn_g + col] = a.feature_norm ? acc0a : 0.f;
+    if (64 + col < I) gp[L.fn_g + 64 + col] = a.feature_norm ? acc0b : 0.f;
   } else {
     gp[L.ln2_b + col] = acc2; gp[L.ln1_b + col] = acc1;
-    if (col < I) gp[L.fn_b + col] = a.feature_norm ? acc0 : 0.f;
+    if (col < I) gp[L.fn_b + col] = a.feature_norm ? acc0a : 0.f;
+    if (64 + col < I) gp[L.fn_b + 64 + col] = a.feature_norm ? acc0b : 0.f;
   }
   tc::fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<64>(tmem_base);
+  if (warp == 0) tc::tmem_dealloc<128>(tmem_base);
 }
 
 bool mx_front_bwd_tc_usable(const FrontBwdArgs& a) {

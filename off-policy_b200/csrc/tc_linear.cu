@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
 int g_mx_front_tc = 1;        // 1: tcgen05 3xTF32 kernel (default), 0: FFMA kernel (mx_set_option("front_tc", 0))
 int g_mx_front_tc_wide = 0;   // 1: 64 < in_dim <= 128 also runs on tcgen05 (k_front_fwd_tc_wide); off until it has been timed on a B200
 int g_mx_tc_swap = 0;
-extern int g_mx_wgrad_tc;      // tc_bwd.cu
+extern int g_mx_wgrad_tc, g_mx_wgrad_tc_wide;      // tc_bwd.cu
 int g_mx_mixer_rm = 0;        // tuning overrides (0 = automatic): rows per thread of the mixer / backward front tiles
 int g_mx_front_bwd_rm = 0;
 
@@ -508,6 +508,7 @@ extern "C" int mx_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "front_tc")) { g_mx_front_tc = value; return 0; }
   if (!strcmp(name, "front_tc_wide")) { g_mx_front_tc_wide = value; return 0; }
   if (!strcmp(name, "wgrad_tc")) { g_mx_wgrad_tc = value; return 0; }
+  if (!strcmp(name, "wgrad_tc_wide")) { g_mx_wgrad_tc_wide = value; return 0; }
   if (!strcmp(name, "tc_swap_ls")) { g_mx_tc_swap = value; return 0; }
   if (!strcmp(name, "mixer_rm")) { g_mx_mixer_rm = value; return 0; }
   if (!strcmp(name, "front_bwd_rm")) { g_mx_front_bwd_rm = value; return 0; }

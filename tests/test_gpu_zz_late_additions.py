@@ -114,3 +114,21 @@ def test_tensor_core_backward_mlp_variant(gpu_engine, mode):
         mc.check_vs_oracle(B=1000, steps=2, avail=True)
     finally:
         lib.mx_set_option(b"wgrad_tc", 0)
+
+
+@pytest.mark.parametrize("obs_dim,n_agents,B,T,mode", [(80, 8, 8, 20, 2), (80, 5, 32, 30, 1), (112, 3, 16, 12, 2)])
+def test_tensor_core_backward_wide_inputs_vs_oracle(gpu_engine, obs_dim, n_agents, B, T, mode):
+    """SMAC-sized observations (8m / 2s3z: 80) through the wide tensor-core forward AND backward kernels."""
+    from oracle.qmix import QmixConfig, synth_batch
+    lib = gpu_engine.lib()
+    cfg = QmixConfig(n_agents=n_agents, obs_dim=obs_dim, act_dim=11, state_dim=60, gain=1.0)
+    lib.mx_set_option(b"front_tc_wide", 1)
+    lib.mx_set_option(b"wgrad_tc", mode)
+    try:
+        L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T, debug=False)
+        tr.use_step_graph = False
+        batch = synth_batch(cfg, B, T, seed=4, avail_p=0.7, var_len=True) + (None, None)
+        qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
+    finally:
+        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"front_tc_wide", 0)
