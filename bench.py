@@ -40,7 +40,7 @@ WORKLOADS = {
     # --use_reward_normalization, no available-action masks) -- the reference's own CPU-runnable case
     "qmix_mpe_spread": (3, 18, 5, 54, 25, 32, False),
 }
-PROFILE_REPS, PROFILE_INNER, E2E_MIN_STEPS, CPU_STEPS = 6, 8, 20, 20     # loop lengths (tests/test_bench_dryrun.py shrinks them)
+PROFILE_REPS, PROFILE_INNER, E2E_MIN_STEPS, CPU_STEPS, E2E_WARM = 6, 8, 20, 20, 5     # loop lengths (tests/test_bench_dryrun.py shrinks them)
 NO_AVAIL = {"qmix_mpe_spread"}       # MPE passes avail_acts = None (runner/rnn/mpe_runner.py:62) and normalises rewards
 
 
@@ -505,7 +505,7 @@ def run_engine(args):
         tr.soft_target_updates()
         return float(info["loss"])                                                    # D2H read of the step's result (syncs)
 
-    for i in range(5):
+    for i in range(E2E_WARM):
         e2e_step(i)
     barrier()
     n_e2e = max(E2E_MIN_STEPS, min(args.steps, 200))
@@ -537,7 +537,7 @@ def run_engine(args):
         return float(pins[k ^ 1][0])                                                  # D2H result of the PREVIOUS step
 
     evts[1].record()
-    for i in range(4):
+    for i in range(min(4, E2E_WARM)):
         e2e_step_lagged(i)
     barrier()
     t0 = time.perf_counter()
@@ -777,7 +777,7 @@ def run_mlp(args):
         tr.soft_target_updates()
         return float(info_t["loss"])
 
-    for i in range(5):
+    for i in range(E2E_WARM):
         e2e_step(i)
     torch.cuda.synchronize()
     n_e2e = max(E2E_MIN_STEPS, min(args.steps, 200))

@@ -24,7 +24,7 @@ def build(verbose=False):
         objs.append(obj)
         if os.path.exists(obj) and os.path.getmtime(obj) > newest:
             continue
-        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-DMARL_EMU", "-I", HERE, "-I", CSRC, "-x", "c++", "-c", src, "-o", obj,
+        cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-DMARL_EMU", "-I", HERE, "-I", CSRC, "-x", "c++", "-c", src, "-o", obj,
                "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-sign-compare", "-Wno-unused-variable"]
         procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     fail = False

@@ -22,6 +22,37 @@ static char* get_stack(size_t i) {
   return stack_pool[i];
 }
 
+#if EMU_FAST_SWITCH
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
+static inline void to_sched() { emu_switch(&cur->sp, g.sched_sp); }
+static inline void to_fiber(Fiber& f) { emu_switch(&g.sched_sp, f.sp); }
+#else
+static inline void to_sched() { swapcontext(&cur->ctx, &g.sched); }
+static inline void to_fiber(Fiber& f) { swapcontext(&g.sched, &f.ctx); }
+#endif
+
 static void trampoline() {
   (*g.body)();
   cur->done = true;
@@ -29,10 +60,11 @@ static void trampoline() {
   g.progress++;
   // a thread that exits no longer takes part in block barriers (CUDA semantics for exited threads)
   if (g.alive > 0 && g.arrived == g.alive) { g.arrived = 0; g.gen++; }
-  swapcontext(&cur->ctx, &g.sched);
+  to_sched();
+  abort();      // a finished fiber is never resumed
 }
 
-void yield() { swapcontext(&cur->ctx, &g.sched); }
+void yield() { to_sched(); }
 
 void syncthreads() {
   int gen = g.gen;
@@ -93,11 +125,21 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
           f.warp = i / 32;
           f.done = false;
           f.stack = get_stack(i);
+#if EMU_FAST_SWITCH
+          {   // initial frame: six callee-saved registers (don't care) + return address = trampoline; at its entry rsp % 16 == 8
+            uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack) + kStack) & ~uintptr_t(15);
+            void** sp = reinterpret_cast<void**>(top - 8);        // slot that a caller's `call` would have filled (alignment)
+            *--sp = reinterpret_cast<void*>(trampoline);
+            for (int k = 0; k < 6; ++k) *--sp = nullptr;
+            f.sp = sp;
+          }
+#else
           getcontext(&f.ctx);
           f.ctx.uc_stack.ss_sp = f.stack;
           f.ctx.uc_stack.ss_size = kStack;
           f.ctx.uc_link = &g.sched;
           makecontext(&f.ctx, (void (*)())trampoline, 0);
+#endif
           order[i] = (order_mode == 1) ? nt - 1 - i : i;
         }
         long idle_passes = 0;
@@ -113,7 +155,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
             Fiber& f = g.fibers[order[k]];
             if (f.done) continue;
             cur = &f;
-            swapcontext(&g.sched, &f.ctx);
+            to_fiber(f);
           }
           if (g.progress == before) {
             if (++idle_passes > 4) {

@@ -6,10 +6,10 @@
 // fallback: the product loader (off-policy_b200/offpolicy/_b200/capi.py) only ever loads the nvcc-built
 // libmarl_b200.so and raises when there is no CUDA device.  Nothing here is shipped or timed.
 //
-// Model: blocks run one after another; the threads of a block are ucontext fibers scheduled round-robin
+// Model: blocks run one after another; the threads of a block are fibers (own stacks, cooperative switch) scheduled round-robin
 // (or in reverse / pseudo-random order, EMU_ORDER=reverse|random, to shake out missing barriers);
 // __syncthreads / warp collectives are cooperative barriers.  `__shared__` becomes `static` (valid
-// because blocks are sequential).  TMA / tcgen05 / mbarrier / clusters are out of scope for emulation.
+// because blocks are sequential).  tcgen05 / TMEM / mbarrier are restated in csrc/mx_tc.cuh's MX_EMU half; TMA and clusters are not emulated.
 #pragma once
 #include <ucontext.h>
 
@@ -50,8 +50,17 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 
 namespace emu {
 
+// Context switch: on x86-64 a hand-written register swap (callee-saved registers + stack pointer, ~15 instructions); swapcontext()
+// makes two rt_sigprocmask system calls per switch, which dominated the emulated test time.  Elsewhere: ucontext.
+#if defined(__x86_64__)
+#define EMU_FAST_SWITCH 1
+#else
+#define EMU_FAST_SWITCH 0
+#endif
+
 struct Fiber {
   ucontext_t ctx;
+  void* sp;                // EMU_FAST_SWITCH: saved stack pointer
   uint3 tid;
   int lin, lane, warp;
   bool done;
@@ -68,6 +77,7 @@ struct Globals {
   int nthreads, alive, arrived, gen;
   long progress;
   ucontext_t sched;
+  void* sched_sp;
   std::vector<Fiber> fibers;
   std::vector<Warp> warps;
   std::vector<char> dynsmem;

@@ -48,7 +48,7 @@ def bench_mod(emu_engine, monkeypatch):
     lines = []
     monkeypatch.setattr(bench, "emit", lambda line: lines.append(json.loads(json.dumps(line))))
     monkeypatch.setattr(bench.ClockSampler, "run", lambda self: None)
-    for k, v in dict(PROFILE_REPS=1, PROFILE_INNER=2, E2E_MIN_STEPS=3, CPU_STEPS=3).items():
+    for k, v in dict(PROFILE_REPS=1, PROFILE_INNER=2, E2E_MIN_STEPS=2, CPU_STEPS=2, E2E_WARM=1).items():
         monkeypatch.setattr(bench, k, v)
     bench._lines = lines
     return bench

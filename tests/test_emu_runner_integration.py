@@ -22,7 +22,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "offpolicy",
 RUNS = {
     # name: (algorithm, env steps, extra reference flags, compare against the pure reference?)   [name smac_*: run_smac_like.py]
     # also exercises the runner's periodic evaluation (greedy rollouts) and checkpoint saving (state_dict -> torch.save)
-    "qmix": ("qmix", 150, ["--save_interval", "50", "--use_eval", "--eval_interval", "75", "--num_eval_episodes", "2"], True),
+    "qmix": ("qmix", 125, ["--save_interval", "50", "--use_eval", "--eval_interval", "75", "--num_eval_episodes", "2"], True),
     # scripts/train_mpe_qmix.sh:14 normalises rewards; `--use_soft_update` is a store_false flag, i.e. HARD target updates every
     # hard_update_interval_episode episodes like the shipped train_smac_qmix.sh
     "qmix_reward_norm": ("qmix", 125, ["--use_reward_normalization", "--use_soft_update", "--hard_update_interval_episode", "2"], True),

@@ -38,7 +38,7 @@ def test_qmix_step_front_paths_match_reference_golden(emu_engine, front_tc):
         lib.mx_set_option(b"front_tc", 1)
 
 
-@pytest.mark.parametrize("obs_dim", [128])          # (65 / 80 / 112 run in test_tensor_core_backward_wide_inputs_vs_oracle)
+@pytest.mark.parametrize("obs_dim", [65, 80, 100, 128])
 def test_wide_input_front_kernel_vs_oracle(emu_engine, obs_dim):
     """64 < obs_dim <= 128 (SMAC 8m / 2s3z observations are 80 wide): fc1's K dimension fed to the tensor core in two chunks that
     accumulate in TMEM (k_front_fwd_tc_wide, option front_tc_wide).  More than 128 rows so a CTA runs several tiles."""
@@ -79,7 +79,8 @@ def test_wide_input_kernel_is_what_runs(emu_engine):
     assert "k_front_fwd_tc_wide" in names[1] and "k_front_fwd" not in names[1] and "k_tc_prep_weights" in names[1]
 
 
-@pytest.mark.parametrize("name,mode", [("qmix_small", 1), ("qmix_small", 2), ("qmix_5ag", 2), ("qmix_small_prev_act", 2), ("qmix_small_per", 1)])
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name", ["qmix_small", "qmix_5ag", "qmix_small_prev_act", "qmix_small_per", "qmix_small_huber_nodq", "qmix_small_hyper1"])
 def test_tensor_core_weight_gradients_match_reference_golden(emu_engine, name, mode):
     """Option wgrad_tc.  1: k_wgrad_tc produces every dW / db of the front layers and the GRU matrices, the LayerNorm gradients and the
     data-gradient chain still come from k_front_bwd.  2: k_front_bwd_tc (data-gradient chain + LayerNorm gradients on tcgen05) replaces
@@ -92,7 +93,8 @@ def test_tensor_core_weight_gradients_match_reference_golden(emu_engine, name, m
         lib.mx_set_option(b"wgrad_tc", 0)
 
 
-@pytest.mark.parametrize("B,T,N,obs,mode", [(12, 5, 5, 30, 2), (7, 9, 3, 64, 1), (3, 2, 2, 17, 2)])
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("B,T,N,obs", [(24, 5, 5, 30), (7, 9, 3, 64), (3, 2, 2, 17), (32, 12, 3, 30)])
 def test_tensor_core_weight_gradients_vs_oracle(emu_engine, B, T, N, obs, mode):
     """Row counts that are not multiples of the 64-row chunks, more chunks than CTAs (several accumulation rounds per CTA) and fewer
     (CTAs without rows write zero partials), input widths up to 64."""
@@ -108,7 +110,8 @@ def test_tensor_core_weight_gradients_vs_oracle(emu_engine, B, T, N, obs, mode):
         lib.mx_set_option(b"wgrad_tc", 0)
 
 
-@pytest.mark.parametrize("name,mode", [("mqmix_small", 1), ("mqmix_small_per_huber_nodq", 2)])
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name", ["mqmix_small", "mqmix_small_per_huber_nodq", "mqmix_small_noavail"])
 def test_tensor_core_backward_mlp_variant_matches_reference_golden(emu_engine, name, mode):
     """The MLP (transition-level) learner through the tensor-core backward: no recurrent matrix -- its slots of the gradient partials are
     never written and stay zero (mqmix_checks asserts that the unused slots of the parameter vector do not move)."""
@@ -122,7 +125,8 @@ def test_tensor_core_backward_mlp_variant_matches_reference_golden(emu_engine, n
         lib.mx_set_option(b"wgrad_tc", 0)
 
 
-@pytest.mark.parametrize("obs_dim,mode", [(65, 1), (80, 2), (112, 2)])
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("obs_dim", [65, 80, 96, 112])
 def test_tensor_core_backward_wide_inputs_vs_oracle(emu_engine, obs_dim, mode):
     """64 < obs_dim <= 112 through the tensor-core backward (fc1's transposed weight image takes turns with fc2's in shared memory, the
     feature LayerNorm's gradients are summed in two 64-column rounds, dW1 is read from two 64-column blocks of TMEM), together with the
@@ -130,7 +134,7 @@ def test_tensor_core_backward_wide_inputs_vs_oracle(emu_engine, obs_dim, mode):
     from oracle.qmix import QmixConfig, synth_batch
     lib = emu_engine.lib()
     cfg = QmixConfig(n_agents=5, obs_dim=obs_dim, act_dim=6, state_dim=20, gain=1.0)
-    B, T = 12, 5           # 360 rows: 3 tiles / 6 chunks on the emulator's 4 "SMs"
+    B, T = 24, 5           # 720 rows: 6 tiles / 12 chunks on the emulator's 4 "SMs"
     lib.mx_set_option(b"front_tc_wide", 1)
     lib.mx_set_option(b"wgrad_tc", mode)
     try:
