@@ -144,3 +144,21 @@ def test_tensor_core_backward_wide_inputs_vs_oracle(emu_engine, obs_dim, mode):
     finally:
         lib.mx_set_option(b"wgrad_tc", 0)
         lib.mx_set_option(b"front_tc_wide", 0)
+
+
+def test_config2_full_size_all_tensor_core_kernels_vs_oracle(emu_engine):
+    """BASELINE config 2 at its real size (B = 32, T = 60, N = 3: 5 856 agent-net rows = 46 tiles / 92 chunks) with every tensor-core
+    kernel on: k_front_fwd_tc, k_front_bwd_tc, k_wgrad_tc."""
+    from oracle.qmix import QmixConfig, synth_batch
+    import torch
+    lib = emu_engine.lib()
+    torch.set_num_threads(4)
+    cfg = QmixConfig(gain=1.0)
+    lib.mx_set_option(b"wgrad_tc", 2)
+    try:
+        L, args, pol, tr = qc.oracle_and_trainer(cfg, 32, 60, debug=False)
+        batch = synth_batch(cfg, 32, 60, seed=5, avail_p=0.8, var_len=True) + (None, None)
+        qc.compare_step(L, pol, tr, batch, cfg, steps=1, param_tol=1e-2)
+    finally:
+        lib.mx_set_option(b"wgrad_tc", 0)
+        torch.set_num_threads(1)
