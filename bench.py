@@ -163,6 +163,9 @@ def run_maddpg(args):
     ms = e0.elapsed_time(e1) / args.steps
     launches = int(lib.mx_launch_count() - l0)
     torch.cuda.synchronize()
+    if args.quick:          # tuning sweeps: the device-resident number only (not a bench line)
+        emit(dict(quick=True, workload=args.workload, value=1000.0 / ms, ms_per_step=ms, opts=args.opt, kernels_per_step=launches / args.steps))
+        return
     for _ in range(10):
         float(step()["critic_loss"])
     torch.cuda.synchronize()

@@ -337,6 +337,7 @@ struct MxMaddpgWs {
   // actor-phase branch (rows Mr = N*B*T)
   int64_t r_x, r_h0, r_gi, r_h, r_u1, r_u2, r_st0, r_st1, r_st2, r_sto, r_gates, r_hn, r_q, r_dout, r_dh, r_dgi, r_dx;
   int64_t gpart_a, gpart_c, grad_a, grad_c, spart, info, prio, adam_ta, adam_tc, scal_c, scal_a;
+  int64_t tc_da2, tc_da1, tc_imgT;      // scratch of the tensor-core backward (option wgrad_tc), shared by the critic and actor updates
   int64_t total;
 };
 
@@ -434,6 +435,11 @@ static int64_t maddpg_ws_layout(const mx_maddpg_cfg* c, int64_t Pa, int64_t Pc, 
   W->r_q = tk(Mr * K); W->r_dout = tk(Mr * K); W->r_dh = tk(Mr * MX_H); W->r_dgi = tk(Mr * MX_G); W->r_dx = tk(Mr * ldc);
   W->gpart_a = tk((int64_t)npart * Pa); W->gpart_c = tk((int64_t)npart * Pc); W->grad_a = tk(Pa + 8); W->grad_c = tk(Pc + 8);
   W->spart = tk(16); W->info = tk(8); W->prio = tk(B); W->adam_ta = tk(8); W->adam_tc = tk(8); W->scal_c = tk(8); W->scal_a = tk(8);
+  {
+    const int64_t Mx = Ma > Mc ? Ma : Mc;
+    const size_t ia = mx_tc_imageT_floats(c->obs_dim), ic = mx_tc_imageT_floats(critic_in_dim(c));
+    W->tc_da2 = tk(Mx * MX_H); W->tc_da1 = tk(Mx * MX_H); W->tc_imgT = tk((int64_t)(ia > ic ? ia : ic));
+  }
   W->total = o;
   return o * 4;
 }
@@ -639,6 +645,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   fb.X = ws + W.c_x; fb.ldx = ldc; fb.M = Mc; fb.T = T; fb.N = 1; fb.T1 = T; fb.feature_norm = 1; fb.theta = h->th_c; fb.L = LC;
   fb.u1 = fc.u1; fb.u2 = fc.u2; fb.st0 = fc.st0; fb.st1 = fc.st1; fb.st2 = fc.st2; fb.dgi = gb.dgi; fb.gates = gc.gates; fb.hall = gc.hall[0];
   fb.gpart = ws + W.gpart_c; fb.P = h->Pc;
+  fb.da2_out = ws + W.tc_da2; fb.da1_out = ws + W.tc_da1; fb.tc_imgT = ws + W.tc_imgT;      // (option wgrad_tc)
   if (mx_launch_front_bwd(fb, &parts[0], s)) return 1;
   if (optimise(h, false, parts, head_grid, s)) return 1;
 
@@ -716,6 +723,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
     fba.X = b->obs; fba.ldx = b->obs_ld; fba.M = Ma; fba.T = T; fba.N = N; fba.feature_norm = 1; fba.theta = h->th_a; fba.L = LA;
     fba.u1 = ff.u1; fba.u2 = ff.u2; fba.st0 = ff.st0; fba.st1 = ff.st1; fba.st2 = ff.st2; fba.dgi = gba.dgi; fba.gates = gf.gates; fba.hall = gf.hall[0];
     fba.gpart = ws + W.gpart_a; fba.P = h->Pa;
+    fba.da2_out = ws + W.tc_da2; fba.da1_out = ws + W.tc_da1; fba.tc_imgT = ws + W.tc_imgT;
     int aparts[2] = {0, 0};
     if (mx_launch_front_bwd(fba, &aparts[0], s)) return 1;
     if (optimise(h, true, aparts, ahead_grid, s)) return 1;

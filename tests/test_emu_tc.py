@@ -162,3 +162,19 @@ def test_config2_full_size_all_tensor_core_kernels_vs_oracle(emu_engine):
     finally:
         lib.mx_set_option(b"wgrad_tc", 0)
         torch.set_num_threads(1)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_disc", "matd3_disc_avail", "maddpg_box_per"])
+def test_maddpg_updates_through_the_tensor_core_backward(emu_engine, name, mode):
+    """R-MADDPG / R-MATD3: the critic's (input 60 / 69 wide) and the actor's (18 wide) weight-gradient passes on k_wgrad_tc /
+    k_front_bwd_tc; the frozen-critic pass that only needs the action gradient stays on k_front_bwd."""
+    import maddpg_checks as mc
+    lib = emu_engine.lib()
+    lib.mx_set_option(b"front_tc_wide", 1)
+    lib.mx_set_option(b"wgrad_tc", mode)
+    try:
+        mc.check_golden(name)
+    finally:
+        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"front_tc_wide", 0)

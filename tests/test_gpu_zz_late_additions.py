@@ -132,3 +132,17 @@ def test_tensor_core_backward_wide_inputs_vs_oracle(gpu_engine, obs_dim, n_agent
     finally:
         lib.mx_set_option(b"wgrad_tc", 0)
         lib.mx_set_option(b"front_tc_wide", 0)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name", ["maddpg_box", "matd3_disc_avail"])
+def test_maddpg_updates_through_the_tensor_core_backward(gpu_engine, name, mode):
+    import maddpg_checks as mc
+    lib = gpu_engine.lib()
+    lib.mx_set_option(b"front_tc_wide", 1)
+    lib.mx_set_option(b"wgrad_tc", mode)
+    try:
+        mc.check_golden(name)
+    finally:
+        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"front_tc_wide", 0)

@@ -27,6 +27,9 @@ if [ "${2:-}" != "quick" ]; then
   for w in qmix_8m_per qmix_2s3z; do for o in 1 2; do
     timeout 200 python bench.py --workload $w --quick --steps 50 --warmup 5 --buffer 2000 --opt front_tc_wide=1 --opt wgrad_tc=$o >> gpurun_out/sweep_wide_all.log 2>> gpurun_out/sweep_wide_all.err
   done; done; cat gpurun_out/sweep_wide_all.log
+  for o in 0 2; do for w in rmaddpg_spread rmatd3_spread_disc; do
+    timeout 200 python bench.py --workload $w --quick --steps 100 --warmup 10 --opt front_tc_wide=1 --opt wgrad_tc=$o >> gpurun_out/sweep_maddpg.log 2>> gpurun_out/sweep_maddpg.err
+  done; done; cat gpurun_out/sweep_maddpg.log
   timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-200 gpurun_out/bench_ref.json
   timeout 200 python tools/gather_sweep.py > gpurun_out/gather_sweep.log 2> gpurun_out/gather_sweep.err; cut -c1-200 gpurun_out/gather_sweep.log
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv \
