@@ -128,5 +128,6 @@ struct mx_qmix {
   cudaEvent_t ev_fork = nullptr, ev_prep = nullptr, ev_batch = nullptr, ev_hyper = nullptr, ev_core = nullptr, ev_hbwd = nullptr;
 #endif
   int prep_pending = 0;    // mx_qmix_prefork() already launched the weight-image prep for the coming step
+  int imgT_fresh = 0;      // the transposed images (tensor-core backward) were rebuilt with the forward ones for this step
 };
 int mx_qmix_prefork(mx_qmix* q, int B, void* stream);   // optional: start the parameter-only work of the next step before its batch is sampled

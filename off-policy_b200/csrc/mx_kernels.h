@@ -168,7 +168,10 @@ struct FrontBwdArgs {
   float *da2_out, *da1_out;   // [M][H] each: gradient at the fc2 / fc1 pre-activation outputs (after the ReLU mask)
   int wgrad_external;      // set by the launcher, not by callers
   float* tc_imgT;          // scratch for the transposed TF32 weight images of the all-tensor-core backward (option wgrad_tc = 2)
+  int tc_imgT_ready;       // 1: the caller already built them for the current parameters (mx_launch_tc_prep_weights_T)
 };
+int mx_launch_tc_prep_weights_T(const float* theta, const MxNetLayout& L, float* imgT, cudaStream_t s);
+bool mx_tc_prep_T_wanted(int in_dim);
 size_t mx_tc_imageT_floats(int in_dim);
 int mx_launch_front_bwd(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s);
 int mx_launch_wgrad_tc(const FrontBwdArgs& a, int nparts, cudaStream_t s);

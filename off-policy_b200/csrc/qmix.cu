@@ -296,7 +296,13 @@ static inline void join_from_side(mx_qmix* q, cudaEvent_t ev, cudaStream_t s) { 
 static int launch_prep(mx_qmix* q, cudaStream_t s) {
   const float* const th2[2] = {q->theta, q->theta_tgt};
   float* const img2[2] = {q->ws + q->W.tcimg[0], q->ws + q->W.tcimg[1]};
-  return mx_launch_tc_prep_weights(th2, q->agent, img2, 2, s);
+  if (mx_launch_tc_prep_weights(th2, q->agent, img2, 2, s)) return 1;
+  q->imgT_fresh = 0;
+  if (mx_tc_prep_T_wanted(q->agent.in_dim)) {      // the backward's transposed images: same parameters, same (side) branch
+    if (mx_launch_tc_prep_weights_T(q->theta, q->agent, q->ws + q->W.tcimgT, s)) return 1;
+    q->imgT_fresh = 1;
+  }
+  return 0;
 }
 
 // Parameter-only work of the coming step (TF32 hi/lo weight images of the front layers), started on the side branch so that it
@@ -408,7 +414,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
     fbm.X = X; fbm.ldx = ldx; fbm.M = M; fbm.T = T; fbm.N = N; fbm.feature_norm = 1; fbm.no_gru = 1;
     fbm.theta = q->theta; fbm.L = q->agent; fbm.u1 = ff.u1; fbm.u2 = ff.u2; fbm.st0 = ff.st0; fbm.st1 = ff.st1; fbm.st2 = ff.st2;
     fbm.dgi = ws + W.dgi; fbm.gpart = mx.gpart; fbm.P = q->P;
-    fbm.da2_out = ws + W.da2; fbm.da1_out = ws + W.da1; fbm.tc_imgT = ws + W.tcimgT;      // (option wgrad_tc)
+    fbm.da2_out = ws + W.da2; fbm.da1_out = ws + W.da1; fbm.tc_imgT = ws + W.tcimgT; fbm.tc_imgT_ready = q->imgT_fresh; q->imgT_fresh = 0;      // (option wgrad_tc)
     if (mx_launch_front_bwd(fbm, &parts[0], s)) return 1;
 #if !MX_EMU
     if (split && overlap) join_from_side(q, q->ev_hbwd, s);
@@ -491,7 +497,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   fb.X = X; fb.ldx = ldx; fb.M = M; fb.T = T; fb.N = N; fb.feature_norm = 1;
   fb.theta = q->theta; fb.L = q->agent; fb.u1 = ff.u1; fb.u2 = ff.u2; fb.st0 = ff.st0; fb.st1 = ff.st1; fb.st2 = ff.st2;
   fb.dgi = gb.dgi; fb.gates = gf.gates; fb.hall = gf.hall[0]; fb.gpart = mx.gpart; fb.P = q->P;
-  fb.da2_out = ws + W.da2; fb.da1_out = ws + W.da1; fb.tc_imgT = ws + W.tcimgT;      // used when the tensor-core weight-gradient kernel is enabled (option wgrad_tc)
+  fb.da2_out = ws + W.da2; fb.da1_out = ws + W.da1; fb.tc_imgT = ws + W.tcimgT; fb.tc_imgT_ready = q->imgT_fresh; q->imgT_fresh = 0;      // used when the tensor-core weight-gradient kernel is enabled (option wgrad_tc)
   if (mx_launch_front_bwd(fb, &parts[0], s)) return 1;
 
 #if !MX_EMU

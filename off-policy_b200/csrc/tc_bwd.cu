@@ -537,13 +537,18 @@ bool mx_front_bwd_tc_usable(const FrontBwdArgs& a) {
 }
 
 // k_tc_prep_weights_T -> k_front_bwd_tc -> k_wgrad_tc ; *nparts_used = the number of gradient partials written
-int mx_launch_front_bwd_tc(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
-  const int Kp16 = mx_round_up(a.L.in_dim, 16);
-  const int n = 3 * 4096 + 4096 + Kp16 * 64;
-  MX_LAUNCH_PDL(k_tc_prep_weights_T, dim3((n + 255) / 256), dim3(256), 0, s, a.theta, a.L, a.tc_imgT);
+bool mx_tc_prep_T_wanted(int in_dim) { return g_mx_wgrad_tc >= 2 && in_dim <= (g_mx_wgrad_tc_wide ? WG_MAX_IN : 64); }
+int mx_launch_tc_prep_weights_T(const float* theta, const MxNetLayout& L, float* imgT, cudaStream_t s) {
+  const int n = 3 * 4096 + 4096 + mx_round_up(L.in_dim, 16) * 64;
+  MX_LAUNCH_PDL(k_tc_prep_weights_T, dim3((n + 255) / 256), dim3(256), 0, s, theta, L, imgT);
   MX_COUNT();
   MX_MARK("k_tc_prep_weights_T", s);
-  if (MX_CHECK_LAUNCH("tc_prep_weights_T")) return 1;
+  return MX_CHECK_LAUNCH("tc_prep_weights_T");
+}
+
+int mx_launch_front_bwd_tc(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
+  const int Kp16 = mx_round_up(a.L.in_dim, 16);
+  if (!a.tc_imgT_ready && mx_launch_tc_prep_weights_T(a.theta, a.L, a.tc_imgT, s)) return 1;
   BwdTcSmem sm = bwd_tc_smem(Kp16);
 #if !MX_EMU
   static int configured = 0;
