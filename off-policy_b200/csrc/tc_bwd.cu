@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
   __shared__ __align__(8) tc::Bar bar_s;
   __shared__ uint32_t tmem_s;
   __shared__ float par_s[4 * 64 + 2 * 128];  // ln2 g,b | ln1 g,b | fn g (128), fn b (128)
+  __shared__ float st_s[3 * 2 * WG_ROWS];    // (mean, rstd) of the chunk's rows for LN2 | LN1 | the feature LayerNorm
   const FrontBwdArgs& a = w.f;
   const MxNetLayout L = a.L;
   const float* __restrict__ th = a.theta;
@@ -95,6 +96,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
   for (int chunk = blockIdx.x; chunk < w.nchunks; chunk += gridDim.x, ++iter) {
     const int row0 = chunk * WG_ROWS;
     const uint32_t acc0 = iter > 0 ? 1u : 0u;
+    for (int i = tid; i < 3 * 2 * WG_ROWS; i += blockDim.x) {      // (the previous chunk's readers are past their last MMA wait)
+      const int which = i / (2 * WG_ROWS), rr = (i % (2 * WG_ROWS)) >> 1, comp = i & 1;
+      const int m = row0 + rr;
+      const float* src = which == 0 ? a.st2 : (which == 1 ? a.st1 : a.st0);
+      st_s[i] = (m < a.M && (which < 2 || a.feature_norm)) ? src[2 * (size_t)m + comp] : 0.f;
+    }
+    __syncthreads();
     // ---- B = [x2 | h_prev | 1 | 0..]  (144 features) ----
 #pragma unroll 2
     for (int p = tid; p < 144 * 16; p += blockDim.x) {
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
         const int m = row0 + 4 * kq + j;
         float v = 0.f;
         if (m < a.M) {
-          if (n < 64) v = (a.u2[(size_t)m * MX_H + n] - a.st2[2 * (size_t)m]) * a.st2[2 * (size_t)m + 1] * par_s[n] + par_s[64 + n];
+          if (n < 64) v = (a.u2[(size_t)m * MX_H + n] - st_s[2 * (m - row0)]) * st_s[2 * (m - row0) + 1] * par_s[n] + par_s[64 + n];
           else if (n < 128) {
             if (a.no_gru) v = 0.f;                     // MLP variant: no recurrent matrix
             else if (((m / N) % T1) > 0) v = a.hall[(size_t)(m - N) * MX_H + (n - 64)];
@@ -172,11 +180,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
         const int m = row0 + 4 * kq + j;
         float v = 0.f;
         if (m < a.M) {
-          if (n < 64) v = (a.u1[(size_t)m * MX_H + n] - a.st1[2 * (size_t)m]) * a.st1[2 * (size_t)m + 1] * par_s[128 + n] + par_s[192 + n];
+          if (n < 64) v = (a.u1[(size_t)m * MX_H + n] - st_s[2 * WG_ROWS + 2 * (m - row0)]) * st_s[2 * WG_ROWS + 2 * (m - row0) + 1] * par_s[128 + n] + par_s[192 + n];
           else if (n < 64 + I) {
             const int c = n - 64;
             const float xr = a.X[(size_t)m * a.ldx + c];
-            v = a.feature_norm ? (xr - a.st0[2 * (size_t)m]) * a.st0[2 * (size_t)m + 1] * par_s[256 + c] + par_s[384 + c] : xr;
+            v = a.feature_norm ? (xr - st_s[4 * WG_ROWS + 2 * (m - row0)]) * st_s[4 * WG_ROWS + 2 * (m - row0) + 1] * par_s[256 + c] + par_s[384 + c] : xr;
           } else if (n == ones3) v = 1.f;
         }
         x[j] = v;
