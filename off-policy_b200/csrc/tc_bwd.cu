@@ -241,11 +241,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
       *reinterpret_cast<float4*>(gp + L.w2 + (size_t)r * MX_H + 4 * c4) = any ? make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
     float* dst = gp + L.w1 + (size_t)(r - 64) * I;
-    for (int cb = 0; 64 * cb < I; ++cb) {        // (warp-uniform trip count)
-      if (cb > 0 && any) tc::tmem_ld64(trow + 2 * WG_DSTRIDE + 64 + 64 * cb, v);
+#pragma unroll
+    for (int c = 0; c < 64; ++c)
+      if (c < I) dst[c] = any ? v[c] : 0.f;
+    if (I > 64) {                                 // wide inputs: the second 64-column block of x0 (CTA-uniform branch)
+      float v2[64];
+      if (any) tc::tmem_ld64(trow + 2 * WG_DSTRIDE + 128, v2);
 #pragma unroll
       for (int c = 0; c < 64; ++c)
-        if (64 * cb + c < I) dst[64 * cb + c] = any ? v[c] : 0.f;
+        if (64 + c < I) dst[64 + c] = any ? v2[c] : 0.f;
     }
   }
   if (any) tc::tmem_ld32(trow + 2 * WG_DSTRIDE + ones3 - 16, t);      // 32 columns around the ones column (inside this accumulator)
