@@ -1,6 +1,6 @@
 #!/bin/bash
 # One standard GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list + full capture, summaries.
-# Usage (from the build container):  gpurun --timeout 1500 -- 'bash tools/gpu_round.sh <tag> [quick]'
+# Usage (from the build container):  gpurun --timeout 2700 -- 'bash tools/gpu_round.sh <tag> [quick]'   (~30 min with the option sweeps)
 #   then:  python tools/ncu_summary.py <tag> gpurun_out/launches.csv gpurun_out/prof_<tag>.ncu-rep   (writes profiles/<tag>_ncu_*)
 set -u
 TAG=${1:-rXX}
@@ -36,5 +36,12 @@ if [ "${2:-}" != "quick" ]; then
       python bench.py --steps 3 --warmup 3 --buffer 512 > gpurun_out/ncu_launch.log 2>&1
   timeout 500 ncu --set full --clock-control none --import-source on -k regex:'k_' -s 40 -c 16 \
       -o gpurun_out/prof_$TAG -f python bench.py --steps 3 --warmup 3 --buffer 512 > gpurun_out/ncu_full.log 2>&1
+  # first profiles of the tensor-core backward and the wide forward (written without a GPU): launch list + full set
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_tcbwd.csv \
+      python bench.py --quick --steps 3 --warmup 3 --buffer 512 --opt wgrad_tc=2 > gpurun_out/ncu_launch_tcbwd.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_wgrad_tc|k_front_bwd_tc' -s 6 -c 6 \
+      -o gpurun_out/prof_${TAG}_tcbwd -f python bench.py --quick --steps 3 --warmup 3 --buffer 512 --opt wgrad_tc=2 > gpurun_out/ncu_full_tcbwd.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_front_fwd_tc_wide|k_wgrad_tc|k_front_bwd_tc' -s 6 -c 6 \
+      -o gpurun_out/prof_${TAG}_8m_tc -f python bench.py --workload qmix_8m_per --quick --steps 2 --warmup 3 --buffer 512 --opt front_tc_wide=1 --opt wgrad_tc=2 > gpurun_out/ncu_full_8m_tc.log 2>&1
 fi
-ls -la gpurun_out | head -30
+ls -la gpurun_out | head -40
