@@ -3,7 +3,8 @@
 A transition is stored as an EPISODE OF LENGTH 1 of the episode replay (csrc/replay.cu): step 0 = (obs, share_obs, avail_acts),
 step 1 = (next_obs, next_share_obs, next_avail_acts), plus acts / rewards / dones / dones_env of the single step.  Insert, ring
 wrap, uniform and prioritised sampling (device-side fp64 trees), running reward statistics and the 128-bit gather kernel are the ones
-of the recurrent path; `sample()` returns the reference's 11- (13-, PER) tuple whose entries materialise the reference's NumPy layout
+of the recurrent path; `sample()` returns the reference's 13-tuple (11 fields + importance weights + indices, the last two None for
+uniform sampling) whose entries materialise the reference's NumPy layout
 on access while the B200 trainer (algorithms/mqmix/mqmix.py) reads the device-side batch directly.  `valid_transition` is not
 consumed by any shared-policy learner kernel and is kept in a host-side array.
 """
@@ -24,8 +25,8 @@ class MlpSampledBatch(object):
     def __init__(self, buffers, B, p_ids, weights=None, idxes=None, per=False, host_inds=None):
         self.buffers, self.B, self._p_ids = buffers, B, p_ids
         self.serial = {p: buffers[p].rep.sample_serial for p in p_ids}
-        self._n = 13 if per else 11
-        self._items = [None] * 11 + ([weights, idxes] if per else [])
+        self._n = 13          # uniform sampling returns (..., None, None) like the reference (mlp_buffer.py:98)
+        self._items = [None] * 11 + [weights, idxes]
         self.host_inds = host_inds
 
     def __len__(self):

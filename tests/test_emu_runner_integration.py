@@ -42,6 +42,10 @@ RUNS = {
     "mlp_mqmix_reward_norm": ("mqmix", 125, ["--runner", "mlp", "--use_reward_normalization"], True),
     "mlp_mqmix_per": ("mqmix", 100, ["--runner", "mlp", "--use_per"], False),       # reference PER insert bug (mlp_buffer.py:282)
     "mlp_mvdn": ("mvdn", 100, ["--runner", "mlp"], False),                         # reference M_VDNMixer is broken (App. D-5)
+    # MLP MADDPG / MATD3 have no B200 learner: the shadow package lets them fall through to the reference's own
+    # trainer, which then trains from the HBM transition replay (its sample materialises the reference's 13-tuple) -- same run, bit for bit
+    "mlp_maddpg": ("maddpg", 100, ["--runner", "mlp"], True),
+    "mlp_matd3": ("matd3", 100, ["--runner", "mlp"], True),
 }
 
 
