@@ -20,6 +20,16 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        # a kernel that never finishes must fail the run, not hang the box: per-test limit enforced from a watchdog thread (the main
+        # thread may be blocked inside a CUDA call, where a signal would not be delivered); on expiry pytest-timeout dumps the stacks
+        # and exits the process, which tears the CUDA context down
+        try:
+            import pytest_timeout  # noqa: F401
+            for it in items:
+                if "gpu" in it.keywords and not any(m.name == "timeout" for m in it.iter_markers()):
+                    it.add_marker(pytest.mark.timeout(600, method="thread"))
+        except Exception:
+            pass
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:
