@@ -47,6 +47,19 @@ def test_mlp_step_graph_vs_eager(gpu_engine, per):
     mc.check_step_graph_vs_eager(per=per, B=1000, E=4096)
 
 
+def test_c_host_example_runs(gpu_engine, tmp_path):
+    """examples/c_host.c: the C-ABI driven from plain C (cudaMalloc'd buffers, no Python / torch in the process)."""
+    import subprocess
+    from test_c_host_example import build_c_host
+    exe = build_c_host(str(tmp_path / "c_host"))
+    r = subprocess.run([exe, "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("step ")]
+    assert len(lines) == 4 and r.stdout.strip().splitlines()[-1].startswith("ok"), r.stdout
+
+
+# ---- option-gated tensor-core kernels written without a GPU (off by default): last, so that a failure here hides nothing else ----
+
 @pytest.mark.parametrize("obs_dim,n_agents,B,T", [(80, 8, 8, 20), (128, 3, 16, 12), (72, 5, 32, 10)])
 def test_wide_input_tcgen05_front_kernel_vs_oracle(gpu_engine, obs_dim, n_agents, B, T):
     """k_front_fwd_tc_wide (64 < obs_dim <= 128, option front_tc_wide, off by default until timed): emulator-verified indexing; this is its
