@@ -26,7 +26,10 @@ if [ "${2:-}" != "quick" ]; then
   # obs-80 workloads with every tensor-core kernel on
   for w in qmix_8m_per qmix_2s3z; do for o in 1 2; do
     timeout 200 python bench.py --workload $w --quick --steps 50 --warmup 5 --buffer 2000 --opt front_tc_wide=1 --opt wgrad_tc=$o >> gpurun_out/sweep_wide_all.log 2>> gpurun_out/sweep_wide_all.err
-  done; done; cat gpurun_out/sweep_wide_all.log
+  done; done
+  # 8m with the split mixer + k_mid on ONE stream (no forked branch at this size): k_qhead + k_qhead_bwd are 150 us of the fused-mixer step
+  timeout 200 python bench.py --workload qmix_8m_per --quick --steps 50 --warmup 5 --buffer 2000 --opt front_tc_wide=1 --opt wgrad_tc=2 --opt mixer_split=2 >> gpurun_out/sweep_wide_all.log 2>> gpurun_out/sweep_wide_all.err
+  cat gpurun_out/sweep_wide_all.log
   for o in 0 2; do for w in rmaddpg_spread rmatd3_spread_disc; do
     timeout 200 python bench.py --workload $w --quick --steps 100 --warmup 10 --opt front_tc_wide=1 --opt wgrad_tc=$o >> gpurun_out/sweep_maddpg.log 2>> gpurun_out/sweep_maddpg.err
   done; done; cat gpurun_out/sweep_maddpg.log
