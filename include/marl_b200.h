@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MX_ABI_VERSION 1
+#define MX_ABI_VERSION 2
 #define MX_MAX_NAME 64
 
 typedef struct mx_replay mx_replay;   /* one policy's episode store + sampler (RecPolicyBuffer + PER trees) */
@@ -161,6 +161,8 @@ typedef struct mx_qmix_cfg {
                                 net is MLPBase + Linear head without a GRU (mqmix/algorithm/agent_q_function.py), a "batch" is B single
                                 transitions stored as episodes of length 1 (step 0 = obs, step 1 = next_obs), episode_len must be 1.
                                 The head occupies the first act_dim rows of the (otherwise zero) weight_ih slot of the flat vector. */
+  int32_t no_feature_norm;   /* 1: --use_feature_normalization switched off (config.py: store_false; mlp.py:64-65): the input LayerNorm
+                                is skipped and its two tensors are absent from the parameter list */
 } mx_qmix_cfg;
 
 typedef struct mx_param_entry {
@@ -309,6 +311,7 @@ typedef struct mx_policy_step_args {
   float* h_copy;           /* optional second destination of the new state [rows][64] (e.g. mapped pinned host memory), or NULL */
   int32_t mlp;             /* 1: non-recurrent net (M_QMixPolicy.get_actions, mQMixPolicy.py:60-110): MLPBase -> head stored in the
                               weight_ih slot (see mx_qmix_cfg.mlp); h_in / h_out are ignored (h_out may be NULL) */
+  int32_t no_feature_norm; /* 1: the network has no input LayerNorm (mx_qmix_cfg.no_feature_norm) */
 } mx_policy_step_args;
 /* x / avail / out / greedy / greedy_q / h_copy may point into MAPPED PINNED HOST memory (cudaHostAlloc; same address on the
  * device under UVA): the kernel then reads the observation and writes the actions straight over PCIe and one env step costs one

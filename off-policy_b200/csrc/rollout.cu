@@ -29,6 +29,7 @@ struct RollArgs {
   float* greedy_q;         // [R] or null
   int R;
   int mlp;                 // non-recurrent net: head = first out_dim rows of the W_ih slot applied to the MLPBase output
+  int no_feature_norm;     // no input LayerNorm (--use_feature_normalization switched off)
 };
 
 // LayerNorm of v[0..n) in shared memory, in place (two-pass, biased variance, eps inside the sqrt like ATen); warp 0 only
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(MX_ROLL_THREADS) k_policy_step(RollArgs a) {
     for (int k = tid; k < I; k += MX_ROLL_THREADS) xs[k] = a.x[(size_t)r * a.x_ld + k];
     if (tid < MX_H) hs[tid] = a.h_in ? a.h_in[(size_t)r * MX_H + tid] : 0.f;
     __syncthreads();
-    roll_layer_norm(xs, I, th + L.fn_g, th + L.fn_b);                                   // mlp.py:64-65
+    if (!a.no_feature_norm) roll_layer_norm(xs, I, th + L.fn_g, th + L.fn_b);            // mlp.py:64-65 (block-uniform branch)
     {   // fc1: Linear -> ReLU -> LayerNorm                                               mlp.py:19-20
       const float d = roll_dot4(th + L.w1 + (size_t)u * I, xs, I, q);
       if (q == 0) v1[u] = fmaxf(d + th[L.b1 + u], 0.f);
@@ -142,7 +143,7 @@ extern "C" int mx_policy_step(const mx_policy_step_args* p, void* stream) {
   a.theta = p->theta;
   mx_net_layout(p->in_dim, p->out_dim, 0, &a.L);
   a.x = p->x; a.x_ld = p->x_ld; a.h_in = p->h_in; a.h_out = p->h_out; a.h_copy = p->h_copy; a.out = p->out;
-  a.avail = p->avail; a.avail_ld = p->avail_ld; a.greedy = p->greedy; a.greedy_q = p->greedy_q; a.R = p->rows; a.mlp = p->mlp;
+  a.avail = p->avail; a.avail_ld = p->avail_ld; a.greedy = p->greedy; a.greedy_q = p->greedy_q; a.R = p->rows; a.mlp = p->mlp; a.no_feature_norm = p->no_feature_norm;
   int grid = p->rows;
   const int cap = mx_num_sms() * 4;
   if (grid > cap) grid = cap;

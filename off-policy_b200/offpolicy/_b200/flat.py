@@ -76,7 +76,8 @@ def reference_style_init(entries, cfg, gain, use_orthogonal=True, hyper_layers=2
         out[prefix + ".weight"], out[prefix + ".bias"] = torch.ones(n), torch.zeros(n)
 
     if any(n.startswith("agent.") for n, *_ in entries):
-        lnorm("agent.rnn.feature_norm", I)
+        if any(n == "agent.rnn.feature_norm.weight" for n, *_ in entries):      # absent with --use_feature_normalization off
+            lnorm("agent.rnn.feature_norm", I)
         linear("agent.rnn.mlp.fc1.0", I, H, relu_gain)
         lnorm("agent.rnn.mlp.fc1.2", H)
         linear("agent.rnn.mlp.fc_h.0", H, H, relu_gain)

@@ -26,9 +26,10 @@ def _host_ptr(x):
 
 
 class PolicyStepper(object):
-    def __init__(self, in_dim, out_dim, mlp=False):
+    def __init__(self, in_dim, out_dim, mlp=False, feature_norm=True):
         self.in_dim, self.out_dim = int(in_dim), int(out_dim)
         self.mlp = bool(mlp)      # non-recurrent net (M_QMixPolicy): no state is carried
+        self.feature_norm = bool(feature_norm)      # False: --use_feature_normalization switched off
         self.dev = capi.device()
         self.rows = 0
         self._last_h = None      # (host array handed out, rows): its device copy is in self.d_h
@@ -78,6 +79,7 @@ class PolicyStepper(object):
         a.in_dim, a.out_dim, a.rows, a.x_ld, a.avail_ld = I, A, R, I, A
         a.x = base + 4 * o_x
         a.mlp = int(self.mlp)
+        a.no_feature_norm = 0 if self.feature_norm else 1
         a.h_in = None if self.mlp else (self.d_h.data_ptr() if resident else base + 4 * o_h)
         a.h_out = None if self.mlp else self.d_h.data_ptr()
         a.h_copy = None if self.mlp else base + 4 * o_hn

@@ -31,7 +31,8 @@ def mlp_reference_style_init(entries, in_dim, hidden, act_dim, gain, use_orthogo
     def lnorm(prefix, n):
         out[prefix + ".weight"], out[prefix + ".bias"] = torch.ones(n), torch.zeros(n)
 
-    lnorm("mlp.feature_norm", in_dim)
+    if any(n.endswith("mlp.feature_norm.weight") for n, *_ in entries):      # absent with --use_feature_normalization off
+        lnorm("mlp.feature_norm", in_dim)
     linear("mlp.mlp.fc1.0", in_dim, hidden, relu_gain)
     lnorm("mlp.mlp.fc1.2", hidden)
     linear("mlp.mlp.fc_h.0", hidden, hidden, relu_gain)
@@ -57,7 +58,7 @@ class M_QMixPolicy(object):
         self.multidiscrete = "MultiDiscrete" in self.act_space.__class__.__name__
         if self.multidiscrete:
             raise NotImplementedError("B200 M-QMIX path: MultiDiscrete action spaces are not implemented")
-        for flag, want in (("use_feature_normalization", True), ("use_ReLU", True), ("use_conv1d", False)):
+        for flag, want in (("use_ReLU", True), ("use_conv1d", False)):
             if getattr(self.args, flag, want) != want:
                 raise NotImplementedError("B200 M-QMIX path requires %s=%s" % (flag, want))
         if getattr(self.args, "layer_N", 1) != 1:
@@ -79,7 +80,7 @@ class M_QMixPolicy(object):
     def _step(self, obs, available_actions=None):
         if self._roll is None:
             from offpolicy._b200.rollout import PolicyStepper
-            self._roll = PolicyStepper(self.obs_dim, self.act_dim, mlp=True)
+            self._roll = PolicyStepper(self.obs_dim, self.act_dim, mlp=True, feature_norm=bool(getattr(self.args, "use_feature_normalization", True)))
         q, _, greedy, greedy_q = self._roll.step(self.q_network.flat, obs, None, available_actions)
         return q, greedy, greedy_q
 

@@ -26,7 +26,8 @@ def qmix_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, ma
         use_huber=int(args.use_huber_loss), use_per=int(args.use_per), use_avail=int(use_avail), world_size=world_size,
         gamma=args.gamma, huber_delta=args.huber_delta, per_nu=args.per_nu, per_eps=args.per_eps, lr=args.lr,
         adam_beta1=0.9, adam_beta2=0.999, adam_eps=args.opti_eps, max_grad_norm=args.max_grad_norm, tau=args.tau,
-        prev_act_inp=0 if mlp else int(bool(getattr(args, "prev_act_inp", False))), mlp=int(bool(mlp)))
+        prev_act_inp=0 if mlp else int(bool(getattr(args, "prev_act_inp", False))), mlp=int(bool(mlp)),
+        no_feature_norm=0 if getattr(args, "use_feature_normalization", True) else 1)
 
 
 def param_entries(cfg):
@@ -54,7 +55,7 @@ class QMixPolicy(object):
         self.discrete = is_discrete(self.act_space)
         self.multidiscrete = False
         self.prev_act_inp = bool(getattr(self.args, "prev_act_inp", False))
-        for flag, want in (("use_rnn_layer", True), ("use_feature_normalization", True), ("use_ReLU", True), ("use_conv1d", False)):
+        for flag, want in (("use_rnn_layer", True), ("use_ReLU", True), ("use_conv1d", False)):
             if getattr(self.args, flag, want) != want:
                 raise NotImplementedError("B200 QMIX path requires %s=%s" % (flag, want))
         if getattr(self.args, "layer_N", 1) != 1 or getattr(self.args, "recurrent_N", 1) != 1:
@@ -84,7 +85,7 @@ class QMixPolicy(object):
     def _stepper(self):
         if self._roll is None:
             from offpolicy._b200.rollout import PolicyStepper
-            self._roll = PolicyStepper(self.q_network_input_dim, self.act_dim)
+            self._roll = PolicyStepper(self.q_network_input_dim, self.act_dim, feature_norm=bool(getattr(self.args, "use_feature_normalization", True)))
         return self._roll
 
     def _step(self, obs, rnn_states, available_actions=None, prev_actions=None):

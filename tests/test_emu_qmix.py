@@ -99,3 +99,16 @@ def test_mpe_shapes_without_avail_masks(emu_engine):
 def test_prev_act_inp_matches_reference_golden(emu_engine, debug):
     """--prev_act_inp (config.py:81): the agent net reads [obs | previous one-hot action]; golden made by the reference with the flag."""
     qc.check_step_against(None, "qmix_small_prev_act", intermediates=False, debug=debug)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(front_tc=0), dict(wgrad_tc=2)], ids=["default", "ffma_front", "tc_backward"])
+def test_feature_normalization_off_matches_reference_golden(emu_engine, opts):
+    """--use_feature_normalization (a store_false flag): no input LayerNorm, its two tensors absent from the state_dict."""
+    lib = emu_engine.lib()
+    for k, v in opts.items():
+        lib.mx_set_option(k.encode(), v)
+    try:
+        qc.check_step_against(None, "qmix_small_nofn", intermediates=False, debug=False)
+    finally:
+        lib.mx_set_option(b"front_tc", 1)
+        lib.mx_set_option(b"wgrad_tc", 0)

@@ -44,6 +44,9 @@ RUNS = {
     "mlp_mvdn": ("mvdn", 100, ["--runner", "mlp"], False),                         # reference M_VDNMixer is broken (App. D-5)
     # MLP MADDPG / MATD3 have no B200 learner: the shadow package lets them fall through to the reference's own
     # trainer, which then trains from the HBM transition replay (its sample materialises the reference's 13-tuple) -- same run, bit for bit
+    # --use_feature_normalization is a store_false flag: the networks lose their input LayerNorm (rollout kernel + learner)
+    "qmix_no_feature_norm": ("qmix", 100, ["--use_feature_normalization"], True),
+    "mlp_mqmix_no_feature_norm": ("mqmix", 100, ["--runner", "mlp", "--use_feature_normalization"], True),
     "mlp_maddpg": ("maddpg", 100, ["--runner", "mlp"], True),
     "mlp_matd3": ("matd3", 100, ["--runner", "mlp"], True),
 }
