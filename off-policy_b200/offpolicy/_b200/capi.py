@@ -37,6 +37,9 @@ class Episodes(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "share_obs", "acts", "rewards", "dones", "dones_env", "avail")]
 
 
+ABI_VERSION = 2        # MX_ABI_VERSION of include/marl_b200.h the struct mirrors below correspond to
+
+
 class QmixCfg(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("n_agents", "obs_dim", "act_dim", "state_dim", "hidden", "mixer_hidden", "hyper_hidden",
                                           "hyper_layers", "episode_len", "max_batch", "vdn", "double_q", "use_huber", "use_per",
@@ -156,6 +159,9 @@ def _declare(lib):
         fn.argtypes = args
     if missing:
         raise MxError("libmarl_b200 is missing symbols declared in include/marl_b200.h: %s" % ", ".join(missing))
+    if int(lib.mx_abi_version()) != ABI_VERSION:      # the ctypes mirrors of the structs above were written for this version
+        raise MxError("libmarl_b200 reports ABI version %d, these bindings expect %d: rebuild (python __graft_entry__.py build)"
+                      % (int(lib.mx_abi_version()), ABI_VERSION))
     return lib
 
 

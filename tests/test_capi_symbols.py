@@ -28,7 +28,10 @@ def test_cuda_library_exports_every_declared_symbol():
     lib.mx_is_cuda_build.restype = ctypes.c_int
     assert lib.mx_is_cuda_build() == 1
     lib.mx_abi_version.restype = ctypes.c_int
-    assert lib.mx_abi_version() == 1
+    from offpolicy._b200 import capi
+    header = open(os.path.join(ROOT, "include", "marl_b200.h")).read()
+    want = int(re.search(r"#define\s+MX_ABI_VERSION\s+(\d+)", header).group(1))
+    assert lib.mx_abi_version() == want == capi.ABI_VERSION      # header, library and ctypes mirrors agree
 
 
 def test_product_loader_refuses_to_run_without_gpu():
