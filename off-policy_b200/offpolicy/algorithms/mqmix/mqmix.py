@@ -10,8 +10,7 @@ import numpy as np
 import torch
 
 from offpolicy._b200 import capi
-from offpolicy._b200.flat import FlatModule, reference_style_init
-from offpolicy.algorithms.qmix.algorithm.QMixPolicy import qmix_cfg_struct, param_entries
+from offpolicy.algorithms.qmix.algorithm.QMixPolicy import qmix_cfg_struct
 from offpolicy.algorithms.qmix.qmix import QMix
 from offpolicy.utils.mlp_buffer import MlpSampledBatch
 from offpolicy.utils.rec_buffer import DeviceArray

@@ -9,9 +9,8 @@ on access while the B200 trainer (algorithms/mqmix/mqmix.py) reads the device-si
 consumed by any shared-policy learner kernel and is kept in a host-side array.
 """
 import numpy as np
-import torch
 
-from offpolicy.utils.rec_buffer import RecPolicyBuffer, DeviceArray, _LazyField
+from offpolicy.utils.rec_buffer import RecPolicyBuffer, _LazyField
 
 MLP_FIELDS = ("obs", "share_obs", "acts", "rewards", "next_obs", "next_share_obs", "dones", "dones_env", "valid_transition",
               "avail_acts", "next_avail_acts")

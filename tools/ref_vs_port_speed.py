@@ -7,7 +7,7 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden
     sys.path.insert(0, p)
 import numpy as np, torch
 import bench
-from oracle.qmix import QmixConfig
+
 
 threads = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 cfg, T, B = bench.make_cfg("qmix_3m")
