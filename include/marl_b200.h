@@ -338,7 +338,7 @@ int mx_tc_linear_probe(const float* X, const float* W, float* Y, int32_t M, int3
  *   front_tc (1)        time-batched front layers on the tcgen05 3xTF32 kernel (input width <= 64); 0 = the FFMA kernel
  *   front_tc_wide (0)   64 < input width <= 128 on tcgen05 too (k_front_fwd_tc_wide; emulator-verified, off until timed on a B200)
  *   wgrad_tc (0)        backward of the front layers on tcgen05: 1 = weight gradients (k_wgrad_tc) beside k_front_bwd, 2 = k_front_bwd_tc +
- *                       k_wgrad_tc replace k_front_bwd (input width <= 112, wgrad_tc_wide = 0 limits it to 64; emulator-verified, off until timed on a B200)
+ *                       k_wgrad_tc replace k_front_bwd (input width <= 128, wgrad_tc_wide = 0 limits it to 64; emulator-verified, off until timed on a B200)
  *   tc_swap_ls (0)      shared-memory descriptor stride convention (see mx_tc_linear_probe)
  *   overlap (1) / overlap_rows (12288)   state-only kernels on a forked stream / graph branch: 0 off, 1 when B*(T+1)*N <= overlap_rows, 2 always
  *   mixer_split (1), mid_fused (1)       split hypernet / core mixer kernels; k_mid between the recurrences (0 = separate kernels)

@@ -171,7 +171,7 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, const char* a_hi, c
 // Same, for a layer whose K dimension is fed in chunks (the operand tiles are refilled between calls): acc0 = 0 starts the
 // accumulator, acc0 = 1 adds this chunk's products to what the previous calls left in TMEM.  The caller waits on `bar` after each call.
 __device__ __forceinline__ void issue_layer_acc(uint32_t tmem_d, const char* a_hi, const char* a_lo, const char* b_hi, const char* b_lo, int N, int K,
-                                                int swap_ls, uint32_t acc0, uint32_t bar) {
+                                                int swap_ls, uint32_t acc0, uint32_t bar, bool do_commit = true) {
   const uint32_t kstride = 128, mstride = (uint32_t)(K >> 2) * 128;
   const uint32_t lbo = swap_ls ? mstride : kstride, sbo = swap_ls ? kstride : mstride;
   const uint32_t idesc = make_idesc_tf32(128, N);
@@ -184,7 +184,7 @@ __device__ __forceinline__ void issue_layer_acc(uint32_t tmem_d, const char* a_h
       acc = 1;
     }
   }
-  commit(bar);
+  if (do_commit) commit(bar);      // (one commit may cover several groups of MMAs issued back to back)
 }
 
 }  // namespace tc
@@ -303,7 +303,7 @@ inline void issue_layer(uint32_t tmem_d, const char* a_hi, const char* a_lo, con
 // Same, for a layer whose K dimension is fed in chunks (the operand tiles are refilled between calls): acc0 = 0 starts the
 // accumulator, acc0 = 1 adds this chunk's products to what the previous calls left in TMEM.  The caller waits on `bar` after each call.
 inline void issue_layer_acc(uint32_t tmem_d, const char* a_hi, const char* a_lo, const char* b_hi, const char* b_lo, int N, int K,
-                                                int swap_ls, uint32_t acc0, uint32_t bar) {
+                                                int swap_ls, uint32_t acc0, uint32_t bar, bool do_commit = true) {
   const uint32_t kstride = 128, mstride = (uint32_t)(K >> 2) * 128;
   const uint32_t lbo = swap_ls ? mstride : kstride, sbo = swap_ls ? kstride : mstride;
   const uint32_t idesc = make_idesc_tf32(128, N);
@@ -316,7 +316,7 @@ inline void issue_layer_acc(uint32_t tmem_d, const char* a_hi, const char* a_lo,
       acc = 1;
     }
   }
-  commit(bar);
+  if (do_commit) commit(bar);      // (one commit may cover several groups of MMAs issued back to back)
 }
 
 }  // namespace tc

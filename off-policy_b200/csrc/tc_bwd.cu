@@ -10,7 +10,8 @@
 // of a column of ones appended to B.  Three accumulators live in TMEM for the whole CTA (rows are split over CTAs in chunks of 64):
 //   D1[128][144] = [dgi_r | dgi_z]^T     . [x2 | h_prev | 1]   -> dW_ih[0:128], dW_hh[0:128], db_ih[0:128] (= db_hh[0:128])
 //   D2[128][144] = [dgi_n | dgi_n * r]^T . [x2 | h_prev | 1]   -> dW_ih[128:192] (rows 0-63, cols 0-63), dW_hh[128:192] (rows 64-127, cols 64-127)
-//   D3[128][..]  = [da2   | da1]^T       . [x1 | x0 | 1]       -> dW2 (rows 0-63, cols 0-63), dW1 (rows 64-127, cols 64..), db2, db1
+//   D3[128][..]  = [da2   | da1]^T       . [x1 | x0]           -> dW2 (rows 0-63, cols 0-63), dW1 (rows 64-127, cols 64..)
+//   D4[128][16]  = [da2   | da1]^T       . [1 | 0..]           -> db2, db1 (a 16-column accumulator in D1's padding; same A tile, same commit)
 // The off-diagonal blocks of D2 / D3 are products nobody needs (half of two of the three MMAs): the tensor core is not the limit here.
 // Each CTA writes its sums as ONE gradient partial (its row of gpart), like k_front_bwd does for the LayerNorm parameters it keeps.
 #include "mx_internal.h"
@@ -25,8 +26,9 @@ int g_mx_wgrad_tc_wide = 1;   // with wgrad_tc: input widths 65 .. 112 too (SMAC
 #define WG_ROWS 64            // rows per MMA group (the K extent of one staged tile)
 #define WG_DSTRIDE 160        // TMEM column stride between the three accumulators
 
-#define WG_MAX_IN 112          // input widths up to here: D3 = [x1 | x0 | 1] is 64 + round_up(I, 16) + 16 <= 192 columns, the rest of TMEM
-struct WgradSmem { int o_ahi, o_alo, o_bhi, o_blo, total; };
+#define WG_MAX_IN 128          // input widths up to here: D3 = [x1 | x0] is 64 + round_up(I, 16) <= 192 columns, the rest of TMEM
+#define WG_ONES_COL 144        // db2 / db1 = [da2 | da1]^T . 1: a 16-column accumulator in the padding between D1 (144 wide) and D2 (at 160)
+struct WgradSmem { int o_ahi, o_alo, o_bhi, o_blo, o_ones, total; };
 static WgradSmem wgrad_smem(int n3) {
   const int nb = n3 > 144 ? n3 : 144;
   WgradSmem s;
@@ -35,6 +37,7 @@ static WgradSmem wgrad_smem(int n3) {
   s.o_alo = o; o += 128 * WG_ROWS * 4;
   s.o_bhi = o; o += nb * WG_ROWS * 4;
   s.o_blo = o; o += nb * WG_ROWS * 4;
+  s.o_ones = o; o += 2 * 16 * WG_ROWS * 4;      // [16][64] hi | lo: feature 0 = 1 for the chunk's valid rows
   s.total = o;
   return s;
 }
@@ -73,9 +76,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
   const float* __restrict__ th = a.theta;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int I = L.in_dim, N = a.N, T1 = a.T1 > 0 ? a.T1 : a.T + 1;
-  const int Kp16 = w.Kp16, N3 = 64 + Kp16 + 16, ones3 = 64 + Kp16;
+  const int Kp16 = w.Kp16, N3 = 64 + Kp16;
   char* base = reinterpret_cast<char*>(smem_raw);
   char *a_hi = base + sm.o_ahi, *a_lo = base + sm.o_alo, *b_hi = base + sm.o_bhi, *b_lo = base + sm.o_blo;
+  char *o_hi = base + sm.o_ones, *o_lo = o_hi + 16 * WG_ROWS * 4;
   const uint32_t bar = tc::bar_addr(&bar_s);
   if (warp == 0) tc::tmem_alloc<512>(&tmem_s);
   if (tid == 0) {
@@ -185,17 +189,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
             const int c = n - 64;
             const float xr = a.X[(size_t)m * a.ldx + c];
             v = a.feature_norm ? (xr - st_s[4 * WG_ROWS + 2 * (m - row0)]) * st_s[4 * WG_ROWS + 2 * (m - row0) + 1] * par_s[256 + c] + par_s[384 + c] : xr;
-          } else if (n == ones3) v = 1.f;
+          }
         }
         x[j] = v;
       }
       wg_put(b_hi, b_lo, n, kq, x);
     }
+    for (int p = tid; p < 16 * 16; p += blockDim.x) {      // the ones block: feature 0 = 1 for valid rows (lo part: zeros)
+      int n, kq;
+      wg_pair(p, &n, &kq);
+      float x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = (n == 0 && row0 + 4 * kq + j < a.M) ? 1.f : 0.f;
+      wg_put(o_hi, o_lo, n, kq, x);
+    }
     tc::fence_async_smem();
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
-    if (tid == 0) tc::issue_layer_acc(tmem_base + 2 * WG_DSTRIDE, a_hi, a_lo, b_hi, b_lo, N3, WG_ROWS, swap_ls, acc0, bar);
+    if (tid == 0) {
+      tc::issue_layer_acc(tmem_base + 2 * WG_DSTRIDE, a_hi, a_lo, b_hi, b_lo, N3, WG_ROWS, swap_ls, acc0, bar, false);
+      tc::issue_layer_acc(tmem_base + WG_ONES_COL, a_hi, a_lo, o_hi, o_lo, 16, WG_ROWS, swap_ls, acc0, bar, true);      // one commit for both
+    }
     tc::mbar_wait(bar, phase);
     phase ^= 1;
     tc::fence_after();
@@ -220,9 +235,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
     for (int c4 = 0; c4 < 16; ++c4)
       *reinterpret_cast<float4*>(gp + L.whh + (size_t)r * MX_H + 4 * c4) = any ? make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (any) tc::tmem_ld32(trow + 128, t);
+  if (any) tc::tmem_ld32(trow + 128, t);      // column 128: D1's ones column; column 144 (= t[16]): [da2 | da1]^T . 1
   gp[L.bih + r] = any ? t[0] : 0.f;
   if (gru) gp[L.bhh + r] = any ? t[0] : 0.f;
+  gp[(r < 64 ? L.b2 : L.b1) + (r & 63)] = any ? t[16] : 0.f;
   // D2: n gate.  rows 0-63: dW_ih[128 + r] = cols 0-63, db_ih ; rows 64-127: dW_hh[128 + r - 64] = cols 64-127, db_hh
   if (any) tc::tmem_ld64(trow + WG_DSTRIDE + (r < 64 ? 0 : 64), v);
   if (r < 64 || gru) {
@@ -252,8 +268,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
         if (64 + c < I) dst[64 + c] = any ? v2[c] : 0.f;
     }
   }
-  if (any) tc::tmem_ld32(trow + 2 * WG_DSTRIDE + ones3 - 16, t);      // 32 columns around the ones column (inside this accumulator)
-  gp[(r < 64 ? L.b2 : L.b1) + (r & 63)] = any ? t[16] : 0.f;
   }
   if (w.ln_zero_from >= 0 && (int)blockIdx.x >= w.ln_zero_from) {
     for (int c = tid; c < MX_H; c += blockDim.x) { gp[L.ln2_g + c] = 0.f; gp[L.ln2_b + c] = 0.f; gp[L.ln1_g + c] = 0.f; gp[L.ln1_b + c] = 0.f; }
@@ -277,7 +291,7 @@ static int launch_wgrad_tc(const FrontBwdArgs& a, int nparts, int ln_zero_from, 
   w.ln_zero_from = ln_zero_from;
   w.nchunks = mx_ceil_div(a.M, WG_ROWS);
   w.Kp16 = mx_round_up(a.L.in_dim, 16);
-  WgradSmem sm = wgrad_smem(64 + w.Kp16 + 16);
+  WgradSmem sm = wgrad_smem(64 + w.Kp16);
 #if !MX_EMU
   static int configured = 0;
   if (sm.total > configured) {

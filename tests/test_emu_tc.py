@@ -126,9 +126,9 @@ def test_tensor_core_backward_mlp_variant_matches_reference_golden(emu_engine, n
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("obs_dim", [65, 80, 96, 112])
+@pytest.mark.parametrize("obs_dim", [65, 80, 96, 112, 128])
 def test_tensor_core_backward_wide_inputs_vs_oracle(emu_engine, obs_dim, mode):
-    """64 < obs_dim <= 112 through the tensor-core backward (fc1's transposed weight image takes turns with fc2's in shared memory, the
+    """64 < obs_dim <= 128 through the tensor-core backward (fc1's transposed weight image takes turns with fc2's in shared memory, the
     feature LayerNorm's gradients are summed in two 64-column rounds, dW1 is read from two 64-column blocks of TMEM), together with the
     wide forward kernel."""
     from oracle.qmix import QmixConfig, synth_batch

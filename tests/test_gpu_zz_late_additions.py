@@ -129,7 +129,7 @@ def test_tensor_core_backward_mlp_variant(gpu_engine, mode):
         lib.mx_set_option(b"wgrad_tc", 0)
 
 
-@pytest.mark.parametrize("obs_dim,n_agents,B,T,mode", [(80, 8, 8, 20, 2), (80, 5, 32, 30, 1), (112, 3, 16, 12, 2)])
+@pytest.mark.parametrize("obs_dim,n_agents,B,T,mode", [(80, 8, 8, 20, 2), (80, 5, 32, 30, 1), (128, 3, 16, 12, 2)])
 def test_tensor_core_backward_wide_inputs_vs_oracle(gpu_engine, obs_dim, n_agents, B, T, mode):
     """SMAC-sized observations (8m / 2s3z: 80) through the wide tensor-core forward AND backward kernels."""
     from oracle.qmix import QmixConfig, synth_batch
