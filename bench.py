@@ -368,6 +368,11 @@ def kernel_work(cfg, T, B, P):
         "k_qhead_bwd": 2.0 * M * 3 * H,
         "k_gru_bwd": 2.0 * M * 3 * H * H,
         "k_front_bwd": 2.0 * M * (2 * 3 * H * H * 2 + 3 * H * H + 2 * H * H + H * H + 2 * O * H + O * H) / 1.0,
+        # tensor-core variants (options front_tc_wide / wgrad_tc): same algorithmic work as the kernels they replace, split in two for the backward
+        "k_front_fwd_tc": 2 * 2.0 * M * (O * H + H * H + 3 * H * H),
+        "k_front_fwd_tc_wide": 2 * 2.0 * M * (O * H + H * H + 3 * H * H),
+        "k_front_bwd_tc": 2.0 * M * (3 * H * H + H * H + O * H),                      # dx2 = dgi.W_ih, dx1 = da2.W2, dx0 = da1.W1
+        "k_wgrad_tc": 2.0 * M * (2 * 3 * H * H + H * H + O * H),                     # dW_ih, dW_hh, dW2, dW1
     }
     fields = 4.0 * B * (N * (T + 1) * O + (T + 1) * S + N * T * A + N * (T + 1) * A + 3 * N * T + T)
     by = {"k_gather": 2 * fields, "k_adam": 4.0 * P * 7, "k_polyak": 4.0 * P * 3, "k_grad_reduce": 4.0 * P * 2}
