@@ -77,16 +77,25 @@ def test_mlp_workload_dry_run(bench_mod, monkeypatch):
     assert bench._lines[-1]["quick"] is True
 
 
+@pytest.mark.parametrize("opts", [{}, {"wgrad_tc": 2}], ids=["default", "tc_backward"])
 @pytest.mark.parametrize("workload,shape", [("qmix_mpe_spread", (3, 18, 5, 54, 5, 4, False))])
-def test_recurrent_workload_dry_run(bench_mod, monkeypatch, workload, shape):
+def test_recurrent_workload_dry_run(bench_mod, monkeypatch, emu_engine, workload, shape, opts):
     """The default bench arm (run_engine) at shrunken shapes: the MPE workload (no availability masks, reward normalisation)."""
     bench = bench_mod
     monkeypatch.setitem(bench.WORKLOADS, workload, shape)
     monkeypatch.setattr(bench, "best_cpu_threads", lambda *a, **k: 1)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
-    args = types.SimpleNamespace(workload=workload, impl="b200", gpus=1, steps=3, warmup=3, buffer=48, quick=False, opt=[])
-    bench.run_engine(args)
+    args = types.SimpleNamespace(workload=workload, impl="b200", gpus=1, steps=3, warmup=3, buffer=48, quick=False, opt=["%s=%d" % kv for kv in opts.items()])
+    for k, v in opts.items():
+        emu_engine.lib().mx_set_option(k.encode(), v)
+    try:
+        bench.run_engine(args)
+    finally:
+        for k in opts:
+            emu_engine.lib().mx_set_option(k.encode(), 0)
     line = bench._lines[-1]
+    if opts.get("wgrad_tc") == 2:
+        assert "k_wgrad_tc" in line["kernels"] and "k_front_bwd_tc" in line["kernels"] and "k_front_bwd" not in line["kernels"]
     for k in CONTRACT:
         assert k in line, k
     assert line["config"]["workload"] == workload
