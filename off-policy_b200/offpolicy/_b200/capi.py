@@ -53,7 +53,7 @@ class MaddpgCfg(C.Structure):
                                           "actor_update_interval", "use_huber", "use_per")] +
                 [(n, C.c_float) for n in ("gamma", "huber_delta", "per_nu", "per_eps", "lr", "adam_beta1", "adam_beta2", "adam_eps",
                                           "max_grad_norm", "tau", "weight_decay", "target_noise")] +
-                [("discrete", C.c_int32)])
+                [("discrete", C.c_int32), ("no_feature_norm", C.c_int32)])
 
 
 class ParamEntry(C.Structure):

@@ -45,7 +45,8 @@ def maddpg_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, 
                           use_huber=int(args.use_huber_loss), use_per=int(args.use_per), gamma=args.gamma, huber_delta=args.huber_delta,
                           per_nu=args.per_nu, per_eps=args.per_eps, lr=args.lr, adam_beta1=0.9, adam_beta2=0.999, adam_eps=args.opti_eps,
                           max_grad_norm=args.max_grad_norm, tau=args.tau, weight_decay=float(getattr(args, "weight_decay", 0) or 0),
-                          target_noise=float(target_noise or 0.0), discrete=int(bool(discrete)))
+                          target_noise=float(target_noise or 0.0), discrete=int(bool(discrete)),
+                          no_feature_norm=0 if getattr(args, "use_feature_normalization", True) else 1)
 
 
 def maddpg_entries(cfg, which):
@@ -75,7 +76,8 @@ def _init_net(mod, in_dim, hidden, out_specs, gain, use_orthogonal):
     def lnorm(prefix, n):
         sd[prefix + ".weight"], sd[prefix + ".bias"] = torch.ones(n), torch.zeros(n)
 
-    lnorm("rnn.feature_norm", in_dim)
+    if "rnn.feature_norm.weight" in mod.views:      # absent with --use_feature_normalization off
+        lnorm("rnn.feature_norm", in_dim)
     linear("rnn.mlp.fc1.0", in_dim, hidden, relu_gain); lnorm("rnn.mlp.fc1.2", hidden)
     linear("rnn.mlp.fc_h.0", hidden, hidden, relu_gain); lnorm("rnn.mlp.fc_h.2", hidden)
     for k in ("0.weight", "0.bias", "2.weight", "2.bias"):
@@ -102,7 +104,7 @@ class R_MADDPGPolicy(object):
         self.weight_decay = getattr(self.args, "weight_decay", 0)
         if getattr(self.args, "prev_act_inp", False):
             raise NotImplementedError("B200 R-MADDPG path: --prev_act_inp is not implemented")
-        for flag, want in (("use_feature_normalization", True), ("use_ReLU", True), ("use_conv1d", False)):      # fail loudly, never approximate
+        for flag, want in (("use_ReLU", True), ("use_conv1d", False)):      # fail loudly, never approximate
             if getattr(self.args, flag, want) != want:
                 raise NotImplementedError("B200 R-MADDPG path requires %s=%s" % (flag, want))
         if getattr(self.args, "layer_N", 1) != 1 or getattr(self.args, "hidden_size", 64) != 64:
@@ -151,7 +153,7 @@ class R_MADDPGPolicy(object):
     def _stepper(self):
         if getattr(self, "_roll", None) is None:
             from offpolicy._b200.rollout import PolicyStepper
-            self._roll = PolicyStepper(self.obs_dim, self.act_dim)
+            self._roll = PolicyStepper(self.obs_dim, self.act_dim, feature_norm=bool(getattr(self.args, "use_feature_normalization", True)))
         return self._roll
 
     def get_actions(self, obs, prev_actions, rnn_states, available_actions=None, t_env=None, explore=False, use_target=False, use_gumbel=False):

@@ -269,7 +269,7 @@ def gen_maddpg(name, cfg, flags=(), B=4, T=6, steps=2, per=False, use_avail=Fals
             for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
                 out.update(sd_np("final.%s." % tag, mod))
     out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, cfg.hidden, B, T, steps, int(cfg.td3), int(per),
-                                int(cfg.discrete)])
+                                int(cfg.discrete), int(not args.use_feature_normalization)])
     out["meta.hparams"] = np.array([args.gamma, args.lr, args.opti_eps, args.max_grad_norm, args.tau, args.huber_delta, args.per_nu,
                                     args.per_eps, float(args.target_action_noise_std), args.weight_decay], dtype=np.float64)
     path = os.path.join(HERE, name + ".npz")
@@ -475,4 +475,6 @@ if __name__ == "__main__" and "nofn" in sys.argv[1:]:
     # --use_feature_normalization is a store_false flag (config.py): passing it switches the input LayerNorm off
     torch.set_num_threads(1)
     gen_qmix("qmix_small_nofn", QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48, feature_norm=False), flags=["--use_feature_normalization"], steps=2)
+    from oracle.maddpg import MaddpgConfig
+    gen_maddpg("matd3_disc_nofn", MaddpgConfig(act_dim=5, discrete=True, td3=True, actor_update_interval=2, feature_norm=False), flags=["--use_feature_normalization"], steps=2)
     gen_mqmix("mqmix_small_nofn", QmixConfig(n_agents=3, obs_dim=18, act_dim=5, state_dim=54, feature_norm=False), flags=["--use_feature_normalization"], steps=1)

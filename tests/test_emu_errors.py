@@ -81,14 +81,14 @@ def test_trainer_rejects_what_it_does_not_implement(emu_engine):
         setattr(a2, flag, val)
         with pytest.raises(NotImplementedError):
             QMixPolicy({"args": a2, "device": emu_engine.device()}, info)
-    # the recurrent MADDPG / MATD3 policies validate the same flags (feature normalisation off is implemented for the QMIX family only)
+    # the recurrent MADDPG / MATD3 policies validate the same flags
     import maddpg_checks as mdc
     from oracle.maddpg import MaddpgConfig
     from offpolicy.algorithms.r_maddpg.algorithm.rMADDPGPolicy import R_MADDPGPolicy
     margs = mdc.make_args(MaddpgConfig(n_agents=2, obs_dim=5, act_dim=2, state_dim=6), 4)
     minfo = dict(obs_space=[5], share_obs_space=[6], act_space=mdc.Box(2), cent_obs_dim=6, cent_act_dim=4)
     R_MADDPGPolicy({"args": margs, "device": emu_engine.device()}, minfo)
-    for flag, val in (("use_feature_normalization", False), ("use_ReLU", False), ("layer_N", 2), ("hidden_size", 128), ("prev_act_inp", True)):
+    for flag, val in (("use_ReLU", False), ("layer_N", 2), ("hidden_size", 128), ("prev_act_inp", True)):
         a2 = types.SimpleNamespace(**vars(margs))
         setattr(a2, flag, val)
         with pytest.raises(NotImplementedError):

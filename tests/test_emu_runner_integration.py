@@ -47,6 +47,7 @@ RUNS = {
     # --use_feature_normalization is a store_false flag: the networks lose their input LayerNorm (rollout kernel + learner)
     "qmix_no_feature_norm": ("qmix", 100, ["--use_feature_normalization"], True),
     "mlp_mqmix_no_feature_norm": ("mqmix", 100, ["--runner", "mlp", "--use_feature_normalization"], True),
+    "rmatd3_no_feature_norm": ("rmatd3", 100, ["--actor_train_interval_step", "1", "--use_feature_normalization"], True),
     "mlp_maddpg": ("maddpg", 100, ["--runner", "mlp"], True),
     "mlp_matd3": ("matd3", 100, ["--runner", "mlp"], True),
 }
