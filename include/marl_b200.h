@@ -163,6 +163,7 @@ typedef struct mx_qmix_cfg {
                                 The head occupies the first act_dim rows of the (otherwise zero) weight_ih slot of the flat vector. */
   int32_t no_feature_norm;   /* 1: --use_feature_normalization switched off (config.py: store_false; mlp.py:64-65): the input LayerNorm
                                 is skipped and its two tensors are absent from the parameter list */
+  int32_t use_tanh;          /* 1: --use_ReLU switched off (config.py: store_false; mlp.py:12,19-22): tanh instead of ReLU in fc1 / fc2 */
 } mx_qmix_cfg;
 
 typedef struct mx_param_entry {
@@ -257,6 +258,7 @@ typedef struct mx_maddpg_cfg {
   int32_t discrete;               /* 1: Discrete(act_dim) actions -- one-hot buffer actions, arg-max one-hot / hard Gumbel-softmax
                                      actor outputs (rMADDPGPolicy.py:104-120, util.py:106-166); 0: Box(act_dim)              */
   int32_t no_feature_norm;   /* 1: --use_feature_normalization switched off: no input LayerNorm in the actor and the critic */
+  int32_t use_tanh;          /* 1: --use_ReLU switched off: tanh instead of ReLU in the fc1 / fc2 blocks of both networks */
 } mx_maddpg_cfg;
 /* which = 0: actor ("rnn.*", "act.action_out.*"), 1: critic ("rnn.*", "q_outs.k.*"); names = reference state_dict keys */
 int mx_maddpg_param_layout(const mx_maddpg_cfg* cfg, int32_t which, mx_param_entry* out, int32_t max_entries, int64_t* total_floats);
@@ -313,6 +315,7 @@ typedef struct mx_policy_step_args {
   int32_t mlp;             /* 1: non-recurrent net (M_QMixPolicy.get_actions, mQMixPolicy.py:60-110): MLPBase -> head stored in the
                               weight_ih slot (see mx_qmix_cfg.mlp); h_in / h_out are ignored (h_out may be NULL) */
   int32_t no_feature_norm; /* 1: the network has no input LayerNorm (mx_qmix_cfg.no_feature_norm) */
+  int32_t use_tanh;        /* 1: tanh instead of ReLU in fc1 / fc2 (mx_qmix_cfg.use_tanh) */
 } mx_policy_step_args;
 /* x / avail / out / greedy / greedy_q / h_copy may point into MAPPED PINNED HOST memory (cudaHostAlloc; same address on the
  * device under UVA): the kernel then reads the observation and writes the actions straight over PCIe and one env step costs one

@@ -268,7 +268,7 @@ static FrontBwdSmem front_bwd_smem(int in_dim, int TM) {
 // LayerNorm backward on a 64-wide row spread over a half-warp; v = upstream grad w.r.t. LN output (cols 4tx+j),
 // u = LN input.  Returns grad w.r.t. LN input, masked by ReLU (u > 0); dgamma/dbeta partials accumulate in registers.
 template <int RM>
-MX_DEVINL void ln64_bwd_relu(float (&v)[RM][4], const float* u_s, int ld, const float* stat /*[TM][2]*/, const float* gamma_s,
+MX_DEVINL void ln64_bwd_relu(bool act_tanh, float (&v)[RM][4], const float* u_s, int ld, const float* stat /*[TM][2]*/, const float* gamma_s,
                              float (&dg)[4], float (&db)[4]) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
@@ -291,7 +291,7 @@ MX_DEVINL void ln64_bwd_relu(float (&v)[RM][4], const float* u_s, int ld, const 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float du = rstd * (dx[j] - s1 - xh[j] * s2);
-      v[i][j] = uu[j] > 0.f ? du : 0.f;
+      v[i][j] = act_tanh ? du * (1.f - uu[j] * uu[j]) : (uu[j] > 0.f ? du : 0.f);
     }
   }
 }
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
       mx_mm_nn<RM>(dgi_s + nc * 64, sm.ldg, Wc, sm.ld64, v);
     }
     // ---- LN2 backward + ReLU mask -> da2 ----
-    ln64_bwd_relu<RM>(v, u_s, sm.ld64, st2_s, ln2g_s, dg2, db2);
+    ln64_bwd_relu<RM>(a.act_tanh != 0, v, u_s, sm.ld64, st2_s, ln2g_s, dg2, db2);
     __syncthreads();     // x_s (x2), u_s (u2) no longer needed by anyone
 #pragma unroll
     for (int i = 0; i < RM; ++i) mx_st4(da_s + (ty * RM + i) * sm.ld64 + 4 * tx, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
 #pragma unroll
       for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
     mx_mm_nn<RM>(da_s, sm.ld64, Wc, sm.ld64, v);
-    ln64_bwd_relu<RM>(v, u_s, sm.ld64, st1_s, ln1g_s, dg1, db1);
+    ln64_bwd_relu<RM>(a.act_tanh != 0, v, u_s, sm.ld64, st1_s, ln1g_s, dg1, db1);
     __syncthreads();     // da_s (da2) consumed by everyone
 #pragma unroll
     for (int i = 0; i < RM; ++i) mx_st4(da_s + (ty * RM + i) * sm.ld64 + 4 * tx, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
 #pragma unroll
       for (int i = 0; i < RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaxf(acc[i][j] + th[b_off + tx + 16 * j], 0.f);
+        for (int j = 0; j < 4; ++j) { const float z = acc[i][j] + th[b_off + tx + 16 * j]; acc[i][j] = a.act_tanh ? tanhf(z) : fmaxf(z, 0.f); }
       float mean[RM], rstd[RM];
       mx_row_stats64<RM>(acc, mean, rstd);
       float* u_out = layer == 0 ? a.u1 : a.u2;

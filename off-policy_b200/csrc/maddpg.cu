@@ -551,7 +551,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   // ---------- A. actor: live + target over the T+1 steps ----------
   FrontFwdArgs ff;
   memset(&ff, 0, sizeof(ff));
-  ff.X = b->obs; ff.ldx = b->obs_ld; ff.M = Ma; ff.feature_norm = c.no_feature_norm ? 0 : 1;
+  ff.X = b->obs; ff.ldx = b->obs_ld; ff.M = Ma; ff.feature_norm = c.no_feature_norm ? 0 : 1; ff.act_tanh = c.use_tanh;
   ff.theta[0] = h->th_a; ff.theta[1] = h->th_a_tgt; ff.L = LA;
   ff.gi[0] = ws + W.a_gi[0]; ff.gi[1] = ws + W.a_gi[1];
   ff.u1 = ws + W.a_u1; ff.u2 = ws + W.a_u2; ff.st0 = ws + W.a_st0; ff.st1 = ws + W.a_st1; ff.st2 = ws + W.a_st2;
@@ -586,7 +586,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   MX_LAUNCH(k_pack_critic_in, dim3(launch1d((long long)Mc * ldc)), dim3(256), 0, s, pk); MX_COUNT(); MX_MARK("k_pack_critic_in", s);
   FrontFwdArgs fc;
   memset(&fc, 0, sizeof(fc));
-  fc.X = ws + W.c_x; fc.ldx = ldc; fc.M = Mc; fc.feature_norm = c.no_feature_norm ? 0 : 1;
+  fc.X = ws + W.c_x; fc.ldx = ldc; fc.M = Mc; fc.feature_norm = c.no_feature_norm ? 0 : 1; fc.act_tanh = c.use_tanh;
   fc.theta[0] = h->th_c; fc.theta[1] = h->th_c_tgt; fc.L = LC;
   fc.gi[0] = ws + W.c_gi[0]; fc.gi[1] = ws + W.c_gi[1];
   fc.u1 = ws + W.c_u1; fc.u2 = ws + W.c_u2; fc.st0 = ws + W.c_st0; fc.st1 = ws + W.c_st1; fc.st2 = ws + W.c_st2;
@@ -608,7 +608,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   MX_LAUNCH(k_pack_critic_in, dim3(launch1d((long long)Mc * ldc)), dim3(256), 0, s, pk); MX_COUNT(); MX_MARK("k_pack_critic_in", s);
   FrontFwdArgs ft;
   memset(&ft, 0, sizeof(ft));
-  ft.X = ws + W.t_x; ft.ldx = ldc; ft.M = Mc; ft.feature_norm = c.no_feature_norm ? 0 : 1; ft.theta[0] = h->th_c_tgt; ft.L = LC; ft.gi[0] = ws + W.t_gi;
+  ft.X = ws + W.t_x; ft.ldx = ldc; ft.M = Mc; ft.feature_norm = c.no_feature_norm ? 0 : 1; ft.act_tanh = c.use_tanh; ft.theta[0] = h->th_c_tgt; ft.L = LC; ft.gi[0] = ws + W.t_gi;
   if (mx_launch_front_fwd(ft, 1, s)) return 1;
   GruFwdArgs gt;
   memset(&gt, 0, sizeof(gt));
@@ -642,7 +642,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   int parts[2] = {0, 0};
   FrontBwdArgs fb;
   memset(&fb, 0, sizeof(fb));
-  fb.X = ws + W.c_x; fb.ldx = ldc; fb.M = Mc; fb.T = T; fb.N = 1; fb.T1 = T; fb.feature_norm = c.no_feature_norm ? 0 : 1; fb.theta = h->th_c; fb.L = LC;
+  fb.X = ws + W.c_x; fb.ldx = ldc; fb.M = Mc; fb.T = T; fb.N = 1; fb.T1 = T; fb.feature_norm = c.no_feature_norm ? 0 : 1; fb.act_tanh = c.use_tanh; fb.theta = h->th_c; fb.L = LC;
   fb.u1 = fc.u1; fb.u2 = fc.u2; fb.st0 = fc.st0; fb.st1 = fc.st1; fb.st2 = fc.st2; fb.dgi = gb.dgi; fb.gates = gc.gates; fb.hall = gc.hall[0];
   fb.gpart = ws + W.gpart_c; fb.P = h->Pc;
   fb.da2_out = ws + W.tc_da2; fb.da1_out = ws + W.tc_da1; fb.tc_imgT = ws + W.tc_imgT;      // (option wgrad_tc)
@@ -654,7 +654,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
     // live critic recurrence over the buffer sequence again (its parameters just changed)
     FrontFwdArgs f2;
     memset(&f2, 0, sizeof(f2));
-    f2.X = ws + W.c_x; f2.ldx = ldc; f2.M = Mc; f2.feature_norm = c.no_feature_norm ? 0 : 1; f2.theta[0] = h->th_c; f2.L = LC; f2.gi[0] = ws + W.c_gi[0];
+    f2.X = ws + W.c_x; f2.ldx = ldc; f2.M = Mc; f2.feature_norm = c.no_feature_norm ? 0 : 1; f2.act_tanh = c.use_tanh; f2.theta[0] = h->th_c; f2.L = LC; f2.gi[0] = ws + W.c_gi[0];
     if (mx_launch_front_fwd(f2, 1, s)) return 1;
     GruFwdArgs g2;
     memset(&g2, 0, sizeof(g2));
@@ -672,7 +672,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
     MX_LAUNCH(k_pack_critic_in, dim3(launch1d((long long)Mr * ldc)), dim3(256), 0, s, pk); MX_COUNT(); MX_MARK("k_pack_critic_in", s);
     FrontFwdArgs fr;
     memset(&fr, 0, sizeof(fr));
-    fr.X = ws + W.r_x; fr.ldx = ldc; fr.M = Mr; fr.feature_norm = c.no_feature_norm ? 0 : 1; fr.theta[0] = h->th_c; fr.L = LC; fr.gi[0] = ws + W.r_gi;
+    fr.X = ws + W.r_x; fr.ldx = ldc; fr.M = Mr; fr.feature_norm = c.no_feature_norm ? 0 : 1; fr.act_tanh = c.use_tanh; fr.theta[0] = h->th_c; fr.L = LC; fr.gi[0] = ws + W.r_gi;
     fr.u1 = ws + W.r_u1; fr.u2 = ws + W.r_u2; fr.st0 = ws + W.r_st0; fr.st1 = ws + W.r_st1; fr.st2 = ws + W.r_st2;
     if (mx_launch_front_fwd(fr, 1, s)) return 1;
     GruFwdArgs gr;
@@ -698,7 +698,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
     if (mx_launch_gru_bwd(gbr, s)) return 1;
     FrontBwdArgs fbr;
     memset(&fbr, 0, sizeof(fbr));
-    fbr.X = ws + W.r_x; fbr.ldx = ldc; fbr.M = Mr; fbr.T = 0; fbr.N = 1; fbr.T1 = 1; fbr.h0 = ws + W.r_h0; fbr.feature_norm = c.no_feature_norm ? 0 : 1; fbr.theta = h->th_c; fbr.L = LC;
+    fbr.X = ws + W.r_x; fbr.ldx = ldc; fbr.M = Mr; fbr.T = 0; fbr.N = 1; fbr.T1 = 1; fbr.h0 = ws + W.r_h0; fbr.feature_norm = c.no_feature_norm ? 0 : 1; fbr.act_tanh = c.use_tanh; fbr.theta = h->th_c; fbr.L = LC;
     fbr.u1 = fr.u1; fbr.u2 = fr.u2; fbr.st0 = fr.st0; fbr.st1 = fr.st1; fbr.st2 = fr.st2; fbr.dgi = gbr.dgi; fbr.gates = gr.gates; fbr.hall = gr.hall[0];
     fbr.gpart = ws + W.gpart_c; fbr.P = h->Pc; fbr.dX = ws + W.r_dx; fbr.skip_wgrad = 1;
     int dummy = 0;
@@ -720,7 +720,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
     if (mx_launch_gru_bwd(gba, s)) return 1;
     FrontBwdArgs fba;
     memset(&fba, 0, sizeof(fba));
-    fba.X = b->obs; fba.ldx = b->obs_ld; fba.M = Ma; fba.T = T; fba.N = N; fba.feature_norm = c.no_feature_norm ? 0 : 1; fba.theta = h->th_a; fba.L = LA;
+    fba.X = b->obs; fba.ldx = b->obs_ld; fba.M = Ma; fba.T = T; fba.N = N; fba.feature_norm = c.no_feature_norm ? 0 : 1; fba.act_tanh = c.use_tanh; fba.theta = h->th_a; fba.L = LA;
     fba.u1 = ff.u1; fba.u2 = ff.u2; fba.st0 = ff.st0; fba.st1 = ff.st1; fba.st2 = ff.st2; fba.dgi = gba.dgi; fba.gates = gf.gates; fba.hall = gf.hall[0];
     fba.gpart = ws + W.gpart_a; fba.P = h->Pa;
     fba.da2_out = ws + W.tc_da2; fba.da1_out = ws + W.tc_da1; fba.tc_imgT = ws + W.tc_imgT;

@@ -12,6 +12,7 @@ struct FrontFwdArgs {
   float *u1, *u2;          // live: post-ReLU pre-LN activations [M][H]
   float *st0, *st1, *st2;  // live: (mean, rstd) per row for the three LayerNorms
   const float* tc_img[2];  // optional: pre-split TF32 hi/lo weight images in UMMA layout (mx_launch_tc_prep_weights)
+  int act_tanh;            // 1: tanh instead of ReLU after fc1 / fc2 (--use_ReLU switched off)
 };
 size_t mx_tc_image_floats(int in_dim);
 int mx_launch_tc_prep_weights(const float* const theta[2], const MxNetLayout& L, float* const img[2], int nets, cudaStream_t s);
@@ -169,6 +170,7 @@ struct FrontBwdArgs {
   int wgrad_external;      // set by the launcher, not by callers
   float* tc_imgT;          // scratch for the transposed TF32 weight images of the all-tensor-core backward (option wgrad_tc = 2)
   int tc_imgT_ready;       // 1: the caller already built them for the current parameters (mx_launch_tc_prep_weights_T)
+  int act_tanh;            // 1: tanh instead of ReLU (the saved u1 / u2 are the activations' outputs: tanh' = 1 - u^2)
 };
 int mx_launch_tc_prep_weights_T(const float* theta, const MxNetLayout& L, float* imgT, cudaStream_t s);
 bool mx_tc_prep_T_wanted(int in_dim);

@@ -365,7 +365,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
   }
   FrontFwdArgs ff;
   memset(&ff, 0, sizeof(ff));
-  ff.X = X; ff.ldx = ldx; ff.M = M; ff.feature_norm = c.no_feature_norm ? 0 : 1;
+  ff.X = X; ff.ldx = ldx; ff.M = M; ff.feature_norm = c.no_feature_norm ? 0 : 1; ff.act_tanh = c.use_tanh;
   ff.theta[0] = q->theta; ff.theta[1] = q->theta_tgt; ff.L = q->agent;
   ff.gi[0] = ws + W.gi[0]; ff.gi[1] = ws + W.gi[1];
   ff.u1 = ws + W.u1; ff.u2 = ws + W.u2; ff.st0 = ws + W.st0; ff.st1 = ws + W.st1; ff.st2 = ws + W.st2;
@@ -411,7 +411,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
     if (mx_launch_mlp_dgi(mx.dq_taken, b->act_idx, ld_tn, ws + W.dgi, B, N, s)) return 1;
     FrontBwdArgs fbm;
     memset(&fbm, 0, sizeof(fbm));
-    fbm.X = X; fbm.ldx = ldx; fbm.M = M; fbm.T = T; fbm.N = N; fbm.feature_norm = c.no_feature_norm ? 0 : 1; fbm.no_gru = 1;
+    fbm.X = X; fbm.ldx = ldx; fbm.M = M; fbm.T = T; fbm.N = N; fbm.feature_norm = c.no_feature_norm ? 0 : 1; fbm.act_tanh = c.use_tanh; fbm.no_gru = 1;
     fbm.theta = q->theta; fbm.L = q->agent; fbm.u1 = ff.u1; fbm.u2 = ff.u2; fbm.st0 = ff.st0; fbm.st1 = ff.st1; fbm.st2 = ff.st2;
     fbm.dgi = ws + W.dgi; fbm.gpart = mx.gpart; fbm.P = q->P;
     fbm.da2_out = ws + W.da2; fbm.da1_out = ws + W.da1; fbm.tc_imgT = ws + W.tcimgT; fbm.tc_imgT_ready = q->imgT_fresh; q->imgT_fresh = 0;      // (option wgrad_tc)
@@ -494,7 +494,7 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
 
   FrontBwdArgs fb;
   memset(&fb, 0, sizeof(fb));
-  fb.X = X; fb.ldx = ldx; fb.M = M; fb.T = T; fb.N = N; fb.feature_norm = c.no_feature_norm ? 0 : 1;
+  fb.X = X; fb.ldx = ldx; fb.M = M; fb.T = T; fb.N = N; fb.feature_norm = c.no_feature_norm ? 0 : 1; fb.act_tanh = c.use_tanh;
   fb.theta = q->theta; fb.L = q->agent; fb.u1 = ff.u1; fb.u2 = ff.u2; fb.st0 = ff.st0; fb.st1 = ff.st1; fb.st2 = ff.st2;
   fb.dgi = gb.dgi; fb.gates = gf.gates; fb.hall = gf.hall[0]; fb.gpart = mx.gpart; fb.P = q->P;
   fb.da2_out = ws + W.da2; fb.da1_out = ws + W.da1; fb.tc_imgT = ws + W.tcimgT; fb.tc_imgT_ready = q->imgT_fresh; q->imgT_fresh = 0;      // used when the tensor-core weight-gradient kernel is enabled (option wgrad_tc)

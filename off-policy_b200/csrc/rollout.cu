@@ -30,6 +30,7 @@ struct RollArgs {
   int R;
   int mlp;                 // non-recurrent net: head = first out_dim rows of the W_ih slot applied to the MLPBase output
   int no_feature_norm;     // no input LayerNorm (--use_feature_normalization switched off)
+  int act_tanh;            // tanh instead of ReLU (--use_ReLU switched off)
 };
 
 // LayerNorm of v[0..n) in shared memory, in place (two-pass, biased variance, eps inside the sqrt like ATen); warp 0 only
@@ -71,13 +72,13 @@ __global__ void __launch_bounds__(MX_ROLL_THREADS) k_policy_step(RollArgs a) {
     if (!a.no_feature_norm) roll_layer_norm(xs, I, th + L.fn_g, th + L.fn_b);            // mlp.py:64-65 (block-uniform branch)
     {   // fc1: Linear -> ReLU -> LayerNorm                                               mlp.py:19-20
       const float d = roll_dot4(th + L.w1 + (size_t)u * I, xs, I, q);
-      if (q == 0) v1[u] = fmaxf(d + th[L.b1 + u], 0.f);
+      if (q == 0) { const float z = d + th[L.b1 + u]; v1[u] = a.act_tanh ? tanhf(z) : fmaxf(z, 0.f); }
     }
     __syncthreads();
     roll_layer_norm(v1, MX_H, th + L.ln1_g, th + L.ln1_b);
     {   // fc2[0]                                                                          mlp.py:21-29
       const float d = roll_dot4(th + L.w2 + (size_t)u * MX_H, v1, MX_H, q);
-      if (q == 0) v2[u] = fmaxf(d + th[L.b2 + u], 0.f);
+      if (q == 0) { const float z = d + th[L.b2 + u]; v2[u] = a.act_tanh ? tanhf(z) : fmaxf(z, 0.f); }
     }
     __syncthreads();
     roll_layer_norm(v2, MX_H, th + L.ln2_g, th + L.ln2_b);
@@ -143,7 +144,7 @@ extern "C" int mx_policy_step(const mx_policy_step_args* p, void* stream) {
   a.theta = p->theta;
   mx_net_layout(p->in_dim, p->out_dim, 0, &a.L);
   a.x = p->x; a.x_ld = p->x_ld; a.h_in = p->h_in; a.h_out = p->h_out; a.h_copy = p->h_copy; a.out = p->out;
-  a.avail = p->avail; a.avail_ld = p->avail_ld; a.greedy = p->greedy; a.greedy_q = p->greedy_q; a.R = p->rows; a.mlp = p->mlp; a.no_feature_norm = p->no_feature_norm;
+  a.avail = p->avail; a.avail_ld = p->avail_ld; a.greedy = p->greedy; a.greedy_q = p->greedy_q; a.R = p->rows; a.mlp = p->mlp; a.no_feature_norm = p->no_feature_norm; a.act_tanh = p->use_tanh;
   int grid = p->rows;
   const int cap = mx_num_sms() * 4;
   if (grid > cap) grid = cap;

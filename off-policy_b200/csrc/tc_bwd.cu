@@ -385,7 +385,7 @@ __device__ __forceinline__ void bt_colsum_read(const float* sc0, const float* sc
 }
 // LayerNorm backward + ReLU mask for one row held in registers: dy -> da (in place); the products for the gain / bias gradients go
 // straight into the scratch rows (sc0: dy * xhat, sc1: dy)
-__device__ __forceinline__ void bt_ln_bwd_relu(float (&dy)[64], const float* __restrict__ urow, bool ok, float mean, float rstd, const float* gamma_s,
+__device__ __forceinline__ void bt_ln_bwd_relu(bool act_tanh, float (&dy)[64], const float* __restrict__ urow, bool ok, float mean, float rstd, const float* gamma_s,
                                                float* sc0, float* sc1, int tid) {
   float u[64];
 #pragma unroll
@@ -412,7 +412,7 @@ __device__ __forceinline__ void bt_ln_bwd_relu(float (&dy)[64], const float* __r
   for (int c = 0; c < 64; ++c) {
     const float xh = ok ? (u[c] - mean) * rstd : 0.f;
     const float du = rstd * (dy[c] - s1 - xh * s2);
-    dy[c] = u[c] > 0.f ? du : 0.f;
+    dy[c] = act_tanh ? du * (1.f - u[c] * u[c]) : (u[c] > 0.f ? du : 0.f);
   }
 }
 
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
       const float* st = layer == 0 ? a.st2 : a.st1;
       const float* uu = layer == 0 ? a.u2 : a.u1;
       // (the MMAs that read the A tile have completed: its shared memory is the scratch until the next operand is written)
-      bt_ln_bwd_relu(v, uu + mm * MX_H, ok, ok ? st[2 * mm] : 0.f, ok ? st[2 * mm + 1] : 0.f, par_s + 64 * layer, sc0, sc1, tid);
+      bt_ln_bwd_relu(a.act_tanh != 0, v, uu + mm * MX_H, ok, ok ? st[2 * mm] : 0.f, ok ? st[2 * mm + 1] : 0.f, par_s + 64 * layer, sc0, sc1, tid);
       bt_colsum_read(sc0, sc1, tid, layer == 0 ? &acc2 : &acc1);
       float* da_out = layer == 0 ? a.da2_out : a.da1_out;
       if (ok) {

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
       tc::tmem_ld64(tmem_row, v);
       const float* bs = par_s + layer * 3 * MX_H;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) v[c] = fmaxf(v[c] + bs[c], 0.f);
+      for (int c = 0; c < 64; ++c) { const float z = v[c] + bs[c]; v[c] = a.act_tanh ? tanhf(z) : fmaxf(z, 0.f); }
       const float mean = tc_sum64(v) * (1.f / 64.f);
       const float rstd = rsqrtf(tc_sumsq64(v, mean, 64) * (1.f / 64.f) + MX_LN_EPS);
       float* u_out = layer == 0 ? a.u1 : a.u2;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
       tc::tmem_ld64(tmem_row, v);
       const float* bs = par_s + layer * 3 * MX_H;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) v[c] = fmaxf(v[c] + bs[c], 0.f);
+      for (int c = 0; c < 64; ++c) { const float z = v[c] + bs[c]; v[c] = a.act_tanh ? tanhf(z) : fmaxf(z, 0.f); }
       const float mu = tc_sum64(v) * (1.f / 64.f);
       const float rs = rsqrtf(tc_sumsq64(v, mu, 64) * (1.f / 64.f) + MX_LN_EPS);
       float* u_out = layer == 0 ? a.u1 : a.u2;

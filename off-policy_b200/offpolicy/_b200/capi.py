@@ -45,7 +45,7 @@ class QmixCfg(C.Structure):
                                           "hyper_layers", "episode_len", "max_batch", "vdn", "double_q", "use_huber", "use_per",
                                           "use_avail", "world_size")] +
                 [(n, C.c_float) for n in ("gamma", "huber_delta", "per_nu", "per_eps", "lr", "adam_beta1", "adam_beta2", "adam_eps",
-                                          "max_grad_norm", "tau")] + [("prev_act_inp", C.c_int32), ("mlp", C.c_int32), ("no_feature_norm", C.c_int32)])
+                                          "max_grad_norm", "tau")] + [("prev_act_inp", C.c_int32), ("mlp", C.c_int32), ("no_feature_norm", C.c_int32), ("use_tanh", C.c_int32)])
 
 
 class MaddpgCfg(C.Structure):
@@ -53,7 +53,7 @@ class MaddpgCfg(C.Structure):
                                           "actor_update_interval", "use_huber", "use_per")] +
                 [(n, C.c_float) for n in ("gamma", "huber_delta", "per_nu", "per_eps", "lr", "adam_beta1", "adam_beta2", "adam_eps",
                                           "max_grad_norm", "tau", "weight_decay", "target_noise")] +
-                [("discrete", C.c_int32), ("no_feature_norm", C.c_int32)])
+                [("discrete", C.c_int32), ("no_feature_norm", C.c_int32), ("use_tanh", C.c_int32)])
 
 
 class ParamEntry(C.Structure):
@@ -68,7 +68,7 @@ class Batch(C.Structure):
 
 class PolicyStepArgs(C.Structure):
     _fields_ = ([("theta", C.c_void_p)] + [(n, C.c_int32) for n in ("in_dim", "out_dim", "rows", "x_ld", "avail_ld")] +
-                [(n, C.c_void_p) for n in ("x", "h_in", "h_out", "out", "avail", "greedy", "greedy_q", "h_copy")] + [("mlp", C.c_int32), ("no_feature_norm", C.c_int32)])
+                [(n, C.c_void_p) for n in ("x", "h_in", "h_out", "out", "avail", "greedy", "greedy_q", "h_copy")] + [("mlp", C.c_int32), ("no_feature_norm", C.c_int32), ("use_tanh", C.c_int32)])
 
 
 class MxError(RuntimeError):

@@ -55,7 +55,7 @@ class FlatModule(object):
         return self
 
 
-def reference_style_init(entries, cfg, gain, use_orthogonal=True, hyper_layers=2, seed_modules=True):
+def reference_style_init(entries, cfg, gain, use_orthogonal=True, hyper_layers=2, seed_modules=True, use_relu=True):
     """Initial weights in the construction ORDER of the reference so that, under the same torch.manual_seed, the
     CPU RNG is consumed the same way (mlp.py:14-23, rnn.py:8-17, act.py:10-20, q_mixer.py:33-66):
     nn.Linear/nn.GRU default init first, then orthogonal_/xavier_uniform_ x gain, biases 0, LayerNorm (1, 0).
@@ -63,7 +63,7 @@ def reference_style_init(entries, cfg, gain, use_orthogonal=True, hyper_layers=2
     import torch.nn as nn
     H, I, A = cfg["hidden"], cfg["obs_dim"], cfg["act_dim"]
     init_w = nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_
-    relu_gain = nn.init.calculate_gain("relu")
+    relu_gain = nn.init.calculate_gain("relu" if use_relu else "tanh")      # mlp.py:12: gain of the activation in use
     out = {}
 
     def linear(prefix, i, o, g):

@@ -26,10 +26,11 @@ def _host_ptr(x):
 
 
 class PolicyStepper(object):
-    def __init__(self, in_dim, out_dim, mlp=False, feature_norm=True):
+    def __init__(self, in_dim, out_dim, mlp=False, feature_norm=True, tanh=False):
         self.in_dim, self.out_dim = int(in_dim), int(out_dim)
         self.mlp = bool(mlp)      # non-recurrent net (M_QMixPolicy): no state is carried
         self.feature_norm = bool(feature_norm)      # False: --use_feature_normalization switched off
+        self.tanh = bool(tanh)                      # True: --use_ReLU switched off
         self.dev = capi.device()
         self.rows = 0
         self._last_h = None      # (host array handed out, rows): its device copy is in self.d_h
@@ -80,6 +81,7 @@ class PolicyStepper(object):
         a.x = base + 4 * o_x
         a.mlp = int(self.mlp)
         a.no_feature_norm = 0 if self.feature_norm else 1
+        a.use_tanh = 1 if self.tanh else 0
         a.h_in = None if self.mlp else (self.d_h.data_ptr() if resident else base + 4 * o_h)
         a.h_out = None if self.mlp else self.d_h.data_ptr()
         a.h_copy = None if self.mlp else base + 4 * o_hn

@@ -14,12 +14,12 @@ from offpolicy._b200.host_util import LinearDecay, space_dim, is_discrete, oneho
 from offpolicy.algorithms.qmix.algorithm.QMixPolicy import qmix_cfg_struct, param_entries
 
 
-def mlp_reference_style_init(entries, in_dim, hidden, act_dim, gain, use_orthogonal=True):
+def mlp_reference_style_init(entries, in_dim, hidden, act_dim, gain, use_orthogonal=True, use_relu=True):
     """Initial weights in the reference's construction order (MLPBase: feature LayerNorm, fc1, fc_h, fc2 = clone of fc_h, mlp.py:14-29;
     then ACTLayer, act.py:10-20) so that a seeded run consumes torch's generator identically."""
     import torch.nn as nn
     init_w = nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_
-    relu_gain = nn.init.calculate_gain("relu")
+    relu_gain = nn.init.calculate_gain("relu" if use_relu else "tanh")
     out = {}
 
     def linear(prefix, i, o, g):
@@ -58,7 +58,7 @@ class M_QMixPolicy(object):
         self.multidiscrete = "MultiDiscrete" in self.act_space.__class__.__name__
         if self.multidiscrete:
             raise NotImplementedError("B200 M-QMIX path: MultiDiscrete action spaces are not implemented")
-        for flag, want in (("use_ReLU", True), ("use_conv1d", False)):
+        for flag, want in (("use_conv1d", False),):
             if getattr(self.args, flag, want) != want:
                 raise NotImplementedError("B200 M-QMIX path requires %s=%s" % (flag, want))
         if getattr(self.args, "layer_N", 1) != 1:
@@ -71,7 +71,7 @@ class M_QMixPolicy(object):
         flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.q_network = FlatModule(flat, entries, "agent.")
         self.q_network.load_state_dict(mlp_reference_style_init(entries, self.obs_dim, self.hidden_size, self.act_dim, self.args.gain,
-                                                                self.args.use_orthogonal))
+                                                                self.args.use_orthogonal, use_relu=bool(getattr(self.args, "use_ReLU", True))))
         self._roll = None
         if train:
             self.exploration = LinearDecay(self.args.epsilon_start, self.args.epsilon_finish, self.args.epsilon_anneal_time)
@@ -80,7 +80,8 @@ class M_QMixPolicy(object):
     def _step(self, obs, available_actions=None):
         if self._roll is None:
             from offpolicy._b200.rollout import PolicyStepper
-            self._roll = PolicyStepper(self.obs_dim, self.act_dim, mlp=True, feature_norm=bool(getattr(self.args, "use_feature_normalization", True)))
+            self._roll = PolicyStepper(self.obs_dim, self.act_dim, mlp=True, feature_norm=bool(getattr(self.args, "use_feature_normalization", True)),
+                                       tanh=not getattr(self.args, "use_ReLU", True))
         q, _, greedy, greedy_q = self._roll.step(self.q_network.flat, obs, None, available_actions)
         return q, greedy, greedy_q
 

@@ -27,7 +27,7 @@ def qmix_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, ma
         gamma=args.gamma, huber_delta=args.huber_delta, per_nu=args.per_nu, per_eps=args.per_eps, lr=args.lr,
         adam_beta1=0.9, adam_beta2=0.999, adam_eps=args.opti_eps, max_grad_norm=args.max_grad_norm, tau=args.tau,
         prev_act_inp=0 if mlp else int(bool(getattr(args, "prev_act_inp", False))), mlp=int(bool(mlp)),
-        no_feature_norm=0 if getattr(args, "use_feature_normalization", True) else 1)
+        no_feature_norm=0 if getattr(args, "use_feature_normalization", True) else 1, use_tanh=0 if getattr(args, "use_ReLU", True) else 1)
 
 
 def param_entries(cfg):
@@ -55,7 +55,7 @@ class QMixPolicy(object):
         self.discrete = is_discrete(self.act_space)
         self.multidiscrete = False
         self.prev_act_inp = bool(getattr(self.args, "prev_act_inp", False))
-        for flag, want in (("use_rnn_layer", True), ("use_ReLU", True), ("use_conv1d", False)):
+        for flag, want in (("use_rnn_layer", True), ("use_conv1d", False)):
             if getattr(self.args, flag, want) != want:
                 raise NotImplementedError("B200 QMIX path requires %s=%s" % (flag, want))
         if getattr(self.args, "layer_N", 1) != 1 or getattr(self.args, "recurrent_N", 1) != 1:
@@ -71,7 +71,7 @@ class QMixPolicy(object):
         flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.q_network = FlatModule(flat, entries, "agent.")
         init = reference_style_init(entries, dict(hidden=self.hidden_size, obs_dim=self.q_network_input_dim, act_dim=self.act_dim),
-                                    gain=self.args.gain, use_orthogonal=self.args.use_orthogonal)
+                                    gain=self.args.gain, use_orthogonal=self.args.use_orthogonal, use_relu=bool(getattr(self.args, "use_ReLU", True)))
         self.q_network.load_state_dict({k[len("agent."):]: v for k, v in init.items()})
         self._roll = None
         if train:
@@ -85,7 +85,8 @@ class QMixPolicy(object):
     def _stepper(self):
         if self._roll is None:
             from offpolicy._b200.rollout import PolicyStepper
-            self._roll = PolicyStepper(self.q_network_input_dim, self.act_dim, feature_norm=bool(getattr(self.args, "use_feature_normalization", True)))
+            self._roll = PolicyStepper(self.q_network_input_dim, self.act_dim, feature_norm=bool(getattr(self.args, "use_feature_normalization", True)),
+                                       tanh=not getattr(self.args, "use_ReLU", True))
         return self._roll
 
     def _step(self, obs, rnn_states, available_actions=None, prev_actions=None):

@@ -46,7 +46,8 @@ def maddpg_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, 
                           per_nu=args.per_nu, per_eps=args.per_eps, lr=args.lr, adam_beta1=0.9, adam_beta2=0.999, adam_eps=args.opti_eps,
                           max_grad_norm=args.max_grad_norm, tau=args.tau, weight_decay=float(getattr(args, "weight_decay", 0) or 0),
                           target_noise=float(target_noise or 0.0), discrete=int(bool(discrete)),
-                          no_feature_norm=0 if getattr(args, "use_feature_normalization", True) else 1)
+                          no_feature_norm=0 if getattr(args, "use_feature_normalization", True) else 1,
+                          use_tanh=0 if getattr(args, "use_ReLU", True) else 1)
 
 
 def maddpg_entries(cfg, which):
@@ -60,11 +61,11 @@ def maddpg_entries(cfg, which):
     return [(e.name.decode(), int(e.offset), int(e.rows), int(e.cols)) for e in arr], int(total.value)
 
 
-def _init_net(mod, in_dim, hidden, out_specs, gain, use_orthogonal):
+def _init_net(mod, in_dim, hidden, out_specs, gain, use_orthogonal, use_relu=True):
     """Reference construction order (RNNBase then the head, mlp.py:14-23, rnn.py:8-17, act.py / r_actor_critic.py:90-93)."""
     import torch.nn as nn
     init_w = nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_
-    relu_gain = nn.init.calculate_gain("relu")
+    relu_gain = nn.init.calculate_gain("relu" if use_relu else "tanh")
     sd = {}
 
     def linear(prefix, i, o, g):
@@ -104,7 +105,7 @@ class R_MADDPGPolicy(object):
         self.weight_decay = getattr(self.args, "weight_decay", 0)
         if getattr(self.args, "prev_act_inp", False):
             raise NotImplementedError("B200 R-MADDPG path: --prev_act_inp is not implemented")
-        for flag, want in (("use_ReLU", True), ("use_conv1d", False)):      # fail loudly, never approximate
+        for flag, want in (("use_conv1d", False),):      # fail loudly, never approximate
             if getattr(self.args, flag, want) != want:
                 raise NotImplementedError("B200 R-MADDPG path requires %s=%s" % (flag, want))
         if getattr(self.args, "layer_N", 1) != 1 or getattr(self.args, "hidden_size", 64) != 64:
@@ -134,17 +135,18 @@ class R_MADDPGPolicy(object):
         self.target_actor = FlatModule(self.actor_vecs[1], self._a_entries, "")
         self.critic = FlatModule(self.critic_vecs[0], self._c_entries, "")
         self.target_critic = FlatModule(self.critic_vecs[1], self._c_entries, "")
+        relu = bool(getattr(self.args, "use_ReLU", True))
         _init_net(self.actor, self.obs_dim, self.hidden_size, [("act.action_out", self.act_dim, self.args.gain)], self.args.gain,
-                  self.args.use_orthogonal)
+                  self.args.use_orthogonal, use_relu=relu)
         _init_net(self.critic, self.central_obs_dim + self.central_act_dim, self.hidden_size,
-                  [("q_outs.%d" % k, 1, 1.0) for k in range(2 if td3 else 1)], 1.0, self.args.use_orthogonal)
+                  [("q_outs.%d" % k, 1, 1.0) for k in range(2 if td3 else 1)], 1.0, self.args.use_orthogonal, use_relu=relu)
         # the reference constructs the two target networks like the live ones (rMADDPGPolicy.py:45-46) before overwriting them with
         # the live weights (:49-50): their initialisation consumes torch's generator, so it is replayed here -- a seeded run then
         # draws the same warm-up / exploration actions as the reference
         _init_net(self.target_actor, self.obs_dim, self.hidden_size, [("act.action_out", self.act_dim, self.args.gain)], self.args.gain,
-                  self.args.use_orthogonal)
+                  self.args.use_orthogonal, use_relu=relu)
         _init_net(self.target_critic, self.central_obs_dim + self.central_act_dim, self.hidden_size,
-                  [("q_outs.%d" % k, 1, 1.0) for k in range(2 if td3 else 1)], 1.0, self.args.use_orthogonal)
+                  [("q_outs.%d" % k, 1, 1.0) for k in range(2 if td3 else 1)], 1.0, self.args.use_orthogonal, use_relu=relu)
         self.actor_vecs[1].copy_(self.actor_vecs[0])          # rMADDPGPolicy.py:49-50
         self.critic_vecs[1].copy_(self.critic_vecs[0])
         self._trainer = None
@@ -153,7 +155,8 @@ class R_MADDPGPolicy(object):
     def _stepper(self):
         if getattr(self, "_roll", None) is None:
             from offpolicy._b200.rollout import PolicyStepper
-            self._roll = PolicyStepper(self.obs_dim, self.act_dim, feature_norm=bool(getattr(self.args, "use_feature_normalization", True)))
+            self._roll = PolicyStepper(self.obs_dim, self.act_dim, feature_norm=bool(getattr(self.args, "use_feature_normalization", True)),
+                                       tanh=not getattr(self.args, "use_ReLU", True))
         return self._roll
 
     def get_actions(self, obs, prev_actions, rnn_states, available_actions=None, t_env=None, explore=False, use_target=False, use_gumbel=False):

@@ -39,6 +39,7 @@ class MaddpgConfig:
     hidden: int = 64
     layer_n: int = 1
     feature_norm: bool = True
+    relu: bool = True              # use_ReLU (store_false flag): False = tanh blocks
     gamma: float = 0.99
     lr: float = 5e-4
     opti_eps: float = 1e-5
@@ -88,7 +89,7 @@ class _ActHead(nn.Module):
 class ActorNet(nn.Module):
     def __init__(self, cfg):
         super().__init__()
-        self.rnn = _RNNBase(cfg.obs_dim, cfg.hidden, cfg.layer_n, cfg.feature_norm)
+        self.rnn = _RNNBase(cfg.obs_dim, cfg.hidden, cfg.layer_n, cfg.feature_norm, cfg.relu)
         self.act = _ActHead(cfg.hidden, cfg.act_dim)
         self.hidden = cfg.hidden
 
@@ -103,7 +104,7 @@ class CriticNet(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         k = 2 if cfg.td3 else 1
-        self.rnn = _RNNBase(cfg.state_dim + cfg.n_agents * cfg.act_dim, cfg.hidden, cfg.layer_n, cfg.feature_norm)
+        self.rnn = _RNNBase(cfg.state_dim + cfg.n_agents * cfg.act_dim, cfg.hidden, cfg.layer_n, cfg.feature_norm, cfg.relu)
         self.q_outs = nn.ModuleList([nn.Linear(cfg.hidden, 1) for _ in range(k)])
         self.hidden = cfg.hidden
 

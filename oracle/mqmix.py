@@ -22,11 +22,11 @@ from oracle.qmix import _MLP, _Head, QMixerNet, VDNMixerNet, init_like_reference
 
 
 class _MLPBase(nn.Module):
-    def __init__(self, i, h, layer_n, feature_norm):
+    def __init__(self, i, h, layer_n, feature_norm, relu=True):
         super().__init__()
         if feature_norm:
             self.feature_norm = nn.LayerNorm(i)
-        self.mlp = _MLP(i, h, layer_n)
+        self.mlp = _MLP(i, h, layer_n, relu)
         self._fn = feature_norm
 
     def forward(self, x):
@@ -40,7 +40,7 @@ class MAgentNet(nn.Module):
 
     def __init__(self, cfg):
         super().__init__()
-        self.mlp = _MLPBase(cfg.obs_dim, cfg.hidden, cfg.layer_n, cfg.feature_norm)
+        self.mlp = _MLPBase(cfg.obs_dim, cfg.hidden, cfg.layer_n, cfg.feature_norm, getattr(cfg, "relu", True))
         self.q = _Head(cfg.hidden, cfg.act_dim)
 
     def forward(self, x):

@@ -49,6 +49,7 @@ class QmixConfig:
     per_eps: float = 1e-6
     vdn: bool = False
     feature_norm: bool = True
+    relu: bool = True              # config.py use_ReLU (store_false): False = tanh blocks (mlp.py:12,19-22)
     prev_act_inp: bool = False     # config.py:81: agent-net input = [obs | previous one-hot action] (QMixPolicy.py:29,54-58)
     gain: float = 0.01
 
@@ -60,15 +61,15 @@ def _lin(i, o):
 class _Block(nn.Sequential):
     """Linear -> ReLU -> LayerNorm (mlp.py:19-23)."""
 
-    def __init__(self, i, o):
-        super().__init__(_lin(i, o), nn.ReLU(), nn.LayerNorm(o))
+    def __init__(self, i, o, relu=True):
+        super().__init__(_lin(i, o), nn.ReLU() if relu else nn.Tanh(), nn.LayerNorm(o))
 
 
 class _MLP(nn.Module):
-    def __init__(self, i, h, layer_n):
+    def __init__(self, i, h, layer_n, relu=True):
         super().__init__()
-        self.fc1 = _Block(i, h)
-        self.fc_h = _Block(h, h)                      # registered, never used in forward (mlp.py:21-29)
+        self.fc1 = _Block(i, h, relu)
+        self.fc_h = _Block(h, h, relu)                      # registered, never used in forward (mlp.py:21-29)
         self.fc2 = nn.ModuleList([copy.deepcopy(self.fc_h) for _ in range(layer_n)])
 
     def forward(self, x):
@@ -86,11 +87,11 @@ class _GRUWrap(nn.Module):
 
 
 class _RNNBase(nn.Module):
-    def __init__(self, i, h, layer_n, feature_norm):
+    def __init__(self, i, h, layer_n, feature_norm, relu=True):
         super().__init__()
         if feature_norm:
             self.feature_norm = nn.LayerNorm(i)
-        self.mlp = _MLP(i, h, layer_n)
+        self.mlp = _MLP(i, h, layer_n, relu)
         self.rnn = _GRUWrap(h)
         self._fn = feature_norm
 
@@ -111,7 +112,7 @@ class _Head(nn.Module):
 class AgentNet(nn.Module):
     def __init__(self, cfg, in_dim=None, out_dim=None):
         super().__init__()
-        self.rnn = _RNNBase(in_dim or cfg.obs_dim, cfg.hidden, cfg.layer_n, cfg.feature_norm)
+        self.rnn = _RNNBase(in_dim or cfg.obs_dim, cfg.hidden, cfg.layer_n, cfg.feature_norm, getattr(cfg, "relu", True))
         self.q = _Head(cfg.hidden, out_dim or cfg.act_dim)
         self.hidden = cfg.hidden
 
@@ -313,10 +314,10 @@ def agent_trace(net, x):
         rb = net.rnn
         x0 = rb.feature_norm(x) if rb._fn else x
         fc1 = rb.mlp.fc1
-        u1 = F.relu(fc1[0](x0))
+        u1 = fc1[1](fc1[0](x0))
         x1 = fc1[2](u1)
         blk = rb.mlp.fc2[0]
-        u2 = F.relu(blk[0](x1))
+        u2 = blk[1](blk[0](x1))
         x2 = blk[2](u2)
         g = rb.rnn.rnn
         H = net.hidden

@@ -92,7 +92,7 @@ def gen_qmix(name, cfg, flags=(), B=4, T=8, steps=2, avail_p=0.7, var_len=True, 
         out.update(sd_np("s%d.tgt_mixer." % s, tr.target_mixer))
     out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, cfg.hidden, cfg.mixer_hidden,
                                 cfg.hyper_hidden, cfg.hyper_layers, B, T, steps])
-    out["meta.flags"] = np.array([args.use_double_q, args.use_huber_loss, per, bool(args.prev_act_inp), not args.use_feature_normalization], dtype=np.int64)
+    out["meta.flags"] = np.array([args.use_double_q, args.use_huber_loss, per, bool(args.prev_act_inp), not args.use_feature_normalization, not args.use_ReLU], dtype=np.int64)
     out["meta.hparams"] = np.array([args.gamma, args.lr, args.opti_eps, args.max_grad_norm, args.tau, args.huber_delta,
                                     args.per_nu, args.per_eps], dtype=np.float64)
     path = os.path.join(HERE, name + ".npz")
@@ -170,7 +170,7 @@ def gen_replay(name="replay_small"):
     print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
-if __name__ == "__main__" and "maddpg" not in sys.argv[1:] and "rollout" not in sys.argv[1:] and "prev_act" not in sys.argv[1:] and "mqmix" not in sys.argv[1:] and "mlp_replay" not in sys.argv[1:] and "nofn" not in sys.argv[1:]:
+if __name__ == "__main__" and "maddpg" not in sys.argv[1:] and "rollout" not in sys.argv[1:] and "prev_act" not in sys.argv[1:] and "mqmix" not in sys.argv[1:] and "mlp_replay" not in sys.argv[1:] and "nofn" not in sys.argv[1:] and "tanh" not in sys.argv[1:]:
     torch.set_num_threads(1)
     small = QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48)
     gen_qmix("qmix_small", small)
@@ -269,7 +269,7 @@ def gen_maddpg(name, cfg, flags=(), B=4, T=6, steps=2, per=False, use_avail=Fals
             for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
                 out.update(sd_np("final.%s." % tag, mod))
     out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, cfg.hidden, B, T, steps, int(cfg.td3), int(per),
-                                int(cfg.discrete), int(not args.use_feature_normalization)])
+                                int(cfg.discrete), int(not args.use_feature_normalization), int(not args.use_ReLU)])
     out["meta.hparams"] = np.array([args.gamma, args.lr, args.opti_eps, args.max_grad_norm, args.tau, args.huber_delta, args.per_nu,
                                     args.per_eps, float(args.target_action_noise_std), args.weight_decay], dtype=np.float64)
     path = os.path.join(HERE, name + ".npz")
@@ -416,7 +416,7 @@ def gen_mqmix(name, cfg, flags=(), B=8, steps=2, per=False, avail=True):
         out["roll.q_all"] = pol.get_q_values(torch.from_numpy(r_obs)).numpy().copy()
     out["meta.cfg"] = np.array([cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim, cfg.hidden, cfg.mixer_hidden, cfg.hyper_hidden,
                                 cfg.hyper_layers, B, 1, steps])
-    out["meta.flags"] = np.array([args.use_double_q, args.use_huber_loss, per, False, not args.use_feature_normalization], dtype=np.int64)
+    out["meta.flags"] = np.array([args.use_double_q, args.use_huber_loss, per, False, not args.use_feature_normalization, not args.use_ReLU], dtype=np.int64)
     out["meta.hparams"] = np.array([args.gamma, args.lr, args.opti_eps, args.max_grad_norm, args.tau, args.huber_delta, args.per_nu, args.per_eps],
                                    dtype=np.float64)
     path = os.path.join(HERE, name + ".npz")
@@ -469,6 +469,15 @@ def gen_mlp_replay():
 
 if __name__ == "__main__" and "mlp_replay" in sys.argv[1:]:
     gen_mlp_replay()
+
+
+if __name__ == "__main__" and "tanh" in sys.argv[1:]:
+    # --use_ReLU is a store_false flag (config.py): passing it makes the fc blocks Linear -> Tanh -> LayerNorm (mlp.py:12,19-22)
+    torch.set_num_threads(1)
+    from oracle.maddpg import MaddpgConfig
+    gen_qmix("qmix_small_tanh", QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48, relu=False), flags=["--use_ReLU"], steps=2)
+    gen_mqmix("mqmix_small_tanh", QmixConfig(n_agents=3, obs_dim=18, act_dim=5, state_dim=54, relu=False), flags=["--use_ReLU"], steps=1)
+    gen_maddpg("maddpg_box_tanh", MaddpgConfig(relu=False), flags=["--use_ReLU"], steps=2)
 
 
 if __name__ == "__main__" and "nofn" in sys.argv[1:]:

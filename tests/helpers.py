@@ -20,10 +20,11 @@ def golden_cfg(g):
     dq, hub, per = fl[:3]
     prev = fl[3] if len(fl) > 3 else False
     nofn = fl[4] if len(fl) > 4 else False
+    tanh = fl[5] if len(fl) > 5 else False
     gamma, lr, eps, mgn, tau, hd, nu, peps = [float(v) for v in g["meta.hparams"]]
     cfg = QmixConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, hidden=h, mixer_hidden=me, hyper_hidden=hy,
                      hyper_layers=hl, gamma=gamma, lr=lr, opti_eps=eps, max_grad_norm=mgn, tau=tau, double_q=dq,
-                     huber=hub, huber_delta=hd, use_per=per, per_nu=nu, per_eps=peps, prev_act_inp=prev, feature_norm=not nofn)
+                     huber=hub, huber_delta=hd, use_per=per, per_nu=nu, per_eps=peps, prev_act_inp=prev, feature_norm=not nofn, relu=not tanh)
     return cfg, B, T, steps
 
 

@@ -23,7 +23,7 @@ class Discrete(object):
 
 def make_args(cfg, B):
     return types.SimpleNamespace(
-        hidden_size=cfg.hidden, layer_N=1, use_ReLU=True, use_feature_normalization=bool(cfg.feature_norm), use_orthogonal=True, gain=cfg.gain,
+        hidden_size=cfg.hidden, layer_N=1, use_ReLU=bool(cfg.relu), use_feature_normalization=bool(cfg.feature_norm), use_orthogonal=True, gain=cfg.gain,
         use_conv1d=False, stacked_frames=1, use_rnn_layer=True, recurrent_N=1, prev_act_inp=False, gamma=cfg.gamma, use_per=cfg.use_per,
         per_nu=cfg.per_nu, per_eps=cfg.per_eps, use_huber_loss=cfg.huber, huber_delta=cfg.huber_delta, max_grad_norm=cfg.max_grad_norm,
         lr=cfg.lr, opti_eps=cfg.opti_eps, weight_decay=cfg.weight_decay, tau=cfg.tau, use_popart=False, use_value_active_masks=False,

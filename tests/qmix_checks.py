@@ -17,7 +17,7 @@ from replay_checks import Discrete
 
 def make_args(cfg, B, **over):
     a = types.SimpleNamespace(
-        hidden_size=cfg.hidden, layer_N=1, use_ReLU=True, use_feature_normalization=bool(cfg.feature_norm), use_orthogonal=True, gain=cfg.gain,
+        hidden_size=cfg.hidden, layer_N=1, use_ReLU=bool(getattr(cfg, "relu", True)), use_feature_normalization=bool(cfg.feature_norm), use_orthogonal=True, gain=cfg.gain,
         use_conv1d=False, stacked_frames=1, use_rnn_layer=True, recurrent_N=1, prev_act_inp=bool(getattr(cfg, "prev_act_inp", False)), use_double_q=cfg.double_q,
         hypernet_layers=cfg.hyper_layers, mixer_hidden_dim=cfg.mixer_hidden, hypernet_hidden_dim=cfg.hyper_hidden, gamma=cfg.gamma,
         use_per=cfg.use_per, per_nu=cfg.per_nu, per_eps=cfg.per_eps, per_alpha=0.6, use_huber_loss=cfg.huber,

@@ -76,7 +76,7 @@ def test_trainer_rejects_what_it_does_not_implement(emu_engine):
     args = qc.make_args(cfg, 4)
     info = dict(obs_space=[cfg.obs_dim], share_obs_space=[cfg.state_dim], act_space=rc.Discrete(cfg.act_dim), cent_obs_dim=cfg.state_dim,
                 cent_act_dim=cfg.act_dim * cfg.n_agents)
-    for flag, val in (("layer_N", 2), ("use_rnn_layer", False), ("use_conv1d", True), ("use_ReLU", False)):
+    for flag, val in (("layer_N", 2), ("use_rnn_layer", False), ("use_conv1d", True)):
         a2 = types.SimpleNamespace(**vars(args))
         setattr(a2, flag, val)
         with pytest.raises(NotImplementedError):
@@ -88,7 +88,7 @@ def test_trainer_rejects_what_it_does_not_implement(emu_engine):
     margs = mdc.make_args(MaddpgConfig(n_agents=2, obs_dim=5, act_dim=2, state_dim=6), 4)
     minfo = dict(obs_space=[5], share_obs_space=[6], act_space=mdc.Box(2), cent_obs_dim=6, cent_act_dim=4)
     R_MADDPGPolicy({"args": margs, "device": emu_engine.device()}, minfo)
-    for flag, val in (("use_ReLU", False), ("layer_N", 2), ("hidden_size", 128), ("prev_act_inp", True)):
+    for flag, val in (("layer_N", 2), ("hidden_size", 128), ("prev_act_inp", True)):
         a2 = types.SimpleNamespace(**vars(margs))
         setattr(a2, flag, val)
         with pytest.raises(NotImplementedError):

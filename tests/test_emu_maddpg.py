@@ -4,12 +4,12 @@ import pytest
 import maddpg_checks as mc
 
 
-@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_box_per", "maddpg_disc", "matd3_disc", "matd3_disc_avail", "matd3_disc_nofn"])
+@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_box_per", "maddpg_disc", "matd3_disc", "matd3_disc_avail", "matd3_disc_nofn", "maddpg_box_tanh"])
 def test_step_matches_reference_golden(emu_engine, name):
     mc.check_golden(name)
 
 
-@pytest.mark.parametrize("name", ["maddpg_box", "maddpg_disc", "matd3_disc", "matd3_disc_nofn"])
+@pytest.mark.parametrize("name", ["maddpg_box", "maddpg_disc", "matd3_disc", "matd3_disc_nofn", "maddpg_box_tanh"])
 def test_rollout_actions_match_reference(emu_engine, name):
     mc.check_get_actions(name)
 

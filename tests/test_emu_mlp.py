@@ -5,7 +5,7 @@ import mqmix_checks as mc
 
 
 @pytest.mark.parametrize("debug", [True, False])
-@pytest.mark.parametrize("name", ["mqmix_small", "mqmix_small_per_huber_nodq", "mqmix_small_noavail", "mqmix_small_nofn"])
+@pytest.mark.parametrize("name", ["mqmix_small", "mqmix_small_per_huber_nodq", "mqmix_small_noavail", "mqmix_small_nofn", "mqmix_small_tanh"])
 def test_mqmix_matches_reference_golden(emu_engine, name, debug):
     mc.check_golden(name, debug)
 

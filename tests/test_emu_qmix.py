@@ -112,3 +112,17 @@ def test_feature_normalization_off_matches_reference_golden(emu_engine, opts):
     finally:
         lib.mx_set_option(b"front_tc", 1)
         lib.mx_set_option(b"wgrad_tc", 0)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(front_tc=0), dict(wgrad_tc=2)], ids=["default", "ffma_front", "tc_backward"])
+def test_tanh_networks_match_reference_golden(emu_engine, opts):
+    """--use_ReLU (a store_false flag): Linear -> Tanh -> LayerNorm blocks (mlp.py:12,19-22); the backward uses tanh' = 1 - u^2 on the saved
+    activation outputs."""
+    lib = emu_engine.lib()
+    for k, v in opts.items():
+        lib.mx_set_option(k.encode(), v)
+    try:
+        qc.check_step_against(None, "qmix_small_tanh", intermediates=True, debug="wgrad_tc" not in opts)
+    finally:
+        lib.mx_set_option(b"front_tc", 1)
+        lib.mx_set_option(b"wgrad_tc", 0)

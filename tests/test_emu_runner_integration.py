@@ -47,6 +47,9 @@ RUNS = {
     # --use_feature_normalization is a store_false flag: the networks lose their input LayerNorm (rollout kernel + learner)
     "qmix_no_feature_norm": ("qmix", 100, ["--use_feature_normalization"], True),
     "mlp_mqmix_no_feature_norm": ("mqmix", 100, ["--runner", "mlp", "--use_feature_normalization"], True),
+    # --use_ReLU is a store_false flag too: tanh networks (different init gain, mlp.py:12), rollout kernel + learner
+    "qmix_tanh": ("qmix", 100, ["--use_ReLU"], True),
+    "rmaddpg_tanh": ("rmaddpg", 100, ["--actor_train_interval_step", "1", "--use_ReLU"], True),
     "rmatd3_no_feature_norm": ("rmatd3", 100, ["--actor_train_interval_step", "1", "--use_feature_normalization"], True),
     "mlp_maddpg": ("maddpg", 100, ["--runner", "mlp"], True),
     "mlp_matd3": ("matd3", 100, ["--runner", "mlp"], True),

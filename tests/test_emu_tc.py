@@ -165,7 +165,7 @@ def test_config2_full_size_all_tensor_core_kernels_vs_oracle(emu_engine):
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_disc", "matd3_disc_avail", "maddpg_box_per", "matd3_disc_nofn"])
+@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_disc", "matd3_disc_avail", "maddpg_box_per", "matd3_disc_nofn", "maddpg_box_tanh"])
 def test_maddpg_updates_through_the_tensor_core_backward(emu_engine, name, mode):
     """R-MADDPG / R-MATD3: the critic's (input 60 / 69 wide) and the actor's (18 wide) weight-gradient passes on k_wgrad_tc /
     k_front_bwd_tc; the frozen-critic pass that only needs the action gradient stays on k_front_bwd."""

@@ -12,10 +12,11 @@ def maddpg_from_golden(g):
     n, o, a, s, h, B, T, steps, td3, per = meta[:10]
     disc = bool(meta[10]) if len(meta) > 10 else False
     nofn = bool(meta[11]) if len(meta) > 11 else False
+    tanh = bool(meta[12]) if len(meta) > 12 else False
     gamma, lr, eps, mgn, tau, hd, nu, peps, tn, wd = [float(v) for v in g["meta.hparams"]]
     cfg = MaddpgConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, hidden=h, gamma=gamma, lr=lr, opti_eps=eps, max_grad_norm=mgn,
                        tau=tau, huber_delta=hd, per_nu=nu, per_eps=peps, td3=bool(td3), target_noise=tn, weight_decay=wd,
-                       use_per=bool(per), actor_update_interval=2 if td3 else 1, discrete=disc, feature_norm=not nofn)
+                       use_per=bool(per), actor_update_interval=2 if td3 else 1, discrete=disc, feature_norm=not nofn, relu=not tanh)
     L = MaddpgLearner(cfg)
     for tag, mod in (("actor", L.actor), ("critic", L.critic), ("tgt_actor", L.tgt_actor), ("tgt_critic", L.tgt_critic)):
         mod.load_state_dict(sub(g, "init.%s." % tag))
@@ -32,7 +33,7 @@ def actor_noise(g, s):
     return g.get("s%d.in.actor_noise" % s)
 
 
-@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_box_per", "maddpg_disc", "matd3_disc", "matd3_disc_avail", "matd3_disc_nofn"])
+@pytest.mark.parametrize("name", ["maddpg_box", "matd3_box", "maddpg_box_per", "maddpg_disc", "matd3_disc", "matd3_disc_avail", "matd3_disc_nofn", "maddpg_box_tanh"])
 def test_oracle_reproduces_reference_maddpg(name):
     torch.set_num_threads(1)
     g = load_golden(name)

@@ -6,7 +6,7 @@ import torch
 
 from helpers import load_golden, golden_cfg, sub, rel_err
 
-CASES = ["mqmix_small", "mqmix_small_per_huber_nodq", "mqmix_small_noavail", "mqmix_small_nofn"]
+CASES = ["mqmix_small", "mqmix_small_per_huber_nodq", "mqmix_small_noavail", "mqmix_small_nofn", "mqmix_small_tanh"]
 TFIELDS = ["obs", "share", "acts", "rew", "nobs", "nshare", "dones", "dones_env", "valid", "avail", "navail"]
 
 

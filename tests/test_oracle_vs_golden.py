@@ -9,7 +9,7 @@ import torch
 
 from helpers import load_golden, oracle_from_golden, golden_batch, rel_err
 
-CASES = ["qmix_small", "qmix_small_huber_nodq", "qmix_small_per", "qmix_small_hyper1", "qmix_5ag", "qmix_small_prev_act", "qmix_small_nofn"]
+CASES = ["qmix_small", "qmix_small_huber_nodq", "qmix_small_per", "qmix_small_hyper1", "qmix_5ag", "qmix_small_prev_act", "qmix_small_nofn", "qmix_small_tanh"]
 
 
 @pytest.mark.parametrize("name", CASES)
