@@ -58,6 +58,32 @@ def test_c_host_example_runs(gpu_engine, tmp_path):
     assert len(lines) == 4 and r.stdout.strip().splitlines()[-1].startswith("ok"), r.stdout
 
 
+@pytest.mark.parametrize("front_tc", [1, 0])
+@pytest.mark.parametrize("name", ["qmix_small_nofn", "qmix_small_tanh"])
+def test_network_structure_flags_match_reference_golden(gpu_engine, name, front_tc):
+    """--use_feature_normalization / --use_ReLU switched off (store_false flags): no input LayerNorm, tanh blocks -- tcgen05 and FFMA front."""
+    lib = gpu_engine.lib()
+    lib.mx_set_option(b"front_tc", front_tc)
+    try:
+        qc.check_step_against(None, name, intermediates=True, debug=True)
+        qc.check_step_against(None, name, intermediates=False, debug=False)
+    finally:
+        lib.mx_set_option(b"front_tc", 1)
+
+
+@pytest.mark.parametrize("name", ["mqmix_small_nofn", "mqmix_small_tanh"])
+def test_network_structure_flags_mlp(gpu_engine, name):
+    import mqmix_checks as mc
+    mc.check_golden(name, debug=False)          # includes the rollout surface (k_policy_step with the same flags)
+
+
+@pytest.mark.parametrize("name", ["matd3_disc_nofn", "maddpg_box_tanh"])
+def test_network_structure_flags_maddpg(gpu_engine, name):
+    import maddpg_checks as mdc
+    mdc.check_golden(name)
+    mdc.check_get_actions(name)
+
+
 # ---- option-gated tensor-core kernels written without a GPU (off by default): last, so that a failure here hides nothing else ----
 
 @pytest.mark.parametrize("obs_dim,n_agents,B,T", [(80, 8, 8, 20), (128, 3, 16, 12), (72, 5, 32, 10)])
