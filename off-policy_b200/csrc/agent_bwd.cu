@@ -95,79 +95,78 @@ __global__ void __launch_bounds__(256) k_qhead_bwd(QHeadBwdArgs a) {
 // =====================================================================================================
 // GRU backward through time
 // =====================================================================================================
-#define BWD_PF 4
-#define BWD_RING (BWD_PF + 1)
 #define BWD_THREADS 256
 
 template <int RPC>
 __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
-  // dh_{t-1}[k] = z*dh + sum_{j<192} W_hh[j][k] dgh[j].  Thread = 8*kp + s owns the column pair k = 2kp, 2kp+1 restricted
-  // to the interleaved j-slice {32m + 4s + c : m < 6, c < 4} (2 x 24 weights in registers): 6 conflict-free LDS.128 per
-  // step (24 KB of shared->register traffic per row-step), two 24-FFMA chains, then an 8-lane xor-shuffle reduction.
-  // Lanes s = 0,1 of each octet do the gate derivatives of unit k = 2kp + s and publish d(gh) into the OTHER buffer ->
-  // ONE barrier per step.  Operands of step t (r, z, n, hn, h_{t-1}, dL/dh_t) are streamed BWD_PF steps ahead by cp.async.
-  __shared__ __align__(16) float ops_s[BWD_RING][RPC][6][MX_H];
+  // dh_{t-1}[k] = z*dh + sum_{j<192} W_hh[j][k] dgh[j].  Thread = 4*k + s owns column k restricted to the interleaved j-slice
+  // {16m + 4s + c : m < 12, c < 4} (48 weights in registers, packed in pairs along j): 12 LDS.128 per step (the quad's four slices
+  // are 64 contiguous bytes -> one wavefront per warp instruction), 24 packed FFMA2 in three 8-deep chains, then a two-level
+  // xor-shuffle.  All four lanes of a quad carry dh[k] and do the (cheap) gate derivatives of unit k redundantly, so no lane
+  // diverges; lane s publishes ONE of d(gh)_r / d(gh)_z / d(gh)_n into the buffer of this step's parity -> ONE barrier per step.
+  // Operands of step t (r, z, n, hn, h_{t-1}, dL/dh_t) are streamed PF steps ahead by cp.async into a power-of-two ring.
+  constexpr int RING = RPC <= 2 ? 8 : 4;
+  constexpr int PF = RING - 2;
+  __shared__ __align__(16) float ops_s[RING][RPC][6][MX_H];
   __shared__ __align__(16) float dgh_s[2][RPC][MX_G];
   const int tid = threadIdx.x;
-  const int kp = tid >> 3, s = tid & 7;
+  const int k = tid >> 2, s = tid & 3;
   const int row0 = blockIdx.x * RPC;
-  float w0[24], w1[24];
+  float2 w[24];
 #pragma unroll
-  for (int m = 0; m < 6; ++m)
+  for (int m = 0; m < 12; ++m)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int j = 32 * m + 4 * s + c;
-      w0[4 * m + c] = a.theta[a.whh + j * MX_H + 2 * kp];
-      w1[4 * m + c] = a.theta[a.whh + j * MX_H + 2 * kp + 1];
+    for (int c = 0; c < 2; ++c) {
+      const int j = 16 * m + 4 * s + 2 * c;
+      w[2 * m + c] = make_float2(a.theta[a.whh + j * MX_H + k], a.theta[a.whh + (j + 1) * MX_H + k]);
     }
   const int T1 = a.T1 > 0 ? a.T1 : a.T + 1, N = a.N;
-  const int ku = 2 * kp + (s & 1);          // unit whose gate derivatives this lane computes (lanes s = 0, 1)
   MX_PDL_WAIT();        // W_hh columns above are parameter data; the operand streams below are the predecessor's outputs
 
-  // prefetch assignment: RPC*96 16-byte pieces per step, up to two per thread
+  // prefetch assignment: RPC*96 16-byte pieces per step, up to two per thread; sources walk backwards in time
   constexpr int NPIECE = (RPC * 96 + BWD_THREADS - 1) / BWD_THREADS;
-  const float* pf_src[NPIECE];
+  const float* pf_src[NPIECE];      // source of the NEXT step to prefetch (h_{t-1} pieces: already one step earlier)
   size_t pf_stride[NPIECE];
-  int pf_dst[NPIECE];       // float offset inside one ring slot, -1: no piece
+  int pf_dst[NPIECE];               // float offset inside one ring slot, -1: no piece / row past R (slot stays zero)
   bool pf_hprev[NPIECE];
   const float* pf_h0[NPIECE];
+  const int t_first = a.T - 1;
 #pragma unroll
   for (int u = 0; u < NPIECE; ++u) {
     const int c = tid + u * BWD_THREADS;
-    pf_dst[u] = -1; pf_src[u] = nullptr; pf_stride[u] = 0; pf_hprev[u] = false; pf_h0[u] = nullptr;
+    pf_dst[u] = -1; pf_src[u] = a.hall; pf_stride[u] = 0; pf_hprev[u] = false; pf_h0[u] = nullptr;
     if (c < RPC * 96) {
       const int r = c / 96, rem = c % 96, op = rem / 16, q4 = rem % 16;
       const int row = row0 + r;
-      pf_dst[u] = (r * 6 + op) * MX_H + 4 * q4;
       if (row < a.R) {
+        pf_dst[u] = (r * 6 + op) * MX_H + 4 * q4;
         const size_t m0 = ((size_t)(row / N) * T1) * N + (row % N);
-        if (op < 3) { pf_src[u] = a.gates + m0 * MX_G + op * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_G; }
-        else if (op == 3) { pf_src[u] = a.hn + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; }
-        else if (op == 4) { pf_src[u] = a.hall + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; pf_hprev[u] = true;
+        const float* base;
+        if (op < 3) { base = a.gates + m0 * MX_G + op * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_G; }
+        else if (op == 3) { base = a.hn + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; }
+        else if (op == 4) { base = a.hall + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; pf_hprev[u] = true;
                             if (a.h0) pf_h0[u] = a.h0 + (size_t)row * MX_H + 4 * q4; }
-        else { pf_src[u] = a.dh_out + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; }
+        else { base = a.dh_out + m0 * MX_H + 4 * q4; pf_stride[u] = (size_t)N * MX_H; }
+        pf_src[u] = base + (ptrdiff_t)(pf_hprev[u] ? t_first - 1 : t_first) * (ptrdiff_t)pf_stride[u];
       }
     }
   }
-  auto prefetch = [&](int t) {
+  auto prefetch = [&](int t) {        // called with t = T-1, T-2, ... in order
     if (t >= 0) {
 #pragma unroll
       for (int u = 0; u < NPIECE; ++u) {
         if (pf_dst[u] >= 0) {
-          float* dst = &ops_s[t % BWD_RING][0][0][0] + pf_dst[u];
-          const int ts = pf_hprev[u] ? t - 1 : t;            // h_{t-1} lives one step earlier; h_{-1} = h0 (or 0)
-          if (pf_src[u] && ts >= 0) mx_cp16(dst, pf_src[u] + (size_t)ts * pf_stride[u]);
-          else if (pf_h0[u]) mx_cp16(dst, pf_h0[u]);
-          else mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+          float* dst = &ops_s[t & (RING - 1)][0][0][0] + pf_dst[u];
+          const bool first = pf_hprev[u] && t == 0;             // h_{-1} = h0, or zeros (zero-fill form of the copy: no branch)
+          mx_cp16z(dst, first ? (pf_h0[u] ? pf_h0[u] : a.hall) : pf_src[u], (first && !pf_h0[u]) ? 0 : 16);
+          pf_src[u] -= pf_stride[u];
         }
       }
     }
     mx_cp_commit();
   };
 
-  float carry[RPC];
-#pragma unroll
-  for (int r = 0; r < RPC; ++r) carry[r] = 0.f;
+  for (int idx = tid; idx < RING * RPC * 6 * MX_H; idx += BWD_THREADS) (&ops_s[0][0][0][0])[idx] = 0.f;     // rows past R stay zero
   // zero the rows of dgi that receive no gradient (t >= TB; for QMIX: the bootstrap step t == T)
   for (int tz = a.T; tz < T1; ++tz)
     for (int idx = tid; idx < RPC * MX_G; idx += BWD_THREADS) {
@@ -178,61 +177,71 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
         a.dgi[mm * MX_G + c] = 0.f;
       }
     }
-  size_t mrow[RPC];
-  bool valid[RPC];
+  // lane s of a quad writes d(gi)_s of unit k (s = 0, 1, 2: r, z, n) and publishes d(gh)_s (lane 3 repeats lane 2's shared store)
+  float* dgp[RPC];
+  bool dg_on[RPC];
+  float carry[RPC];
+  const size_t dg_stride = (size_t)N * MX_G;
+  const int sq = s < 3 ? s : 2;
 #pragma unroll
   for (int r = 0; r < RPC; ++r) {
     const int row = row0 + r;
-    valid[r] = row < a.R;
-    mrow[r] = valid[r] ? ((size_t)(row / N) * T1) * N + (row % N) : 0;
+    const bool valid = row < a.R;
+    const size_t m0 = valid ? ((size_t)(row / N) * T1) * N + (row % N) : 0;
+    dgp[r] = a.dgi + (m0 + (size_t)t_first * N) * MX_G + sq * MX_H + k;
+    dg_on[r] = valid && s < 3;
+    carry[r] = 0.f;
   }
+  __syncthreads();          // the zero fill precedes the first asynchronous copies into the ring
 #pragma unroll
-  for (int d = 1; d <= BWD_PF; ++d) prefetch(a.T - d);
-  mx_cp_wait<BWD_PF - 1>();
+  for (int d = 0; d < PF; ++d) prefetch(t_first - d);
+  mx_cp_wait<PF - 1>();
   __syncthreads();
-  for (int t = a.T - 1; t >= 0; --t) {
-    const int cur = t & 1;
-    prefetch(t - BWD_PF);              // slot (t-BWD_PF) % RING == (t+1) % RING: last read one full step (one barrier) ago
-    if (s < 2) {
+
+  auto step = [&](const int t, const int cur) {
+    prefetch(t - PF);                  // slot (t-PF) & (RING-1) == (t+2) & (RING-1): last read two barriers ago
+    const float* os = &ops_s[t & (RING - 1)][0][0][0];
+    float cz[RPC];
 #pragma unroll
-      for (int r = 0; r < RPC; ++r) {
-        const float* o = &ops_s[t % BWD_RING][r][0][0];
-        const float rg = o[ku], zg = o[MX_H + ku], ng = o[2 * MX_H + ku], hn = o[3 * MX_H + ku], hp = o[4 * MX_H + ku];
-        const float dh = o[5 * MX_H + ku] + carry[r];
-        const float d_n = dh * (1.f - zg) * (1.f - ng * ng);     // d pre-activation of n
-        const float d_z = dh * (hp - ng) * zg * (1.f - zg);
-        const float d_r = d_n * hn * rg * (1.f - rg);
-        dgh_s[cur][r][ku] = d_r; dgh_s[cur][r][MX_H + ku] = d_z; dgh_s[cur][r][2 * MX_H + ku] = d_n * rg;   // reaches W_hn h + b_hn
-        carry[r] = dh * zg;
-        if (valid[r]) {
-          const size_t mm = mrow[r] + (size_t)t * N;
-          a.dgi[mm * MX_G + ku] = d_r;
-          a.dgi[mm * MX_G + MX_H + ku] = d_z;
-          a.dgi[mm * MX_G + 2 * MX_H + ku] = d_n;
-        }
-      }
+    for (int r = 0; r < RPC; ++r) {
+      const float* o = os + r * 6 * MX_H;
+      const float rg = o[k], zg = o[MX_H + k], ng = o[2 * MX_H + k], hn = o[3 * MX_H + k], hp = o[4 * MX_H + k];
+      const float dh = o[5 * MX_H + k] + carry[r];
+      const float d_n = dh * (1.f - zg) * (1.f - ng * ng);     // d pre-activation of n
+      const float d_z = dh * (hp - ng) * zg * (1.f - zg);
+      const float d_r = d_n * hn * rg * (1.f - rg);
+      const float vg = s == 0 ? d_r : (s == 1 ? d_z : d_n);
+      const float vs = s == 0 ? d_r : (s == 1 ? d_z : d_n * rg);                  // the n row reaches W_hn h + b_hn through r
+      dgh_s[cur][r][sq * MX_H + k] = vs;
+      if (dg_on[r]) *dgp[r] = vg;
+      dgp[r] -= dg_stride;
+      cz[r] = dh * zg;
     }
-    mx_cp_wait<BWD_PF - 1>();   // operands of step t-1 have landed (the newer groups may still be in flight)
+    mx_cp_wait<PF - 1>();       // operands of step t-1 have landed (the newer groups may still be in flight)
     __syncthreads();            // publishes dgh_s[cur] and the ring slot of step t-1
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
-      float4 dv[6];
+      float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0;
 #pragma unroll
-      for (int m = 0; m < 6; ++m) dv[m] = mx_ld4(&dgh_s[cur][r][32 * m + 4 * s]);
-      float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-      for (int m = 0; m < 6; ++m) {
-        p0 = fmaf(w0[4 * m], dv[m].x, p0); p1 = fmaf(w1[4 * m], dv[m].x, p1);
-        p0 = fmaf(w0[4 * m + 1], dv[m].y, p0); p1 = fmaf(w1[4 * m + 1], dv[m].y, p1);
-        p0 = fmaf(w0[4 * m + 2], dv[m].z, p0); p1 = fmaf(w1[4 * m + 2], dv[m].z, p1);
-        p0 = fmaf(w0[4 * m + 3], dv[m].w, p0); p1 = fmaf(w1[4 * m + 3], dv[m].w, p1);
+      for (int m = 0; m < 12; m += 3) {
+        const float4 d0 = mx_ld4(&dgh_s[cur][r][16 * m + 4 * s]);
+        const float4 d1 = mx_ld4(&dgh_s[cur][r][16 * (m + 1) + 4 * s]);
+        const float4 d2 = mx_ld4(&dgh_s[cur][r][16 * (m + 2) + 4 * s]);
+        p0 = mx_ffma2(w[2 * m], make_float2(d0.x, d0.y), p0); p0 = mx_ffma2(w[2 * m + 1], make_float2(d0.z, d0.w), p0);
+        p1 = mx_ffma2(w[2 * m + 2], make_float2(d1.x, d1.y), p1); p1 = mx_ffma2(w[2 * m + 3], make_float2(d1.z, d1.w), p1);
+        p2 = mx_ffma2(w[2 * m + 4], make_float2(d2.x, d2.y), p2); p2 = mx_ffma2(w[2 * m + 5], make_float2(d2.z, d2.w), p2);
       }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
-      carry[r] += (s & 1) ? p1 : p0;    // dh_{t-1}[ku] = z*dh + W_hh^T dgh   (meaningful on lanes s = 0, 1)
+      p0 = mx_fadd2(mx_fadd2(p0, p1), p2);
+      float p = p0.x + p0.y;
+      p += __shfl_xor_sync(0xffffffffu, p, 1);
+      p += __shfl_xor_sync(0xffffffffu, p, 2);
+      carry[r] = cz[r] + p;     // dh_{t-1}[k] = z*dh + W_hh^T dgh
     }
     // the next step writes dgh_s[cur ^ 1]; readers of dgh_s[cur] are separated from its next writer by the next barrier
-  }
+  };
+  int t = t_first;
+  for (; t >= 1; t -= 2) { step(t, 0); step(t - 1, 1); }
+  if (t == 0) step(0, 0);
   mx_cp_wait<0>();
 }
 

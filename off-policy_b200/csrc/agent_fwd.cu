@@ -155,18 +155,20 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_fwd(FrontFwdArgs a) {
 // =====================================================================================================
 // GRU recurrence
 // =====================================================================================================
-#define GRU_PF 4                 // gi rows are prefetched this many steps ahead (L2 latency ~ 2-3 step times)
-#define GRU_RING (GRU_PF + 1)
+#define GRU_PF 5                 // gi rows are prefetched this many steps ahead (L2 latency ~ 2-3 step times)
+#define GRU_RING 8               // power of two: slot = t & 7;  GRU_PF + 2 <= GRU_RING (a slot is rewritten two barriers after its last read)
 #define GRU_THREADS 256
 
 template <int RPC>
 __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
   // K-split quad layout: thread = 4*i + q owns, for unit i, the r/z/n rows of W_hh restricted to the interleaved
-  // k-slice {16m + 4q + c : m,c < 4} (3 x 16 weights in registers).  Per step a thread reads only ITS 16 h values
-  // (4 conflict-free LDS.128 -> 16 KB of shared->register traffic per row-step instead of 64 KB), runs three
-  // 16-FFMA chains, and the quad completes the dot products with xor-shuffles.  Every lane of the quad then holds the
-  // full pre-activations, so the gates need no shared-memory exchange; h is double-buffered -> ONE barrier per step.
-  // gi_t is streamed GRU_PF steps ahead with cp.async into a shared-memory ring.
+  // k-slice {16m + 4q + c : m,c < 4} (3 x 16 weights in registers, packed in pairs).  Per step a thread reads only ITS 16 h values
+  // (4 LDS.128, the quad's four slices are 64 contiguous bytes -> one wavefront per warp instruction), runs 24 packed FFMA2
+  // (two 4-deep chains per gate), and the quad completes the dot products with two xor-shuffles.  Every lane of the quad then
+  // holds the full pre-activations, so the gates need no shared-memory exchange; h is double-buffered -> ONE barrier per step.
+  // gi_t is streamed GRU_PF steps ahead with cp.async into a shared-memory ring.  The per-step instruction stream is what bounds
+  // this kernel (a dependent chain, two warps per scheduler): stores are lane-uniform (lane q of a quad writes ONE of h / r / z / n
+  // through a per-lane pointer, no divergent branches), the step loop is unrolled by two so the h buffers are compile-time.
   __shared__ __align__(16) float h_s[2][RPC][MX_H];
   __shared__ __align__(16) float gi_s[GRU_RING][RPC][MX_G];
   const int net = blockIdx.y;
@@ -175,15 +177,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
   const int i = tid >> 2, q = tid & 3;
   const int row0 = blockIdx.x * RPC;
   const bool live = (net == 0) && a.gates != nullptr;     // only the live net keeps gate activations for the backward pass
-  float wr[16], wz[16], wn[16];
+  float2 wr[8], wz[8], wn[8];
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int k = 16 * m + 4 * q + c;
-      wr[4 * m + c] = th[a.whh + i * MX_H + k];
-      wz[4 * m + c] = th[a.whh + (MX_H + i) * MX_H + k];
-      wn[4 * m + c] = th[a.whh + (2 * MX_H + i) * MX_H + k];
+    for (int c = 0; c < 2; ++c) {
+      const int k = 16 * m + 4 * q + 2 * c;
+      wr[2 * m + c] = make_float2(th[a.whh + i * MX_H + k], th[a.whh + i * MX_H + k + 1]);
+      wz[2 * m + c] = make_float2(th[a.whh + (MX_H + i) * MX_H + k], th[a.whh + (MX_H + i) * MX_H + k + 1]);
+      wn[2 * m + c] = make_float2(th[a.whh + (2 * MX_H + i) * MX_H + k], th[a.whh + (2 * MX_H + i) * MX_H + k + 1]);
     }
   const float br = th[a.bhh + i], bz = th[a.bhh + MX_H + i], bn = th[a.bhh + 2 * MX_H + i];
   MX_PDL_WAIT();        // the W_hh slice above is parameter data; everything below reads the predecessor's outputs
@@ -191,88 +193,88 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
     const int r = (idx / MX_H) % RPC, c = idx % MX_H;
     (&h_s[0][0][0])[idx] = (a.h0 && row0 + r < a.R) ? a.h0[(size_t)(row0 + r) * MX_H + c] : 0.f;
   }
+  for (int idx = tid; idx < GRU_RING * RPC * MX_G; idx += GRU_THREADS) (&gi_s[0][0][0])[idx] = 0.f;   // rows past R stay zero
 
   const float* gi = a.gi[net];
-  float* hall = a.hall[net];
   const int T1 = a.T + 1, N = a.N;
-  size_t mrow[RPC];
-  bool valid[RPC];
+  // lane-uniform stores: lane q of a quad writes value q of (h, r, z, n) of its unit; lane 0 also writes W_hn h + b_hn
+  float* stp[RPC];
+  float* hnp[RPC];
+  bool st_on[RPC], hn_on[RPC];
+  const size_t st_stride = (size_t)N * (q == 0 ? MX_H : MX_G), hn_stride = (size_t)N * MX_H;
 #pragma unroll
   for (int r = 0; r < RPC; ++r) {
     const int row = row0 + r;
-    valid[r] = row < a.R;
-    const int b = valid[r] ? row / N : 0, n = valid[r] ? row % N : 0;
-    mrow[r] = ((size_t)b * T1) * N + n;      // + t*N per step
+    const bool valid = row < a.R;
+    const int b = valid ? row / N : 0, n = valid ? row % N : 0;
+    const size_t m0 = ((size_t)b * T1) * N + n;      // + t*N per step
+    stp[r] = (q == 0) ? a.hall[net] + m0 * MX_H + i : (live ? a.gates + m0 * MX_G + (q - 1) * MX_H + i : nullptr);
+    hnp[r] = live ? a.hn + m0 * MX_H + i : nullptr;
+    st_on[r] = valid && (q == 0 || live);
+    hn_on[r] = valid && live && q == 0;
   }
   // prefetch assignment: RPC*48 16-byte pieces per step, at most one per thread (RPC <= 4)
   const int pf_r = tid / (MX_G / 4), pf_q = tid % (MX_G / 4);
-  const bool pf_on = tid < RPC * (MX_G / 4);
-  const bool pf_valid = pf_on && (row0 + pf_r) < a.R;
+  const bool pf_on = tid < RPC * (MX_G / 4) && (row0 + pf_r) < a.R;
   const float* pf_src = gi;
-  if (pf_valid) {
+  float* pf_dst = &gi_s[0][0][0];
+  if (pf_on) {
     const int row = row0 + pf_r;
     pf_src = gi + (((size_t)(row / N) * T1) * N + (row % N)) * MX_G + 4 * pf_q;
+    pf_dst = &gi_s[0][pf_r][4 * pf_q];
   }
   const size_t pf_stride = (size_t)N * MX_G;
-  auto prefetch = [&](int t) {
-    if (t < T1 && pf_on) {
-      float* dst = &gi_s[t % GRU_RING][pf_r][4 * pf_q];
-      if (pf_valid) mx_cp16(dst, pf_src + (size_t)t * pf_stride);
-      else mx_st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
-    }
+  auto prefetch = [&](int t) {          // called with t = 0, 1, 2, ... in order: the source pointer just advances
+    if (pf_on && t < T1) { mx_cp16(pf_dst + (t & (GRU_RING - 1)) * (RPC * MX_G), pf_src); pf_src += pf_stride; }
     mx_cp_commit();
   };
+  __syncthreads();          // the zero fill above precedes the first asynchronous copies into the ring
 #pragma unroll
   for (int t = 0; t < GRU_PF; ++t) prefetch(t);
   mx_cp_wait<GRU_PF - 1>();
   __syncthreads();
 
-  for (int t = 0; t < T1; ++t) {
-    const int cur = t & 1, nxt = cur ^ 1;
-    prefetch(t + GRU_PF);               // slot (t+GRU_PF) % RING == (t-1) % RING: last read one full step (one barrier) ago
-    float pr[RPC], pz[RPC], pn[RPC];
+  auto step = [&](const int t, const int cur) {
+    const int nxt = cur ^ 1;
+    prefetch(t + GRU_PF);               // slot (t+GRU_PF) & 7: last read at step t+GRU_PF-8 <= t-3, at least two barriers ago
+    const float* gs = &gi_s[t & (GRU_RING - 1)][0][0];
 #pragma unroll
     for (int r = 0; r < RPC; ++r) {
+      const float* hrow = &h_s[cur][r][0];
+      const float* g = gs + r * MX_G;
       float4 hv[4];
 #pragma unroll
-      for (int m = 0; m < 4; ++m) hv[m] = mx_ld4(&h_s[cur][r][16 * m + 4 * q]);
-      float sr = 0.f, sz = 0.f, sn = 0.f;
+      for (int m = 0; m < 4; ++m) hv[m] = mx_ld4(hrow + 16 * m + 4 * q);
+      const float gr = g[i] + br, gz = g[MX_H + i] + bz, gn = g[2 * MX_H + i], hp = hrow[i];      // off the dependent chain
+      float2 r0 = make_float2(0.f, 0.f), r1 = r0, z0 = r0, z1 = r0, n0 = r0, n1 = r0;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        sr = fmaf(wr[4 * m], hv[m].x, sr); sz = fmaf(wz[4 * m], hv[m].x, sz); sn = fmaf(wn[4 * m], hv[m].x, sn);
-        sr = fmaf(wr[4 * m + 1], hv[m].y, sr); sz = fmaf(wz[4 * m + 1], hv[m].y, sz); sn = fmaf(wn[4 * m + 1], hv[m].y, sn);
-        sr = fmaf(wr[4 * m + 2], hv[m].z, sr); sz = fmaf(wz[4 * m + 2], hv[m].z, sz); sn = fmaf(wn[4 * m + 2], hv[m].z, sn);
-        sr = fmaf(wr[4 * m + 3], hv[m].w, sr); sz = fmaf(wz[4 * m + 3], hv[m].w, sz); sn = fmaf(wn[4 * m + 3], hv[m].w, sn);
+        const float2 lo = make_float2(hv[m].x, hv[m].y), hi = make_float2(hv[m].z, hv[m].w);
+        r0 = mx_ffma2(wr[2 * m], lo, r0); z0 = mx_ffma2(wz[2 * m], lo, z0); n0 = mx_ffma2(wn[2 * m], lo, n0);
+        r1 = mx_ffma2(wr[2 * m + 1], hi, r1); z1 = mx_ffma2(wz[2 * m + 1], hi, z1); n1 = mx_ffma2(wn[2 * m + 1], hi, n1);
       }
-      pr[r] = sr; pz[r] = sz; pn[r] = sn;
-    }
-#pragma unroll
-    for (int r = 0; r < RPC; ++r) {        // quad all-reduce of the three partial dot products
-      pr[r] += __shfl_xor_sync(0xffffffffu, pr[r], 1); pz[r] += __shfl_xor_sync(0xffffffffu, pz[r], 1); pn[r] += __shfl_xor_sync(0xffffffffu, pn[r], 1);
-      pr[r] += __shfl_xor_sync(0xffffffffu, pr[r], 2); pz[r] += __shfl_xor_sync(0xffffffffu, pz[r], 2); pn[r] += __shfl_xor_sync(0xffffffffu, pn[r], 2);
-    }
-#pragma unroll
-    for (int r = 0; r < RPC; ++r) {
-      const float* g = &gi_s[t % GRU_RING][r][0];
-      const float rg = mx_sigmoid_fast(pr[r] + br + g[i]);
-      const float zg = mx_sigmoid_fast(pz[r] + bz + g[MX_H + i]);
-      const float hn = pn[r] + bn;
-      const float ng = mx_tanh_fast(g[2 * MX_H + i] + rg * hn);
-      const float hnew = (1.f - zg) * ng + zg * h_s[cur][r][i];
-      if (q == 0) h_s[nxt][r][i] = hnew;
-      if (valid[r]) {
-        const size_t mm = mrow[r] + (size_t)t * N;
-        if (q == 0) hall[mm * MX_H + i] = hnew;
-        if (live) {
-          if (q == 1) { a.gates[mm * MX_G + i] = rg; a.gates[mm * MX_G + MX_H + i] = zg; }
-          else if (q == 2) a.gates[mm * MX_G + 2 * MX_H + i] = ng;
-          else if (q == 3) a.hn[mm * MX_H + i] = hn;
-        }
-      }
+      r0 = mx_fadd2(r0, r1); z0 = mx_fadd2(z0, z1); n0 = mx_fadd2(n0, n1);
+      float pr = r0.x + r0.y, pz = z0.x + z0.y, pn = n0.x + n0.y;
+      pr += __shfl_xor_sync(0xffffffffu, pr, 1); pn += __shfl_xor_sync(0xffffffffu, pn, 1); pz += __shfl_xor_sync(0xffffffffu, pz, 1);
+      pr += __shfl_xor_sync(0xffffffffu, pr, 2); pn += __shfl_xor_sync(0xffffffffu, pn, 2); pz += __shfl_xor_sync(0xffffffffu, pz, 2);
+      const float rg = mx_sigmoid_fast(pr + gr);
+      const float hn = pn + bn;
+      const float ng = mx_tanh_fast(fmaf(rg, hn, gn));
+      const float zg = mx_sigmoid_fast(pz + gz);
+      const float hnew = fmaf(zg, hp - ng, ng);             // (1-z)*n + z*h
+      h_s[nxt][r][i] = hnew;              // all four lanes of the quad store the same value: keeps every lane on ONE path (a q == 0
+                                          // guard lets the compiler specialise the other lanes and the warp then runs both paths)
+      const float v = q == 0 ? hnew : (q == 1 ? rg : (q == 2 ? zg : ng));
+      if (st_on[r]) *stp[r] = v;
+      if (hn_on[r]) *hnp[r] = hn;
+      stp[r] += st_stride; hnp[r] += hn_stride;
     }
     mx_cp_wait<GRU_PF - 1>();           // gi of step t+1 has landed (this thread's copies); the barrier publishes it
     __syncthreads();
-  }
+  };
+  int t = 0;
+  for (; t + 1 < T1; t += 2) { step(t, 0); step(t + 1, 1); }
+  if (t < T1) step(t, 0);
   mx_cp_wait<0>();
 }
 

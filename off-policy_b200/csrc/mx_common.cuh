@@ -122,6 +122,16 @@ MX_DEVINL void mx_cp16(float* sdst, const float* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 #endif
 }
+// 16-byte copy that reads only `nbytes` (0 or 16) from global memory and zero-fills the rest: a branch-free "copy or clear"
+MX_DEVINL void mx_cp16z(float* sdst, const float* gsrc, int nbytes) {
+#if MX_EMU
+  if (nbytes) *reinterpret_cast<float4*>(sdst) = *reinterpret_cast<const float4*>(gsrc);
+  else *reinterpret_cast<float4*>(sdst) = float4{0.f, 0.f, 0.f, 0.f};
+#else
+  unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(nbytes) : "memory");
+#endif
+}
 MX_DEVINL void mx_cp4(float* sdst, const float* gsrc) {
 #if MX_EMU
   *sdst = *gsrc;
@@ -142,13 +152,43 @@ MX_DEVINL void mx_cp_wait() {   // wait until at most N of this thread's committ
 #endif
 }
 
-// fast transcendental forms for the recurrence (absolute error ~1e-7: ex2.approx + rcp.approx)
-MX_DEVINL float mx_sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-MX_DEVINL float mx_tanh_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = __expf(-2.0f * ax);
-  const float r = __fdividef(1.0f - t, 1.0f + t);
-  return x < 0.f ? -r : r;
+// fast transcendental forms for the recurrences (absolute error ~2e-7): ex2.approx.ftz + rcp.approx.ftz, no range fix-ups -- the
+// saturated cases fall out of IEEE inf / 0 arithmetic (ex2 -> +inf gives rcp -> 0; ex2 -> 0 gives rcp(1) = 1)
+MX_DEVINL float mx_ex2(float x) {
+#if MX_EMU
+  return exp2f(x);
+#else
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+MX_DEVINL float mx_rcp(float x) {
+#if MX_EMU
+  return 1.0f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+MX_DEVINL float mx_sigmoid_fast(float x) { return mx_rcp(1.0f + mx_ex2(-1.4426950408889634f * x)); }
+MX_DEVINL float mx_tanh_fast(float x) { return fmaf(2.0f, mx_rcp(1.0f + mx_ex2(-2.8853900817779268f * x)), -1.0f); }   // 2*sigmoid(2x) - 1
+
+// packed two-lane fp32 FMA (Blackwell FFMA2: one issue slot for two multiply-adds)
+MX_DEVINL float2 mx_ffma2(float2 a, float2 b, float2 c) {
+#if MX_EMU
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#else
+  return __ffma2_rn(a, b, c);
+#endif
+}
+MX_DEVINL float2 mx_fadd2(float2 a, float2 b) {
+#if MX_EMU
+  return make_float2(a.x + b.x, a.y + b.y);
+#else
+  return __fadd2_rn(a, b);
+#endif
 }
 
 // LayerNorm statistics the way ATen's CPU/CUDA kernels define them: biased variance, eps inside the sqrt.

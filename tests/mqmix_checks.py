@@ -190,28 +190,31 @@ def check_vs_oracle(N=3, O=18, A=5, S=54, B=64, steps=2, avail=False, per=False,
     if not vdn:
         tr.mixer.load_state_dict(L.mixer.state_dict())
         tr.target_mixer.load_state_dict(L.tgt_mixer.state_dict())
+    import kink
     for s in range(steps):
         b = synth_transitions(cfg, B, seed=50 + s, avail=avail)
         w = (np.random.RandomState(60 + s).rand(B) * 0.9 + 0.1) if per else None
+        L0 = kink.snapshot(L)
         info_t, prio, _ = tr.train_policy_on_batch(_to_dicts(b, w), True)
         gv = {k: v.clone() for k, v in tr.grad_views().items()}
-        tr.soft_target_updates()
         ref, rprio, _ = L.step(b + (w, None))
         coef = min(1.0, cfg.max_grad_norm / (float(ref["grad_norm"]) + 1e-6))
+        bad = qc.grad_failures(gv, coef, L, cfg, 1e-4)
+        if bad:      # ReLU kink?  (tests/kink.py: B = 1000 transitions x 3 agents x 128 hidden units -- a pre-activation within round-off of zero is likely)
+            masks = kink.engine_masks(tr, B, 1, N, mlp=True)
+            (ref, rprio, _), flips, max_pre = kink.redo_with_engine_masks(L0, lambda LL: LL.step(b + (w, None)), masks)
+            assert flips > 0 and max_pre < kink.KINK_TOL, (s, "gradient mismatch not explained by ReLU kinks", flips, max_pre, bad[:3])
+            kink.adopt(L, L0)
+            coef = min(1.0, cfg.max_grad_norm / (float(ref["grad_norm"]) + 1e-6))
+            bad = qc.grad_failures(gv, coef, L, cfg, 1e-4)
+            print("kink-aware comparison: %d ReLU unit(s) within %.1e of zero flipped" % (flips, max_pre))
+        assert not bad, (s, bad[:4])
+        tr.soft_target_updates()
         L.soft_update()
         for k in ("loss", "grad_norm", "Q_tot"):
             assert rel_err(info_t[k].cpu(), ref[k]) < 1e-4, (s, k, float(info_t[k]), float(ref[k]))
         if per:
             assert rel_err(np.asarray(prio), rprio) < 1e-4
-        named = dict(("agent." + k, p) for k, p in L.agent.named_parameters())
-        if not vdn:
-            named.update(("mixer." + k, p) for k, p in L.mixer.named_parameters())
-        for k, p in named.items():
-            if p.grad is None:
-                assert float(gv[k].abs().max()) == 0.0, k
-                continue
-            ok, err, lim = qc.close(gv[k] * coef, p.grad, 1e-4)
-            assert ok, (s, k, err, lim)
         for k, v in pol.q_network.state_dict().items():
             assert float((v.cpu() - L.agent.state_dict()[k]).abs().max()) <= 5e-3 * cfg.lr * (s + 1) + 1e-7, (s, k)
         for k, v in tr.target_q_network.state_dict().items():
