@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MX_ABI_VERSION 2
+#define MX_ABI_VERSION 3
 #define MX_MAX_NAME 64
 
 typedef struct mx_replay mx_replay;   /* one policy's episode store + sampler (RecPolicyBuffer + PER trees) */
@@ -124,6 +124,11 @@ int mx_replay_gather_host(mx_replay* r, const int64_t* idx_host, int32_t B, void
 /* PrioritizedRecReplayBuffer.sample (rec_buffer.py:272-304): masses from np.random.random semantics,
  * fp64 prefix-sum descent, IS weights, gather. */
 int mx_replay_sample_per(mx_replay* r, int32_t B, double beta, void* stream);
+/* The PER draw inside a captured whole-step sequence (mx_graph_capture / mx_maddpg_graph_capture with flag 2) reads its
+ * importance-sampling exponent from a device scalar, initialised with the `beta` given at capture.  The reference anneals beta
+ * towards 1 on every train step (runner/rnn/base_runner.py:159-160,235 -> rec_buffer.py:278): call this before a mx_graph_launch
+ * to change it (one tiny launch on `stream`, by-value argument, no synchronisation). */
+int mx_replay_set_beta(mx_replay* r, double beta, void* stream);
 /* update_priorities (rec_buffer.py:306-324): leaf = prio**alpha into both trees, duplicate idx: last wins;
  * max_priority = max(max_priority, max(prio)).  prio_dev fp32[B] (the trainer hands NumPy fp32), or pass
  * leaves_f64_dev != NULL to store pre-powered fp64 leaf values verbatim (parity tests). */

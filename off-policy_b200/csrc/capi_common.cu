@@ -29,6 +29,7 @@ int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "overlap")) { g_mx_overlap = value; return 0; }
   if (!strcmp(name, "overlap_rows")) { g_mx_overlap_rows = value; return 0; }
   if (!strcmp(name, "mid_fused")) { g_mx_mid_fused = value; return 0; }
+  if (!strcmp(name, "optim_fused")) { g_mx_optim_fused = value; return 0; }
   if (!strcmp(name, "gru_fwd_rpc")) { g_mx_gru_fwd_rpc = value; return 0; }
   if (!strcmp(name, "gru_bwd_rpc")) { g_mx_gru_bwd_rpc = value; return 0; }
   return -1;

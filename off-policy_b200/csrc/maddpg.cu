@@ -739,9 +739,10 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
 extern "C" int mx_maddpg_graph_capture(mx_replay* r, mx_maddpg* h, int32_t B, double beta, uint32_t flags, const float* target_noise_dev,
                                        const float* actor_noise_dev, int32_t update_actor, void* stream, mx_graph** out) {
   if (!r || !h || !out) { mx_set_error("mx_maddpg_graph_capture: null argument"); return 1; }
+  if ((flags & 2u) && mx_replay_set_beta(r, beta, stream)) return 1;
   auto seq = [=](void* st) -> int {
     if (flags & 1u) { if (mx_replay_sample_uniform(r, B, st)) return 1; }
-    else if (flags & 2u) { if (mx_replay_sample_per(r, B, beta, st)) return 1; }
+    else if (flags & 2u) { if (mx_replay_sample_per_state_beta(r, B, st)) return 1; }      // exponent: device scalar (mx_replay_set_beta)
     mx_batch b;
     if (mx_replay_batch(r, B, &b)) return 1;
     h->force_update_actor = update_actor ? 1 : 0;

@@ -200,8 +200,20 @@ struct OptimArgs {
   int normpart_n;           //   or null when the gradient is all-reduced in between (world_size > 1)
   int fuse_polyak;          // Adam epilogue also applies the soft target update (graph mode)
   float weight_decay;       // torch.optim.Adam(weight_decay): g += wd * p after clipping
+  // k_optim_fused: grid barrier words (device, zero-initialised): [0] exchange arrivals, [1] barrier arrivals, [2] barrier generation,
+  // [3] sticky abort flag (a peer never arrived)
+  unsigned* sync;
+  int phase;                // k_optim_fused: 0 = whole kernel (grid barrier); 1 / 2 = the halves before / after the barrier as two launches (emulator)
+  // data-parallel exchange over peer memory (p2p.cu layout): base of every rank's symmetric block, floats per slot, rank / world (0: none)
+  float* p2p_blocks[16];
+  long long p2p_slot;
+  int p2p_rank, p2p_world;
 };
 static inline int mx_grad_reduce_blocks(long long P) { return (int)((P + 255) / 256); }   // 256 parameters per block
 int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s);
 int mx_launch_adam(const OptimArgs& a, cudaStream_t s);
+// reduce + [peer-memory all-reduce] + clip + Adam [+ Polyak] in ONE launch (grid barrier); returns -1 when the configuration cannot use
+// it (the caller then launches k_grad_reduce / [exchange] / k_adam)
+int mx_launch_optim_fused(const OptimArgs& a, cudaStream_t s);
+extern int g_mx_optim_fused;
 int mx_launch_polyak(float* tgt, const float* src, long long n, float tau, cudaStream_t s);

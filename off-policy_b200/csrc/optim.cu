@@ -13,47 +13,44 @@
 #include "mx_internal.h"
 #include "mx_kernels.h"
 
-__global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
+// ---- phase 1 of the optimiser, shared by k_grad_reduce and k_optim_fused -------------------------------------------------------------
+// scalar block: sum(1-bad), loss numerator, sum Q_tot(1-bad), element count -> grad[P .. P+3]; PER priorities.  Returns the four scalars.
+MX_DEVINL float4 optim_scalars(const OptimArgs& a) {
   const int tid = threadIdx.x;
-  MX_PDL_WAIT();
-  if (blockIdx.x == gridDim.x - 1) {
-    // ---- scalar sums: sum(1-bad), loss numerator, sum Q_tot(1-bad) ----
-    __shared__ float red[3][256];
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int i = tid; i < a.spart_n; i += blockDim.x) { s0 += a.spart[i * 8]; s1 += a.spart[i * 8 + 1]; s2 += a.spart[i * 8 + 2]; }
-    red[0][tid] = s0; red[1][tid] = s1; red[2][tid] = s2;
-    __syncthreads();
-    if (tid == 0) {
-      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-      for (int i = 0; i < (int)blockDim.x; ++i) { t0 += red[0][i]; t1 += red[1][i]; t2 += red[2][i]; }
-      a.grad[a.P + 0] = t0;
-      a.grad[a.P + 1] = t1;
-      a.grad[a.P + 2] = t2;
-      a.grad[a.P + 3] = (float)(a.B * a.T);
-      // Adam step count (1-based) and the running powers beta^t for the bias corrections (first step: 1 * beta)
-      const double t_old = a.adam_t[0];
-      a.adam_t[0] = t_old + 1.0;
-      a.adam_t[1] = (t_old == 0.0 ? 1.0 : a.adam_t[1]) * (double)a.beta1;
-      a.adam_t[2] = (t_old == 0.0 ? 1.0 : a.adam_t[2]) * (double)a.beta2;
-    }
-    // ---- PER: new priority = (1-nu) * mean_t|e| + nu * max_t|e| + eps  (mean over all T, masked steps are zeros) ----
-    if (a.prio) {
-      for (int b = tid; b < a.B; b += blockDim.x) {
-        float mx = 0.f, sm = 0.f;
-        for (int t = 0; t < a.T; ++t) {
-          const float e = fabsf(a.err[(size_t)b * a.T + t]);
-          sm += e;
-          mx = fmaxf(mx, e);
-        }
-        a.prio[b] = (1.f - a.per_nu) * (sm / (float)a.T) + a.per_nu * mx + a.per_eps;
-      }
-    }
-    return;
+  __shared__ float red[3][256];
+  __shared__ float4 s_out;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int i = tid; i < a.spart_n; i += blockDim.x) { s0 += a.spart[i * 8]; s1 += a.spart[i * 8 + 1]; s2 += a.spart[i * 8 + 2]; }
+  red[0][tid] = s0; red[1][tid] = s1; red[2][tid] = s2;
+  __syncthreads();
+  if (tid == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int i = 0; i < (int)blockDim.x; ++i) { t0 += red[0][i]; t1 += red[1][i]; t2 += red[2][i]; }
+    s_out = make_float4(t0, t1, t2, (float)(a.B * a.T));
+    mx_st4(a.grad + a.P, s_out);
   }
-  // 64 float4 columns (256 parameters) per block x 4 slices of the partial index: thread (c, sl) sums partials sl, sl+4, ... of
-  // its column with 16-byte loads (8 in flight), then the four slices are added in fixed order -> deterministic result.
+  // ---- PER: new priority = (1-nu) * mean_t|e| + nu * max_t|e| + eps  (mean over all T, masked steps are zeros) ----
+  if (a.prio) {
+    for (int b = tid; b < a.B; b += blockDim.x) {
+      float mx = 0.f, sm = 0.f;
+      for (int t = 0; t < a.T; ++t) {
+        const float e = fabsf(a.err[(size_t)b * a.T + t]);
+        sm += e;
+        mx = fmaxf(mx, e);
+      }
+      a.prio[b] = (1.f - a.per_nu) * (sm / (float)a.T) + a.per_nu * mx + a.per_eps;
+    }
+  }
+  __syncthreads();
+  return s_out;
+}
+
+// parameter block: 64 float4 columns (256 parameters) per block x 4 slices of the partial index: thread (c, sl) sums partials sl, sl+4, ...
+// of its column with 16-byte loads (8 in flight), then the four slices are added in fixed order -> deterministic result.  Threads
+// tid < 64 return the reduced float4 of column tid (zeros past P).
+MX_DEVINL float4 optim_reduce_partials(const OptimArgs& a) {
+  const int tid = threadIdx.x;
   __shared__ float4 sl_sum[4][64];
-  __shared__ float sq[2];
   const int c = tid & 63, sl = tid >> 6;
   const long long i = ((long long)blockIdx.x * 64 + c) * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -87,22 +84,204 @@ __global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
   }
   sl_sum[sl][c] = acc;
   __syncthreads();
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid < 64) {
     const float4 s0 = sl_sum[0][tid], s1 = sl_sum[1][tid], s2 = sl_sum[2][tid], s3 = sl_sum[3][tid];
-    float4 g;
     g.x = (s0.x + s1.x) + (s2.x + s3.x); g.y = (s0.y + s1.y) + (s2.y + s3.y);
     g.z = (s0.z + s1.z) + (s2.z + s3.z); g.w = (s0.w + s1.w) + (s2.w + s3.w);
-    const long long j = ((long long)blockIdx.x * 64 + tid) * 4;
-    float q = 0.f;
-    if (j < a.P) {
-      mx_st4(a.grad + j, g);
-      q = (g.x * g.x + g.y * g.y) + (g.z * g.z + g.w * g.w);
-    }
-    q = mx_warp_sum(q);                       // per-block sum of squares: lets k_adam skip re-reading the whole gradient
+  }
+  return g;
+}
+
+// per-block sum of squares of the reduced float4 columns (threads tid < 64) -> normpart[blockIdx.x]
+MX_DEVINL void optim_block_sumsq(const OptimArgs& a, float4 g, long long j) {
+  const int tid = threadIdx.x;
+  __shared__ float sq[2];
+  if (tid < 64) {
+    float q = (j < a.P) ? (g.x * g.x + g.y * g.y) + (g.z * g.z + g.w * g.w) : 0.f;
+    q = mx_warp_sum(q);
     if ((tid & 31) == 0) sq[tid >> 5] = q;
   }
   __syncthreads();
   if (tid == 0 && a.normpart) a.normpart[blockIdx.x] = sq[0] + sq[1];
+}
+
+// Adam step count (1-based) and the running powers beta^t for the bias corrections (first step: 1 * beta)
+MX_DEVINL void optim_bump_step(const OptimArgs& a) {
+  const double t_old = a.adam_t[0];
+  a.adam_t[0] = t_old + 1.0;
+  a.adam_t[1] = (t_old == 0.0 ? 1.0 : a.adam_t[1]) * (double)a.beta1;
+  a.adam_t[2] = (t_old == 0.0 ? 1.0 : a.adam_t[2]) * (double)a.beta2;
+}
+
+__global__ void __launch_bounds__(256) k_grad_reduce(OptimArgs a) {
+  const int tid = threadIdx.x;
+  MX_PDL_WAIT();
+  if (blockIdx.x == gridDim.x - 1) {
+    optim_scalars(a);
+    if (tid == 0) optim_bump_step(a);
+    return;
+  }
+  const float4 g = optim_reduce_partials(a);
+  const long long j = ((long long)blockIdx.x * 64 + tid) * 4;
+  if (tid < 64 && j < a.P) mx_st4(a.grad + j, g);
+  optim_block_sumsq(a, g, j);      // lets k_adam skip re-reading the whole gradient
+}
+
+// ---- one-launch optimiser: partial reduction -> [all-reduce over peer memory] -> global-norm clip -> Adam [-> Polyak] ----------------
+// Grid = the k_grad_reduce grid (one block per 256 parameters + the scalar block), all co-resident (checked by the launcher), joined
+// by ONE grid barrier (sense-reversing counter in device memory) between the reduction and the update: the global gradient norm needs
+// every block's sum of squares.  The reduced gradient never leaves the registers of the 64 threads that apply it.
+// Data parallel (a.p2p_world > 1): every block PUSHES its reduced columns into slot [step parity][own rank] of every peer's symmetric
+// block (remote stores are fire-and-forget; the later reads are local), the last block to finish raises flag[own rank] = step on
+// every peer, all blocks wait for the world's flags (which also orders the local blocks) and add the slots in rank order -- every
+// rank computes the same bits.  A peer that never arrives (10 s) sets the sticky abort word: NO rank-local update is applied and
+// info[7] = -1 tells the host, which raises.
+MX_DEVINL unsigned optim_ld_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+MX_DEVINL float4 optim_ld4_volatile(const float* p) {
+#if MX_EMU
+  return *reinterpret_cast<const float4*>(p);
+#else
+  float4 r;      // never served from a stale L1 line (written by another GPU / another SM during this kernel)
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+#endif
+}
+
+__global__ void __launch_bounds__(256) k_optim_fused(OptimArgs a) {
+  const int tid = threadIdx.x;
+  const bool scalar_blk = blockIdx.x == gridDim.x - 1;
+  __shared__ unsigned s_gen, s_last;
+  __shared__ double red[8];
+  __shared__ float s_scale, s_step, s_bc2s;
+  MX_PDL_WAIT();
+  if (tid == 0) s_gen = optim_ld_volatile(a.sync + 2);       // barrier generation, read before this block arrives anywhere
+  const double t_old = a.adam_t[0];                          // (rewritten by the scalar block only after the grid barrier)
+  const double b1p = (t_old == 0.0 ? 1.0 : a.adam_t[1]) * (double)a.beta1, b2p = (t_old == 0.0 ? 1.0 : a.adam_t[2]) * (double)a.beta2;
+  const unsigned step = (unsigned)t_old + 1u;
+  const long long j = ((long long)blockIdx.x * 64 + tid) * 4;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 sc = g;
+  if (a.phase == 2) {                    // second launch of the two-launch form: the reduced columns come back from memory
+    if (!scalar_blk && tid < 64 && j < a.P) g = mx_ld4(a.grad + j);
+  } else if (scalar_blk) sc = optim_scalars(a);
+  else {
+    g = optim_reduce_partials(a);
+    if (a.p2p_world <= 1 && tid < 64 && j < a.P) mx_st4(a.grad + j, g);
+  }
+  if (a.p2p_world > 1 && a.phase == 0) {
+    const int W = a.p2p_world;
+    const size_t slot0 = (size_t)(step & 1u) * W * a.p2p_slot;
+    const long long col = scalar_blk ? a.P : j;                       // the scalar block owns the four scalars behind the parameters
+    const bool owner = scalar_blk ? tid == 0 : (tid < 64 && j < a.P);
+    const float4 mine = scalar_blk ? sc : g;
+    if (owner)
+      for (int p = 0; p < W; ++p) mx_st4(a.p2p_blocks[p] + slot0 + (size_t)a.p2p_rank * a.p2p_slot + col, mine);
+    __threadfence_system();              // this thread's slot writes are visible to the peers before anything that follows
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned last = (atomicAdd(a.sync + 0, 1u) == gridDim.x - 1) ? 1u : 0u;
+      if (last) a.sync[0] = 0u;
+      s_last = last;
+    }
+    __syncthreads();
+    unsigned* my_flags = reinterpret_cast<unsigned*>(a.p2p_blocks[a.p2p_rank] + 2 * (size_t)W * a.p2p_slot);
+    if (s_last && tid < W) {             // every block of this rank has fenced its part of the slot: tell the peers (and ourselves)
+      __threadfence_system();
+      volatile unsigned* f = reinterpret_cast<unsigned*>(a.p2p_blocks[tid] + 2 * (size_t)W * a.p2p_slot) + a.p2p_rank;
+      *f = step;
+    }
+    if (tid < W) {
+#if !MX_EMU
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (optim_ld_volatile(my_flags + tid) < step) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) { atomicExch(a.sync + 3, 1u); break; }      // 10 s: a peer died; do not hang the device
+      }
+      __threadfence_system();            // acquire: the peer's slot writes precede its flag store
+#endif
+    }
+    __syncthreads();
+    if (owner) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < W; ++p) {      // rank order on every rank: bit-identical sums everywhere
+        const float4 v = optim_ld4_volatile(a.p2p_blocks[a.p2p_rank] + slot0 + (size_t)p * a.p2p_slot + col);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      mx_st4(a.grad + col, acc);
+      if (scalar_blk) sc = acc; else g = acc;
+    }
+  }
+  if (!scalar_blk && a.phase != 2) optim_block_sumsq(a, g, j);
+  if (a.phase == 1) return;
+  // ---- grid barrier ----
+  __syncthreads();
+  if (tid == 0 && a.phase == 0) {
+    __threadfence();
+    if (atomicAdd(a.sync + 1, 1u) == gridDim.x - 1) {
+      a.sync[1] = 0u;
+      __threadfence();
+      atomicAdd(a.sync + 2, 1u);
+    } else {
+      while (optim_ld_volatile(a.sync + 2) == s_gen) {}
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (optim_ld_volatile(a.sync + 3)) {       // a peer never arrived: nothing is applied anywhere on this rank
+    if (blockIdx.x == 0 && tid == 0) a.info[7] = -1.f;
+    return;
+  }
+  // ---- ||g||, clip, Adam on the columns still held in registers ----
+  const float* gtail = a.grad + a.P;
+  const float denom = __ldcg(gtail + 0);
+  const float invd = 1.0f / denom;
+  double sp = 0.0;
+  for (int i = tid; i < a.normpart_n; i += blockDim.x) sp += (double)__ldcg(a.normpart + i);
+  sp = mx_warp_sum_d(sp);
+  if ((tid & 31) == 0) red[tid >> 5] = sp;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    const float norm = (float)sqrt(t * ((double)invd * (double)invd));
+    float coef = a.max_grad_norm / (norm + 1e-6f);       // clip_grad_norm_: always applied, clamped to 1
+    if (coef > 1.f) coef = 1.f;
+    s_scale = coef * invd;
+    s_step = a.lr / (float)(1.0 - b1p);
+    s_bc2s = (float)sqrt(1.0 - b2p);
+    if (blockIdx.x == 0) {
+      a.info[0] = __ldcg(gtail + 1) * invd;                // loss
+      a.info[1] = norm;                                    // grad_norm (pre-clip)
+      a.info[2] = __ldcg(gtail + 2) / __ldcg(gtail + 3);   // Q_tot mean over all (t,b)
+      a.info[3] = denom;
+    }
+    if (scalar_blk) { a.adam_t[0] = t_old + 1.0; a.adam_t[1] = b1p; a.adam_t[2] = b2p; }
+  }
+  __syncthreads();
+  if (scalar_blk || tid >= 64 || j >= a.P) return;
+  const float scale = s_scale, stp = s_step, bc2s = s_bc2s;
+  const float gg[4] = {g.x, g.y, g.z, g.w};
+  const float4 th4 = mx_ld4(a.theta + j), m4 = mx_ld4(a.adam_m + j), v4 = mx_ld4(a.adam_v + j);
+  float th[4] = {th4.x, th4.y, th4.z, th4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float ge = gg[e] * scale;
+    if (a.weight_decay != 0.f) ge = fmaf(a.weight_decay, th[e], ge);     // torch Adam: grad.add(param, alpha=weight_decay)
+    m[e] = m[e] + (ge - m[e]) * (1.f - a.beta1);                         // exp_avg.lerp_(grad, 1 - beta1)
+    v[e] = v[e] * a.beta2 + (1.f - a.beta2) * ge * ge;                   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float den = sqrtf(v[e]) / bc2s + a.eps;
+    th[e] = th[e] - stp * (m[e] / den);
+  }
+  mx_st4(a.theta + j, make_float4(th[0], th[1], th[2], th[3]));
+  mx_st4(a.adam_m + j, make_float4(m[0], m[1], m[2], m[3]));
+  mx_st4(a.adam_v + j, make_float4(v[0], v[1], v[2], v[3]));
+  if (a.fuse_polyak) {                                                    // util.py:132-134 fused epilogue
+    const float4 t4 = mx_ld4(a.theta_tgt + j);
+    mx_st4(a.theta_tgt + j, make_float4(t4.x * (1.0f - a.tau) + th[0] * a.tau, t4.y * (1.0f - a.tau) + th[1] * a.tau,
+                                        t4.z * (1.0f - a.tau) + th[2] * a.tau, t4.w * (1.0f - a.tau) + th[3] * a.tau));
+  }
 }
 
 __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
@@ -110,6 +289,7 @@ __global__ void __launch_bounds__(1024) k_adam(OptimArgs a) {
   __shared__ float s_scale, s_step, s_bc2s;
   const int tid = threadIdx.x;
   MX_PDL_WAIT();
+  if (a.info[7] < 0.f) return;        // the peer-memory exchange timed out (p2p.cu): the sums are not trustworthy, apply nothing
   const float denom = a.grad[a.P + 0];
   const float invd = 1.0f / denom;
   // ||g||^2 over the full vector, identical summation order in every CTA (no grid-wide barrier needed)
@@ -185,6 +365,35 @@ int mx_launch_grad_reduce(const OptimArgs& a, cudaStream_t s) {
   MX_COUNT();
   MX_MARK("k_grad_reduce", s);
   return MX_CHECK_LAUNCH("grad_reduce");
+}
+int g_mx_optim_fused = 1;
+int mx_launch_optim_fused(const OptimArgs& a, cudaStream_t s) {
+#if MX_EMU
+  // the emulator runs one CTA at a time, so a grid barrier cannot complete there: the same kernel as two launches (before / after
+  // the barrier).  The peer-memory exchange inside the kernel needs concurrently running ranks: the emulated tests use the separate
+  // exchange kernels (p2p.cu) instead.
+  if (!g_mx_optim_fused || !a.sync || !a.normpart || a.p2p_world > 1) return -1;
+  OptimArgs b = a;
+  const int grid = mx_grad_reduce_blocks(a.P) + 1;
+  b.phase = 1;
+  MX_LAUNCH(k_optim_fused, dim3(grid), dim3(256), 0, s, b);
+  b.phase = 2;
+  MX_LAUNCH(k_optim_fused, dim3(grid), dim3(256), 0, s, b);
+  MX_COUNT();
+  MX_MARK("k_optim_fused", s);
+  return 0;
+#else
+  if (!g_mx_optim_fused || !a.sync || !a.normpart) return -1;
+  const int grid = mx_grad_reduce_blocks(a.P) + 1;
+  static int per_sm = -1;
+  if (per_sm < 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_optim_fused, 256, 0) != cudaSuccess) per_sm = 0;
+  if (grid > per_sm * mx_num_sms()) return -1;        // not all blocks co-resident: no grid barrier
+  MX_LAUNCH_PDL(k_optim_fused, dim3(grid), dim3(256), 0, s, a);
+  MX_PDL_THETA_WRITTEN();
+  MX_COUNT();
+  MX_MARK("k_optim_fused", s);
+  return MX_CHECK_LAUNCH("optim_fused");
+#endif
 }
 int mx_launch_adam(const OptimArgs& a, cudaStream_t s) {
   int grid = (int)((a.P + 4095) / 4096);

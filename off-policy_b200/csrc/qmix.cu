@@ -154,6 +154,7 @@ static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W
   W->spart = tk((int64_t)npart * 8);
   W->adam_t = tk(8);
   W->normpart = tk(mx_grad_reduce_blocks(P));
+  W->sync = tk(8);
   W->tcimg[0] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c))); W->tcimg[1] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c)));
   W->xin = tk(c->prev_act_inp ? M * mx_round_up(agent_in_dim(c), 4) : 0);
   W->da2 = tk(M * MX_H); W->da1 = tk(M * MX_H);
@@ -255,7 +256,7 @@ static int check_batch(const mx_qmix* q, const mx_batch* b) {
   return 0;
 }
 
-static OptimArgs optim_args(mx_qmix* q, int B, const int parts[4]) {   // parts: front_bwd, qhead_bwd, mixer gradient partials, scalar partials
+static OptimArgs optim_args(mx_qmix* q, int B, const int parts[4], bool after_external_allreduce = false) {   // parts: front_bwd, qhead_bwd, mixer gradient partials, scalar partials
   const mx_qmix_cfg& c = q->cfg;
   OptimArgs o;
   memset(&o, 0, sizeof(o));
@@ -274,7 +275,12 @@ static OptimArgs optim_args(mx_qmix* q, int B, const int parts[4]) {   // parts:
   o.prio = c.use_per ? ws + q->W.prio : nullptr;
   o.lr = c.lr; o.beta1 = c.adam_beta1; o.beta2 = c.adam_beta2; o.eps = c.adam_eps; o.max_grad_norm = c.max_grad_norm; o.tau = c.tau;
   o.world_size = c.world_size;
-  if (c.world_size == 1) { o.normpart = ws + q->W.normpart; o.normpart_n = mx_grad_reduce_blocks(q->P); }   // else: all-reduced in between
+  // per-block sums of squares of the reduced numerators: valid for k_adam on one GPU and inside k_optim_fused (computed after its
+  // exchange); k_adam after an external all-reduce (NCCL / the separate p2p kernels) recomputes the norm from the summed buffer
+  if (c.world_size == 1 || !after_external_allreduce) { o.normpart = ws + q->W.normpart; o.normpart_n = mx_grad_reduce_blocks(q->P); }
+  o.sync = reinterpret_cast<unsigned*>(ws + q->W.sync);
+  o.p2p_world = q->p2p_world; o.p2p_rank = q->p2p_rank; o.p2p_slot = mx_round_up64(q->P + 8, 64);
+  for (int p = 0; p < q->p2p_world; ++p) o.p2p_blocks[p] = q->p2p_blocks[p];
   return o;
 }
 
@@ -321,7 +327,9 @@ int mx_qmix_prefork(mx_qmix* q, int B, void* stream) {
   return 0;
 }
 
-extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream) {
+// everything of the step up to (not including) the optimiser: forward, loss, backward; leaves the per-CTA gradient partials and
+// fills `*oa` with the optimiser's arguments
+static int backward_core(mx_qmix* q, const mx_batch* b, void* stream, OptimArgs* oa) {
   if (check_batch(q, b)) return 1;
   const mx_qmix_cfg& c = q->cfg;
   cudaStream_t s = (cudaStream_t)stream;
@@ -419,8 +427,8 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
 #if !MX_EMU
     if (split && overlap) join_from_side(q, q->ev_hbwd, s);
 #endif
-    OptimArgs om = optim_args(q, B, parts);
-    return mx_launch_grad_reduce(om, s);
+    *oa = optim_args(q, B, parts);
+    return 0;
   }
 
   GruFwdArgs gf;
@@ -503,20 +511,33 @@ extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream
 #if !MX_EMU
   if (split && overlap) join_from_side(q, q->ev_hbwd, s);
 #endif
-  OptimArgs o = optim_args(q, B, parts);
-  return mx_launch_grad_reduce(o, s);
+  *oa = optim_args(q, B, parts);
+  return 0;
+}
+
+extern "C" int mx_qmix_backward_only(mx_qmix* q, const mx_batch* b, void* stream) {
+  OptimArgs o;
+  if (backward_core(q, b, stream, &o)) return 1;
+  return mx_launch_grad_reduce(o, (cudaStream_t)stream);
 }
 
 extern "C" int mx_qmix_apply_ex(mx_qmix* q, uint32_t flags, void* stream) {
   const int parts[4] = {0, 0, 0, 0};
-  OptimArgs o = optim_args(q, q->cfg.max_batch, parts);
+  OptimArgs o = optim_args(q, q->cfg.max_batch, parts, true);
   o.fuse_polyak = (flags & MX_STEP_FUSE_SOFT_UPDATE) ? 1 : 0;
   return mx_launch_adam(o, (cudaStream_t)stream);
 }
 extern "C" int mx_qmix_apply(mx_qmix* q, void* stream) { return mx_qmix_apply_ex(q, 0, stream); }
 
 extern "C" int mx_qmix_step_ex(mx_qmix* q, const mx_batch* b, uint32_t flags, void* stream) {
-  if (mx_qmix_backward_only(q, b, stream)) return 1;
+  OptimArgs o;
+  if (backward_core(q, b, stream, &o)) return 1;
+  if (q->cfg.world_size == 1 || q->p2p_world) {      // ONE launch: partial reduction + [exchange over peer memory] + clip + Adam [+ Polyak]
+    o.fuse_polyak = (flags & MX_STEP_FUSE_SOFT_UPDATE) ? 1 : 0;
+    const int rc = mx_launch_optim_fused(o, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
+  if (mx_launch_grad_reduce(o, (cudaStream_t)stream)) return 1;
   if (q->cfg.world_size > 1) {
     if (!q->p2p_world) return 0;         // NCCL path: the caller all-reduces mx_qmix_grad_buffer(), then mx_qmix_apply[_ex]()
     if (mx_qmix_p2p_publish(q, stream) || mx_qmix_p2p_reduce(q, stream)) return 1;   // one-shot all-reduce over peer memory
@@ -541,7 +562,7 @@ extern "C" int mx_qmix_hard_update(mx_qmix* q, void* stream) {
 static int run_sequence(mx_replay* r, mx_qmix* q, int B, double beta, uint32_t flags, void* stream) {
   if ((flags & 3u) && mx_qmix_prefork(q, B, stream)) return 1;      // weight-image prep overlaps the draw + gather
   if (flags & 1u) { if (mx_replay_sample_uniform(r, B, stream)) return 1; }
-  else if (flags & 2u) { if (mx_replay_sample_per(r, B, beta, stream)) return 1; }
+  else if (flags & 2u) { (void)beta; if (mx_replay_sample_per_state_beta(r, B, stream)) return 1; }     // beta: device scalar, see mx_graph_capture
   mx_batch b;
   if (mx_replay_batch(r, B, &b)) return 1;
   const bool fuse = (flags & 4u) && (q->cfg.world_size == 1 || q->p2p_world);
@@ -590,6 +611,7 @@ int mx_graph_capture_seq(std::function<int(void*)> seq, std::function<void()> af
 
 extern "C" int mx_graph_capture(mx_replay* r, mx_qmix* q, int32_t B, double beta, uint32_t flags, void* stream, mx_graph** out) {
   if (!r || !q || !out) { mx_set_error("mx_graph_capture: null argument"); return 1; }
+  if ((flags & 2u) && mx_replay_set_beta(r, beta, stream)) return 1;     // initial exponent; mx_replay_set_beta() before a launch changes it
   return mx_graph_capture_seq([=](void* st) { return run_sequence(r, q, B, beta, flags, st); }, nullptr, stream, out);
 }
 

@@ -249,7 +249,7 @@ struct DrawArgs {
   // PER
   const double *sum_tree, *min_tree;
   int cap;
-  double beta;
+  double beta;                 // < 0: read state->per_beta (whole-step graphs: the exponent anneals between replays of one captured launch)
   double* w_out;               // fp64 [B]
   float* w32_out;              // fp32 [B]
 };
@@ -378,10 +378,11 @@ __global__ void __launch_bounds__(256) k_draw(DrawArgs a) {
     }
     int leaf = node - a.cap;
     a.idx_out[i] = leaf;
+    const double beta = a.beta < 0.0 ? a.state->per_beta : a.beta;
     double p_min = s_min / s_all;
-    double max_w = pow(p_min * (double)n, -a.beta);
+    double max_w = pow(p_min * (double)n, -beta);
     double p_s = a.sum_tree[a.cap + leaf] / s_all;
-    double w = pow(p_s * (double)n, -a.beta) / max_w;
+    double w = pow(p_s * (double)n, -beta) / max_w;
     a.w_out[i] = w;
     a.w32_out[i] = (float)w;
   }
@@ -791,11 +792,27 @@ extern "C" int mx_replay_gather_host(mx_replay* r, const int64_t* idx_host, int3
   return launch_gather(r, at<int64_t>(r, r->L.off_b_idx), B, s);
 }
 
+__global__ void k_set_beta(MxReplayState* st, double beta) { st->per_beta = beta; }
+
+// Importance-sampling exponent for the NEXT replays of a captured whole-step sequence (rec_buffer.py:278: beta is an argument of every
+// sample() and the runner anneals it, base_runner.py:159-160,235): a by-value kernel argument, so no host memory has to stay alive.
+extern "C" int mx_replay_set_beta(mx_replay* r, double beta, void* stream) {
+  if (!r || !r->cfg.use_per) { mx_set_error("mx_replay_set_beta: replay created without use_per"); return 1; }
+  if (!(beta > 0)) { mx_set_error("mx_replay_set_beta: beta must be > 0"); return 1; }
+  MX_LAUNCH(k_set_beta, dim3(1), dim3(1), 0, (cudaStream_t)stream, at<MxReplayState>(r, r->L.off_state), beta);
+  return MX_CHECK_LAUNCH("set_beta");
+}
+
+static int sample_per_impl(mx_replay* r, int32_t B, double beta, void* stream);
 extern "C" int mx_replay_sample_per(mx_replay* r, int32_t B, double beta, void* stream) {
+  if (!(beta > 0)) { mx_set_error("sample_per: beta must be > 0"); return 1; }                                                                  // rec_buffer.py:289
+  return sample_per_impl(r, B, beta, stream);
+}
+int mx_replay_sample_per_state_beta(mx_replay* r, int32_t B, void* stream) { return sample_per_impl(r, B, -1.0, stream); }
+static int sample_per_impl(mx_replay* r, int32_t B, double beta, void* stream) {
   if (check_sample(r, B)) return 1;
   if (!r->cfg.use_per) { mx_set_error("sample_per: replay created without use_per"); return 1; }
   if (!(r->filled > B)) { mx_set_error("Cannot sample with no completed episodes in the buffer! (len %d <= batch %d)", r->filled, B); return 1; }  // rec_buffer.py:287-288
-  if (!(beta > 0)) { mx_set_error("sample_per: beta must be > 0"); return 1; }                                                                  // rec_buffer.py:289
   cudaStream_t s = (cudaStream_t)stream;
   DrawArgs d;
   memset(&d, 0, sizeof(d));

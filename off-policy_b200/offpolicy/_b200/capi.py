@@ -37,7 +37,7 @@ class Episodes(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "share_obs", "acts", "rewards", "dones", "dones_env", "avail")]
 
 
-ABI_VERSION = 2        # MX_ABI_VERSION of include/marl_b200.h the struct mirrors below correspond to
+ABI_VERSION = 3        # MX_ABI_VERSION of include/marl_b200.h the struct mirrors below correspond to
 
 
 class QmixCfg(C.Structure):
@@ -103,6 +103,7 @@ def _declare(lib):
         "mx_replay_gather": (C.c_int, [vp, vp, i32, vp]),
         "mx_replay_gather_host": (C.c_int, [vp, vp, i32, vp]),
         "mx_replay_sample_per": (C.c_int, [vp, i32, dbl, vp]),
+        "mx_replay_set_beta": (C.c_int, [vp, dbl, vp]),
         "mx_replay_update_priorities": (C.c_int, [vp, vp, vp, vp, vp, i32, vp]),
         "mx_replay_batch": (C.c_int, [vp, i32, C.POINTER(Batch)]),
         "mx_qmix_param_layout": (C.c_int, [C.POINTER(QmixCfg), C.POINTER(ParamEntry), i32, C.POINTER(i64)]),

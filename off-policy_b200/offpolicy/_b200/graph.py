@@ -33,8 +33,14 @@ class StepGraph(object):
         self.handle = g
         self.num_kernels = int(lib.mx_graph_num_kernels(g))
         self._keep = (buffer, trainer)
+        self._per, self._rep, self._beta = per, pb, float(beta)
 
-    def launch(self):
+    def launch(self, beta=None):
+        """`beta`: PER importance-sampling exponent of this step (the runner anneals it every step, base_runner.py:159-160); it lives
+        in a device scalar the captured draw reads, so changing it costs one tiny launch and no re-capture."""
+        if beta is not None and self._per and float(beta) != self._beta:
+            capi.check(capi.lib().mx_replay_set_beta(self._rep.handle, float(beta), self._sp))
+            self._beta = float(beta)
         capi.check(capi.lib().mx_graph_launch(self.handle, self._sp))
 
     def synchronize(self):
@@ -94,9 +100,13 @@ class MaddpgStepGraph(object):
             self.graphs[upd] = g
         self.num_kernels = {u: int(lib.mx_graph_num_kernels(g)) for u, g in self.graphs.items()}
         self._keep = (buffer, trainer)
+        self._per, self._rep, self._beta = per, pb, float(beta)
 
-    def launch(self):
+    def launch(self, beta=None):
         tr, pol = self.trainer, self.pol
+        if beta is not None and self._per and float(beta) != self._beta:       # annealed PER exponent: device scalar (see StepGraph.launch)
+            capi.check(self.lib.mx_replay_set_beta(self._rep.handle, float(beta), self._sp))
+            self._beta = float(beta)
         T, N, Ac, B = tr.episode_length, tr.num_agents, pol.act_dim, self.B
         upd = 1 if tr.num_updates[self.p_id] % tr.actor_update_interval == 0 else 0
         k = self._slot

@@ -92,6 +92,7 @@ class M_QMix(QMix):
             capi.check(lib.mx_qmix_apply(self.handle, stream))
         else:
             capi.check(lib.mx_qmix_step(self.handle, C.byref(b), stream))
+        self._check_exchange()
         v = self._info_views
         train_info = {"loss": v[0], "grad_norm": v[1], "Q_tot": v[2]}
         new_priorities = DeviceArray(self._prio_view[:b.B]) if self.use_per else None

@@ -270,10 +270,32 @@ class QMix(object):
                 capi.check(lib.mx_qmix_apply(self.handle, stream))
             else:
                 capi.check(lib.mx_qmix_step(self.handle, C.byref(b), stream))
+        self._check_exchange()
         v = self._info_views
         train_info = {"loss": v[0], "grad_norm": v[1], "Q_tot": v[2]}                   # qmix.py:195-198 (0-dim device tensors)
         new_priorities = DeviceArray(self._prio_view[:B]) if self.use_per else None
         return train_info, new_priorities, batch[8]
+
+    def _check_exchange(self):
+        """Peer-memory exchange watchdog.  A rank that waits more than 10 s for a peer sets info[7] = -1 on the device and applies NO
+        update from then on (csrc/optim.cu, csrc/p2p.cu).  The flag is mirrored to pinned host memory after every step without a
+        synchronisation; the copy of the PREVIOUS step is inspected here, so a dead peer turns into an exception one step later
+        instead of silently diverging replicas."""
+        if not self._p2p or self.dev.type != "cuda":
+            return
+        if getattr(self, "_xchg_host", None) is None:
+            self._xchg_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self._xchg_ev = torch.cuda.Event()
+            self._xchg_pending = False
+        if self._xchg_pending and self._xchg_ev.query():
+            self._xchg_pending = False
+            if float(self._xchg_host[0]) < 0.0:
+                raise RuntimeError("marl_b200: a data-parallel peer did not deliver its gradient within 10 s; no update was applied "
+                                   "(replicas are still identical). Restart the job or set MARL_B200_P2P=0 for the NCCL exchange.")
+        if not self._xchg_pending:
+            self._xchg_host.copy_(self._info[7:8], non_blocking=True)
+            self._xchg_ev.record(torch.cuda.current_stream(self.dev))
+            self._xchg_pending = True
 
     def _step_graph(self, batch, B):
         """The learner step on a sampled batch always reads the replay's batch region, so its launch sequence is captured once

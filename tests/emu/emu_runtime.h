@@ -168,6 +168,7 @@ template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; 
 template <class T> inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
 
 template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
 inline float __expf(float x) { return expf(x); }
 inline float __logf(float x) { return logf(x); }
 inline float __fdividef(float a, float b) { return a / b; }

@@ -253,7 +253,7 @@ def check_step_graph_vs_eager(per=False, steps=3, B=32, E=300):
         buf.seed_device_rng(77)
         if mode == "eager":
             for s in range(steps):
-                smp = buf.sample(B, 0.4) if per else buf.sample(B)
+                smp = buf.sample(B, 0.4 + 0.15 * s) if per else buf.sample(B)       # annealed exponent (base_runner.py:159-160)
                 info, prio, idx = tr.train_policy_on_batch(smp, True)
                 if per:
                     buf.update_priorities(idx, prio, "policy_0")
@@ -261,7 +261,7 @@ def check_step_graph_vs_eager(per=False, steps=3, B=32, E=300):
         else:
             g = StepGraph(buf, tr, B, beta=0.4)
             for s in range(steps):
-                g.launch()
+                g.launch(beta=0.4 + 0.15 * s)          # device-resident exponent: no re-capture (mx_replay_set_beta)
             g.synchronize()
             g.close()
         outs.append((tr.theta.clone().cpu(), tr.theta_tgt.clone().cpu(), tr.adam_m.clone().cpu()))
