@@ -24,7 +24,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "off-policy_b200"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "off-policy_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -76,8 +76,8 @@ def run_maddpg(args):
     whole update replayed from captured CUDA graphs; `e2e`: the eager drop-in calls (one C call enqueues the ~40 kernels of an
     update) with a D2H loss read per step; CPU arm = the pinned oracle port."""
     from offpolicy._b200 import capi
-    import maddpg_checks as mc
-    import replay_checks as rc
+    from offpolicy._b200 import factory as mc
+    from offpolicy._b200 import factory as rc
     from oracle.maddpg import MaddpgConfig, MaddpgLearner, synth_batch_cont, synth_batch_disc, sample_gumbel
     n, o, a, sdim, T, B, td3, disc = MADDPG_WORKLOADS[args.workload]
     cfg = MaddpgConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim, td3=td3, actor_update_interval=2 if td3 else 1, gain=1.0, discrete=disc)
@@ -131,10 +131,10 @@ def run_maddpg(args):
     buf = RecReplayBuffer(info, {"policy_0": list(range(n))}, E, T, True, False, rng="device", max_batch=128)
     for c in range(0, E, 128):
         k = min(128, E - c)
-        buf.insert(k, *[rc.d(x) for x in episodes(k)], None)
+        buf.insert(k, *[rc.pd(x) for x in episodes(k)], None)
     torch.manual_seed(1)
     with contextlib.redirect_stdout(sys.stderr):        # (the drop-in classes mirror the reference's prints)
-        margs, pol, tr = mc.build(cfg, B, T)
+        margs, pol, tr = mc.build_maddpg(cfg, B, T)
     buf.seed_device_rng(1)
 
     def step():
@@ -204,9 +204,25 @@ def run_maddpg(args):
 
 
 def make_cfg(w):
-    from oracle.qmix import QmixConfig
+    from offpolicy._b200.factory import LearnerConfig
     n, o, a, s, T, B, per = WORKLOADS[w]
-    return QmixConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, use_per=per, gain=1.0), T, B
+    return LearnerConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, use_per=per, gain=1.0), T, B
+
+
+def workload_config(args, cfg, T, B, world):
+    """The `config` object of the JSON line: a function of the command line only, so both arms (--impl engine / reference) print the
+    same thing for the same workload.  Arm-specific detail goes to the `notes` key."""
+    E = args.buffer // world if world > 1 else args.buffer
+    return dict(workload=args.workload, batch_per_gpu=B, episode_len=T, n_agents=cfg.n_agents, obs_dim=cfg.obs_dim, act_dim=cfg.act_dim,
+                state_dim=cfg.state_dim, buffer_episodes_per_gpu=E, parallelism="dp%d" % world if world > 1 else "single",
+                l2="inputs gathered from a replay larger than L2; the per-step working set is L2-resident by design")
+
+
+def oracle_cfg(cfg):
+    """The CPU arm's view of the same workload: the oracle's config dataclass (same field names)."""
+    import dataclasses
+    from oracle.qmix import QmixConfig
+    return QmixConfig(**dataclasses.asdict(cfg))
 
 
 def synth_episodes(cfg, T, n, rs, avail=True):
@@ -273,6 +289,7 @@ def best_cpu_threads(cfg, T, B, E, avail=True):
 def cpu_learner_steps_per_s(cfg, T, B, E, steps, warmup, threads, avail=True):
     from oracle.qmix import QmixLearner
     from oracle.replay import UniformReplay, PrioritizedReplay
+    cfg = oracle_cfg(cfg)
     torch.set_num_threads(threads)
     rs = np.random.default_rng(0)
     N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
@@ -306,6 +323,7 @@ def torch_eager_gpu_steps_per_s(cfg, T, B, E, steps, warmup, avail=True):
     copied up per step like the reference's to_torch(...).to(device).  ~10^4 small ATen launches per step."""
     from oracle.qmix import QmixLearner
     from oracle.replay import UniformReplay, PrioritizedReplay
+    cfg = oracle_cfg(cfg)
     rs = np.random.default_rng(0)
     N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
     buf = (PrioritizedReplay(0.6, E, T, N, O, S, A) if cfg.use_per else UniformReplay(E, T, N, O, S, A, use_avail=avail, reward_norm=not avail))
@@ -335,14 +353,14 @@ def run_reference(args):
     if rank != 0:
         return
     cfg, T, B = make_cfg(args.workload)
-    E = min(args.buffer, 1024)
+    world = max(1, args.gpus)
+    E = args.buffer // world if world > 1 else args.buffer         # one rank's shard: the CPU arm is one learner on the host cores
     avail = args.workload not in NO_AVAIL
-    cores = best_cpu_threads(cfg, T, B, E, avail)
+    cores = best_cpu_threads(cfg, T, B, min(E, 256), avail)         # (thread-count probe on a small replay: the learner dominates)
     sps, ms = cpu_learner_steps_per_s(cfg, T, B, E, args.steps, args.warmup, cores, avail)
     line = dict(metric="learner grad-steps/sec", value=sps, unit="steps/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=args.workload, batch=B, episode_len=T, n_agents=cfg.n_agents, obs_dim=cfg.obs_dim, act_dim=cfg.act_dim,
-                            state_dim=cfg.state_dim, buffer_episodes=E),
+                config=workload_config(args, cfg, T, B, world),
                 cpu_baseline=dict(value=sps, unit="steps/s", cores=cores, host_cores=os.cpu_count(), kind="port",
                                   sample="%d timed learner steps (sample+train+soft update) of the same workload, replay of %d episodes" % (args.steps, E)),
                 e2e=dict(value=sps, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
@@ -375,14 +393,13 @@ def kernel_work(cfg, T, B, P):
         "k_wgrad_tc": 2.0 * M * (2 * 3 * H * H + H * H + O * H),                     # dW_ih, dW_hh, dW2, dW1
     }
     fields = 4.0 * B * (N * (T + 1) * O + (T + 1) * S + N * T * A + N * (T + 1) * A + 3 * N * T + T)
-    by = {"k_gather": 2 * fields, "k_adam": 4.0 * P * 7, "k_polyak": 4.0 * P * 3, "k_grad_reduce": 4.0 * P * 2}
+    by = {"k_gather": 2 * fields, "k_adam": 4.0 * P * 7, "k_polyak": 4.0 * P * 3, "k_grad_reduce": 4.0 * P * 2,
+          "k_optim_fused": 4.0 * P * (7 + 3)}            # Adam + fused Polyak (the per-CTA partials it also sums are an implementation cost)
     return fl, by
 
 
 def run_engine(args):
-    from offpolicy._b200 import capi
-    import qmix_checks as qc
-    import replay_checks as rc
+    from offpolicy._b200 import capi, factory
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -400,17 +417,17 @@ def run_engine(args):
     E = args.buffer // world if world > 1 else args.buffer            # replay sharded by episode across ranks
     rs = np.random.default_rng(rank)
     avail = args.workload not in NO_AVAIL
-    buf = rc.make_buffers(N, O, A, S, T, E, per_alpha=0.6 if cfg.use_per else None, norm=not avail, rng="device", max_batch=max(B, 128), avail=avail)
+    buf = factory.make_rec_buffers(N, O, A, S, T, E, per_alpha=0.6 if cfg.use_per else None, norm=not avail, rng="device", max_batch=max(B, 128), avail=avail)
 
     def wrap(ep):
-        return [rc.d(x) if x is not None else None for x in ep]
+        return [factory.pd(x) if x is not None else None for x in ep]
     for c in range(0, E, 128):
         n = min(128, E - c)
         buf.insert(n, *wrap(synth_episodes(cfg, T, n, rs, avail)))
     torch.manual_seed(1)
     np.random.seed(1)
     with contextlib.redirect_stdout(sys.stderr):        # the drop-in QMix mirrors the reference's "double Q learning will be used" print
-        args_ns, pol, tr = qc.build_trainer(cfg, B, T, debug=False)      # product configuration: no debug outputs, k_mid
+        args_ns, pol, tr = factory.build_qmix(cfg, B, T, debug=False)      # product configuration: no debug outputs, k_mid
     pb = buf.policy_buffers["policy_0"]
     buf.seed_device_rng(1 + rank)
     stream = torch.cuda.current_stream()
@@ -604,6 +621,20 @@ def run_engine(args):
     else:
         ach = by.get(top, 0.0) / (kavg[top] * 1e-3) / 1e9
         roof = dict(bound="hbm", kernel=top, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=ncu_traffic(top), peak_source=pk["src"])
+    # latency model of the serial recurrences ("give the latency model alongside the roofline fraction"): the step
+    # contains (T+1) dependent GRU steps forward (live and target nets side by side) and T backward; `floor` = the dependency chain of
+    # one step counted from the SASS (LDS -> 4 FFMA2 -> 2 shuffles -> sigmoid -> tanh -> blend -> STS -> barrier)
+    csum = clocks.summary()
+    sm_hz = 1e6 * float(csum.get("sm_mhz") or csum.get("sm_max_mhz") or 1965.0)
+    t_f, t_b = kavg.get("k_gru_fwd"), kavg.get("k_gru_bwd")
+    if t_f and t_b:
+        FLOOR_F, FLOOR_B = 330.0, 230.0
+        cyc_f, cyc_b = t_f * 1e-3 * sm_hz / (T + 1), t_b * 1e-3 * sm_hz / T
+        floor_ms = ((T + 1) * FLOOR_F + T * FLOOR_B) / sm_hz * 1e3
+        roof["latency_model"] = dict(serial_steps=2 * T + 1, t_step_cycles=dict(fwd=round(cyc_f, 1), bwd=round(cyc_b, 1)),
+                                     floor_cycles=dict(fwd=FLOOR_F, bwd=FLOOR_B), chain_ms=round(t_f + t_b, 5), floor_ms=round(floor_ms, 5),
+                                     frac=round(floor_ms / (t_f + t_b), 4), share_of_step=round((t_f + t_b) / ms_step, 4),
+                                     sm_mhz=round(sm_hz / 1e6, 1))
     gather_gbs = by["k_gather"] / (kavg.get("k_gather", 1e9) * 1e-3) / 1e9
     breakdown = {k: dict(ms=round(v, 5), share=round(v / ksum, 4)) for k, v in sorted(kavg.items(), key=lambda kv: -kv[1])}
 
@@ -625,15 +656,13 @@ def run_engine(args):
     line = dict(
         metric="learner grad-steps/sec", value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=args.workload, batch_per_gpu=B, episode_len=T, n_agents=N, obs_dim=O, act_dim=A, state_dim=S,
-                    buffer_episodes_per_gpu=E, parallelism="dp%d" % world if world > 1 else "single",
-                    grad_exchange=("one-shot all-reduce over NVLink peer memory inside the step graph (k_p2p_publish/k_p2p_reduce)" if p2p
-                                   else "NCCL all-reduce of the flat gradient buffer") if world > 1 else None,
-                    value_definition="batch-%d grad-steps/s summed over ranks (each rank samples its own shard; one flat all-reduce)" % B,
-                    l2="inputs gathered from a replay larger than L2 (%.0f MB); the per-step working set is L2-resident by design" %
-                       (pb.L.total_bytes / 1e6),
-                    step="CUDA graph: device MT19937 draw + gather + fused QMIX learner + Adam + Polyak; state-only kernels (weight images, mixer "
-                         "hypernets) on a forked graph branch beside the agent-net kernels" if (graph or tgraph) else "eager"),
+        config=workload_config(args, cfg, T, B, world),
+        notes=dict(grad_exchange=("all-reduce over NVLink peer memory INSIDE the optimiser kernel (k_optim_fused: push to every peer's slot, local rank-ordered sum)" if p2p
+                                  else "NCCL all-reduce of the flat gradient buffer") if world > 1 else None,
+                   value_definition="batch-%d grad-steps/s summed over ranks (each rank samples its own shard; one flat all-reduce)" % B,
+                   replay_mb=round(pb.L.total_bytes / 1e6, 1),
+                   step="CUDA graph: device MT19937 draw + gather + fused QMIX learner + one-launch reduce/clip/Adam/Polyak; state-only kernels (weight images, "
+                        "mixer hypernets) on a forked graph branch beside the agent-net kernels" if (graph or tgraph) else "eager"),
         e2e=dict(value=e2e_sps, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=n_e2e,
                  lagged_read_value=e2e_lagged_sps,      # same loop, each step's loss read one step late (asynchronous logging)
                  path="RecReplayBuffer.insert(1 episode, pinned) + sample(np.random.choice) + QMix.train_policy_on_batch + soft_target_updates + D2H info"),
@@ -667,9 +696,9 @@ MLP_WORKLOADS = {
 
 
 def mlp_cfg(w):
-    from oracle.qmix import QmixConfig
+    from offpolicy._b200.factory import LearnerConfig
     n, o, a, s, B, E = MLP_WORKLOADS[w]
-    return QmixConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, gain=1.0), B, E
+    return LearnerConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=s, gain=1.0), B, E
 
 
 def synth_steps(cfg, n, rs):
@@ -682,6 +711,7 @@ def synth_steps(cfg, n, rs):
 
 def mlp_cpu_steps_per_s(cfg, B, E, steps, warmup, threads):
     from oracle.mqmix import MqmixLearner, TransitionReplay
+    cfg = oracle_cfg(cfg)
     torch.set_num_threads(threads)
     rs = np.random.default_rng(0)
     buf = TransitionReplay(E, cfg.n_agents, cfg.obs_dim, cfg.state_dim, cfg.act_dim, use_avail=False, reward_norm=False)
@@ -734,7 +764,7 @@ def run_mlp(args):
     from offpolicy._b200 import capi
     from offpolicy._b200.graph import StepGraph
     from offpolicy.utils.mlp_buffer import MlpReplayBuffer
-    import mqmix_checks as mc
+    from offpolicy._b200 import factory as mc
     torch.cuda.set_device(0)
     torch.set_num_threads(1)
     lib, dev = capi.lib(), capi.device()
@@ -749,7 +779,7 @@ def run_mlp(args):
     torch.manual_seed(1)
     np.random.seed(1)
     with contextlib.redirect_stdout(sys.stderr):
-        margs, pol, tr = mc.build(cfg, B, debug=False)
+        margs, pol, tr = mc.build_mqmix(cfg, B, debug=False)
     rep = buf.policy_buffers["policy_0"].rep
     buf.seed_device_rng(1)
     sp = capi.stream_ptr

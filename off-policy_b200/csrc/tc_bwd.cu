@@ -20,7 +20,9 @@
 
 #include <string.h>
 
-int g_mx_wgrad_tc = 0;        // off until timed on a B200 (emulator-verified): mx_set_option("wgrad_tc", 1)
+int g_mx_wgrad_tc = -1;       // -1 (default): by input width -- measured on B200 (profiles/r02_option_sweeps.md): inputs <= 64 (3m, MPE) are faster on the
+                              // FFMA backward (185 vs 212 us), wider inputs (8m / 2s3z, obs 80) on k_front_bwd_tc + k_wgrad_tc (1.51 vs 1.59 ms); 0 / 1 / 2 force a mode
+static inline int wgrad_mode(int in_dim) { return g_mx_wgrad_tc >= 0 ? g_mx_wgrad_tc : (in_dim > 64 ? 2 : 0); }
 int g_mx_wgrad_tc_wide = 1;   // with wgrad_tc: input widths 65 .. 112 too (SMAC 8m / 2s3z observations are 80 wide)
 
 #define WG_ROWS 64            // rows per MMA group (the K extent of one staged tile)
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
 }
 
 bool mx_wgrad_tc_usable(const FrontBwdArgs& a) {
-  return g_mx_wgrad_tc && a.da2_out && a.da1_out && !a.skip_wgrad && a.L.in_dim <= (g_mx_wgrad_tc_wide ? WG_MAX_IN : 64) && a.M >= 1;
+  return wgrad_mode(a.L.in_dim) && a.da2_out && a.da1_out && !a.skip_wgrad && a.L.in_dim <= (g_mx_wgrad_tc_wide ? WG_MAX_IN : 64) && a.M >= 1;
 }
 
 extern int g_mx_tc_swap;
@@ -559,11 +561,11 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
 }
 
 bool mx_front_bwd_tc_usable(const FrontBwdArgs& a) {
-  return g_mx_wgrad_tc >= 2 && mx_wgrad_tc_usable(a) && a.tc_imgT && !a.dX && !a.h0 && (a.ldx & 3) == 0;
+  return wgrad_mode(a.L.in_dim) >= 2 && mx_wgrad_tc_usable(a) && a.tc_imgT && !a.dX && !a.h0 && (a.ldx & 3) == 0;
 }
 
 // k_tc_prep_weights_T -> k_front_bwd_tc -> k_wgrad_tc ; *nparts_used = the number of gradient partials written
-bool mx_tc_prep_T_wanted(int in_dim) { return g_mx_wgrad_tc >= 2 && in_dim <= (g_mx_wgrad_tc_wide ? WG_MAX_IN : 64); }
+bool mx_tc_prep_T_wanted(int in_dim) { return wgrad_mode(in_dim) >= 2 && in_dim <= (g_mx_wgrad_tc_wide ? WG_MAX_IN : 64); }
 int mx_launch_tc_prep_weights_T(const float* theta, const MxNetLayout& L, float* imgT, cudaStream_t s) {
   const int n = 3 * 4096 + 4096 + mx_round_up(L.in_dim, 16) * 64;
   MX_LAUNCH_PDL(k_tc_prep_weights_T, dim3((n + 255) / 256), dim3(256), 0, s, theta, L, imgT);

@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
 }
 
 int g_mx_front_tc = 1;        // 1: tcgen05 3xTF32 kernel (default), 0: FFMA kernel (mx_set_option("front_tc", 0))
-int g_mx_front_tc_wide = 0;   // 1: 64 < in_dim <= 128 also runs on tcgen05 (k_front_fwd_tc_wide); off until it has been timed on a B200
+int g_mx_front_tc_wide = 1;   // 1 (default): 64 < in_dim <= 128 also runs on tcgen05 (k_front_fwd_tc_wide): 8m 1.76 -> 1.59 ms, 2s3z 0.683 -> 0.647 ms (r02 sweeps)
 int g_mx_tc_swap = 0;
 extern int g_mx_wgrad_tc, g_mx_wgrad_tc_wide;      // tc_bwd.cu
 int g_mx_mixer_rm = 0;        // tuning overrides (0 = automatic): rows per thread of the mixer / backward front tiles

@@ -9,42 +9,7 @@ from qmix_checks import close
 from test_oracle_maddpg import maddpg_from_golden, maddpg_batch, actor_noise
 
 
-class Box(object):
-    def __init__(self, d, low=-1.0, high=1.0):
-        self.shape = (d,)
-        self.low = np.full(d, low, np.float32)
-        self.high = np.full(d, high, np.float32)
-
-
-class Discrete(object):
-    def __init__(self, n):
-        self.n = n
-
-
-def make_args(cfg, B):
-    return types.SimpleNamespace(
-        hidden_size=cfg.hidden, layer_N=1, use_ReLU=bool(cfg.relu), use_feature_normalization=bool(cfg.feature_norm), use_orthogonal=True, gain=cfg.gain,
-        use_conv1d=False, stacked_frames=1, use_rnn_layer=True, recurrent_N=1, prev_act_inp=False, gamma=cfg.gamma, use_per=cfg.use_per,
-        per_nu=cfg.per_nu, per_eps=cfg.per_eps, use_huber_loss=cfg.huber, huber_delta=cfg.huber_delta, max_grad_norm=cfg.max_grad_norm,
-        lr=cfg.lr, opti_eps=cfg.opti_eps, weight_decay=cfg.weight_decay, tau=cfg.tau, use_popart=False, use_value_active_masks=False,
-        use_same_share_obs=True, batch_size=B, episode_length=0, epsilon_start=1.0, epsilon_finish=0.05, epsilon_anneal_time=50000,
-        act_noise_std=0.1, target_action_noise_std=cfg.target_noise)
-
-
-def build(cfg, B, T):
-    from offpolicy._b200 import capi
-    if cfg.td3:
-        from offpolicy.algorithms.r_matd3.algorithm.rMATD3Policy import R_MATD3Policy as Policy
-        from offpolicy.algorithms.r_matd3.r_matd3 import R_MATD3 as Trainer
-    else:
-        from offpolicy.algorithms.r_maddpg.algorithm.rMADDPGPolicy import R_MADDPGPolicy as Policy
-        from offpolicy.algorithms.r_maddpg.r_maddpg import R_MADDPG as Trainer
-    args = make_args(cfg, B)
-    info = dict(obs_space=Box(cfg.obs_dim, -np.inf, np.inf), share_obs_space=Box(cfg.state_dim, -np.inf, np.inf), act_space=Discrete(cfg.act_dim) if cfg.discrete else Box(cfg.act_dim),
-                cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
-    pol = Policy({"args": args, "device": capi.device()}, info)
-    tr = Trainer(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=capi.device(), episode_length=T)
-    return args, pol, tr
+from offpolicy._b200.factory import Box, Discrete, maddpg_args as make_args, build_maddpg as build  # noqa: E402,F401
 
 
 def ref_tuple(b):

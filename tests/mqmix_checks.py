@@ -9,16 +9,8 @@ from replay_checks import Discrete
 
 
 def build(cfg, B, debug=True):
-    from offpolicy.algorithms.mqmix.algorithm.mQMixPolicy import M_QMixPolicy
-    from offpolicy.algorithms.mqmix.mqmix import M_QMix
-    from offpolicy._b200 import capi
-    args = qc.make_args(cfg, B)
-    info = dict(obs_space=[cfg.obs_dim], share_obs_space=[cfg.state_dim], act_space=Discrete(cfg.act_dim), cent_obs_dim=cfg.state_dim,
-                cent_act_dim=cfg.act_dim * cfg.n_agents)
-    pol = M_QMixPolicy({"args": args, "device": capi.device()}, info)
-    tr = M_QMix(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=capi.device())
-    capi.lib().mx_qmix_set_debug(tr.handle, 1 if debug else 0)
-    return args, pol, tr
+    from offpolicy._b200 import factory
+    return factory.build_mqmix(cfg, B, debug=debug)
 
 
 def golden_transitions(g, s):

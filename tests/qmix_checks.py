@@ -16,32 +16,15 @@ from replay_checks import Discrete
 
 
 def make_args(cfg, B, **over):
-    a = types.SimpleNamespace(
-        hidden_size=cfg.hidden, layer_N=1, use_ReLU=bool(getattr(cfg, "relu", True)), use_feature_normalization=bool(cfg.feature_norm), use_orthogonal=True, gain=cfg.gain,
-        use_conv1d=False, stacked_frames=1, use_rnn_layer=True, recurrent_N=1, prev_act_inp=bool(getattr(cfg, "prev_act_inp", False)), use_double_q=cfg.double_q,
-        hypernet_layers=cfg.hyper_layers, mixer_hidden_dim=cfg.mixer_hidden, hypernet_hidden_dim=cfg.hyper_hidden, gamma=cfg.gamma,
-        use_per=cfg.use_per, per_nu=cfg.per_nu, per_eps=cfg.per_eps, per_alpha=0.6, use_huber_loss=cfg.huber,
-        huber_delta=cfg.huber_delta, max_grad_norm=cfg.max_grad_norm, lr=cfg.lr, opti_eps=cfg.opti_eps, weight_decay=0, tau=cfg.tau,
-        use_popart=False, use_value_active_masks=False, use_same_share_obs=True, batch_size=B, episode_length=0,
-        epsilon_start=1.0, epsilon_finish=0.05, epsilon_anneal_time=50000, use_available_actions=True)
-    for k, v in over.items():
-        setattr(a, k, v)
-    return a
+    from offpolicy._b200 import factory
+    return factory.qmix_args(cfg, B, **over)
 
 
 def build_trainer(cfg, B, T, vdn=False, debug=True, **over):
-    from offpolicy.algorithms.qmix.algorithm.QMixPolicy import QMixPolicy
-    from offpolicy.algorithms.qmix.qmix import QMix
-    from offpolicy._b200 import capi
-    args = make_args(cfg, B, **over)
-    info = dict(obs_space=[cfg.obs_dim], share_obs_space=[cfg.state_dim], act_space=Discrete(cfg.act_dim),
-                cent_obs_dim=cfg.state_dim, cent_act_dim=cfg.act_dim * cfg.n_agents)
-    pol = QMixPolicy({"args": args, "device": capi.device()}, info)
-    tr = QMix(args, cfg.n_agents, {"policy_0": pol}, lambda a: "policy_0", device=capi.device(), episode_length=T, vdn=vdn)
     # debug: also materialise per-action Q values for the intermediate checks (and keep k_qhead / k_mix_core / k_qhead_bwd as
     # separate launches); debug=False runs the product configuration (the fused k_mid between the recurrences)
-    capi.lib().mx_qmix_set_debug(tr.handle, 1 if debug else 0)
-    return args, pol, tr
+    from offpolicy._b200 import factory
+    return factory.build_qmix(cfg, B, T, vdn=vdn, debug=debug, **over)
 
 
 def load_state(pol, tr, agent_sd, mixer_sd, tgt_agent_sd, tgt_mixer_sd):

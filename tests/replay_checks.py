@@ -9,28 +9,12 @@ from oracle.replay import UniformReplay, PrioritizedReplay
 REF_FIELDS = ["obs", "share_obs", "acts", "rewards", "dones", "dones_env", "avail_acts"]
 
 
-class Box(object):      # duck-typed gym.spaces.Box / Discrete for the constructor
+from offpolicy._b200.factory import Discrete, make_rec_buffers as make_buffers, pd as d  # noqa: E402,F401
+
+
+class Box(object):      # duck-typed gym.spaces.Box for the constructor
     def __init__(self, d):
         self.shape = (d,)
-
-
-class Discrete(object):
-    def __init__(self, n):
-        self.n = n
-
-
-def make_buffers(N, O, A, S, T, E, per_alpha=None, norm=False, rng="numpy", max_batch=32, avail=True):
-    from offpolicy.utils.rec_buffer import RecReplayBuffer, PrioritizedRecReplayBuffer
-    info = {"policy_0": dict(obs_space=[O], share_obs_space=[S], act_space=Discrete(A))}
-    agents = {"policy_0": list(range(N))}
-    if per_alpha is None:
-        return RecReplayBuffer(info, agents, E, T, True, avail, use_reward_normalization=norm, rng=rng, max_batch=max_batch)
-    return PrioritizedRecReplayBuffer(per_alpha, info, agents, E, T, True, avail, use_reward_normalization=norm, rng=rng,
-                                      max_batch=max_batch)
-
-
-def d(x):
-    return {"policy_0": x}
 
 
 def golden_insert(g, tag, j):

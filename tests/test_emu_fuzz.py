@@ -33,8 +33,8 @@ def test_random_shapes_and_options_vs_oracle(emu_engine, c):
         batch = synth_batch(cfg, c["B"], c["T"], seed=c["it"], avail_p=0.7, var_len=True) + (w, np.arange(c["B"]) if c["per"] else None)
         qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=2e-2)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
-        lib.mx_set_option(b"front_tc_wide", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
+        lib.mx_set_option(b"front_tc_wide", 1)
 
 
 @pytest.mark.parametrize("wgrad_tc", [0, 2], ids=["default", "tc_backward"])
@@ -66,4 +66,4 @@ def test_hundred_consecutive_steps_stay_in_lock_step_with_the_oracle(emu_engine,
         for k, v in tr.target_q_network.state_dict().items():
             assert float((v.cpu() - L.tgt_agent.state_dict()[k]).abs().max()) < lim, k
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)

@@ -111,7 +111,7 @@ def test_feature_normalization_off_matches_reference_golden(emu_engine, opts):
         qc.check_step_against(None, "qmix_small_nofn", intermediates=False, debug=False)
     finally:
         lib.mx_set_option(b"front_tc", 1)
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
 
 
 @pytest.mark.parametrize("opts", [dict(), dict(front_tc=0), dict(wgrad_tc=2)], ids=["default", "ffma_front", "tc_backward"])
@@ -125,4 +125,4 @@ def test_tanh_networks_match_reference_golden(emu_engine, opts):
         qc.check_step_against(None, "qmix_small_tanh", intermediates=True, debug="wgrad_tc" not in opts)
     finally:
         lib.mx_set_option(b"front_tc", 1)
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)

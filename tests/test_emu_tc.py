@@ -54,7 +54,7 @@ def test_wide_input_front_kernel_vs_oracle(emu_engine, obs_dim):
         # at obs 100, with the gradients themselves equal to 9e-7 of their maximum)
         qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
     finally:
-        lib.mx_set_option(b"front_tc_wide", 0)
+        lib.mx_set_option(b"front_tc_wide", 1)
 
 
 def test_wide_input_kernel_is_what_runs(emu_engine):
@@ -74,7 +74,7 @@ def test_wide_input_kernel_is_what_runs(emu_engine):
             n = lib.mx_profile_end(None, buf, 8192, ms, 128)
             names[opt] = buf.value.decode().split(";")[:n]
         finally:
-            lib.mx_set_option(b"front_tc_wide", 0)
+            lib.mx_set_option(b"front_tc_wide", 1)
     assert "k_front_fwd" in names[0] and "k_front_fwd_tc_wide" not in names[0]
     assert "k_front_fwd_tc_wide" in names[1] and "k_front_fwd" not in names[1] and "k_tc_prep_weights" in names[1]
 
@@ -90,7 +90,7 @@ def test_tensor_core_weight_gradients_match_reference_golden(emu_engine, name, m
     try:
         qc.check_step_against(None, name, intermediates=False, debug=False)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -107,7 +107,7 @@ def test_tensor_core_weight_gradients_vs_oracle(emu_engine, B, T, N, obs, mode):
         batch = synth_batch(cfg, B, T, seed=4, avail_p=0.7, var_len=True) + (None, None)
         qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -122,7 +122,7 @@ def test_tensor_core_backward_mlp_variant_matches_reference_golden(emu_engine, n
         mc.check_golden(name, debug=False)
         mc.check_vs_oracle(B=200, steps=1, avail=True)        # 1 200 rows: more 64-row chunks than the emulator's 4 "SMs"
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -142,8 +142,8 @@ def test_tensor_core_backward_wide_inputs_vs_oracle(emu_engine, obs_dim, mode):
         batch = synth_batch(cfg, B, T, seed=4, avail_p=0.7, var_len=True) + (None, None)
         qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
-        lib.mx_set_option(b"front_tc_wide", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
+        lib.mx_set_option(b"front_tc_wide", 1)
 
 
 def test_config2_full_size_all_tensor_core_kernels_vs_oracle(emu_engine):
@@ -160,7 +160,7 @@ def test_config2_full_size_all_tensor_core_kernels_vs_oracle(emu_engine):
         batch = synth_batch(cfg, 32, 60, seed=5, avail_p=0.8, var_len=True) + (None, None)
         qc.compare_step(L, pol, tr, batch, cfg, steps=1, param_tol=1e-2)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
         torch.set_num_threads(1)
 
 
@@ -176,5 +176,5 @@ def test_maddpg_updates_through_the_tensor_core_backward(emu_engine, name, mode)
     try:
         mc.check_golden(name)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
-        lib.mx_set_option(b"front_tc_wide", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
+        lib.mx_set_option(b"front_tc_wide", 1)

@@ -108,7 +108,7 @@ def test_wide_input_tcgen05_front_kernel_vs_oracle(gpu_engine, obs_dim, n_agents
         assert "k_front_fwd_tc_wide" in buf.value.decode().split(";")[:n]
         qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
     finally:
-        lib.mx_set_option(b"front_tc_wide", 0)
+        lib.mx_set_option(b"front_tc_wide", 1)
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -122,7 +122,7 @@ def test_tensor_core_weight_gradients_match_reference_golden(gpu_engine, name, m
     try:
         qc.check_step_against(None, name, intermediates=False, debug=False)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -139,7 +139,7 @@ def test_tensor_core_weight_gradients_vs_oracle(gpu_engine, B, T, N, obs, mode):
         batch = synth_batch(cfg, B, T, seed=4, avail_p=0.7, var_len=True) + (None, None)
         qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -152,7 +152,7 @@ def test_tensor_core_backward_mlp_variant(gpu_engine, mode):
         mc.check_golden("mqmix_small", debug=False)
         mc.check_vs_oracle(B=1000, steps=2, avail=True)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
 
 
 @pytest.mark.parametrize("obs_dim,n_agents,B,T,mode", [(80, 8, 8, 20, 2), (80, 5, 32, 30, 1), (128, 3, 16, 12, 2)])
@@ -169,8 +169,8 @@ def test_tensor_core_backward_wide_inputs_vs_oracle(gpu_engine, obs_dim, n_agent
         batch = synth_batch(cfg, B, T, seed=4, avail_p=0.7, var_len=True) + (None, None)
         qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
-        lib.mx_set_option(b"front_tc_wide", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
+        lib.mx_set_option(b"front_tc_wide", 1)
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -183,5 +183,5 @@ def test_maddpg_updates_through_the_tensor_core_backward(gpu_engine, name, mode)
     try:
         mc.check_golden(name)
     finally:
-        lib.mx_set_option(b"wgrad_tc", 0)
-        lib.mx_set_option(b"front_tc_wide", 0)
+        lib.mx_set_option(b"wgrad_tc", -1)
+        lib.mx_set_option(b"front_tc_wide", 1)

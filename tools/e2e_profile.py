@@ -3,12 +3,12 @@ and per-phase cost with a device sync after each phase.  Usage: python tools/e2e
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "off-policy_b200"))
 import numpy as np
 import torch
 import bench
 from offpolicy._b200 import capi
-import qmix_checks as qc
-import replay_checks as rc
+from offpolicy._b200 import factory
 
 w = sys.argv[1] if len(sys.argv) > 1 else "qmix_3m"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 200
@@ -19,11 +19,11 @@ cfg, T, B = bench.make_cfg(w)
 N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
 E = 1024
 rs = np.random.default_rng(0)
-buf = rc.make_buffers(N, O, A, S, T, E, per_alpha=0.6 if cfg.use_per else None, rng="numpy", max_batch=max(B, 128))
+buf = factory.make_rec_buffers(N, O, A, S, T, E, per_alpha=0.6 if cfg.use_per else None, rng="numpy", max_batch=max(B, 128))
 for c in range(0, E, 128):
-    buf.insert(128, *[rc.d(x) for x in bench.synth_episodes(cfg, T, 128, rs)])
+    buf.insert(128, *[factory.pd(x) for x in bench.synth_episodes(cfg, T, 128, rs)])
 torch.manual_seed(1); np.random.seed(1)
-args_ns, pol, tr = qc.build_trainer(cfg, B, T)
+args_ns, pol, tr = factory.build_qmix(cfg, B, T, debug=False)
 fresh = [bench.synth_episodes(cfg, T, 1, rs) for _ in range(8)]
 phases = ["insert", "sample", "train", "prio", "soft", "loss"]
 
@@ -33,7 +33,7 @@ def run(sync):
     t_all = time.perf_counter()
     for i in range(n):
         t = time.perf_counter()
-        buf.insert(1, *[rc.d(x) for x in fresh[i % 8]])
+        buf.insert(1, *[factory.pd(x) for x in fresh[i % 8]])
         if sync: torch.cuda.synchronize()
         t2 = time.perf_counter(); acc["insert"] += t2 - t; t = t2
         smp = buf.sample(B, 0.4, "policy_0") if cfg.use_per else buf.sample(B)
