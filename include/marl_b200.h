@@ -264,6 +264,11 @@ typedef struct mx_maddpg_cfg {
                                      actor outputs (rMADDPGPolicy.py:104-120, util.py:106-166); 0: Box(act_dim)              */
   int32_t no_feature_norm;   /* 1: --use_feature_normalization switched off: no input LayerNorm in the actor and the critic */
   int32_t use_tanh;          /* 1: --use_ReLU switched off: tanh instead of ReLU in the fc1 / fc2 blocks of both networks */
+  /* several policies (config.py:61 share_policy = False, train/train_mpe.py:139-150: one policy per agent, possibly with different
+   * observation / action spaces): every policy owns one mx_maddpg for ITS n_agents agents; the centralised critic still sees the
+   * actions of all agents.  cent_act_dim = total action width over all agents (policy_info['cent_act_dim']), act_offset = first
+   * column of this policy's agents inside it.  0 / 0 = one shared policy (cent_act_dim = n_agents * act_dim). */
+  int32_t cent_act_dim, act_offset;
 } mx_maddpg_cfg;
 /* which = 0: actor ("rnn.*", "act.action_out.*"), 1: critic ("rnn.*", "q_outs.k.*"); names = reference state_dict keys */
 int mx_maddpg_param_layout(const mx_maddpg_cfg* cfg, int32_t which, mx_param_entry* out, int32_t max_entries, int64_t* total_floats);
@@ -281,6 +286,10 @@ int mx_maddpg_step(mx_maddpg* h, const mx_batch* batch, const float* target_nois
  * update the actor; batch->avail (or NULL) masks unavailable actions to -1e10 like util.py:115,141. */
 int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* batch, const float* target_noise_dev, const float* actor_noise_dev,
                       int32_t* update_actor_out, void* stream);
+/* Several policies: r_maddpg.py:40-105 (get_update_info).  Runs src's TARGET actor over src_batch (noise as in mx_maddpg_step_ex) and
+ * writes src's columns of the two centralised action vectors (buffer actions; target actions at t+1) into dst's workspace.  Before
+ * mx_maddpg_step_ex(dst, ...) call it once per policy, dst itself included (same stream). */
+int mx_maddpg_cent_contribute(mx_maddpg* src, const mx_batch* src_batch, const float* target_noise_dev, mx_maddpg* dst, void* stream);
 /* Whole-update CUDA graph (declared with mx_graph below): [sample ->] step [-> PER write-back] [-> soft update when the actor
  * was updated, base_runner.py:250-252]; flags as for mx_graph_capture.  One graph per variant (update_actor = 1 / 0); the two
  * noise pointers are fixed device buffers the caller refills before every mx_graph_launch. */

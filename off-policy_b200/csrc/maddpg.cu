@@ -27,10 +27,15 @@ struct PackArgs {
   int ldx;
   const float* hseq;        // mode 2: live critic states [B*T][H] -> h0 rows
   float* h0;                // mode 2: [rows][H]
+  // several policies (share_policy = False): the critic sees the actions of ALL agents; this policy's N agents occupy columns
+  // [off, off + N*Ac) of the CA-wide centralised action vector, the other policies' slices come from the assembled buffers
+  int CA, off, ca_ld;
+  const float* cent_acts;   // [B][T][ca_ld] buffer actions of every agent (mx_maddpg_cent_contribute), or null: single shared policy
+  const float* cent_nacts;  // [B][T][ca_ld] target-actor actions at t+1 of every agent
 };
 
 __global__ void __launch_bounds__(256) k_pack_critic_in(PackArgs a) {
-  const int IC = a.S + a.N * a.Ac;
+  const int IC = a.S + (a.cent_acts ? a.CA : a.N * a.Ac);
   const long long rows = (long long)(a.mode == 2 ? a.N : 1) * a.B * a.T;
   const long long total = rows * a.ldx;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -43,6 +48,15 @@ __global__ void __launch_bounds__(256) k_pack_critic_in(PackArgs a) {
     float v = 0.f;
     if (c < a.S) {
       v = a.share[((size_t)b * (a.T + 1) + t + (a.mode == 1 ? 1 : 0)) * a.share_ld + c];
+    } else if (c < IC && a.cent_acts) {
+      const int j = c - a.S;                                           // column of the centralised action vector
+      const size_t cj = ((size_t)b * a.T + t) * a.ca_ld + j;
+      if (a.mode == 0) v = a.cent_acts[cj];
+      else if (a.mode == 1) v = a.cent_nacts[cj];
+      else {
+        const int jo = j - a.off;                                      // own agent i's slot is replaced by the live actor's action
+        v = (jo >= i * a.Ac && jo < (i + 1) * a.Ac) ? a.actor_out[(((size_t)b * (a.T + 1) + t) * a.N + i) * a.Ac + (jo - i * a.Ac)] : a.cent_acts[cj];
+      }
     } else if (c < IC) {
       const int n = (c - a.S) / a.Ac, k = (c - a.S) % a.Ac;
       if (a.mode == 0) v = a.acts[(((size_t)b * a.T + t) * a.N + n) * a.act_ld + k];
@@ -268,14 +282,14 @@ __global__ void __launch_bounds__(256) k_actor_loss(ActorLossArgs a) {   // ONE 
 // d(actor action of agent i at (b,t)) = dX[(i,b,t)][S + i*Ac + k]   ->   dense head gradient of the actor [M_a][Ac].
 // Discrete actors (soft != null): the action is the straight-through hard Gumbel-softmax sample, so the gradient reaches the
 // logits through the soft sample y = softmax(logits + g):  dlogit_k = y_k (d_k - sum_j d_j y_j)            (util.py:160-165)
-__global__ void __launch_bounds__(256) k_scatter_actor_grad(const float* dX, int ldx, int B, int T, int N, int S, int Ac, const float* soft, float* dact) {
+__global__ void __launch_bounds__(256) k_scatter_actor_grad(const float* dX, int ldx, int B, int T, int N, int S, int Ac, const float* soft, float* dact, int off) {
   const long long rows = (long long)B * (T + 1) * N;
   for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < rows; m += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(m % N);
     const long long bt1 = m / N;
     const int t = (int)(bt1 % (T + 1)), b = (int)(bt1 / (T + 1));
     float d[8];
-    for (int k = 0; k < Ac; ++k) d[k] = t < T ? dX[(((size_t)n * B + b) * T + t) * ldx + S + n * Ac + k] : 0.f;
+    for (int k = 0; k < Ac; ++k) d[k] = t < T ? dX[(((size_t)n * B + b) * T + t) * ldx + S + off + n * Ac + k] : 0.f;
     if (soft) {
       float dot = 0.f;
       for (int k = 0; k < Ac; ++k) dot += d[k] * soft[m * Ac + k];
@@ -338,6 +352,7 @@ struct MxMaddpgWs {
   int64_t r_x, r_h0, r_gi, r_h, r_u1, r_u2, r_st0, r_st1, r_st2, r_sto, r_gates, r_hn, r_q, r_dout, r_dh, r_dgi, r_dx;
   int64_t gpart_a, gpart_c, grad_a, grad_c, spart, info, prio, adam_ta, adam_tc, scal_c, scal_a;
   int64_t tc_da2, tc_da1, tc_imgT;      // scratch of the tensor-core backward (option wgrad_tc), shared by the critic and actor updates
+  int64_t cent_acts, cent_nacts;        // [B*T][ca_ld] centralised action vectors assembled from all policies (cent_act_dim > 0)
   int64_t total;
 };
 
@@ -354,7 +369,8 @@ struct mx_maddpg {
 };
 
 static inline int mx_imin_host(int a, int b) { return a < b ? a : b; }
-static int critic_in_dim(const mx_maddpg_cfg* c) { return c->state_dim + c->n_agents * c->act_dim; }
+static int cent_act_width(const mx_maddpg_cfg* c) { return c->cent_act_dim > 0 ? c->cent_act_dim : c->n_agents * c->act_dim; }
+static int critic_in_dim(const mx_maddpg_cfg* c) { return c->state_dim + cent_act_width(c); }
 
 static int maddpg_check(const mx_maddpg_cfg* c) {
   if (!c) { mx_set_error("null cfg"); return 1; }
@@ -362,6 +378,10 @@ static int maddpg_check(const mx_maddpg_cfg* c) {
   if (c->n_agents <= 0 || c->obs_dim <= 0 || c->act_dim <= 0 || c->state_dim <= 0 || c->episode_len <= 0 || c->max_batch <= 0) { mx_set_error("mx_maddpg: non-positive dimension"); return 1; }
   if (c->num_q < 1 || c->num_q > 4 || c->act_dim > 8) { mx_set_error("mx_maddpg: num_q must be 1..4 and act_dim <= 8"); return 1; }
   if (c->max_batch * c->episode_len > 65536) { mx_set_error("mx_maddpg: B*T too large"); return 1; }
+  if (c->cent_act_dim < 0 || c->act_offset < 0 || (c->cent_act_dim > 0 && c->act_offset + c->n_agents * c->act_dim > c->cent_act_dim)) {
+    mx_set_error("mx_maddpg: act_offset %d + n_agents*act_dim %d exceeds cent_act_dim %d", c->act_offset, c->n_agents * c->act_dim, c->cent_act_dim); return 1;
+  }
+  if (c->cent_act_dim == 0 && c->act_offset != 0) { mx_set_error("mx_maddpg: act_offset needs cent_act_dim"); return 1; }
   return 0;
 }
 
@@ -439,6 +459,10 @@ static int64_t maddpg_ws_layout(const mx_maddpg_cfg* c, int64_t Pa, int64_t Pc, 
     const int64_t Mx = Ma > Mc ? Ma : Mc;
     const size_t ia = mx_tc_imageT_floats(c->obs_dim), ic = mx_tc_imageT_floats(critic_in_dim(c));
     W->tc_da2 = tk(Mx * MX_H); W->tc_da1 = tk(Mx * MX_H); W->tc_imgT = tk((int64_t)(ia > ic ? ia : ic));
+  }
+  {
+    const int64_t ca_ld = c->cent_act_dim > 0 ? mx_round_up(c->cent_act_dim, 4) : 0;
+    W->cent_acts = tk(Mc * ca_ld); W->cent_nacts = tk(Mc * ca_ld);
   }
   W->total = o;
   return o * 4;
@@ -547,6 +571,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   const MxNetLayout& LA = h->actor;
   const MxNetLayout& LC = h->critic;
   const int hstride = MX_H + 4;
+  const bool multi = c.cent_act_dim > 0;       // several policies: the centralised action vectors were assembled by mx_maddpg_cent_contribute
 
   // ---------- A. actor: live + target over the T+1 steps ----------
   FrontFwdArgs ff;
@@ -582,6 +607,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   memset(&pk, 0, sizeof(pk));
   pk.B = B; pk.T = T; pk.N = N; pk.S = S; pk.Ac = Ac; pk.share = b->share; pk.share_ld = b->share_ld; pk.acts = b->acts; pk.act_ld = b->act_ld;
   pk.ldx = ldc;
+  if (multi) { pk.CA = c.cent_act_dim; pk.off = c.act_offset; pk.ca_ld = mx_round_up(c.cent_act_dim, 4); pk.cent_acts = ws + W.cent_acts; pk.cent_nacts = ws + W.cent_nacts; }
   pk.mode = 0; pk.x = ws + W.c_x;
   MX_LAUNCH(k_pack_critic_in, dim3(launch1d((long long)Mc * ldc)), dim3(256), 0, s, pk); MX_COUNT(); MX_MARK("k_pack_critic_in", s);
   FrontFwdArgs fc;
@@ -704,7 +730,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
     int dummy = 0;
     if (mx_launch_front_bwd(fbr, &dummy, s)) return 1;
     MX_LAUNCH(k_scatter_actor_grad, dim3(launch1d(Ma)), dim3(256), 0, s, (const float*)(ws + W.r_dx), ldc, B, T, N, S, Ac,
-              (const float*)(c.discrete ? ws + W.a_soft : nullptr), ws + W.a_dout);
+              (const float*)(c.discrete ? ws + W.a_soft : nullptr), ws + W.a_dout, multi ? c.act_offset : 0);
     MX_COUNT(); MX_MARK("k_scatter_actor_grad", s);
     // actor backward + Adam
     const int ahead_grid = mx_imin_host(mx_num_sms(), mx_ceil_div(Ma, 32));
@@ -731,6 +757,70 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
   if (update_actor_out) *update_actor_out = update_actor ? 1 : 0;
   if (h->force_update_actor < 0) h->num_updates += 1;      // (graph replays count in mx_graph_launch)
   return 0;
+}
+
+// ---- several policies (share_policy = False, scripts/train_mpe_rmaddpg.sh:14 -> train/train_mpe.py:139-150) ------------------------------
+// The reference's update of policy p (r_maddpg.py:114-331) calls get_update_info (r_maddpg.py:40-105), which walks over EVERY policy q:
+// buffer actions of q's agents, and next actions from q's TARGET actor on q's own observation sequence; concatenated over all agents
+// they form the centralised action vectors the critic of p consumes.  Here every policy owns one mx_maddpg (its agents, its obs /
+// action widths, the shared centralised observation) with cfg.cent_act_dim = total action width and cfg.act_offset = where its agents sit.
+// mx_maddpg_cent_contribute(src, src_batch, noise, dst): src's target actor over src_batch (T+1 steps, Gaussian / Gumbel noise and the
+// Discrete transforms exactly as in the single-policy step), then src's slices of the two assembled vectors are written into dst's
+// workspace.  Call it for every policy (dst = the policy about to be updated, itself included), then mx_maddpg_step_ex(dst, ...).
+__global__ void __launch_bounds__(256) k_cent_scatter(const float* __restrict__ nact, const float* __restrict__ acts, int act_ld, int B, int T, int N, int Ac,
+                                                      float* __restrict__ cent_acts, float* __restrict__ cent_nacts, int ca_ld, int off) {
+  const long long total = (long long)B * T * N * Ac;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Ac);
+    const long long r = idx / Ac;
+    const int n = (int)(r % N);
+    const long long bt = r / N;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const size_t dst = ((size_t)b * T + t) * ca_ld + off + n * Ac + k;
+    cent_acts[dst] = acts[(((size_t)b * T + t) * N + n) * act_ld + k];
+    cent_nacts[dst] = nact[(((size_t)b * (T + 1) + t + 1) * N + n) * Ac + k];          // the target actor's action at the NEXT step
+  }
+}
+
+extern "C" int mx_maddpg_cent_contribute(mx_maddpg* src, const mx_batch* b, const float* target_noise_dev, mx_maddpg* dst, void* stream) {
+  if (!src || !dst || !b) { mx_set_error("mx_maddpg_cent_contribute: null argument"); return 1; }
+  const mx_maddpg_cfg& c = src->cfg;
+  const mx_maddpg_cfg& d = dst->cfg;
+  if (c.cent_act_dim <= 0 || d.cent_act_dim != c.cent_act_dim || d.episode_len != c.episode_len) { mx_set_error("mx_maddpg_cent_contribute: both learners need the same cent_act_dim > 0 and episode length"); return 1; }
+  if (b->B <= 0 || b->B > c.max_batch || b->B > d.max_batch) { mx_set_error("mx_maddpg_cent_contribute: batch size outside [1, max_batch]"); return 1; }
+  if (!b->obs || !b->acts) { mx_set_error("mx_maddpg_cent_contribute: missing batch field"); return 1; }
+  if (c.target_noise > 0.f && !target_noise_dev) { mx_set_error("mx_maddpg_cent_contribute: MATD3 target noise expected"); return 1; }
+  cudaStream_t s = (cudaStream_t)stream;
+  float* ws = src->ws;
+  const MxMaddpgWs& W = src->W;
+  const int B = b->B, T = c.episode_len, N = c.n_agents, Ac = c.act_dim;
+  const int Ma = B * (T + 1) * N;
+  const MxNetLayout& LA = src->actor;
+  FrontFwdArgs ff;
+  memset(&ff, 0, sizeof(ff));
+  ff.X = b->obs; ff.ldx = b->obs_ld; ff.M = Ma; ff.feature_norm = c.no_feature_norm ? 0 : 1; ff.act_tanh = c.use_tanh;
+  ff.theta[0] = src->th_a_tgt; ff.L = LA; ff.gi[0] = ws + W.a_gi[1];
+  if (mx_launch_front_fwd(ff, 1, s)) return 1;
+  GruFwdArgs gf;
+  memset(&gf, 0, sizeof(gf));
+  gf.theta[0] = src->th_a_tgt; gf.whh = LA.whh; gf.bhh = LA.bhh; gf.gi[0] = ff.gi[0]; gf.hall[0] = ws + W.a_h[1]; gf.R = B * N; gf.T = T; gf.N = N;
+  if (mx_launch_gru_fwd(gf, 1, s)) return 1;
+  HeadArgs ha;
+  memset(&ha, 0, sizeof(ha));
+  ha.lno_g = LA.lno_g; ha.lno_b = LA.lno_b; ha.w = LA.wq; ha.b = LA.bq; ha.OD = Ac; ha.b_stride = 1; ha.w_stride = MX_H; ha.M = Ma;
+  ha.theta = src->th_a_tgt; ha.h = gf.hall[0]; ha.out = ws + W.a_nact; ha.noise = c.target_noise > 0.f ? target_noise_dev : nullptr;
+  MX_LAUNCH(k_head_fwd, dim3(launch1d((long long)Ma * 32)), dim3(256), 0, s, ha); MX_COUNT(); MX_MARK("k_head_fwd", s);
+  if (c.discrete) {
+    ActXformArgs ax;
+    memset(&ax, 0, sizeof(ax));
+    ax.M = Ma; ax.Ac = Ac; ax.mode = c.target_noise > 0.f ? 1 : 0; ax.logits = ws + W.a_nact; ax.out = ws + W.a_nact;
+    ax.avail = b->avail; ax.avail_ld = b->act_ld;
+    MX_LAUNCH(k_act_transform, dim3(launch1d(Ma)), dim3(256), 0, s, ax); MX_COUNT(); MX_MARK("k_act_transform", s);
+  }
+  MX_LAUNCH(k_cent_scatter, dim3(launch1d((long long)B * T * N * Ac)), dim3(256), 0, s, (const float*)(ws + W.a_nact), b->acts, b->act_ld, B, T, N, Ac,
+            dst->ws + dst->W.cent_acts, dst->ws + dst->W.cent_nacts, mx_round_up(d.cent_act_dim, 4), c.act_offset);
+  MX_COUNT(); MX_MARK("k_cent_scatter", s);
+  return MX_CHECK_LAUNCH("cent_contribute");
 }
 
 // [sample ->] shared_train_policy_on_batch [-> PER write-back] [-> soft update] as one CUDA graph.  The actor is updated only

@@ -53,7 +53,7 @@ class MaddpgCfg(C.Structure):
                                           "actor_update_interval", "use_huber", "use_per")] +
                 [(n, C.c_float) for n in ("gamma", "huber_delta", "per_nu", "per_eps", "lr", "adam_beta1", "adam_beta2", "adam_eps",
                                           "max_grad_norm", "tau", "weight_decay", "target_noise")] +
-                [("discrete", C.c_int32), ("no_feature_norm", C.c_int32), ("use_tanh", C.c_int32)])
+                [("discrete", C.c_int32), ("no_feature_norm", C.c_int32), ("use_tanh", C.c_int32), ("cent_act_dim", C.c_int32), ("act_offset", C.c_int32)])
 
 
 class ParamEntry(C.Structure):
@@ -132,6 +132,7 @@ def _declare(lib):
         "mx_maddpg_destroy": (None, [vp]),
         "mx_maddpg_step": (C.c_int, [vp, C.POINTER(Batch), vp, C.POINTER(i32), vp]),
         "mx_maddpg_step_ex": (C.c_int, [vp, C.POINTER(Batch), vp, vp, C.POINTER(i32), vp]),
+        "mx_maddpg_cent_contribute": (C.c_int, [vp, C.POINTER(Batch), vp, vp, vp]),
         "mx_maddpg_info": (vp, [vp]),
         "mx_maddpg_priorities": (vp, [vp]),
         "mx_maddpg_grad_views": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),

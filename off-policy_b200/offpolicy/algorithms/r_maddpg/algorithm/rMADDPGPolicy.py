@@ -39,7 +39,7 @@ def gumbel_softmax_hard(logits, avail=None):
 
 
 def maddpg_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, max_batch, td3, target_noise, actor_update_interval,
-                      discrete=False):
+                      discrete=False, cent_act_dim=0, act_offset=0):
     return capi.MaddpgCfg(n_agents=n_agents, obs_dim=obs_dim, act_dim=act_dim, state_dim=state_dim, hidden=args.hidden_size,
                           episode_len=episode_len, max_batch=max_batch, num_q=2 if td3 else 1, actor_update_interval=actor_update_interval,
                           use_huber=int(args.use_huber_loss), use_per=int(args.use_per), gamma=args.gamma, huber_delta=args.huber_delta,
@@ -47,7 +47,7 @@ def maddpg_cfg_struct(args, n_agents, obs_dim, act_dim, state_dim, episode_len, 
                           max_grad_norm=args.max_grad_norm, tau=args.tau, weight_decay=float(getattr(args, "weight_decay", 0) or 0),
                           target_noise=float(target_noise or 0.0), discrete=int(bool(discrete)),
                           no_feature_norm=0 if getattr(args, "use_feature_normalization", True) else 1,
-                          use_tanh=0 if getattr(args, "use_ReLU", True) else 1)
+                          use_tanh=0 if getattr(args, "use_ReLU", True) else 1, cent_act_dim=int(cent_act_dim), act_offset=int(act_offset))
 
 
 def maddpg_entries(cfg, which):
@@ -122,10 +122,11 @@ class R_MADDPGPolicy(object):
         if self.discrete and train:
             self.exploration = LinearDecay(self.args.epsilon_start, self.args.epsilon_finish, self.args.epsilon_anneal_time)   # :57-60
         self.td3, self.target_noise = bool(td3), target_noise
-        n_agents = self.central_act_dim // self.act_dim
         capi.lib()
         self.dev = capi.device()
-        cfg = maddpg_cfg_struct(self.args, n_agents, self.obs_dim, self.act_dim, self.central_obs_dim, 1, 1, td3, target_noise, 1, self.discrete)
+        # parameter layouts only: the critic's input is [cent_obs | actions of ALL agents] whatever the number of policies
+        cfg = maddpg_cfg_struct(self.args, 1, self.obs_dim, self.act_dim, self.central_obs_dim, 1, 1, td3, target_noise, 1, self.discrete,
+                                cent_act_dim=self.central_act_dim)
         self._a_entries, self.Pa = maddpg_entries(cfg, 0)
         self._c_entries, self.Pc = maddpg_entries(cfg, 1)
         z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.dev)
@@ -150,6 +151,7 @@ class R_MADDPGPolicy(object):
         self.actor_vecs[1].copy_(self.actor_vecs[0])          # rMADDPGPolicy.py:49-50
         self.critic_vecs[1].copy_(self.critic_vecs[0])
         self._trainer = None
+        self._handle = None          # this policy's mx_maddpg (created by the trainer)
 
     # -- rollout-time single step: ONE launch of k_policy_step (csrc/rollout.cu) per env step -----------------------------
     def _stepper(self):
@@ -215,7 +217,7 @@ class R_MADDPGPolicy(object):
     def soft_target_updates(self):
         if self._trainer is None:
             raise RuntimeError("soft_target_updates: no trainer attached")
-        capi.check(capi.lib().mx_maddpg_soft_update(self._trainer.handle, capi.stream_ptr()))
+        capi.check(capi.lib().mx_maddpg_soft_update(self._handle, capi.stream_ptr()))
 
     def hard_target_updates(self):
         self.actor_vecs[1].copy_(self.actor_vecs[0])

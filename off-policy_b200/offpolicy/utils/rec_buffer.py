@@ -336,6 +336,12 @@ class RecPolicyBuffer(object):
         capi.check(capi.lib().mx_replay_sample_per(self.handle, int(B), float(beta), capi.stream_ptr()))
         self.sample_serial += 1
 
+    def gather_device(self, idx_dev, B):
+        """Gather the episodes whose indices another policy's buffer has just drawn (device int64 tensor): with several policies the
+        reference draws ONE index set and applies it to every policy's store (rec_buffer.py:76-80, 291-299)."""
+        capi.check(capi.lib().mx_replay_gather(self.handle, capi.ptr(idx_dev), int(B), capi.stream_ptr()))
+        self.sample_serial += 1
+
     def batch_struct(self, B):
         b = capi.Batch()
         capi.check(capi.lib().mx_replay_batch(self.handle, int(B), C.byref(b)))
@@ -354,13 +360,15 @@ class RecPolicyBuffer(object):
     def adopt_numpy_rng(self):
         st = np.random.get_state()
         key = (C.c_uint32 * 624)(*[int(v) for v in st[1]])
+        self._np_gauss = (int(st[3]), float(st[4]))       # NumPy's cached second Gaussian of a pair: not part of the MT19937 key, handed back on export
         capi.check(capi.lib().mx_replay_set_rng_state(self.handle, key, int(st[2]), capi.stream_ptr()))
 
     def export_rng_to_numpy(self):
         key = (C.c_uint32 * 624)()
         pos = C.c_int32()
         capi.check(capi.lib().mx_replay_get_rng_state(self.handle, key, C.byref(pos), capi.stream_ptr()))
-        np.random.set_state(("MT19937", np.array(list(key), dtype=np.uint32), int(pos.value), 0, 0.0))
+        has_gauss, cached = getattr(self, "_np_gauss", (0, 0.0))
+        np.random.set_state(("MT19937", np.array(list(key), dtype=np.uint32), int(pos.value), has_gauss, cached))
 
     # -- checkpoint / resume (the reference checkpoints network weights only) -------------
     def state_dict(self):
@@ -426,8 +434,6 @@ class RecReplayBuffer(object):
                  use_reward_normalization=False, rng="numpy", max_batch=None, _per_alpha=None):
         self.policy_info = policy_info
         self.rng = rng
-        if list(policy_info.keys()) != ["policy_0"]:
-            raise NotImplementedError("B200 replay: only the shared-policy layout ('policy_0') is implemented")
         self.policy_buffers = {
             p_id: RecPolicyBuffer(buffer_size, episode_length, len(policy_agents[p_id]), policy_info[p_id]["obs_space"],
                                   policy_info[p_id]["share_obs_space"], policy_info[p_id]["act_space"], use_same_share_obs,
@@ -435,8 +441,11 @@ class RecReplayBuffer(object):
                                   per_alpha=_per_alpha or 0.0, max_batch=max_batch)
             for p_id in self.policy_info.keys()}
 
+    def _first(self):
+        return self.policy_buffers["policy_0"] if "policy_0" in self.policy_buffers else next(iter(self.policy_buffers.values()))
+
     def __len__(self):
-        return self.policy_buffers["policy_0"].filled_i
+        return self._first().filled_i                  # rec_buffer.py:54-55 (every policy's store holds the same episodes)
 
     def insert(self, num_insert_episodes, obs, share_obs, acts, rewards, dones, dones_env, avail_acts):
         idx_range = None
@@ -466,14 +475,18 @@ class RecReplayBuffer(object):
 
     def sample(self, batch_size):
         p_ids = list(self.policy_info.keys())
-        buf = self.policy_buffers["policy_0"]
+        buf = self._first()
         if self.rng == "device":
             buf.sample_device_uniform(batch_size)
+            for other in self.policy_buffers.values():      # several policies: ONE index set for every policy's store (rec_buffer.py:76-80)
+                if other is not buf:
+                    other.gather_device(buf.sampled_indices(batch_size).tensor, batch_size)
         else:
             # rec_buffer.py:76 draws np.random.choice(len, B); randint(0, len, B) is the same call underneath (same masked-rejection
             # draws from the global MT19937 stream, same int64 result: tests/test_oracle_rng.py) without choice()'s argument checks
             inds = np.random.randint(0, self.__len__(), batch_size)
-            buf.gather(inds)
+            for b in self.policy_buffers.values():
+                b.gather(inds)
         return SampledBatch(self.policy_buffers, batch_size, None, None, p_ids)
 
 
@@ -489,7 +502,7 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
     def sample(self, batch_size, beta=0, p_id=None):
         assert len(self) > batch_size, "Cannot sample with no completed episodes in the buffer!"   # rec_buffer.py:287
         assert beta > 0                                                                              # rec_buffer.py:289
-        buf = self.policy_buffers[p_id or "policy_0"]
+        buf = self.policy_buffers[p_id] if p_id else self._first()
         if self.rng != "device":
             # host draw keeps the process-global NumPy stream shared with the env (np.random.random, rec_buffer.py:274)
             buf.adopt_numpy_rng()
@@ -497,8 +510,11 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
             buf.export_rng_to_numpy()
         else:
             buf.sample_device_per(batch_size, beta)
+        for other in self.policy_buffers.values():          # the indices drawn from p_id's tree select the episodes of EVERY policy (rec_buffer.py:291-299)
+            if other is not buf:
+                other.gather_device(buf.sampled_indices(batch_size).tensor, batch_size)
         return SampledBatch(self.policy_buffers, batch_size, buf.sampled_weights(batch_size), buf.sampled_indices(batch_size),
                             list(self.policy_info.keys()))
 
     def update_priorities(self, idxes, priorities, p_id=None):
-        self.policy_buffers[p_id or "policy_0"].update_priorities(idxes, priorities)
+        (self.policy_buffers[p_id] if p_id else self._first()).update_priorities(idxes, priorities)

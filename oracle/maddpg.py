@@ -284,3 +284,119 @@ def synth_avail(cfg, B, T, seed=0):
     av = (rs.rand(cfg.n_agents, T + 1, B, cfg.act_dim) < 0.7).astype(np.float32)
     av[..., 0] = 1.0
     return av
+
+
+# =====================================================================================================================
+# several policies (share_policy = False): config.py:61, scripts/train/train_mpe.py:139-150, r_maddpg.py:40-105 + 114-331
+# =====================================================================================================================
+class MaddpgMultiLearner(object):
+    """One MaddpgLearner-like state per policy; `step(p, ...)` restates r_maddpg.py:114-331 for update_policy_id = policy p when every
+    policy controls exactly its own agents (in the reference's scripts: one agent per policy, heterogeneous obs / action widths).
+
+    specs: [(obs_dim, act_dim)] per policy (policy i controls agent i).  Batch per round: obs {p: (1,T+1,B,O_p)}, share (T+1,B,S),
+    acts {p: (1,T,B,A_p)}, rew (T,B,1), dones {p: (1,T,B,1)}, dones_env (T,B,1).  The centralised action vector concatenates the
+    policies' agents in sorted-id order (r_maddpg.py:62-105)."""
+
+    def __init__(self, specs, state_dim, base_cfg):
+        import dataclasses
+        self.specs, self.S = list(specs), state_dim
+        self.CA = sum(a for _, a in specs)
+        self.cfgs, self.actor, self.critic, self.tgt_actor, self.tgt_critic, self.actor_opt, self.critic_opt = [], [], [], [], [], [], []
+        for i, (o, a) in enumerate(specs):
+            c = dataclasses.replace(base_cfg, n_agents=1, obs_dim=o, act_dim=a, state_dim=state_dim)
+            self.cfgs.append(c)
+            actor = init_like_reference(ActorNet(c), c, 1 + i)
+            cc = dataclasses.replace(c, n_agents=1, act_dim=self.CA)            # critic input = state + all agents' actions
+            critic = init_like_reference(CriticNet(cc), c, 2 + i)
+            self.actor.append(actor); self.critic.append(critic)
+            self.tgt_actor.append(copy.deepcopy(actor)); self.tgt_critic.append(copy.deepcopy(critic))
+            kw = dict(lr=c.lr, eps=c.opti_eps, weight_decay=c.weight_decay)
+            self.actor_opt.append(torch.optim.Adam(actor.parameters(), **kw))
+            self.critic_opt.append(torch.optim.Adam(critic.parameters(), **kw))
+        self.num_updates = [0] * len(specs)
+
+    def _loss(self, cfg, e):
+        if cfg.huber:
+            d = cfg.huber_delta
+            small = (e.abs() <= d).float()
+            return small * e ** 2 / 2 + (1 - small) * d * (e.abs() - d / 2)
+        return e ** 2
+
+    def step(self, p, obs, share, acts, rew, dones, dones_env, noises=None, actor_noise=None):
+        """noises: {q: (T+1, B, A_q)} target-action draws of every policy (MATD3) or None; actor_noise: (T, B, A_p) Gumbel draws (Discrete)."""
+        cfg = self.cfgs[p]
+        t32 = lambda x: torch.as_tensor(x, dtype=torch.float32)
+        P = len(self.specs)
+        T, B = acts[0].shape[1], acts[0].shape[2]
+        s, de, r = t32(share), t32(dones_env), t32(rew)
+        curr = torch.cat([torch.zeros(1, B, 1), de[:T - 1]], 0)
+        cent_act = torch.cat([t32(acts[q][0]) for q in range(P)], dim=-1)                  # (T, B, CA)
+        update_actor = self.num_updates[p] % cfg.actor_update_interval == 0
+        info = {}
+        with torch.no_grad():                                                            # r_maddpg.py:62-105, every policy's target actor
+            nacts = []
+            for q in range(P):
+                cq = self.cfgs[q]
+                na, _ = self.tgt_actor[q](t32(obs[q][0]))
+                if cq.discrete:
+                    na = hard_gumbel_softmax(na, t32(noises[q])) if cq.td3 else onehot_of_max(na)
+                elif cq.td3:
+                    na = na + t32(noises[q])
+                nacts.append(na[1:])
+            cent_nact = torch.cat(nacts, dim=-1)                                          # (T, B, CA)
+        q_seq, _ = self.critic[p](s[:-1], cent_act)
+        with torch.no_grad():
+            h = torch.zeros(B, cfg.hidden)
+            nq = []
+            for t in range(T):
+                _, h = self.tgt_critic[p](s[t], cent_act[t], h)
+                qs, _ = self.tgt_critic[p](s[t + 1], cent_nact[t], h)
+                nq.append(torch.cat(qs, dim=-1).min(dim=-1, keepdim=True)[0])
+            nq = (1 - de) * torch.stack(nq)
+        target = (r + cfg.gamma * nq) * (1 - curr)
+        errs = [q * (1 - curr) - target for q in q_seq]
+        denom = (1 - curr).sum()
+        closs = torch.stack([self._loss(cfg, e).sum() / denom for e in errs]).sum()
+        self.critic_opt[p].zero_grad()
+        closs.backward()
+        cgn = torch.nn.utils.clip_grad_norm_(self.critic[p].parameters(), cfg.max_grad_norm)
+        self.critic_grads = {k: v.grad.clone() for k, v in self.critic[p].named_parameters() if v.grad is not None}
+        self.critic_opt[p].step()
+        info["critic_loss"], info["critic_grad_norm"] = closs.detach(), cgn.detach()
+        if update_actor:                                                                 # r_maddpg.py:232-322 with num_update_agents = 1
+            for prm in self.critic[p].parameters():
+                prm.requires_grad = False
+            a_seq, _ = self.actor[p](t32(obs[p][0])[:-1])
+            if cfg.discrete:
+                a_seq = hard_gumbel_softmax(a_seq, t32(actor_noise))
+            parts = [a_seq if q == p else t32(acts[q][0]) for q in range(P)]
+            repl = torch.cat(parts, dim=-1)
+            dm = torch.cat([torch.zeros(1, B, 1), t32(dones[p][0])[:T - 1]], 0)
+            h = torch.zeros(B, cfg.hidden)
+            qs_t = []
+            for t in range(T):
+                q, _ = self.critic[p](s[t], repl[t], h)
+                qs_t.append(q[0])
+                _, h = self.critic[p](s[t], cent_act[t], h)
+            qa = torch.stack(qs_t) * (1 - dm)
+            aloss = (-qa).sum() / (1 - dm).sum()
+            self.critic_opt[p].zero_grad()
+            self.actor_opt[p].zero_grad()
+            aloss.backward()
+            agn = torch.nn.utils.clip_grad_norm_(self.actor[p].parameters(), cfg.max_grad_norm)
+            self.actor_grads = {k: v.grad.clone() for k, v in self.actor[p].named_parameters() if v.grad is not None}
+            self.actor_opt[p].step()
+            for prm in self.critic[p].parameters():
+                prm.requires_grad = True
+            info["actor_loss"], info["actor_grad_norm"] = aloss.detach(), agn.detach()
+        info["update_actor"] = update_actor
+        self.num_updates[p] += 1
+        return info
+
+    def soft_update_all(self):
+        with torch.no_grad():
+            for p in range(len(self.specs)):
+                tau = self.cfgs[p].tau
+                for tgt, src in ((self.tgt_critic[p], self.critic[p]), (self.tgt_actor[p], self.actor[p])):
+                    for t, s in zip(tgt.parameters(), src.parameters()):
+                        t.copy_(t * (1.0 - tau) + s * tau)

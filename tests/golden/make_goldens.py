@@ -170,7 +170,7 @@ def gen_replay(name="replay_small"):
     print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
-if __name__ == "__main__" and "maddpg" not in sys.argv[1:] and "rollout" not in sys.argv[1:] and "prev_act" not in sys.argv[1:] and "mqmix" not in sys.argv[1:] and "mlp_replay" not in sys.argv[1:] and "nofn" not in sys.argv[1:] and "tanh" not in sys.argv[1:]:
+if __name__ == "__main__" and "maddpg" not in sys.argv[1:] and "rollout" not in sys.argv[1:] and "prev_act" not in sys.argv[1:] and "mqmix" not in sys.argv[1:] and "mlp_replay" not in sys.argv[1:] and "nofn" not in sys.argv[1:] and "tanh" not in sys.argv[1:] and "multi" not in sys.argv[1:]:
     torch.set_num_threads(1)
     small = QmixConfig(n_agents=3, obs_dim=30, act_dim=9, state_dim=48)
     gen_qmix("qmix_small", small)
@@ -487,3 +487,104 @@ if __name__ == "__main__" and "nofn" in sys.argv[1:]:
     from oracle.maddpg import MaddpgConfig
     gen_maddpg("matd3_disc_nofn", MaddpgConfig(act_dim=5, discrete=True, td3=True, actor_update_interval=2, feature_norm=False), flags=["--use_feature_normalization"], steps=2)
     gen_mqmix("mqmix_small_nofn", QmixConfig(n_agents=3, obs_dim=18, act_dim=5, state_dim=54, feature_norm=False), flags=["--use_feature_normalization"], steps=1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# several policies (share_policy = False; scripts/train_mpe_rmaddpg.sh:14 -> train/train_mpe.py:139-150): one policy per agent,
+# heterogeneous observation / action widths (simple_speaker_listener: speaker obs 3 / Discrete(3), listener obs 11 / Discrete(5))
+# ---------------------------------------------------------------------------------------------------------
+def gen_maddpg_multi(name, specs, state_dim, td3=False, discrete=True, B=4, T=6, rounds=2):
+    """specs: [(obs_dim, act_dim)] per agent = per policy.  One round = the runner's batch_train (base_runner.py:225-256): every policy
+    updated once from the SAME sample, then soft updates of all policies when the actor was updated."""
+    rh.import_reference()
+    sp = rh.gym_spaces()
+    algo = "rmatd3" if td3 else "rmaddpg"
+    args = rh.make_args(["--algorithm_name", algo, "--gain", "1.0", "--lr", "0.0005"])
+    if td3:
+        from offpolicy.algorithms.r_matd3.algorithm.rMATD3Policy import R_MATD3Policy as Policy
+        from offpolicy.algorithms.r_matd3.r_matd3 import R_MATD3 as Trainer
+    else:
+        from offpolicy.algorithms.r_maddpg.algorithm.rMADDPGPolicy import R_MADDPGPolicy as Policy
+        from offpolicy.algorithms.r_maddpg.r_maddpg import R_MADDPG as Trainer
+    from offpolicy.utils.util import sample_gumbel as ref_gumbel
+    torch.manual_seed(1)
+    np.random.seed(1)
+    N = len(specs)
+    CA = sum(a for _, a in specs)
+    dev = torch.device("cpu")
+    pols = {}
+    for i, (o, a) in enumerate(specs):
+        info = dict(obs_space=sp.Box(-np.inf, np.inf, (o,)), share_obs_space=sp.Box(-np.inf, np.inf, (state_dim,)),
+                    act_space=sp.Discrete(a) if discrete else sp.Box(-1.0, 1.0, (a,)), cent_obs_dim=state_dim, cent_act_dim=CA)
+        pols["policy_%d" % i] = Policy({"args": args, "device": dev}, info)
+    tr = Trainer(args, N, pols, lambda a: "policy_%d" % a, device=dev, episode_length=T)
+    out = {}
+    for i in range(N):
+        pol = pols["policy_%d" % i]
+        randomize_all(pol.actor, 21 + 10 * i); randomize_all(pol.critic, 22 + 10 * i)
+        pol.hard_target_updates()
+        randomize_all(pol.target_actor, 23 + 10 * i, scale=0.05); randomize_all(pol.target_critic, 24 + 10 * i, scale=0.05)
+        for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
+            out.update(sd_np("init.p%d.%s." % (i, tag), mod))
+    for r in range(rounds):
+        rs = np.random.RandomState(400 + r)
+        share = rs.randn(T + 1, B, state_dim).astype(np.float32)
+        length = rs.randint(T // 2, T + 1, size=B)
+        de = (np.arange(T)[:, None] >= length[None, :] - 1).astype(np.float32)[..., None]            # env done from step len-1 on
+        rew = rs.randn(T, B, 1).astype(np.float32)
+        obs, acts, dones = {}, {}, {}
+        for i, (o, a) in enumerate(specs):
+            p = "policy_%d" % i
+            obs[p] = rs.randn(1, T + 1, B, o).astype(np.float32)
+            acts[p] = (np.eye(a, dtype=np.float32)[rs.randint(0, a, (1, T, B))] if discrete else rs.uniform(-1, 1, (1, T, B, a)).astype(np.float32))
+            dones[p] = np.repeat(de[None], 1, 0).copy()
+            out["r%d.in.p%d.obs" % (r, i)], out["r%d.in.p%d.acts" % (r, i)], out["r%d.in.p%d.dones" % (r, i)] = obs[p], acts[p], dones[p]
+        out["r%d.in.share" % r], out["r%d.in.rew" % r], out["r%d.in.dones_env" % r] = share, rew, de
+        pd = lambda v: {"policy_%d" % i: v for i in range(N)}
+        batch = (obs, pd(share), acts, pd(np.repeat(rew[None], 1, 0)), dones, pd(de), pd(None), None, None)
+        upd_any = False
+        for i in range(N):
+            p = "policy_%d" % i
+            seed = 2000 + 10 * r + i
+            # replay the reference's own draws for this update (r_maddpg.py:62-105 walks the policies in id order, then the actor update)
+            torch.manual_seed(seed)
+            if td3:
+                for q, (oq, aq) in enumerate(specs):
+                    shape = (T + 1, B, aq)
+                    out["r%d.u%d.noise.p%d" % (r, i, q)] = (ref_gumbel(shape).numpy() if discrete else
+                                                             torch.empty(*shape).normal_(mean=0, std=float(args.target_action_noise_std)).numpy())
+            if discrete and tr.num_updates[p] % tr.actor_update_interval == 0:
+                out["r%d.u%d.actor_noise" % (r, i)] = ref_gumbel((T, B, specs[i][1])).numpy()
+            torch.manual_seed(seed)
+            info_t, prio, _ = tr.shared_train_policy_on_batch(p, batch)
+            pol = pols[p]
+            out["r%d.u%d.critic_loss" % (r, i)] = info_t["critic_loss"].detach().numpy()
+            out["r%d.u%d.critic_grad_norm" % (r, i)] = np.asarray(float(info_t["critic_grad_norm"]), np.float32)
+            out["r%d.u%d.update_actor" % (r, i)] = np.asarray(int(info_t["update_actor"]))
+            if info_t["update_actor"]:
+                upd_any = True
+                out["r%d.u%d.actor_loss" % (r, i)] = info_t["actor_loss"].detach().numpy()
+                out["r%d.u%d.actor_grad_norm" % (r, i)] = np.asarray(float(info_t["actor_grad_norm"]), np.float32)
+                for k, prm in pol.actor.named_parameters():
+                    if prm.grad is not None:
+                        out["r%d.u%d.grad.actor.%s" % (r, i, k)] = prm.grad.numpy().copy()
+        if upd_any:
+            for i in range(N):
+                pols["policy_%d" % i].soft_target_updates()           # base_runner.py:250-252
+    for i in range(N):
+        pol = pols["policy_%d" % i]
+        for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
+            out.update(sd_np("final.p%d.%s." % (i, tag), mod))
+    out["meta.cfg"] = np.array([N, state_dim, args.hidden_size, B, T, rounds, int(td3), int(discrete)])
+    out["meta.specs"] = np.array(specs)
+    out["meta.hparams"] = np.array([args.gamma, args.lr, args.opti_eps, args.max_grad_norm, args.tau, args.huber_delta, args.per_nu,
+                                    args.per_eps, float(args.target_action_noise_std), args.weight_decay], dtype=np.float64)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024), "critic_loss", out["r0.u0.critic_loss"])
+
+
+if __name__ == "__main__" and "multi" in sys.argv[1:]:
+    gen_maddpg_multi("maddpg_multi_disc", [(3, 3), (11, 5)], state_dim=14)                       # simple_speaker_listener shapes (train_mpe_rmaddpg.sh)
+    gen_maddpg_multi("matd3_multi_box", [(5, 2), (7, 3), (6, 2)], state_dim=18, td3=True, discrete=False, rounds=3)
+    gen_maddpg_multi("matd3_multi_disc", [(4, 3), (6, 4)], state_dim=10, td3=True, discrete=True, rounds=2)

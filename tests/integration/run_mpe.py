@@ -61,6 +61,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--runner", default="rnn", choices=["rnn", "mlp"], help="runner/rnn/mpe_runner.py (recurrent algorithms) or runner/mlp/mpe_runner.py")
+    ap.add_argument("--scenario", default="simple_spread")
+    ap.add_argument("--agents", type=int, default=3)
     a, extra = ap.parse_known_args()          # unknown flags go to the reference's own parser (config.py)
     a.extra = extra
     rh = install_shims()
@@ -95,7 +97,7 @@ def main():
     parser.add_argument("--num_landmarks", type=int, default=3)
     parser.add_argument('--num_agents', type=int, default=3)
     parser.add_argument('--use_same_share_obs', action='store_false', default=True)
-    argv = ["--env_name", "MPE", "--algorithm_name", a.algo, "--experiment_name", "b200", "--scenario_name", "simple_spread", "--num_agents", "3",
+    argv = ["--env_name", "MPE", "--algorithm_name", a.algo, "--experiment_name", "b200", "--scenario_name", a.scenario, "--num_agents", str(a.agents),
             "--num_landmarks", "3", "--seed", str(a.seed), "--episode_length", "25", "--tau", "0.005", "--lr", "7e-4",
             "--num_env_steps", str(a.steps), "--batch_size", "4" if a.runner == "rnn" else "16", "--buffer_size", "64" if a.runner == "rnn" else "512",
             "--num_random_episodes", "2", "--train_interval", "25",
@@ -110,12 +112,19 @@ def main():
         env.seed(all_args.seed)
         return env
     env = DummyVecEnv([init_env])
-    policy_info = {'policy_0': {"cent_obs_dim": get_dim_from_space(env.share_observation_space[0]), "cent_act_dim": get_cent_act_dim(env.action_space),
-                                "obs_space": env.observation_space[0], "share_obs_space": env.share_observation_space[0],
-                                "act_space": env.action_space[0]}}
+    if all_args.share_policy:
+        policy_info = {'policy_0': {"cent_obs_dim": get_dim_from_space(env.share_observation_space[0]), "cent_act_dim": get_cent_act_dim(env.action_space),
+                                    "obs_space": env.observation_space[0], "share_obs_space": env.share_observation_space[0],
+                                    "act_space": env.action_space[0]}}
+        mapping = lambda i: 'policy_0'
+    else:       # `--share_policy` is a store_false flag (config.py:61): one policy per agent, train/train_mpe.py:139-150
+        policy_info = {'policy_' + str(i): {"cent_obs_dim": get_dim_from_space(env.share_observation_space[i]), "cent_act_dim": get_cent_act_dim(env.action_space),
+                                            "obs_space": env.observation_space[i], "share_obs_space": env.share_observation_space[i],
+                                            "act_space": env.action_space[i]} for i in range(a.agents)}
+        mapping = lambda i: 'policy_' + str(i)
     from pathlib import Path
-    config = {"args": all_args, "policy_info": policy_info, "policy_mapping_fn": lambda i: 'policy_0', "env": env, "eval_env": env,
-              "num_agents": 3, "device": device, "use_same_share_obs": all_args.use_same_share_obs, "run_dir": Path(tempfile.mkdtemp())}
+    config = {"args": all_args, "policy_info": policy_info, "policy_mapping_fn": mapping, "env": env, "eval_env": env,
+              "num_agents": a.agents, "device": device, "use_same_share_obs": all_args.use_same_share_obs, "run_dir": Path(tempfile.mkdtemp())}
     stdout = sys.stdout
     sys.stdout = sys.stderr                                # the reference prints progress
     runner = MPERunner(config=config)

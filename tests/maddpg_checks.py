@@ -185,3 +185,104 @@ def check_replay_batch_equals_host_batch(T=5, B=4, E=9):
     assert outs[0][0] == outs[1][0], (outs[0][0], outs[1][0])
     for x, y in zip(outs[0][1], outs[1][1]):
         assert torch.equal(x, y)
+
+
+# ---- several policies (share_policy = False) -------------------------------------------------------------------------------------------
+def build_multi(specs, state_dim, td3, discrete, B, T, args_from):
+    """One drop-in policy per agent + ONE trainer over all of them, like train/train_mpe.py:139-150 + runner/rnn/base_runner.py:110-150."""
+    from offpolicy._b200 import capi, factory
+    if td3:
+        from offpolicy.algorithms.r_matd3.algorithm.rMATD3Policy import R_MATD3Policy as Policy
+        from offpolicy.algorithms.r_matd3.r_matd3 import R_MATD3 as Trainer
+    else:
+        from offpolicy.algorithms.r_maddpg.algorithm.rMADDPGPolicy import R_MADDPGPolicy as Policy
+        from offpolicy.algorithms.r_maddpg.r_maddpg import R_MADDPG as Trainer
+    args = factory.maddpg_args(args_from, B)
+    CA = sum(a for _, a in specs)
+    pols = {}
+    for i, (o, a) in enumerate(specs):
+        info = dict(obs_space=Box(o, -np.inf, np.inf), share_obs_space=Box(state_dim, -np.inf, np.inf), act_space=Discrete(a) if discrete else Box(a),
+                    cent_obs_dim=state_dim, cent_act_dim=CA)
+        pols["policy_%d" % i] = Policy({"args": args, "device": capi.device()}, info)
+    tr = Trainer(args, len(specs), pols, lambda a: "policy_%d" % a, device=capi.device(), episode_length=T)
+    return args, pols, tr
+
+
+def check_multi_golden(name, through_buffer=False):
+    """Engine vs the reference's own outputs for one-policy-per-agent training (tests/golden/*_multi_*.npz, make_goldens.py multi): every
+    policy updated from the same sample in id order, soft updates of all policies after a round that updated the actors.  With
+    through_buffer the episodes go through a multi-policy RecReplayBuffer (insert -> sample with fixed indices) instead of host batches."""
+    from test_oracle_maddpg import multi_from_golden, multi_round_inputs
+    g = load_golden(name)
+    L, specs, B, T, rounds, td3, disc = multi_from_golden(g)
+    N = len(specs)
+    S = int(g["meta.cfg"][1])
+    args, pols, tr = build_multi(specs, S, td3, disc, B, T, L.cfgs[0])
+    for i in range(N):
+        pol = pols["policy_%d" % i]
+        for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
+            mod.load_state_dict(sub(g, "init.p%d.%s." % (i, tag)))
+    problems = []
+    pd = lambda v: {"policy_%d" % i: v for i in range(N)}
+    lr = L.cfgs[0].lr
+    for r in range(rounds):
+        obs, share, acts, rew, dones, de = multi_round_inputs(g, r, N)
+        batch = ({"policy_%d" % i: obs[i] for i in range(N)}, pd(share), {"policy_%d" % i: acts[i] for i in range(N)}, pd(rew[None]),
+                 {"policy_%d" % i: dones[i] for i in range(N)}, pd(de), pd(None), None, None)
+        if through_buffer:
+            from offpolicy.utils.rec_buffer import RecReplayBuffer
+            info = {"policy_%d" % i: dict(obs_space=[o], share_obs_space=[S], act_space=Discrete(a) if disc else Box(a)) for i, (o, a) in enumerate(specs)}
+            buf = RecReplayBuffer(info, {"policy_%d" % i: [i] for i in range(N)}, B, T, True, False, rng="numpy", max_batch=max(B, 8))
+            ep = lambda d_: {k: np.swapaxes(v, 0, 1) if v.ndim == 4 else v for k, v in d_.items()}       # (N_p,T,B,D) -> (T,B,N_p,D) insert layout
+            buf.insert(B, ep(batch[0]), {k: np.repeat(share[:, :, None], 1, 2) for k in batch[1]}, ep(batch[2]), ep(batch[3]), ep(batch[4]), batch[5], None)
+            for pb in buf.policy_buffers.values():
+                pb.gather(np.arange(B))                    # fixed indices: the sample IS the golden batch
+            from offpolicy.utils.rec_buffer import SampledBatch
+            batch = SampledBatch(buf.policy_buffers, B, None, None, list(info.keys()))
+        upd_any = False
+        for i in range(N):
+            p = "policy_%d" % i
+            pol = pols[p]
+            noises = {q: g["r%d.u%d.noise.p%d" % (r, i, q)] for q in range(N)} if td3 else None
+            torch.manual_seed(2000 + 10 * r + i)            # the trainer draws the MATD3 / Gumbel noise from torch's CPU RNG in the reference's order
+            info_t, _, _ = tr.shared_train_policy_on_batch(p, batch)
+            ref = L.step(i, obs, share, acts, rew, dones, de, noises, g.get("r%d.u%d.actor_noise" % (r, i)))
+            ga, gc = tr.grad_views(p)
+            for key in ("critic_loss", "critic_grad_norm"):
+                e = rel_err(info_t[key].cpu(), g["r%d.u%d.%s" % (r, i, key)])
+                if e > 1e-4:
+                    problems.append("round %d policy %d %s rel err %.3e (got %r want %r)" % (r, i, key, e, float(info_t[key]), float(g["r%d.u%d.%s" % (r, i, key)])))
+            coef = min(1.0, L.cfgs[i].max_grad_norm / (float(ref["critic_grad_norm"]) + 1e-6))
+            cviews = named_views(gc, pol._c_entries)
+            for k, gr in L.critic_grads.items():
+                ok, err, lim = close(cviews[k] / gc[pol.Pc] * coef, gr, 1e-4)
+                if not ok:
+                    problems.append("round %d policy %d critic grad %s err %.3e > %.3e" % (r, i, k, err, lim))
+            assert bool(info_t["update_actor"]) == bool(int(g["r%d.u%d.update_actor" % (r, i)]))
+            if info_t["update_actor"]:
+                upd_any = True
+                for key in ("actor_loss", "actor_grad_norm"):
+                    e = rel_err(info_t[key].cpu(), g["r%d.u%d.%s" % (r, i, key)])
+                    if e > 1e-4:
+                        problems.append("round %d policy %d %s rel err %.3e (got %r want %r)" % (r, i, key, e, float(info_t[key]), float(g["r%d.u%d.%s" % (r, i, key)])))
+                coef = min(1.0, L.cfgs[i].max_grad_norm / (float(g["r%d.u%d.actor_grad_norm" % (r, i)]) + 1e-6))
+                aviews = named_views(ga, pol._a_entries)
+                for k, v in aviews.items():
+                    key = "r%d.u%d.grad.actor.%s" % (r, i, k)
+                    if key in g:
+                        ok, err, lim = close(v / ga[pol.Pa] * coef, g[key], 1e-4)
+                        if not ok:
+                            problems.append("round %d policy %d actor grad %s err %.3e > %.3e" % (r, i, k, err, lim))
+        if upd_any:
+            for i in range(N):
+                pols["policy_%d" % i].soft_target_updates()
+            L.soft_update_all()
+    for i in range(N):
+        pol = pols["policy_%d" % i]
+        for tag, mod in (("actor", pol.actor), ("critic", pol.critic), ("tgt_actor", pol.target_actor), ("tgt_critic", pol.target_critic)):
+            for k, v in mod.state_dict().items():
+                want = g["final.p%d.%s.%s" % (i, tag, k)]
+                err = np.abs(v.cpu().numpy() - want).max()
+                if err > 5e-3 * lr * rounds + 1e-7:
+                    problems.append("final p%d %s.%s err %.3e" % (i, tag, k, err))
+    assert not problems, "\n".join(problems[:40])

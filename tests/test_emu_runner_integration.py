@@ -31,6 +31,12 @@ RUNS = {
     "qmix_prev_act": ("qmix", 100, ["--prev_act_inp"], False),
     "rmaddpg": ("rmaddpg", 125, ["--actor_train_interval_step", "1", "--save_interval", "50"], True),
     "rmatd3": ("rmatd3", 125, ["--actor_train_interval_step", "1"], True),
+    # scripts/train_mpe_rmaddpg.sh passes `--share_policy` (store_false: ONE POLICY PER AGENT, train/train_mpe.py:139-150) and
+    # --use_reward_normalization.  Its scenario (simple_speaker_listener: different observation widths per agent) cannot be stepped by the
+    # reference's own DummyVecEnv under NumPy >= 1.24 (np.array of ragged observations raises, envs/env_wrappers.py), so the runner runs
+    # simple_spread with three per-agent policies; the heterogeneous shapes are pinned by the *_multi_* goldens (tests/test_emu_maddpg.py)
+    "rmaddpg_per_agent": ("rmaddpg", 125, ["--actor_train_interval_step", "1", "--share_policy", "--use_reward_normalization"], True),
+    "rmatd3_per_agent": ("rmatd3", 125, ["--actor_train_interval_step", "1", "--share_policy"], True),
     "qmix_per": ("qmix", 100, ["--use_per"], False),   # the reference's PER insert raises IndexError for 1-episode inserts (App. D-2): drop-in only
     "vdn": ("vdn", 100, [], False),          # the reference's recurrent VDN mixer is shape-broken: drop-in only
     # offpolicy/runner/rnn/smac_runner.py (scripts/train_smac_qmix.sh) on a synthetic env with the 3m interface: availability masks

@@ -185,3 +185,16 @@ def test_maddpg_updates_through_the_tensor_core_backward(gpu_engine, name, mode)
     finally:
         lib.mx_set_option(b"wgrad_tc", -1)
         lib.mx_set_option(b"front_tc_wide", 1)
+
+
+@pytest.mark.parametrize("name", ["maddpg_multi_disc", "matd3_multi_box", "matd3_multi_disc"])
+def test_per_agent_policies_match_reference_golden(gpu_engine, name):
+    """share_policy = False (scripts/train_mpe_rmaddpg.sh:14 -> train/train_mpe.py:139-150): one policy per agent with its own observation /
+    action widths; every policy's target actor feeds the centralised action vectors (mx_maddpg_cent_contribute)."""
+    import maddpg_checks as mdc
+    mdc.check_multi_golden(name)
+
+
+def test_per_agent_policies_through_the_multi_policy_buffer(gpu_engine):
+    import maddpg_checks as mdc
+    mdc.check_multi_golden("maddpg_multi_disc", through_buffer=True)

@@ -71,3 +71,57 @@ def test_oracle_gumbel_draws_match_reference_stream():
     g2 = sample_gumbel((T, n * B, a))
     assert np.array_equal(g1.numpy(), g["s0.in.noise"])
     assert np.array_equal(g2.numpy(), g["s0.in.actor_noise"])
+
+
+def multi_from_golden(g):
+    from oracle.maddpg import MaddpgConfig, MaddpgMultiLearner
+    N, S, H, B, T, rounds, td3, disc = [int(v) for v in g["meta.cfg"]]
+    specs = [tuple(int(x) for x in row) for row in g["meta.specs"]]
+    gamma, lr, eps, mgn, tau, hd, nu, peps, tn, wd = [float(v) for v in g["meta.hparams"]]
+    base = MaddpgConfig(hidden=H, gamma=gamma, lr=lr, opti_eps=eps, max_grad_norm=mgn, tau=tau, huber_delta=hd, per_nu=nu, per_eps=peps, td3=bool(td3),
+                        target_noise=tn, weight_decay=wd, actor_update_interval=2 if td3 else 1, discrete=bool(disc), gain=1.0)
+    L = MaddpgMultiLearner(specs, S, base)
+    for i in range(N):
+        for tag, mods in (("actor", L.actor), ("critic", L.critic), ("tgt_actor", L.tgt_actor), ("tgt_critic", L.tgt_critic)):
+            mods[i].load_state_dict(sub(g, "init.p%d.%s." % (i, tag)))
+    return L, specs, B, T, rounds, bool(td3), bool(disc)
+
+
+def multi_round_inputs(g, r, N):
+    obs = [g["r%d.in.p%d.obs" % (r, i)] for i in range(N)]
+    acts = [g["r%d.in.p%d.acts" % (r, i)] for i in range(N)]
+    dones = [g["r%d.in.p%d.dones" % (r, i)] for i in range(N)]
+    return obs, g["r%d.in.share" % r], acts, g["r%d.in.rew" % r], dones, g["r%d.in.dones_env" % r]
+
+
+@pytest.mark.parametrize("name", ["maddpg_multi_disc", "matd3_multi_box", "matd3_multi_disc"])
+def test_oracle_reproduces_reference_per_agent_policies(name):
+    """share_policy = False (scripts/train_mpe_rmaddpg.sh:14): one policy per agent; goldens = the unmodified reference's
+    shared_train_policy_on_batch called for every policy on one sample, then soft updates (base_runner.py:225-256)."""
+    torch.set_num_threads(1)
+    g = load_golden(name)
+    L, specs, B, T, rounds, td3, disc = multi_from_golden(g)
+    N = len(specs)
+    for r in range(rounds):
+        obs, share, acts, rew, dones, de = multi_round_inputs(g, r, N)
+        upd_any = False
+        for i in range(N):
+            noises = {q: g["r%d.u%d.noise.p%d" % (r, i, q)] for q in range(N)} if td3 else None
+            info = L.step(i, obs, share, acts, rew, dones, de, noises, g.get("r%d.u%d.actor_noise" % (r, i)))
+            assert rel_err(info["critic_loss"], g["r%d.u%d.critic_loss" % (r, i)]) < 1e-6
+            assert rel_err(info["critic_grad_norm"], g["r%d.u%d.critic_grad_norm" % (r, i)]) < 1e-5
+            assert int(info["update_actor"]) == int(g["r%d.u%d.update_actor" % (r, i)])
+            if info["update_actor"]:
+                upd_any = True
+                assert rel_err(info["actor_loss"], g["r%d.u%d.actor_loss" % (r, i)]) < 1e-5
+                assert rel_err(info["actor_grad_norm"], g["r%d.u%d.actor_grad_norm" % (r, i)]) < 1e-5
+                for k, gr in L.actor_grads.items():
+                    key = "r%d.u%d.grad.actor.%s" % (r, i, k)
+                    if key in g:
+                        assert rel_err(gr, g[key]) < 2e-5, key
+        if upd_any:
+            L.soft_update_all()
+    for i in range(N):
+        for tag, mods in (("actor", L.actor), ("critic", L.critic), ("tgt_actor", L.tgt_actor), ("tgt_critic", L.tgt_critic)):
+            for k, v in mods[i].state_dict().items():
+                assert rel_err(v, g["final.p%d.%s.%s" % (i, tag, k)]) < 5e-6, (i, tag, k)
