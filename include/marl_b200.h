@@ -38,6 +38,10 @@ typedef struct mx_qmix mx_qmix;       /* recurrent QMIX / VDN learner (QMix trai
 
 const char* mx_last_error(void);
 int mx_abi_version(void);
+/* sizeof() of a public struct by its C name ("mx_batch", "mx_replay_cfg", "mx_replay_layout", "mx_qmix_cfg", "mx_maddpg_cfg",
+ * "mx_param_entry", "mx_policy_step_args", "mx_episodes"); -1 for an unknown name.  Lets a binding written in another language verify its
+ * struct mirrors at load time. */
+int64_t mx_sizeof(const char* struct_name);
 /* 1 when built by nvcc for sm_100a, 0 for the CPU-emulated unit-test build (tests/emu; never shipped) */
 int mx_is_cuda_build(void);
 

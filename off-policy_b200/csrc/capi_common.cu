@@ -44,6 +44,14 @@ void mx_set_error(const char* fmt, ...) {
 
 extern "C" const char* mx_last_error(void) { return g_err; }
 extern "C" int mx_abi_version(void) { return MX_ABI_VERSION; }
+extern "C" int64_t mx_sizeof(const char* n) {
+  if (!n) return -1;
+#define MX_SZ(T) if (!strcmp(n, #T)) return (int64_t)sizeof(T)
+  MX_SZ(mx_batch); MX_SZ(mx_replay_cfg); MX_SZ(mx_replay_layout); MX_SZ(mx_qmix_cfg); MX_SZ(mx_maddpg_cfg); MX_SZ(mx_param_entry);
+  MX_SZ(mx_policy_step_args); MX_SZ(mx_episodes);
+#undef MX_SZ
+  return -1;
+}
 extern "C" int mx_is_cuda_build(void) { return MX_EMU ? 0 : 1; }
 extern "C" int64_t mx_launch_count(void) { return g_mx_launches; }
 

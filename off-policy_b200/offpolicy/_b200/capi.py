@@ -85,6 +85,7 @@ def _declare(lib):
     sig = {
         "mx_last_error": (C.c_char_p, []),
         "mx_abi_version": (C.c_int, []),
+        "mx_sizeof": (i64, [C.c_char_p]),
         "mx_is_cuda_build": (C.c_int, []),
         "mx_launch_count": (i64, []),
         "mx_replay_layout_query": (C.c_int, [C.POINTER(ReplayCfg), C.POINTER(ReplayLayout)]),

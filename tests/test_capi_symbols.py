@@ -67,3 +67,24 @@ def test_layout_queries_need_no_gpu():
     q.hidden = 128
     assert lib.mx_qmix_param_layout(ctypes.byref(q), None, 0, ctypes.byref(total)) < 0
     assert b"hidden_size" in lib.mx_last_error()
+
+
+def test_struct_mirrors_have_the_library_sizes():
+    """Every ctypes mirror in offpolicy/_b200/capi.py and the stub printed in INTEGRATION.md section 2 (what a maintainer copies) must
+    have sizeof() equal to the C struct's: a short struct makes the kernels read garbage strides."""
+    from offpolicy._b200 import capi
+    lib = capi.load_symbols_only()
+    for name, t in (("mx_batch", capi.Batch), ("mx_replay_cfg", capi.ReplayCfg), ("mx_replay_layout", capi.ReplayLayout), ("mx_qmix_cfg", capi.QmixCfg),
+                    ("mx_maddpg_cfg", capi.MaddpgCfg), ("mx_param_entry", capi.ParamEntry), ("mx_policy_step_args", capi.PolicyStepArgs),
+                    ("mx_episodes", capi.Episodes)):
+        assert int(lib.mx_sizeof(name.encode())) == ctypes.sizeof(t), name
+    assert int(lib.mx_sizeof(b"no_such_struct")) == -1
+    # the INTEGRATION.md stub: run its struct definitions and compare
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = md[md.index("# offpolicy/utils/b200.py"):]
+    block = block[:block.index("```")]
+    defs = block[block.index("class ReplayCfg"):block.index("assert lib.mx_abi_version()")]
+    ns = {"C": ctypes}
+    exec(defs, ns)
+    for name, cls in (("mx_replay_cfg", "ReplayCfg"), ("mx_batch", "Batch"), ("mx_replay_layout", "ReplayLayout")):
+        assert int(lib.mx_sizeof(name.encode())) == ctypes.sizeof(ns[cls]), "INTEGRATION.md stub of %s is out of date" % name
