@@ -484,6 +484,9 @@ def run_engine(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if p2p:
+        tr.ws_view("xstat").zero_()          # exchange breakdown accumulated by the optimiser kernel over the timed steps
+        torch.cuda.synchronize()
     launches0 = lib.mx_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
@@ -496,6 +499,17 @@ def run_engine(args):
     if world > 1:
         torch.distributed.all_reduce(ms_total, op=torch.distributed.ReduceOp.MAX)
     ms_step = float(ms_total) / args.steps
+    exchange = None
+    if p2p:
+        # per rank: mean us per step spent pushing the gradient to the peers (+ system fence), waiting for the last peer's flag (rank skew +
+        # NVLink latency), adding the slots; and the longest single wait
+        x = tr.ws_view("xstat").clone()
+        n = max(float(x[3]), 1.0)
+        mine = torch.tensor([float(x[0]) / n / 1e3, float(x[1]) / n / 1e3, float(x[2]) / n / 1e3, float(x[4]) / 1e3], device=dev)
+        allx = [torch.zeros_like(mine) for _ in range(world)]
+        torch.distributed.all_gather(allx, mine)
+        exchange = dict(per_rank_us=[dict(push=round(float(v[0]), 2), wait=round(float(v[1]), 2), sum=round(float(v[2]), 2), max_wait=round(float(v[3]), 1)) for v in allx],
+                        note="wait = time from this rank's push to the LAST peer's flag: the rank that arrives last waits ~the NVLink flag latency, the others wait for it")
     launches = int(lib.mx_launch_count() - launches0)
     if tgraph is not None:
         launches = kernels_per_step * args.steps
@@ -503,7 +517,7 @@ def run_engine(args):
     if args.quick:          # tuning sweeps: the device-resident number only (not a bench line)
         if rank == 0:
             emit(dict(quick=True, workload=args.workload, value=world * 1000.0 / ms_step, ms_per_step=ms_step, opts=args.opt,
-                      kernels_per_step=kernels_per_step))
+                      kernels_per_step=kernels_per_step, n_gpus=world, exchange=exchange))
             sys.stdout.flush()
         if graph is not None:
             graph.close()
@@ -676,6 +690,8 @@ def run_engine(args):
                                       sample="10 timed steps of the oracle port of the reference learner with its networks on cuda:0 (eager PyTorch, "
                                              "host-side NumPy replay + H2D per step): the reference's own `--cuda` mode on this GPU"),
         clocks=clocks.summary())
+    if exchange is not None:
+        line["exchange"] = exchange
     emit(line)
     sys.stdout.flush()
     if graph is not None:

@@ -42,6 +42,11 @@ int mx_abi_version(void);
  * "mx_param_entry", "mx_policy_step_args", "mx_episodes"); -1 for an unknown name.  Lets a binding written in another language verify its
  * struct mirrors at load time. */
 int64_t mx_sizeof(const char* struct_name);
+/* Host fences for pinned staging buffers a binding reuses: alloc once (id >= 0, -1 on error); record after enqueueing the copy that reads
+ * the buffer; wait before rewriting it (returns at once if never recorded).  Not thread-safe; at most 256 fences per process. */
+int mx_host_fence_alloc(void);
+int mx_host_fence_record(int id, void* stream);
+int mx_host_fence_wait(int id);
 /* 1 when built by nvcc for sm_100a, 0 for the CPU-emulated unit-test build (tests/emu; never shipped) */
 int mx_is_cuda_build(void);
 

@@ -278,6 +278,96 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
   mx_cp_wait<0>();
 }
 
+// ---- 128-thread variant (one row per CTA): K split over TWO lanes ---------------------------------------------------------------------------
+// thread = 2*i + q owns, for unit i, the r/z/n rows of W_hh restricted to the interleaved k-slice {8m + 4q + c : m < 8, c < 4} (3 x 32
+// weights in registers).  Half the warps of k_gru_fwd per row: on an SM that hosts two rows (192 row-CTAs on 148 SMs at the 3m shapes)
+// every scheduler sees two warps instead of four, and on the others one -- the step is a dependent chain, fewer co-resident warps means
+// less issue and LSU contention; one xor-shuffle level instead of two.  Measured against the 256-thread kernel in profiles/ (r02).
+#define GRU2_THREADS 128
+__global__ void __launch_bounds__(GRU2_THREADS, 2) k_gru_fwd2(GruFwdArgs a) {
+  __shared__ __align__(16) float h_s[2][MX_H];
+  __shared__ __align__(16) float gi_s[GRU_RING][MX_G];
+  const int net = blockIdx.y;
+  const float* __restrict__ th = net ? a.theta[1] : a.theta[0];
+  const int tid = threadIdx.x;
+  const int i = tid >> 1, q = tid & 1;
+  const int row = blockIdx.x;
+  const bool live = (net == 0) && a.gates != nullptr;
+  float2 wr[16], wz[16], wn[16];
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int k = 8 * m + 4 * q + 2 * c;
+      wr[2 * m + c] = make_float2(th[a.whh + i * MX_H + k], th[a.whh + i * MX_H + k + 1]);
+      wz[2 * m + c] = make_float2(th[a.whh + (MX_H + i) * MX_H + k], th[a.whh + (MX_H + i) * MX_H + k + 1]);
+      wn[2 * m + c] = make_float2(th[a.whh + (2 * MX_H + i) * MX_H + k], th[a.whh + (2 * MX_H + i) * MX_H + k + 1]);
+    }
+  const float br = th[a.bhh + i], bz = th[a.bhh + MX_H + i], bn = th[a.bhh + 2 * MX_H + i];
+  MX_PDL_WAIT();
+  for (int idx = tid; idx < 2 * MX_H; idx += GRU2_THREADS) (&h_s[0][0])[idx] = (a.h0 && idx < MX_H) ? a.h0[(size_t)row * MX_H + idx] : 0.f;
+  const float* gi = net ? a.gi[1] : a.gi[0];
+  float* hall = net ? a.hall[1] : a.hall[0];
+  const int T1 = a.T + 1, N = a.N;
+  const int b = row / N, n = row % N;
+  const size_t m0 = ((size_t)b * T1) * N + n;
+  // lane-uniform stores: lane 0 of a pair writes h, r, W_hn h + b_hn; lane 1 writes z, n
+  float* p1 = q == 0 ? hall + m0 * MX_H + i : (live ? a.gates + m0 * MX_G + MX_H + i : hall);
+  float* p2 = live ? a.gates + m0 * MX_G + (q == 0 ? 0 : 2 * MX_H) + i : hall;
+  float* p3 = live ? a.hn + m0 * MX_H + i : hall;
+  const bool on1 = q == 0 || live, on2 = live, on3 = live && q == 0;
+  const size_t s1 = (size_t)N * ((q == 0) ? MX_H : MX_G), s2 = (size_t)N * MX_G, s3 = (size_t)N * MX_H;
+  const bool pf_on = tid < MX_G / 4;
+  const float* pf_src = gi + m0 * MX_G + 4 * (pf_on ? tid : 0);
+  float* pf_dst = &gi_s[0][4 * (pf_on ? tid : 0)];
+  const size_t pf_stride = (size_t)N * MX_G;
+  auto prefetch = [&](int t) {
+    if (pf_on && t < T1) { mx_cp16(pf_dst + (t & (GRU_RING - 1)) * MX_G, pf_src); pf_src += pf_stride; }
+    mx_cp_commit();
+  };
+#pragma unroll
+  for (int t = 0; t < GRU_PF; ++t) prefetch(t);
+  mx_cp_wait<GRU_PF - 1>();
+  __syncthreads();
+
+  auto step = [&](const int t, const int cur) {
+    const int nxt = cur ^ 1;
+    prefetch(t + GRU_PF);
+    const float* g = &gi_s[t & (GRU_RING - 1)][0];
+    const float* hrow = &h_s[cur][0];
+    float4 hv[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) hv[m] = mx_ld4(hrow + 8 * m + 4 * q);
+    const float gr = g[i] + br, gz = g[MX_H + i] + bz, gn = g[2 * MX_H + i], hp = hrow[i];
+    float2 r0 = make_float2(0.f, 0.f), r1 = r0, z0 = r0, z1 = r0, n0 = r0, n1 = r0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const float2 lo = make_float2(hv[m].x, hv[m].y), hi = make_float2(hv[m].z, hv[m].w);
+      r0 = mx_ffma2(wr[2 * m], lo, r0); n0 = mx_ffma2(wn[2 * m], lo, n0); z0 = mx_ffma2(wz[2 * m], lo, z0);
+      r1 = mx_ffma2(wr[2 * m + 1], hi, r1); n1 = mx_ffma2(wn[2 * m + 1], hi, n1); z1 = mx_ffma2(wz[2 * m + 1], hi, z1);
+    }
+    r0 = mx_fadd2(r0, r1); n0 = mx_fadd2(n0, n1); z0 = mx_fadd2(z0, z1);
+    float pr = r0.x + r0.y, pn = n0.x + n0.y, pz = z0.x + z0.y;
+    pr += __shfl_xor_sync(0xffffffffu, pr, 1); pn += __shfl_xor_sync(0xffffffffu, pn, 1); pz += __shfl_xor_sync(0xffffffffu, pz, 1);
+    const float rg = mx_sigmoid_fast(pr + gr);
+    const float hn = pn + bn;
+    const float ng = mx_tanh_fast(fmaf(rg, hn, gn));
+    const float zg = mx_sigmoid_fast(pz + gz);
+    const float hnew = fmaf(zg, hp - ng, ng);
+    h_s[nxt][i] = hnew;                  // both lanes of the pair store the same value: one code path for every lane
+    if (on1) *p1 = q == 0 ? hnew : zg;
+    if (on2) *p2 = q == 0 ? rg : ng;
+    if (on3) *p3 = hn;
+    p1 += s1; p2 += s2; p3 += s3;
+    mx_cp_wait<GRU_PF - 1>();
+    __syncthreads();
+  };
+  int t = 0;
+  for (; t + 1 < T1; t += 2) { step(t, 0); step(t + 1, 1); }
+  if (t < T1) step(t, 0);
+  mx_cp_wait<0>();
+}
+
 // =====================================================================================================
 // Q head + action selection (one warp per row-step)
 // =====================================================================================================
@@ -468,6 +558,13 @@ int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s) {
   int rpc = 1;     // one resident CTA per SM (the kernel is register heavy): grow rows-per-CTA until the grid fits one wave
   while (rpc < 4 && mx_ceil_div(a.R, rpc) * nets > 2 * sms) rpc *= 2;   // two CTAs fit per SM (<= 128 registers): co-resident CTAs hide each other's latencies
   if (g_mx_gru_fwd_rpc == 1 || g_mx_gru_fwd_rpc == 2 || g_mx_gru_fwd_rpc == 4) rpc = g_mx_gru_fwd_rpc;
+  // few rows (every row-CTA resident at once, at most a handful per SM): the 128-thread kernel
+  if (g_mx_gru_threads == 128 || (g_mx_gru_threads == 0 && g_mx_gru_fwd_rpc == 0 && a.R * nets <= 2 * sms)) {
+    MX_LAUNCH_PDL(k_gru_fwd2, dim3(a.R, nets), dim3(GRU2_THREADS), 0, s, a);
+    MX_COUNT();
+    MX_MARK("k_gru_fwd", s);
+    return MX_CHECK_LAUNCH("gru_fwd2");
+  }
   dim3 grid(mx_ceil_div(a.R, rpc), nets);
   if (rpc == 1) MX_LAUNCH_PDL(k_gru_fwd<1>, grid, dim3(GRU_THREADS), 0, s, a);
   else if (rpc == 2) MX_LAUNCH_PDL(k_gru_fwd<2>, grid, dim3(GRU_THREADS), 0, s, a);

@@ -18,6 +18,7 @@ int g_mx_mixer_split = 1;      // 1: split mixer (hypernet-forward / core / hype
 int g_mx_mixer_split_rm = 0;   // rows per thread of the split mixer's tiles (0 = automatic)
 int g_mx_overlap = 1;          // state-only kernels (weight-image prep, mixer hypernets) on a forked branch beside the agent-net
                                // kernels: 1 = when the step is latency-bound (rows <= g_mx_overlap_rows), 2 = always, 0 = never
+int g_mx_gru_threads = 0;
 int g_mx_mid_fused = 1;        // 1: k_qhead + k_mix_core + k_qhead_bwd as ONE kernel (k_mid) when the split mixer is in use and no debug
                                //    outputs are requested; 0: three launches
 int g_mx_gru_fwd_rpc = 0;      // tuning overrides: sequence rows per CTA of the recurrence kernels (0 = automatic; 1, 2 or 4)
@@ -30,6 +31,7 @@ int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "overlap_rows")) { g_mx_overlap_rows = value; return 0; }
   if (!strcmp(name, "mid_fused")) { g_mx_mid_fused = value; return 0; }
   if (!strcmp(name, "optim_fused")) { g_mx_optim_fused = value; return 0; }
+  if (!strcmp(name, "gru_threads")) { g_mx_gru_threads = value; return 0; }      // 0: by size, 128 / 256: force the recurrence kernels' CTA width
   if (!strcmp(name, "gru_fwd_rpc")) { g_mx_gru_fwd_rpc = value; return 0; }
   if (!strcmp(name, "gru_bwd_rpc")) { g_mx_gru_bwd_rpc = value; return 0; }
   return -1;
@@ -44,6 +46,42 @@ void mx_set_error(const char* fmt, ...) {
 
 extern "C" const char* mx_last_error(void) { return g_err; }
 extern "C" int mx_abi_version(void) { return MX_ABI_VERSION; }
+
+// ---- host fences: "has the stream consumed this pinned staging buffer yet?" -------------------------------------------------------------
+// The drop-in buffers reuse a few pinned host blocks (insert staging, sampled-index ring); a block may be rewritten only after the copy
+// that read it has completed.  A pool of timing-less CUDA events behind three tiny calls: a torch.cuda.Event().record() costs the
+// host ~8 us per call (it resolves the current stream object first), these ~1 us.
+#define MX_MAX_FENCES 256
+#if !MX_EMU
+static cudaEvent_t g_fence[MX_MAX_FENCES];
+static unsigned char g_fence_set[MX_MAX_FENCES];
+#endif
+static int g_fence_n = 0;
+extern "C" int mx_host_fence_alloc(void) {
+  if (g_fence_n >= MX_MAX_FENCES) { mx_set_error("mx_host_fence_alloc: out of fences"); return -1; }
+#if !MX_EMU
+  if (cudaEventCreateWithFlags(&g_fence[g_fence_n], cudaEventDisableTiming) != cudaSuccess) { mx_set_error("mx_host_fence_alloc: cudaEventCreate failed"); return -1; }
+  g_fence_set[g_fence_n] = 0;
+#endif
+  return g_fence_n++;
+}
+extern "C" int mx_host_fence_record(int id, void* stream) {
+  if (id < 0 || id >= g_fence_n) { mx_set_error("mx_host_fence_record: bad fence"); return 1; }
+#if !MX_EMU
+  if (cudaEventRecord(g_fence[id], (cudaStream_t)stream) != cudaSuccess) { mx_set_error("mx_host_fence_record: cudaEventRecord failed"); return 1; }
+  g_fence_set[id] = 1;
+#else
+  (void)stream;
+#endif
+  return 0;
+}
+extern "C" int mx_host_fence_wait(int id) {       // returns once everything enqueued before the last record of this fence has completed
+  if (id < 0 || id >= g_fence_n) { mx_set_error("mx_host_fence_wait: bad fence"); return 1; }
+#if !MX_EMU
+  if (g_fence_set[id] && cudaEventSynchronize(g_fence[id]) != cudaSuccess) { mx_set_error("mx_host_fence_wait: cudaEventSynchronize failed"); return 1; }
+#endif
+  return 0;
+}
 extern "C" int64_t mx_sizeof(const char* n) {
   if (!n) return -1;
 #define MX_SZ(T) if (!strcmp(n, #T)) return (int64_t)sizeof(T)

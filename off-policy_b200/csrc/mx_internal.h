@@ -10,7 +10,7 @@ void mx_set_error(const char* fmt, ...);
 extern long long g_mx_launches;
 extern int g_mx_prof_on;
 void mx_prof_mark(const char* name, cudaStream_t s);
-extern int g_mx_mixer_split, g_mx_mixer_split_rm, g_mx_overlap, g_mx_overlap_rows, g_mx_mid_fused, g_mx_gru_fwd_rpc, g_mx_gru_bwd_rpc, g_mx_optim_fused;
+extern int g_mx_mixer_split, g_mx_mixer_split_rm, g_mx_overlap, g_mx_overlap_rows, g_mx_mid_fused, g_mx_gru_fwd_rpc, g_mx_gru_bwd_rpc, g_mx_optim_fused, g_mx_gru_threads;
 int mx_set_option_common(const char* name, int value);   // 0 when `name` was one of the build-independent options
 #define MX_COUNT() (++g_mx_launches)
 #define MX_MARK(name, s) do { if (g_mx_prof_on) mx_prof_mark((name), (s)); } while (0)
@@ -95,6 +95,7 @@ struct MxQmixWs {           // offsets in floats into the workspace
   int64_t spart;            // [npart][8] per-CTA scalar partials (denominator, loss numerator, sum Q_tot)
   int64_t adam_t;           // double[4]: step count, beta1^t, beta2^t
   int64_t normpart;         // [ceil(P/256)] per-block sums of squares of the reduced gradient numerators
+  int64_t xstat;            // float[8]: exchange breakdown accumulated by k_optim_fused (ns: push, wait, sum; launches; max wait)
   int64_t sync;             // uint32[8]: grid-barrier / exchange words of k_optim_fused (zero-initialised with the workspace)
   int64_t tcimg[2];         // pre-split TF32 weight images of the agent front layers (live, target)
   int64_t xin;              // prev_act_inp: packed network input rows [M][round_up(O + A, 4)]

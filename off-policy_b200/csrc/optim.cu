@@ -171,6 +171,11 @@ __global__ void __launch_bounds__(256) k_optim_fused(OptimArgs a) {
   }
   if (a.p2p_world > 1 && a.phase == 0) {
     const int W = a.p2p_world;
+#if !MX_EMU
+    unsigned long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0;       // exchange breakdown (scalar block, thread 0): where the data-parallel step loses time
+    const bool stamp = scalar_blk && tid == 0 && a.xstat;
+    if (stamp) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts0));
+#endif
     const size_t slot0 = (size_t)(step & 1u) * W * a.p2p_slot;
     const long long col = scalar_blk ? a.P : j;                       // the scalar block owns the four scalars behind the parameters
     const bool owner = scalar_blk ? tid == 0 : (tid < 64 && j < a.P);
@@ -191,6 +196,9 @@ __global__ void __launch_bounds__(256) k_optim_fused(OptimArgs a) {
       volatile unsigned* f = reinterpret_cast<unsigned*>(a.p2p_blocks[tid] + 2 * (size_t)W * a.p2p_slot) + a.p2p_rank;
       *f = step;
     }
+#if !MX_EMU
+    if (stamp) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts1));
+#endif
     if (tid < W) {
 #if !MX_EMU
       unsigned long long t0, t1;
@@ -203,6 +211,9 @@ __global__ void __launch_bounds__(256) k_optim_fused(OptimArgs a) {
 #endif
     }
     __syncthreads();
+#if !MX_EMU
+    if (stamp) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts2));
+#endif
     if (owner) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int p = 0; p < W; ++p) {      // rank order on every rank: bit-identical sums everywhere
@@ -212,6 +223,14 @@ __global__ void __launch_bounds__(256) k_optim_fused(OptimArgs a) {
       mx_st4(a.grad + col, acc);
       if (scalar_blk) sc = acc; else g = acc;
     }
+#if !MX_EMU
+    if (stamp) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts3));
+      const float w = (float)(ts2 - ts1);
+      a.xstat[0] += (float)(ts1 - ts0); a.xstat[1] += w; a.xstat[2] += (float)(ts3 - ts2); a.xstat[3] += 1.f;
+      if (w > a.xstat[4]) a.xstat[4] = w;
+    }
+#endif
   }
   if (!scalar_blk && a.phase != 2) optim_block_sumsq(a, g, j);
   if (a.phase == 1) return;

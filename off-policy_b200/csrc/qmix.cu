@@ -155,6 +155,7 @@ static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W
   W->adam_t = tk(8);
   W->normpart = tk(mx_grad_reduce_blocks(P));
   W->sync = tk(8);
+  W->xstat = tk(8);
   W->tcimg[0] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c))); W->tcimg[1] = tk((int64_t)mx_tc_image_floats(agent_in_dim(c)));
   W->xin = tk(c->prev_act_inp ? M * mx_round_up(agent_in_dim(c), 4) : 0);
   W->da2 = tk(M * MX_H); W->da1 = tk(M * MX_H);
@@ -225,7 +226,7 @@ extern "C" int mx_qmix_ws_lookup(const mx_qmix* q, const char* name, int64_t* by
       {"st0", W.st0, M * 2}, {"st1", W.st1, M * 2}, {"st2", W.st2, M * 2}, {"sto", W.sto, M * 2}, {"gates", W.gates, M * MX_G},
       {"hn", W.hn, M * MX_H}, {"greedy", W.greedy, M}, {"q_taken", W.q_taken, E * N}, {"q_next", W.q_next, E * N}, {"qtot", W.qtot, E},
       {"qtot_next", W.qtot_next, E}, {"err", W.err, E}, {"dq_taken", W.dq_taken, E * N}, {"dh_out", W.dh_out, M * MX_H},
-      {"dgi", W.dgi, M * MX_G}, {"grad", W.grad, q->P + 8}, {"info", W.info, 8}, {"adam_t", W.adam_t, 8}, {"prio", W.prio, B}, {"gpart", W.gpart, (int64_t)q->npart * q->P},
+      {"xstat", W.xstat, 8}, {"dgi", W.dgi, M * MX_G}, {"grad", W.grad, q->P + 8}, {"info", W.info, 8}, {"adam_t", W.adam_t, 8}, {"prio", W.prio, B}, {"gpart", W.gpart, (int64_t)q->npart * q->P},
   };
   for (const Ent& e : tab)
     if (!strcmp(e.n, name)) { *byte_offset = e.off * 4; *n_elems = e.cnt; return 0; }
@@ -279,6 +280,7 @@ static OptimArgs optim_args(mx_qmix* q, int B, const int parts[4], bool after_ex
   // exchange); k_adam after an external all-reduce (NCCL / the separate p2p kernels) recomputes the norm from the summed buffer
   if (c.world_size == 1 || !after_external_allreduce) { o.normpart = ws + q->W.normpart; o.normpart_n = mx_grad_reduce_blocks(q->P); }
   o.sync = reinterpret_cast<unsigned*>(ws + q->W.sync);
+  o.xstat = ws + q->W.xstat;
   o.p2p_world = q->p2p_world; o.p2p_rank = q->p2p_rank; o.p2p_slot = mx_round_up64(q->P + 8, 64);
   for (int p = 0; p < q->p2p_world; ++p) o.p2p_blocks[p] = q->p2p_blocks[p];
   return o;

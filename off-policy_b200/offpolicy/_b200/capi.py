@@ -86,6 +86,9 @@ def _declare(lib):
         "mx_last_error": (C.c_char_p, []),
         "mx_abi_version": (C.c_int, []),
         "mx_sizeof": (i64, [C.c_char_p]),
+        "mx_host_fence_alloc": (C.c_int, []),
+        "mx_host_fence_record": (C.c_int, [C.c_int, vp]),
+        "mx_host_fence_wait": (C.c_int, [C.c_int]),
         "mx_is_cuda_build": (C.c_int, []),
         "mx_launch_count": (i64, []),
         "mx_replay_layout_query": (C.c_int, [C.POINTER(ReplayCfg), C.POINTER(ReplayLayout)]),

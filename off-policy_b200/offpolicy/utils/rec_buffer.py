@@ -233,7 +233,7 @@ class RecPolicyBuffer(object):
         i = self._stage_i
         self._stage_i ^= 1
         if self._stage_evt[i] is not None:
-            self._stage_evt[i].synchronize()
+            capi.check(capi.lib().mx_host_fence_wait(self._stage_evt[i]))
         if self._stage[i] is None or self._stage[i].numel() < nbytes:
             pin = self.dev.type == "cuda"
             self._stage[i] = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, pin_memory=pin)
@@ -284,10 +284,10 @@ class RecPolicyBuffer(object):
         first = self._first_slot
         capi.check(capi.lib().mx_replay_insert_packed_async(self.handle, C.c_void_p(stage.data_ptr()), total, n_ep, C.byref(first),
                                                             capi.stream_ptr()))
-        if self.dev.type == "cuda":
-            evt = self._stage_evt[si] or torch.cuda.Event()
-            evt.record()
-            self._stage_evt[si] = evt
+        if self.dev.type == "cuda":           # the staging block may be rewritten once this copy has been consumed (library-side event: ~1 us)
+            if self._stage_evt[si] is None:
+                self._stage_evt[si] = capi.lib().mx_host_fence_alloc()
+            capi.check(capi.lib().mx_host_fence_record(self._stage_evt[si], capi.stream_ptr()))
         return (first.value + np.arange(n_ep)) % self.buffer_size
 
     # -- sampling -----------------------------------------------------------------------------------
@@ -316,13 +316,14 @@ class RecPolicyBuffer(object):
                 self._idx_ring_evt = [None] * 4
             k = self._idx_k
             self._idx_k = (k + 1) & 3
+            lib, sp = capi.lib(), capi.stream_ptr()
             if self._idx_ring_evt[k] is not None:
-                self._idx_ring_evt[k].synchronize()
+                capi.check(lib.mx_host_fence_wait(self._idx_ring_evt[k]))
+            else:
+                self._idx_ring_evt[k] = lib.mx_host_fence_alloc()
             self._idx_ring_np[k][:B] = inds
-            capi.check(capi.lib().mx_replay_gather_host(self.handle, self._idx_ring_ptr[k], B, capi.stream_ptr()))
-            evt = self._idx_ring_evt[k] or torch.cuda.Event()
-            evt.record()
-            self._idx_ring_evt[k] = evt
+            capi.check(lib.mx_replay_gather_host(self.handle, self._idx_ring_ptr[k], B, sp))
+            capi.check(lib.mx_host_fence_record(self._idx_ring_evt[k], sp))
         else:
             dev = self.upload_indices(inds)
             capi.check(capi.lib().mx_replay_gather(self.handle, capi.ptr(dev), B, capi.stream_ptr()))

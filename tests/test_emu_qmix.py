@@ -126,3 +126,28 @@ def test_tanh_networks_match_reference_golden(emu_engine, opts):
     finally:
         lib.mx_set_option(b"front_tc", 1)
         lib.mx_set_option(b"wgrad_tc", -1)
+
+
+@pytest.mark.parametrize("threads", [128, 256])
+@pytest.mark.parametrize("name,debug", [("qmix_small", True), ("qmix_small", False), ("qmix_5ag", False), ("qmix_small_per", False)])
+def test_recurrence_kernel_variants_match_reference_golden(emu_engine, name, debug, threads):
+    """Both CTA widths of the GRU recurrences (option gru_threads: the 128-thread kernels k_gru_fwd2 / k_gru_bwd2 are picked when all rows
+    are resident at once, the 256-thread ones otherwise) against the reference goldens, intermediates included."""
+    lib = emu_engine.lib()
+    lib.mx_set_option(b"gru_threads", threads)
+    try:
+        qc.check_step_against(None, name, intermediates=True, debug=debug)
+    finally:
+        lib.mx_set_option(b"gru_threads", 0)
+
+
+@pytest.mark.parametrize("name", ["maddpg_box", "matd3_disc_avail"])
+def test_recurrence_kernel_128_threads_maddpg(emu_engine, name):
+    """R-MADDPG uses the recurrences with an initial state (branch steps, h0) and T1 != T + 1: the 128-thread kernels on those paths."""
+    import maddpg_checks as mdc
+    lib = emu_engine.lib()
+    lib.mx_set_option(b"gru_threads", 128)
+    try:
+        mdc.check_golden(name)
+    finally:
+        lib.mx_set_option(b"gru_threads", 0)
