@@ -1,0 +1,196 @@
+// Episode gather on the TMA unit (rec_buffer.py:192-240: RecPolicyBuffer.sample_inds -- B sampled episodes, every field).
+//
+// The replay is episode-major: one episode's slice of a field is ONE contiguous 16-byte-aligned run, so sampling
+// B episodes is B straight copies per field.  Each field is described to the TMA unit twice as a 2-D tensor [rows][episode words]:
+// the store (`capacity` rows) and the batch region (`max_batch` rows).  A copy is a tile load of 256 words at (x, episode index) into
+// shared memory, completion signalled on an mbarrier by byte count, followed by a tile store to (x, batch row); the last box of a row
+// is clipped by the tensor bounds.  One elected lane per warp runs a four-stage pipeline (two loads in flight ahead of the store being
+// issued); no thread touches the data except for the reward normalisation ((r - mean) / std on the rewards field, rec_buffer.py:221-223),
+// which the warp applies in shared memory between the load and the store.  The kernel issues UTMALDG / UTMASTG only: address
+// generation, bounds handling and the 128-byte transactions are the copy engine's.
+#include <string.h>
+
+#include "mx_internal.h"
+#include "mx_kernels.h"
+
+#if !MX_EMU
+#include <cuda.h>
+
+#define GT_WARPS 4
+#define GT_STAGES 4
+#define GT_AHEAD 2
+#define GT_BOX 256            // 32-bit words per box (the TMA limit per dimension)
+
+struct GatherTmaMaps {
+  CUtensorMap src[8];
+  CUtensorMap dst[8];
+};
+struct GatherTmaArgs {
+  int nf, B, rew_field;
+  int cum[9];                  // boxes per episode before field f (cum[nf] = boxes per episode)
+  const long long* idx;        // [B] sampled episode indices
+  const MxReplayState* state;
+};
+
+__device__ __forceinline__ uint32_t gt_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(GT_WARPS * 32) k_gather_tma(const __grid_constant__ GatherTmaMaps maps, GatherTmaArgs a) {
+  __shared__ __align__(128) float stage[GT_WARPS][GT_STAGES][GT_BOX];
+  __shared__ __align__(8) unsigned long long bars[GT_WARPS][GT_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    for (int s = 0; s < GT_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gt_smem(&bars[warp][s])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  MX_PDL_WAIT();
+  const int per_ep = a.cum[a.nf];
+  const long long total = (long long)per_ep * a.B;
+  const long long first = (long long)blockIdx.x * GT_WARPS + warp, stride = (long long)gridDim.x * GT_WARPS;
+  const int n_my = first < total ? (int)((total - first + stride - 1) / stride) : 0;
+  float mean = 0.f, stdv = 1.f;
+  if (a.rew_field >= 0) { mean = (float)a.state->reward_mean; stdv = (float)a.state->reward_std; }
+
+  auto decode = [&](int k, int& f, int& x, int& b) {
+    const long long item = first + (long long)k * stride;
+    b = (int)(item / per_ep);
+    const int rem = (int)(item - (long long)b * per_ep);
+    f = 0;
+    while (f + 1 < a.nf && rem >= a.cum[f + 1]) ++f;
+    x = (rem - a.cum[f]) * GT_BOX;
+  };
+  auto load = [&](int k) {          // lane 0 only
+    int f, x, b;
+    decode(k, f, x, b);
+    const int e = (int)a.idx[b];
+    const uint32_t bar = gt_smem(&bars[warp][k % GT_STAGES]), dst = gt_smem(&stage[warp][k % GT_STAGES][0]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(GT_BOX * 4) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(&maps.src[f]), "r"(x), "r"(e), "r"(bar)
+                 : "memory");
+  };
+  if (lane == 0)
+    for (int k = 0; k < GT_AHEAD && k < n_my; ++k) load(k);
+  for (int k = 0; k < n_my; ++k) {
+    if (lane == 0 && k + GT_AHEAD < n_my) {
+      // the stage of item k + AHEAD was last used by item k + AHEAD - STAGES: its store must have finished READING shared memory.
+      // Stores committed so far: items 0 .. k-1; allowing STAGES - AHEAD - 1 pending groups leaves exactly that one complete.
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(GT_STAGES - GT_AHEAD - 1) : "memory");
+      load(k + GT_AHEAD);
+    }
+    int f, x, b;
+    decode(k, f, x, b);
+    const uint32_t bar = gt_smem(&bars[warp][k % GT_STAGES]);
+    const uint32_t parity = (uint32_t)((k / GT_STAGES) & 1);
+    const bool transform = f == a.rew_field;           // warp-uniform
+    if (lane == 0 || transform) {
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+    if (transform) {
+      float* sbuf = &stage[warp][k % GT_STAGES][0];
+      for (int i = lane; i < GT_BOX; i += 32) sbuf[i] = (sbuf[i] - mean) / stdv;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes before the async-proxy (TMA) read
+      __syncwarp();
+    }
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&maps.dst[f]),
+                   "r"(gt_smem(&stage[warp][k % GT_STAGES][0])), "r"(x), "r"(b)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    __syncwarp();        // the other lanes never run ahead of the elected one (a lane a full ring ahead would misread the barrier parity)
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static int tried = 0;
+  if (!tried) {
+    tried = 1;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+struct MxGatherTma {
+  GatherTmaMaps maps;
+  GatherTmaArgs args;
+};
+
+static bool encode_rows(EncodeTiledFn fn, CUtensorMap* m, void* base, long long rows, long long row_words) {
+  const cuuint64_t dims[2] = {(cuuint64_t)row_words, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)row_words * 4};
+  const cuuint32_t box[2] = {GT_BOX, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Tensor maps of every field of a replay (built once at mx_replay_create).  Returns null when the driver entry point is missing or a
+// field cannot be described (the vectorised k_gather is used then).
+void* mx_gather_tma_create(mx_replay* r) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return nullptr;
+  const mx_replay_layout& L = r->L;
+  MxGatherTma* g = new MxGatherTma();
+  memset(g, 0, sizeof(*g));
+  int nf = 0, cum = 0;
+  bool ok = true;
+  auto add = [&](int64_t src_off, int64_t dst_off, int64_t ep_words) {
+    if (ep_words == 0 || !ok) return;
+    ok = ok && encode_rows(fn, &g->maps.src[nf], r->blob + src_off, r->cfg.capacity, ep_words) &&
+         encode_rows(fn, &g->maps.dst[nf], r->blob + dst_off, r->cfg.max_batch, ep_words);
+    g->args.cum[nf] = cum;
+    cum += (int)((ep_words + GT_BOX - 1) / GT_BOX);
+    ++nf;
+  };
+  add(L.off_obs, L.off_b_obs, L.ep_obs);
+  add(L.off_share, L.off_b_share, L.ep_share);
+  add(L.off_acts, L.off_b_acts, L.ep_acts);
+  add(L.off_avail, L.off_b_avail, L.ep_avail);
+  g->args.rew_field = r->cfg.reward_norm ? nf : -1;
+  add(L.off_rew, L.off_b_rew, L.ep_rew);
+  add(L.off_dones, L.off_b_dones, L.ep_dones);
+  add(L.off_dones_env, L.off_b_dones_env, L.ep_dones_env);
+  add(L.off_actidx, L.off_b_actidx, L.ep_actidx);
+  g->args.cum[nf] = cum;
+  g->args.nf = nf;
+  g->args.state = reinterpret_cast<const MxReplayState*>(r->blob + L.off_state);
+  if (!ok) { delete g; return nullptr; }
+  return g;
+}
+void mx_gather_tma_destroy(void* p) { delete reinterpret_cast<MxGatherTma*>(p); }
+
+int g_mx_gather_tma = 1;
+// returns -1 when the TMA path is not available / switched off (the caller launches k_gather)
+int mx_launch_gather_tma(void* p, const int64_t* idx_dev, int B, cudaStream_t s) {
+  if (!p || !g_mx_gather_tma) return -1;
+  MxGatherTma* g = reinterpret_cast<MxGatherTma*>(p);
+  GatherTmaArgs a = g->args;
+  a.B = B;
+  a.idx = (const long long*)idx_dev;
+  const long long total = (long long)a.cum[a.nf] * B;
+  const int sms = mx_num_sms();
+  long long want = (total + GT_WARPS - 1) / GT_WARPS;          // one box per warp at least
+  int grid = (int)(want < 1 ? 1 : want);
+  if (grid > sms * 4) grid = sms * 4;                          // four resident CTAs of four pipelines per SM
+  else if (grid > sms) grid = grid / sms * sms;
+  MX_LAUNCH_PDL(k_gather_tma, dim3(grid), dim3(GT_WARPS * 32), 0, s, g->maps, a);
+  MX_COUNT();
+  MX_MARK("k_gather", s);
+  return MX_CHECK_LAUNCH("gather_tma");
+}
+#else
+void* mx_gather_tma_create(mx_replay*) { return nullptr; }
+void mx_gather_tma_destroy(void*) {}
+int g_mx_gather_tma = 0;
+int mx_launch_gather_tma(void*, const int64_t*, int, cudaStream_t) { return -1; }
+#endif

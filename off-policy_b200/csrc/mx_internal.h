@@ -52,7 +52,12 @@ struct mx_replay {
   mx_replay_layout L;
   char* blob;
   int32_t filled, cursor;   // host mirror (inserts are host-driven)
+  void* tma = nullptr;      // tensor maps of the fields (gather_tma.cu), null: vectorised gather
 };
+void* mx_gather_tma_create(mx_replay* r);
+void mx_gather_tma_destroy(void* p);
+int mx_launch_gather_tma(void* p, const int64_t* idx_dev, int B, cudaStream_t s);     // -1: not available
+extern int g_mx_gather_tma;
 
 // ---- agent net / mixer parameter layouts (offsets in floats inside the flat vector) --------------
 struct MxNetLayout {       // RNNBase (LN -> fc1 -> LN -> fc2 -> LN -> GRU -> LN) + Linear head

@@ -536,10 +536,14 @@ extern "C" int mx_replay_create(const mx_replay_cfg* cfg, void* blob, void* stre
     cudaStreamSynchronize((cudaStream_t)stream);
     delete[] tmp;
   }
+  r->tma = mx_gather_tma_create(r);
   *out = r;
   return 0;
 }
-extern "C" void mx_replay_destroy(mx_replay* r) { delete r; }
+extern "C" void mx_replay_destroy(mx_replay* r) {
+  if (r) mx_gather_tma_destroy(r->tma);
+  delete r;
+}
 // Checkpoint restore: after the caller has copied a saved blob back into device memory, re-read the host mirror of the ring
 // position from the blob's device scalars (synchronises the stream).
 extern "C" int mx_replay_restore(mx_replay* r, void* stream) {
@@ -712,6 +716,10 @@ extern "C" int mx_replay_get_rng_state(mx_replay* r, uint32_t key[624], int32_t*
 }
 
 static int launch_gather(mx_replay* r, const int64_t* idx_dev, int B, cudaStream_t s) {
+  {
+    const int rc = mx_launch_gather_tma(r->tma, idx_dev, B, s);      // TMA tile copies (gather_tma.cu); -1: vectorised loads below
+    if (rc >= 0) return rc;
+  }
   const mx_replay_cfg& c = r->cfg;
   const mx_replay_layout& L = r->L;
   GatherArgs g;

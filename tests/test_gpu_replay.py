@@ -68,3 +68,31 @@ def test_full_size_gather_properties(gpu_engine):
             assert np.array_equal(rew[:, :, b], r.transpose(1, 0, 2))
             assert np.array_equal(de[:, b], den)
             assert np.array_equal(av[:, :, b], avl.transpose(1, 0, 2))
+
+
+@pytest.mark.parametrize("shape", [(3, 30, 9, 48, 60, 300, 32, False), (8, 80, 14, 168, 120, 200, 64, False), (3, 18, 5, 54, 25, 100, 32, True), (5, 7, 3, 9, 7, 40, 16, True)])
+def test_tma_gather_equals_vectorised_gather(gpu_engine, shape):
+    """k_gather_tma (tensor-map tile loads / stores, csrc/gather_tma.cu) against k_gather (16-byte vector loads): the whole batch region must be
+    bit-identical for the same indices -- full boxes, the clipped last box of every field, and the reward-normalisation transform."""
+    N, O, A, S, T, E, B, norm = shape
+    lib = gpu_engine.lib()
+    outs = []
+    for tma in (1, 0):
+        lib.mx_set_option(b"gather_tma", tma)
+        try:
+            buf = rc.make_buffers(N, O, A, S, T, E, norm=norm, rng="numpy", max_batch=B)
+            rs = np.random.RandomState(5)
+            for c in range(0, E, 50):
+                n = min(50, E - c)
+                ep = [rs.randn(T + 1, n, N, O), np.repeat(rs.randn(T + 1, n, 1, S), N, 2), np.eye(A)[rs.randint(0, A, (T, n, N))],
+                      np.repeat(3.0 + rs.randn(T, n, 1, 1), N, 2), np.zeros((T, n, N, 1)), np.zeros((T, n, 1)), (rs.rand(T + 1, n, N, A) < 0.7) * 1.0]
+                buf.insert(n, *[rc.d(x.astype(np.float32)) for x in ep])
+            pb = buf.policy_buffers["policy_0"]
+            pb.gather(np.random.RandomState(6).randint(0, E, B))
+            torch.cuda.synchronize()
+            lo, hi = int(pb.L.off_b_obs), int(pb.L.off_b_idx)
+            outs.append(pb.blob[lo:hi].clone())
+        finally:
+            lib.mx_set_option(b"gather_tma", 1)
+    assert torch.equal(outs[0], outs[1])
+    assert float(outs[0].view(torch.float32)[:1024].abs().sum()) > 0.0
