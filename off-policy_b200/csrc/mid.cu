@@ -23,8 +23,8 @@
 #define MID_YLD 66
 MX_DEVINL int mid_col(int j) { return j + (j >> 5); }
 
-struct MidSmem { int o_wq, o_bq, o_ln, o_y, o_dw, o_db, o_dg, total; };
-static MidSmem mid_smem(int A) {
+struct MidSmem { int o_wq, o_bq, o_ln, o_y, o_dw, o_db, o_dg, o_stage, stage_ld, total; };
+static MidSmem mid_smem(int A, int N, int gP, int gM) {
   MidSmem s;
   int o = 0;
   s.o_wq = o; o += 2 * 32 * MID_WLD;            // [net][32][65]
@@ -34,6 +34,10 @@ static MidSmem mid_smem(int A) {
   s.o_dw = o; o += MID_WARPS * A * MX_H;        // per-warp private dWq
   s.o_db = o; o += MID_WARPS * 32;              // per-warp private dbq
   s.o_dg = o; o += 2 * MID_WARPS * MX_H;        // per-warp d gamma, d beta
+  // per-warp operand staging (cp.async at the top of an element, ONE exposed L2 latency instead of one per agent and per mixer term):
+  // h rows [live t | live t+1 | target t+1][N][64], mixer hypernet outputs p1[2][gP], b1[2][gM], p2[2][gM], availability [N][32]
+  s.stage_ld = (3 * N * MX_H + 2 * gP + 4 * gM + N * 32 + 3) & ~3;
+  s.o_stage = o; o += MID_WARPS * s.stage_ld;
   s.total = o;
   return s;
 }
@@ -93,6 +97,7 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
   float* ys = smem + sm.o_y + warp * MID_YLD;
   float* my_dw = smem + sm.o_dw + warp * A * MX_H;
   float* my_db = smem + sm.o_db + warp * 32;
+  float* stg = smem + sm.o_stage + warp * sm.stage_ld;
   for (int net = 0; net < 2; ++net) {
     const float* th = net ? a.mix.theta_tgt : a.mix.theta;
     for (int i = tid; i < A * MX_H; i += MID_THREADS) wq_s[net * 32 * MID_WLD + (i / MX_H) * MID_WLD + mid_col(i % MX_H)] = th[a.wq + i];
@@ -118,15 +123,41 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
     const float w = a.mix.weights ? a.mix.weights[b] : 1.f;
     const float b2v[2] = {a.mix.hyp_b2[0][e], a.mix.hyp_b2[1][e]};
     float qt_reg = 0.f, qn_reg = 0.f;                     // lane n: q_taken[n], q_next[n]
+    // ---- stage every operand of this element with asynchronous copies: all of them are in flight at once ----
+    float* st_h = stg;                                    // [3][N][64]: live t, live t+1, target t+1
+    float* st_p1 = st_h + 3 * N * MX_H;                   // [2][gP]
+    float* st_b1 = st_p1 + 2 * a.mix.gP;                  // [2][gM]
+    float* st_p2 = st_b1 + 2 * a.mix.gM;                  // [2][gM]
+    float* st_av = st_p2 + 2 * a.mix.gM;                  // [N][32]
+    {
+      const int hv = N * (MX_H / 4);                      // 16-byte pieces per block of N rows (rows of a step are contiguous)
+      const float* s0 = a.hall[0] + m0 * MX_H;
+      const float* s1 = a.hall[0] + (m0 + N) * MX_H;
+      const float* s2 = a.hall[1] + (m0 + N) * MX_H;
+      for (int i = lane; i < hv; i += 32) { mx_cp16(st_h + 4 * i, s0 + 4 * i); mx_cp16(st_h + N * MX_H + 4 * i, s1 + 4 * i); mx_cp16(st_h + 2 * N * MX_H + 4 * i, s2 + 4 * i); }
+      for (int net = 0; net < 2; ++net) {
+        const float* p1 = a.mix.hyp_p1[net] + (size_t)e * a.mix.gP;
+        for (int i = lane; i < a.mix.gP / 4; i += 32) mx_cp16(st_p1 + net * a.mix.gP + 4 * i, p1 + 4 * i);
+        const float* b1 = a.mix.hyp_b1[net] + (size_t)e * a.mix.gM;
+        const float* p2 = a.mix.hyp_p2[net] + (size_t)e * a.mix.gM;
+        for (int i = lane; i < a.mix.gM / 4; i += 32) { mx_cp16(st_b1 + net * a.mix.gM + 4 * i, b1 + 4 * i); mx_cp16(st_p2 + net * a.mix.gM + 4 * i, p2 + 4 * i); }
+      }
+      if (a.avail && lane < A)
+        for (int n = 0; n < N; ++n) mx_cp4(st_av + n * 32 + lane, a.avail + (m0 + N + n) * a.act_ld + lane);
+      mx_cp_commit();
+    }
+    const int act_l = lane < N ? a.act_idx[(size_t)b * a.ld_tn + (size_t)t * N + lane] : 0;       // lane n: taken action of agent n
+    mx_cp_wait<0>();
+    __syncwarp();
     // ---------------- Q head: taken-action Q (live, t), greedy action (live, t+1), bootstrap Q (target, t+1) ----------------
     for (int n = 0; n < N; ++n) {
-      const float* hl = a.hall[0] + (m0 + n) * MX_H;
-      const float* hl1 = a.hall[0] + (m0 + N + n) * MX_H;
-      const float* ht1 = a.hall[1] + (m0 + N + n) * MX_H;
+      const float* hl = st_h + n * MX_H;
+      const float* hl1 = st_h + (N + n) * MX_H;
+      const float* ht1 = st_h + (2 * N + n) * MX_H;
       const float h0a = hl[lane], h0b = hl[lane + 32], h1a = hl1[lane], h1b = hl1[lane + 32], g1a = ht1[lane], g1b = ht1[lane + 32];
-      const int act = a.act_idx[(size_t)b * a.ld_tn + (size_t)t * N + n];
+      const int act = __shfl_sync(0xffffffffu, act_l, n);
       float av = 1.f;
-      if (a.avail && lane < A) av = a.avail[(m0 + N + n) * a.act_ld + lane];
+      if (a.avail && lane < A) av = st_av[n * 32 + lane];
       float xh0, xh1, y0, y1, rstd;
       mid_ln(h0a, h0b, lg, lb, lane, xh0, xh1, y0, y1, rstd);
       ys[lane] = y0; ys[lane + 33] = y1;
@@ -156,19 +187,19 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
     float hp[2], hvv[2], p2v[2];
 #pragma unroll
     for (int net = 1; net >= 0; --net) {
-      const float* p1 = a.mix.hyp_p1[net] + (size_t)e * a.mix.gP;
+      const float* p1 = st_p1 + net * a.mix.gP;
       float part = 0.f;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int k = lane + 32 * j;
-        float v = k < ME ? a.mix.hyp_b1[net][(size_t)e * a.mix.gM + k] : 0.f;
+        float v = k < ME ? st_b1[net * a.mix.gM + k] : 0.f;
         for (int n = 0; n < N; ++n) {
           const float qv = __shfl_sync(0xffffffffu, net ? qn_reg : qt_reg, n);
           if (k < ME) v = fmaf(qv, fabsf(p1[n * ME + k]), v);
         }
         if (k < ME) {
           const float hv = v > 0.f ? v : (expf(v) - 1.f);
-          const float p2 = a.mix.hyp_p2[net][(size_t)e * a.mix.gM + k];
+          const float p2 = st_p2[net * a.mix.gM + k];
           part = fmaf(hv, fabsf(p2), part);
           if (net == 0) { hp[j] = v; hvv[j] = hv; p2v[j] = p2; }
         }
@@ -203,7 +234,7 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
     }
     float dqt_reg = 0.f;                                   // lane n: d q_taken[n]
     {
-      const float* p1 = a.mix.hyp_p1[0] + (size_t)e * a.mix.gP;
+      const float* p1 = st_p1;
       for (int n = 0; n < N; ++n) {
         const float qn = __shfl_sync(0xffffffffu, qt_reg, n);
         float acc = 0.f;
@@ -223,8 +254,8 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
     // ---------------- Q head backward for the rows of step t ----------------
     for (int n = 0; n < N; ++n) {
       const float dqv = __shfl_sync(0xffffffffu, dqt_reg, n);
-      const int act = a.act_idx[(size_t)b * a.ld_tn + (size_t)t * N + n];
-      const float* hl = a.hall[0] + (m0 + n) * MX_H;
+      const int act = __shfl_sync(0xffffffffu, act_l, n);
+      const float* hl = st_h + n * MX_H;
       float xh0, xh1, y0, y1, rstd;
       mid_ln(hl[lane], hl[lane + 32], lg, lb, lane, xh0, xh1, y0, y1, rstd);
       const float dy0 = dqv * wq0[act * MID_WLD + lane], dy1 = dqv * wq0[act * MID_WLD + lane + 33];
@@ -280,13 +311,17 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
   }
 }
 
-int mx_mid_supported(const MidArgs& a) { return mx_mixer_split_supported(a.mix.L) && a.A <= 32 && a.N <= 32; }
+int mx_mid_supported(const MidArgs& a) {
+  if (!(mx_mixer_split_supported(a.mix.L) && a.A <= 32 && a.N <= 32)) return 0;
+  const MidSmem sm = mid_smem(a.A, a.N, a.mix.gP, a.mix.gM);
+  return (size_t)sm.total * sizeof(float) + 16 <= 200 * 1024;          // the per-warp operand staging must fit (N <= ~11 at A = 14)
+}
 
 int mx_launch_mid(const MidArgs& a, int* parts_used, cudaStream_t s) {
   const int E = a.mix.B * a.T;
   int grid = mx_ceil_div(E, MID_WARPS);
   if (grid > mx_num_sms()) grid = mx_num_sms();
-  MidSmem sm = mid_smem(a.A);
+  MidSmem sm = mid_smem(a.A, a.N, a.mix.gP, a.mix.gM);
   const size_t bytes = (size_t)sm.total * sizeof(float) + 16;
 #if !MX_EMU
   static size_t configured = 0;
