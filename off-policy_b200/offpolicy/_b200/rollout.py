@@ -65,8 +65,10 @@ class PolicyStepper(object):
         resident = False
         if rnn_states is None:
             blk[o_h:o_h + R * H] = 0.0
-        elif self._last_h is not None and self._last_h[1] == R and _host_ptr(rnn_states) == _host_ptr(self._last_h[0]):
-            # the very buffer we handed out last step (holding a reference keeps its memory from being reused)
+        elif self._last_h is not None and self._last_h[1] == R and _host_ptr(rnn_states) == _host_ptr(self._last_h[0]) and \
+                np.array_equal(self._last_h[0], self._last_h[2]):
+            # the very buffer we handed out last step (holding a reference keeps its memory from being reused) AND nobody has edited it
+            # in place since (a caller that zeroes the rows of finished envs must see its edit honoured): the device copy is current
             resident = True
         else:
             hs = rnn_states.detach().cpu().numpy() if isinstance(rnn_states, torch.Tensor) else np.asarray(rnn_states)
@@ -96,5 +98,5 @@ class PolicyStepper(object):
         h_new = blk[o_hn:o_hn + R * H].reshape(R, H).copy()
         gi = blk[o_gi:o_gi + R].view(np.int32).astype(np.int64) if want_greedy else None
         gq = blk[o_gq:o_gq + R].copy() if want_greedy else None
-        self._last_h = (h_new, R)
+        self._last_h = (h_new, R, h_new.copy())
         return out, h_new, gi, gq

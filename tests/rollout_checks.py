@@ -1,5 +1,7 @@
 """Rollout-time policy surface (QMixPolicy.get_actions / get_q_values / get_random_actions) against the reference golden
 `tests/golden/qmix_rollout.npz` (made by tests/golden/make_goldens.py rollout): shared by the emulated and the GPU tests."""
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -56,3 +58,26 @@ def check_errors():
     a = capi.PolicyStepArgs()
     assert capi.lib().mx_policy_step(C.byref(a), None) != 0
     assert b"null" in capi.lib().mx_last_error()
+
+
+def check_in_place_state_edit_is_honoured():
+    """The resident-state fast path keeps the recurrent state on the device when the runner hands back the array it was given.  A caller that
+    edits that array IN PLACE (e.g. zeroes the rows of finished environments) must get the edited state, not the stale device copy."""
+    from offpolicy._b200 import capi
+    from offpolicy._b200.rollout import PolicyStepper
+    I, A, R = 7, 4, 3
+    cfg = capi.QmixCfg(n_agents=R, obs_dim=I, act_dim=A, state_dim=5, hidden=64, mixer_hidden=32, hyper_hidden=64, hyper_layers=2, episode_len=4, max_batch=2)
+    total = C.c_int64()
+    capi.lib().mx_qmix_param_layout(C.byref(cfg), None, 0, C.byref(total))
+    theta = (0.1 * torch.randn(int(total.value), generator=torch.Generator().manual_seed(1))).to(capi.device())
+    rs = np.random.RandomState(0)
+    o1, o2 = rs.randn(R, I).astype(np.float32), rs.randn(R, I).astype(np.float32)
+    a, b = PolicyStepper(I, A), PolicyStepper(I, A)
+    _, h, _, _ = a.step(theta, o1, None)
+    h[0] = 0.0                                         # in-place edit of the array the stepper handed out
+    out_a, h_a, _, _ = a.step(theta, o2, h)
+    out_b, h_b, _, _ = b.step(theta, o2, h.copy())     # a fresh stepper given the same (edited) state: always uploads it
+    assert np.array_equal(out_a, out_b) and np.array_equal(h_a, h_b)
+    out_c, _, _, _ = a.step(theta, o1, h_a)             # unedited hand-back: resident path, same result as an upload
+    out_d, _, _, _ = b.step(theta, o1, h_b.copy())
+    assert np.array_equal(out_c, out_d)

@@ -8,3 +8,7 @@ def test_qmix_rollout_matches_reference(emu_engine):
 
 def test_policy_step_argument_errors(emu_engine):
     rc.check_errors()
+
+
+def test_in_place_edit_of_the_returned_state_is_honoured(emu_engine):
+    rc.check_in_place_state_edit_is_honoured()
