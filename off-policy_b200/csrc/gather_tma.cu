@@ -4,7 +4,7 @@
 // B episodes is B straight copies per field.  Each field is described to the TMA unit twice as a 2-D tensor [rows][episode words]:
 // the store (`capacity` rows) and the batch region (`max_batch` rows).  A copy is a tile load of 256 words at (x, episode index) into
 // shared memory, completion signalled on an mbarrier by byte count, followed by a tile store to (x, batch row); the last box of a row
-// is clipped by the tensor bounds.  One elected lane per warp runs a four-stage pipeline (two loads in flight ahead of the store being
+// is clipped by the tensor bounds.  One elected lane per warp runs an eight-stage pipeline (six loads in flight ahead of the store being
 // issued); no thread touches the data except for the reward normalisation ((r - mean) / std on the rewards field, rec_buffer.py:221-223),
 // which the warp applies in shared memory between the load and the store.  The kernel issues UTMALDG / UTMASTG only: address
 // generation, bounds handling and the 128-byte transactions are the copy engine's.
@@ -17,8 +17,8 @@
 #include <cuda.h>
 
 #define GT_WARPS 4
-#define GT_STAGES 4
-#define GT_AHEAD 2
+#define GT_STAGES 8
+#define GT_AHEAD 6            // loads in flight per pipeline: 4 CTAs x 4 warps x 6 KB = 96 KB per SM (HBM latency x bandwidth needs ~45 KB)
 #define GT_BOX 256            // 32-bit words per box (the TMA limit per dimension)
 
 struct GatherTmaMaps {

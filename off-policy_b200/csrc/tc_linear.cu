@@ -280,6 +280,201 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc(FrontFwdArgs a, FrontTc
 }
 
 
+// ---- 256-thread variant: TWO threads per accumulator row ------------------------------------------------------------------------------------
+// Warps w and w + 4 share TMEM lane quadrant w & 3, so thread (r, half) reads columns [32 half, 32 half + 32) of row r: every epilogue
+// (bias, activation, LayerNorm, TF32 split, operand write-back, activation stores) is half as long per thread, eight warps instead of four
+// hide each other's latencies, and the unrolled code a warp walks through is half as large (the 128-thread kernel spends ~30 % of its
+// time on instruction-cache misses: profiles/r02c).  LayerNorm statistics cross the pair through shared memory (four values per layer).
+__device__ __forceinline__ float tc_pair_sum(float v, float (*ex)[2][128], int& buf, int half, int r) {
+  ex[buf][half][r] = v;
+  __syncthreads();
+  const float o = ex[buf][half ^ 1][r];
+  buf ^= 1;          // the next exchange uses the other buffer: this one is rewritten only after another barrier
+  return half ? o + v : v + o;      // same operand order in both threads of the pair
+}
+__device__ __forceinline__ float tc_sum32(const float (&v)[32]) {
+  float p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = v[i];
+#pragma unroll
+  for (int c = 8; c < 32; c += 8)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] += v[c + i];
+  return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+}
+__device__ __forceinline__ float tc_sumsq32(const float (&v)[32], float mean, int c0, int n_valid) {
+  float p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; c += 8)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = (c0 + c + i < n_valid) ? v[c + i] - mean : 0.f; p[i] = fmaf(d, d, p[i]); }
+  return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+}
+// this thread's 32 columns [c0, c0 + 32) of row r into the A tiles (K = 64), 16 bytes at a time
+__device__ __forceinline__ void tc_put_row32(char* hi, char* lo, int r, int c0, const float (&x)[32]) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    float4 h, l;
+    h.x = tc::to_tf32(x[4 * k4]); h.y = tc::to_tf32(x[4 * k4 + 1]); h.z = tc::to_tf32(x[4 * k4 + 2]); h.w = tc::to_tf32(x[4 * k4 + 3]);
+    l.x = x[4 * k4] - h.x; l.y = x[4 * k4 + 1] - h.y; l.z = x[4 * k4 + 2] - h.z; l.w = x[4 * k4 + 3] - h.w;
+    const uint32_t o = tc::core_off_bytes(r, c0 + 4 * k4, 64);
+    *reinterpret_cast<float4*>(hi + o) = h;
+    *reinterpret_cast<float4*>(lo + o) = l;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) k_front_fwd_tc2(FrontFwdArgs a, FrontTcSmem sm, int swap_ls) {
+  MX_DYN_SMEM_RAW(smem_raw);
+  __shared__ __align__(8) tc::Bar bar_s;
+  __shared__ uint32_t tmem_s;
+  __shared__ float par_s[6 * MX_H + MX_G + 2 * 64];      // b1,g1,be1,b2,g2,be2 | b_ih | fn_g, fn_b
+  __shared__ float ex_s[2][2][128];                        // pair exchange of LayerNorm partial sums
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7, c0 = 32 * half;
+  const int net = blockIdx.y;
+  const float* __restrict__ th = a.theta[net];
+  const MxNetLayout L = a.L;
+  const bool live = (net == 0);
+  const int I = L.in_dim, Kp = (I + 7) & ~7;
+  char* base = reinterpret_cast<char*>(smem_raw);
+  char *a_hi = base + sm.o_ahi, *a_lo = base + sm.o_alo;
+  char *w1h = base + sm.o_w1h, *w1l = base + sm.o_w1l, *w2h = base + sm.o_w2h, *w2l = base + sm.o_w2l, *wih = base + sm.o_wih, *wil = base + sm.o_wil;
+  const uint32_t bar = tc::bar_addr(&bar_s);
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_s);
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::mbar_init_fence();
+  }
+  for (int i = tid; i < MX_H; i += blockDim.x) {
+    par_s[i] = th[L.b1 + i]; par_s[MX_H + i] = th[L.ln1_g + i]; par_s[2 * MX_H + i] = th[L.ln1_b + i];
+    par_s[3 * MX_H + i] = th[L.b2 + i]; par_s[4 * MX_H + i] = th[L.ln2_g + i]; par_s[5 * MX_H + i] = th[L.ln2_b + i];
+    par_s[6 * MX_H + MX_G + i] = i < I ? th[L.fn_g + i] : 0.f; par_s[6 * MX_H + MX_G + 64 + i] = i < I ? th[L.fn_b + i] : 0.f;
+  }
+  for (int i = tid; i < MX_G; i += blockDim.x) par_s[6 * MX_H + i] = th[L.bih + i];
+  MX_PDL_WAIT();
+  if (a.tc_img[net]) {
+    const int nvec = (sm.total - sm.o_w1h) >> 4, nvec12 = (sm.o_wih - sm.o_w1h) >> 4;
+    const float* src = a.tc_img[net];
+    float* dst = reinterpret_cast<float*>(w1h);
+    for (int v = tid; v < nvec12; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
+    mx_cp_commit();
+    for (int v = nvec12 + tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
+    mx_cp_commit();
+  } else {
+    tc_stage_weight(w1h, w1l, th + L.w1, MX_H, I, Kp);
+    tc_stage_weight(w2h, w2l, th + L.w2, MX_H, MX_H, MX_H);
+    tc_stage_weight(wih, wil, th + L.wih, MX_G, MX_H, MX_H);
+  }
+  const float* bih_s = par_s + 6 * MX_H;
+  const float* fng_s = par_s + 6 * MX_H + MX_G;
+  const float* fnb_s = fng_s + 64;
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = tmem_s;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);       // warps w and w + 4 read the same lane quadrant
+  uint32_t phase = 0;
+  int xb = 0;
+  const int ntiles = (a.M + 127) / 128;
+  const int I4 = (I + 3) >> 2;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m = tile * 128 + r;
+    const bool ok = m < a.M;
+    // ---- input row, columns [c0, c0 + 32): LayerNorm over I features (pair-wise statistics), split, layer-1 A tile (K = Kp) ----
+    {
+      float x[32];
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && 8 * half + c4 < I4) v = *reinterpret_cast<const float4*>(a.X + (size_t)m * a.ldx + c0 + 4 * c4);
+        x[4 * c4] = v.x; x[4 * c4 + 1] = v.y; x[4 * c4 + 2] = v.z; x[4 * c4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) if (c0 + c >= I) x[c] = 0.f;
+      const float mean = tc_pair_sum(tc_sum32(x), ex_s, xb, half, r) / (float)I;
+      const float rstd = rsqrtf(tc_pair_sum(tc_sumsq32(x, mean, c0, I), ex_s, xb, half, r) / (float)I + MX_LN_EPS);
+      if (live && ok && a.st0 && half == 0) { a.st0[2 * (size_t)m] = mean; a.st0[2 * (size_t)m + 1] = rstd; }
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4)
+        if (c0 + 4 * c4 < Kp) {
+          float4 h, l;
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = c0 + 4 * c4 + j;
+            v[j] = c < I ? (a.feature_norm ? ((x[4 * c4 + j] - mean) * rstd * fng_s[c] + fnb_s[c]) : x[4 * c4 + j]) : 0.f;
+          }
+          h.x = tc::to_tf32(v[0]); h.y = tc::to_tf32(v[1]); h.z = tc::to_tf32(v[2]); h.w = tc::to_tf32(v[3]);
+          l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+          const uint32_t o = tc::core_off_bytes(r, c0 + 4 * c4, Kp);
+          *reinterpret_cast<float4*>(a_hi + o) = h;
+          *reinterpret_cast<float4*>(a_lo + o) = l;
+        }
+    }
+    // ---- fc1, fc2 ----
+    for (int layer = 0; layer < 2; ++layer) {
+      mx_cp_wait<1>();
+      tc::fence_async_smem();
+      tc::fence_before();
+      __syncthreads();
+      tc::fence_after();
+      if (tid == 0) tc::issue_layer(tmem_base, a_hi, a_lo, layer == 0 ? w1h : w2h, layer == 0 ? w1l : w2l, MX_H, layer == 0 ? Kp : MX_H, 3, swap_ls, bar);
+      tc::mbar_wait(bar, phase);
+      phase ^= 1;
+      tc::fence_after();
+      float v[32];
+      tc::tmem_ld32(tmem_row + c0, v);
+      const float* bs = par_s + layer * 3 * MX_H;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { const float z = v[c] + bs[c0 + c]; v[c] = a.act_tanh ? tanhf(z) : fmaxf(z, 0.f); }
+      const float mean = tc_pair_sum(tc_sum32(v), ex_s, xb, half, r) * (1.f / 64.f);
+      const float rstd = rsqrtf(tc_pair_sum(tc_sumsq32(v, mean, c0, 64), ex_s, xb, half, r) * (1.f / 64.f) + MX_LN_EPS);
+      float* u_out = layer == 0 ? a.u1 : a.u2;
+      float* st_out = layer == 0 ? a.st1 : a.st2;
+      if (live && ok && u_out) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) *reinterpret_cast<float4*>(u_out + (size_t)m * MX_H + c0 + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        if (st_out && half == 0) { st_out[2 * (size_t)m] = mean; st_out[2 * (size_t)m + 1] = rstd; }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = (v[c] - mean) * rstd * bs[MX_H + c0 + c] + bs[2 * MX_H + c0 + c];
+      tc_put_row32(a_hi, a_lo, r, c0, v);      // the MMAs that read the previous A tile have completed (mbarrier)
+    }
+    // ---- gi = x2 . W_ih^T + b_ih: columns [96 half, 96 half + 96) ----
+    mx_cp_wait<0>();
+    tc::fence_async_smem();
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    if (tid == 0) tc::issue_layer(tmem_base, a_hi, a_lo, wih, wil, MX_G, MX_H, 3, swap_ls, bar);
+    tc::mbar_wait(bar, phase);
+    phase ^= 1;
+    tc::fence_after();
+    float* gi = a.gi[net];
+#pragma unroll 1
+    for (int g0 = 96 * half; g0 < 96 * half + 96; g0 += 32) {
+      float t0[32];
+      tc::tmem_ld32(tmem_row + g0, t0);
+      if (ok) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          *reinterpret_cast<float4*>(gi + (size_t)m * MX_G + g0 + 4 * c4) =
+              make_float4(t0[4 * c4] + bih_s[g0 + 4 * c4], t0[4 * c4 + 1] + bih_s[g0 + 4 * c4 + 1], t0[4 * c4 + 2] + bih_s[g0 + 4 * c4 + 2],
+                          t0[4 * c4 + 3] + bih_s[g0 + 4 * c4 + 3]);
+      }
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
+}
+
+
 // =====================================================================================================
 // Wide inputs (64 < in_dim <= 128: SMAC 8m / 2s3z observations): same pipeline, but fc1's K dimension is fed in chunks of 64
 // columns that accumulate in TMEM -- the A tile stays [128][64] and only one fc1 weight chunk is resident (restaged per tile from
@@ -456,6 +651,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
 }
 
 int g_mx_front_tc = 1;        // 1: tcgen05 3xTF32 kernel (default), 0: FFMA kernel (mx_set_option("front_tc", 0))
+int g_mx_front_tc_threads = 256;   // inputs <= 64: 256 = two threads per accumulator row (k_front_fwd_tc2), 128 = one (k_front_fwd_tc)
 int g_mx_front_tc_wide = 1;   // 1 (default): 64 < in_dim <= 128 also runs on tcgen05 (k_front_fwd_tc_wide): 8m 1.76 -> 1.59 ms, 2s3z 0.683 -> 0.647 ms (r02 sweeps)
 int g_mx_tc_swap = 0;
 extern int g_mx_wgrad_tc, g_mx_wgrad_tc_wide;      // tc_bwd.cu
@@ -497,6 +693,19 @@ int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
     configured = smem;
   }
 #endif
+  if (g_mx_front_tc_threads == 256) {
+#if !MX_EMU
+    static size_t configured2 = 0;
+    if (smem > configured2) {
+      if (cudaFuncSetAttribute(k_front_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { mx_set_error("front_fwd_tc2: smem %zu too large", smem); return 1; }
+      configured2 = smem;
+    }
+#endif
+    MX_LAUNCH_PDL(k_front_fwd_tc2, dim3(gx, nets), dim3(256), smem, s, a, sm, g_mx_tc_swap);
+    MX_COUNT();
+    MX_MARK("k_front_fwd_tc", s);
+    return MX_CHECK_LAUNCH("front_fwd_tc2");
+  }
   MX_LAUNCH_PDL(k_front_fwd_tc, dim3(gx, nets), dim3(128), smem, s, a, sm, g_mx_tc_swap);
   MX_COUNT();
   MX_MARK("k_front_fwd_tc", s);
@@ -507,6 +716,7 @@ extern "C" int mx_set_option(const char* name, int32_t value) {
   if (mx_set_option_common(name, value) == 0) return 0;
   if (!strcmp(name, "front_tc")) { g_mx_front_tc = value; return 0; }
   if (!strcmp(name, "front_tc_wide")) { g_mx_front_tc_wide = value; return 0; }
+  if (!strcmp(name, "front_tc_threads")) { g_mx_front_tc_threads = value; return 0; }
   if (!strcmp(name, "wgrad_tc")) { g_mx_wgrad_tc = value; return 0; }
   if (!strcmp(name, "wgrad_tc_wide")) { g_mx_wgrad_tc_wide = value; return 0; }
   if (!strcmp(name, "tc_swap_ls")) { g_mx_tc_swap = value; return 0; }

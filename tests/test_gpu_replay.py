@@ -80,7 +80,7 @@ def test_tma_gather_equals_vectorised_gather(gpu_engine, shape):
     for tma in (1, 0):
         lib.mx_set_option(b"gather_tma", tma)
         try:
-            buf = rc.make_buffers(N, O, A, S, T, E, norm=norm, rng="numpy", max_batch=B)
+            buf = rc.make_buffers(N, O, A, S, T, E, norm=norm, rng="numpy", max_batch=max(B, 64))
             rs = np.random.RandomState(5)
             for c in range(0, E, 50):
                 n = min(50, E - c)
