@@ -10,6 +10,7 @@
 #include "mx_internal.h"
 #include "mx_kernels.h"
 #include "mx_tile.cuh"
+#include "mx_mma.cuh"
 
 // =====================================================================================================
 // Q head backward (one warp per row-step)
@@ -463,11 +464,13 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     // ---- GRU weight gradients: dW_ih = dgi^T x2 ; dW_hh = [dgi_r, dgi_z, dgi_n*r]^T h_{t-1} ----
     if (wgemm) {
       for (int nb = 0; nb < 3; ++nb) {
-        mx_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
+        if (a.use_mma) mx_mma_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
+        else mx_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
         if (a.no_gru) continue;
         const float* dgh = nb < 2 ? dgi_s + nb * 64 : dgn_s;
         const int ldd = nb < 2 ? sm.ldg : sm.ld64;
-        mx_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
+        if (a.use_mma) mx_mma_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
+        else mx_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
       }
       mx_colsum(dgi_s, sm.ldg, TM, MX_G, gp + L.bih, accum);
       if (!a.no_gru) {
@@ -481,6 +484,26 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     for (int i = 0; i < RM; ++i)
 #pragma unroll
       for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
+    if (a.use_mma) {       // tensor-core tiles (mx_mma.cuh): warp w owns 8 output columns; the result goes through da_s back to the (ty, tx) row layout
+      float cfr[RM][4];
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx) cfr[i][jx] = 0.f;
+      for (int nc = 0; nc < 3; ++nc) {
+        __syncthreads();
+        mx_stage_weight(Wc, sm.ld64, th + L.wih, MX_G, MX_H, MX_H, nc * 64, 0, 64);
+        __syncthreads();
+        mx_mma_dgrad_acc<RM>(cfr, dgi_s + nc * 64, sm.ldg, Wc, sm.ld64);
+      }
+      mx_mma_store<RM>(cfr, da_s, sm.ld64);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        const float4 q = mx_ld4(da_s + (ty * RM + i) * sm.ld64 + 4 * tx);
+        v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+      }
+    } else
     for (int nc = 0; nc < 3; ++nc) {
       __syncthreads();
       mx_stage_weight(Wc, sm.ld64, th + L.wih, MX_G, MX_H, MX_H, nc * 64, 0, 64);
@@ -511,15 +534,31 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     __syncthreads();
     // ---- fc2: dW2 = da2^T x1, db2 ; dx1 = da2 . W2 ----
     if (wgemm) {
-      mx_wgrad_block(da_s, sm.ld64, x_s, sm.ld64, TM, gp + L.w2, MX_H, MX_H, 0, 0, accum);
+      if (a.use_mma) mx_mma_wgrad_block(da_s, sm.ld64, x_s, sm.ld64, TM, gp + L.w2, MX_H, MX_H, 0, 0, accum);
+      else mx_wgrad_block(da_s, sm.ld64, x_s, sm.ld64, TM, gp + L.w2, MX_H, MX_H, 0, 0, accum);
       mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b2, accum);
     }
     mx_stage_weight(Wc, sm.ld64, th + L.w2, MX_H, MX_H, MX_H, 0, 0, 64);
-    __syncthreads();
+    __syncthreads();      // W2 staged; every warp is past the fc2 weight gradient that read x_s (x1)
 #pragma unroll
     for (int i = 0; i < RM; ++i)
 #pragma unroll
       for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
+    if (a.use_mma) {
+      float cfr[RM][4];
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx) cfr[i][jx] = 0.f;
+      mx_mma_dgrad_acc<RM>(cfr, da_s, sm.ld64, Wc, sm.ld64);
+      mx_mma_store<RM>(cfr, x_s, sm.ld64);          // x1 is dead: its buffer carries dx1 back to the row layout
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        const float4 q = mx_ld4(x_s + (ty * RM + i) * sm.ld64 + 4 * tx);
+        v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+      }
+    } else
     mx_mm_nn<RM>(da_s, sm.ld64, Wc, sm.ld64, v);
     ln64_bwd_relu<RM>(a.act_tanh != 0, v, u_s, sm.ld64, st1_s, ln1g_s, dg1, db1);
     __syncthreads();     // da_s (da2) consumed by everyone
@@ -548,7 +587,10 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     __syncthreads();
     // ---- fc1: dW1 = da1^T x0, db1 ; dx0 = da1 . W1 (only for the LN0 gain/bias) ----
     if (wgemm) {
-      for (int kb = 0; kb * 64 < I; ++kb) mx_wgrad_block(da_s, sm.ld64, x0_s + kb * 64, sm.ldi, TM, gp + L.w1, MX_H, I, 0, kb * 64, accum);
+      for (int kb = 0; kb * 64 < I; ++kb) {
+        if (a.use_mma) mx_mma_wgrad_block(da_s, sm.ld64, x0_s + kb * 64, sm.ldi, TM, gp + L.w1, MX_H, I, 0, kb * 64, accum);
+        else mx_wgrad_block(da_s, sm.ld64, x0_s + kb * 64, sm.ldi, TM, gp + L.w1, MX_H, I, 0, kb * 64, accum);
+      }
       mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b1, accum);
     }
     if (a.feature_norm || a.dX) {
@@ -560,6 +602,21 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
         for (int i = 0; i < RM; ++i)
 #pragma unroll
           for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
+        if (a.use_mma) {
+          float cfr[RM][4];
+#pragma unroll
+          for (int i = 0; i < RM; ++i)
+#pragma unroll
+            for (int jx = 0; jx < 4; ++jx) cfr[i][jx] = 0.f;
+          mx_mma_dgrad_acc<RM>(cfr, da_s, sm.ld64, Wc, sm.ld64);
+          mx_mma_store<RM>(cfr, dx0_s + kb * 64, sm.ldi);
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < RM; ++i) {
+            const float4 q = mx_ld4(dx0_s + (ty * RM + i) * sm.ldi + kb * 64 + 4 * tx);
+            v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+          }
+        } else
         mx_mm_nn<RM>(da_s, sm.ld64, Wc, sm.ld64, v);
         float cg[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -739,12 +796,14 @@ static int front_bwd_launch(const FrontBwdArgs& a, int* nparts_used, cudaStream_
 }
 
 extern int g_mx_front_bwd_rm;
+int g_mx_front_bwd_mma = 1;      // 1 (default): the GEMMs of k_front_bwd on mma.sync 3xTF32 tiles; 0: FFMA micro-kernels (mx_set_option("front_bwd_mma", 0))
 bool mx_front_bwd_tc_usable(const FrontBwdArgs& a);
 int mx_launch_front_bwd_tc(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s);
 int mx_launch_front_bwd(const FrontBwdArgs& a_in, int* nparts_used, cudaStream_t s) {
   if (mx_front_bwd_tc_usable(a_in)) return mx_launch_front_bwd_tc(a_in, nparts_used, s);
   FrontBwdArgs a = a_in;
   a.wgrad_external = mx_wgrad_tc_usable(a) ? 1 : 0;
+  a.use_mma = g_mx_front_bwd_mma ? 1 : 0;
   const int rm = g_mx_front_bwd_rm ? g_mx_front_bwd_rm : front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms());
   int rc;
   if (rm == 3) rc = front_bwd_launch<3>(a, nparts_used, s);

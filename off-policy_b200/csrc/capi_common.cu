@@ -31,6 +31,7 @@ int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "overlap_rows")) { g_mx_overlap_rows = value; return 0; }
   if (!strcmp(name, "mid_fused")) { g_mx_mid_fused = value; return 0; }
   if (!strcmp(name, "optim_fused")) { g_mx_optim_fused = value; return 0; }
+  if (!strcmp(name, "front_bwd_mma")) { g_mx_front_bwd_mma = value; return 0; }
   if (!strcmp(name, "gather_tma")) { g_mx_gather_tma = value; return 0; }      // 1: episode gather on the TMA unit (default), 0: vectorised loads
   if (!strcmp(name, "gru_threads")) { g_mx_gru_threads = value; return 0; }      // 0: by size, 128 / 256: force the recurrence kernels' CTA width
   if (!strcmp(name, "gru_fwd_rpc")) { g_mx_gru_fwd_rpc = value; return 0; }

@@ -164,3 +164,17 @@ def test_front_tcgen05_kernel_variants_match_reference_golden(emu_engine, name, 
         qc.check_step_against(None, name, intermediates=(name != "qmix_small_prev_act"), debug=True)
     finally:
         lib.mx_set_option(b"front_tc_threads", 256)
+
+
+@pytest.mark.parametrize("mma", [0, 1])
+@pytest.mark.parametrize("name", ["qmix_small", "qmix_5ag", "qmix_small_nofn"])
+def test_front_backward_gemm_variants_match_reference_golden(emu_engine, name, mma):
+    """k_front_bwd with its GEMMs on mma.sync 3xTF32 tiles (csrc/mx_mma.cuh, default) and on the FFMA micro-kernels (option front_bwd_mma)."""
+    lib = emu_engine.lib()
+    lib.mx_set_option(b"front_bwd_mma", mma)
+    lib.mx_set_option(b"wgrad_tc", 0)
+    try:
+        qc.check_step_against(None, name, intermediates=False, debug=False)
+    finally:
+        lib.mx_set_option(b"front_bwd_mma", 1)
+        lib.mx_set_option(b"wgrad_tc", -1)
