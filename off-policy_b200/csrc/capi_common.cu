@@ -19,6 +19,7 @@ int g_mx_mixer_split_rm = 0;   // rows per thread of the split mixer's tiles (0 
 int g_mx_overlap = 1;          // state-only kernels (weight-image prep, mixer hypernets) on a forked branch beside the agent-net
                                // kernels: 1 = when the step is latency-bound (rows <= g_mx_overlap_rows), 2 = always, 0 = never
 int g_mx_gru_threads = 0;
+int g_mx_hyper_late = 1;        // 1: the hypernet branch forks after the front kernel (beside the recurrence), 0: before it
 int g_mx_mid_fused = 1;        // 1: k_qhead + k_mix_core + k_qhead_bwd as ONE kernel (k_mid) when the split mixer is in use and no debug
                                //    outputs are requested; 0: three launches
 int g_mx_gru_fwd_rpc = 0;      // tuning overrides: sequence rows per CTA of the recurrence kernels (0 = automatic; 1, 2 or 4)
@@ -31,6 +32,7 @@ int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "overlap_rows")) { g_mx_overlap_rows = value; return 0; }
   if (!strcmp(name, "mid_fused")) { g_mx_mid_fused = value; return 0; }
   if (!strcmp(name, "optim_fused")) { g_mx_optim_fused = value; return 0; }
+  if (!strcmp(name, "hyper_late")) { g_mx_hyper_late = value; return 0; }
   if (!strcmp(name, "front_bwd_mma")) { g_mx_front_bwd_mma = value; return 0; }
   if (!strcmp(name, "gather_tma")) { g_mx_gather_tma = value; return 0; }      // 1: episode gather on the TMA unit (default), 0: vectorised loads
   if (!strcmp(name, "gru_threads")) { g_mx_gru_threads = value; return 0; }      // 0: by size, 128 / 256: force the recurrence kernels' CTA width

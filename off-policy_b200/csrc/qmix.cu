@@ -388,12 +388,20 @@ static int backward_core(mx_qmix* q, const mx_batch* b, void* stream, OptimArgs*
     } else if (launch_prep(q, s)) return 1;
     ff.tc_img[0] = ws + W.tcimg[0]; ff.tc_img[1] = ws + W.tcimg[1];
   }
+  // the mixer's hypernetworks depend on the sampled states and the parameters only: forked branch beside the agent nets.
+  // hyper_late (default): the fork sits AFTER the tensor-core front kernel -- that kernel fills an SM's shared memory (224 KB of operand
+  // tiles), so hypernet CTAs resident on an SM keep a front CTA out and the two serialise; beside the recurrence (6.6 KB per CTA) they
+  // share SMs.  hyper_late = 0: fork before the front kernel (the r01 arrangement, FFMA front layers).
+  const bool late = g_mx_hyper_late != 0;
 #if !MX_EMU
-  // the mixer's hypernetworks depend on the sampled states and the parameters only: forked branch beside the agent nets
-  if (split && overlap) fork_to_side(q, q->ev_batch, s);
+  if (split && overlap && !late) fork_to_side(q, q->ev_batch, s);
 #endif
-  if (split && overlap) { if (mx_launch_mix_hyper_fwd(mx, side)) return 1; }
+  if (split && overlap && !late) { if (mx_launch_mix_hyper_fwd(mx, side)) return 1; }
   if (mx_launch_front_fwd(ff, 2, s)) return 1;
+#if !MX_EMU
+  if (split && overlap && late) fork_to_side(q, q->ev_batch, s);
+#endif
+  if (split && overlap && late) { if (mx_launch_mix_hyper_fwd(mx, side)) return 1; }
 
   if (c.mlp) {      // ---- transition-level variant (M_QMix / M_VDN): no recurrence, Q = columns [0, A) of the "gi" rows ----
     int parts[4] = {0, 0, 0, 0};

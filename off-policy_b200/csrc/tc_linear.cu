@@ -693,7 +693,8 @@ int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
     configured = smem;
   }
 #endif
-  if (g_mx_front_tc_threads == 256) {
+  // (inputs of 57..64 columns fill the 227 KB with operand tiles: the pair-exchange buffer of the 256-thread kernel no longer fits beside them)
+  if (g_mx_front_tc_threads == 256 && smem + 5 * 1024 + 256 <= 227 * 1024) {
 #if !MX_EMU
     static size_t configured2 = 0;
     if (smem > configured2) {
