@@ -19,7 +19,8 @@ int g_mx_mixer_split_rm = 0;   // rows per thread of the split mixer's tiles (0 
 int g_mx_overlap = 1;          // state-only kernels (weight-image prep, mixer hypernets) on a forked branch beside the agent-net
                                // kernels: 1 = when the step is latency-bound (rows <= g_mx_overlap_rows), 2 = always, 0 = never
 int g_mx_gru_threads = 0;
-int g_mx_hyper_late = 1;        // 1: the hypernet branch forks after the front kernel (beside the recurrence), 0: before it
+int g_mx_hyper_late = 0;        // 0 (default): the hypernet branch forks before the front kernel; 1: after it, beside the recurrence -- measured slower
+                                // (3m 198.7 vs 184.3 us, MPE 159.7 vs 128.2 us, profiles/r02_option_sweeps.md: the recurrence is the kernel that suffers most from co-residents)
 int g_mx_mid_fused = 1;        // 1: k_qhead + k_mix_core + k_qhead_bwd as ONE kernel (k_mid) when the split mixer is in use and no debug
                                //    outputs are requested; 0: three launches
 int g_mx_gru_fwd_rpc = 0;      // tuning overrides: sequence rows per CTA of the recurrence kernels (0 = automatic; 1, 2 or 4)

@@ -389,9 +389,8 @@ static int backward_core(mx_qmix* q, const mx_batch* b, void* stream, OptimArgs*
     ff.tc_img[0] = ws + W.tcimg[0]; ff.tc_img[1] = ws + W.tcimg[1];
   }
   // the mixer's hypernetworks depend on the sampled states and the parameters only: forked branch beside the agent nets.
-  // hyper_late (default): the fork sits AFTER the tensor-core front kernel -- that kernel fills an SM's shared memory (224 KB of operand
-  // tiles), so hypernet CTAs resident on an SM keep a front CTA out and the two serialise; beside the recurrence (6.6 KB per CTA) they
-  // share SMs.  hyper_late = 0: fork before the front kernel (the r01 arrangement, FFMA front layers).
+  // Default: fork before the front kernel.  hyper_late = 1 moves the fork AFTER the tensor-core front kernel (which fills an SM's shared
+  // memory, so hypernet CTAs and front CTAs cannot share an SM) -- measured slower: beside the recurrence the hypernet CTAs cost more.
   const bool late = g_mx_hyper_late != 0;
 #if !MX_EMU
   if (split && overlap && !late) fork_to_side(q, q->ev_batch, s);

@@ -176,5 +176,5 @@ def test_front_backward_gemm_variants_match_reference_golden(emu_engine, name, m
     try:
         qc.check_step_against(None, name, intermediates=False, debug=False)
     finally:
-        lib.mx_set_option(b"front_bwd_mma", 1)
+        lib.mx_set_option(b"front_bwd_mma", 0)
         lib.mx_set_option(b"wgrad_tc", -1)

@@ -15,8 +15,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STEP = ["k_draw", "k_gather", "k_tc_prep_weights", "k_front_fwd_tc", "k_front_fwd", "k_gru_fwd", "k_qhead", "k_mixer", "k_mix_hyper_fwd", "k_mix_core",
-        "k_mix_hyper_bwd", "k_mid", "k_qhead_bwd", "k_gru_bwd", "k_front_bwd", "k_grad_reduce", "k_adam", "k_polyak"]
+STEP = ["k_draw", "k_gather", "k_gather_tma", "k_tc_prep_weights", "k_front_fwd_tc", "k_front_fwd_tc2", "k_front_fwd", "k_gru_fwd", "k_gru_fwd2", "k_qhead", "k_mixer",
+        "k_mix_hyper_fwd", "k_mix_core", "k_mix_hyper_bwd", "k_mid", "k_qhead_bwd", "k_gru_bwd", "k_gru_bwd2", "k_front_bwd", "k_grad_reduce", "k_adam", "k_optim_fused", "k_polyak"]
 
 
 def short(name):
@@ -66,7 +66,11 @@ def main():
     cols = [("gpu__time_duration.sum", "time us"), ("launch__grid_size", "grid"), ("launch__registers_per_thread", "regs"),
             ("launch__shared_mem_per_block_dynamic", "dyn smem KB"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
             ("sm__inst_issued.avg.pct_of_peak_sustained_active", "issue active %"), ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma pipe %"),
-            ("sm__inst_executed_pipe_tensor.sum", "tensor inst"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
+            ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe % (cycles active)"),
+            ("sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "hmma subpipe inst %"),
+            ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "tmem inst %"),
+            ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor-memory (TMA) cycles %"),
+            ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
             ("lts__t_sectors_op_read.sum", "L2 rd sectors"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
             ("sm__cycles_elapsed.max", "cycles")]
     cols = [(c, n) for c, n in cols if c in hdr]
