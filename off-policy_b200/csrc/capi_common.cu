@@ -19,6 +19,7 @@ int g_mx_mixer_split_rm = 0;   // rows per thread of the split mixer's tiles (0 
 int g_mx_overlap = 1;          // state-only kernels (weight-image prep, mixer hypernets) on a forked branch beside the agent-net
                                // kernels: 1 = when the step is latency-bound (rows <= g_mx_overlap_rows), 2 = always, 0 = never
 int g_mx_gru_threads = 0;
+int g_mx_side_prio = 0;         // priority of a learner's forked branch (read when the learner is created): 0 default, 1 lower, -1 higher
 int g_mx_hyper_late = 0;        // 0 (default): the hypernet branch forks before the front kernel; 1: after it, beside the recurrence -- measured slower
                                 // (3m 198.7 vs 184.3 us, MPE 159.7 vs 128.2 us, profiles/r02_option_sweeps.md: the recurrence is the kernel that suffers most from co-residents)
 int g_mx_mid_fused = 1;        // 1: k_qhead + k_mix_core + k_qhead_bwd as ONE kernel (k_mid) when the split mixer is in use and no debug
@@ -33,6 +34,7 @@ int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "overlap_rows")) { g_mx_overlap_rows = value; return 0; }
   if (!strcmp(name, "mid_fused")) { g_mx_mid_fused = value; return 0; }
   if (!strcmp(name, "optim_fused")) { g_mx_optim_fused = value; return 0; }
+  if (!strcmp(name, "side_prio")) { g_mx_side_prio = value; return 0; }
   if (!strcmp(name, "hyper_late")) { g_mx_hyper_late = value; return 0; }
   if (!strcmp(name, "front_bwd_mma")) { g_mx_front_bwd_mma = value; return 0; }
   if (!strcmp(name, "gather_tma")) { g_mx_gather_tma = value; return 0; }      // 1: episode gather on the TMA unit (default), 0: vectorised loads

@@ -24,7 +24,7 @@ MX_DEVINL int mx_ld_dev(int k) { return ((k + 7) / 8) * 8 + 4; }
 // outside the matrix are zero-filled.  Returns after this thread's copies have landed; the caller's
 // __syncthreads() publishes the chunk.
 MX_DEVINL void mx_stage_weight(float* Wc, int ldw, const float* __restrict__ W, int nrows, int ncols_total, int ldg, int row0, int col0,
-                               int ncols_pad) {
+                               int ncols_pad, bool wait = true) {      // wait = false: one committed cp.async group, the caller waits (pipelined staging)
   const int tid = threadIdx.x;
   const bool vec = ((ldg & 3) == 0) && ((col0 & 3) == 0) && ((ncols_total & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   if (vec) {
@@ -50,7 +50,7 @@ MX_DEVINL void mx_stage_weight(float* Wc, int ldw, const float* __restrict__ W, 
     }
   }
   mx_cp_commit();
-  mx_cp_wait<0>();
+  if (wait) mx_cp_wait<0>();
 }
 
 // Copy `nrows_tile` rows of `ncols` floats (ncols % 4 == 0, rows 16-byte aligned, row stride ldg) starting at global

@@ -197,7 +197,14 @@ extern "C" int mx_qmix_create(const mx_qmix_cfg* c, float* theta, float* theta_t
   q->ws_bytes = workspace_bytes;
   q->split_ok = !c->vdn && mx_mixer_split_supported(q->mix);
 #if !MX_EMU
-  if (cudaStreamCreateWithFlags(&q->side, cudaStreamNonBlocking) != cudaSuccess) { mx_set_error("mx_qmix_create: cudaStreamCreate failed"); delete q; return 1; }
+  {
+    // side branch priority (option side_prio, read at creation): 0 = default, 1 = LOWER than the caller's stream (the agent-net kernels are
+    // scheduled first when both branches have CTAs pending), -1 = higher
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);            // lo = numerically largest = least priority
+    const int prio = g_mx_side_prio > 0 ? lo : (g_mx_side_prio < 0 ? hi : 0);
+    if (cudaStreamCreateWithPriority(&q->side, cudaStreamNonBlocking, prio) != cudaSuccess) { mx_set_error("mx_qmix_create: cudaStreamCreate failed"); delete q; return 1; }
+  }
   cudaEvent_t* evs[6] = {&q->ev_fork, &q->ev_prep, &q->ev_batch, &q->ev_hyper, &q->ev_core, &q->ev_hbwd};
   for (cudaEvent_t* e : evs) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
 #endif
