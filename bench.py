@@ -527,9 +527,8 @@ def run_engine(args):
         return
 
     # ---------------- e2e: host inputs through the drop-in API ----------------
-    buf.rng = "numpy"
     fresh = [synth_episodes(cfg, T, 1, rs, avail) for _ in range(8)]
-    h2d = sum(x.nbytes for x in fresh[0] if x is not None) + B * 8
+    h2d = sum(x.nbytes for x in fresh[0] if x is not None)
     d2h = 4
 
     def e2e_step(i):
@@ -544,18 +543,27 @@ def run_engine(args):
         tr.soft_target_updates()
         return float(info["loss"])                                                    # D2H read of the step's result (syncs)
 
-    for i in range(E2E_WARM):
-        e2e_step(i)
-    barrier()
+    def e2e_run(n):
+        for i in range(E2E_WARM):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n):
+            e2e_step(i)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+        return world * n / float(dt)
+
     n_e2e = max(E2E_MIN_STEPS, min(args.steps, 200))
-    t0 = time.perf_counter()
-    for i in range(n_e2e):
-        e2e_step(i)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
-    e2e_sps = world * n_e2e / float(e2e_s)
+    # (1) indices drawn per call from NumPy's process-global stream on the host, as the reference does (one extra H2D of B int64)
+    buf.rng = "numpy"
+    e2e_host_rng_sps = e2e_run(n_e2e)
+    # (2) the same NumPy stream continued ON THE DEVICE (RecReplayBuffer.adopt_numpy_rng(): bit-identical indices as long as nothing else
+    #     draws from np.random between two samples, which holds here; no index upload, no host draw) -- the headline e2e number
+    buf.adopt_numpy_rng()
+    e2e_sps = e2e_run(n_e2e)
 
     # same loop with the loss read lagging ONE step (copied to pinned memory asynchronously, read after the next step has been
     # enqueued): what a runner that logs train_info asynchronously sees.  Reported beside, not instead of, the synchronous number.
@@ -678,8 +686,10 @@ def run_engine(args):
                    step="CUDA graph: device MT19937 draw + gather + fused QMIX learner + one-launch reduce/clip/Adam/Polyak; state-only kernels (weight images, "
                         "mixer hypernets) on a forked graph branch beside the agent-net kernels" if (graph or tgraph) else "eager"),
         e2e=dict(value=e2e_sps, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=n_e2e,
+                 host_rng_value=e2e_host_rng_sps,       # same loop with np.random drawn on the host per call (+ B*8 bytes H2D): the reference's own mode
                  lagged_read_value=e2e_lagged_sps,      # same loop, each step's loss read one step late (asynchronous logging)
-                 path="RecReplayBuffer.insert(1 episode, pinned) + sample(np.random.choice) + QMix.train_policy_on_batch + soft_target_updates + D2H info"),
+                 path="RecReplayBuffer.insert(1 episode, pinned host memory -> H2D) + sample (NumPy's MT19937 stream continued on the device after "
+                      "adopt_numpy_rng()) + QMix.train_policy_on_batch + soft_target_updates + D2H read of the loss, every step"),
         gpu_launches=launches, kernels_per_step=kernels_per_step,
         roofline=roof, kernels=breakdown, kernel_sum_ms=round(ksum, 5),        # > ms_per_step when branches of the step graph overlap
         gather_gbs=gather_gbs,

@@ -399,7 +399,7 @@ MX_DEVINL void ln64_bwd_relu(bool act_tanh, float (&v)[RM][4], const float* u_s,
   }
 }
 
-template <int RM>
+template <int RM, bool MMA>
 __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, FrontBwdSmem sm) {
   constexpr int TM = 16 * RM;
   MX_DYN_SMEM(smem);
@@ -464,12 +464,12 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     // ---- GRU weight gradients: dW_ih = dgi^T x2 ; dW_hh = [dgi_r, dgi_z, dgi_n*r]^T h_{t-1} ----
     if (wgemm) {
       for (int nb = 0; nb < 3; ++nb) {
-        if (a.use_mma) mx_mma_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
+        if (MMA) mx_mma_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
         else mx_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
         if (a.no_gru) continue;
         const float* dgh = nb < 2 ? dgi_s + nb * 64 : dgn_s;
         const int ldd = nb < 2 ? sm.ldg : sm.ld64;
-        if (a.use_mma) mx_mma_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
+        if (MMA) mx_mma_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
         else mx_wgrad_block(dgh, ldd, hp_s, sm.ld64, TM, gp + L.whh + nb * 64 * MX_H, 64, MX_H, 0, 0, accum);
       }
       mx_colsum(dgi_s, sm.ldg, TM, MX_G, gp + L.bih, accum);
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     for (int i = 0; i < RM; ++i)
 #pragma unroll
       for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
-    if (a.use_mma) {       // tensor-core tiles (mx_mma.cuh): warp w owns 8 output columns; the result goes through da_s back to the (ty, tx) row layout
+    if (MMA) {       // tensor-core tiles (mx_mma.cuh): warp w owns 8 output columns; the result goes through da_s back to the (ty, tx) row layout
       float cfr[RM][4];
 #pragma unroll
       for (int i = 0; i < RM; ++i)
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     __syncthreads();
     // ---- fc2: dW2 = da2^T x1, db2 ; dx1 = da2 . W2 ----
     if (wgemm) {
-      if (a.use_mma) mx_mma_wgrad_block(da_s, sm.ld64, x_s, sm.ld64, TM, gp + L.w2, MX_H, MX_H, 0, 0, accum);
+      if (MMA) mx_mma_wgrad_block(da_s, sm.ld64, x_s, sm.ld64, TM, gp + L.w2, MX_H, MX_H, 0, 0, accum);
       else mx_wgrad_block(da_s, sm.ld64, x_s, sm.ld64, TM, gp + L.w2, MX_H, MX_H, 0, 0, accum);
       mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b2, accum);
     }
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     for (int i = 0; i < RM; ++i)
 #pragma unroll
       for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
-    if (a.use_mma) {
+    if (MMA) {
       float cfr[RM][4];
 #pragma unroll
       for (int i = 0; i < RM; ++i)
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     // ---- fc1: dW1 = da1^T x0, db1 ; dx0 = da1 . W1 (only for the LN0 gain/bias) ----
     if (wgemm) {
       for (int kb = 0; kb * 64 < I; ++kb) {
-        if (a.use_mma) mx_mma_wgrad_block(da_s, sm.ld64, x0_s + kb * 64, sm.ldi, TM, gp + L.w1, MX_H, I, 0, kb * 64, accum);
+        if (MMA) mx_mma_wgrad_block(da_s, sm.ld64, x0_s + kb * 64, sm.ldi, TM, gp + L.w1, MX_H, I, 0, kb * 64, accum);
         else mx_wgrad_block(da_s, sm.ld64, x0_s + kb * 64, sm.ldi, TM, gp + L.w1, MX_H, I, 0, kb * 64, accum);
       }
       mx_colsum(da_s, sm.ld64, TM, MX_H, gp + L.b1, accum);
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
         for (int i = 0; i < RM; ++i)
 #pragma unroll
           for (int jx = 0; jx < 4; ++jx) v[i][jx] = 0.f;
-        if (a.use_mma) {
+        if (MMA) {
           float cfr[RM][4];
 #pragma unroll
           for (int i = 0; i < RM; ++i)
@@ -774,7 +774,7 @@ static int front_bwd_pick_rm(int M, int in_dim, int sms) {
   return best;
 }
 
-template <int RM>
+template <int RM, bool MMA>
 static int front_bwd_launch(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
   const int TM = 16 * RM;
   FrontBwdSmem sm = front_bwd_smem(a.L.in_dim, TM);
@@ -782,7 +782,7 @@ static int front_bwd_launch(const FrontBwdArgs& a, int* nparts_used, cudaStream_
   const int ntiles = mx_ceil_div(a.M, TM);
   int grid = mx_num_sms();
   if (grid > ntiles) grid = ntiles;
-  auto kern = k_front_bwd<RM>;
+  auto kern = k_front_bwd<RM, MMA>;
 #if !MX_EMU
   if (smem > 227 * 1024) { mx_set_error("front_bwd: %zu bytes of shared memory needed (obs_dim too large)", smem); return 1; }
   static size_t configured = 0;
@@ -807,9 +807,13 @@ int mx_launch_front_bwd(const FrontBwdArgs& a_in, int* nparts_used, cudaStream_t
   a.use_mma = g_mx_front_bwd_mma ? 1 : 0;
   const int rm = g_mx_front_bwd_rm ? g_mx_front_bwd_rm : front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms());
   int rc;
-  if (rm == 3) rc = front_bwd_launch<3>(a, nparts_used, s);
-  else if (rm == 4) rc = front_bwd_launch<4>(a, nparts_used, s);
-  else rc = front_bwd_launch<2>(a, nparts_used, s);
+  if (a.use_mma) {        // separate instantiations: the FFMA kernel's register allocation must not pay for the mma path
+    if (rm == 3) rc = front_bwd_launch<3, true>(a, nparts_used, s);
+    else if (rm == 4) rc = front_bwd_launch<4, true>(a, nparts_used, s);
+    else rc = front_bwd_launch<2, true>(a, nparts_used, s);
+  } else if (rm == 3) rc = front_bwd_launch<3, false>(a, nparts_used, s);
+  else if (rm == 4) rc = front_bwd_launch<4, false>(a, nparts_used, s);
+  else rc = front_bwd_launch<2, false>(a, nparts_used, s);
   if (rc || !a.wgrad_external) return rc;
   return mx_launch_wgrad_tc(a, *nparts_used, s);      // one gradient partial per k_front_bwd CTA: the same rows of gpart
 }

@@ -145,6 +145,7 @@ static EncodeTiledFn encode_fn() {
 struct MxGatherTma {
   GatherTmaMaps maps;
   GatherTmaArgs args;
+  long long bytes_per_episode;
 };
 
 static bool encode_lines(EncodeTiledFn fn, CUtensorMap* m, void* base, long long rows, long long row_words, long long lines) {
@@ -182,6 +183,7 @@ void* mx_gather_tma_create(mx_replay* r) {
     if (lines > 0)
       ok = ok && encode_lines(fn, &g->maps.src3[nf], r->blob + src_off, r->cfg.capacity, ep_words, lines) &&
            encode_lines(fn, &g->maps.dst3[nf], r->blob + dst_off, r->cfg.max_batch, ep_words, lines);
+    g->bytes_per_episode += ep_words * 4;
     g->args.lines[nf] = (int)lines;
     g->args.nbig[nf] = (int)((lines + GT_ROWS - 1) / GT_ROWS);
     g->args.tail[nf] = (ep_words % GT_BOX) ? 1 : 0;
@@ -211,6 +213,9 @@ int g_mx_gather_tma = 1;
 int mx_launch_gather_tma(void* p, const int64_t* idx_dev, int B, cudaStream_t s) {
   if (!p || !g_mx_gather_tma) return -1;
   MxGatherTma* g = reinterpret_cast<MxGatherTma*>(p);
+  // Measured (tools/gather_sweep.py, 8m shapes, profiles/README.md): the TMA copy wins for small batches (B = 64: 65 % vs 61 % of the HBM peak),
+  // the vectorised loads for large ones (B = 1024: 83 % vs 93 %); crossover near 100 MB per gather.  gather_tma = 2 forces TMA at any size.
+  if (g_mx_gather_tma == 1 && (long long)g->bytes_per_episode * B > (96ll << 20)) return -1;
   GatherTmaArgs a = g->args;
   a.B = B;
   a.idx = (const long long*)idx_dev;

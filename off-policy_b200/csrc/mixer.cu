@@ -32,7 +32,7 @@ static MixSmem mix_smem_layout(const MxMixLayout& L, int TE) {
   m.o_hid = o; o += TE * m.ldM;
   m.o_q = o; o += TE * 32;
   m.o_vec = o; o += 8 * TE;         // b2, Q, Qn, dQ, valid, ...
-  m.o_wc = o; o += 2 * 64 * m.ldw;      // two weight-chunk buffers: the next chunk streams in while the current one is multiplied
+  m.o_wc = o; o += 64 * m.ldw;
   m.total = o;
   return m;
 }
@@ -106,69 +106,25 @@ __device__ MX_NOINLINE void tile_wgrad(const float* dY_s, int ldy, int Nout, con
   mx_colsum(dY_s, ldy, TE, Nout, db, accumulate);
 }
 
-// the state-only hypernetwork layers of one tile: h1/h2/hb (post-ReLU), p1 = hyper_w1(s), p2 = hyper_w2(s), b1 = hyper_b1(s).
-// The layers are a list of 64-row weight chunks; chunk i + 1 is streamed into the second staging buffer (cp.async) while chunk i is
-// multiplied, so one L2 round trip is exposed per tile instead of one per chunk (seven to nine chunks: this kernel was a chain of them).
-struct HyperChunk { const float* W; const float* b; const float* X; float* Y; int Nout, K, nc, ldx, ldy, relu; };
+// the state-only hypernetwork layers of one tile: h1/h2/hb (post-ReLU), p1 = hyper_w1(s), p2 = hyper_w2(s), b1 = hyper_b1(s)
 template <int RM>
 MX_DEVINL void mixer_hyper(const float* __restrict__ th, const MxMixLayout& L, const MixSmem& sm, float* smem) {
   float* s_s = smem + sm.o_s;
   float* h1_s = smem + sm.o_h1; float* h2_s = smem + sm.o_h2; float* hb_s = smem + sm.o_hb;
   float* p1_s = smem + sm.o_p1; float* b1_s = smem + sm.o_b1; float* p2_s = smem + sm.o_p2;
-  float* Wc0 = smem + sm.o_wc;
+  float* Wc = smem + sm.o_wc;
   const int NM = L.N * L.ME;
-  HyperChunk ch[12];
-  int n = 0;
-  auto add = [&](const float* X, int ldx, int K, int w, int b, int Nout, float* Y, int ldy, int relu) {
-    for (int nc = 0; nc * 64 < Nout && n < 12; ++nc) { ch[n].W = th + w; ch[n].b = th + b; ch[n].X = X; ch[n].Y = Y; ch[n].Nout = Nout; ch[n].K = K; ch[n].nc = nc; ch[n].ldx = ldx; ch[n].ldy = ldy; ch[n].relu = relu; ++n; }
-  };
-  // order: every first layer (inputs = the staged states) before the layers that consume their outputs
   if (L.layers == 2) {
-    add(s_s, sm.ldS, L.S, L.w1a, L.b1a, L.HY, h1_s, sm.ldH, 1);
-    add(s_s, sm.ldS, L.S, L.w2a, L.b2a, L.HY, h2_s, sm.ldH, 1);
-    add(s_s, sm.ldS, L.S, L.wb1, L.bb1, L.ME, b1_s, sm.ldM, 0);
-    add(s_s, sm.ldS, L.S, L.wb2a, L.bb2a, L.HY, hb_s, sm.ldH, 1);
-    add(h1_s, sm.ldH, L.HY, L.w1b, L.b1b, NM, p1_s, sm.ldP, 0);
-    add(h2_s, sm.ldH, L.HY, L.w2b, L.b2b, L.ME, p2_s, sm.ldM, 0);
+    tile_linear<RM>(s_s, sm.ldS, L.S, th + L.w1a, th + L.b1a, L.HY, h1_s, sm.ldH, true, Wc, sm.ldw);
+    tile_linear<RM>(h1_s, sm.ldH, L.HY, th + L.w1b, th + L.b1b, NM, p1_s, sm.ldP, false, Wc, sm.ldw);
+    tile_linear<RM>(s_s, sm.ldS, L.S, th + L.w2a, th + L.b2a, L.HY, h2_s, sm.ldH, true, Wc, sm.ldw);
+    tile_linear<RM>(h2_s, sm.ldH, L.HY, th + L.w2b, th + L.b2b, L.ME, p2_s, sm.ldM, false, Wc, sm.ldw);
   } else {
-    add(s_s, sm.ldS, L.S, L.w1b, L.b1b, NM, p1_s, sm.ldP, 0);
-    add(s_s, sm.ldS, L.S, L.w2b, L.b2b, L.ME, p2_s, sm.ldM, 0);
-    add(s_s, sm.ldS, L.S, L.wb1, L.bb1, L.ME, b1_s, sm.ldM, 0);
-    add(s_s, sm.ldS, L.S, L.wb2a, L.bb2a, L.HY, hb_s, sm.ldH, 1);
+    tile_linear<RM>(s_s, sm.ldS, L.S, th + L.w1b, th + L.b1b, NM, p1_s, sm.ldP, false, Wc, sm.ldw);
+    tile_linear<RM>(s_s, sm.ldS, L.S, th + L.w2b, th + L.b2b, L.ME, p2_s, sm.ldM, false, Wc, sm.ldw);
   }
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  auto stage = [&](int i) {
-    const HyperChunk& c = ch[i];
-    mx_stage_weight(Wc0 + (i & 1) * 64 * sm.ldw, sm.ldw, c.W, c.Nout, c.K, c.K, c.nc * 64, 0, (c.K + 3) & ~3, false);
-  };
-  stage(0);
-  for (int i = 0; i < n; ++i) {
-    if (i + 1 < n) stage(i + 1); else mx_cp_commit();      // (an empty group keeps "all but the newest group" = chunk i)
-    mx_cp_wait<1>();
-    __syncthreads();          // chunk i has landed for every thread; the outputs of chunk i - 1 are visible
-    const HyperChunk& c = ch[i];
-    const float* Wc = Wc0 + (i & 1) * 64 * sm.ldw;
-    float acc[RM][4];
-#pragma unroll
-    for (int r = 0; r < RM; ++r)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
-    mx_mm_nt<RM>(c.X, c.ldx, Wc, sm.ldw, (c.K + 3) & ~3, acc);
-#pragma unroll
-    for (int r = 0; r < RM; ++r)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int col = c.nc * 64 + tx + 16 * j;
-        float v = 0.f;
-        if (col < c.Nout) {
-          v = acc[r][j] + c.b[col];
-          if (c.relu) v = fmaxf(v, 0.f);
-        }
-        c.Y[(ty * RM + r) * c.ldy + col] = v;
-      }
-    __syncthreads();          // buffer i & 1 is free for chunk i + 2; Y is published
-  }
-  mx_cp_wait<0>();
+  tile_linear<RM>(s_s, sm.ldS, L.S, th + L.wb1, th + L.bb1, L.ME, b1_s, sm.ldM, false, Wc, sm.ldw);
+  tile_linear<RM>(s_s, sm.ldS, L.S, th + L.wb2a, th + L.bb2a, L.HY, hb_s, sm.ldH, true, Wc, sm.ldw);
 }
 
 template <int RM>

@@ -28,7 +28,7 @@ L = pb.L
 ep_bytes = 4 * (L.ep_obs + L.ep_share + L.ep_acts + L.ep_avail + L.ep_rew + L.ep_dones + L.ep_dones_env + L.ep_actidx)
 lib, K = capi.lib(), 20
 stream = torch.cuda.current_stream()
-for tma in (1, 0):      # TMA tile copies (default) vs 16-byte vector loads
+for tma in (2, 0):      # TMA tile copies (forced at every size) vs 16-byte vector loads
     lib.mx_set_option(b"gather_tma", tma)
     for B in (64, 128, 256, 512, 1024):
         sets = [torch.from_numpy(rs.permutation(E)[:B].astype(np.int64)).cuda() for _ in range(K)]     # distinct episodes: no reuse inside a batch
