@@ -744,7 +744,7 @@ int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
   int rpc = 1;
   while (rpc < 4 && mx_ceil_div(a.R, rpc) > 2 * sms) rpc *= 2;
   if (g_mx_gru_bwd_rpc == 1 || g_mx_gru_bwd_rpc == 2 || g_mx_gru_bwd_rpc == 4) rpc = g_mx_gru_bwd_rpc;
-  if (g_mx_gru_threads == 128 || (g_mx_gru_threads == 0 && g_mx_gru_bwd_rpc == 0)) {      // default at every size (r02 sweeps)
+  if (g_mx_gru_threads == 128 || (g_mx_gru_threads == 0 && g_mx_gru_bwd_rpc == 0 && a.T >= 8)) {      // default at every size (r02 sweeps)
     MX_LAUNCH_PDL(k_gru_bwd2, dim3(a.R), dim3(BWD2_THREADS), 0, s, a);
     MX_COUNT();
     MX_MARK("k_gru_bwd", s);

@@ -559,7 +559,7 @@ int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s) {
   while (rpc < 4 && mx_ceil_div(a.R, rpc) * nets > 2 * sms) rpc *= 2;   // two CTAs fit per SM (<= 128 registers): co-resident CTAs hide each other's latencies
   if (g_mx_gru_fwd_rpc == 1 || g_mx_gru_fwd_rpc == 2 || g_mx_gru_fwd_rpc == 4) rpc = g_mx_gru_fwd_rpc;
   // the 128-thread kernel (one row per CTA); the 256-thread kernels stay behind gru_threads=256 / gru_*_rpc
-  if (g_mx_gru_threads == 128 || (g_mx_gru_threads == 0 && g_mx_gru_fwd_rpc == 0)) {      // default at every size (r02 sweeps: 3m 174 vs 188 us, 2s3z 555 vs 619, 8m 1408 vs 1494)
+  if (g_mx_gru_threads == 128 || (g_mx_gru_threads == 0 && g_mx_gru_fwd_rpc == 0 && a.T + 1 >= 8)) {      // (one-step "branch" calls of R-MADDPG keep the multi-row CTAs: a CTA per row would spend its time loading W_hh)      // default at every size (r02 sweeps: 3m 174 vs 188 us, 2s3z 555 vs 619, 8m 1408 vs 1494)
     MX_LAUNCH_PDL(k_gru_fwd2, dim3(a.R, nets), dim3(GRU2_THREADS), 0, s, a);
     MX_COUNT();
     MX_MARK("k_gru_fwd", s);
