@@ -14,8 +14,7 @@
 #include "mx_internal.h"
 #include "mx_kernels.h"
 
-#define MID_WARPS 16
-#define MID_THREADS (32 * MID_WARPS)
+#define MID_WARPS_MAX 16      // 16 warps per CTA when the per-warp slices fit in shared memory, 8 otherwise (SMAC 8m: 8 agents x 14 actions)
 // Head-weight row k lives at k * 66 with column j at j + (j >= 32): the two half-warps of the A <= 16 path (columns 0..31 and
 // 32..63 of the same rows) then read banks 2k + j and 2k + 1 + j -- all 32 lanes conflict-free; the LayerNorm output row uses the
 // same one-float gap, so its two broadcast reads per step also hit different banks.
@@ -24,7 +23,7 @@
 MX_DEVINL int mid_col(int j) { return j + (j >> 5); }
 
 struct MidSmem { int o_wq, o_bq, o_ln, o_y, o_dw, o_db, o_dg, o_stage, stage_ld, total; };
-static MidSmem mid_smem(int A, int N, int gP, int gM) {
+static MidSmem mid_smem(int A, int N, int gP, int gM, int MID_WARPS) {
   MidSmem s;
   int o = 0;
   s.o_wq = o; o += 2 * 32 * MID_WLD;            // [net][32][65]
@@ -87,7 +86,9 @@ MX_DEVINL void mid_argmax(float v, int A, int lane, float& best, int& idx) {
   best = bv; idx = bi;
 }
 
-__global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
+template <int MID_WARPS>
+__global__ void __launch_bounds__(32 * MID_WARPS) k_mid(MidArgs a, MidSmem sm) {
+  constexpr int MID_THREADS = 32 * MID_WARPS;
   MX_DYN_SMEM(smem);
   const MxMixLayout L = a.mix.L;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -311,28 +312,42 @@ __global__ void __launch_bounds__(MID_THREADS) k_mid(MidArgs a, MidSmem sm) {
   }
 }
 
+static int mid_pick_warps(const MidArgs& a) {      // 0: does not fit even with 8 warps
+  for (int w = MID_WARPS_MAX; w >= 8; w >>= 1) {
+    const MidSmem sm = mid_smem(a.A, a.N, a.mix.gP, a.mix.gM, w);
+    if ((size_t)sm.total * sizeof(float) + 16 <= 220 * 1024) return w;
+  }
+  return 0;
+}
 int mx_mid_supported(const MidArgs& a) {
   if (!(mx_mixer_split_supported(a.mix.L) && a.A <= 32 && a.N <= 32)) return 0;
-  const MidSmem sm = mid_smem(a.A, a.N, a.mix.gP, a.mix.gM);
-  return (size_t)sm.total * sizeof(float) + 16 <= 200 * 1024;          // the per-warp operand staging must fit (N <= ~11 at A = 14)
+  return mid_pick_warps(a) != 0;          // the per-warp operand staging must fit
 }
 
-int mx_launch_mid(const MidArgs& a, int* parts_used, cudaStream_t s) {
+template <int W>
+static int mid_launch(const MidArgs& a, int* parts_used, cudaStream_t s) {
   const int E = a.mix.B * a.T;
-  int grid = mx_ceil_div(E, MID_WARPS);
+  int grid = mx_ceil_div(E, W);
   if (grid > mx_num_sms()) grid = mx_num_sms();
-  MidSmem sm = mid_smem(a.A, a.N, a.mix.gP, a.mix.gM);
+  MidSmem sm = mid_smem(a.A, a.N, a.mix.gP, a.mix.gM, W);
   const size_t bytes = (size_t)sm.total * sizeof(float) + 16;
 #if !MX_EMU
   static size_t configured = 0;
   if (bytes > 48 * 1024 && bytes > configured) {
-    if (cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) { mx_set_error("mid: smem %zu too large", bytes); return 1; }
+    if (cudaFuncSetAttribute(k_mid<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) { mx_set_error("mid: smem %zu too large", bytes); return 1; }
     configured = bytes;
   }
 #endif
-  MX_LAUNCH_PDL(k_mid, dim3(grid), dim3(MID_THREADS), bytes, s, a, sm);
+  MX_LAUNCH_PDL(k_mid<W>, dim3(grid), dim3(32 * W), bytes, s, a, sm);
   MX_COUNT();
   MX_MARK("k_mid", s);
   *parts_used = grid;
   return MX_CHECK_LAUNCH("mid");
+}
+int mx_launch_mid(const MidArgs& a, int* parts_used, cudaStream_t s) {
+  const int w = mid_pick_warps(a);
+  if (w == 16) return mid_launch<16>(a, parts_used, s);
+  if (w == 8) return mid_launch<8>(a, parts_used, s);
+  mx_set_error("mid: configuration does not fit (N %d, A %d)", a.N, a.A);
+  return 1;
 }

@@ -61,6 +61,32 @@ def test_mixer_shapes_vs_oracle(emu_engine, split, mixer_hidden, hyper_hidden, n
         lib.mx_set_option(b"mixer_split", 1)
 
 
+def test_fused_mid_kernel_eight_warp_variant_vs_oracle(emu_engine):
+    """SMAC 8m widths (8 agents x 14 actions): the per-warp operand slices of k_mid no longer fit 16 warps into shared memory, so the
+    launcher takes the 8-warp instantiation (mid.cu mid_pick_warps).  Product configuration (debug outputs off), PER + Huber."""
+    from oracle.qmix import QmixConfig, synth_batch
+    lib = emu_engine.lib()
+    cfg = QmixConfig(n_agents=8, obs_dim=9, act_dim=14, state_dim=11, gain=1.0, use_per=True, huber=True, huber_delta=0.8)
+    B, T = 4, 5
+    L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T, debug=False)
+    w = np.random.RandomState(4).rand(B) * 0.9 + 0.1
+    batch = synth_batch(cfg, B, T, seed=11, avail_p=0.7, var_len=True) + (w, np.arange(B))
+    # gradients are held to 1e-4 as everywhere; some fc2 gradient entries here are ~6e-6, the size of Adam's eps, where the first
+    # Adam step amplifies fp32 round-off of the gradient -- hence the wider bound on the PARAMETERS only
+    c0 = lib.mx_launch_count()
+    qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=3e-2)
+    with_mid = lib.mx_launch_count() - c0
+    lib.mx_set_option(b"mid_fused", 0)
+    try:
+        L2, args2, pol2, tr2 = qc.oracle_and_trainer(cfg, B, T, debug=False)
+        c0 = lib.mx_launch_count()
+        qc.compare_step(L2, pol2, tr2, batch, cfg, steps=2, param_tol=3e-2)
+        separate = lib.mx_launch_count() - c0
+    finally:
+        lib.mx_set_option(b"mid_fused", 1)
+    assert separate > with_mid, (separate, with_mid)          # k_mid really was the kernel that ran
+
+
 @pytest.mark.parametrize("name", ["qmix_small", "qmix_small_huber_nodq", "qmix_small_per", "qmix_small_hyper1", "qmix_5ag"])
 def test_product_configuration_matches_reference_golden(emu_engine, name):
     """debug outputs off = what bench.py / the runner execute: k_qhead + k_mix_core + k_qhead_bwd run as the single k_mid."""
