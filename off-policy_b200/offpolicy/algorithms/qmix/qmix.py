@@ -87,6 +87,10 @@ class QMix(object):
         self.policy_agents = {p: sorted(a for a in range(num_agents) if policy_mapping_fn(a) == p) for p in self.policies}
         if self.policy_ids != ["policy_0"]:
             raise NotImplementedError("B200 QMIX path: only the shared-policy configuration ('policy_0') is implemented")
+        if getattr(args, "use_popart", False) and getattr(self, "_mlp", False):
+            # mqmix.py:184-187 normalises the TD target with PopArt; the recurrent qmix.py:44-45 only constructs the normaliser and
+            # never applies it, so the flag is a no-op there and needs no check
+            raise NotImplementedError("B200 M_QMix path: --use_popart is not implemented")
         self.episode_length = args.episode_length if episode_length is None else episode_length
         self.use_same_share_obs = getattr(args, "use_same_share_obs", True)
         self.vdn = bool(vdn)

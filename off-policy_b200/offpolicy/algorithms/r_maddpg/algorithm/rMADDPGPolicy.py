@@ -108,8 +108,8 @@ class R_MADDPGPolicy(object):
         for flag, want in (("use_conv1d", False),):      # fail loudly, never approximate
             if getattr(self.args, flag, want) != want:
                 raise NotImplementedError("B200 R-MADDPG path requires %s=%s" % (flag, want))
-        if getattr(self.args, "layer_N", 1) != 1 or getattr(self.args, "hidden_size", 64) != 64:
-            raise NotImplementedError("B200 R-MADDPG path requires layer_N=1, hidden_size=64")
+        if getattr(self.args, "layer_N", 1) != 1 or getattr(self.args, "hidden_size", 64) != 64 or getattr(self.args, "recurrent_N", 1) != 1:
+            raise NotImplementedError("B200 R-MADDPG path requires layer_N=1, recurrent_N=1, hidden_size=64")
         self.central_obs_dim, self.central_act_dim = policy_config["cent_obs_dim"], policy_config["cent_act_dim"]
         self.obs_space, self.act_space = policy_config["obs_space"], policy_config["act_space"]
         self.obs_dim, self.act_dim = space_dim(self.obs_space), space_dim(self.act_space)

@@ -88,7 +88,7 @@ def test_trainer_rejects_what_it_does_not_implement(emu_engine):
     margs = mdc.make_args(MaddpgConfig(n_agents=2, obs_dim=5, act_dim=2, state_dim=6), 4)
     minfo = dict(obs_space=[5], share_obs_space=[6], act_space=mdc.Box(2), cent_obs_dim=6, cent_act_dim=4)
     R_MADDPGPolicy({"args": margs, "device": emu_engine.device()}, minfo)
-    for flag, val in (("layer_N", 2), ("hidden_size", 128), ("prev_act_inp", True)):
+    for flag, val in (("layer_N", 2), ("hidden_size", 128), ("prev_act_inp", True), ("recurrent_N", 2)):
         a2 = types.SimpleNamespace(**vars(margs))
         setattr(a2, flag, val)
         with pytest.raises(NotImplementedError):
@@ -96,6 +96,14 @@ def test_trainer_rejects_what_it_does_not_implement(emu_engine):
     pols = {"policy_%d" % i: QMixPolicy({"args": args, "device": emu_engine.device()}, info) for i in range(3)}
     with pytest.raises(NotImplementedError):                              # one policy per agent (share_policy=False)
         QMix(args, 3, pols, lambda a: "policy_%d" % a, device=emu_engine.device(), episode_length=4)
+    # PopArt: applied by the reference only in mqmix.py:184-187 (the recurrent qmix.py constructs it and never uses it)
+    from offpolicy.algorithms.mqmix.mqmix import M_QMix
+    a2 = types.SimpleNamespace(**vars(args))
+    a2.use_popart = True
+    one = {"policy_0": pols["policy_0"]}
+    QMix(a2, 3, one, lambda a: "policy_0", device=emu_engine.device(), episode_length=4)       # a no-op flag there: accepted
+    with pytest.raises(NotImplementedError):
+        M_QMix(a2, 3, one, lambda a: "policy_0", device=emu_engine.device())
     from offpolicy.utils.rec_buffer import RecReplayBuffer
     with pytest.raises(NotImplementedError):
         RecReplayBuffer({"policy_0": info}, {"policy_0": [0, 1, 2]}, 8, 4, False, True)               # use_same_share_obs=False
