@@ -346,15 +346,15 @@ struct FrontBwdSmem {
   int ldi, ld64, ldg;
   int o_dgi, o_dgn, o_x, o_hp, o_u, o_da, o_x0, o_xh0, o_dx0, o_wc, o_col, o_stat, o_lnp, total;
 };
-static FrontBwdSmem front_bwd_smem(int in_dim, int TM) {
+static FrontBwdSmem front_bwd_smem(int in_dim, int TM, bool gru_ext = false) {     // gru_ext: k_gru_wgrad owns dW_ih / dW_hh (no h_{t-1}, dgi_n * r tiles here)
   FrontBwdSmem s;
   const int I64 = mx_round_up(in_dim, 64);
   s.ldi = mx_ld(I64); s.ld64 = mx_ld(64); s.ldg = mx_ld(MX_G);
   int o = 0;
   s.o_dgi = o; o += TM * s.ldg;     // dgi tile (r,z,n)
-  s.o_dgn = o; o += TM * s.ld64;    // dgi_n * r  (gradient reaching W_hn h)
+  s.o_dgn = o; o += gru_ext ? 0 : TM * s.ld64;    // dgi_n * r  (gradient reaching W_hn h)
   s.o_x = o; o += TM * s.ld64;      // r gate (staging), then x2, later x1
-  s.o_hp = o; o += TM * s.ld64;     // h_{t-1}
+  s.o_hp = o; o += gru_ext ? 0 : TM * s.ld64;     // h_{t-1}
   s.o_u = o; o += TM * s.ld64;      // u2, later u1 (post-ReLU, pre-LN)
   s.o_da = o; o += TM * s.ld64;     // gradient w.r.t. the Linear output (after ReLU mask)
   s.o_x0 = o; o += TM * s.ldi;      // raw input rows, then LN0 output (fc1 input)
@@ -420,6 +420,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
   const bool ldx_vec = (a.ldx & 3) == 0;
   const bool wg = !a.skip_wgrad;
   const bool wgemm = wg && !a.wgrad_external;      // the weight-gradient GEMMs and bias column sums run here (else: k_wgrad_tc)
+  const bool gru_here = !a.gru_wgrad_ext;          // else k_gru_wgrad (beside this kernel) produces dW_ih / dW_hh / db_ih / db_hh
   float* dx0_s = smem + sm.o_dx0;
   float* gp = a.gpart + (size_t)blockIdx.x * a.P;
   for (int i = tid; i < 2 * I64 + 4 * 64; i += MX_TILE_THREADS) col0g[i] = 0.f;
@@ -433,10 +434,11 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     __syncthreads();
     // ---- stage the tile's raw operands with cp.async: dgi, r gate, u2, u1?, h_{t-1}, the input rows, LN statistics ----
     mx_stage_rows(dgi_s, sm.ldg, a.dgi, MX_G, m0, a.M, TM, MX_G);
-    if (!a.no_gru) mx_stage_rows(x_s, sm.ld64, a.gates, MX_G, m0, a.M, TM, MX_H);          // r gate = first 64 columns of the gates row
+    if (!gru_here) {}
+    else if (!a.no_gru) mx_stage_rows(x_s, sm.ld64, a.gates, MX_G, m0, a.M, TM, MX_H);          // r gate = first 64 columns of the gates row
     else for (int i = tid; i < TM * sm.ld64; i += MX_TILE_THREADS) x_s[i] = 0.f;
     mx_stage_rows(u_s, sm.ld64, a.u2, MX_H, m0, a.M, TM, MX_H);
-    for (int r = tid >> 4; r < TM; r += MX_TILE_THREADS / 16) {
+    for (int r = tid >> 4; gru_here && r < TM; r += MX_TILE_THREADS / 16) {
       const int m = m0 + r;
       const bool has = !a.no_gru && m < a.M && ((m / N) % T1) > 0;
       float* d = hp_s + r * sm.ld64 + 4 * tx;
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     }
     mx_cp_wait<0>();
     __syncthreads();
-    for (int idx = tid; idx < TM * MX_H; idx += MX_TILE_THREADS) {
+    for (int idx = tid; gru_here && idx < TM * MX_H; idx += MX_TILE_THREADS) {
       const int r = idx >> 6, c = idx & 63;
       const int o = r * sm.ld64 + c;
       dgn_s[o] = dgi_s[r * sm.ldg + 2 * MX_H + c] * x_s[o];                                // dgi_n * r
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
     }
     __syncthreads();
     // ---- GRU weight gradients: dW_ih = dgi^T x2 ; dW_hh = [dgi_r, dgi_z, dgi_n*r]^T h_{t-1} ----
-    if (wgemm) {
+    if (wgemm && gru_here) {
       for (int nb = 0; nb < 3; ++nb) {
         if (MMA) mx_mma_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
         else mx_wgrad_block(dgi_s + nb * 64, sm.ldg, x_s, sm.ld64, TM, gp + L.wih, MX_G, MX_H, nb * 64, 0, accum);
@@ -688,6 +690,123 @@ __global__ void __launch_bounds__(MX_TILE_THREADS) k_front_bwd(FrontBwdArgs a, F
   }
 }
 
+
+// =====================================================================================================
+// k_gru_wgrad: the GRU weight gradients of the time-batched backward as their own kernel,
+//   dW_ih = dgi^T x2, db_ih ;  dW_hh = [dgi_r, dgi_z, dgi_n * r]^T h_{t-1}, db_hh
+// They depend only on what k_gru_bwd left (dgi) and on saved forward rows, not on k_front_bwd's data-gradient chain, so the QMIX
+// step launches this on the forked branch BESIDE k_front_bwd (option gru_wgrad_split): same tiles, same grid, CTA b of both kernels
+// fills disjoint columns of gradient partial b; the two CTAs fit one SM together (shared memory ~77 + ~134 KB at 3m).
+// 256 threads at <= 128 registers so that a CTA of each kernel is resident together.  Two passes per tile (W_ih, then W_hh); thread
+// (tn, tk) owns rows {64 g + 2 tn, + 1 : g = 0..2} x columns 8 tk .. + 7 of the pass's matrix: per tile row 3 LDS.64 + 2 LDS.128 feed
+// 24 FFMA2 (pairs along the gate-row dimension, the x / h value duplicated).
+// =====================================================================================================
+struct GruWgradSmem { int ld64, ldg, o_dgi, o_dgn, o_x, o_hp, o_stat, o_lnp, total; };
+static GruWgradSmem gru_wgrad_smem(int TM) {
+  GruWgradSmem s;
+  s.ld64 = mx_ld(64); s.ldg = mx_ld(MX_G);
+  int o = 0;
+  s.o_dgi = o; o += TM * s.ldg;
+  s.o_dgn = o; o += TM * s.ld64;     // r gate, then dgi_n * r in place
+  s.o_x = o; o += TM * s.ld64;       // u2, then x2 = LN2(u2) in place
+  s.o_hp = o; o += TM * s.ld64;      // h_{t-1}
+  s.o_stat = o; o += 2 * TM;
+  s.o_lnp = o; o += 2 * 64;
+  s.total = o;
+  return s;
+}
+
+template <int RM>
+__global__ void __launch_bounds__(MX_TILE_THREADS, 2) k_gru_wgrad(FrontBwdArgs a, GruWgradSmem sm) {
+  constexpr int TM = 16 * RM;
+  MX_DYN_SMEM(smem);
+  const MxNetLayout L = a.L;
+  const float* __restrict__ th = a.theta;
+  float* dgi_s = smem + sm.o_dgi; float* dgn_s = smem + sm.o_dgn; float* x_s = smem + sm.o_x; float* hp_s = smem + sm.o_hp;
+  float* st2_s = smem + sm.o_stat; float* ln2g_s = smem + sm.o_lnp; float* ln2b_s = ln2g_s + 64;
+  const int tid = threadIdx.x, tx = tid & 15;
+  const int tk = tid & 7, tn = tid >> 3;
+  const int ntiles = (a.M + TM - 1) / TM;
+  const int T1 = a.T1 > 0 ? a.T1 : a.T + 1, N = a.N;
+  float* gp = a.gpart + (size_t)blockIdx.x * a.P;
+  if (tid < 64) { ln2g_s[tid] = th[L.ln2_g + tid]; ln2b_s[tid] = th[L.ln2_b + tid]; }
+  int iter = 0;
+  MX_PDL_WAIT();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+    const int m0 = tile * TM;
+    __syncthreads();
+    mx_stage_rows(dgi_s, sm.ldg, a.dgi, MX_G, m0, a.M, TM, MX_G);
+    mx_stage_rows(dgn_s, sm.ld64, a.gates, MX_G, m0, a.M, TM, MX_H);          // r gate = first 64 columns of the gates row
+    mx_stage_rows(x_s, sm.ld64, a.u2, MX_H, m0, a.M, TM, MX_H);
+    for (int r = tid >> 4; r < TM; r += MX_TILE_THREADS / 16) {
+      const int m = m0 + r;
+      const bool has = m < a.M && ((m / N) % T1) > 0;
+      float* d = hp_s + r * sm.ld64 + 4 * tx;
+      if (has) mx_cp16(d, a.hall + (size_t)(m - N) * MX_H + 4 * tx);
+      else if (m < a.M && a.h0) mx_cp16(d, a.h0 + (size_t)m * MX_H + 4 * tx);
+      else mx_st4(d, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    mx_cp_commit();
+    for (int i = tid; i < 2 * TM; i += MX_TILE_THREADS) {
+      const int m = m0 + (i >> 1);
+      st2_s[i] = m < a.M ? a.st2[2 * (size_t)m + (i & 1)] : 0.f;
+    }
+    mx_cp_wait<0>();
+    __syncthreads();
+    for (int idx = tid; idx < TM * MX_H; idx += MX_TILE_THREADS) {
+      const int r = idx >> 6, c = idx & 63;
+      const int o = r * sm.ld64 + c;
+      dgn_s[o] = dgi_s[r * sm.ldg + 2 * MX_H + c] * dgn_s[o];                              // dgi_n * r
+      x_s[o] = (m0 + r < a.M) ? (x_s[o] - st2_s[2 * r]) * st2_s[2 * r + 1] * ln2g_s[c] + ln2b_s[c] : 0.f;   // x2 = LN2(u2)
+    }
+    __syncthreads();
+    const bool accum = iter > 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const float* X_s = pass ? hp_s : x_s;
+      const float* D2_s = pass ? dgn_s + 2 * tn : dgi_s + 2 * MX_H + 2 * tn;      // the n-gate rows: dgi_n for W_in, dgi_n * r for W_hn
+      const int ld2 = pass ? sm.ld64 : sm.ldg;
+      float2 acc[3][8];
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[g][k] = make_float2(0.f, 0.f);
+#pragma unroll 2
+      for (int r = 0; r < TM; ++r) {
+        const float4 x0 = mx_ld4(X_s + r * sm.ld64 + 8 * tk), x1 = mx_ld4(X_s + r * sm.ld64 + 8 * tk + 4);
+        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const float2 d0 = *reinterpret_cast<const float2*>(dgi_s + r * sm.ldg + 2 * tn);
+        const float2 d1 = *reinterpret_cast<const float2*>(dgi_s + r * sm.ldg + MX_H + 2 * tn);
+        const float2 d2 = *reinterpret_cast<const float2*>(D2_s + r * ld2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 xx = make_float2(xs[k], xs[k]);
+          acc[0][k] = mx_ffma2(d0, xx, acc[0][k]);
+          acc[1][k] = mx_ffma2(d1, xx, acc[1][k]);
+          acc[2][k] = mx_ffma2(d2, xx, acc[2][k]);
+        }
+      }
+      float* W = gp + (pass ? L.whh : L.wih);
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {          // the two rows of the pair
+          float* w = W + (size_t)(64 * g + 2 * tn + h) * MX_H + 8 * tk;
+          float4 lo = make_float4(h ? acc[g][0].y : acc[g][0].x, h ? acc[g][1].y : acc[g][1].x, h ? acc[g][2].y : acc[g][2].x, h ? acc[g][3].y : acc[g][3].x);
+          float4 hi = make_float4(h ? acc[g][4].y : acc[g][4].x, h ? acc[g][5].y : acc[g][5].x, h ? acc[g][6].y : acc[g][6].x, h ? acc[g][7].y : acc[g][7].x);
+          if (accum) {
+            const float4 p0 = mx_ld4(w), p1 = mx_ld4(w + 4);
+            lo.x += p0.x; lo.y += p0.y; lo.z += p0.z; lo.w += p0.w; hi.x += p1.x; hi.y += p1.y; hi.z += p1.z; hi.w += p1.w;
+          }
+          mx_st4(w, lo); mx_st4(w + 4, hi);
+        }
+    }
+    mx_colsum(dgi_s, sm.ldg, TM, MX_G, gp + L.bih, accum);
+    mx_colsum(dgi_s, sm.ldg, TM, 2 * MX_H, gp + L.bhh, accum);
+    mx_colsum(dgn_s, sm.ld64, TM, MX_H, gp + L.bhh + 2 * MX_H, accum);
+  }
+}
+
 // =====================================================================================================
 // launchers
 // =====================================================================================================
@@ -761,11 +880,11 @@ int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
 
 // Tile height: the grid is one persistent CTA per SM, so the kernel takes `waves` tile-times; pick the 16*RM rows per tile that
 // minimise waves * (fixed per-tile cost + RM) -- e.g. 3m: 5856 rows = 183 tiles of 32 (2 waves) but 122 tiles of 48 (1 wave).
-static int front_bwd_pick_rm(int M, int in_dim, int sms) {
+static int front_bwd_pick_rm(int M, int in_dim, int sms, bool gru_ext) {
   int best = 2;
   double best_cost = 1e30;
   for (int rm = 2; rm <= 4; ++rm) {
-    FrontBwdSmem sm = front_bwd_smem(in_dim, 16 * rm);
+    FrontBwdSmem sm = front_bwd_smem(in_dim, 16 * rm, gru_ext);
     if ((size_t)sm.total * sizeof(float) + 16 > 227 * 1024) continue;
     const int tiles = mx_ceil_div(M, 16 * rm);
     const double cost = (double)mx_ceil_div(tiles, sms) * (1.0 + rm);
@@ -777,7 +896,7 @@ static int front_bwd_pick_rm(int M, int in_dim, int sms) {
 template <int RM, bool MMA>
 static int front_bwd_launch(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
   const int TM = 16 * RM;
-  FrontBwdSmem sm = front_bwd_smem(a.L.in_dim, TM);
+  FrontBwdSmem sm = front_bwd_smem(a.L.in_dim, TM, a.gru_wgrad_ext != 0);
   const size_t smem = (size_t)sm.total * sizeof(float) + 16;
   const int ntiles = mx_ceil_div(a.M, TM);
   int grid = mx_num_sms();
@@ -796,6 +915,7 @@ static int front_bwd_launch(const FrontBwdArgs& a, int* nparts_used, cudaStream_
 }
 
 extern int g_mx_front_bwd_rm;
+int g_mx_gru_wgrad_split = 1;    // 1 (default): the QMIX step runs the GRU weight gradients as k_gru_wgrad on the forked branch beside k_front_bwd
 int g_mx_front_bwd_mma = 0;      // 1: the GEMMs of k_front_bwd on mma.sync 3xTF32 tiles (mx_mma.cuh); 0 (default): FFMA micro-kernels.  Measured on B200
                                  // (profiles/r02_option_sweeps.md): the legacy mma.sync TF32 path is SLOWER here -- k_front_bwd 60.3 vs 50.0 us at 3m, 8m step 2.22 vs 1.52 ms
 bool mx_front_bwd_tc_usable(const FrontBwdArgs& a);
@@ -805,7 +925,7 @@ int mx_launch_front_bwd(const FrontBwdArgs& a_in, int* nparts_used, cudaStream_t
   FrontBwdArgs a = a_in;
   a.wgrad_external = mx_wgrad_tc_usable(a) ? 1 : 0;
   a.use_mma = g_mx_front_bwd_mma ? 1 : 0;
-  const int rm = g_mx_front_bwd_rm ? g_mx_front_bwd_rm : front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms());
+  const int rm = g_mx_front_bwd_rm ? g_mx_front_bwd_rm : front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms(), a.gru_wgrad_ext != 0);
   int rc;
   if (a.use_mma) {        // separate instantiations: the FFMA kernel's register allocation must not pay for the mma path
     if (rm == 3) rc = front_bwd_launch<3, true>(a, nparts_used, s);
@@ -816,4 +936,36 @@ int mx_launch_front_bwd(const FrontBwdArgs& a_in, int* nparts_used, cudaStream_t
   else rc = front_bwd_launch<2, false>(a, nparts_used, s);
   if (rc || !a.wgrad_external) return rc;
   return mx_launch_wgrad_tc(a, *nparts_used, s);      // one gradient partial per k_front_bwd CTA: the same rows of gpart
+}
+
+// ---- k_gru_wgrad beside k_front_bwd ----
+bool mx_wgrad_tc_usable(const FrontBwdArgs& a);
+bool mx_gru_wgrad_split_usable(const FrontBwdArgs& a) {
+  if (!g_mx_gru_wgrad_split || g_mx_front_bwd_mma || a.no_gru || a.skip_wgrad) return false;
+  return !mx_front_bwd_tc_usable(a) && !mx_wgrad_tc_usable(a);
+}
+template <int RM>
+static int gru_wgrad_launch(const FrontBwdArgs& a, cudaStream_t s) {
+  const int TM = 16 * RM;
+  GruWgradSmem sm = gru_wgrad_smem(TM);
+  const size_t smem = (size_t)sm.total * sizeof(float) + 16;
+  const int ntiles = mx_ceil_div(a.M, TM);
+  int grid = mx_num_sms();
+  if (grid > ntiles) grid = ntiles;
+#if !MX_EMU
+  static size_t configured = 0;
+  if (smem > configured) { cudaFuncSetAttribute(k_gru_wgrad<RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+#endif
+  MX_LAUNCH_PDL(k_gru_wgrad<RM>, dim3(grid), dim3(MX_TILE_THREADS), smem, s, a, sm);
+  MX_COUNT();
+  MX_MARK("k_gru_wgrad", s);
+  return MX_CHECK_LAUNCH("gru_wgrad");
+}
+// `a` must be the arguments the following mx_launch_front_bwd call gets (gru_wgrad_ext = 1): same tile height, same grid, so CTA b
+// of both kernels writes gradient partial b
+int mx_launch_gru_wgrad(const FrontBwdArgs& a, cudaStream_t s) {
+  const int rm = g_mx_front_bwd_rm ? g_mx_front_bwd_rm : front_bwd_pick_rm(a.M, a.L.in_dim, mx_num_sms(), true);
+  if (rm == 3) return gru_wgrad_launch<3>(a, s);
+  if (rm == 4) return gru_wgrad_launch<4>(a, s);
+  return gru_wgrad_launch<2>(a, s);
 }

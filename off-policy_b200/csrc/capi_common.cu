@@ -26,7 +26,8 @@ int g_mx_mid_fused = 1;        // 1: k_qhead + k_mix_core + k_qhead_bwd as ONE k
                                //    outputs are requested; 0: three launches
 int g_mx_gru_fwd_rpc = 0;      // tuning overrides: sequence rows per CTA of the recurrence kernels (0 = automatic; 1, 2 or 4)
 int g_mx_gru_bwd_rpc = 0;
-int g_mx_overlap_rows = 12288; // measured on B200 (profiles/r01l_overlap_sweep.log): 3m (5 856 rows) +16 %, 8m (61 952 rows) -8 %
+int g_mx_overlap_rows = 1 << 20; // measured on B200 with the fused k_mid in place (profiles/r02_option_sweeps.md, visit 12): forked branch 3m +16 %, 2s3z (19 360 rows) +12 %,
+                               // 8m (61 952 rows) +7 %; round 1 (without k_mid for 8 agents) had 8m at -8 % and a 12 288-row limit.  Beyond 1M rows: unmeasured, serial
 int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "mixer_split")) { g_mx_mixer_split = value; return 0; }
   if (!strcmp(name, "mixer_split_rm")) { g_mx_mixer_split_rm = value; return 0; }
@@ -37,6 +38,7 @@ int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "side_prio")) { g_mx_side_prio = value; return 0; }
   if (!strcmp(name, "hyper_late")) { g_mx_hyper_late = value; return 0; }
   if (!strcmp(name, "front_bwd_mma")) { g_mx_front_bwd_mma = value; return 0; }
+  if (!strcmp(name, "gru_wgrad_split")) { g_mx_gru_wgrad_split = value; return 0; }
   if (!strcmp(name, "gather_tma")) { g_mx_gather_tma = value; return 0; }      // 1: episode gather on the TMA unit (default), 0: vectorised loads
   if (!strcmp(name, "gru_threads")) { g_mx_gru_threads = value; return 0; }      // 0: by size, 128 / 256: force the recurrence kernels' CTA width
   if (!strcmp(name, "gru_fwd_rpc")) { g_mx_gru_fwd_rpc = value; return 0; }

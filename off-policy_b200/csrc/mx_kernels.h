@@ -172,7 +172,10 @@ struct FrontBwdArgs {
   float* tc_imgT;          // scratch for the transposed TF32 weight images of the all-tensor-core backward (option wgrad_tc = 2)
   int tc_imgT_ready;       // 1: the caller already built them for the current parameters (mx_launch_tc_prep_weights_T)
   int act_tanh;            // 1: tanh instead of ReLU (the saved u1 / u2 are the activations' outputs: tanh' = 1 - u^2)
+  int gru_wgrad_ext;       // 1: dW_ih / dW_hh / db_ih / db_hh come from k_gru_wgrad (mx_launch_gru_wgrad with these same arguments), not from k_front_bwd
 };
+bool mx_gru_wgrad_split_usable(const FrontBwdArgs& a);      // with gru_wgrad_ext = 0
+int mx_launch_gru_wgrad(const FrontBwdArgs& a, cudaStream_t s);
 int mx_launch_tc_prep_weights_T(const float* theta, const MxNetLayout& L, float* imgT, cudaStream_t s);
 bool mx_tc_prep_T_wanted(int in_dim);
 size_t mx_tc_imageT_floats(int in_dim);

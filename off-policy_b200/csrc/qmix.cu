@@ -205,7 +205,7 @@ extern "C" int mx_qmix_create(const mx_qmix_cfg* c, float* theta, float* theta_t
     const int prio = g_mx_side_prio > 0 ? lo : (g_mx_side_prio < 0 ? hi : 0);
     if (cudaStreamCreateWithPriority(&q->side, cudaStreamNonBlocking, prio) != cudaSuccess) { mx_set_error("mx_qmix_create: cudaStreamCreate failed"); delete q; return 1; }
   }
-  cudaEvent_t* evs[6] = {&q->ev_fork, &q->ev_prep, &q->ev_batch, &q->ev_hyper, &q->ev_core, &q->ev_hbwd};
+  cudaEvent_t* evs[7] = {&q->ev_fork, &q->ev_prep, &q->ev_batch, &q->ev_hyper, &q->ev_core, &q->ev_hbwd, &q->ev_gbwd};
   for (cudaEvent_t* e : evs) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
 #endif
   *out = q;
@@ -214,7 +214,7 @@ extern "C" int mx_qmix_create(const mx_qmix_cfg* c, float* theta, float* theta_t
 extern "C" void mx_qmix_destroy(mx_qmix* q) {
   if (!q) return;
 #if !MX_EMU
-  cudaEvent_t evs[6] = {q->ev_fork, q->ev_prep, q->ev_batch, q->ev_hyper, q->ev_core, q->ev_hbwd};
+  cudaEvent_t evs[7] = {q->ev_fork, q->ev_prep, q->ev_batch, q->ev_hyper, q->ev_core, q->ev_hbwd, q->ev_gbwd};
   for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
   if (q->side) cudaStreamDestroy(q->side);
 #endif
@@ -522,10 +522,18 @@ static int backward_core(mx_qmix* q, const mx_batch* b, void* stream, OptimArgs*
   fb.theta = q->theta; fb.L = q->agent; fb.u1 = ff.u1; fb.u2 = ff.u2; fb.st0 = ff.st0; fb.st1 = ff.st1; fb.st2 = ff.st2;
   fb.dgi = gb.dgi; fb.gates = gf.gates; fb.hall = gf.hall[0]; fb.gpart = mx.gpart; fb.P = q->P;
   fb.da2_out = ws + W.da2; fb.da1_out = ws + W.da1; fb.tc_imgT = ws + W.tcimgT; fb.tc_imgT_ready = q->imgT_fresh; q->imgT_fresh = 0;      // used when the tensor-core weight-gradient kernel is enabled (option wgrad_tc)
+  const bool gsplit = mx_gru_wgrad_split_usable(fb);      // GRU weight gradients as their own kernel, beside k_front_bwd when forked
+  if (gsplit) {
+    fb.gru_wgrad_ext = 1;
+#if !MX_EMU
+    if (overlap) fork_to_side(q, q->ev_gbwd, s);
+#endif
+    if (mx_launch_gru_wgrad(fb, side)) return 1;
+  }
   if (mx_launch_front_bwd(fb, &parts[0], s)) return 1;
 
 #if !MX_EMU
-  if (split && overlap) join_from_side(q, q->ev_hbwd, s);
+  if ((split || gsplit) && overlap) join_from_side(q, q->ev_hbwd, s);
 #endif
   *oa = optim_args(q, B, parts);
   return 0;

@@ -192,6 +192,30 @@ def test_front_tcgen05_kernel_variants_match_reference_golden(emu_engine, name, 
         lib.mx_set_option(b"front_tc_threads", 256)
 
 
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("name", ["qmix_small", "qmix_5ag", "qmix_small_per", "qmix_small_tanh"])
+def test_gru_weight_gradient_kernel_split_matches_reference_golden(emu_engine, name, split):
+    """Option gru_wgrad_split: dW_ih / dW_hh / db_ih / db_hh from k_gru_wgrad (its own kernel, launched beside k_front_bwd on the GPU;
+    default) or from inside k_front_bwd (0).  Same gradient partial rows either way; one more launch per step with the split."""
+    lib = emu_engine.lib()
+    lib.mx_set_option(b"gru_wgrad_split", split)
+    lib.mx_set_option(b"wgrad_tc", 0)
+    try:
+        c0 = lib.mx_launch_count()
+        qc.check_step_against(None, name, intermediates=False, debug=False)
+        n = lib.mx_launch_count() - c0
+    finally:
+        lib.mx_set_option(b"gru_wgrad_split", 1)
+        lib.mx_set_option(b"wgrad_tc", -1)
+    test_gru_weight_gradient_kernel_split_matches_reference_golden.counts[(name, split)] = n
+    both = test_gru_weight_gradient_kernel_split_matches_reference_golden.counts
+    if (name, 0) in both and (name, 1) in both:
+        assert both[(name, 1)] > both[(name, 0)], both
+
+
+test_gru_weight_gradient_kernel_split_matches_reference_golden.counts = {}
+
+
 @pytest.mark.parametrize("mma", [0, 1])
 @pytest.mark.parametrize("name", ["qmix_small", "qmix_5ag", "qmix_small_nofn"])
 def test_front_backward_gemm_variants_match_reference_golden(emu_engine, name, mma):
