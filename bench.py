@@ -386,6 +386,7 @@ def kernel_work(cfg, T, B, P):
         "k_qhead_bwd": 2.0 * M * 3 * H,
         "k_gru_bwd": 2.0 * M * 3 * H * H,
         "k_front_bwd": 2.0 * M * (2 * 3 * H * H * 2 + 3 * H * H + 2 * H * H + H * H + 2 * O * H + O * H) / 1.0,
+        "k_gru_wgrad": 2.0 * M * (2 * 3 * H * H),      # dW_ih + dW_hh when they run as their own kernel (option gru_wgrad_split): taken off k_front_bwd below
         # tensor-core variants (options front_tc_wide / wgrad_tc): same algorithmic work as the kernels they replace, split in two for the backward
         "k_front_fwd_tc": 2 * 2.0 * M * (O * H + H * H + 3 * H * H),
         "k_front_fwd_tc_wide": 2 * 2.0 * M * (O * H + H * H + 3 * H * H),
@@ -633,6 +634,8 @@ def run_engine(args):
     kavg = {k: float(np.median(v)) for k, v in kern.items()}
     ksum = sum(kavg.values())
     fl, by = kernel_work(cfg, T, B, tr.P)
+    if "k_gru_wgrad" in kavg:
+        fl["k_front_bwd"] -= fl["k_gru_wgrad"]
     top = max(kavg, key=kavg.get)
     pk = peaks()
     if top in fl:

@@ -39,6 +39,11 @@ int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "hyper_late")) { g_mx_hyper_late = value; return 0; }
   if (!strcmp(name, "front_bwd_mma")) { g_mx_front_bwd_mma = value; return 0; }
   if (!strcmp(name, "gru_wgrad_split")) { g_mx_gru_wgrad_split = value; return 0; }
+#if !MX_EMU
+  if (!strcmp(name, "smem_carveout")) { g_mx_smem_carveout = value; return 0; }
+#else
+  if (!strcmp(name, "smem_carveout")) return 0;
+#endif
   if (!strcmp(name, "gather_tma")) { g_mx_gather_tma = value; return 0; }      // 1: episode gather on the TMA unit (default), 0: vectorised loads
   if (!strcmp(name, "gru_threads")) { g_mx_gru_threads = value; return 0; }      // 0: by size, 128 / 256: force the recurrence kernels' CTA width
   if (!strcmp(name, "gru_fwd_rpc")) { g_mx_gru_fwd_rpc = value; return 0; }
@@ -179,6 +184,15 @@ extern "C" int mx_profile_end(void* stream, char* names_buf, int32_t buf_len, fl
 #endif
 
 #if !MX_EMU
+int g_mx_smem_carveout = 100;
+void mx_prefer_carveout(const void* kern) {
+  static const void* seen[128];
+  static int nseen = 0, applied = -2;
+  if (applied != g_mx_smem_carveout) { nseen = 0; applied = g_mx_smem_carveout; }      // option changed: re-apply to every kernel
+  for (int i = 0; i < nseen; ++i) if (seen[i] == kern) return;
+  if (nseen < 128) seen[nseen++] = kern;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_mx_smem_carveout < 0 ? -1 : g_mx_smem_carveout);
+}
 int mx_num_sms() {
   static int sms = 0;
   if (!sms) {

@@ -32,8 +32,13 @@ extern int g_mx_pdl_skip_next;
     asm volatile("griddepcontrol.wait;" ::: "memory");                    \
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");       \
   } while (0)
+// Kernels of the two branches of a step only share an SM if the SM's L1 / shared-memory split, fixed while any CTA is resident, leaves
+// room for both: every step kernel asks for the largest shared-memory carveout once (option smem_carveout, percent; < 0 = driver default).
+extern int g_mx_smem_carveout;
+void mx_prefer_carveout(const void* kern);
 template <typename... KArgs, typename... Args>
 static inline void mx_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  mx_prefer_carveout(reinterpret_cast<const void*>(kern));
   cudaLaunchConfig_t cfg;
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[1];

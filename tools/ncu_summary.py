@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STEP = ["k_draw", "k_gather", "k_gather_tma", "k_tc_prep_weights", "k_front_fwd_tc", "k_front_fwd_tc2", "k_front_fwd", "k_gru_fwd", "k_gru_fwd2", "k_qhead", "k_mixer",
-        "k_mix_hyper_fwd", "k_mix_core", "k_mix_hyper_bwd", "k_mid", "k_qhead_bwd", "k_gru_bwd", "k_gru_bwd2", "k_front_bwd", "k_grad_reduce", "k_adam", "k_optim_fused", "k_polyak"]
+        "k_mix_hyper_fwd", "k_mix_core", "k_mix_hyper_bwd", "k_mid", "k_qhead_bwd", "k_gru_bwd", "k_gru_bwd2", "k_gru_wgrad", "k_front_bwd", "k_grad_reduce", "k_adam", "k_optim_fused", "k_polyak"]
 
 
 def short(name):
