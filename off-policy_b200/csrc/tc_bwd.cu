@@ -110,48 +110,79 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
     }
     __syncthreads();
     // ---- B = [x2 | h_prev | 1 | 0..]  (144 features) ----
-#pragma unroll 2
-    for (int p = tid; p < 144 * 16; p += blockDim.x) {
-      int n, kq;
-      wg_pair(p, &n, &kq);
-      float x[4];
+    // Every staging phase below is two loops: all global loads of the phase first (independent, all in flight together), then the
+    // LayerNorm / TF32 split / shared-memory stores -- one memory round trip per phase instead of one per loop iteration.
+    {
+      constexpr int NIT = (144 * 16 + WG_THREADS - 1) / WG_THREADS;
+      float raw[NIT][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = row0 + 4 * kq + j;
-        float v = 0.f;
-        if (m < a.M) {
-          if (n < 64) v = (a.u2[(size_t)m * MX_H + n] - st_s[2 * (m - row0)]) * st_s[2 * (m - row0) + 1] * par_s[n] + par_s[64 + n];
-          else if (n < 128) {
-            if (a.no_gru) v = 0.f;                     // MLP variant: no recurrent matrix
-            else if (((m / N) % T1) > 0) v = a.hall[(size_t)(m - N) * MX_H + (n - 64)];
-            else if (a.h0) v = a.h0[(size_t)m * MX_H + (n - 64)];
-          } else if (n == 128) v = 1.f;
-        }
-        x[j] = v;
-      }
-      wg_put(b_hi, b_lo, n, kq, x);
-    }
-    // ---- A = [dgi_r | dgi_z] -> D1 ; then A = [dgi_n | dgi_n * r] -> D2 (same B) ----
-    for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll 2
-      for (int p = tid; p < 128 * 16; p += blockDim.x) {
-        int f, kq;
-        wg_pair(p, &f, &kq);
-        float x[4];
+      for (int it = 0; it < NIT; ++it) {
+        const int p = tid + it * WG_THREADS;
+        int n, kq;
+        wg_pair(p, &n, &kq);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int m = row0 + 4 * kq + j;
           float v = 0.f;
-          if (m < a.M) {
-            if (pass == 0) v = a.dgi[(size_t)m * MX_G + f];
-            else {
-              v = a.dgi[(size_t)m * MX_G + 2 * MX_H + (f & 63)];
-              if (f >= 64) v = a.no_gru ? 0.f : v * a.gates[(size_t)m * MX_G + (f - 64)];
-            }
+          if (p < 144 * 16 && m < a.M) {
+            if (n < 64) v = a.u2[(size_t)m * MX_H + n];
+            else if (n < 128) {
+              if (a.no_gru) v = 0.f;                     // MLP variant: no recurrent matrix
+              else if (((m / N) % T1) > 0) v = a.hall[(size_t)(m - N) * MX_H + (n - 64)];
+              else if (a.h0) v = a.h0[(size_t)m * MX_H + (n - 64)];
+            } else if (n == 128) v = 1.f;
           }
-          x[j] = v;
+          raw[it][j] = v;
         }
-        wg_put(a_hi, a_lo, f, kq, x);
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int p = tid + it * WG_THREADS;
+        if (p >= 144 * 16) break;
+        int n, kq;
+        wg_pair(p, &n, &kq);
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = 4 * kq + j;
+          x[j] = (n < 64 && row0 + rr < a.M) ? (raw[it][j] - st_s[2 * rr]) * st_s[2 * rr + 1] * par_s[n] + par_s[64 + n] : raw[it][j];
+        }
+        wg_put(b_hi, b_lo, n, kq, x);
+      }
+    }
+    // ---- A = [dgi_r | dgi_z] -> D1 ; then A = [dgi_n | dgi_n * r] -> D2 (same B) ----
+    for (int pass = 0; pass < 2; ++pass) {
+      {
+        constexpr int NIT = 128 * 16 / WG_THREADS;
+        static_assert(NIT * WG_THREADS == 128 * 16, "A tile pairs must divide over the CTA");
+        float raw[NIT][4], rg[NIT][4];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          int f, kq;
+          wg_pair(tid + it * WG_THREADS, &f, &kq);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int m = row0 + 4 * kq + j;
+            float v = 0.f, g = 1.f;
+            if (m < a.M) {
+              if (pass == 0) v = a.dgi[(size_t)m * MX_G + f];
+              else {
+                v = a.dgi[(size_t)m * MX_G + 2 * MX_H + (f & 63)];
+                if (f >= 64) g = a.no_gru ? 0.f : a.gates[(size_t)m * MX_G + (f - 64)];
+              }
+            }
+            raw[it][j] = v; rg[it][j] = g;
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          int f, kq;
+          wg_pair(tid + it * WG_THREADS, &f, &kq);
+          float x[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = (pass == 1 && f >= 64) ? raw[it][j] * rg[it][j] : raw[it][j];
+          wg_put(a_hi, a_lo, f, kq, x);
+        }
       }
       tc::fence_async_smem();
       tc::fence_before();
@@ -163,39 +194,65 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
       tc::fence_after();
     }
     // ---- A = [da2 | da1], B = [x1 | x0 | 1] -> D3 ----
-#pragma unroll 2
-    for (int p = tid; p < 128 * 16; p += blockDim.x) {
-      int f, kq;
-      wg_pair(p, &f, &kq);
-      const float* src = f < 64 ? a.da2_out : a.da1_out;
-      float x[4];
+    {
+      constexpr int NA = 128 * 16 / WG_THREADS;
+      constexpr int NB = ((64 + WG_MAX_IN) * 16 + WG_THREADS - 1) / WG_THREADS;
+      float ra[NA][4], rb[NB][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = row0 + 4 * kq + j;
-        x[j] = m < a.M ? src[(size_t)m * MX_H + (f & 63)] : 0.f;
-      }
-      wg_put(a_hi, a_lo, f, kq, x);
-    }
-#pragma unroll 2
-    for (int p = tid; p < N3 * 16; p += blockDim.x) {
-      int n, kq;
-      wg_pair(p, &n, &kq);
-      float x[4];
+      for (int it = 0; it < NA; ++it) {
+        int f, kq;
+        wg_pair(tid + it * WG_THREADS, &f, &kq);
+        const float* src = f < 64 ? a.da2_out : a.da1_out;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = row0 + 4 * kq + j;
-        float v = 0.f;
-        if (m < a.M) {
-          if (n < 64) v = (a.u1[(size_t)m * MX_H + n] - st_s[2 * WG_ROWS + 2 * (m - row0)]) * st_s[2 * WG_ROWS + 2 * (m - row0) + 1] * par_s[128 + n] + par_s[192 + n];
-          else if (n < 64 + I) {
-            const int c = n - 64;
-            const float xr = a.X[(size_t)m * a.ldx + c];
-            v = a.feature_norm ? (xr - st_s[4 * WG_ROWS + 2 * (m - row0)]) * st_s[4 * WG_ROWS + 2 * (m - row0) + 1] * par_s[256 + c] + par_s[384 + c] : xr;
-          }
+        for (int j = 0; j < 4; ++j) {
+          const int m = row0 + 4 * kq + j;
+          ra[it][j] = m < a.M ? src[(size_t)m * MX_H + (f & 63)] : 0.f;
         }
-        x[j] = v;
       }
-      wg_put(b_hi, b_lo, n, kq, x);
+#pragma unroll
+      for (int it = 0; it < NB; ++it) {
+        const int p = tid + it * WG_THREADS;
+        int n, kq;
+        wg_pair(p, &n, &kq);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = row0 + 4 * kq + j;
+          float v = 0.f;
+          if (p < N3 * 16 && m < a.M) {
+            if (n < 64) v = a.u1[(size_t)m * MX_H + n];
+            else if (n < 64 + I) v = a.X[(size_t)m * a.ldx + (n - 64)];
+          }
+          rb[it][j] = v;
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < NA; ++it) {
+        int f, kq;
+        wg_pair(tid + it * WG_THREADS, &f, &kq);
+        wg_put(a_hi, a_lo, f, kq, ra[it]);
+      }
+#pragma unroll
+      for (int it = 0; it < NB; ++it) {
+        const int p = tid + it * WG_THREADS;
+        if (p >= N3 * 16) break;
+        int n, kq;
+        wg_pair(p, &n, &kq);
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = 4 * kq + j;
+          float v = rb[it][j];
+          if (row0 + rr < a.M) {
+            if (n < 64) v = (v - st_s[2 * WG_ROWS + 2 * rr]) * st_s[2 * WG_ROWS + 2 * rr + 1] * par_s[128 + n] + par_s[192 + n];
+            else if (n < 64 + I && a.feature_norm) {
+              const int c = n - 64;
+              v = (v - st_s[4 * WG_ROWS + 2 * rr]) * st_s[4 * WG_ROWS + 2 * rr + 1] * par_s[256 + c] + par_s[384 + c];
+            }
+          }
+          x[j] = v;
+        }
+        wg_put(b_hi, b_lo, n, kq, x);
+      }
     }
     for (int p = tid; p < 16 * 16; p += blockDim.x) {      // the ones block: feature 0 = 1 for valid rows (lo part: zeros)
       int n, kq;

@@ -507,7 +507,6 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
   }
   MX_PDL_WAIT();
   const float* img = a.tc_img[net];
-  const float* img_w1c[2] = {img, img + 2 * 64 * 64};
   {   // resident layers: fc2 and W_ih (contiguous in the image after the two fc1 chunks, contiguous in shared memory from o_w2h)
     const float* src = img + 2 * 64 * Kp;
     float* dst = reinterpret_cast<float*>(w2h);
@@ -530,21 +529,34 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
     const int m = tile * 128 + tid;
     const bool ok = m < a.M;
     const float* xrow = a.X + (size_t)(ok ? m : 0) * a.ldx;
-    // ---- row statistics over all I features (two reads of the row; the second pass and the chunk loads below hit L1) ----
+    // ---- row statistics over all I features (two reads of the row; loads issued eight float4 at a time so that a thread has 128 bytes
+    //      of its row in flight instead of one dependent load per iteration) ----
     float mean = 0.f, rstd = 1.f;
     {
       float p[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int c4 = 0; c4 < I4; ++c4) {
-        const float4 v = ok ? *reinterpret_cast<const float4*>(xrow + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        p[0] += (4 * c4 < I) ? v.x : 0.f; p[1] += (4 * c4 + 1 < I) ? v.y : 0.f; p[2] += (4 * c4 + 2 < I) ? v.z : 0.f; p[3] += (4 * c4 + 3 < I) ? v.w : 0.f;
+      for (int cb = 0; cb < I4; cb += 8) {
+        float4 q8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q8[i] = (ok && cb + i < I4) ? *reinterpret_cast<const float4*>(xrow + 4 * (cb + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = 4 * (cb + i);
+          p[0] += (c < I) ? q8[i].x : 0.f; p[1] += (c + 1 < I) ? q8[i].y : 0.f; p[2] += (c + 2 < I) ? q8[i].z : 0.f; p[3] += (c + 3 < I) ? q8[i].w : 0.f;
+        }
       }
       mean = ((p[0] + p[1]) + (p[2] + p[3])) / (float)I;
       float q[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int c4 = 0; c4 < I4; ++c4) {
-        const float4 v = ok ? *reinterpret_cast<const float4*>(xrow + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float d0 = (4 * c4 < I) ? v.x - mean : 0.f, d1 = (4 * c4 + 1 < I) ? v.y - mean : 0.f, d2 = (4 * c4 + 2 < I) ? v.z - mean : 0.f,
-                    d3 = (4 * c4 + 3 < I) ? v.w - mean : 0.f;
-        q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
+      for (int cb = 0; cb < I4; cb += 8) {
+        float4 q8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q8[i] = (ok && cb + i < I4) ? *reinterpret_cast<const float4*>(xrow + 4 * (cb + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = 4 * (cb + i);
+          const float d0 = (c < I) ? q8[i].x - mean : 0.f, d1 = (c + 1 < I) ? q8[i].y - mean : 0.f, d2 = (c + 2 < I) ? q8[i].z - mean : 0.f,
+                      d3 = (c + 3 < I) ? q8[i].w - mean : 0.f;
+          q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
+        }
       }
       rstd = rsqrtf(((q[0] + q[1]) + (q[2] + q[3])) / (float)I + MX_LN_EPS);
       if (live && ok && a.st0) { a.st0[2 * (size_t)m] = mean; a.st0[2 * (size_t)m + 1] = rstd; }
@@ -553,16 +565,25 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
     for (int ch = 0; ch < 2; ++ch) {
       const int Kc = ch == 0 ? 64 : Kc1;
       {
-        const float* src = img_w1c[ch];
+        const float* src = ch == 0 ? img : img + 2 * 64 * 64;
         float* dst = reinterpret_cast<float*>(w1h);
         const int nvec = (2 * 64 * Kc * 4) >> 4;          // hi tile then lo tile, contiguous in the image
         for (int v = tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
         mx_cp_commit();
       }
-      for (int c4 = 0; 4 * c4 < Kc; ++c4) {
+      for (int cb = 0; 4 * cb < Kc; cb += 8) {
+        float4 q8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c0 = 64 * ch + 4 * (cb + i);
+          q8[i] = (ok && 4 * (cb + i) < Kc && c0 < I) ? *reinterpret_cast<const float4*>(xrow + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c4 = cb + i;
+        if (4 * c4 >= Kc) continue;
         const int c0 = 64 * ch + 4 * c4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && c0 < I) v = *reinterpret_cast<const float4*>(xrow + c0);
+        const float4 v = q8[i];
         float x[4] = {v.x, v.y, v.z, v.w};
         float4 h, l;
 #pragma unroll
@@ -575,6 +596,7 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
         const uint32_t o = tc::core_off_bytes(tid, 4 * c4, Kc);
         *reinterpret_cast<float4*>(a_hi + o) = h;
         *reinterpret_cast<float4*>(a_lo + o) = l;
+      }
       }
       mx_cp_wait<0>();
       tc::fence_async_smem();
