@@ -148,6 +148,23 @@ MX_DEVINL float4 optim_ld4_volatile(const float* p) {
 #endif
 }
 
+// ---- flag-in-data ("LL") exchange lines: a float4 of gradient columns travels as two 16-byte lines {x, flag, y, flag} {z, flag, w, flag};
+// a line is written by ONE vector store and read by ONE vector load, so data and flags arrive together: no fence, no arrival counter,
+// no separate flag hop -- a column's owner thread adds a peer's contribution the moment that peer's two lines show this step's flag.
+#if !MX_EMU
+__device__ __forceinline__ void optim_ll_store(float* dst, float4 v, unsigned flag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(__float_as_uint(v.x)), "r"(flag), "r"(__float_as_uint(v.y)), "r"(flag) : "memory");
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "r"(__float_as_uint(v.z)), "r"(flag), "r"(__float_as_uint(v.w)), "r"(flag) : "memory");
+}
+__device__ __forceinline__ bool optim_ll_load(const float* src, float4* v, unsigned flag) {
+  unsigned a0, a1, a2, a3, b0, b1, b2, b3;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "l"(src) : "memory");
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "l"(src + 4) : "memory");
+  *v = make_float4(__uint_as_float(a0), __uint_as_float(a2), __uint_as_float(b0), __uint_as_float(b2));
+  return a1 == flag && a3 == flag && b1 == flag && b3 == flag;
+}
+#endif
+
 __global__ void __launch_bounds__(256) k_optim_fused(OptimArgs a) {
   const int tid = threadIdx.x;
   const bool scalar_blk = blockIdx.x == gridDim.x - 1;
@@ -169,6 +186,51 @@ __global__ void __launch_bounds__(256) k_optim_fused(OptimArgs a) {
     g = optim_reduce_partials(a);
     if (a.p2p_world <= 1 && tid < 64 && j < a.P) mx_st4(a.grad + j, g);
   }
+#if !MX_EMU
+  if (a.p2p_world > 1 && a.phase == 0 && a.p2p_ll) {
+    // ---- data-parallel exchange, flag-in-data lines (default): push this rank's columns into every peer's line array of this step's
+    //      parity, then add the peers' lines in rank order as they arrive (the line arrays follow the slots + flags of the protocol below) ----
+    const int W = a.p2p_world;
+    unsigned long long ts0 = 0, ts1 = 0, ts2 = 0;
+    const bool stamp = scalar_blk && tid == 0 && a.xstat;
+    if (stamp) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts0));
+    const long long col = scalar_blk ? a.P : j;
+    const bool owner = scalar_blk ? tid == 0 : (tid < 64 && j < a.P);
+    const float4 mine = scalar_blk ? sc : g;
+    const size_t ll0 = 2 * (size_t)W * a.p2p_slot + 64 + (size_t)(step & 1u) * W * 2 * a.p2p_slot;
+    if (owner) {
+      for (int p = 0; p < W; ++p)
+        if (p != a.p2p_rank) optim_ll_store(a.p2p_blocks[p] + ll0 + (size_t)a.p2p_rank * 2 * a.p2p_slot + 2 * col, mine, step);
+      if (stamp) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts1));
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned long long t0 = 0;
+      for (int p = 0; p < W; ++p) {        // rank order on every rank: bit-identical sums everywhere
+        float4 v = mine;
+        if (p != a.p2p_rank) {
+          const float* src = a.p2p_blocks[a.p2p_rank] + ll0 + (size_t)p * 2 * a.p2p_slot + 2 * col;
+          unsigned spins = 0;
+          while (!optim_ll_load(src, &v, step)) {
+            if ((++spins & 1023u) == 0) {
+              unsigned long long t1;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+              if (t0 == 0) t0 = t1;
+              if (t1 - t0 > 10000000000ull || optim_ld_volatile(a.sync + 3)) { atomicExch(a.sync + 3, 1u); break; }     // 10 s: a peer died; do not hang the device
+            }
+          }
+        }
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      mx_st4(a.grad + col, acc);
+      if (scalar_blk) sc = acc; else g = acc;
+      if (stamp) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts2));
+        const float w = (float)(ts2 - ts1);
+        a.xstat[0] += (float)(ts1 - ts0); a.xstat[1] += w; a.xstat[3] += 1.f;
+        if (w > a.xstat[4]) a.xstat[4] = w;
+      }
+    }
+  } else
+#endif
   if (a.p2p_world > 1 && a.phase == 0) {
     const int W = a.p2p_world;
 #if !MX_EMU

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) k_p2p_sum(P2pArgs a) {
 extern "C" int64_t mx_qmix_p2p_block_bytes(const mx_qmix* q) {
   const int64_t slot = mx_round_up64(q->P + 8, 64);
   const int64_t world = q->cfg.world_size > 1 ? q->cfg.world_size : 1;
-  return (2 * world * slot + 64) * 4;
+  return (2 * world * slot + 64 + 2 * world * 2 * slot) * 4;      // slots of both parities | flags | flag-in-data line arrays of both parities (k_optim_fused)
 }
 
 extern "C" int mx_qmix_set_peers(mx_qmix* q, int32_t rank, int32_t world, void* const* peer_blocks, uint32_t* counter_dev) {

@@ -56,7 +56,10 @@ def test_two_rank_peer_memory_exchange_equals_single_batch_reference(emu_engine,
         for k, v in ranks[0][0].q_network.state_dict().items():
             want = g["s%d.agent.%s" % (s, k)]
             assert np.abs(v.numpy() - want).max() <= 2.0 * cfg.lr, k     # same bound family as qmix_checks (Adam step ~ lr)
-    flags = blocks[0][2 * ((n - 64) // 2):].view(torch.int32)
+    # block layout (csrc/p2p.cu mx_qmix_p2p_block_bytes): slots of both parities [2][world][slot] | 64 flag words | the fused kernel's line arrays
+    slot = -(-(ranks[0][1].P + 8) // 64) * 64
+    assert n == 2 * 2 * slot + 64 + 2 * 2 * 2 * slot
+    flags = blocks[0][2 * 2 * slot:2 * 2 * slot + 64].view(torch.int32)
     assert int(flags[0]) == 2 and int(flags[1]) == 2
 
 
