@@ -94,7 +94,10 @@ extern "C" int mx_host_fence_record(int id, void* stream) {
 extern "C" int mx_host_fence_wait(int id) {       // returns once everything enqueued before the last record of this fence has completed
   if (id < 0 || id >= g_fence_n) { mx_set_error("mx_host_fence_wait: bad fence"); return 1; }
 #if !MX_EMU
-  if (g_fence_set[id] && cudaEventSynchronize(g_fence[id]) != cudaSuccess) { mx_set_error("mx_host_fence_wait: cudaEventSynchronize failed"); return 1; }
+  if (g_fence_set[id]) {
+    const cudaError_t e = cudaEventSynchronize(g_fence[id]);      // also the first place an asynchronous fault of earlier work surfaces
+    if (e != cudaSuccess) { mx_set_error("mx_host_fence_wait: cudaEventSynchronize failed: %s", cudaGetErrorString(e)); return 1; }
+  }
 #endif
   return 0;
 }
