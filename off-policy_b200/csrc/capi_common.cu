@@ -8,7 +8,11 @@
 static thread_local char g_err[512] = "";
 long long g_mx_launches = 0;
 #if !MX_EMU
-int g_mx_pdl = 0;     // measured slower on B200: dependents' prologues share the SM with the latency-bound recurrences
+int g_mx_pdl = -1;    // programmatic dependent launch: -1 (default) = for latency-bound learner steps only (rows <= g_mx_pdl_rows; set per step by the
+                      // learner), 1 = every launch, 0 = never.  B200, visit 16: 3m 172.0 -> 164.5 us with PDL; 2s3z 463 -> 478, 8m 1126 -> 1156 (the
+                      // dependents' prologues then take SM resources from kernels that are throughput-bound)
+int g_mx_pdl_rows = 12288;
+int g_mx_pdl_auto = 0;      // the learner's per-step decision in automatic mode
 int g_mx_pdl_skip_next = 0;
 #endif
 

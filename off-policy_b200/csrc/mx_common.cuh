@@ -24,7 +24,7 @@
 // only by the optimiser kernels, which call MX_PDL_THETA_WRITTEN() so that the NEXT launch is a plain, fully ordered one.
 // MX_PDL_WAIT() = griddepcontrol.wait (returns at once in a plain launch) followed by launch_dependents, i.e. a dependent may
 // start as soon as every CTA of this grid is past its own wait -- never before this grid's predecessor has completed.
-extern int g_mx_pdl;              // 0 (default): every launch is a plain one; mx_set_option("pdl", 1) enables PDL
+extern int g_mx_pdl, g_mx_pdl_auto, g_mx_pdl_rows;      // option pdl: -1 automatic (per learner step, by size), 0 off, 1 on
 extern int g_mx_pdl_skip_next;
 #define MX_PDL_THETA_WRITTEN() (g_mx_pdl_skip_next = 1)
 #define MX_PDL_WAIT()                                                     \
@@ -43,7 +43,7 @@ static inline void mx_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[1];
   cfg.attrs = at; cfg.numAttrs = 0;
-  if (g_mx_pdl && !g_mx_pdl_skip_next) {
+  if ((g_mx_pdl > 0 || (g_mx_pdl < 0 && g_mx_pdl_auto)) && !g_mx_pdl_skip_next) {
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 1;

@@ -347,6 +347,7 @@ static int backward_core(mx_qmix* q, const mx_batch* b, void* stream, OptimArgs*
   const int B = b->B, T = c.episode_len, N = c.n_agents;
   const int M = B * (T + 1) * N;
 #if !MX_EMU
+  g_mx_pdl_auto = M <= g_mx_pdl_rows ? 1 : 0;      // programmatic dependent launches for this step's kernels (and the sample that follows it)
   const bool overlap = use_overlap(q, B), wanted = want_overlap(q, B);
   cudaStream_t side = overlap ? q->side : s;
 #else

@@ -747,6 +747,7 @@ extern "C" int mx_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "front_bwd_rm")) { g_mx_front_bwd_rm = value; return 0; }
 #if !MX_EMU
   if (!strcmp(name, "pdl")) { g_mx_pdl = value; return 0; }
+  if (!strcmp(name, "pdl_rows")) { g_mx_pdl_rows = value; return 0; }
 #endif
   mx_set_error("mx_set_option: unknown option %s", name);
   return 1;
