@@ -553,7 +553,7 @@ extern "C" int mx_maddpg_step_ex(mx_maddpg* h, const mx_batch* b, const float* t
                                  int32_t* update_actor_out, void* stream) {
   const mx_maddpg_cfg& c = h->cfg;
 #if !MX_EMU
-  g_mx_pdl_auto = 0;      // automatic PDL is the QMIX step's decision (measured there); this update keeps plain launches unless option pdl = 1
+  g_mx_pdl_auto = 1;      // ~40 small dependent launches per update: programmatic dependent launch measured 491 -> 469 us (R-MADDPG), 372 -> 355 us (R-MATD3)
 #endif
   if (!b || b->B <= 0 || b->B > c.max_batch) { mx_set_error("maddpg step: batch size outside [1, max_batch=%d]", c.max_batch); return 1; }
   if (!b->obs || !b->share || !b->acts || !b->rewards || !b->dones || !b->dones_env) { mx_set_error("maddpg step: missing batch field"); return 1; }

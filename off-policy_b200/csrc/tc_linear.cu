@@ -672,9 +672,224 @@ __global__ void __launch_bounds__(128, 1) k_front_fwd_tc_wide(FrontFwdArgs a, Fr
   if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
 }
 
+// =====================================================================================================
+// k_front_fwd_tc_wide2: the wide-input pipeline with EVERY weight operand streamed through one 32 KB chunk buffer (fc1 chunk 0, fc1
+// chunk 1, fc2, W_ih gate r, z, n -- six [64][K] hi | lo pairs per tile, copied from the L2-resident image with cp.async), so a CTA needs
+// 96 KB of shared memory and 256 TMEM columns and TWO CTAs share an SM: while one waits for an MMA, a copy or its row loads, the other
+// runs its epilogue (ncu on k_front_fwd_tc_wide at 8m: 4 warps per SM, issue-active 11 %, long-scoreboard 5 warps per issue).  The copy
+// of chunk i + 1 is issued as soon as the MMAs of chunk i have completed, i.e. it flies during the epilogue between them; the three gate
+// blocks of gi accumulate in their own TMEM columns, so the epilogue of gate g overlaps the copy of gate g + 1.
+// =====================================================================================================
+struct FrontTcWide2Smem { int o_ahi, o_alo, o_wc, total; };
+static FrontTcWide2Smem front_tc_wide2_smem() {
+  FrontTcWide2Smem s;
+  s.o_ahi = 0; s.o_alo = 128 * 64 * 4; s.o_wc = 2 * 128 * 64 * 4; s.total = s.o_wc + 2 * 64 * 64 * 4;
+  return s;
+}
+__device__ __forceinline__ void tcw_stage(char* dst, const float* __restrict__ src, int nbytes) {
+  float* d = reinterpret_cast<float*>(dst);
+  for (int v = threadIdx.x; v < (nbytes >> 4); v += blockDim.x) mx_cp16(d + 4 * v, src + 4 * v);
+}
+__global__ void __launch_bounds__(128, 2) k_front_fwd_tc_wide2(FrontFwdArgs a, FrontTcWide2Smem sm, int swap_ls) {
+  MX_DYN_SMEM_RAW(smem_raw);
+  __shared__ __align__(8) tc::Bar bar_s;
+  __shared__ uint32_t tmem_s;
+  __shared__ float par_s[6 * MX_H + MX_G + 2 * 128];      // b1,g1,be1,b2,g2,be2 | b_ih | feature-norm gain, bias
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int net = blockIdx.y;
+  const float* __restrict__ th = a.theta[net];
+  const MxNetLayout L = a.L;
+  const bool live = (net == 0);
+  const int I = L.in_dim, Kp = (I + 7) & ~7, Kc1 = Kp - 64;
+  char* base = reinterpret_cast<char*>(smem_raw);
+  char *a_hi = base + sm.o_ahi, *a_lo = base + sm.o_alo, *wc = base + sm.o_wc;
+  const uint32_t bar = tc::bar_addr(&bar_s);
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_s);
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::mbar_init_fence();
+  }
+  float* bih_s = par_s + 6 * MX_H;
+  float* fng = bih_s + MX_G;
+  float* fnb = fng + 128;
+  for (int i = tid; i < MX_H; i += blockDim.x) {
+    par_s[i] = th[L.b1 + i]; par_s[MX_H + i] = th[L.ln1_g + i]; par_s[2 * MX_H + i] = th[L.ln1_b + i];
+    par_s[3 * MX_H + i] = th[L.b2 + i]; par_s[4 * MX_H + i] = th[L.ln2_g + i]; par_s[5 * MX_H + i] = th[L.ln2_b + i];
+  }
+  for (int i = tid; i < MX_G; i += blockDim.x) bih_s[i] = th[L.bih + i];
+  for (int i = tid; i < 128; i += blockDim.x) { fng[i] = (i < I && a.feature_norm) ? th[L.fn_g + i] : 1.f; fnb[i] = (i < I && a.feature_norm) ? th[L.fn_b + i] : 0.f; }
+  MX_PDL_WAIT();
+  // image: [fc1 chunk 0 hi|lo][fc1 chunk 1 hi|lo][fc2 hi|lo][W_ih hi (192 rows)][W_ih lo]
+  const float* img = a.tc_img[net];
+  const float* img_c1 = img + 2 * 64 * 64;
+  const float* img_w2 = img + 2 * 64 * Kp;
+  const float* img_wih = img_w2 + 2 * 4096;
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = tmem_s;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  uint32_t phase = 0;
+  const int ntiles = (a.M + 127) / 128;
+  const int I4 = (I + 3) >> 2;
+  if ((int)blockIdx.x < ntiles) { tcw_stage(wc, img, 2 * 64 * 64 * 4); mx_cp_commit(); }      // first tile's fc1 chunk 0
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m = tile * 128 + tid;
+    const bool ok = m < a.M;
+    const float* xrow = a.X + (size_t)(ok ? m : 0) * a.ldx;
+    float mean = 0.f, rstd = 1.f;
+    {
+      float p[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int cb = 0; cb < I4; cb += 8) {
+        float4 q8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q8[i] = (ok && cb + i < I4) ? *reinterpret_cast<const float4*>(xrow + 4 * (cb + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = 4 * (cb + i);
+          p[0] += (c < I) ? q8[i].x : 0.f; p[1] += (c + 1 < I) ? q8[i].y : 0.f; p[2] += (c + 2 < I) ? q8[i].z : 0.f; p[3] += (c + 3 < I) ? q8[i].w : 0.f;
+        }
+      }
+      mean = ((p[0] + p[1]) + (p[2] + p[3])) / (float)I;
+      float q[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int cb = 0; cb < I4; cb += 8) {
+        float4 q8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q8[i] = (ok && cb + i < I4) ? *reinterpret_cast<const float4*>(xrow + 4 * (cb + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = 4 * (cb + i);
+          const float d0 = (c < I) ? q8[i].x - mean : 0.f, d1 = (c + 1 < I) ? q8[i].y - mean : 0.f, d2 = (c + 2 < I) ? q8[i].z - mean : 0.f,
+                      d3 = (c + 3 < I) ? q8[i].w - mean : 0.f;
+          q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
+        }
+      }
+      rstd = rsqrtf(((q[0] + q[1]) + (q[2] + q[3])) / (float)I + MX_LN_EPS);
+      if (live && ok && a.st0) { a.st0[2 * (size_t)m] = mean; a.st0[2 * (size_t)m + 1] = rstd; }
+      if (!a.feature_norm) { mean = 0.f; rstd = 1.f; }      // (gain 1 / bias 0 in shared memory): the raw input goes through unchanged
+    }
+    // ---- fc1 in two K chunks ----
+    for (int ch = 0; ch < 2; ++ch) {
+      const int Kc = ch == 0 ? 64 : Kc1;
+      for (int cb = 0; 4 * cb < Kc; cb += 8) {
+        float4 q8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c0 = 64 * ch + 4 * (cb + i);
+          q8[i] = (ok && 4 * (cb + i) < Kc && c0 < I) ? *reinterpret_cast<const float4*>(xrow + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c4 = cb + i;
+          if (4 * c4 >= Kc) continue;
+          const int c0 = 64 * ch + 4 * c4;
+          float x[4] = {q8[i].x, q8[i].y, q8[i].z, q8[i].w};
+          float4 h, l;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            x[j] = (ok && c < I) ? ((x[j] - mean) * rstd * fng[c] + fnb[c]) : 0.f;
+          }
+          h.x = tc::to_tf32(x[0]); h.y = tc::to_tf32(x[1]); h.z = tc::to_tf32(x[2]); h.w = tc::to_tf32(x[3]);
+          l.x = x[0] - h.x; l.y = x[1] - h.y; l.z = x[2] - h.z; l.w = x[3] - h.w;
+          const uint32_t o = tc::core_off_bytes(tid, 4 * c4, Kc);
+          *reinterpret_cast<float4*>(a_hi + o) = h;
+          *reinterpret_cast<float4*>(a_lo + o) = l;
+        }
+      }
+      mx_cp_wait<0>();
+      tc::fence_async_smem();
+      tc::fence_before();
+      __syncthreads();
+      tc::fence_after();
+      if (tid == 0) tc::issue_layer_acc(tmem_base, a_hi, a_lo, wc, wc + 64 * Kc * 4, MX_H, Kc, swap_ls, ch > 0 ? 1u : 0u, bar);
+      tc::mbar_wait(bar, phase);        // the MMAs have read the A tile and the chunk buffer: both may be refilled
+      phase ^= 1;
+      tc::fence_after();
+      if (ch == 0) tcw_stage(wc, img_c1, 2 * 64 * Kc1 * 4); else tcw_stage(wc, img_w2, 2 * 4096 * 4);
+      mx_cp_commit();
+    }
+    // ---- fc1 epilogue, fc2, fc2 epilogue ----
+    for (int layer = 0; layer < 2; ++layer) {
+      if (layer == 1) {
+        mx_cp_wait<0>();
+        tc::fence_async_smem();
+        tc::fence_before();
+        __syncthreads();
+        tc::fence_after();
+        if (tid == 0) tc::issue_layer(tmem_base, a_hi, a_lo, wc, wc + 4096 * 4, MX_H, MX_H, 3, swap_ls, bar);
+        tc::mbar_wait(bar, phase);
+        phase ^= 1;
+        tc::fence_after();
+        tcw_stage(wc, img_wih, 4096 * 4); tcw_stage(wc + 4096 * 4, img_wih + 3 * 4096, 4096 * 4);      // gate r: hi | lo
+        mx_cp_commit();
+      }
+      float v[64];
+      tc::tmem_ld64(tmem_row, v);
+      const float* bs = par_s + layer * 3 * MX_H;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) { const float z = v[c] + bs[c]; v[c] = a.act_tanh ? tanhf(z) : fmaxf(z, 0.f); }
+      const float mu = tc_sum64(v) * (1.f / 64.f);
+      const float rs = rsqrtf(tc_sumsq64(v, mu, 64) * (1.f / 64.f) + MX_LN_EPS);
+      float* u_out = layer == 0 ? a.u1 : a.u2;
+      float* st_out = layer == 0 ? a.st1 : a.st2;
+      if (live && ok && u_out) {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) *reinterpret_cast<float4*>(u_out + (size_t)m * MX_H + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        if (st_out) { st_out[2 * (size_t)m] = mu; st_out[2 * (size_t)m + 1] = rs; }
+      }
+#pragma unroll
+      for (int c = 0; c < 64; ++c) v[c] = (v[c] - mu) * rs * bs[MX_H + c] + bs[2 * MX_H + c];
+      tc::fence_before();
+      __syncthreads();          // every thread has drained its TMEM reads before the next layer's MMAs overwrite the accumulator
+      tc::fence_after();
+      tc_put_row64(a_hi, a_lo, tid, v);
+    }
+    // ---- gi = x2 . W_ih^T + b_ih, one gate block (64 columns) at a time into TMEM columns 64 + 64 g ----
+    float* gi = a.gi[net];
+#pragma unroll 1
+    for (int g = 0; g < 3; ++g) {
+      mx_cp_wait<0>();
+      tc::fence_async_smem();
+      tc::fence_before();
+      __syncthreads();
+      tc::fence_after();
+      if (tid == 0) tc::issue_layer(tmem_base + 64 + 64 * g, a_hi, a_lo, wc, wc + 4096 * 4, MX_H, MX_H, 3, swap_ls, bar);
+      tc::mbar_wait(bar, phase);
+      phase ^= 1;
+      tc::fence_after();
+      if (g < 2) {
+        tcw_stage(wc, img_wih + (g + 1) * 4096, 4096 * 4); tcw_stage(wc + 4096 * 4, img_wih + (3 + g + 1) * 4096, 4096 * 4);
+        mx_cp_commit();
+      } else if (tile + (int)gridDim.x < ntiles) {
+        tcw_stage(wc, img, 2 * 64 * 64 * 4);       // the next tile's fc1 chunk 0
+        mx_cp_commit();
+      }
+      float t0[64];
+      tc::tmem_ld64(tmem_row + 64 + 64 * g, t0);
+      if (ok) {
+        const int c0 = 64 * g;
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4)
+          *reinterpret_cast<float4*>(gi + (size_t)m * MX_G + c0 + 4 * c4) =
+              make_float4(t0[4 * c4] + bih_s[c0 + 4 * c4], t0[4 * c4 + 1] + bih_s[c0 + 4 * c4 + 1], t0[4 * c4 + 2] + bih_s[c0 + 4 * c4 + 2],
+                          t0[4 * c4 + 3] + bih_s[c0 + 4 * c4 + 3]);
+      }
+    }
+    tc::fence_before();
+    __syncthreads();     // TMEM reads drained; the A tile is free for the next tile
+    tc::fence_after();
+  }
+  mx_cp_wait<0>();
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
+}
+
 int g_mx_front_tc = 1;        // 1: tcgen05 3xTF32 kernel (default), 0: FFMA kernel (mx_set_option("front_tc", 0))
 int g_mx_front_tc_threads = 256;   // inputs <= 64: 256 = two threads per accumulator row (k_front_fwd_tc2), 128 = one (k_front_fwd_tc)
 int g_mx_front_tc_wide = 1;   // 1 (default): 64 < in_dim <= 128 also runs on tcgen05 (k_front_fwd_tc_wide): 8m 1.76 -> 1.59 ms, 2s3z 0.683 -> 0.647 ms (r02 sweeps)
+int g_mx_front_tc_wide2 = 1;  // wide inputs: 1 (default) = k_front_fwd_tc_wide2 (weights streamed, two CTAs per SM), 0 = k_front_fwd_tc_wide (weights resident, one CTA per SM)
 int g_mx_tc_swap = 0;
 extern int g_mx_wgrad_tc, g_mx_wgrad_tc_wide;      // tc_bwd.cu
 int g_mx_mixer_rm = 0;        // tuning overrides (0 = automatic): rows per thread of the mixer / backward front tiles
@@ -696,6 +911,23 @@ int mx_launch_front_fwd_tc(const FrontFwdArgs& a, int nets, cudaStream_t s) {
   if (gx < 1) gx = 1;
   if (wide) {
     if (!a.tc_img[0] || (nets > 1 && !a.tc_img[1])) { mx_set_error("front_fwd_tc_wide: weight images missing"); return 1; }
+    if (g_mx_front_tc_wide2) {
+      FrontTcWide2Smem s2 = front_tc_wide2_smem();
+      int g2 = 2 * mx_num_sms() / nets;
+      if (g2 > ntiles) g2 = ntiles;
+      if (g2 < 1) g2 = 1;
+#if !MX_EMU
+      static bool configured_w2 = false;
+      if (!configured_w2) {
+        if (cudaFuncSetAttribute(k_front_fwd_tc_wide2, cudaFuncAttributeMaxDynamicSharedMemorySize, s2.total) != cudaSuccess) { mx_set_error("front_fwd_tc_wide2: smem %d too large", s2.total); return 1; }
+        configured_w2 = true;
+      }
+#endif
+      MX_LAUNCH_PDL(k_front_fwd_tc_wide2, dim3(g2, nets), dim3(128), (size_t)s2.total, s, a, s2, g_mx_tc_swap);
+      MX_COUNT();
+      MX_MARK("k_front_fwd_tc_wide", s);
+      return MX_CHECK_LAUNCH("front_fwd_tc_wide2");
+    }
 #if !MX_EMU
     static bool configured_w = false;
     if (!configured_w) {
@@ -739,6 +971,7 @@ extern "C" int mx_set_option(const char* name, int32_t value) {
   if (mx_set_option_common(name, value) == 0) return 0;
   if (!strcmp(name, "front_tc")) { g_mx_front_tc = value; return 0; }
   if (!strcmp(name, "front_tc_wide")) { g_mx_front_tc_wide = value; return 0; }
+  if (!strcmp(name, "front_tc_wide2")) { g_mx_front_tc_wide2 = value; return 0; }
   if (!strcmp(name, "front_tc_threads")) { g_mx_front_tc_threads = value; return 0; }
   if (!strcmp(name, "wgrad_tc")) { g_mx_wgrad_tc = value; return 0; }
   if (!strcmp(name, "wgrad_tc_wide")) { g_mx_wgrad_tc_wide = value; return 0; }
