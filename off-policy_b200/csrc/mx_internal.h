@@ -94,6 +94,7 @@ struct MxQmixWs {           // offsets in floats into the workspace
   int64_t dh_out;           // [M][H]
   int64_t dgi;              // [M][3H]
   int64_t gpart;            // [npart][P]
+  int64_t lnpart;           // [2 npart][512]: LayerNorm gain / bias sums of k_front_bwd_tc CTAs (streamed mode, two CTAs per SM)
   int64_t grad;             // [P + 8]   flat gradient numerators + scalars (all-reduce payload)
   int64_t info;             // [8]
   int64_t prio;             // [max_batch]

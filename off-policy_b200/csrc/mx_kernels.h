@@ -172,6 +172,8 @@ struct FrontBwdArgs {
   float* tc_imgT;          // scratch for the transposed TF32 weight images of the all-tensor-core backward (option wgrad_tc = 2)
   int tc_imgT_ready;       // 1: the caller already built them for the current parameters (mx_launch_tc_prep_weights_T)
   int act_tanh;            // 1: tanh instead of ReLU (the saved u1 / u2 are the activations' outputs: tanh' = 1 - u^2)
+  float* ln_part;          // optional [ln_part_rows][512] side array: lets k_front_bwd_tc run more CTAs than there are gradient partial rows (streamed mode)
+  int ln_part_rows;
   int gru_wgrad_ext;       // 1: dW_ih / dW_hh / db_ih / db_hh come from k_gru_wgrad (mx_launch_gru_wgrad with these same arguments), not from k_front_bwd
 };
 bool mx_gru_wgrad_split_usable(const FrontBwdArgs& a);      // with gru_wgrad_ext = 0

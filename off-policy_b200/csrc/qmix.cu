@@ -148,6 +148,7 @@ static int64_t ws_layout(const mx_qmix_cfg* c, int64_t P, int npart, MxQmixWs* W
   W->dh_out = tk(M * MX_H);
   W->dgi = tk(M * MX_G);
   W->gpart = tk((int64_t)npart * P);
+  W->lnpart = tk((int64_t)2 * npart * 512);      // LayerNorm sums of k_front_bwd_tc when it runs two CTAs per SM
   W->grad = tk(P + 8);
   W->info = tk(8);
   W->prio = tk(B);
@@ -439,6 +440,7 @@ static int backward_core(mx_qmix* q, const mx_batch* b, void* stream, OptimArgs*
     fbm.X = X; fbm.ldx = ldx; fbm.M = M; fbm.T = T; fbm.N = N; fbm.feature_norm = c.no_feature_norm ? 0 : 1; fbm.act_tanh = c.use_tanh; fbm.no_gru = 1;
     fbm.theta = q->theta; fbm.L = q->agent; fbm.u1 = ff.u1; fbm.u2 = ff.u2; fbm.st0 = ff.st0; fbm.st1 = ff.st1; fbm.st2 = ff.st2;
     fbm.dgi = ws + W.dgi; fbm.gpart = mx.gpart; fbm.P = q->P;
+    fbm.ln_part = ws + W.lnpart; fbm.ln_part_rows = 2 * q->npart;
     fbm.da2_out = ws + W.da2; fbm.da1_out = ws + W.da1; fbm.tc_imgT = ws + W.tcimgT; fbm.tc_imgT_ready = q->imgT_fresh; q->imgT_fresh = 0;      // (option wgrad_tc)
     if (mx_launch_front_bwd(fbm, &parts[0], s)) return 1;
 #if !MX_EMU
@@ -522,6 +524,7 @@ static int backward_core(mx_qmix* q, const mx_batch* b, void* stream, OptimArgs*
   fb.X = X; fb.ldx = ldx; fb.M = M; fb.T = T; fb.N = N; fb.feature_norm = c.no_feature_norm ? 0 : 1; fb.act_tanh = c.use_tanh;
   fb.theta = q->theta; fb.L = q->agent; fb.u1 = ff.u1; fb.u2 = ff.u2; fb.st0 = ff.st0; fb.st1 = ff.st1; fb.st2 = ff.st2;
   fb.dgi = gb.dgi; fb.gates = gf.gates; fb.hall = gf.hall[0]; fb.gpart = mx.gpart; fb.P = q->P;
+  fb.ln_part = ws + W.lnpart; fb.ln_part_rows = 2 * q->npart;
   fb.da2_out = ws + W.da2; fb.da1_out = ws + W.da1; fb.tc_imgT = ws + W.tcimgT; fb.tc_imgT_ready = q->imgT_fresh; q->imgT_fresh = 0;      // used when the tensor-core weight-gradient kernel is enabled (option wgrad_tc)
   const bool gsplit = mx_gru_wgrad_split_usable(fb);      // GRU weight gradients as their own kernel, beside k_front_bwd when forked
   if (gsplit) {

@@ -64,6 +64,7 @@ struct WgradArgs {
   FrontBwdArgs f;
   int nchunks, Kp16;
   int ln_zero_from;      // CTAs from this index on also zero the LayerNorm ranges of their partial (k_front_bwd_tc ran fewer CTAs); -1: none
+  int ln_parts;          // > 0: k_front_bwd_tc left its LayerNorm sums in f.ln_part[ln_parts][512] (streamed mode) instead of the partial rows
 };
 
 #define WG_THREADS 512        // staging is load-latency bound: 16 warps keep enough loads in flight; warps 0-3 own the TMEM lanes in the epilogue
@@ -328,6 +329,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradArgs w, WgradSm
     }
   }
   }
+  if (w.ln_parts > 0) {      // LayerNorm sums of k_front_bwd_tc's CTAs blockIdx.x, + gridDim.x, ... (fixed order) -> this partial row
+    for (int c = tid; c < 512; c += blockDim.x) {
+      float sum = 0.f;
+      for (int r = blockIdx.x; r < w.ln_parts; r += gridDim.x) sum += a.ln_part[(size_t)r * 512 + c];
+      const int which = c >> 6;      // 0 ln2_g, 1 ln2_b, 2 ln1_g, 3 ln1_b, 4-5 fn_g, 6-7 fn_b
+      if (which < 4) gp[(which == 0 ? L.ln2_g : which == 1 ? L.ln2_b : which == 2 ? L.ln1_g : L.ln1_b) + (c & 63)] = sum;
+      else { const int cc = (c - 256) & 127; if (cc < I) gp[(c < 384 ? L.fn_g : L.fn_b) + cc] = sum; }
+    }
+  } else
   if (w.ln_zero_from >= 0 && (int)blockIdx.x >= w.ln_zero_from) {
     for (int c = tid; c < MX_H; c += blockDim.x) { gp[L.ln2_g + c] = 0.f; gp[L.ln2_b + c] = 0.f; gp[L.ln1_g + c] = 0.f; gp[L.ln1_b + c] = 0.f; }
     for (int c = tid; c < I; c += blockDim.x) { gp[L.fn_g + c] = 0.f; gp[L.fn_b + c] = 0.f; }
@@ -342,12 +352,13 @@ bool mx_wgrad_tc_usable(const FrontBwdArgs& a) {
 }
 
 extern int g_mx_tc_swap;
-static int launch_wgrad_tc(const FrontBwdArgs& a, int nparts, int ln_zero_from, cudaStream_t s);
+static int launch_wgrad_tc(const FrontBwdArgs& a, int nparts, int ln_zero_from, cudaStream_t s, int ln_parts = 0);
 int mx_launch_wgrad_tc(const FrontBwdArgs& a, int nparts, cudaStream_t s) { return launch_wgrad_tc(a, nparts, -1, s); }
-static int launch_wgrad_tc(const FrontBwdArgs& a, int nparts, int ln_zero_from, cudaStream_t s) {
+static int launch_wgrad_tc(const FrontBwdArgs& a, int nparts, int ln_zero_from, cudaStream_t s, int ln_parts) {
   WgradArgs w;
   w.f = a;
   w.ln_zero_from = ln_zero_from;
+  w.ln_parts = ln_parts;
   w.nchunks = mx_ceil_div(a.M, WG_ROWS);
   w.Kp16 = mx_round_up(a.L.in_dim, 16);
   WgradSmem sm = wgrad_smem(64 + w.Kp16);
@@ -376,11 +387,18 @@ static int launch_wgrad_tc(const FrontBwdArgs& a, int nparts, int ln_zero_from, 
 // tile's shared memory, free between MMAs) and threads 0-63 / 64-127 keep running sums of one column each.
 // =====================================================================================================
 struct BwdTcSmem { int o_ahi, o_alo, o_wih, o_w2, o_w1, total; };
-static BwdTcSmem bwd_tc_smem(int Kp16) {
+int g_mx_front_bwd_tc_stream = 1;      // 1 (default): every weight operand of k_front_bwd_tc goes through ONE chunk buffer, two CTAs per SM (inputs <= 96)
+static BwdTcSmem bwd_tc_smem(int Kp16, bool stream = false) {
   BwdTcSmem s;
   int o = 0;
   s.o_ahi = o; o += 128 * 64 * 4;
   s.o_alo = o; o += 128 * 64 * 4;
+  if (stream) {      // gate chunks, W2^T and W1^T take turns in one region (copied from the image while the previous operand's epilogue runs)
+    s.o_wih = s.o_w2 = s.o_w1 = o;
+    o += 2 * (Kp16 > 64 ? Kp16 : 64) * 64 * 4;
+    s.total = o;
+    return s;
+  }
   s.o_wih = o; o += 3 * 2 * 64 * 64 * 4;      // three gate chunks, each [64][64] hi | lo
   s.o_w2 = o;
   if (Kp16 <= 64) {                           // everything resident: 224 KB at obs 64
@@ -475,7 +493,7 @@ __device__ __forceinline__ void bt_ln_bwd_relu(bool act_tanh, float (&dy)[64], c
   }
 }
 
-__global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSmem sm, int swap_ls) {
+__global__ void __launch_bounds__(128, 2) k_front_bwd_tc(FrontBwdArgs a, BwdTcSmem sm, int swap_ls) {
   MX_DYN_SMEM_RAW(smem_raw);
   __shared__ __align__(8) tc::Bar bar_s;
   __shared__ uint32_t tmem_s;
@@ -489,7 +507,8 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
   float* sc0 = reinterpret_cast<float*>(a_hi);
   float* sc1 = reinterpret_cast<float*>(a_lo);
   const uint32_t bar = tc::bar_addr(&bar_s);
-  const bool restage = sm.o_w1 == sm.o_w2;
+  const bool stream = sm.o_wih == sm.o_w2;              // one chunk buffer for every weight operand (two CTAs per SM)
+  const bool restage = !stream && sm.o_w1 == sm.o_w2;
   const float* img_w2 = a.tc_imgT + 2 * 3 * 4096;
   const float* img_w1 = img_w2 + 2 * 4096;
   if (warp == 0) tc::tmem_alloc<128>(&tmem_s);
@@ -502,10 +521,15 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
   {   // the transposed weight images are byte-identical to the shared-memory weight region (resident part)
     const float* src = a.tc_imgT;
     float* dst = reinterpret_cast<float*>(wih);
-    const int nvec = ((restage ? sm.o_w2 : sm.total) - sm.o_wih) >> 4;
+    const int nvec = stream ? (2 * 4096 * 4) >> 4 : ((restage ? sm.o_w2 : sm.total) - sm.o_wih) >> 4;      // streamed: the first gate chunk only
     for (int v = tid; v < nvec; v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
     mx_cp_commit();
   }
+  auto stage_chunk = [&](const float* src, int nbytes) {      // streamed mode: the chunk buffer is free once the MMAs that read it have completed
+    float* dst = reinterpret_cast<float*>(wih);
+    for (int v = tid; v < (nbytes >> 4); v += blockDim.x) mx_cp16(dst + 4 * v, src + 4 * v);
+    mx_cp_commit();
+  };
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
@@ -532,10 +556,12 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
       tc::fence_before();
       __syncthreads();
       tc::fence_after();
-      if (tid == 0) tc::issue_layer_acc(tmem_base, a_hi, a_lo, wih + ch * 2 * 4096 * 4, wih + ch * 2 * 4096 * 4 + 4096 * 4, 64, 64, swap_ls, ch > 0 ? 1u : 0u, bar);
+      const char* wch = stream ? wih : wih + ch * 2 * 4096 * 4;
+      if (tid == 0) tc::issue_layer_acc(tmem_base, a_hi, a_lo, wch, wch + 4096 * 4, 64, 64, swap_ls, ch > 0 ? 1u : 0u, bar);
       tc::mbar_wait(bar, phase);
       phase ^= 1;
       tc::fence_after();
+      if (stream) stage_chunk(ch < 2 ? a.tc_imgT + (ch + 1) * 2 * 4096 : img_w2, 2 * 4096 * 4);      // next gate chunk, then W2^T: in flight during the loads / epilogue
     }
     // ---- LN2', ReLU' -> da2 ; then fc2 and LN1', ReLU' -> da1 ----
     for (int layer = 0; layer < 2; ++layer) {
@@ -552,7 +578,8 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
         for (int c4 = 0; c4 < 16; ++c4) *reinterpret_cast<float4*>(da_out + mm * MX_H + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
       }
       bt_put_row64(a_hi, a_lo, tid, v);
-      if (restage) {      // the previous MMAs that read this region have completed (every issue is waited for)
+      if (stream) mx_cp_wait<0>();
+      else if (restage) {      // the previous MMAs that read this region have completed (every issue is waited for)
         const float* src = layer == 0 ? img_w2 : img_w1;
         float* dst = reinterpret_cast<float*>(w2);
         const int nvec = (layer == 0 ? 2 * 4096 * 4 : 2 * Kp16 * 64 * 4) >> 4;
@@ -571,6 +598,10 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
       tc::mbar_wait(bar, phase);
       phase ^= 1;
       tc::fence_after();
+      if (stream) {
+        if (layer == 0) stage_chunk(img_w1, 2 * Kp16 * 64 * 4);
+        else if (tile + (int)gridDim.x < ntiles) stage_chunk(a.tc_imgT, 2 * 4096 * 4);      // the next tile's first gate chunk
+      }
     }
     // ---- dx0 -> gain / bias gradients of the feature LayerNorm (64 input columns per round) ----
     {
@@ -601,8 +632,15 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
     tc::fence_after();
   }
   // ---- this CTA's partial of the LayerNorm gain / bias gradients ----
-  float* gp = a.gpart + (size_t)blockIdx.x * a.P;
   const int col = tid & 63;
+  if (a.ln_part) {      // two CTAs per SM = more CTAs than gradient partial rows: the sums go to a side array [CTA][512] that k_wgrad_tc folds in
+    float* lp = a.ln_part + (size_t)blockIdx.x * 512;      // ln2_g | ln2_b | ln1_g | ln1_b | fn_g[128] | fn_b[128]
+    const int half = tid < 64 ? 0 : 1;
+    lp[64 * half + col] = acc2; lp[128 + 64 * half + col] = acc1;
+    lp[256 + 128 * half + col] = (col < I && a.feature_norm) ? acc0a : 0.f;
+    lp[256 + 128 * half + 64 + col] = (64 + col < I && a.feature_norm) ? acc0b : 0.f;
+  } else {
+  float* gp = a.gpart + (size_t)blockIdx.x * a.P;
   if (tid < 64) {
     gp[L.ln2_g + col] = acc2; gp[L.ln1_g + col] = acc1;
     if (col < I) gp[L.fn_g + col] = a.feature_norm ? acc0a : 0.f;
@@ -612,6 +650,8 @@ __global__ void __launch_bounds__(128, 1) k_front_bwd_tc(FrontBwdArgs a, BwdTcSm
     if (col < I) gp[L.fn_b + col] = a.feature_norm ? acc0a : 0.f;
     if (64 + col < I) gp[L.fn_b + 64 + col] = a.feature_norm ? acc0b : 0.f;
   }
+  }
+  mx_cp_wait<0>();
   tc::fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<128>(tmem_base);
@@ -634,7 +674,8 @@ int mx_launch_tc_prep_weights_T(const float* theta, const MxNetLayout& L, float*
 int mx_launch_front_bwd_tc(const FrontBwdArgs& a, int* nparts_used, cudaStream_t s) {
   const int Kp16 = mx_round_up(a.L.in_dim, 16);
   if (!a.tc_imgT_ready && mx_launch_tc_prep_weights_T(a.theta, a.L, a.tc_imgT, s)) return 1;
-  BwdTcSmem sm = bwd_tc_smem(Kp16);
+  const bool stream = g_mx_front_bwd_tc_stream != 0 && a.ln_part != nullptr;      // needs the side array for the LayerNorm sums
+  BwdTcSmem sm = bwd_tc_smem(Kp16, stream);
 #if !MX_EMU
   static int configured = 0;
   if (sm.total > configured) {
@@ -644,14 +685,18 @@ int mx_launch_front_bwd_tc(const FrontBwdArgs& a, int* nparts_used, cudaStream_t
 #endif
   const int ntiles = mx_ceil_div(a.M, 128), nchunks = mx_ceil_div(a.M, WG_ROWS);
   int ga = mx_num_sms(), gb = mx_num_sms();
+  if (stream && 2 * (sm.total + 2048) <= 227 * 1024) ga = 2 * mx_num_sms();      // two CTAs per SM fit
   if (ga > ntiles) ga = ntiles;
   if (gb > nchunks) gb = nchunks;
   FrontBwdArgs b = a;
   b.wgrad_external = 1;
+  if (!stream) b.ln_part = nullptr;
+  if (ga > a.ln_part_rows && stream) ga = a.ln_part_rows;
   MX_LAUNCH_PDL(k_front_bwd_tc, dim3(ga), dim3(128), (size_t)sm.total, s, b, sm, g_mx_tc_swap);
   MX_COUNT();
   MX_MARK("k_front_bwd_tc", s);
   if (MX_CHECK_LAUNCH("front_bwd_tc")) return 1;
   *nparts_used = gb;
+  if (stream) return launch_wgrad_tc(b, gb, -1, s, ga);
   return launch_wgrad_tc(b, gb, ga < gb ? ga : -1, s);
 }

@@ -891,7 +891,7 @@ int g_mx_front_tc_threads = 256;   // inputs <= 64: 256 = two threads per accumu
 int g_mx_front_tc_wide = 1;   // 1 (default): 64 < in_dim <= 128 also runs on tcgen05 (k_front_fwd_tc_wide): 8m 1.76 -> 1.59 ms, 2s3z 0.683 -> 0.647 ms (r02 sweeps)
 int g_mx_front_tc_wide2 = 1;  // wide inputs: 1 (default) = k_front_fwd_tc_wide2 (weights streamed, two CTAs per SM), 0 = k_front_fwd_tc_wide (weights resident, one CTA per SM)
 int g_mx_tc_swap = 0;
-extern int g_mx_wgrad_tc, g_mx_wgrad_tc_wide;      // tc_bwd.cu
+extern int g_mx_wgrad_tc, g_mx_wgrad_tc_wide, g_mx_front_bwd_tc_stream;      // tc_bwd.cu
 int g_mx_mixer_rm = 0;        // tuning overrides (0 = automatic): rows per thread of the mixer / backward front tiles
 int g_mx_front_bwd_rm = 0;
 
@@ -975,6 +975,7 @@ extern "C" int mx_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "front_tc_threads")) { g_mx_front_tc_threads = value; return 0; }
   if (!strcmp(name, "wgrad_tc")) { g_mx_wgrad_tc = value; return 0; }
   if (!strcmp(name, "wgrad_tc_wide")) { g_mx_wgrad_tc_wide = value; return 0; }
+  if (!strcmp(name, "front_bwd_tc_stream")) { g_mx_front_bwd_tc_stream = value; return 0; }
   if (!strcmp(name, "tc_swap_ls")) { g_mx_tc_swap = value; return 0; }
   if (!strcmp(name, "mixer_rm")) { g_mx_mixer_rm = value; return 0; }
   if (!strcmp(name, "front_bwd_rm")) { g_mx_front_bwd_rm = value; return 0; }

@@ -146,6 +146,28 @@ def test_tensor_core_backward_wide_inputs_vs_oracle(emu_engine, obs_dim, mode):
         lib.mx_set_option(b"front_tc_wide", 1)
 
 
+@pytest.mark.parametrize("obs_dim", [80, 128])
+def test_resident_weight_variants_of_the_wide_kernels_vs_oracle(emu_engine, obs_dim):
+    """The defaults stream every weight operand through one chunk buffer so that two CTAs share an SM (k_front_fwd_tc_wide2; k_front_bwd_tc
+    in streamed mode, its LayerNorm sums folded in by k_wgrad_tc from the side array).  Options front_tc_wide2 = 0 / front_bwd_tc_stream = 0
+    select the one-CTA-per-SM kernels with resident weights: same results."""
+    from oracle.qmix import QmixConfig, synth_batch
+    lib = emu_engine.lib()
+    cfg = QmixConfig(n_agents=5, obs_dim=obs_dim, act_dim=6, state_dim=20, gain=1.0)
+    B, T = 24, 5
+    lib.mx_set_option(b"front_tc_wide2", 0)
+    lib.mx_set_option(b"front_bwd_tc_stream", 0)
+    lib.mx_set_option(b"wgrad_tc", 2)
+    try:
+        L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T, debug=False)
+        batch = synth_batch(cfg, B, T, seed=4, avail_p=0.7, var_len=True) + (None, None)
+        qc.compare_step(L, pol, tr, batch, cfg, steps=2, param_tol=1e-2)
+    finally:
+        lib.mx_set_option(b"wgrad_tc", -1)
+        lib.mx_set_option(b"front_tc_wide2", 1)
+        lib.mx_set_option(b"front_bwd_tc_stream", 1)
+
+
 def test_config2_full_size_all_tensor_core_kernels_vs_oracle(emu_engine):
     """BASELINE config 2 at its real size (B = 32, T = 60, N = 3: 5 856 agent-net rows = 46 tiles / 92 chunks) with every tensor-core
     kernel on: k_front_fwd_tc, k_front_bwd_tc, k_wgrad_tc."""
