@@ -212,7 +212,7 @@ def make_cfg(w):
 def workload_config(args, cfg, T, B, world):
     """The `config` object of the JSON line: a function of the command line only, so both arms (--impl engine / reference) print the
     same thing for the same workload.  Arm-specific detail goes to the `notes` key."""
-    E = args.buffer // world if world > 1 else args.buffer
+    E = args.buffer            # weak scaling: every GPU keeps a full-size replay shard (larger than L2) and its own batch
     return dict(workload=args.workload, batch_per_gpu=B, episode_len=T, n_agents=cfg.n_agents, obs_dim=cfg.obs_dim, act_dim=cfg.act_dim,
                 state_dim=cfg.state_dim, buffer_episodes_per_gpu=E, parallelism="dp%d" % world if world > 1 else "single",
                 l2="inputs gathered from a replay larger than L2; the per-step working set is L2-resident by design")
@@ -354,7 +354,7 @@ def run_reference(args):
         return
     cfg, T, B = make_cfg(args.workload)
     world = max(1, args.gpus)
-    E = args.buffer // world if world > 1 else args.buffer         # one rank's shard: the CPU arm is one learner on the host cores
+    E = args.buffer         # one rank's shard: the CPU arm is one learner on the host cores
     avail = args.workload not in NO_AVAIL
     cores = best_cpu_threads(cfg, T, B, min(E, 256), avail)         # (thread-count probe on a small replay: the learner dominates)
     sps, ms = cpu_learner_steps_per_s(cfg, T, B, E, args.steps, args.warmup, cores, avail)
@@ -415,7 +415,7 @@ def run_engine(args):
     dev = capi.device()
     cfg, T, B = make_cfg(args.workload)
     N, O, A, S = cfg.n_agents, cfg.obs_dim, cfg.act_dim, cfg.state_dim
-    E = args.buffer // world if world > 1 else args.buffer            # replay sharded by episode across ranks
+    E = args.buffer            # one full-size replay shard per rank (weak scaling: per-GPU batch AND per-GPU replay fixed; the shard stays larger than L2 at every N)
     rs = np.random.default_rng(rank)
     avail = args.workload not in NO_AVAIL
     buf = factory.make_rec_buffers(N, O, A, S, T, E, per_alpha=0.6 if cfg.use_per else None, norm=not avail, rng="device", max_batch=max(B, 128), avail=avail)
@@ -510,7 +510,7 @@ def run_engine(args):
         allx = [torch.zeros_like(mine) for _ in range(world)]
         torch.distributed.all_gather(allx, mine)
         exchange = dict(per_rank_us=[dict(push=round(float(v[0]), 2), wait=round(float(v[1]), 2), sum=round(float(v[2]), 2), max_wait=round(float(v[3]), 1)) for v in allx],
-                        note="wait = time from this rank's push to the LAST peer's flag: the rank that arrives last waits ~the NVLink flag latency, the others wait for it")
+                        note="stamped by the thread that owns the four scalar columns: push = its stores to the peers, wait = until every peer's lines for those columns have arrived and are summed (flag-in-data lines; option p2p_ll=0: push + fence, wait for the last peer's flag, local sum)")
     launches = int(lib.mx_launch_count() - launches0)
     if tgraph is not None:
         launches = kernels_per_step * args.steps
