@@ -212,6 +212,7 @@ struct OptimArgs {
   int phase;                // k_optim_fused: 0 = whole kernel (grid barrier); 1 / 2 = the halves before / after the barrier as two launches (emulator)
   // data-parallel exchange over peer memory (p2p.cu layout): base of every rank's symmetric block, floats per slot, rank / world (0: none)
   float* p2p_blocks[16];
+  unsigned long long p2p_timeout_ns;      // a peer that has not delivered after this long sets the sticky abort word (option p2p_timeout_ms, default 10 s)
   int p2p_ll;              // 1: flag-in-data exchange lines (option p2p_ll, default); 0: slots + one flag per rank
   float* xstat;             // [8] accumulated by the scalar block (data parallel only): ns spent in push+fence, wait for peers, local sum; launches; max wait
   long long p2p_slot;

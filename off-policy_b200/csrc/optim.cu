@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) k_optim_fused(OptimArgs a) {
               unsigned long long t1;
               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
               if (t0 == 0) t0 = t1;
-              if (t1 - t0 > 10000000000ull || optim_ld_volatile(a.sync + 3)) { atomicExch(a.sync + 3, 1u); break; }     // 10 s: a peer died; do not hang the device
+              if (t1 - t0 > a.p2p_timeout_ns || optim_ld_volatile(a.sync + 3)) { atomicExch(a.sync + 3, 1u); break; }     // 10 s: a peer died; do not hang the device
             }
           }
         }
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256) k_optim_fused(OptimArgs a) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
       while (optim_ld_volatile(my_flags + tid) < step) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 10000000000ull) { atomicExch(a.sync + 3, 1u); break; }      // 10 s: a peer died; do not hang the device
+        if (t1 - t0 > a.p2p_timeout_ns) { atomicExch(a.sync + 3, 1u); break; }      // 10 s: a peer died; do not hang the device
       }
       __threadfence_system();            // acquire: the peer's slot writes precede its flag store
 #endif

@@ -30,6 +30,7 @@ struct P2pArgs {
   unsigned* counter;           // local: CTAs of k_p2p_push that have finished
   float* info;                 // info[7] = -1 when a peer never arrived (time-out)
   int rank, world;
+  unsigned long long timeout_ns;   // option p2p_timeout_ms (default 10 s)
 };
 
 MX_DEVINL unsigned* p2p_flags(float* block, long long slot_floats, int world) { return reinterpret_cast<unsigned*>(block + 2 * (size_t)world * slot_floats); }
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(256) k_p2p_sum(P2pArgs a) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*f < step) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 10000000000ull) { s_bad = 1; break; }      // 10 s: a peer died; do not hang the device
+      if (t1 - t0 > a.timeout_ns) { s_bad = 1; break; }      // 10 s: a peer died; do not hang the device
     }
     __threadfence_system();              // acquire: the peer's slot writes precede its flag store
 #else
@@ -130,6 +131,7 @@ static P2pArgs p2p_args(mx_qmix* q) {
   a.counter = q->p2p_counter;
   a.info = q->ws + q->W.info;
   a.rank = q->p2p_rank; a.world = q->p2p_world;
+  a.timeout_ns = (unsigned long long)(g_mx_p2p_timeout_ms > 0 ? g_mx_p2p_timeout_ms : 10000) * 1000000ull;
   return a;
 }
 

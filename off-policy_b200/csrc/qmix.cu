@@ -290,6 +290,7 @@ static OptimArgs optim_args(mx_qmix* q, int B, const int parts[4], bool after_ex
   o.sync = reinterpret_cast<unsigned*>(ws + q->W.sync);
   o.xstat = ws + q->W.xstat;
   o.p2p_world = q->p2p_world; o.p2p_rank = q->p2p_rank; o.p2p_slot = mx_round_up64(q->P + 8, 64); o.p2p_ll = g_mx_p2p_ll ? 1 : 0;
+  o.p2p_timeout_ns = (unsigned long long)(g_mx_p2p_timeout_ms > 0 ? g_mx_p2p_timeout_ms : 10000) * 1000000ull;
   for (int p = 0; p < q->p2p_world; ++p) o.p2p_blocks[p] = q->p2p_blocks[p];
   return o;
 }

@@ -198,3 +198,45 @@ def test_per_agent_policies_match_reference_golden(gpu_engine, name):
 def test_per_agent_policies_through_the_multi_policy_buffer(gpu_engine):
     import maddpg_checks as mdc
     mdc.check_multi_golden("maddpg_multi_disc", through_buffer=True)
+
+
+@pytest.mark.parametrize("ll", [1, 0])
+def test_dead_peer_aborts_the_update_and_the_host_raises(gpu_engine, ll):
+    """ADVICE (round 1): a rank whose peer never delivers must not apply an update from stale or partial sums.  One GPU is enough to
+    show it: a world-2 learner is given its own symmetric block plus a second local block that nobody ever writes (the "peer" that
+    died).  With the wait shortened to 30 ms (option p2p_timeout_ms; 10 s in production) the step must end with info[7] = -1,
+    parameters, targets and Adam state untouched, and the NEXT train call must raise (QMix._check_exchange).  Both exchange protocols."""
+    import time
+    import torch
+    from helpers import load_golden, oracle_from_golden, golden_batch, sub
+    capi = gpu_engine
+    lib = capi.lib()
+    g = load_golden("qmix_small")
+    L, cfg, B, T, steps = oracle_from_golden(g)
+    lib.mx_set_option(b"p2p_timeout_ms", 30)
+    lib.mx_set_option(b"p2p_ll", ll)
+    try:
+        args, pol, tr = qc.build_trainer(cfg, B, T, debug=False, dp_world_size=2)
+        qc.load_state(pol, tr, sub(g, "init.agent."), sub(g, "init.mixer."), sub(g, "init.tgt_agent."), sub(g, "init.tgt_mixer."))
+        n = int(lib.mx_qmix_p2p_block_bytes(tr.handle)) // 4
+        blocks = [torch.zeros(n, dtype=torch.float32, device=tr.dev) for _ in range(2)]
+        tr.attach_peer_blocks(0, [b.data_ptr() for b in blocks], keep=blocks)
+        tr.use_step_graph = False
+        before = [t.clone() for t in (tr.theta, tr.theta_tgt, tr.adam_m, tr.adam_v)]
+        t_before = tr.ws_view("adam_t", torch.float64).clone()
+        batch = golden_batch(g, 0)
+        t0 = time.time()
+        tr.train_policy_on_batch(qc.ref_tuple(batch))
+        torch.cuda.synchronize()
+        assert time.time() - t0 < 5.0                                        # the shortened wait, not the 10 s default
+        assert float(tr._info[7]) == -1.0
+        for a, b in zip(before, (tr.theta, tr.theta_tgt, tr.adam_m, tr.adam_v)):
+            assert torch.equal(a, b)                                          # nothing was applied
+        assert torch.equal(t_before, tr.ws_view("adam_t", torch.float64))
+        with pytest.raises(RuntimeError, match="did not deliver"):
+            for _ in range(3):                                                # the mirrored flag is read one step late, without a sync
+                tr.train_policy_on_batch(qc.ref_tuple(batch))
+                torch.cuda.synchronize()
+    finally:
+        lib.mx_set_option(b"p2p_timeout_ms", 10000)
+        lib.mx_set_option(b"p2p_ll", 1)
