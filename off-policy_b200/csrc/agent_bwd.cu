@@ -253,13 +253,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_gru_bwd(GruBwdArgs a) {
 // 48 packed FFMA2 per thread in four 12-deep chains, two xor-shuffle levels for the two column sums.  Lanes s = 0, 1 (and their
 // duplicates 2, 3) own unit 2kp + (s & 1) for the gate derivatives; the stores of a unit are split between the two duplicates.
 #define BWD2_THREADS 128
+// ROWS = 2: two sequence rows per CTA through the same register-resident W_hh slice (see k_gru_fwd2), for shapes with more rows than
+// two CTAs per SM hold at once
+template <int ROWS>
 __global__ void __launch_bounds__(BWD2_THREADS, 2) k_gru_bwd2(GruBwdArgs a) {
   constexpr int RING = 8, PF = 6;
-  __shared__ __align__(16) float ops_s[RING][6][MX_H];
-  __shared__ __align__(16) float dgh_s[2][MX_G];
+  __shared__ __align__(16) float ops_s[RING][ROWS][6][MX_H];
+  __shared__ __align__(16) float dgh_s[2][ROWS][MX_G];
   const int tid = threadIdx.x;
   const int kp = tid >> 2, s = tid & 3;
-  const int row = blockIdx.x;
   float2 w0[24], w1[24];
 #pragma unroll
   for (int m = 0; m < 12; ++m)
@@ -271,32 +273,51 @@ __global__ void __launch_bounds__(BWD2_THREADS, 2) k_gru_bwd2(GruBwdArgs a) {
     }
   const int T1 = a.T1 > 0 ? a.T1 : a.T + 1, N = a.N;
   MX_PDL_WAIT();
-  const size_t m0 = ((size_t)(row / N) * T1) * N + (row % N);
   const int t_first = a.T - 1;
-  // prefetch: 96 16-byte pieces per step, one per thread (threads < 96)
+  // prefetch: 96 16-byte pieces per row-step, one per thread (threads < 96)
   const bool pf_on = tid < 96;
   const int op = pf_on ? tid / 16 : 0, q4 = tid % 16;
   const bool pf_hprev = op == 4;
-  size_t pf_stride = (size_t)N * (op < 3 ? MX_G : MX_H);
-  const float* base = op < 3 ? a.gates + m0 * MX_G + op * MX_H + 4 * q4 : (op == 3 ? a.hn : (op == 4 ? a.hall : a.dh_out)) + m0 * MX_H + 4 * q4;
-  const float* pf_src = base + (ptrdiff_t)(pf_hprev ? t_first - 1 : t_first) * (ptrdiff_t)pf_stride;
-  const float* pf_h0 = (pf_hprev && a.h0) ? a.h0 + (size_t)row * MX_H + 4 * q4 : nullptr;
-  float* pf_dst = &ops_s[0][op][4 * q4];
+  const size_t pf_stride = (size_t)N * (op < 3 ? MX_G : MX_H);
+  const int ku = 2 * kp + (s & 1);          // unit of this lane; the lane and its duplicate (s ^ 2) split the unit's stores
+  const int half = s >> 1;
+  const size_t dg_stride = (size_t)N * MX_G;
+  bool rok[ROWS];
+  const float* pf_src[ROWS];
+  const float* pf_h0[ROWS];
+  float* dgp[ROWS];
+  float carry[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int row = blockIdx.x * ROWS + r;
+    rok[r] = row < a.R;
+    const int rr = rok[r] ? row : 0;
+    const size_t m0 = ((size_t)(rr / N) * T1) * N + (rr % N);
+    const float* base = op < 3 ? a.gates + m0 * MX_G + op * MX_H + 4 * q4 : (op == 3 ? a.hn : (op == 4 ? a.hall : a.dh_out)) + m0 * MX_H + 4 * q4;
+    pf_src[r] = base + (ptrdiff_t)(pf_hprev ? t_first - 1 : t_first) * (ptrdiff_t)pf_stride;
+    pf_h0[r] = (pf_hprev && a.h0) ? a.h0 + (size_t)rr * MX_H + 4 * q4 : nullptr;
+    if (rok[r])
+      for (int tz = a.T; tz < T1; ++tz)       // rows of dgi that receive no gradient (t >= TB; for QMIX: the bootstrap step t == T)
+        for (int c = tid; c < MX_G; c += BWD2_THREADS) a.dgi[(m0 + (size_t)tz * N) * MX_G + c] = 0.f;
+    dgp[r] = a.dgi + (m0 + (size_t)t_first * N) * MX_G + ku;
+    carry[r] = 0.f;
+  }
+  float* pf_dst = &ops_s[0][0][op][4 * q4];
   auto prefetch = [&](int t) {        // called with t = T-1, T-2, ... in order
     if (t >= 0 && pf_on) {
       const bool first = pf_hprev && t == 0;             // h_{-1} = h0, or zeros (zero-fill form of the copy: no branch)
-      mx_cp16z(pf_dst + (t & (RING - 1)) * (6 * MX_H), first ? (pf_h0 ? pf_h0 : a.hall) : pf_src, (first && !pf_h0) ? 0 : 16);
-      pf_src -= pf_stride;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if (rok[r]) mx_cp16z(pf_dst + ((t & (RING - 1)) * ROWS + r) * (6 * MX_H), first ? (pf_h0[r] ? pf_h0[r] : a.hall) : pf_src[r], (first && !pf_h0[r]) ? 0 : 16);
+        pf_src[r] -= pf_stride;
+      }
     }
     mx_cp_commit();
   };
-  for (int tz = a.T; tz < T1; ++tz)       // rows of dgi that receive no gradient (t >= TB; for QMIX: the bootstrap step t == T)
-    for (int c = tid; c < MX_G; c += BWD2_THREADS) a.dgi[(m0 + (size_t)tz * N) * MX_G + c] = 0.f;
-  const int ku = 2 * kp + (s & 1);          // unit of this lane; the lane and its duplicate (s ^ 2) split the unit's stores
-  const int half = s >> 1;
-  float* dgp = a.dgi + (m0 + (size_t)t_first * N) * MX_G + ku;
-  const size_t dg_stride = (size_t)N * MX_G;
-  float carry = 0.f;
+  if (ROWS > 1) {      // a row slot without a row (odd R): its operands stay zero, nothing of it is stored
+    for (int idx = tid; idx < RING * ROWS * 6 * MX_H; idx += BWD2_THREADS) (&ops_s[0][0][0][0])[idx] = 0.f;
+    __syncthreads();
+  }
 #pragma unroll
   for (int d = 0; d < PF; ++d) prefetch(t_first - d);
   mx_cp_wait<PF - 1>();
@@ -304,34 +325,43 @@ __global__ void __launch_bounds__(BWD2_THREADS, 2) k_gru_bwd2(GruBwdArgs a) {
 
   auto step = [&](const int t, const int cur) {
     prefetch(t - PF);
-    const float* o = &ops_s[t & (RING - 1)][0][0];
-    const float rg = o[ku], zg = o[MX_H + ku], ng = o[2 * MX_H + ku], hn = o[3 * MX_H + ku], hp = o[4 * MX_H + ku];
-    const float dh = o[5 * MX_H + ku] + carry;
-    const float d_n = dh * (1.f - zg) * (1.f - ng * ng);
-    const float d_z = dh * (hp - ng) * zg * (1.f - zg);
-    const float d_r = d_n * hn * rg * (1.f - rg);
-    // half 0: r (and z); half 1: n
-    dgh_s[cur][(half ? 2 * MX_H : 0) + ku] = half ? d_n * rg : d_r;
-    if (!half) dgh_s[cur][MX_H + ku] = d_z;
-    dgp[half ? 2 * MX_H : 0] = half ? d_n : d_r;
-    if (!half) dgp[MX_H] = d_z;
-    dgp -= dg_stride;
-    const float cz = dh * zg;
+    float cz[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float* o = &ops_s[t & (RING - 1)][r][0][0];
+      const float rg = o[ku], zg = o[MX_H + ku], ng = o[2 * MX_H + ku], hn = o[3 * MX_H + ku], hp = o[4 * MX_H + ku];
+      const float dh = o[5 * MX_H + ku] + carry[r];
+      const float d_n = dh * (1.f - zg) * (1.f - ng * ng);
+      const float d_z = dh * (hp - ng) * zg * (1.f - zg);
+      const float d_r = d_n * hn * rg * (1.f - rg);
+      // half 0: r (and z); half 1: n
+      dgh_s[cur][r][(half ? 2 * MX_H : 0) + ku] = half ? d_n * rg : d_r;
+      if (!half) dgh_s[cur][r][MX_H + ku] = d_z;
+      if (rok[r]) {
+        dgp[r][half ? 2 * MX_H : 0] = half ? d_n : d_r;
+        if (!half) dgp[r][MX_H] = d_z;
+      }
+      dgp[r] -= dg_stride;
+      cz[r] = dh * zg;
+    }
     mx_cp_wait<PF - 1>();
     __syncthreads();
-    float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
 #pragma unroll
-    for (int m = 0; m < 12; ++m) {
-      const float4 d = mx_ld4(&dgh_s[cur][16 * m + 4 * s]);
-      const float2 lo = make_float2(d.x, d.y), hi = make_float2(d.z, d.w);
-      a0 = mx_ffma2(w0[2 * m], lo, a0); b0 = mx_ffma2(w1[2 * m], lo, b0);
-      a1 = mx_ffma2(w0[2 * m + 1], hi, a1); b1 = mx_ffma2(w1[2 * m + 1], hi, b1);
+    for (int r = 0; r < ROWS; ++r) {
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+      for (int m = 0; m < 12; ++m) {
+        const float4 d = mx_ld4(&dgh_s[cur][r][16 * m + 4 * s]);
+        const float2 lo = make_float2(d.x, d.y), hi = make_float2(d.z, d.w);
+        a0 = mx_ffma2(w0[2 * m], lo, a0); b0 = mx_ffma2(w1[2 * m], lo, b0);
+        a1 = mx_ffma2(w0[2 * m + 1], hi, a1); b1 = mx_ffma2(w1[2 * m + 1], hi, b1);
+      }
+      a0 = mx_fadd2(a0, a1); b0 = mx_fadd2(b0, b1);
+      float p0 = a0.x + a0.y, p1 = b0.x + b0.y;
+      p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+      p0 += __shfl_xor_sync(0xffffffffu, p0, 2); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+      carry[r] = cz[r] + ((s & 1) ? p1 : p0);     // dh_{t-1}[ku] = z*dh + W_hh^T dgh
     }
-    a0 = mx_fadd2(a0, a1); b0 = mx_fadd2(b0, b1);
-    float p0 = a0.x + a0.y, p1 = b0.x + b0.y;
-    p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
-    p0 += __shfl_xor_sync(0xffffffffu, p0, 2); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
-    carry = cz + ((s & 1) ? p1 : p0);     // dh_{t-1}[ku] = z*dh + W_hh^T dgh
   };
   int t = t_first;
   for (; t >= 1; t -= 2) { step(t, 0); step(t - 1, 1); }
@@ -864,7 +894,9 @@ int mx_launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
   while (rpc < 4 && mx_ceil_div(a.R, rpc) > 2 * sms) rpc *= 2;
   if (g_mx_gru_bwd_rpc == 1 || g_mx_gru_bwd_rpc == 2 || g_mx_gru_bwd_rpc == 4) rpc = g_mx_gru_bwd_rpc;
   if (g_mx_gru_threads == 128 || (g_mx_gru_threads == 0 && g_mx_gru_bwd_rpc == 0 && a.T >= 8)) {      // default at every size (r02 sweeps)
-    MX_LAUNCH_PDL(k_gru_bwd2, dim3(a.R), dim3(BWD2_THREADS), 0, s, a);
+    const bool two = g_mx_gru_rows == 2 || (g_mx_gru_rows == 0 && a.R > 2 * mx_num_sms());      // more row-CTAs than fit at once
+    if (two) MX_LAUNCH_PDL(k_gru_bwd2<2>, dim3((a.R + 1) / 2), dim3(BWD2_THREADS), 0, s, a);
+    else MX_LAUNCH_PDL(k_gru_bwd2<1>, dim3(a.R), dim3(BWD2_THREADS), 0, s, a);
     MX_COUNT();
     MX_MARK("k_gru_bwd", s);
     return MX_CHECK_LAUNCH("gru_bwd2");

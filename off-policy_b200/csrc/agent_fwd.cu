@@ -284,14 +284,16 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) k_gru_fwd(GruFwdArgs a) {
 // every scheduler sees two warps instead of four, and on the others one -- the step is a dependent chain, fewer co-resident warps means
 // less issue and LSU contention; one xor-shuffle level instead of two.  Measured against the 256-thread kernel in profiles/ (r02).
 #define GRU2_THREADS 128
+// ROWS = 2: the CTA carries two sequence rows through the same register-resident weights (their two dependent chains interleave), for
+// shapes with more row-CTAs than two per SM can hold at once (SMAC 8m: 1 024 row-CTAs = 3.5 waves of 296; option gru_rows)
+template <int ROWS>
 __global__ void __launch_bounds__(GRU2_THREADS, 2) k_gru_fwd2(GruFwdArgs a) {
-  __shared__ __align__(16) float h_s[2][MX_H];
-  __shared__ __align__(16) float gi_s[GRU_RING][MX_G];
+  __shared__ __align__(16) float h_s[2][ROWS][MX_H];
+  __shared__ __align__(16) float gi_s[GRU_RING][ROWS][MX_G];
   const int net = blockIdx.y;
   const float* __restrict__ th = net ? a.theta[1] : a.theta[0];
   const int tid = threadIdx.x;
   const int i = tid >> 1, q = tid & 1;
-  const int row = blockIdx.x;
   const bool live = (net == 0) && a.gates != nullptr;
   float2 wr[16], wz[16], wn[16];
 #pragma unroll
@@ -305,24 +307,39 @@ __global__ void __launch_bounds__(GRU2_THREADS, 2) k_gru_fwd2(GruFwdArgs a) {
     }
   const float br = th[a.bhh + i], bz = th[a.bhh + MX_H + i], bn = th[a.bhh + 2 * MX_H + i];
   MX_PDL_WAIT();
-  for (int idx = tid; idx < 2 * MX_H; idx += GRU2_THREADS) (&h_s[0][0])[idx] = (a.h0 && idx < MX_H) ? a.h0[(size_t)row * MX_H + idx] : 0.f;
   const float* gi = net ? a.gi[1] : a.gi[0];
   float* hall = net ? a.hall[1] : a.hall[0];
   const int T1 = a.T + 1, N = a.N;
-  const int b = row / N, n = row % N;
-  const size_t m0 = ((size_t)b * T1) * N + n;
   // lane-uniform stores: lane 0 of a pair writes h, r, W_hn h + b_hn; lane 1 writes z, n
-  float* p1 = q == 0 ? hall + m0 * MX_H + i : (live ? a.gates + m0 * MX_G + MX_H + i : hall);
-  float* p2 = live ? a.gates + m0 * MX_G + (q == 0 ? 0 : 2 * MX_H) + i : hall;
-  float* p3 = live ? a.hn + m0 * MX_H + i : hall;
+  float *p1[ROWS], *p2[ROWS], *p3[ROWS];
+  bool rok[ROWS];
+  const float* pf_src[ROWS];
+  const bool pf_on = tid < MX_G / 4;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int row = blockIdx.x * ROWS + r;
+    rok[r] = row < a.R;
+    const int rr = rok[r] ? row : 0;
+    for (int idx = tid; idx < 2 * MX_H; idx += GRU2_THREADS) (&h_s[0][0][0])[(idx >> 6) * ROWS * MX_H + r * MX_H + (idx & 63)] = (a.h0 && idx < MX_H && rok[r]) ? a.h0[(size_t)rr * MX_H + idx] : 0.f;
+    const int b = rr / N, n = rr % N;
+    const size_t m0 = ((size_t)b * T1) * N + n;
+    p1[r] = q == 0 ? hall + m0 * MX_H + i : (live ? a.gates + m0 * MX_G + MX_H + i : hall);
+    p2[r] = live ? a.gates + m0 * MX_G + (q == 0 ? 0 : 2 * MX_H) + i : hall;
+    p3[r] = live ? a.hn + m0 * MX_H + i : hall;
+    pf_src[r] = gi + m0 * MX_G + 4 * (pf_on ? tid : 0);
+  }
   const bool on1 = q == 0 || live, on2 = live, on3 = live && q == 0;
   const size_t s1 = (size_t)N * ((q == 0) ? MX_H : MX_G), s2 = (size_t)N * MX_G, s3 = (size_t)N * MX_H;
-  const bool pf_on = tid < MX_G / 4;
-  const float* pf_src = gi + m0 * MX_G + 4 * (pf_on ? tid : 0);
-  float* pf_dst = &gi_s[0][4 * (pf_on ? tid : 0)];
+  float* pf_dst = &gi_s[0][0][4 * (pf_on ? tid : 0)];
   const size_t pf_stride = (size_t)N * MX_G;
   auto prefetch = [&](int t) {
-    if (pf_on && t < T1) { mx_cp16(pf_dst + (t & (GRU_RING - 1)) * MX_G, pf_src); pf_src += pf_stride; }
+    if (pf_on && t < T1) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if (rok[r]) mx_cp16(pf_dst + ((t & (GRU_RING - 1)) * ROWS + r) * MX_G, pf_src[r]);
+        pf_src[r] += pf_stride;
+      }
+    }
     mx_cp_commit();
   };
 #pragma unroll
@@ -333,32 +350,37 @@ __global__ void __launch_bounds__(GRU2_THREADS, 2) k_gru_fwd2(GruFwdArgs a) {
   auto step = [&](const int t, const int cur) {
     const int nxt = cur ^ 1;
     prefetch(t + GRU_PF);
-    const float* g = &gi_s[t & (GRU_RING - 1)][0];
-    const float* hrow = &h_s[cur][0];
-    float4 hv[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) hv[m] = mx_ld4(hrow + 8 * m + 4 * q);
-    const float gr = g[i] + br, gz = g[MX_H + i] + bz, gn = g[2 * MX_H + i], hp = hrow[i];
-    float2 r0 = make_float2(0.f, 0.f), r1 = r0, z0 = r0, z1 = r0, n0 = r0, n1 = r0;
+    for (int r = 0; r < ROWS; ++r) {
+      const float* g = &gi_s[t & (GRU_RING - 1)][r][0];
+      const float* hrow = &h_s[cur][r][0];
+      float4 hv[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const float2 lo = make_float2(hv[m].x, hv[m].y), hi = make_float2(hv[m].z, hv[m].w);
-      r0 = mx_ffma2(wr[2 * m], lo, r0); n0 = mx_ffma2(wn[2 * m], lo, n0); z0 = mx_ffma2(wz[2 * m], lo, z0);
-      r1 = mx_ffma2(wr[2 * m + 1], hi, r1); n1 = mx_ffma2(wn[2 * m + 1], hi, n1); z1 = mx_ffma2(wz[2 * m + 1], hi, z1);
+      for (int m = 0; m < 8; ++m) hv[m] = mx_ld4(hrow + 8 * m + 4 * q);
+      const float gr = g[i] + br, gz = g[MX_H + i] + bz, gn = g[2 * MX_H + i], hp = hrow[i];
+      float2 r0 = make_float2(0.f, 0.f), r1 = r0, z0 = r0, z1 = r0, n0 = r0, n1 = r0;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const float2 lo = make_float2(hv[m].x, hv[m].y), hi = make_float2(hv[m].z, hv[m].w);
+        r0 = mx_ffma2(wr[2 * m], lo, r0); n0 = mx_ffma2(wn[2 * m], lo, n0); z0 = mx_ffma2(wz[2 * m], lo, z0);
+        r1 = mx_ffma2(wr[2 * m + 1], hi, r1); n1 = mx_ffma2(wn[2 * m + 1], hi, n1); z1 = mx_ffma2(wz[2 * m + 1], hi, z1);
+      }
+      r0 = mx_fadd2(r0, r1); n0 = mx_fadd2(n0, n1); z0 = mx_fadd2(z0, z1);
+      float pr = r0.x + r0.y, pn = n0.x + n0.y, pz = z0.x + z0.y;
+      pr += __shfl_xor_sync(0xffffffffu, pr, 1); pn += __shfl_xor_sync(0xffffffffu, pn, 1); pz += __shfl_xor_sync(0xffffffffu, pz, 1);
+      const float rg = mx_sigmoid_fast(pr + gr);
+      const float hn = pn + bn;
+      const float ng = mx_tanh_fast(fmaf(rg, hn, gn));
+      const float zg = mx_sigmoid_fast(pz + gz);
+      const float hnew = fmaf(zg, hp - ng, ng);
+      h_s[nxt][r][i] = hnew;                  // both lanes of the pair store the same value: one code path for every lane
+      if (rok[r]) {
+        if (on1) *p1[r] = q == 0 ? hnew : zg;
+        if (on2) *p2[r] = q == 0 ? rg : ng;
+        if (on3) *p3[r] = hn;
+      }
+      p1[r] += s1; p2[r] += s2; p3[r] += s3;
     }
-    r0 = mx_fadd2(r0, r1); n0 = mx_fadd2(n0, n1); z0 = mx_fadd2(z0, z1);
-    float pr = r0.x + r0.y, pn = n0.x + n0.y, pz = z0.x + z0.y;
-    pr += __shfl_xor_sync(0xffffffffu, pr, 1); pn += __shfl_xor_sync(0xffffffffu, pn, 1); pz += __shfl_xor_sync(0xffffffffu, pz, 1);
-    const float rg = mx_sigmoid_fast(pr + gr);
-    const float hn = pn + bn;
-    const float ng = mx_tanh_fast(fmaf(rg, hn, gn));
-    const float zg = mx_sigmoid_fast(pz + gz);
-    const float hnew = fmaf(zg, hp - ng, ng);
-    h_s[nxt][i] = hnew;                  // both lanes of the pair store the same value: one code path for every lane
-    if (on1) *p1 = q == 0 ? hnew : zg;
-    if (on2) *p2 = q == 0 ? rg : ng;
-    if (on3) *p3 = hn;
-    p1 += s1; p2 += s2; p3 += s3;
     mx_cp_wait<GRU_PF - 1>();
     __syncthreads();
   };
@@ -560,7 +582,9 @@ int mx_launch_gru_fwd(const GruFwdArgs& a, int nets, cudaStream_t s) {
   if (g_mx_gru_fwd_rpc == 1 || g_mx_gru_fwd_rpc == 2 || g_mx_gru_fwd_rpc == 4) rpc = g_mx_gru_fwd_rpc;
   // the 128-thread kernel (one row per CTA); the 256-thread kernels stay behind gru_threads=256 / gru_*_rpc
   if (g_mx_gru_threads == 128 || (g_mx_gru_threads == 0 && g_mx_gru_fwd_rpc == 0 && a.T + 1 >= 8)) {      // (one-step "branch" calls of R-MADDPG keep the multi-row CTAs: a CTA per row would spend its time loading W_hh)      // default at every size (r02 sweeps: 3m 174 vs 188 us, 2s3z 555 vs 619, 8m 1408 vs 1494)
-    MX_LAUNCH_PDL(k_gru_fwd2, dim3(a.R, nets), dim3(GRU2_THREADS), 0, s, a);
+    const bool two = g_mx_gru_rows == 2 || (g_mx_gru_rows == 0 && (long long)a.R * nets > 2LL * mx_num_sms());      // more row-CTAs than fit at once
+    if (two) MX_LAUNCH_PDL(k_gru_fwd2<2>, dim3((a.R + 1) / 2, nets), dim3(GRU2_THREADS), 0, s, a);
+    else MX_LAUNCH_PDL(k_gru_fwd2<1>, dim3(a.R, nets), dim3(GRU2_THREADS), 0, s, a);
     MX_COUNT();
     MX_MARK("k_gru_fwd", s);
     return MX_CHECK_LAUNCH("gru_fwd2");

@@ -18,6 +18,7 @@ int g_mx_pdl_skip_next = 0;
 
 // runtime options shared by the product and the emulated build (mx_set_option)
 int g_mx_p2p_timeout_ms = 10000;      // how long a rank waits for a peer's gradient before it sets the sticky abort word (tests shorten it)
+int g_mx_gru_rows = 0;        // rows per CTA of the 128-thread recurrences: 0 = automatic (2 when there are more row-CTAs than two per SM hold at once), 1, 2
 int g_mx_p2p_ll = 1;          // data-parallel exchange inside k_optim_fused: 1 = flag-in-data lines (no fence / counter / flag hop), 0 = slots + per-rank flags
 int g_mx_mixer_split = 1;      // 1: split mixer (hypernet-forward / core / hypernet-backward kernels) whenever the forked branch is
                                //    in use; 2: always; 0: always the single fused k_mixer
@@ -46,6 +47,7 @@ int mx_set_option_common(const char* name, int value) {
   if (!strcmp(name, "front_bwd_mma")) { g_mx_front_bwd_mma = value; return 0; }
   if (!strcmp(name, "gru_wgrad_split")) { g_mx_gru_wgrad_split = value; return 0; }
   if (!strcmp(name, "p2p_ll")) { g_mx_p2p_ll = value; return 0; }
+  if (!strcmp(name, "gru_rows")) { g_mx_gru_rows = value; return 0; }
   if (!strcmp(name, "p2p_timeout_ms")) { g_mx_p2p_timeout_ms = value; return 0; }
 #if !MX_EMU
   if (!strcmp(name, "smem_carveout")) { g_mx_smem_carveout = value; return 0; }

@@ -167,6 +167,33 @@ def test_recurrence_kernel_variants_match_reference_golden(emu_engine, name, deb
         lib.mx_set_option(b"gru_threads", 0)
 
 
+@pytest.mark.parametrize("name,debug", [("qmix_small", True), ("qmix_5ag", False), ("qmix_small_per", False), ("qmix_small_tanh", True)])
+def test_two_rows_per_cta_recurrences_match_reference_golden(emu_engine, name, debug):
+    """Option gru_rows = 2: k_gru_fwd2<2> / k_gru_bwd2<2> carry two sequence rows per CTA through the same register-resident W_hh slice (picked
+    automatically when there are more row-CTAs than two per SM hold at once: SMAC 8m).  Intermediates included; odd row counts leave
+    the last CTA with one empty slot."""
+    lib = emu_engine.lib()
+    lib.mx_set_option(b"gru_rows", 2)
+    try:
+        qc.check_step_against(None, name, intermediates=True, debug=debug)
+    finally:
+        lib.mx_set_option(b"gru_rows", 0)
+
+
+def test_two_rows_per_cta_recurrences_odd_row_count_vs_oracle(emu_engine):
+    from oracle.qmix import QmixConfig, synth_batch
+    lib = emu_engine.lib()
+    cfg = QmixConfig(n_agents=3, obs_dim=9, act_dim=5, state_dim=11, gain=1.0)
+    B, T = 5, 9            # 15 rows: the eighth CTA of each net has one row and one empty slot
+    lib.mx_set_option(b"gru_rows", 2)
+    try:
+        L, args, pol, tr = qc.oracle_and_trainer(cfg, B, T)
+        batch = synth_batch(cfg, B, T, seed=21, avail_p=0.8, var_len=True) + (None, None)
+        qc.compare_step(L, pol, tr, batch, cfg, steps=2)
+    finally:
+        lib.mx_set_option(b"gru_rows", 0)
+
+
 @pytest.mark.parametrize("name", ["maddpg_box", "matd3_disc_avail"])
 def test_recurrence_kernel_128_threads_maddpg(emu_engine, name):
     """R-MADDPG uses the recurrences with an initial state (branch steps, h0) and T1 != T + 1: the 128-thread kernels on those paths."""
@@ -175,8 +202,11 @@ def test_recurrence_kernel_128_threads_maddpg(emu_engine, name):
     lib.mx_set_option(b"gru_threads", 128)
     try:
         mdc.check_golden(name)
+        lib.mx_set_option(b"gru_rows", 2)          # two rows per CTA on the same paths (initial state h0, T1 != T + 1)
+        mdc.check_golden(name)
     finally:
         lib.mx_set_option(b"gru_threads", 0)
+        lib.mx_set_option(b"gru_rows", 0)
 
 
 @pytest.mark.parametrize("threads", [128, 256])
