@@ -18,7 +18,8 @@ int g_mx_pdl_skip_next = 0;
 
 // runtime options shared by the product and the emulated build (mx_set_option)
 int g_mx_p2p_timeout_ms = 10000;      // how long a rank waits for a peer's gradient before it sets the sticky abort word (tests shorten it)
-int g_mx_gru_rows = 0;        // rows per CTA of the 128-thread recurrences: 0 = automatic (2 when there are more row-CTAs than two per SM hold at once), 1, 2
+int g_mx_gru_rows = 1;        // rows per CTA of the 128-thread recurrences: 1 (default), 2, 0 = 2 when there are more row-CTAs than two per SM hold at once.
+                              // B200, visit 20: two rows per CTA do not pay -- 8m 1 060 vs 1 049 us (k_gru_bwd2 105 -> 86 us alone, k_gru_fwd2 unchanged at 156), 2s3z 438 vs 430
 int g_mx_p2p_ll = 1;          // data-parallel exchange inside k_optim_fused: 1 = flag-in-data lines (no fence / counter / flag hop), 0 = slots + per-rank flags
 int g_mx_mixer_split = 1;      // 1: split mixer (hypernet-forward / core / hypernet-backward kernels) whenever the forked branch is
                                //    in use; 2: always; 0: always the single fused k_mixer
