@@ -682,7 +682,7 @@ def run_engine(args):
         metric="learner grad-steps/sec", value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
         config=workload_config(args, cfg, T, B, world),
-        notes=dict(grad_exchange=("all-reduce over NVLink peer memory INSIDE the optimiser kernel (k_optim_fused: push to every peer's slot, local rank-ordered sum)" if p2p
+        notes=dict(grad_exchange=("all-reduce over NVLink peer memory INSIDE the optimiser kernel (k_optim_fused: {value, step} lines pushed to every peer, rank-ordered sum as they arrive)" if p2p
                                   else "NCCL all-reduce of the flat gradient buffer") if world > 1 else None,
                    value_definition="batch-%d grad-steps/s summed over ranks (each rank samples its own shard; one flat all-reduce)" % B,
                    replay_mb=round(pb.L.total_bytes / 1e6, 1),
