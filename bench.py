@@ -78,9 +78,17 @@ def run_maddpg(args):
     from offpolicy._b200 import capi
     from offpolicy._b200 import factory as mc
     from offpolicy._b200 import factory as rc
-    from oracle.maddpg import MaddpgConfig, MaddpgLearner, synth_batch_cont, synth_batch_disc, sample_gumbel
     n, o, a, sdim, T, B, td3, disc = MADDPG_WORKLOADS[args.workload]
-    cfg = MaddpgConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim, td3=td3, actor_update_interval=2 if td3 else 1, gain=1.0, discrete=disc)
+    cfg = mc.MaddpgLearnerConfig(n_agents=n, obs_dim=o, act_dim=a, state_dim=sdim, td3=td3, actor_update_interval=2 if td3 else 1, gain=1.0, discrete=disc)
+
+    def sample_gumbel(shape, eps=1e-20):        # util.py:127-130: one uniform_ draw from torch's CPU generator
+        u = torch.empty(*shape).uniform_()
+        return -torch.log(-torch.log(u + eps) + eps)
+
+    def cpu_learner():        # the CPU arm only: the oracle port of the reference learner, same configuration values
+        import dataclasses
+        from oracle.maddpg import MaddpgConfig, MaddpgLearner
+        return MaddpgLearner(MaddpgConfig(**dataclasses.asdict(cfg)), seed=1)
     E = min(args.buffer, 5000)
     rs = np.random.default_rng(0)
 
@@ -103,7 +111,7 @@ def run_maddpg(args):
         buf = UniformReplay(min(E, 1024), T, n, o, sdim, a, use_avail=False)
         for c in range(0, min(E, 1024), 64):
             buf.insert(64, *episodes(64), None)
-        L = MaddpgLearner(cfg, seed=1)
+        L = cpu_learner()
         np.random.seed(1)
         times = []
         for s in range(args.warmup + args.steps):
@@ -176,7 +184,8 @@ def run_maddpg(args):
     torch.cuda.synchronize()
     e2e = n_e2e / (time.perf_counter() - t0)
     torch.set_num_threads(8)
-    L = MaddpgLearner(cfg, seed=1)
+    L = cpu_learner()
+    from oracle.maddpg import synth_batch_cont, synth_batch_disc
     tms = []
     for s in range(8):
         batch = (synth_batch_disc if disc else synth_batch_cont)(cfg, B, T, seed=s) + (None, None)

@@ -39,6 +39,36 @@ class LearnerConfig:
     gain: float = 0.01
 
 
+@dataclass
+class MaddpgLearnerConfig:
+    """What a bench / example needs to describe an R-MADDPG / R-MATD3 learner (attribute names = the oracle's MaddpgConfig, so the CPU
+    arm can be built from the same values; nothing here imports the oracle)."""
+    n_agents: int = 3
+    obs_dim: int = 18
+    act_dim: int = 2
+    state_dim: int = 54
+    hidden: int = 64
+    layer_n: int = 1
+    feature_norm: bool = True
+    relu: bool = True
+    gamma: float = 0.99
+    lr: float = 5e-4
+    opti_eps: float = 1e-5
+    weight_decay: float = 0.0
+    max_grad_norm: float = 10.0
+    tau: float = 0.005
+    huber: bool = False
+    huber_delta: float = 10.0
+    use_per: bool = False
+    per_nu: float = 0.9
+    per_eps: float = 1e-6
+    td3: bool = False
+    target_noise: float = 0.2
+    actor_update_interval: int = 1
+    gain: float = 0.01
+    discrete: bool = False
+
+
 class Box(object):      # duck-typed gym.spaces.Box: what the policies read is .shape / .low / .high
     def __init__(self, d, low=-1.0, high=1.0):
         self.shape = (d,)

@@ -92,7 +92,7 @@ def test_recurrent_workload_dry_run(bench_mod, monkeypatch, emu_engine, workload
         bench.run_engine(args)
     finally:
         for k in opts:
-            emu_engine.lib().mx_set_option(k.encode(), 0)
+            emu_engine.lib().mx_set_option(k.encode(), -1 if k == "wgrad_tc" else 0)
     line = bench._lines[-1]
     if opts.get("wgrad_tc") == 2:
         assert "k_wgrad_tc" in line["kernels"] and "k_front_bwd_tc" in line["kernels"] and "k_front_bwd" not in line["kernels"]
@@ -102,3 +102,18 @@ def test_recurrent_workload_dry_run(bench_mod, monkeypatch, emu_engine, workload
     assert line["gpu_launches"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["lagged_read_value"] > 0
     assert line["roofline"]["kernel"] in line["kernels"]
     assert line["torch_eager_gpu_baseline"]["value"] is None          # no CUDA device here: the secondary baseline is skipped, the line survives
+
+
+@pytest.mark.parametrize("workload,shape", [("rmatd3_spread", (2, 6, 2, 8, 4, 4, True, False)), ("rmaddpg_spread_disc", (2, 6, 3, 8, 4, 4, False, True))])
+def test_maddpg_workload_dry_run(bench_mod, monkeypatch, emu_engine, workload, shape):
+    """The R-MADDPG / R-MATD3 bench arm (run_maddpg) at shrunken shapes: Box + TD3 target noise, Discrete + Gumbel noise.  The engine side
+    takes its configuration from the package (factory.MaddpgLearnerConfig); the oracle is imported for the CPU baseline only."""
+    bench = bench_mod
+    monkeypatch.setitem(bench.MADDPG_WORKLOADS, workload, shape)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    args = types.SimpleNamespace(workload=workload, impl="b200", gpus=1, steps=3, warmup=3, buffer=48, quick=False, opt=[])
+    bench.run_maddpg(args)
+    line = bench._lines[-1]
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "e2e", "gpu_launches", "cpu_baseline"):
+        assert k in line, k
+    assert line["config"]["workload"] == workload and line["gpu_launches"] > 0
