@@ -51,7 +51,9 @@ def bench_mod(emu_engine, monkeypatch):
     for k, v in dict(PROFILE_REPS=1, PROFILE_INNER=2, E2E_MIN_STEPS=2, CPU_STEPS=2, E2E_WARM=1).items():
         monkeypatch.setattr(bench, k, v)
     bench._lines = lines
-    return bench
+    threads = torch.get_num_threads()
+    yield bench
+    torch.set_num_threads(threads)          # the bench arms pin torch's thread count (1 for the engine arm, 8 for the CPU arms)
 
 
 CONTRACT = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
